@@ -1,0 +1,598 @@
+/*
+ * pa_oracle.c -- TEST INFRASTRUCTURE ONLY.  CPU restatement of prealpha's
+ * pair-distribution path, written to be checked against, never shipped.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this.  The product (prealpha_b200/) never does.
+ *
+ * Parity status: PINNED.  Every routine here is validated bit-for-bit against
+ * the reference's own shipped binary (oracle/_ref/prealpha, run through
+ * oracle/build_ref.sh) on the known-answer cases of SURVEY.md 8c; the outputs
+ * of those runs are committed under tests/golden/ (see tests/golden/make_golden.py).
+ *
+ * Each function cites the reference lines it follows.  Shorthand:
+ *   Distribution:n = Development/Module_Distribution.f90:n   (pre-alpha.f03 +14884)
+ *   Molecular:n    = Development/Module_Molecular.f90:n      (pre-alpha.f03 +1644)
+ *   Angles:n       = Development/Module_Angles.f90:n         (pre-alpha.f03 +1461)
+ *   SETTINGS:n     = Development/Module_SETTINGS.f90:n       (pre-alpha.f03 +1)
+ *
+ * Arithmetic contract: coordinates float32, COM and
+ * minimum image float64 without FMA, squared distance rounded to float32,
+ * everything after that float32.  Build with -ffp-contract=off, no fast-math.
+ */
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <limits.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/prealpha_b200.h"
+
+/* SETTINGS:46 -- `pi` is REAL(8) but the literal has no d0 suffix, so it is the
+ * float32 value of pi widened to double; twopi = 2.0*pi (SETTINGS:47). */
+static const double ORC_PI = (double)3.14159274101257324f;
+#define ORC_TWOPI (2.0 * ORC_PI)
+static const double ORC_DEGREES = 57.295779513082320876798154814105; /* SETTINGS:41 */
+static const double ORC_AVOGADRO = 6.02214076e23;                   /* SETTINGS:42 (true double) */
+static const double ORC_ECHARGE = (double)1.602176634E-19f;         /* SETTINGS:43 (REAL4 literal) */
+static const double ORC_VACPERM = (double)8.8541878128E-12f;        /* SETTINGS:44 (REAL4 literal) */
+
+/* Fortran INT() of a REAL(4) as the x86-64 -O0 build does it (cvttss2si):
+ * NaN and out-of-range give INT_MIN ("integer indefinite"). */
+static int orc_int_of_float(float x)
+{
+    if (!(x > -2147483904.0f && x < 2147483648.0f)) return INT_MIN;
+    return (int)x;
+}
+/* wrapping +1 like the two's-complement ADD the binary executes */
+static int orc_plus1(int v) { return (int)((unsigned)v + 1u); }
+
+/* ------------------------------------------------------------------------ */
+/* give_center_of_mass, Molecular:2804-2834 */
+static void orc_center_of_mass(const pa_traj *t, int step, int type, int mol, double c[3])
+{
+    const pa_type *ty = &t->types[type];
+    const float *r = ty->xyz + ((size_t)step * ty->nmol + mol) * (size_t)ty->natoms * 3;
+    if (t->com_boost) {               /* use_firstatom_as_com, Molecular:2810-2817 */
+        c[0] = (double)r[0]; c[1] = (double)r[1]; c[2] = (double)r[2];
+        return;
+    }
+    c[0] = c[1] = c[2] = 0.0;
+    for (int a = 0; a < ty->natoms; ++a) {
+        double m = ty->atom_mass[a];
+        for (int k = 0; k < 3; ++k) {
+            double w = (double)r[a * 3 + k];
+            w = w * m;                /* weighted_pos = weighted_pos*mass     */
+            c[k] = c[k] + w;          /* com = com + weighted_pos             */
+        }
+    }
+    for (int k = 0; k < 3; ++k) c[k] = c[k] / ty->mass;
+}
+
+/* give_qd_vector + give_center_of_charge, Molecular:2869-2890, 2953-2963 */
+static void orc_center_of_charge(const pa_traj *t, int step, int type, int mol, double c[3])
+{
+    const pa_type *ty = &t->types[type];
+    const float *r = ty->xyz + ((size_t)step * ty->nmol + mol) * (size_t)ty->natoms * 3;
+    c[0] = c[1] = c[2] = 0.0;
+    for (int a = 0; a < ty->natoms; ++a) {
+        double q = ty->atom_charge[a];
+        for (int k = 0; k < 3; ++k) {
+            double w = (double)r[a * 3 + k];
+            w = w * q;
+            c[k] = c[k] + w;
+        }
+    }
+    if (ty->charge != 0)
+        for (int k = 0; k < 3; ++k) c[k] = c[k] / (double)ty->realcharge;
+}
+
+/* wrap_vector, Molecular:1560-1586 (strict compares, at most 1000 moves) */
+static void orc_wrap_vector(const pa_traj *t, double p[3], double shift[3])
+{
+    for (int k = 0; k < 3; ++k) {
+        double L = t->box_hi[k] - t->box_lo[k];      /* box_size, Molecular:937 */
+        shift[k] = 0.0;
+        for (int it = 0; it < 1000; ++it) {
+            if (p[k] < t->box_lo[k]) { p[k] = p[k] + L; shift[k] = shift[k] + L; }
+            else if (p[k] > t->box_hi[k]) { p[k] = p[k] - L; shift[k] = shift[k] - L; }
+            else break;
+        }
+    }
+}
+
+/* give_smallest_distance_squared, Molecular:1430-1469: literal 27-image loop,
+ * a outermost, strict `<` keeps the first minimum and its shift. */
+static double orc_smallest_distance_squared(const pa_traj *t, const double c1[3], const double c2[3],
+                                            double translation[3])
+{
+    double p1[3] = { c1[0], c1[1], c1[2] }, p2[3] = { c2[0], c2[1], c2[2] };
+    double sh1[3], wrapshift[3] = { 0, 0, 0 };
+    double best = t->max_dist_sq;
+    /* `translation` is unassigned in the reference when no image beats the
+     * initial value; zero is our (documented) stand-in. */
+    translation[0] = translation[1] = translation[2] = 0.0;
+    if (!t->wrap_trajectory) {
+        orc_wrap_vector(t, p1, sh1);
+        orc_wrap_vector(t, p2, wrapshift);
+        for (int k = 0; k < 3; ++k) wrapshift[k] = wrapshift[k] - sh1[k];
+    }
+    double L[3];
+    for (int k = 0; k < 3; ++k) L[k] = t->box_hi[k] - t->box_lo[k];
+    for (int a = -1; a <= 1; ++a)
+        for (int b = -1; b <= 1; ++b)
+            for (int c = -1; c <= 1; ++c) {
+                double s[3] = { (double)(float)a * L[0], (double)(float)b * L[1], (double)(float)c * L[2] };
+                double d0 = (p2[0] + s[0]) - p1[0];
+                double d1 = (p2[1] + s[1]) - p1[1];
+                double d2 = (p2[2] + s[2]) - p1[2];
+                double clip = (d0 * d0 + d1 * d1) + d2 * d2;   /* SUM(x**2), sequential */
+                if (clip < best) {
+                    best = clip;
+                    translation[0] = s[0]; translation[1] = s[1]; translation[2] = s[2];
+                }
+            }
+    if (!t->wrap_trajectory)
+        for (int k = 0; k < 3; ++k) translation[k] = translation[k] + wrapshift[k];
+    return best;
+}
+
+/* normalize3D, SETTINGS:1052-1059 (length 0 gives NaN components, error 1 is only printed) */
+static void orc_normalize3d(double v[3])
+{
+    double len = sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+    v[0] = v[0] / len; v[1] = v[1] / len; v[2] = v[2] / len;
+}
+
+/* ------------------------------------------------------------------------ */
+/* prepare_rotation + make_rotation_matrix, Angles:51-115, target = z axis. */
+static void orc_prepare_rotation(const double start[3], double rot[9], int *aligned)
+{
+    const double tolerance = 0.0001;                   /* Angles:8 */
+    double a[3] = { start[0], start[1], start[2] }, b[3] = { 0.0, 0.0, 1.0 };
+    double u[3];
+    orc_normalize3d(a);
+    orc_normalize3d(b);
+    double cosa = ((0.0 + a[0] * b[0]) + a[1] * b[1]) + a[2] * b[2];
+    double sina = sqrt(1 - cosa * cosa);
+    double angle = acos(cosa) * ORC_DEGREES;
+    *aligned = 0;
+    if (angle <= tolerance) {
+        *aligned = 1;
+        for (int i = 0; i < 9; ++i) rot[i] = 0.0;
+        rot[0] = rot[4] = rot[8] = 1.0;
+        return;
+    }
+    if ((180.0 - angle) <= tolerance) {                /* REAL4 180.0 widened */
+        double dummy[3] = { 0, 0, 0 };
+        if (a[0] <= (1.0 - tolerance) && a[0] >= (-1.0 + tolerance)) dummy[0] = 1.0; else dummy[2] = 1.0;
+        u[0] = a[1] * dummy[2] - a[2] * dummy[1];      /* crossproduct, SETTINGS:1045-1050 */
+        u[1] = a[2] * dummy[0] - a[0] * dummy[2];
+        u[2] = a[0] * dummy[1] - a[1] * dummy[0];
+    } else {
+        u[0] = a[1] * b[2] - a[2] * b[1];
+        u[1] = a[2] * b[0] - a[0] * b[2];
+        u[2] = a[0] * b[1] - a[1] * b[0];
+    }
+    orc_normalize3d(u);
+    double omc = 1.0 - cosa;
+    /* row-major R(k,:) ; Angles:53-61 */
+    rot[0] = cosa + (u[0] * u[0]) * omc;
+    rot[1] = u[0] * u[1] * omc - u[2] * sina;
+    rot[2] = u[0] * u[2] * omc + u[1] * sina;
+    rot[3] = u[0] * u[1] * omc + u[2] * sina;
+    rot[4] = cosa + (u[1] * u[1]) * omc;
+    rot[5] = u[1] * u[2] * omc - u[0] * sina;
+    rot[6] = u[0] * u[2] * omc - u[1] * sina;
+    rot[7] = u[2] * u[1] * omc + u[0] * sina;
+    rot[8] = cosa + (u[2] * u[2]) * omc;
+}
+
+/* Row S: Distribution:353-377 (step sizes), :526-527 (maxdist_optimize),
+ * :656 (shift), :665-667 (reference vector, rotation). */
+int orc_job_setup(const pa_traj *t, const pa_job_request *rq, pa_job *job)
+{
+    memset(job, 0, sizeof *job);
+    if (rq->ref_type < 1 || rq->ref_type > t->ntypes) return PA_E_TYPE_INVALID;
+    if (rq->obs_type > t->ntypes) return PA_E_TYPE_INVALID;
+    job->mode = rq->mode;
+    job->ref_type = rq->ref_type; job->obs_type = rq->obs_type;
+    job->bin_a = rq->bin_a < 1 ? 1 : (rq->bin_a > 1000 ? 1000 : rq->bin_a);   /* :601-614 */
+    job->bin_b = rq->bin_b < 1 ? 1 : (rq->bin_b > 1000 ? 1000 : rq->bin_b);
+    job->sampling_interval = rq->sampling_interval;
+    job->weigh_charge = rq->weigh_charge; job->use_coc = rq->use_coc;
+    job->subtract_uniform = rq->subtract_uniform;
+    float maxdist = rq->maxdist;
+    if (rq->maxdist_optimize) {
+        double lim = t->box_hi[0] - t->box_lo[0];                 /* give_box_limit = MINVAL(box_size) */
+        for (int k = 1; k < 3; ++k) { double l = t->box_hi[k] - t->box_lo[k]; if (l < lim) lim = l; }
+        maxdist = (float)(lim / 2.0);                             /* REAL8/REAL4 -> REAL4 */
+        if (maxdist < 0.0f) maxdist = 10.0f;
+    }
+    job->maxdist = maxdist;
+    const float ratio = 0.70710678118654752440f;                  /* 2.0**(-0.5) folded in REAL4 */
+    if (rq->mode == PA_MODE_CDF) {
+        job->step_a = (maxdist * ratio) / (float)job->bin_a;
+        job->step_b = ((2.0f * maxdist) * ratio) / (float)job->bin_b;
+    } else {
+        job->step_a = maxdist / (float)job->bin_a;
+        job->step_b = (float)(ORC_PI / (double)(float)job->bin_b);
+    }
+    job->shift = maxdist * ratio;                                 /* :656 (used by cdf only) */
+    for (int k = 0; k < 3; ++k) { job->ref_xyz[k] = rq->ref_xyz[k]; job->ref_vec[k] = (double)(float)rq->ref_xyz[k]; }
+    if (rq->ref_xyz[0] == 0 && rq->ref_xyz[1] == 0 && rq->ref_xyz[2] == 0) return PA_ERR_UNSUPPORTED;
+    orc_normalize3d(job->ref_vec);
+    orc_prepare_rotation(job->ref_vec, job->rot, &job->aligned);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* fill_histogram, Distribution:762-845, for one frame and one observed type. */
+static void orc_fill_histogram(const pa_traj *t, const pa_job *job, int step, int obs_type0,
+                               int64_t *hist, int64_t *within, int64_t *oob)
+{
+    const int ref0 = job->ref_type - 1;
+    const float maxdist_squared = job->maxdist * job->maxdist;    /* maxdist**2, :659 */
+    const int nref = t->types[ref0].nmol, nobs = t->types[obs_type0].nmol;
+    const int w = job->weigh_charge ? t->types[obs_type0].charge : 1;
+    for (int i = 0; i < nref; ++i) {
+        double cref[3];
+        orc_center_of_mass(t, step, ref0, i, cref);
+        for (int j = 0; j < nobs; ++j) {
+            if (ref0 == obs_type0 && i == j) continue;
+            double cobs[3], link[3];
+            orc_center_of_mass(t, step, obs_type0, j, cobs);
+            float d2 = (float)orc_smallest_distance_squared(t, cref, cobs, link);
+            if (!(d2 < maxdist_squared)) continue;
+            if (job->use_coc) {
+                double qo[3], qr[3];
+                orc_center_of_charge(t, step, obs_type0, j, qo);
+                orc_center_of_charge(t, step, ref0, i, qr);
+                for (int k = 0; k < 3; ++k) link[k] = (link[k] + qo[k]) - qr[k];
+            } else {
+                for (int k = 0; k < 3; ++k) link[k] = (link[k] + cobs[k]) - cref[k];
+            }
+            int ia, ib;
+            if (job->mode == PA_MODE_CDF) {
+                const double *R = job->rot;                        /* rotate, Angles:104-115 */
+                double x = link[0], y = link[1], z = link[2];
+                double rx = (x * R[0] + y * R[1]) + z * R[2];
+                double ry = (x * R[3] + y * R[4]) + z * R[5];
+                double rz = (x * R[6] + y * R[7]) + z * R[8];
+                float a = (float)sqrt(rx * rx + ry * ry);
+                float b = (float)rz;
+                ia = orc_plus1(orc_int_of_float(a / job->step_a));
+                float bs = b + job->shift;
+                ib = orc_plus1(orc_int_of_float(bs / job->step_b));
+                if (ib == 1 && bs < 0) ib = 0;
+            } else {
+                float a = sqrtf(d2);
+                orc_normalize3d(link);
+                double dot = ((0.0 + link[0] * job->ref_vec[0]) + link[1] * job->ref_vec[1]) + link[2] * job->ref_vec[2];
+                float b = (float)acos(dot);
+                ia = orc_plus1(orc_int_of_float(a / job->step_a));
+                ib = orc_plus1(orc_int_of_float(b / job->step_b));
+            }
+            if (ia > 0 && ia <= job->bin_a && ib > 0 && ib <= job->bin_b) {
+                *within += 1;
+                hist[(size_t)(ib - 1) * job->bin_a + (ia - 1)] += w;
+            } else {
+                *oob += 1;
+            }
+        }
+    }
+}
+
+/* iterate_timesteps_parallelised, Distribution:696-760.  Frames are independent;
+ * OpenMP over frames with private histograms like the reference.  first/stride
+ * select a shard of the sampled frames (stride 1, first 0 = everything). */
+int orc_distribution_histogram_shard(const pa_traj *t, const pa_job *job, int shard_rank, int shard_count,
+                                     int nthreads, int64_t *hist, int64_t *within_bin, int64_t *out_of_bounds)
+{
+    const size_t nb = (size_t)job->bin_a * job->bin_b;
+    memset(hist, 0, nb * sizeof(int64_t));
+    int64_t within = 0, oob = 0;
+    const int dt = job->sampling_interval < 1 ? 1 : job->sampling_interval;
+    const int nsamp = (t->nsteps + dt - 1) / dt;
+    if (shard_count < 1) shard_count = 1;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        int64_t *hl = (int64_t *)calloc(nb, sizeof(int64_t));
+        int64_t wl = 0, ol = 0;
+#ifdef _OPENMP
+#pragma omp for schedule(static, 1)
+#endif
+        for (int k = 0; k < nsamp; ++k) {
+            if (k % shard_count != shard_rank) continue;
+            int step = k * dt;
+            if (job->obs_type < 1) {
+                for (int ot = 0; ot < t->ntypes; ++ot) orc_fill_histogram(t, job, step, ot, hl, &wl, &ol);
+            } else {
+                orc_fill_histogram(t, job, step, job->obs_type - 1, hl, &wl, &ol);
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        {
+            for (size_t i = 0; i < nb; ++i) hist[i] += hl[i];
+            within += wl; oob += ol;
+        }
+        free(hl);
+    }
+    *within_bin = within; *out_of_bounds = oob;
+    return 0;
+}
+
+int orc_distribution_histogram(const pa_traj *t, const pa_job *job, int nthreads,
+                               int64_t *hist, int64_t *within_bin, int64_t *out_of_bounds)
+{
+    return orc_distribution_histogram_shard(t, job, 0, 1, nthreads, hist, within_bin, out_of_bounds);
+}
+
+/* ------------------------------------------------------------------------ */
+/* transfer_histogram, Distribution:897-977.  g is (bin_a,bin_b) with a fastest. */
+int orc_transfer_histogram(const pa_traj *t, const pa_job *job, const int64_t *hist, int64_t within_bin,
+                           int64_t out_of_bounds, int verbose, float *g, float *ideal_density_out)
+{
+    (void)out_of_bounds;
+    const int na = job->bin_a, nb = job->bin_b;
+    float within_real;
+    int rc = 0;
+    if (within_bin < 0) {                        /* :904-906, error 101 */
+        rc = PA_E_BIN_OVERFLOW;
+        within_real = 0.0f;
+        for (int b = 0; b < nb; ++b) for (int a = 0; a < na; ++a) within_real = within_real + (float)hist[(size_t)b * na + a];
+    } else within_real = (float)within_bin;
+    float total_volume;
+    if (job->mode == PA_MODE_CDF) {
+        float s3 = (job->shift * job->shift) * job->shift;
+        total_volume = (float)(ORC_TWOPI * (double)s3);                        /* :918 */
+    } else {
+        float m3 = (job->maxdist * job->maxdist) * job->maxdist;
+        total_volume = (float)(((double)(4.0f / 3.0f) * ORC_PI) * (double)m3); /* :920 */
+    }
+    float ideal_density = within_real / total_volume;                          /* :924 */
+    for (size_t i = 0; i < (size_t)na * nb; ++i) g[i] = (float)hist[i] / ideal_density;   /* :926 */
+    if (verbose) {                                                             /* :927-931 */
+        const int dt = job->sampling_interval;
+        int denom = (t->nsteps / dt) * t->types[job->ref_type - 1].nmol;
+        ideal_density = ideal_density / (float)denom;
+    }
+    for (int ia = 1; ia <= na; ++ia) {
+        float a = (float)ia * job->step_a, chunk_area;
+        if (job->mode == PA_MODE_CDF) {
+            float am = a - job->step_a;
+            chunk_area = (float)(ORC_PI * (double)((a * a) - (am * am)));      /* :942 */
+        } else {
+            float am = a - job->step_a;
+            chunk_area = ((a * a) * a) - ((am * am) * am);                     /* :946 */
+            chunk_area = (float)((ORC_TWOPI / (double)3.0f) * (double)chunk_area);   /* :947 */
+        }
+        for (int ib = 1; ib <= nb; ++ib) {
+            float chunk_volume;
+            if (job->mode == PA_MODE_CDF) chunk_volume = chunk_area * job->step_b;   /* :958 */
+            else {
+                float b = (float)ib * job->step_b;
+                chunk_volume = chunk_area * (cosf(b - job->step_b) - cosf(b));       /* :962 */
+            }
+            size_t idx = (size_t)(ib - 1) * na + (ia - 1);
+            g[idx] = g[idx] / chunk_volume;                                          /* :972 */
+        }
+    }
+    *ideal_density_out = ideal_density;
+    return rc;
+}
+
+/* ------------------------------------------------------------------------ */
+/* gfortran list-directed output of one REAL(4) item: 1 blank + G16.9E2 with
+ * scale factor 1 in the E branch (libgfortran write_real / FMT_G rules);
+ * observed with `cat -A` on the reference binary's output. */
+int orc_format_real4(float value, char *buf)
+{
+    double m = fabs((double)value);
+    char tmp[64];
+    if (isnan(value)) { strcpy(buf, "              NaN"); return 17; }
+    if (isinf(value)) { strcpy(buf, value > 0 ? "         Infinity" : "        -Infinity"); return 17; }
+    int use_f = 0, e10 = 0;
+    if (m == 0.0) { use_f = 1; e10 = 0; }
+    else {
+        snprintf(tmp, sizeof tmp, "%.8e", m);      /* 9 significant digits, correctly rounded */
+        e10 = atoi(strchr(tmp, 'e') + 1);
+        use_f = (e10 >= -1 && e10 <= 8);
+    }
+    char body[64];
+    if (use_f) {
+        int decimals = (m == 0.0) ? 8 : 8 - e10;   /* F12.(9-k), k digits before the point */
+        snprintf(body, sizeof body, "%.*f", decimals, (double)value);
+        /* field: w-4 = 12 right-justified, then 4 blanks */
+        snprintf(tmp, sizeof tmp, "%12s    ", body);
+    } else {
+        snprintf(body, sizeof body, "%.8E", (double)value);      /* d.ddddddddE+dd */
+        snprintf(tmp, sizeof tmp, "%16s", body);
+    }
+    buf[0] = ' ';
+    strcpy(buf + 1, tmp);
+    return (int)strlen(buf);
+}
+
+static void orc_write_reals(FILE *f, const float *v, int n)
+{
+    char buf[64];
+    for (int i = 0; i < n; ++i) { orc_format_real4(v[i], buf); fputs(buf, f); }
+    fputc('\n', f);
+}
+
+/* number_integral_trapezoid, Distribution:1159-1169 */
+static float orc_number_trapezoid(float g_a, float g_b, float r_a, float r_b)
+{
+    float n = (r_b * g_a - r_a * g_b) / (r_b - r_a);
+    float m = (g_b - n) / r_b;
+    float rb2 = r_b * r_b, ra2 = r_a * r_a;
+    float upper = (m / 4.0f) * (rb2 * rb2) + (n / 3.0f) * (rb2 * r_b);
+    float lower = (m / 4.0f) * (ra2 * ra2) + (n / 3.0f) * (ra2 * r_a);
+    return (float)(((double)4.0f * ORC_PI) * (double)(upper - lower));
+}
+/* energy_integral_trapezoid, Distribution:1171-1183 */
+static float orc_energy_trapezoid(int reference_charge, float g_a, float g_b, float r_a, float r_b)
+{
+    float n = (r_b * g_a - r_a * g_b) / (r_b - r_a);
+    float m = (g_b - n) / r_b;
+    float rb2 = r_b * r_b, ra2 = r_a * r_a;
+    float upper = (m / 3.0f) * (rb2 * r_b) + (n / 2.0f) * rb2;
+    float lower = (m / 3.0f) * (ra2 * r_a) + (n / 2.0f) * ra2;
+    double v = ((double)(float)reference_charge * (ORC_ECHARGE * ORC_ECHARGE)) / ((double)2.0f * ORC_VACPERM);
+    v = v * (double)(upper - lower);
+    v = v * ORC_AVOGADRO;
+    v = v * (double)1.0e10f;
+    return (float)v;
+}
+
+/* write_distribution_functions, Distribution:982-1185 (cdf and pdf). */
+int orc_write_distribution(const pa_traj *t, const pa_job *job, int reference_number, const char *path_prefix,
+                           const char *input_file_name, float *g, float ideal_density)
+{
+    const int na = job->bin_a, nb = job->bin_b;
+    char base[2048], header[1024], fname[2200];
+    const int reference_charge = t->types[job->ref_type - 1].charge;
+    const int write_energy = (reference_charge != 0) && job->weigh_charge;
+    snprintf(base, sizeof base, "%sreference_%d_", path_prefix, reference_number);
+    snprintf(header, sizeof header, "reference vector %+d %+d %+d, ", job->ref_xyz[0], job->ref_xyz[1], job->ref_xyz[2]);
+    /* TRIM(headerline) drops the trailing blank before the next piece is appended (:1029,:1034) */
+    size_t hl = strlen(header); while (hl && header[hl - 1] == ' ') header[--hl] = 0;
+    if (job->obs_type < 1) {
+        snprintf(base + strlen(base), sizeof base - strlen(base), "all_around_%d", job->ref_type);
+        snprintf(header + hl, sizeof header - hl, " all molecules around type %d,", job->ref_type);
+    } else {
+        snprintf(base + strlen(base), sizeof base - strlen(base), "type_%d_around_%d", job->obs_type, job->ref_type);
+        snprintf(header + hl, sizeof header - hl, " all molecules of type %d around type %d,", job->obs_type, job->ref_type);
+    }
+    float shift_b;
+    const char *unitline;
+    FILE *f3;
+    char mainname[2200];
+    if (job->mode == PA_MODE_CDF) {
+        shift_b = job->maxdist * 0.70710678118654752440f;                       /* :1040 */
+        snprintf(mainname, sizeof mainname, "%s%s_cdf", base, job->weigh_charge ? "_xcharge" : "");
+        strcat(header, " cylindrical distribution function");
+        unitline = "a(perpendicular_distance) b(collinear_distance) g(a,b)";
+    } else {
+        shift_b = 0.0f;
+        char trace_name[2200];
+        snprintf(trace_name, sizeof trace_name, "%s_rdf%s", base, job->weigh_charge ? "_xcharge" : "");
+        snprintf(mainname, sizeof mainname, "%s%s%s_pdf", base, job->weigh_charge ? "_xcharge" : "",
+                 job->subtract_uniform ? "_-trace" : "");
+        FILE *ft = fopen(trace_name, "w");
+        snprintf(fname, sizeof fname, "%s_numberintegral", trace_name);
+        FILE *fn = fopen(fname, "w");
+        FILE *fe = NULL;
+        if (!ft || !fn) { if (ft) fclose(ft); if (fn) fclose(fn); return 26; }
+        fprintf(ft, "%s radial distribution function (trace of pdf)\n", header);
+        fprintf(ft, "distance g(r)\n");
+        fprintf(fn, "%s number integral INT(4*pi*r^2*rho*g(r))dR\n", header);
+        fprintf(fn, "distance n(r)\n");
+        float number_integral = 0.0f, energy_integral = 0.0f, zeros[2] = { 0.0f, 0.0f };
+        if (write_energy) {
+            snprintf(fname, sizeof fname, "%s_energyintegral", trace_name);
+            fe = fopen(fname, "w");
+            if (!fe) { fclose(ft); fclose(fn); return 26; }
+            fprintf(fe, "%s (Coulomb) energy integral INT(z*e^2*r*rho*g(r)/(2*epsilon0))dR\n", header);
+            fprintf(fe, "distance E(r)[J/mol]\n");
+            orc_write_reals(fe, zeros, 2);
+        }
+        orc_write_reals(fn, zeros, 2);
+        float previous = 0.0f;
+        for (int ia = 1; ia <= na; ++ia) {
+            float trace = 0.0f;
+            for (int ib = 0; ib < nb; ++ib) trace = trace + g[(size_t)ib * na + (ia - 1)];
+            trace = trace / (float)nb;                                           /* :1088 */
+            float a = (float)ia * job->step_a;
+            number_integral = number_integral + orc_number_trapezoid(previous, trace, a - job->step_a, a) * ideal_density;
+            float row[2] = { a, number_integral };
+            orc_write_reals(fn, row, 2);
+            if (write_energy) {
+                energy_integral = energy_integral +
+                    orc_energy_trapezoid(reference_charge, previous, trace, a - job->step_a, a) * ideal_density;
+                float rowe[2] = { a, energy_integral };
+                orc_write_reals(fe, rowe, 2);
+            }
+            a = a - 0.5f * job->step_a;
+            float rowt[2] = { a, trace };
+            orc_write_reals(ft, rowt, 2);
+            previous = trace;
+            if (job->subtract_uniform)
+                for (int ib = 0; ib < nb; ++ib) g[(size_t)ib * na + (ia - 1)] = g[(size_t)ib * na + (ia - 1)] - trace;
+        }
+        fclose(ft); fclose(fn); if (fe) fclose(fe);
+        unitline = "a(distance) b(polar_angle) g(a,b)";
+        strcat(header, " polar distribution function");
+    }
+    if (job->weigh_charge) strcat(header, ", weighed by charge");
+    f3 = fopen(mainname, "w");
+    if (!f3) return 26;
+    fprintf(f3, "Output in this file is based on the input file '%s':\n", input_file_name);
+    fprintf(f3, "%s\n%s\n", header, unitline);
+    for (int ia = 1; ia <= na; ++ia)
+        for (int ib = 1; ib <= nb; ++ib) {
+            float a = ((float)ia * job->step_a) - 0.5f * job->step_a;
+            float b = (((float)ib * job->step_b) - 0.5f * job->step_b) - shift_b;
+            if (job->mode == PA_MODE_PDF) b = (float)((double)b * ORC_DEGREES);
+            float row[3] = { a, b, g[(size_t)(ib - 1) * na + (ia - 1)] };
+            orc_write_reals(f3, row, 3);
+        }
+    fclose(f3);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* give_smallest_atom_distance_squared, Molecular:1380-1427: like the COM
+ * version but on two atoms and ALWAYS wrapping both. */
+double orc_smallest_atom_distance_squared(const pa_traj *t, const float r1[3], const float r2[3])
+{
+    pa_traj tt = *t; tt.wrap_trajectory = 0;
+    double c1[3] = { (double)r1[0], (double)r1[1], (double)r1[2] };
+    double c2[3] = { (double)r2[0], (double)r2[1], (double)r2[2] };
+    double tr[3];
+    return orc_smallest_distance_squared(&tt, c1, c2, tr);
+}
+
+int orc_abi_version(void) { return PA_ABI_VERSION; }
+
+/* ------------------------------------------------------------------------ */
+/* Minimal xyz body reader, Molecular:4872-4881 (2 header lines per frame) and
+ * :5032-5046 (`READ(3,*) element_name, coordinates`): element token, then three
+ * REAL(4) items converted decimal->float32 directly (strtof), rest of line ignored.
+ * out: [nsteps][natoms_total][3]; elements: [natoms_total][4] from frame 1. */
+int orc_read_xyz(const char *path, int natoms_total, int nsteps, float *out, char *elements)
+{
+    FILE *f = fopen(path, "r");
+    if (!f) return PA_ERR_IO;
+    char *line = NULL; size_t cap = 0;
+    for (int s = 0; s < nsteps; ++s) {
+        if (getline(&line, &cap, f) < 0 || getline(&line, &cap, f) < 0) { fclose(f); free(line); return 84; }
+        for (int a = 0; a < natoms_total; ++a) {
+            if (getline(&line, &cap, f) < 0) { fclose(f); free(line); return 84; }
+            char *p = line;
+            while (*p == ' ' || *p == '\t') ++p;
+            char *e = p;
+            while (*e && *e != ' ' && *e != '\t' && *e != ',' && *e != '\n') ++e;
+            if (s == 0 && elements) {
+                int n = (int)(e - p); if (n > 3) n = 3;
+                memset(elements + a * 4, 0, 4); memcpy(elements + a * 4, p, n);
+            }
+            p = e;
+            for (int k = 0; k < 3; ++k) {
+                while (*p == ' ' || *p == '\t' || *p == ',') ++p;
+                char *q; out[((size_t)s * natoms_total + a) * 3 + k] = strtof(p, &q); p = q;
+            }
+        }
+    }
+    free(line); fclose(f);
+    return 0;
+}

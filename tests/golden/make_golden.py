@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the reference's OWN shipped binary.
+
+Runs only in the build container (needs /root/reference and oracle/_ref, see
+oracle/build_ref.sh).  Each fixture holds
+  * the inputs as the reference parsed them (float32 coordinates per molecule type,
+    type table, box) so that tests can run anywhere without the reference,
+  * the distribution-input text of every job,
+  * what the binary produced: `within bin` / `out of bounds` integers, its stdout and
+    every output file byte for byte.
+The known-answer integers of SURVEY.md section 8c (K1..K9) are re-checked here on the full
+inputs before the (smaller) fixtures are written.
+
+usage: python tests/golden/make_golden.py [case ...]
+"""
+import os
+import shutil
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import oracle_lib as orc  # noqa: E402
+
+REF = os.environ.get("PREALPHA_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def dist_text(mode, refs, **kw):
+    lines = [f"{mode} {len(refs)}"]
+    for vec, rt, ot in refs:
+        lines.append(f"{vec[0]:+d} {vec[1]:+d} {vec[2]:+d} {rt} {ot}")
+    for k, v in kw.items():
+        if k == "maxdist_optimize":
+            if v:
+                lines.append("maxdist_optimize")
+        elif isinstance(v, bool):
+            lines.append(f"{k} {'T' if v else 'F'}")
+        else:
+            lines.append(f"{k} {v}")
+    lines.append("quit")
+    return "\n".join(lines) + "\n"
+
+
+def run_case(name, traj_path, traj_type, types, nsteps, box, jobs, natoms_total, *, expect=None, store_frames=None,
+             lmp_box=None, threads=8, atom_charges=None):
+    """jobs: list of (jobname, mode, refs, kwargs).  Each job runs under its own set_prefix."""
+    wd = tempfile.mkdtemp(prefix=f"golden_{name}_")
+    try:
+        tname = os.path.basename(traj_path)
+        shutil.copy(traj_path, os.path.join(wd, tname))
+        os.makedirs(os.path.join(wd, "out"))
+        with open(os.path.join(wd, "molecular.inp"), "w") as f:
+            f.write(f" {nsteps}\n {len(types)}\n")
+            for ch, na, nm in types:
+                f.write(f" {ch:+d} {na} {nm}\n")
+            if atom_charges is not None:
+                n = sum(len(q) for q in atom_charges)
+                f.write(f"atomic_charges {n}\n")
+                for ti, q in enumerate(atom_charges):
+                    for ai, v in enumerate(q):
+                        f.write(f" {ti + 1} {ai + 1} {float(v)!r}\n")
+            f.write("quit\n")
+        with open(os.path.join(wd, "general.inp"), "w") as f:
+            f.write(f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n')
+            if box is not None:
+                f.write(f" cubic_box_edge {box[0]} {box[1]}\n")
+            f.write(f" trajectory_type {traj_type}\n sequential_read F\n parallel_operation T\n set_threads {threads}\n")
+            for jn, mode, refs, kw in jobs:
+                f.write(f' set_prefix "{jn}_"\n distribution "{jn}.inp"\n')
+            f.write(" quit\n")
+        texts = {}
+        for jn, mode, refs, kw in jobs:
+            texts[jn] = dist_text(mode, refs, **kw)
+            with open(os.path.join(wd, f"{jn}.inp"), "w") as f:
+                f.write(texts[jn])
+        stdout, wall = orc.run_reference(wd)
+        counts = orc.parse_within(stdout)
+        nref_total = sum(len(j[2]) for j in jobs)
+        assert len(counts) == nref_total, (len(counts), nref_total, stdout[-3000:])
+        if expect:
+            for k, v in expect.items():
+                assert counts[k] == v, (name, k, counts[k], v)
+        files = {fn: open(os.path.join(wd, "out", fn), "rb").read() for fn in sorted(os.listdir(os.path.join(wd, "out")))}
+        coords, elements = None, None
+        if traj_type == "xyz":
+            coords, elements = orc.read_xyz(os.path.join(wd, tname), natoms_total, nsteps)
+        return dict(stdout=stdout, counts=counts, files=files, texts=texts, coords=coords, elements=elements, wall=wall)
+    finally:
+        shutil.rmtree(wd, ignore_errors=True)
+
+
+def save(name, res, types, box_lo, box_hi, jobs, coords, elements, extra=None):
+    d = {}
+    d["types"] = np.array(types, dtype=np.int64)
+    d["box_lo"] = np.asarray(box_lo, dtype=np.float64)
+    d["box_hi"] = np.asarray(box_hi, dtype=np.float64)
+    d["coords"] = np.asarray(coords, dtype=np.float32)
+    d["elements"] = np.array(elements)
+    d["counts"] = np.array(res["counts"], dtype=np.int64)
+    d["job_names"] = np.array([j[0] for j in jobs])
+    d["job_texts"] = np.array([res["texts"][j[0]] for j in jobs])
+    d["file_names"] = np.array(list(res["files"].keys()))
+    for i, (fn, content) in enumerate(res["files"].items()):
+        d[f"file_{i}"] = np.frombuffer(content, dtype=np.uint8)
+    d["stdout"] = np.frombuffer(res["stdout"].encode(), dtype=np.uint8)
+    if extra:
+        d.update(extra)
+    path = os.path.join(OUT, f"{name}.npz")
+    np.savez_compressed(path, **d)
+    print(f"wrote {path}: {os.path.getsize(path) / 1024:.0f} KiB, counts={res['counts']}")
+
+
+Z = (0, 0, 1)
+
+
+def case_bmim():
+    src = os.path.join(REF, "Example_BMIMTFSI", "trajectory.xyz")
+    tmp = tempfile.mkdtemp()
+    traj = os.path.join(tmp, "traj.xyz")
+    one = open(src).read()
+    with open(traj, "w") as f:
+        f.write(one * 11)
+    types = [(-1, 15, 512), (+1, 25, 512)]
+    jobs = [
+        ("k1", "pdf", [(Z, 2, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=300, bin_count_b=1)),
+        ("k2", "pdf", [(Z, 1, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=300, bin_count_b=1)),
+        ("k3", "pdf", [(Z, 2, -1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=300, bin_count_b=1)),
+        ("k3w", "pdf", [(Z, 2, -1), (Z, 1, -1)], dict(maxdist_optimize=True, weigh_charge=True, sampling_interval=1,
+                                                     bin_count_a=300, bin_count_b=1)),
+        ("k4", "pdf", [(Z, 2, 1)], dict(maxdist="20.0", sampling_interval=1, bin_count_a=100, bin_count_b=36)),
+        ("k4c", "pdf", [((1, 1, 0), 1, 2), ((-1, 2, 3), 2, 2)],
+         dict(maxdist="18.5", use_coc=True, subtract_uniform=True, sampling_interval=1, bin_count_a=40, bin_count_b=12)),
+        ("k5", "cdf", [((1, 1, 0), 2, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count=100)),
+        ("k5z", "cdf", [(Z, 1, -1), ((0, 0, -1), 2, 1)], dict(maxdist="25.0", weigh_charge=True, sampling_interval=5,
+                                                            bin_count_a=30, bin_count_b=20)),
+        ("si5", "pdf", [(Z, 1, 2)], dict(maxdist_optimize=True, sampling_interval=5, bin_count_a=150, bin_count_b=1)),
+    ]
+    # atomic charges (multiples of 1/16, exact in REAL4) that sum to the formal charges, so that
+    # use_coc has non-trivial centres of charge and %realcharge stays FLOAT(charge)
+    rng = np.random.default_rng(2024)
+    charges = []
+    for ch, na, _ in types:
+        q = rng.integers(-12, 13, size=na) / 16.0
+        q[-1] += ch - q.sum()
+        charges.append(q)
+    res = run_case("bmim", traj, "xyz", types, 11, ("0.0", "63.9223"), jobs, 20480, atom_charges=charges,
+                   expect={0: (1510333, 0), 1: (1503546, 0), 2: (3015419, 0), 5: (368929, 0), 8: (802076, 708257)})
+    shutil.rmtree(tmp)
+    lo, hi = np.float32(0.0), np.float32(63.9223)
+    # all 11 frames are identical: store one
+    assert all(np.array_equal(res["coords"][0], res["coords"][k]) for k in range(11))
+    save("bmim", res, types, [lo] * 3, [hi] * 3, jobs, res["coords"][:1], res["elements"],
+         extra=dict(nsteps=np.int64(11), replicate=np.int64(11), atom_charge_0=charges[0], atom_charge_1=charges[1]))
+
+
+def case_re4():
+    src = os.path.join(REF, "Research_Example_4", "LiG1G1G1DFP-noH-1ns-363K.xyz")
+    types = [(-1, 5, 70), (0, 6, 210), (+1, 1, 70)]
+    # full 40 frames: re-check K6/K7 of SURVEY 8c
+    jobs40 = [("k6", "pdf", [(Z, 3, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=200, bin_count_b=1)),
+              ("k7", "pdf", [(Z, 3, 2)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=200, bin_count_b=1))]
+    r40 = run_case("re4_40", src, "xyz", types, 40, ("0.0", "34.7853"), jobs40, 1680,
+                   expect={0: (104341, 0), 1: (306926, 0)})
+    import hashlib
+    assert hashlib.md5(r40["files"]["k6_reference_1_type_1_around_3_rdf"]).hexdigest() == "ec031c97627ecbed9a22b5055c9f71d7"
+    # fixture: first 12 frames
+    tmp = tempfile.mkdtemp()
+    traj = os.path.join(tmp, "re4_12.xyz")
+    with open(src) as f, open(traj, "w") as g:
+        for _ in range(12 * (1680 + 2)):
+            g.write(f.readline())
+    jobs = [
+        ("k6", "pdf", [(Z, 3, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=200, bin_count_b=1)),
+        ("k7", "pdf", [(Z, 3, 2)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=200, bin_count_b=1)),
+        ("allw", "pdf", [(Z, 3, -1), (Z, 1, -1), (Z, 2, 2)], dict(maxdist_optimize=True, weigh_charge=True,
+                                                                  sampling_interval=2, bin_count_a=120, bin_count_b=1)),
+        ("p2d", "pdf", [((1, 0, 0), 1, 3), ((2, -1, 1), 2, 3)], dict(maxdist="12.0", sampling_interval=1,
+                                                                     bin_count_a=24, bin_count_b=18)),
+        ("c2d", "cdf", [((0, 1, 0), 3, 2), ((3, 1, -2), 2, 1)], dict(maxdist_optimize=True, sampling_interval=3,
+                                                                     bin_count_a=20, bin_count_b=16)),
+    ]
+    res = run_case("re4", traj, "xyz", types, 12, ("0.0", "34.7853"), jobs, 1680)
+    shutil.rmtree(tmp)
+    lo, hi = np.float32(0.0), np.float32(34.7853)
+    save("re4", res, types, [lo] * 3, [hi] * 3, jobs, res["coords"], res["elements"], extra=dict(nsteps=np.int64(12)))
+
+
+def case_re4_atoms():
+    """K8: every atom its own one-atom 'molecule type' after sorting each frame by element (com boost path)."""
+    src = os.path.join(REF, "Research_Example_4", "LiG1G1G1DFP-noH-1ns-363K.xyz")
+    coords, elements = orc.read_xyz(src, 1680, 40)
+    order_el = ["Li", "O", "P", "F", "C"]
+    idx = np.concatenate([[i for i, e in enumerate(elements) if e == el] for el in order_el]).astype(int)
+    counts = [sum(1 for e in elements if e == el) for el in order_el]
+    assert counts == [70, 560, 70, 140, 840], counts
+    types = [(+1, 1, 70), (0, 1, 560), (0, 1, 70), (0, 1, 140), (0, 1, 840)]
+    tmp = tempfile.mkdtemp()
+
+    def write_sorted(path, nfr):
+        lines = open(src).read().split("\n")
+        with open(path, "w") as g:
+            for s in range(nfr):
+                base = s * 1682
+                g.write(lines[base] + "\n" + lines[base + 1] + "\n")
+                for i in idx:
+                    g.write(lines[base + 2 + i] + "\n")
+    p40 = os.path.join(tmp, "sorted40.xyz")
+    write_sorted(p40, 40)
+    jobs40 = [("k8", "pdf", [(Z, 1, 2)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=200, bin_count_b=1))]
+    r40 = run_case("re4a_40", p40, "xyz", types, 40, ("0.0", "34.7853"), jobs40, 1680, expect={0: (822853, 0)})
+    import hashlib
+    assert hashlib.md5(r40["files"]["k8_reference_1_type_2_around_1_rdf"]).hexdigest() == "24928307184a2f74e516215bc175549c"
+    p12 = os.path.join(tmp, "sorted12.xyz")
+    write_sorted(p12, 12)
+    jobs = [
+        ("k8", "pdf", [(Z, 1, 2)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=200, bin_count_b=1)),
+        ("oo", "pdf", [(Z, 2, 2), (Z, 5, -1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=500, bin_count_b=1)),
+        ("lic2d", "pdf", [((0, 0, -1), 1, 5)], dict(maxdist="10.0", sampling_interval=4, bin_count_a=50, bin_count_b=10)),
+    ]
+    res = run_case("re4_atoms", p12, "xyz", types, 12, ("0.0", "34.7853"), jobs, 1680)
+    shutil.rmtree(tmp)
+    lo, hi = np.float32(0.0), np.float32(34.7853)
+    save("re4_atoms", res, types, [lo] * 3, [hi] * 3, jobs, res["coords"], res["elements"], extra=dict(nsteps=np.int64(12)))
+
+
+def synth_frames(seed, nframes, natoms, L):
+    rng = np.random.default_rng(seed)
+    return np.stack([rng.random((natoms, 3)) * L for _ in range(nframes)])
+
+
+def case_synth():
+    """K9 of SURVEY 8c (re-checked), fixture = smaller box of the same generator + exact coincidences on purpose."""
+    tmp = tempfile.mkdtemp()
+    fr = synth_frames(12345, 16, 4000, 50.0)
+    el = ["Na"] * 2000 + ["Cl"] * 2000
+    p = os.path.join(tmp, "k9.xyz")
+    orc.write_xyz(p, el, fr)
+    types = [(+1, 1, 2000), (-1, 1, 2000)]
+    jobs = [("k9", "pdf", [(Z, 1, -1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=500, bin_count_b=1))]
+    r = run_case("k9", p, "xyz", types, 16, ("0.0", "50.0"), jobs, 4000, expect={0: (67010099, 0)})
+    import hashlib
+    assert hashlib.md5(r["files"]["k9_reference_1_all_around_1_rdf"]).hexdigest() == "09313abc30274f9f64bd6c63823b4ea5"
+    # fixture: 1500 atoms x 12 frames, L=30; plant pairs with identical x,y (link exactly along -z/+z),
+    # identical positions (zero distance) and atoms exactly on / outside the box faces.
+    fr = synth_frames(777, 12, 1500, 30.0)
+    fr = np.round(fr, 5)
+    for s in range(12):
+        fr[s, 10, :2] = fr[s, 900, :2]            # same x,y, different type
+        fr[s, 11, :2] = fr[s, 12, :2]             # same x,y, same type
+        fr[s, 13] = fr[s, 901]                    # coincident atoms, different type
+        fr[s, 14] = fr[s, 15]                     # coincident atoms, same type
+        fr[s, 20] = (0.0, 30.0, 15.0)             # on the faces
+        fr[s, 21] = (30.0, 0.0, 15.0)
+        fr[s, 22] = (-0.00001, 30.00001, 45.0)    # just outside -> wrapped
+        fr[s, 23, 0] = fr[s, 24, 0] + 15.0        # |dx| = L/2 exactly (image tie)
+        fr[s, 23, 1:] = fr[s, 24, 1:]
+    el = ["Na"] * 750 + ["Cl"] * 750
+    p = os.path.join(tmp, "syn.xyz")
+    orc.write_xyz(p, el, fr)
+    types = [(+1, 1, 750), (-1, 1, 750)]
+    jobs = [
+        ("s1", "pdf", [(Z, 1, -1), (Z, 2, 2), ((0, 0, -1), 1, 2)], dict(maxdist_optimize=True, sampling_interval=1,
+                                                                       bin_count_a=1000, bin_count_b=1)),
+        ("s2", "pdf", [(Z, 1, 2)], dict(maxdist="7.5", sampling_interval=1, bin_count_a=64, bin_count_b=1)),
+        ("s3", "pdf", [(Z, 1, -1), ((1, 0, 0), 2, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=30, bin_count_b=30)),
+        ("s4", "cdf", [(Z, 1, -1), ((1, 2, 2), 2, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=25, bin_count_b=25)),
+    ]
+    res = run_case("synth", p, "xyz", types, 12, ("0.0", "30.0"), jobs, 1500)
+    shutil.rmtree(tmp)
+    lo, hi = np.float32(0.0), np.float32(30.0)
+    save("synth", res, types, [lo] * 3, [hi] * 3, jobs, res["coords"], res["elements"], extra=dict(nsteps=np.int64(12)))
+
+
+CASES = {"bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+
+if __name__ == "__main__":
+    assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"
+    for c in (sys.argv[1:] or list(CASES)):
+        CASES[c]()
