@@ -1,0 +1,589 @@
+// pa_frontend.cpp -- file-level drop-in for the `distribution` path:
+// general.inp (Main:103-357 header switches, Main:2882-3666 keyword loop), molecular.inp
+// (Molecular:3444-3700), xyz / lmp trajectory readers (Molecular:4827-5063) and the
+// distribution input file (Distribution:328-616), with Fortran list-directed token rules.
+// Everything numeric is delegated to the C ABI (pa_job_setup, pa_distribution_histogram_multi,
+// pa_transfer_histogram, pa_write_distribution).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <map>
+#include <fstream>
+#include <sstream>
+#include <chrono>
+#include <array>
+#include "pa_internal.h"
+
+namespace {
+
+// ---- Fortran list-directed tokens: blanks/commas separate, quotes group, '/' ends the record
+std::vector<std::string> tokens_of(const std::string &line)
+{
+    std::vector<std::string> out;
+    size_t i = 0, n = line.size();
+    while (i < n) {
+        while (i < n && (line[i] == ' ' || line[i] == '\t' || line[i] == ',' || line[i] == '\r')) ++i;
+        if (i >= n) break;
+        if (line[i] == '/') break;
+        if (line[i] == '"' || line[i] == '\'') {
+            const char q = line[i++];
+            std::string t;
+            while (i < n) {
+                if (line[i] == q) { if (i + 1 < n && line[i + 1] == q) { t += q; i += 2; continue; } ++i; break; }
+                t += line[i++];
+            }
+            out.push_back(t);
+        } else {
+            std::string t;
+            while (i < n && line[i] != ' ' && line[i] != '\t' && line[i] != ',' && line[i] != '/' && line[i] != '\r') t += line[i++];
+            out.push_back(t);
+        }
+    }
+    return out;
+}
+
+bool parse_int(const std::string &s, int &v)
+{
+    char *e = nullptr;
+    const long x = strtol(s.c_str(), &e, 10);
+    if (e == s.c_str() || *e) return false;
+    v = (int)x;
+    return true;
+}
+bool parse_real4(const std::string &s, float &v)      // decimal -> REAL(4) directly
+{
+    std::string t = s;
+    for (char &c : t) if (c == 'd' || c == 'D') c = 'e';
+    char *e = nullptr;
+    v = strtof(t.c_str(), &e);
+    return e != t.c_str() && !*e;
+}
+bool parse_real8(const std::string &s, double &v)
+{
+    std::string t = s;
+    for (char &c : t) if (c == 'd' || c == 'D') c = 'e';
+    char *e = nullptr;
+    v = strtod(t.c_str(), &e);
+    return e != t.c_str() && !*e;
+}
+bool parse_logical(const std::string &s, bool &v)
+{
+    size_t i = 0;
+    if (i < s.size() && s[i] == '.') ++i;
+    if (i >= s.size()) return false;
+    if (s[i] == 'T' || s[i] == 't') { v = true; return true; }
+    if (s[i] == 'F' || s[i] == 'f') { v = false; return true; }
+    return false;
+}
+
+bool read_lines(const std::string &path, std::vector<std::string> &lines)
+{
+    std::ifstream f(path);
+    if (!f) return false;
+    std::string l;
+    while (std::getline(f, l)) lines.push_back(l);
+    return true;
+}
+
+// ---- element table, Molecular:9-92 (REAL(4) values)
+const std::map<std::string, float> &default_masses()
+{
+    static const std::map<std::string, float> m = {
+        {"H", 1.008f}, {"He", 4.002f}, {"Li", 6.94f}, {"Be", 9.012f}, {"B", 10.81f}, {"C", 12.011f}, {"N", 14.007f},
+        {"O", 15.999f}, {"F", 18.998f}, {"Ne", 20.1797f}, {"Na", 22.989f}, {"Mg", 24.305f}, {"Al", 26.981f},
+        {"Si", 28.085f}, {"P", 30.973762f}, {"S", 32.06f}, {"Cl", 35.45f}, {"Ar", 39.95f}, {"K", 39.0983f},
+        {"Ca", 40.078f}, {"Sc", 44.955f}, {"Ti", 47.867f}, {"V", 50.9415f}, {"Cr", 51.9961f}, {"Mn", 54.938f},
+        {"Fe", 55.845f}, {"Co", 58.933f}, {"Ni", 58.6934f}, {"Cu", 63.546f}, {"Zn", 65.38f}, {"Ga", 69.723f},
+        {"Ge", 72.63f}, {"As", 74.921f}, {"Se", 78.971f}, {"Br", 79.904f}, {"Kr", 83.798f}, {"Rb", 85.4678f},
+        {"Sr", 87.62f}, {"Y", 88.905f}, {"Zr", 91.222f}, {"Nb", 92.906f}, {"Mo", 95.95f}, {"Ru", 101.07f},
+        {"Rh", 102.905f}, {"Pd", 106.42f}, {"Ag", 107.8682f}, {"Cd", 112.414f}, {"In", 114.818f}, {"Sn", 118.71f},
+        {"Sb", 121.76f}, {"Te", 127.6f}, {"I", 126.904f}, {"Xe", 131.293f}, {"Cs", 132.905f}, {"Ba", 137.327f},
+        {"La", 138.905f}, {"Ce", 140.116f}, {"Pr", 140.907f}, {"Nd", 144.242f}, {"Sm", 150.36f}, {"Eu", 151.964f},
+        {"Gd", 157.249f}, {"Tb", 158.925f}, {"Dy", 162.5f}, {"Ho", 164.93f}, {"Er", 167.259f}, {"Tm", 168.934f},
+        {"Yb", 173.045f}, {"Lu", 174.966f}, {"Hf", 178.486f}, {"Ta", 180.947f}, {"W", 183.84f}, {"Re", 186.207f},
+        {"Os", 190.23f}, {"Ir", 192.217f}, {"Pt", 195.084f}, {"Au", 196.966f}, {"Hg", 200.592f}, {"Tl", 204.38f},
+        {"Pb", 207.2f}, {"Bi", 208.98f}, {"Th", 232.0377f}, {"Pa", 231.035f}, {"U", 238.028f}, {"X", 0.0f}, {"D", 0.0f},
+    };
+    return m;
+}
+
+struct HostType {
+    int charge = 0, natoms = 0, nmol = 0;
+    float realcharge = 0.f;
+    double mass = 0.0;
+    std::vector<std::string> elements;
+    std::vector<double> atom_mass, atom_charge;
+    std::vector<char> mass_manual, charge_manual;
+    std::vector<float> xyz;
+};
+
+struct Run {
+    std::string general_path;
+    std::string traj_file, mol_file, path_traj, path_in, path_out, prefix;
+    std::string traj_type = "lmp";
+    bool box_given = false, read_sequential = false, wrap = false, unwrap = false, extra_velocity = false;
+    bool verbose = true, custom_charges = false;
+    double box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0}, max_dist_sq = 0.0;
+    int nsteps = 0;
+    std::vector<HostType> types;
+    std::map<std::string, float> mass_override, charge_override;
+    int errors = 0;
+    pa_exec exec{};
+
+    void error(int code, const std::string &msg)
+    {
+        ++errors;
+        printf("  #  ERROR %d: %s\n", code, msg.c_str());
+    }
+};
+
+void set_cubic_box(Run &r, float lower, float upper)         // Molecular:931-941
+{
+    for (int k = 0; k < 3; ++k) { r.box_lo[k] = (double)lower; r.box_hi[k] = (double)upper; }
+    const double L = r.box_hi[0] - r.box_lo[0];
+    r.max_dist_sq = L * L + std::sqrt(L * L + L * L);
+    r.box_given = true;
+}
+
+// first occurrence of a switch anywhere before 'quit' (Main:131-357)
+const std::vector<std::string> *find_switch(const std::vector<std::vector<std::string>> &toks,
+                                            std::initializer_list<const char *> names)
+{
+    for (const auto &t : toks) {
+        if (t.empty()) continue;
+        for (const char *n : names) if (t[0] == n) return &t;
+        if (t[0] == "quit") return nullptr;
+    }
+    return nullptr;
+}
+
+bool read_molecular_input(Run &r)                             // Molecular:3444-3700
+{
+    std::vector<std::string> lines;
+    if (!read_lines(r.mol_file, lines)) { r.error(17, "molecular input file '" + r.mol_file + "' not found"); return false; }
+    std::vector<std::vector<std::string>> toks;
+    for (auto &l : lines) { auto t = tokens_of(l); if (!t.empty()) toks.push_back(t); }
+    int ntypes = 0;
+    if (toks.size() < 2 || !parse_int(toks[0][0], r.nsteps) || !parse_int(toks[1][0], ntypes) || ntypes < 1 ||
+        (int)toks.size() < 2 + ntypes) { r.error(7, "molecular input file has the wrong format"); return false; }
+    r.types.assign(ntypes, HostType());
+    int totalcharge = 0;
+    for (int n = 0; n < ntypes; ++n) {
+        HostType &t = r.types[n];
+        const auto &tk = toks[2 + n];
+        if (tk.size() < 3 || !parse_int(tk[0], t.charge) || !parse_int(tk[1], t.natoms) || !parse_int(tk[2], t.nmol)) {
+            r.error(7, "molecular input file has the wrong format"); return false;
+        }
+        if (t.natoms < 1) { r.error(80, "number of atoms per molecule < 1"); return false; }
+        if (t.nmol < 1) { r.error(119, "number of molecules < 1"); return false; }
+        t.realcharge = (float)t.charge;
+        t.elements.assign(t.natoms, "");
+        t.atom_mass.assign(t.natoms, 0.0); t.atom_charge.assign(t.natoms, 0.0);
+        t.mass_manual.assign(t.natoms, 0); t.charge_manual.assign(t.natoms, 0);
+        totalcharge += t.charge * t.nmol;
+    }
+    if (totalcharge != 0) r.error(52, "total charge of the system is not zero (warning)");
+    // optional sections, each searched from the line after the header up to 'quit'
+    auto section = [&](std::initializer_list<const char *> names, size_t &start, int &count) -> bool {
+        for (size_t i = 2 + ntypes; i < toks.size(); ++i) {
+            if (toks[i][0] == "quit") return false;
+            for (const char *nm : names)
+                if (toks[i][0] == nm) {
+                    if (toks[i].size() < 2 || !parse_int(toks[i][1], count)) return false;
+                    start = i + 1;
+                    return count > 0;
+                }
+        }
+        return false;
+    };
+    size_t st; int cnt;
+    if (section({"masses", "default_masses"}, st, cnt))
+        for (int m = 0; m < cnt && st + m < toks.size(); ++m) {
+            float v; const auto &tk = toks[st + m];
+            if (tk.size() < 2 || !parse_real4(tk[1], v)) break;
+            r.mass_override[tk[0].substr(0, 2)] = v;
+        }
+    if (section({"atomic_masses", "atom_masses"}, st, cnt))
+        for (int m = 0; m < cnt && st + m < toks.size(); ++m) {
+            int ti, ai; float v; const auto &tk = toks[st + m];
+            if (tk.size() < 3 || !parse_int(tk[0], ti) || !parse_int(tk[1], ai) || !parse_real4(tk[2], v)) break;
+            if (ti < 1 || ti > ntypes) { r.error(110, "invalid molecule type in atomic_masses"); continue; }
+            if (ai < 1 || ai > r.types[ti - 1].natoms) { r.error(111, "invalid atom index in atomic_masses"); continue; }
+            r.types[ti - 1].atom_mass[ai - 1] = (double)v; r.types[ti - 1].mass_manual[ai - 1] = 1;
+        }
+    if (section({"charges", "default_charges"}, st, cnt)) {
+        r.custom_charges = true;
+        for (int m = 0; m < cnt && st + m < toks.size(); ++m) {
+            float v; const auto &tk = toks[st + m];
+            if (tk.size() < 2 || !parse_real4(tk[1], v)) break;
+            r.charge_override[tk[0].substr(0, 2)] = v;
+        }
+    }
+    if (section({"atomic_charges", "atom_charges"}, st, cnt)) {
+        r.custom_charges = true;
+        for (int m = 0; m < cnt && st + m < toks.size(); ++m) {
+            int ti, ai; float v; const auto &tk = toks[st + m];
+            if (tk.size() < 3 || !parse_int(tk[0], ti) || !parse_int(tk[1], ai) || !parse_real4(tk[2], v)) break;
+            if (ti < 1 || ti > ntypes) { r.error(110, "invalid molecule type in atomic_charges"); continue; }
+            if (ai < 1 || ai > r.types[ti - 1].natoms) { r.error(111, "invalid atom index in atomic_charges"); continue; }
+            r.types[ti - 1].atom_charge[ai - 1] = (double)v; r.types[ti - 1].charge_manual[ai - 1] = 1;
+        }
+    }
+    return true;
+}
+
+float element_mass(Run &r, const std::string &el)
+{
+    auto o = r.mass_override.find(el);
+    if (o != r.mass_override.end()) return o->second;
+    auto d = default_masses().find(el);
+    if (d != default_masses().end()) return d->second;
+    r.error(4, "unknown element '" + el + "'");
+    return 0.0f;
+}
+
+// Trajectory: header pass over frame 1 (elements -> masses / charges, Molecular:4827-4949) and
+// body (Molecular:4951-5063): `READ(3,*) element_name, coordinates` per atom, REAL(4) items.
+bool load_trajectory(Run &r)
+{
+    const std::string path = r.path_traj + r.traj_file;
+    FILE *f = fopen(path.c_str(), "r");
+    if (!f) { r.error(9, "trajectory file '" + path + "' not found"); return false; }
+    const bool lmp = (r.traj_type == "lmp");
+    const int header = lmp ? 9 : 2;
+    long long natoms_total = 0;
+    for (auto &t : r.types) { natoms_total += (long long)t.natoms * t.nmol; t.xyz.assign((size_t)r.nsteps * t.natoms * t.nmol * 3, 0.f); }
+    char *line = nullptr; size_t cap = 0;
+    bool ok = true;
+    int steps_read = 0;
+    for (int s = 0; s < r.nsteps && ok; ++s) {
+        for (int h = 0; h < header; ++h) {
+            if (getline(&line, &cap, f) < 0) { ok = false; break; }
+            if (s == 0 && lmp && h >= 5 && h <= 7) {          // box bounds, Molecular:4851-4857
+                auto tk = tokens_of(line);
+                if (tk.size() < 2 || !parse_real8(tk[0], r.box_lo[h - 5]) || !parse_real8(tk[1], r.box_hi[h - 5])) r.error(71, "cannot read box from lammps header");
+            }
+            if (s == 0 && lmp && h == 8) {
+                auto tk = tokens_of(line);
+                if (tk.size() < 6 || tk[2] != "element") r.error(53, "lammps trajectory must have 'element' as first column");
+                else if (!(tk[3] == "xu" && tk[4] == "yu" && tk[5] == "zu")) r.error(54, "expected 'xu yu zu' columns");
+            }
+            if (s == 0 && h == (lmp ? 3 : 0)) {
+                auto tk = tokens_of(line);
+                int n = 0;
+                if (tk.empty() || !parse_int(tk[0], n)) r.error(71, "cannot read number of atoms");
+                else if (n != natoms_total) r.error(10, "number of atoms in trajectory and molecular input differ");
+            }
+        }
+        if (!ok) break;
+        for (auto &t : r.types) {
+            for (int m = 0; m < t.nmol && ok; ++m)
+                for (int a = 0; a < t.natoms; ++a) {
+                    if (getline(&line, &cap, f) < 0) { ok = false; break; }
+                    char *p = line;
+                    while (*p == ' ' || *p == '\t') ++p;
+                    char *e = p;
+                    while (*e && *e != ' ' && *e != '\t' && *e != ',' && *e != '\n' && *e != '\r') ++e;
+                    if (s == 0 && m == 0) t.elements[a] = std::string(p, (size_t)std::min<ptrdiff_t>(e - p, 2));
+                    float *dst = &t.xyz[(((size_t)s * t.nmol + m) * t.natoms + a) * 3];
+                    p = e;
+                    for (int k = 0; k < 3; ++k) {
+                        while (*p == ' ' || *p == '\t' || *p == ',') ++p;
+                        char *q; dst[k] = strtof(p, &q); p = q;
+                    }
+                }
+            if (!ok) break;
+        }
+        if (ok) steps_read = s + 1;
+    }
+    free(line); fclose(f);
+    if (steps_read < r.nsteps) {                                  // Molecular:5003-5009, error 84
+        r.error(84, "trajectory is shorter than specified; using " + std::to_string(steps_read) + " steps");
+        // re-pack is not needed: arrays are [step][mol][atom][3], truncation just drops the tail
+        for (auto &t : r.types) t.xyz.resize((size_t)steps_read * t.natoms * t.nmol * 3);
+        r.nsteps = steps_read;
+    }
+    if (lmp) {
+        r.box_given = true;
+        const double Lx = r.box_hi[0] - r.box_lo[0], Ly = r.box_hi[1] - r.box_lo[1], Lz = r.box_hi[2] - r.box_lo[2];
+        r.max_dist_sq = Ly * Ly + std::sqrt(Lx * Lx + Lz * Lz);   // Molecular:4857 [sic]
+    } else {
+        r.max_dist_sq = 22500.0;                                   // Molecular:4883
+    }
+    // masses / charges from the elements of frame 1 (Molecular:4896-4924)
+    for (auto &t : r.types) {
+        t.mass = 0.0;
+        for (int a = 0; a < t.natoms; ++a) {
+            float em = element_mass(r, t.elements[a]);
+            if (t.mass_manual[a]) em = (float)t.atom_mass[a]; else t.atom_mass[a] = (double)em;
+            float ec;
+            if (t.natoms == 1) ec = (float)t.charge;
+            else { auto o = r.charge_override.find(t.elements[a]); ec = o != r.charge_override.end() ? o->second : 0.0f; }
+            if (!t.charge_manual[a]) t.atom_charge[a] = (double)ec;
+            t.mass = t.mass + (double)em;
+        }
+        if (r.custom_charges) {                                    // Molecular:4712-4729
+            double sum = 0.0;
+            for (int a = 0; a < t.natoms; ++a) sum = sum + t.atom_charge[a];
+            if (std::fabs(sum - (double)(float)t.charge) > (double)0.001f) { r.error(126, "sum of atomic charges differs from formal charge"); t.realcharge = (float)sum; }
+        }
+    }
+    return true;
+}
+
+struct DistInput {
+    int mode = PA_MODE_PDF;
+    std::vector<std::array<int, 5>> refs;
+    int sampling_interval = 10, bin_a = 100, bin_b = 100;        // Distribution:9-16
+    bool subtract_uniform = false, weigh_charge = false, use_coc = false, maxdist_optimize = false;
+    float maxdist = 10.0f;
+};
+
+int read_distribution_input(Run &r, const std::string &name, DistInput &d)
+{
+    std::vector<std::string> lines;
+    if (!read_lines(r.path_in + name, lines)) { r.error(132, "distribution input file '" + r.path_in + name + "' not found"); return 132; }
+    std::vector<std::vector<std::string>> toks;
+    for (auto &l : lines) { auto t = tokens_of(l); if (!t.empty()) toks.push_back(t); }
+    if (toks.empty()) { r.error(99, "incorrect format in distribution input"); return 99; }
+    std::string mode = toks[0][0];
+    if (mode == "cydf") mode = "cdf";
+    if (mode == "podf") mode = "pdf";
+    if (mode == "cdf") d.mode = PA_MODE_CDF;
+    else if (mode == "pdf") d.mode = PA_MODE_PDF;
+    else if (mode == "charge_arm") { r.error(0, "charge_arm mode is outside the accelerated path (O(N) per frame; see DESIGN.md)"); return PA_ERR_UNSUPPORTED; }
+    else { r.error(99, "incorrect format in distribution input"); return 99; }
+    int nref = 0;
+    if (toks[0].size() < 2 || !parse_int(toks[0][1], nref) || nref < 0 || (int)toks.size() < 1 + nref) { r.error(99, "incorrect format in distribution input"); return 99; }
+    const int ntypes = (int)r.types.size();
+    for (int n = 0; n < nref; ++n) {
+        std::array<int, 5> v{};
+        const auto &tk = toks[1 + n];
+        bool ok = tk.size() >= 5;
+        for (int k = 0; ok && k < 5; ++k) ok = parse_int(tk[k], v[k]);
+        if (!ok) { r.error(99, "incorrect format in distribution input"); return 99; }
+        if (v[3] > ntypes || v[3] < 1 || v[4] > ntypes) { r.error(33, "molecule type index does not exist"); return 33; }
+        d.refs.push_back(v);
+    }
+    for (size_t i = 1 + nref; i < toks.size() && i < (size_t)(1 + nref + 500); ++i) {
+        const auto &tk = toks[i];
+        const std::string &k = tk[0];
+        auto want_int = [&](int &dst, int dflt) { int v; if (tk.size() > 1 && parse_int(tk[1], v)) dst = v; else { r.error(100, "cannot read '" + k + "'"); dst = dflt; } };
+        auto want_log = [&](bool &dst, bool dflt) { bool v; if (tk.size() > 1 && parse_logical(tk[1], v)) dst = v; else { r.error(100, "cannot read '" + k + "'"); dst = dflt; } };
+        if (k == "sampling_interval") want_int(d.sampling_interval, 10);
+        else if (k == "bin_count") { int v = 100; want_int(v, 100); d.bin_a = d.bin_b = v; }
+        else if (k == "bin_count_a") want_int(d.bin_a, 100);
+        else if (k == "bin_count_b") want_int(d.bin_b, 100);
+        else if (k == "maxdist") {
+            d.maxdist_optimize = false;
+            float v; if (tk.size() > 1 && parse_real4(tk[1], v)) d.maxdist = v; else { r.error(100, "cannot read 'maxdist'"); d.maxdist = 10.0f; }
+        } else if (k == "maxdist_optimize" || k == "maxdist_optimise") d.maxdist_optimize = true;
+        else if (k == "subtract_uniform") { if (d.mode == PA_MODE_PDF) want_log(d.subtract_uniform, false); }
+        else if (k == "weigh_charge") want_log(d.weigh_charge, false);
+        else if (k == "use_coc" || k == "use_COC" || k == "center_of_charge" || k == "centre_of_charge") want_log(d.use_coc, false);
+        else if (k == "quit") break;
+        if (d.bin_a < 1) { d.bin_a = 1; r.error(104, "bin count out of range"); } else if (d.bin_a > 1000) { d.bin_a = 1000; r.error(104, "bin count out of range"); }
+        if (d.bin_b < 1) { d.bin_b = 1; r.error(104, "bin count out of range"); } else if (d.bin_b > 1000) { d.bin_b = 1000; r.error(104, "bin count out of range"); }
+    }
+    return 0;
+}
+
+void make_traj(Run &r, std::vector<pa_type> &types, pa_traj &t)
+{
+    types.resize(r.types.size());
+    bool boost = true;
+    for (size_t i = 0; i < r.types.size(); ++i) {
+        HostType &h = r.types[i];
+        pa_type &p = types[i];
+        memset(&p, 0, sizeof p);
+        p.charge = h.charge; p.natoms = h.natoms; p.nmol = h.nmol; p.mass = h.mass; p.realcharge = h.realcharge;
+        p.atom_mass = h.atom_mass.data(); p.atom_charge = h.atom_charge.data(); p.xyz = h.xyz.data();
+        if (h.natoms > 1) boost = false;
+    }
+    memset(&t, 0, sizeof t);
+    t.ntypes = (int)types.size(); t.nsteps = r.nsteps; t.types = types.data();
+    for (int k = 0; k < 3; ++k) { t.box_lo[k] = r.box_lo[k]; t.box_hi[k] = r.box_hi[k]; }
+    t.max_dist_sq = r.max_dist_sq;
+    t.com_boost = boost ? 1 : 0;                              // Molecular:3556-3562
+    t.wrap_trajectory = r.wrap ? 1 : 0;
+}
+
+int perform_distribution(Run &r, const std::string &input_name)     // Distribution:1187-1228
+{
+    if (r.nsteps < 11) { r.error(37, "trajectory is too short for the distribution analysis (< 11 steps)"); return 37; }
+    DistInput d;
+    int rc = read_distribution_input(r, input_name, d);
+    if (rc) return rc;
+    std::vector<pa_type> types; pa_traj traj;
+    make_traj(r, types, traj);
+    std::vector<pa_job> jobs(d.refs.size());
+    for (size_t n = 0; n < d.refs.size(); ++n) {
+        pa_job_request rq{};
+        rq.mode = d.mode;
+        for (int k = 0; k < 3; ++k) rq.ref_xyz[k] = d.refs[n][k];
+        rq.ref_type = d.refs[n][3]; rq.obs_type = d.refs[n][4];
+        rq.bin_a = d.bin_a; rq.bin_b = d.bin_b; rq.sampling_interval = d.sampling_interval;
+        rq.weigh_charge = d.weigh_charge; rq.use_coc = d.use_coc; rq.subtract_uniform = d.subtract_uniform;
+        rq.maxdist_optimize = d.maxdist_optimize; rq.maxdist = d.maxdist;
+        rc = pa_job_setup(&traj, &rq, &jobs[n]);
+        if (rc) { r.error(rc, pa_last_error()); return rc; }
+    }
+    if (jobs.empty()) return 0;
+    const size_t nb = (size_t)jobs[0].bin_a * jobs[0].bin_b;
+    std::vector<std::vector<int64_t>> hist(jobs.size(), std::vector<int64_t>(nb));
+    std::vector<int64_t *> hp(jobs.size());
+    for (size_t n = 0; n < jobs.size(); ++n) hp[n] = hist[n].data();
+    std::vector<int64_t> within(jobs.size()), oob(jobs.size());
+    pa_stats st{};
+    const auto t0 = std::chrono::steady_clock::now();
+    rc = pa_distribution_histogram_multi(&traj, jobs.data(), (int)jobs.size(), &r.exec, hp.data(), within.data(), oob.data(), &st);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (rc) { r.error(rc, std::string("GPU histogram failed: ") + pa_last_error()); return rc; }
+    printf("   ### B200 execution (distribution function): %lld frames, %lld pair evaluations, %lld kernel launches\n",
+           (long long)st.frames_done, (long long)st.pairs_evaluated, (long long)st.kernel_launches);
+    printf("   ### End of accelerated section, took %.3f seconds (kernels %.3f ms)\n", sec, st.kernel_ms);
+    const std::string prefix = r.path_out + r.prefix;
+    for (size_t n = 0; n < jobs.size(); ++n) {
+        printf(" Calculating distribution for reference vector %zu out of %zu.\n", n + 1, jobs.size());
+        printf("   within bin %lld, out of bounds %lld.\n", (long long)within[n], (long long)oob[n]);   // Distribution:911
+        std::vector<float> g(nb);
+        float rho = 0.f;
+        rc = pa_transfer_histogram(&traj, &jobs[n], hist[n].data(), within[n], oob[n], r.verbose ? 1 : 0, g.data(), &rho);
+        if (rc == PA_E_BIN_OVERFLOW) r.error(101, "integer overflow in bin count");
+        if (r.verbose) printf("   ideal density:%10.3E particles/Angstrom^3\n", (double)rho);
+        rc = pa_write_distribution(&traj, &jobs[n], (int)n + 1, prefix.c_str(), input_name.c_str(), g.data(), rho);
+        if (rc) { r.error(rc, pa_last_error()); return rc; }
+    }
+    return 0;
+}
+
+void write_simple_sumrules(Run &r)                            // Distribution:43-67
+{
+    const std::string path = r.path_in + "prealpha_simple.inp";
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) { r.error(46, "cannot write '" + path + "'"); return; }
+    fprintf(f, "pdf %zu\n", r.types.size());
+    for (size_t n = 1; n <= r.types.size(); ++n) fprintf(f, "+0 +0 +1 %zu -1\n", n);
+    fprintf(f, "maxdist_optimize\nsubtract_uniform F\nweigh_charge T\nsampling_interval 1\nbin_count_a 300\nbin_count_b 1\nquit\n");
+    fclose(f);
+    if (r.verbose) printf(" File 'prealpha_simple.inp' written.\n");
+}
+
+const char *kOtherModuleKeywords[] = {
+    "show_settings", "print_atomic_masses", "print_atomic_charges", "print_dipole_statistics", "show_drude",
+    "switch_to_com", "barycentric", "barycenter", "barycentre", "dump_snapshot", "dump_snapshot_simple", "dump_split",
+    "dump_split_simple", "dump_single", "dump_cut", "dump_dimers", "dump_neighbour_traj", "dump_example",
+    "dump_example_simple", "dump_full_gro", "dump_full_gro_simple", "contact_distance", "contact_distance_simple",
+    "remove_drudes", "remove_drudes_simple", "remove_cores", "remove_cores_simple", "drude_temp", "drude_temp_simple",
+    "temperature", "temperature_simple", "gyradius", "gyradius_simple", "jump_velocity", "jump_velocity_simple",
+    "convert", "convert_simple", "convert_coc", "convert_coc_simple", "unwrap_full", "unwrap_full_simple",
+    "correlation", "autocorrelation", "dihedral", "reorientation", "rmm-vcf", "conductivity", "velocity",
+    "conductivity_simple", "diffusion", "diffusion_simple", "cross_diffusion", "cluster", "cluster_simple",
+    "speciation", "speciation_simple", "charge_arm_simple", "clm_simple", "cubic_box_edge_simple", "time_scaling",
+    "time_scaling_factor", "error_output", "time_output", "set_threads", "set_threads_simple", "parallel_operation",
+    "parallel_execution", "print_atom_masses", "print_atomic_weights", "print_atom_weights", "print_atom_charges",
+    "print_dipole_properties", "show_drude_settings", "show_drudes", "drude_temperature", "remove_drude", "remove_core",
+    "dump_slab", "dump_slab_simple", "distance", "distances", "distance_simple", "distances_simple", "DEBUG",
+};
+
+}  // namespace
+
+extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec *exec)
+{
+    if (!general_inp_path) return PA_ERR_BAD_ARG;
+    Run r;
+    if (exec) r.exec = *exec;
+    if (r.exec.shard_count < 1) r.exec.shard_count = 1;
+    r.general_path = general_inp_path;
+    std::vector<std::string> lines;
+    if (!read_lines(r.general_path, lines)) { r.error(5, "general input file '" + r.general_path + "' not found"); return r.errors; }
+    std::vector<std::vector<std::string>> toks;        // non-blank records, list-directed READ skips blank ones
+    for (auto &l : lines) { auto t = tokens_of(l); if (!t.empty()) toks.push_back(t); }
+    if (toks.size() < 5) { r.error(5, "general input file has fewer than five header lines"); return r.errors; }
+    r.traj_file = toks[0][0]; r.mol_file = toks[1][0]; r.path_traj = toks[2][0]; r.path_in = toks[3][0]; r.path_out = toks[4][0];
+    printf(" reading file '%s'\n", r.general_path.c_str());
+    std::vector<std::vector<std::string>> body(toks.begin() + 5, toks.end());
+    // whole-file switches (first occurrence before 'quit'), Main:131-357
+    bool b;
+    if (auto *t = find_switch(body, {"sequential_read", "read_sequential"})) if (t->size() > 1 && parse_logical((*t)[1], b)) r.read_sequential = b;
+    bool type_given = false;
+    if (auto *t = find_switch(body, {"trajectory_type"})) {
+        type_given = true;
+        if (t->size() > 1 && ((*t)[1].substr(0, 3) == "lmp" || (*t)[1].substr(0, 3) == "xyz")) { r.traj_type = (*t)[1].substr(0, 3); r.box_given = (r.traj_type == "lmp"); }
+        else r.error(51, "unknown trajectory format");
+    }
+    if (!type_given) {
+        const std::string ext = r.traj_file.size() >= 4 ? r.traj_file.substr(r.traj_file.size() - 4) : "";
+        if (ext == ".lmp" || ext == ".LMP") { r.traj_type = "lmp"; r.box_given = true; }
+        else if (ext == ".xyz" || ext == ".XYZ") { r.traj_type = "xyz"; r.box_given = false; }
+        else r.error(51, "unknown trajectory format");
+    }
+    if (auto *t = find_switch(body, {"cubic_box_edge", "cubic_box"})) {
+        float lo, hi;
+        if (t->size() > 2 && parse_real4((*t)[1], lo) && parse_real4((*t)[2], hi)) {
+            if (lo > hi) r.error(93, "lower box bound > upper box bound");
+            else { if (r.box_given) r.error(92, "box volume specified twice"); set_cubic_box(r, lo, hi); }
+        } else r.error(19, "cannot read cubic_box_edge");
+    }
+    if (auto *t = find_switch(body, {"wrap_trajectory"})) if (t->size() > 1 && parse_logical((*t)[1], b)) r.wrap = b;
+    if (auto *t = find_switch(body, {"unwrap_trajectory"})) if (t->size() > 1 && parse_logical((*t)[1], b)) r.unwrap = b;
+    if (r.wrap || r.unwrap) {
+        // wrap_full / unwrap_full rewrite the stored float32 coordinates (Molecular:1590-1765); SURVEY 8f-2
+        r.error(0, "wrap_trajectory / unwrap_trajectory pre-passes are not part of this path yet");
+        return r.errors;
+    }
+    if (r.read_sequential) printf(" sequential_read T: frames are streamed in batches anyway; the switch has no effect here.\n");
+    if (!read_molecular_input(r)) return r.errors;
+    if (!load_trajectory(r)) return r.errors;
+    // body, Main:2882-3666
+    int nline = 5;
+    for (const auto &t : body) {
+        ++nline;
+        if (nline - 5 > 500) break;                          // MAXITERATIONS
+        std::string k = t[0];
+        if (k == "exit") k = "quit";
+        if (r.verbose) printf(" Line %d: '%s'\n", nline, k.c_str());
+        if (k == "quit") { printf(" exiting analysis.\n"); break; }
+        if (k == "distribution") {
+            if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
+            if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
+            printf(" Distribution module invoked.\n");
+            perform_distribution(r, t[1]);
+        } else if (k == "distribution_simple") {
+            if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
+            write_simple_sumrules(r);
+            printf(" Distribution module invoked.\n");
+            perform_distribution(r, "prealpha_simple.inp");
+        } else if (k == "set_prefix") {
+            if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
+            r.prefix = t[1];
+            while (!r.prefix.empty() && r.prefix.front() == ' ') r.prefix.erase(r.prefix.begin());
+            printf(" prefix set to '%s'\n", r.prefix.c_str());
+        } else if (k == "verbose_output") {
+            if (t.size() > 1 && parse_logical(t[1], b)) r.verbose = b; else { r.error(19, "cannot read general input line"); break; }
+        } else if (k == "sequential_read" || k == "read_sequential" || k == "wrap_trajectory" || k == "unwrap_trajectory" ||
+                   k == "trajectory_type" || k == "cubic_box_edge" || k == "cubic_box" || k == "extra_velocity" || k == "extra_columns") {
+            if (r.verbose) printf(" skip line (%s)\n", k.c_str());
+        } else if (k[0] == '#' || k[0] == '!') {
+            if (r.verbose) printf(" (is commented out)\n");
+        } else {
+            bool known = false;
+            for (const char *o : kOtherModuleKeywords) if (k == o) { known = true; break; }
+            if (known) printf(" keyword '%s' belongs to a prealpha module outside the accelerated path - skipped.\n", k.c_str());
+            else r.error(20, "unknown keyword '" + k + "' in line " + std::to_string(nline));
+        }
+    }
+    printf("\n Encountered %d errors/warnings globally.\n", r.errors);
+    return r.errors;
+}
+
+// row X is built in a later step of the plan: the entry point exists so that the
+// ABI is stable, and fails loudly instead of silently computing on the host.
+extern "C" int pa_distance_subjobs(const pa_traj *, const pa_dist_job *, pa_dist_result *)
+{
+    pa::set_error("pa_distance_subjobs: not implemented yet");
+    return PA_ERR_UNSUPPORTED;
+}

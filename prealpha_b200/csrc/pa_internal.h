@@ -1,0 +1,120 @@
+// Internal declarations shared by the CUDA kernels (pa_kernels.cu), the session /
+// C-ABI layer (pa_session.cu) and the host-side float32-exact logic (pa_host.cpp).
+#ifndef PA_INTERNAL_H
+#define PA_INTERNAL_H
+
+#include <cstdint>
+#include <cstddef>
+#include <string>
+#include <vector>
+#include <vector_types.h>
+#include "../../include/prealpha_b200.h"
+
+// ---------------------------------------------------------------------------
+// Device-side views
+
+// Per molecule type, resident for a batch of frames.
+struct PaDevType {
+    const float  *xyz;          // [nframes][nmol][natoms][3] raw float32 (batch-local)
+    const double *atom_mass;    // [natoms]
+    const double *atom_charge;  // [natoms]
+    double mass;                // %mass
+    double realcharge;          // DBLE(%realcharge)
+    int32_t natoms, nmol, charge;
+    int32_t offset;             // first slot of this type inside a frame's slot range
+};
+
+// SoA of per-molecule points for a batch: slot = frame*M + type.offset + mol.
+// p = centre of mass after wrap_vector (Molecular:1560); ws = its wrap shift;
+// c = unwrapped centre of mass; q = centre of charge (only when some job uses it).
+struct PaPoints {
+    double *px, *py, *pz;
+    double *wx, *wy, *wz;
+    double *cx, *cy, *cz;
+    double *qx, *qy, *qz;       // may be null
+    int64_t M;                  // slots per frame (sum of nmol over all types)
+};
+
+struct PaBox {
+    double lo[3], hi[3], L[3];  // L = hi - lo in fp64 (box_size, Molecular:937)
+    double max_dist_sq;
+    int32_t wrap_trajectory;    // 1: positions are NOT wrapped by the distance routine
+    int32_t com_boost;
+};
+
+// Per job constants the kernels need.
+struct PaDevJob {
+    int32_t mode;               // PA_MODE_*
+    int32_t bin_a, bin_b;
+    int32_t use_coc;
+    double  ref_vec[3];
+    double  rot[9];
+    float   maxdist, step_a, step_b, shift;
+    float   maxdist_sq_f;       // REAL4 maxdist**2
+    // class tables (device pointers, uint64 bit patterns of non-negative doubles):
+    //   thr_a[k], k=0..bin_a+2: smallest d2 whose a-class is >= k (thr_a[0]=0).
+    //   class bin_a = "inside cutoff but a-bin out of bounds", class bin_a+1 = beyond cutoff,
+    //   thr_a[bin_a+2] = never.
+    const unsigned long long *thr_a;
+    //   thr_b[k], k=1..bin_b+1 (doubles): largest dot product whose b-class INT(acos/step_b) is >= k.
+    const double *thr_b;
+    unsigned long long cut_bits;   // = thr_a[bin_a+1]
+    float   guess_scale;        // 1/step_a
+    int32_t z_sign;             // fast path only: +1 / -1 for reference vector along +z / -z
+    unsigned long long *acc;    // device accumulators: [bin_a*bin_b hist][within][oob]
+};
+
+// One launch = one job x one observed type over all frames of the batch.
+struct PaPass {
+    PaPoints pts;
+    PaBox box;
+    PaDevJob job;
+    int32_t nframes;
+    int32_t ref_off, nref;      // slot range of the reference type inside a frame
+    int32_t obs_off, nobs;
+    int32_t same_type;
+    int32_t n_itiles, n_jsplits, jsplit_len;
+    long long weight;           // +1 or charge of the observed type (weigh_charge)
+    // exception list (pairs that need the literal per-pair evaluation)
+    uint2 *exc_list;
+    unsigned int *exc_count;    // [0] appended this pass, [1] sticky overflow flag, [2] verify failures, [3] total processed
+    unsigned int exc_cap;
+    unsigned int *verify_fail;  // debug counter for the class-guess invariant (may be null)
+};
+
+// kernel launch wrappers (pa_kernels.cu).  All return cudaError_t as int.
+struct PaPrepareArgs {
+    const PaDevType *types;     // device array
+    int32_t ntypes;
+    int32_t nframes;
+    PaPoints pts;
+    PaBox box;
+    int32_t need_coc;
+};
+
+int pa_launch_prepare(const PaPrepareArgs &a, void *stream);
+int pa_launch_rdf_fast(const PaPass &p, int sm_count, void *stream);
+int pa_launch_general(const PaPass &p, int sm_count, void *stream);
+int pa_launch_exceptions(const PaPass &p, unsigned int count, void *stream);
+int pa_kernels_selfcheck();    // returns 0 when a kernel image for the current device exists
+int pa_rdf_ri(int nref);       // reference molecules per thread the fast kernel will use (tile = 128*RI)
+int pa_general_ri(int nref);
+#define PA_TILE_THREADS 128
+#define PA_J_CHUNK 128
+
+// ---------------------------------------------------------------------------
+// Host-side float32-exact logic (pa_host.cpp)
+
+namespace pa {
+
+// class tables, see PaDevJob
+void build_thr_a(const pa_job &job, double max_dist_sq, std::vector<unsigned long long> &thr);
+void build_thr_b(const pa_job &job, std::vector<double> &thr);
+int  a_class_of(const pa_job &job, double max_dist_sq, double d2);   // reference arithmetic
+int  b_class_of(const pa_job &job, double dot);
+bool job_is_rdf_fast(const pa_job &job, const pa_traj &traj);
+void set_error(const std::string &msg);
+
+}  // namespace pa
+
+#endif

@@ -1,0 +1,511 @@
+// pa_session.cu -- device sessions and the compute entry points of the C ABI.
+//
+// Replaces iterate_timesteps_parallelised (Distribution:696-760): where the reference hands
+// frames to OpenMP threads with private histograms and merges them in a CRITICAL section,
+// a session streams batches of frames through pinned staging buffers (cudaMemcpyAsync on a
+// copy stream, double buffered), runs the prepare + pair kernels on a compute stream and keeps
+// one int64 accumulator block per job in HBM.  Frames are independent, so a shard of the
+// sampled frames can be given to each GPU; integer accumulation makes the sum order-free.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "pa_internal.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+#define PA_CK(call)                                                                              \
+    do {                                                                                         \
+        cudaError_t e__ = (call);                                                                \
+        if (e__ != cudaSuccess) {                                                                \
+            pa::set_error(std::string(#call) + ": " + cudaGetErrorString(e__));                  \
+            return e__ == cudaErrorNoDevice || e__ == cudaErrorInsufficientDriver ||             \
+                           e__ == cudaErrorNoKernelImageForDevice ? PA_ERR_NO_DEVICE : PA_ERR_CUDA; \
+        }                                                                                        \
+    } while (0)
+
+struct TypeMeta {
+    int32_t charge, natoms, nmol, offset;
+    double mass, realcharge;
+    bool needed;
+    double *d_mass = nullptr, *d_charge = nullptr;
+    size_t frame_floats() const { return (size_t)nmol * natoms * 3; }
+};
+
+struct JobState {
+    pa_job job;
+    PaDevJob dj;
+    bool fast;
+    size_t acc_off;      // offset (words) inside the accumulator block
+    size_t nbins;
+    unsigned long long *d_thr_a = nullptr;
+    double *d_thr_b = nullptr;
+};
+
+constexpr unsigned int kExcCap = 4u << 20;
+
+}  // namespace
+
+void pa::set_error(const std::string &msg) { g_last_error = msg; }
+
+struct pa_session {
+    int device = 0, sm_count = 148;
+    pa_exec exec{};
+    std::vector<TypeMeta> types;
+    PaBox box{};
+    int64_t M = 0;
+    std::vector<JobState> jobs;
+    bool need_coc = false, force_general = false, verify = false;
+    int max_frames = 0, nframes = 0;       // capacity / resident frames
+    int cur = 0;                            // raw buffer slot holding the resident frames
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_h2d[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
+    bool slot_used[2] = { false, false };
+    std::vector<float *> d_raw[2];
+    float *h_pinned[2] = { nullptr, nullptr };
+    size_t pinned_floats = 0;
+    PaDevType *d_types[2] = { nullptr, nullptr };
+    double *d_pts = nullptr;
+    PaPoints pts{};
+    unsigned long long *d_acc = nullptr;
+    size_t acc_words = 0;
+    uint2 *d_exc = nullptr;
+    unsigned int *d_exc_count = nullptr;    // [0] count, [1] sticky overflow, [2] verify failures
+    pa_stats stats{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+};
+
+namespace {
+
+int upload_types_table(pa_session *s, int slot)
+{
+    std::vector<PaDevType> h(s->types.size());
+    for (size_t t = 0; t < s->types.size(); ++t) {
+        const TypeMeta &m = s->types[t];
+        h[t].xyz = m.needed ? s->d_raw[slot][t] : nullptr;
+        h[t].atom_mass = m.d_mass; h[t].atom_charge = m.d_charge;
+        h[t].mass = m.mass; h[t].realcharge = m.realcharge;
+        h[t].natoms = m.natoms; h[t].nmol = m.nmol; h[t].charge = m.charge; h[t].offset = m.offset;
+    }
+    PA_CK(cudaMemcpy(s->d_types[slot], h.data(), h.size() * sizeof(PaDevType), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pa_abi_version(void) { return PA_ABI_VERSION; }
+const char *pa_last_error(void) { return g_last_error.c_str(); }
+
+int pa_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, d) == cudaSuccess && prop.major == 10) ++ok;
+    }
+    return ok;
+}
+
+int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, const pa_exec *exec,
+                      int32_t max_frames, pa_session **out)
+{
+    if (!traj || !jobs || njobs < 1 || !out || max_frames < 1 || traj->ntypes < 1) { pa::set_error("bad argument"); return PA_ERR_BAD_ARG; }
+    pa_exec ex{};
+    if (exec) ex = *exec;
+    if (ex.shard_count < 1) ex.shard_count = 1;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        pa::set_error("no CUDA device (this path has no CPU fallback)");
+        return PA_ERR_NO_DEVICE;
+    }
+    PA_CK(cudaSetDevice(ex.device));
+    if (pa_kernels_selfcheck() != 0) {
+        cudaGetLastError();
+        pa::set_error("no sm_100a kernel image for this device (library is built for B200 only)");
+        return PA_ERR_NO_DEVICE;
+    }
+    pa_session *s = new pa_session();
+    s->device = ex.device; s->exec = ex;
+    s->force_general = (ex.flags & PA_EXEC_FORCE_GENERAL) != 0;
+    s->verify = (ex.flags & 0x100) != 0;
+    cudaDeviceProp prop;
+    PA_CK(cudaGetDeviceProperties(&prop, ex.device));
+    s->sm_count = prop.multiProcessorCount;
+    for (int k = 0; k < 3; ++k) {
+        s->box.lo[k] = traj->box_lo[k]; s->box.hi[k] = traj->box_hi[k];
+        s->box.L[k] = traj->box_hi[k] - traj->box_lo[k];
+    }
+    s->box.max_dist_sq = traj->max_dist_sq;
+    s->box.wrap_trajectory = traj->wrap_trajectory; s->box.com_boost = traj->com_boost;
+    // validate jobs, decide which types are needed
+    s->types.resize(traj->ntypes);
+    int64_t off = 0;
+    for (int t = 0; t < traj->ntypes; ++t) {
+        const pa_type &ty = traj->types[t];
+        if (ty.natoms < 1 || ty.nmol < 1) { delete s; pa::set_error("molecule type with natoms/nmol < 1"); return PA_ERR_BAD_ARG; }
+        TypeMeta &m = s->types[t];
+        m.charge = ty.charge; m.natoms = ty.natoms; m.nmol = ty.nmol; m.offset = (int32_t)off;
+        m.mass = ty.mass; m.realcharge = (double)ty.realcharge; m.needed = false;
+        off += ty.nmol;
+    }
+    s->M = off;
+    for (int j = 0; j < njobs; ++j) {
+        const pa_job &jb = jobs[j];
+        if (jb.ref_type < 1 || jb.ref_type > traj->ntypes || jb.obs_type > traj->ntypes) {
+            delete s; pa::set_error("molecule type index out of range (error 33)"); return PA_E_TYPE_INVALID;
+        }
+        if (jb.bin_a < 1 || jb.bin_a > 1000 || jb.bin_b < 1 || jb.bin_b > 1000 || jb.sampling_interval < 1 ||
+            (jb.mode != PA_MODE_PDF && jb.mode != PA_MODE_CDF)) {
+            delete s; pa::set_error("invalid job (bins 1..1000, sampling_interval >= 1, mode cdf|pdf)"); return PA_ERR_BAD_ARG;
+        }
+        s->types[jb.ref_type - 1].needed = true;
+        if (jb.obs_type < 1) for (auto &m : s->types) m.needed = true;
+        else s->types[jb.obs_type - 1].needed = true;
+        if (jb.use_coc) s->need_coc = true;
+    }
+    // frames per batch: slots must stay addressable with 32 bits (exception list entries)
+    const int64_t cap_frames = std::max<int64_t>(1, (int64_t)0x7fffffff / std::max<int64_t>(1, s->M));
+    s->max_frames = (int)std::min<int64_t>(max_frames, cap_frames);
+    PA_CK(cudaStreamCreateWithFlags(&s->s_compute, cudaStreamNonBlocking));
+    PA_CK(cudaStreamCreateWithFlags(&s->s_copy, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+        PA_CK(cudaEventCreateWithFlags(&s->ev_h2d[b], cudaEventDisableTiming));
+        PA_CK(cudaEventCreateWithFlags(&s->ev_done[b], cudaEventDisableTiming));
+    }
+    // per-type constants and raw buffers
+    size_t pinned = 0;
+    for (int t = 0; t < traj->ntypes; ++t) {
+        TypeMeta &m = s->types[t];
+        const pa_type &ty = traj->types[t];
+        PA_CK(cudaMalloc(&m.d_mass, sizeof(double) * m.natoms));
+        PA_CK(cudaMalloc(&m.d_charge, sizeof(double) * m.natoms));
+        std::vector<double> zeros(m.natoms, 0.0);
+        PA_CK(cudaMemcpy(m.d_mass, ty.atom_mass ? ty.atom_mass : zeros.data(), sizeof(double) * m.natoms, cudaMemcpyHostToDevice));
+        PA_CK(cudaMemcpy(m.d_charge, ty.atom_charge ? ty.atom_charge : zeros.data(), sizeof(double) * m.natoms, cudaMemcpyHostToDevice));
+        if (m.needed) pinned += m.frame_floats() * (size_t)s->max_frames;
+    }
+    s->pinned_floats = pinned;
+    for (int b = 0; b < 2; ++b) {
+        s->d_raw[b].assign(traj->ntypes, nullptr);
+        for (int t = 0; t < traj->ntypes; ++t)
+            if (s->types[t].needed)
+                PA_CK(cudaMalloc(&s->d_raw[b][t], sizeof(float) * s->types[t].frame_floats() * (size_t)s->max_frames));
+        PA_CK(cudaMallocHost(&s->h_pinned[b], sizeof(float) * std::max<size_t>(pinned, 1)));
+        PA_CK(cudaMalloc(&s->d_types[b], sizeof(PaDevType) * traj->ntypes));
+        int rc = upload_types_table(s, b);
+        if (rc) return rc;
+    }
+    // points SoA
+    const size_t nslots = (size_t)s->max_frames * (size_t)s->M;
+    const int narr = s->need_coc ? 12 : 9;
+    PA_CK(cudaMalloc(&s->d_pts, sizeof(double) * nslots * narr));
+    double *b0 = s->d_pts;
+    s->pts.px = b0; s->pts.py = b0 + nslots; s->pts.pz = b0 + 2 * nslots;
+    s->pts.wx = b0 + 3 * nslots; s->pts.wy = b0 + 4 * nslots; s->pts.wz = b0 + 5 * nslots;
+    s->pts.cx = b0 + 6 * nslots; s->pts.cy = b0 + 7 * nslots; s->pts.cz = b0 + 8 * nslots;
+    if (s->need_coc) { s->pts.qx = b0 + 9 * nslots; s->pts.qy = b0 + 10 * nslots; s->pts.qz = b0 + 11 * nslots; }
+    else s->pts.qx = s->pts.qy = s->pts.qz = nullptr;
+    s->pts.M = s->M;
+    // jobs: tables + accumulators
+    s->jobs.resize(njobs);
+    size_t words = 0;
+    for (int j = 0; j < njobs; ++j) {
+        JobState &js = s->jobs[j];
+        js.job = jobs[j];
+        js.nbins = (size_t)jobs[j].bin_a * jobs[j].bin_b;
+        js.acc_off = words;
+        words += js.nbins + 2;
+    }
+    s->acc_words = words;
+    PA_CK(cudaMalloc(&s->d_acc, sizeof(unsigned long long) * words));
+    PA_CK(cudaMemset(s->d_acc, 0, sizeof(unsigned long long) * words));
+    PA_CK(cudaMalloc(&s->d_exc, sizeof(uint2) * kExcCap));
+    PA_CK(cudaMalloc(&s->d_exc_count, sizeof(unsigned int) * 4));
+    PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 4));
+    for (int j = 0; j < njobs; ++j) {
+        JobState &js = s->jobs[j];
+        const pa_job &jb = js.job;
+        std::vector<unsigned long long> thr_a;
+        std::vector<double> thr_b;
+        pa::build_thr_a(jb, traj->max_dist_sq, thr_a);
+        PA_CK(cudaMalloc(&js.d_thr_a, sizeof(unsigned long long) * thr_a.size()));
+        PA_CK(cudaMemcpy(js.d_thr_a, thr_a.data(), sizeof(unsigned long long) * thr_a.size(), cudaMemcpyHostToDevice));
+        if (jb.mode == PA_MODE_PDF) {
+            pa::build_thr_b(jb, thr_b);
+            PA_CK(cudaMalloc(&js.d_thr_b, sizeof(double) * thr_b.size()));
+            PA_CK(cudaMemcpy(js.d_thr_b, thr_b.data(), sizeof(double) * thr_b.size(), cudaMemcpyHostToDevice));
+        }
+        PaDevJob &d = js.dj;
+        memset(&d, 0, sizeof d);
+        d.mode = jb.mode; d.bin_a = jb.bin_a; d.bin_b = jb.bin_b; d.use_coc = jb.use_coc;
+        for (int k = 0; k < 3; ++k) d.ref_vec[k] = jb.ref_vec[k];
+        for (int k = 0; k < 9; ++k) d.rot[k] = jb.rot[k];
+        d.maxdist = jb.maxdist; d.step_a = jb.step_a; d.step_b = jb.step_b; d.shift = jb.shift;
+        d.maxdist_sq_f = jb.maxdist * jb.maxdist;
+        d.thr_a = js.d_thr_a; d.thr_b = js.d_thr_b;
+        d.cut_bits = thr_a[(size_t)(jb.mode == PA_MODE_PDF ? jb.bin_a : 0) + 1];
+        d.guess_scale = 1.0f / jb.step_a;
+        d.z_sign = jb.ref_vec[2] > 0 ? 1 : -1;
+        d.acc = s->d_acc + js.acc_off;
+        js.fast = !s->force_general && pa::job_is_rdf_fast(jb, *traj);
+    }
+    *out = s;
+    return 0;
+}
+
+int pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, int32_t nframes, int32_t step_stride)
+{
+    if (!s || !traj || nframes < 1 || nframes > s->max_frames || step_stride < 1 || first_step < 0 ||
+        (int64_t)first_step + (int64_t)(nframes - 1) * step_stride >= traj->nsteps || traj->ntypes != (int)s->types.size()) {
+        pa::set_error("pa_session_upload: bad frame range"); return PA_ERR_BAD_ARG;
+    }
+    PA_CK(cudaSetDevice(s->device));
+    const int slot = s->cur ^ 1;
+    // the pinned buffer of this slot may still be read by its previous H2D copy, and the device
+    // buffer by the kernels of the batch that used it
+    if (s->slot_used[slot]) {
+        PA_CK(cudaEventSynchronize(s->ev_h2d[slot]));
+        PA_CK(cudaStreamWaitEvent(s->s_copy, s->ev_done[slot], 0));
+    }
+    size_t poff = 0;
+    for (size_t t = 0; t < s->types.size(); ++t) {
+        const TypeMeta &m = s->types[t];
+        if (!m.needed) continue;
+        const pa_type &ty = traj->types[t];
+        if (!ty.xyz || ty.natoms != m.natoms || ty.nmol != m.nmol) { pa::set_error("pa_session_upload: trajectory does not match the session"); return PA_ERR_BAD_ARG; }
+        const size_t ff = m.frame_floats();
+        float *dst = s->h_pinned[slot] + poff;
+        for (int f = 0; f < nframes; ++f)
+            memcpy(dst + (size_t)f * ff, ty.xyz + (size_t)(first_step + (int64_t)f * step_stride) * ff, ff * sizeof(float));
+        PA_CK(cudaMemcpyAsync(s->d_raw[slot][t], dst, sizeof(float) * ff * nframes, cudaMemcpyHostToDevice, s->s_copy));
+        s->stats.h2d_bytes += (int64_t)(sizeof(float) * ff * nframes);
+        poff += ff * (size_t)s->max_frames;
+    }
+    PA_CK(cudaEventRecord(s->ev_h2d[slot], s->s_copy));
+    s->slot_used[slot] = true;
+    s->cur = slot;
+    s->nframes = nframes;
+    return 0;
+}
+
+int pa_session_run(pa_session *s)
+{
+    if (!s || s->nframes < 1) { pa::set_error("pa_session_run: nothing resident"); return PA_ERR_BAD_ARG; }
+    PA_CK(cudaSetDevice(s->device));
+    const int slot = s->cur;
+    PA_CK(cudaStreamWaitEvent(s->s_compute, s->ev_h2d[slot], 0));
+    cudaEvent_t e0, e1;
+    PA_CK(cudaEventCreate(&e0)); PA_CK(cudaEventCreate(&e1));
+    PA_CK(cudaEventRecord(e0, s->s_compute));
+    PaPrepareArgs pa{};
+    pa.types = s->d_types[slot]; pa.ntypes = (int)s->types.size(); pa.nframes = s->nframes;
+    pa.pts = s->pts; pa.box = s->box; pa.need_coc = s->need_coc ? 1 : 0;
+    PA_CK((cudaError_t)pa_launch_prepare(pa, s->s_compute));
+    s->stats.kernel_launches += 1;
+    const long long target_items = (long long)s->sm_count * 16;
+    for (JobState &js : s->jobs) {
+        const pa_job &jb = js.job;
+        const int r = jb.ref_type - 1;
+        const int o_first = jb.obs_type < 1 ? 0 : jb.obs_type - 1;
+        const int o_last = jb.obs_type < 1 ? (int)s->types.size() - 1 : jb.obs_type - 1;
+        for (int o = o_first; o <= o_last; ++o) {                 // Distribution:727-735
+            PaPass p{};
+            p.pts = s->pts; p.box = s->box; p.job = js.dj;
+            p.nframes = s->nframes;
+            p.ref_off = s->types[r].offset; p.nref = s->types[r].nmol;
+            p.obs_off = s->types[o].offset; p.nobs = s->types[o].nmol;
+            p.same_type = (r == o) ? 1 : 0;
+            p.weight = jb.weigh_charge ? (long long)s->types[o].charge : 1ll;   // Distribution:833-838
+            const int ri = js.fast ? pa_rdf_ri(p.nref) : pa_general_ri(p.nref);
+            const int ti = PA_TILE_THREADS * ri;
+            p.n_itiles = (p.nref + ti - 1) / ti;
+            const long long items0 = (long long)p.nframes * p.n_itiles;
+            const int max_splits = (p.nobs + PA_J_CHUNK - 1) / PA_J_CHUNK;
+            long long want = items0 >= target_items ? 1 : (target_items + items0 - 1) / items0;
+            if (want > max_splits) want = max_splits;
+            int len = (int)((p.nobs + want - 1) / want);
+            len = ((len + PA_J_CHUNK - 1) / PA_J_CHUNK) * PA_J_CHUNK;
+            p.jsplit_len = len;
+            p.n_jsplits = (p.nobs + len - 1) / len;
+            p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = kExcCap;
+            p.verify_fail = s->verify ? s->d_exc_count + 2 : nullptr;
+            if (js.fast) {
+                PA_CK((cudaError_t)pa_launch_rdf_fast(p, s->sm_count, s->s_compute));
+                PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
+                s->stats.kernel_launches += 3;
+            } else {
+                PA_CK((cudaError_t)pa_launch_general(p, s->sm_count, s->s_compute));
+                s->stats.kernel_launches += 1;
+            }
+            s->stats.pairs_evaluated += (int64_t)p.nframes * ((int64_t)p.nref * p.nobs - (p.same_type ? p.nref : 0));
+        }
+    }
+    PA_CK(cudaEventRecord(e1, s->s_compute));
+    PA_CK(cudaEventRecord(s->ev_done[slot], s->s_compute));
+    s->kernel_events.emplace_back(e0, e1);
+    s->stats.frames_done += s->nframes;
+    return 0;
+}
+
+int pa_session_stats(pa_session *s, pa_stats *st)
+{
+    if (!s || !st) return PA_ERR_BAD_ARG;
+    PA_CK(cudaSetDevice(s->device));
+    PA_CK(cudaStreamSynchronize(s->s_compute));
+    for (auto &ev : s->kernel_events) {
+        float ms = 0.f;
+        PA_CK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        s->stats.kernel_ms += ms;
+        cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+    }
+    s->kernel_events.clear();
+    *st = s->stats;
+    return 0;
+}
+
+int pa_session_download(pa_session *s, int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, int32_t reset)
+{
+    if (!s) return PA_ERR_BAD_ARG;
+    PA_CK(cudaSetDevice(s->device));
+    PA_CK(cudaStreamSynchronize(s->s_compute));
+    std::vector<unsigned long long> h(s->acc_words);
+    unsigned int flags[4];
+    PA_CK(cudaMemcpy(h.data(), s->d_acc, sizeof(unsigned long long) * s->acc_words, cudaMemcpyDeviceToHost));
+    PA_CK(cudaMemcpy(flags, s->d_exc_count, sizeof flags, cudaMemcpyDeviceToHost));
+    s->stats.d2h_bytes += (int64_t)(sizeof(unsigned long long) * s->acc_words + sizeof flags);
+    s->stats.exception_pairs = (int64_t)flags[3];
+    int64_t binned = 0;
+    for (size_t j = 0; j < s->jobs.size(); ++j) {
+        const JobState &js = s->jobs[j];
+        if (hists && hists[j]) memcpy(hists[j], h.data() + js.acc_off, sizeof(int64_t) * js.nbins);
+        if (within_bin) within_bin[j] = (int64_t)h[js.acc_off + js.nbins];
+        if (out_of_bounds) out_of_bounds[j] = (int64_t)h[js.acc_off + js.nbins + 1];
+        binned += (int64_t)h[js.acc_off + js.nbins];
+    }
+    s->stats.pairs_binned = binned;
+    if (reset) {
+        PA_CK(cudaMemset(s->d_acc, 0, sizeof(unsigned long long) * s->acc_words));
+        PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 4));
+    }
+    if (flags[1]) {
+        pa::set_error("exception list overflow: too many pairs (anti)parallel to the reference axis; rerun with PA_EXEC_FORCE_GENERAL");
+        return PA_ERR_UNSUPPORTED;
+    }
+    if (flags[2]) {
+        pa::set_error("internal: class-seed invariant violated " + std::to_string(flags[2]) + " times");
+        return PA_ERR_CUDA;
+    }
+    return 0;
+}
+
+int pa_session_device_accumulators(pa_session *s, void **dev_ptr, int64_t *nwords)
+{
+    if (!s || !dev_ptr || !nwords) return PA_ERR_BAD_ARG;
+    PA_CK(cudaSetDevice(s->device));
+    PA_CK(cudaStreamSynchronize(s->s_compute));
+    *dev_ptr = s->d_acc; *nwords = (int64_t)s->acc_words;
+    return 0;
+}
+
+void pa_session_destroy(pa_session *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->s_compute) cudaStreamSynchronize(s->s_compute);
+    if (s->s_copy) cudaStreamSynchronize(s->s_copy);
+    for (auto &ev : s->kernel_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto &m : s->types) { cudaFree(m.d_mass); cudaFree(m.d_charge); }
+    for (int b = 0; b < 2; ++b) {
+        for (float *p : s->d_raw[b]) cudaFree(p);
+        if (s->h_pinned[b]) cudaFreeHost(s->h_pinned[b]);
+        cudaFree(s->d_types[b]);
+        if (s->ev_h2d[b]) cudaEventDestroy(s->ev_h2d[b]);
+        if (s->ev_done[b]) cudaEventDestroy(s->ev_done[b]);
+    }
+    for (auto &js : s->jobs) { cudaFree(js.d_thr_a); cudaFree(js.d_thr_b); }
+    cudaFree(s->d_pts); cudaFree(s->d_acc); cudaFree(s->d_exc); cudaFree(s->d_exc_count);
+    if (s->s_compute) cudaStreamDestroy(s->s_compute);
+    if (s->s_copy) cudaStreamDestroy(s->s_copy);
+    delete s;
+}
+
+// ---------------------------------------------------------------------------
+// one-shot entry points
+
+static int choose_batch(const pa_traj *traj, const pa_exec *ex, int nsamp_local)
+{
+    if (ex && ex->frames_per_batch > 0) return std::min(ex->frames_per_batch, std::max(nsamp_local, 1));
+    int64_t atoms = 0, M = 0;
+    for (int t = 0; t < traj->ntypes; ++t) { atoms += (int64_t)traj->types[t].natoms * traj->types[t].nmol; M += traj->types[t].nmol; }
+    // ~2^24 atoms of raw coordinates (200 MB) and ~2^23 molecule slots (72-96 B each) per batch
+    int64_t b = std::min<int64_t>((int64_t(1) << 24) / std::max<int64_t>(atoms, 1), (int64_t(1) << 23) / std::max<int64_t>(M, 1));
+    b = std::max<int64_t>(1, std::min<int64_t>(b, nsamp_local));
+    return (int)b;
+}
+
+int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int32_t njobs, const pa_exec *exec,
+                                    int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, pa_stats *stats)
+{
+    if (!traj || !jobs || njobs < 1) { pa::set_error("bad argument"); return PA_ERR_BAD_ARG; }
+    pa_exec ex{};
+    if (exec) ex = *exec;
+    if (ex.shard_count < 1) ex.shard_count = 1;
+    if (ex.shard_rank < 0 || ex.shard_rank >= ex.shard_count) { pa::set_error("bad shard"); return PA_ERR_BAD_ARG; }
+    const int dt = jobs[0].sampling_interval;
+    for (int j = 1; j < njobs; ++j)
+        if (jobs[j].sampling_interval != dt) { pa::set_error("jobs of one call must share sampling_interval"); return PA_ERR_BAD_ARG; }
+    if (dt < 1) { pa::set_error("sampling_interval < 1"); return PA_ERR_BAD_ARG; }
+    // sampled frames 0, dt, 2dt, ... (Distribution:718); this shard takes k % count == rank
+    const int nsamp = (traj->nsteps + dt - 1) / dt;
+    const int nlocal = nsamp > ex.shard_rank ? (nsamp - ex.shard_rank + ex.shard_count - 1) / ex.shard_count : 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int batch = choose_batch(traj, &ex, nlocal);
+        pa_session *s = nullptr;
+        int rc = pa_session_create(traj, jobs, njobs, &ex, batch, &s);
+        if (rc) return rc;
+        cudaEvent_t t0, t1;
+        cudaEventCreate(&t0); cudaEventCreate(&t1);
+        cudaEventRecord(t0, s->s_compute);
+        const int first = ex.shard_rank * dt, stride = ex.shard_count * dt;
+        for (int done = 0; done < nlocal && rc == 0; done += s->max_frames) {
+            const int n = std::min(s->max_frames, nlocal - done);
+            rc = pa_session_upload(s, traj, first + done * stride, n, stride);
+            if (rc == 0) rc = pa_session_run(s);
+        }
+        if (rc == 0) rc = pa_session_download(s, hists, within_bin, out_of_bounds, 0);
+        cudaEventRecord(t1, s->s_compute);
+        cudaEventSynchronize(t1);
+        if (stats) {
+            pa_session_stats(s, stats);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, t0, t1);
+            stats->total_ms = ms;
+        }
+        cudaEventDestroy(t0); cudaEventDestroy(t1);
+        pa_session_destroy(s);
+        if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_FORCE_GENERAL)) {   // exception list overflow
+            ex.flags |= PA_EXEC_FORCE_GENERAL;
+            continue;
+        }
+        return rc;
+    }
+    return PA_ERR_UNSUPPORTED;
+}
+
+int pa_distribution_histogram(const pa_traj *traj, const pa_job *job, int64_t *hist, int64_t *within_bin, int64_t *out_of_bounds)
+{
+    int64_t *hp[1] = { hist };
+    return pa_distribution_histogram_multi(traj, job, 1, nullptr, hp, within_bin, out_of_bounds, nullptr);
+}
+
+}  // extern "C"

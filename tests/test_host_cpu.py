@@ -1,0 +1,187 @@
+"""CPU-side checks of the product library (no compute calls): the C ABI loads and exports every
+declared symbol, and the host logic around the hot loop (job set-up, class tables, normalisation,
+writers) reproduces the reference binary's outputs when fed the oracle's histogram."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import fixtures
+from prealpha_b200 import api, capi, inputs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    header = open(os.path.join(ROOT, "include", "prealpha_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pa_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(capi.SIGNATURES), (declared ^ set(capi.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pa_abi_version() == 1
+
+
+def test_struct_layout_matches_header_sizes():
+    # sizes the C compiler produced (pa_debug_* is built from the same header)
+    assert C.sizeof(capi.pa_type) == 56
+    assert C.sizeof(capi.pa_traj) == 16 + 48 + 8 + 8
+    assert C.sizeof(capi.pa_job) == 4 * 6 + 24 + 72 + 16 + 8 * 4
+    assert C.sizeof(capi.pa_exec) == 24
+
+
+@pytest.mark.parametrize("name", fixtures.available())
+def test_job_setup_matches_oracle_bitwise(name, oracle):
+    fx = fixtures.Fixture(name)
+    traj = fx.trajectory()
+    for jn, refnum, rq, _ in fx.jobs():
+        a = api.job_setup(traj, rq)
+        b = oracle.job_setup(traj, rq)
+        assert bytes(a) == bytes(b), (name, jn, refnum)
+
+
+@pytest.mark.parametrize("name", fixtures.available())
+def test_transfer_and_writers_reproduce_reference_files(name, oracle, tmp_path):
+    """Product host code (rows N, W) on the oracle's integer histogram -> the binary's files."""
+    fx = fixtures.Fixture(name)
+    traj = fx.trajectory()
+    for jn, refnum, rq, (within, oob) in fx.jobs():
+        job = api.job_setup(traj, rq)
+        hist, w, o = oracle.histogram(traj, job)
+        assert (w, o) == (within, oob)
+        g, rho, rc = api.transfer(traj, job, hist, w, o, verbose=1)
+        assert rc == 0
+        g0, rho0, _ = oracle.transfer(traj, job, hist, w, o, verbose=1)
+        assert g.tobytes() == g0.tobytes() and np.float32(rho).tobytes() == np.float32(rho0).tobytes()
+        d = tmp_path / f"{jn}_{refnum}"
+        d.mkdir()
+        api.write(traj, job, refnum, str(d) + os.sep, jn + ".inp", g, rho)
+        exp = fx.expected_files(jn)
+        for fn in os.listdir(d):
+            assert (d / fn).read_bytes() == exp[fn], (name, jn, fn)
+
+
+def test_format_real4_matches_oracle(oracle):
+    rng = np.random.default_rng(1)
+    vals = np.concatenate([
+        rng.standard_normal(2000).astype(np.float32) * np.float32(10.0) ** rng.integers(-12, 12, 2000).astype(np.float32),
+        np.array([0.0, 0.1, 0.099999994, 0.09999999, 1e9, 999999999.0, 9.99999999e8, 1.0, -1.0, 123456.789, 1e-38, 3e38,
+                  0.99999994, 9.9999999], dtype=np.float32)])
+    for v in vals:
+        assert api.format_real4(v) == oracle.format_real4(v), float(v)
+    assert api.format_real4(0.159805745) == "  0.159805745    "
+    assert api.format_real4(5.32685816e-02) == "   5.32685816E-02"
+
+
+def _tables(job, mds):
+    lib = capi.load()
+    lib.pa_debug_thr_a.restype = C.c_int
+    lib.pa_debug_thr_a.argtypes = [C.POINTER(capi.pa_job), C.c_double, C.POINTER(C.c_uint64), C.c_int32]
+    lib.pa_debug_thr_b.restype = C.c_int
+    lib.pa_debug_thr_b.argtypes = [C.POINTER(capi.pa_job), C.POINTER(C.c_double), C.c_int32]
+    lib.pa_debug_a_class.restype = C.c_int
+    lib.pa_debug_a_class.argtypes = [C.POINTER(capi.pa_job), C.c_double, C.c_double]
+    lib.pa_debug_b_class.restype = C.c_int
+    lib.pa_debug_b_class.argtypes = [C.POINTER(capi.pa_job), C.c_double]
+    n = lib.pa_debug_thr_a(C.byref(job), mds, None, 0)
+    ta = np.zeros(n, dtype=np.uint64)
+    lib.pa_debug_thr_a(C.byref(job), mds, ta.ctypes.data_as(C.POINTER(C.c_uint64)), n)
+    tb = None
+    if job.mode == capi.PA_MODE_PDF:
+        n = lib.pa_debug_thr_b(C.byref(job), None, 0)
+        tb = np.zeros(n, dtype=np.float64)
+        lib.pa_debug_thr_b(C.byref(job), tb.ctypes.data_as(C.POINTER(C.c_double)), n)
+    return lib, ta, tb
+
+
+@pytest.mark.parametrize("maxdist,bins,mds", [(31.96115, 300, 22500.0), (135.7209, 1000, 22500.0), (7.5, 64, 22500.0),
+                                              (200.0, 500, 22500.0), (10.0, 1, 1e9), (0.5, 1000, 22500.0)])
+def test_a_class_table_equals_reference_arithmetic(maxdist, bins, mds):
+    """#thresholds <= bits(m)  ==  INT(SQRT(REAL4(m))/step_a) etc. for random and boundary m."""
+    fx = fixtures.Fixture("synth")
+    traj = fx.trajectory()
+    rq = capi.make_request(mode="pdf", bin_a=bins, bin_b=1, maxdist=maxdist, sampling_interval=1)
+    job = api.job_setup(traj, rq)
+    lib, ta, _ = _tables(job, mds)
+    assert len(ta) == bins + 3 and ta[0] == 0
+    fin = ta[ta != np.uint64(0xFFFFFFFFFFFFFFFF)]
+    assert np.all(np.diff(fin.astype(np.float64)) >= 0)
+    rng = np.random.default_rng(5)
+    ms = np.concatenate([rng.random(4000) * maxdist ** 2 * 1.3, rng.random(500) * 1e-6, [0.0, 1e300, np.inf, mds, np.nextafter(mds, 0)]])
+    near = []
+    for t in fin[1:]:
+        v = np.array([t], dtype=np.uint64).view(np.float64)[0]
+        near += [v, np.nextafter(v, 0.0), np.nextafter(v, np.inf)]
+    ms = np.concatenate([ms, np.array(near)])
+    bits = ms.view(np.uint64) if ms.dtype == np.float64 else None
+    for m, b in zip(ms, np.asarray(ms, dtype=np.float64).view(np.uint64)):
+        cls_table = int(np.searchsorted(ta[1:], b, side="right"))        # number of k>=1 with thr[k] <= bits
+        assert cls_table == lib.pa_debug_a_class(C.byref(job), mds, float(m)), (m, cls_table)
+
+
+@pytest.mark.parametrize("bins,vec", [(1, (0, 0, 1)), (36, (0, 0, 1)), (18, (1, 1, 0)), (1000, (2, -1, 1))])
+def test_b_class_table_equals_acos_arithmetic(bins, vec):
+    fx = fixtures.Fixture("synth")
+    traj = fx.trajectory()
+    job = api.job_setup(traj, capi.make_request(mode="pdf", vec=vec, bin_a=10, bin_b=bins, maxdist=5.0, sampling_interval=1))
+    lib, _, tb = _tables(job, 22500.0)
+    assert len(tb) == bins + 1
+    assert np.all(np.diff(tb[1:]) <= 0)
+    rng = np.random.default_rng(6)
+    dots = np.concatenate([rng.random(3000) * 2 - 1, [1.0, -1.0, 0.0, -1 + 2.2e-16, -1 + 4.4e-16, -1 + 6.6e-16, 1 - 1.1e-16]])
+    near = []
+    for t in tb[1:]:
+        if -1 <= t <= 1:
+            near += [t, np.nextafter(t, -2.0), np.nextafter(t, 2.0)]
+    dots = np.concatenate([dots, np.clip(np.array(near), -1, 1)])
+    for d in dots:
+        cls_table = int(np.sum(d <= tb[1:]))
+        ref = lib.pa_debug_b_class(C.byref(job), float(d))
+        assert cls_table == min(ref, bins), (d, cls_table, ref)
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    """No CPU fallback: without a device the hot path must return PA_ERR_NO_DEVICE, not a result."""
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    fx = fixtures.Fixture("synth")
+    traj = fx.trajectory()
+    job = api.job_setup(traj, fx.jobs()[0][2])
+    hist = np.zeros(job.bin_a * job.bin_b, dtype=np.int64)
+    w, o = C.c_int64(0), C.c_int64(0)
+    rc = capi.load().pa_distribution_histogram(traj.ptr, C.byref(job), hist.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(w), C.byref(o))
+    assert rc == capi.PA_ERR_NO_DEVICE
+    assert not hist.any()
+    assert b"no CUDA device" in capi.load().pa_last_error() or b"CPU fallback" in capi.load().pa_last_error()
+
+
+def test_rdf_fast_eligibility():
+    fx = fixtures.Fixture("synth")
+    traj = fx.trajectory()
+    lib = capi.load()
+    lib.pa_debug_is_rdf_fast.restype = C.c_int
+    lib.pa_debug_is_rdf_fast.argtypes = [C.POINTER(capi.pa_job)]
+
+    def fast(**kw):
+        return lib.pa_debug_is_rdf_fast(C.byref(api.job_setup(traj, capi.make_request(sampling_interval=1, **kw))))
+    assert fast(mode="pdf", bin_b=1, maxdist=10.0) == 1
+    assert fast(mode="pdf", vec=(0, 0, -3), bin_b=1, maxdist=10.0) == 1
+    assert fast(mode="pdf", bin_b=2, maxdist=10.0) == 0
+    assert fast(mode="pdf", vec=(1, 0, 0), bin_b=1, maxdist=10.0) == 0
+    assert fast(mode="pdf", bin_b=1, maxdist=10.0, use_coc=True) == 0
+    assert fast(mode="cdf", bin_b=1, maxdist=10.0) == 0
+
+
+def test_distribution_input_parser():
+    text = "podf 2\n+0 +0 +1 2 1\n 1, 1, 0, 1 -1 ### comment\nmaxdist 12.5\nbin_count 50\nbin_count_b 2000\nweigh_charge T\nunknown line\nquit\nbin_count_a 7\n"
+    reqs = inputs.parse_distribution_input(text, ntypes=2)
+    assert len(reqs) == 2
+    assert reqs[0].mode == capi.PA_MODE_PDF and reqs[1].obs_type == -1 and list(reqs[1].ref_xyz) == [1, 1, 0]
+    assert reqs[0].bin_a == 50 and reqs[0].bin_b == 1000 and reqs[0].weigh_charge == 1 and reqs[0].sampling_interval == 10
+    assert reqs[0].maxdist == 12.5 and reqs[0].maxdist_optimize == 0
+    with pytest.raises(ValueError):
+        inputs.parse_distribution_input("pdf 1\n0 0 1 3 1\n", ntypes=2)
