@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pair-distribution hot path.
+
+Metric (BASELINE.json): binned atom-pairs/s on the synthetic 1M-atom cubic box (SURVEY 8d "C4"):
+two one-atom types of 500 000 (Na, Cl), L = 271.4418 A (density 0.05 A^-3), xyz semantics,
+references `+0 +0 +1 1 -1` and `+0 +0 +1 2 -1`, maxdist_optimize (cutoff L/2), 1000x1 bins.
+One step = one frame per GPU = 1e12 ordered pair evaluations, ~5.2e11 of them binned.
+Frames are sharded over the GPUs (weak scaling: one frame per GPU per step); the int64 bin
+counts are combined once with an NCCL reduce at the end of the timed region.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun)
+    python bench.py --impl reference ...                    (reference's own CPU build, bounded sample)
+
+One JSON line on stdout (rank 0).  `value` is device-resident throughput, `e2e` goes through the
+C ABI with host buffers (pinned staging + H2D + kernels + D2H inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_BOX = "271.4418"
+N_PER_TYPE = 500_000
+BINS = 1000
+FP64_OPS_PER_PAIR = 26          # separable exact minimum image, non-FMA instruction issues
+METRIC = "binned atom-pairs/s, 1M-atom RDF, 1/2/4/8 B200 vs OpenMP host cores"
+
+
+def synth_frame(frame_index: int, natoms: int, L: float, seed: int = 12345) -> np.ndarray:
+    """Counter-based generator keyed (seed, frame): u*L rounded to 5 decimals, then float32, so a text
+    trajectory written with %.5f and a direct binary feed give identical bits."""
+    g = np.random.Generator(np.random.Philox(key=[seed, frame_index]))
+    return np.round(g.random((natoms, 3)) * L, 5).astype(np.float32)
+
+
+def make_traj(frames: np.ndarray, n_per_type: int, L: float):
+    from prealpha_b200 import capi
+    nsteps = frames.shape[0]
+    lo, hi = capi.cubic_box_edge(0.0, L)
+    types = [dict(charge=+1, natoms=1, nmol=n_per_type, elements=["Na"], xyz=frames[:, :n_per_type].reshape(nsteps, n_per_type, 1, 3)),
+             dict(charge=-1, natoms=1, nmol=n_per_type, elements=["Cl"], xyz=frames[:, n_per_type:].reshape(nsteps, n_per_type, 1, 3))]
+    return capi.Trajectory(types, lo, hi, xyz_format=True)
+
+
+def make_jobs(traj):
+    from prealpha_b200 import api, capi
+    return [api.job_setup(traj, capi.make_request(mode="pdf", vec=(0, 0, 1), ref_type=t, obs_type=-1, bin_a=BINS, bin_b=1,
+                                                  maxdist_optimize=True, sampling_interval=1)) for t in (1, 2)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        # samples under load only (upper half of the power readings)
+        if sm:
+            thr = np.median(power) if len(power) > 2 else 0
+            load = [c for c, p in zip(sm, power) if p >= thr] or sm
+            return {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                    "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+
+# ----------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's OWN shipped binary on a bounded sample of the same
+# generator (brute force: cost per pair is size independent), all host threads.
+
+def cpu_reference_run(n_atoms_half: int, nframes: int, threads: int, workdir: str | None = None):
+    """Returns dict(binned_per_s, pair_evals_per_s, seconds, kind, within)."""
+    from oracle import oracle_lib as orc
+    # same density as the 1M-atom box: scale the edge so that N/L^3 = 0.05
+    n = 2 * n_atoms_half
+    edge = round((n / 0.05) ** (1.0 / 3.0), 4)
+    frames = np.stack([np.round(np.random.Generator(np.random.Philox(key=[12345, 10_000 + f])).random((n, 3)) * edge, 5)
+                       for f in range(nframes)])
+    pair_evals = nframes * 2 * (n_atoms_half * (n - 1))
+    if orc.ref_probe():
+        wd = workdir or tempfile.mkdtemp(prefix="pa_ref_")
+        try:
+            orc.write_xyz(os.path.join(wd, "traj.xyz"), ["Na"] * n_atoms_half + ["Cl"] * n_atoms_half, frames)
+            text = f"pdf 2\n+0 +0 +1 1 -1\n+0 +0 +1 2 -1\nmaxdist_optimize\nsampling_interval 1\nbin_count_a {BINS}\nbin_count_b 1\nquit\n"
+            orc.write_case(wd, "traj.xyz", [(+1, 1, n_atoms_half), (-1, 1, n_atoms_half)], nframes, ("0.0", f"{edge}"),
+                           {"rdf.inp": text}, threads=threads)
+            out, wall = orc.run_reference(wd)
+            took = orc.parse_took_seconds(out)
+            within = sum(w for w, _ in orc.parse_within(out))
+            # the binary prints its own time with one decimal; prefer wall clock of the analysis when too coarse
+            sec = sum(took) if took and sum(took) >= 2.0 else wall
+            return dict(binned_per_s=within / sec, pair_evals_per_s=pair_evals / sec, seconds=sec, kind="reference",
+                        within=within, threads=threads, atoms=n, frames=nframes)
+        finally:
+            if workdir is None:
+                shutil.rmtree(wd, ignore_errors=True)
+    # the shipped binary does not start on this box: time the C restatement instead (labelled "port")
+    from prealpha_b200 import capi
+    lo, hi = capi.cubic_box_edge(0.0, edge)
+    fr32 = frames.astype(np.float32)
+    types = [dict(charge=+1, natoms=1, nmol=n_atoms_half, elements=["Na"], xyz=fr32[:, :n_atoms_half].reshape(nframes, n_atoms_half, 1, 3)),
+             dict(charge=-1, natoms=1, nmol=n_atoms_half, elements=["Cl"], xyz=fr32[:, n_atoms_half:].reshape(nframes, n_atoms_half, 1, 3))]
+    traj = capi.Trajectory(types, lo, hi)
+    t0 = time.time()
+    within = 0
+    for t in (1, 2):
+        job = orc.job_setup(traj, capi.make_request(mode="pdf", ref_type=t, obs_type=-1, bin_a=BINS, bin_b=1, maxdist_optimize=True,
+                                                    sampling_interval=1))
+        _, w, _ = orc.histogram(traj, job, nthreads=threads)
+        within += w
+    sec = time.time() - t0
+    return dict(binned_per_s=within / sec, pair_evals_per_s=pair_evals / sec, seconds=sec, kind="port", within=within,
+                threads=threads, atoms=n, frames=nframes)
+
+
+def cpu_sample_size(threads: int, target_seconds: float):
+    """frames = 2 x threads (balanced STATIC,1 schedule, >= 11 needed by the module); atoms so that the run
+    takes about target_seconds at ~2e6 pair-evals/s/thread of the -O0 reference build."""
+    frames = max(12, 2 * threads)
+    rounds = -(-frames // threads)
+    pairs_per_frame = target_seconds * 2.0e6 / rounds
+    n_half = int(round((pairs_per_frame / 4.0) ** 0.5))      # 2 refs x n_half x 2 n_half pairs
+    return max(500, min(10000, n_half)), frames
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    n_half, frames = cpu_sample_size(threads, 6.0)
+    for _ in range(args.warmup):
+        cpu_reference_run(max(500, n_half // 2), frames, threads)
+    res = []
+    t0 = time.time()
+    for _ in range(args.steps):
+        res.append(cpu_reference_run(n_half, frames, threads))
+    wall = time.time() - t0
+    sec = sum(r["seconds"] for r in res)
+    value = sum(r["within"] for r in res) / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "binned pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic cubic box (same generator and density as the 1M-atom case), {2 * n_half} atoms x {frames} frames, "
+                               "references 1 -1 and 2 -1, maxdist_optimize, 1000x1 bins; brute force, cost per pair independent of N"},
+        "pair_evals_per_s": sum(r["pair_evals_per_s"] * r["seconds"] for r in res) / sec,
+        "cpu_baseline": {"value": value, "unit": "binned pairs/s", "cores": threads, "kind": res[0]["kind"],
+                         "sample": f"{2 * n_half} atoms x {frames} frames per step, {args.steps} steps, "
+                                   + ("shipped prealpha binary (gfortran -fopenmp, -O0), set_threads = all host cores" if res[0]["kind"] == "reference"
+                                      else "C restatement oracle/pa_oracle.c (-O2, OpenMP), the shipped binary did not start here")},
+        "e2e": {"value": value, "unit": "binned pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--atoms-per-type", type=int, default=N_PER_TYPE, help="debug: smaller box (not a valid bench line)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--flags", type=int, default=0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from prealpha_b200 import api, capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, (world, args.gpus)
+    if not torch.cuda.is_available() or api.device_count() < 1:
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W, K = max(args.warmup, 3), args.steps
+    n_half = args.atoms_per_type
+    natoms = 2 * n_half
+    L = float(L_BOX) if n_half == N_PER_TYPE else round((natoms / 0.05) ** (1.0 / 3.0), 4)
+    # frames: step s of rank r is global frame s*world + r (frames sharded round-robin over the GPUs)
+    frames = np.stack([synth_frame(s * world + rank, natoms, L) for s in range(W + K)])
+    traj = make_traj(frames, n_half, L)
+    jobs = make_jobs(traj)
+    ex = api.make_exec(device=local, flags=args.flags)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm (`value`): all W+K frames uploaded before the timed region -------------
+    sess = api.Session(traj, jobs, max_frames=W + K, exec_=ex)
+    sess.upload(traj, 0, W + K)
+    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")    # > 126 MB L2
+    for s in range(W):
+        sess.run(s, 1)
+    sess.download(reset=True)
+    st0 = sess.stats()
+    fp64_rate = api.fp64_issue_rate(local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(K):
+        flush.zero_()                      # L2 flush between timed iterations (torch stream)
+        torch.cuda.synchronize()
+        sess.run(W + s, 1)                 # prepare + pair kernels on the session's compute stream
+    ptr, nwords = sess.device_accumulators()   # synchronises the compute stream
+    if world > 1:
+        class _Acc:   # zero-copy view of the session's int64 accumulators for NCCL
+            __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+        acc = torch.as_tensor(_Acc(), device=f"cuda:{local}")
+        dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)      # integer bin counts combined once over NVLink
+    barrier()
+    t_value = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+    hists, within, oob = sess.download()
+    st1 = sess.stats()
+    kernel_ms = st1.kernel_ms - st0.kernel_ms
+    launches = st1.kernel_launches - st0.kernel_launches
+    pair_evals_rank = st1.pairs_evaluated - st0.pairs_evaluated
+    sess.close()
+    # local (pre-reduce) binned count of this rank: rank 0 holds the reduced sum when world > 1
+    tv = torch.tensor([t_value, kernel_ms], dtype=torch.float64, device="cuda")
+    pe = torch.tensor([float(pair_evals_rank)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pe, op=dist.ReduceOp.SUM)
+    t_value_max, kernel_ms_max = float(tv[0]), float(tv[1])
+    binned_total = int(within.sum())           # rank 0: whole job (after the reduce)
+    pair_evals_total = float(pe[0])
+
+    # ---- end-to-end arm: host buffers through the C ABI, H2D/D2H inside the timed region --------------
+    e2e_traj = make_traj(frames[W:], n_half, L)
+    e2e_jobs = make_jobs(e2e_traj)
+    api.histogram_multi(make_traj(frames[:1], n_half, L), e2e_jobs, api.make_exec(device=local, frames_per_batch=1, flags=args.flags))  # warm
+    barrier()
+    t0 = time.perf_counter()
+    h2, w2, o2, st_e = api.histogram_multi(e2e_traj, e2e_jobs, api.make_exec(device=local, frames_per_batch=1, flags=args.flags))
+    if world > 1:
+        acc2 = torch.from_numpy(np.concatenate([np.concatenate([h2[k], w2[k:k + 1], o2[k:k + 1]]) for k in range(len(e2e_jobs))])).cuda()
+        dist.reduce(acc2, dst=0, op=dist.ReduceOp.SUM)
+        w2_total = int(acc2.cpu().numpy().reshape(len(e2e_jobs), -1)[:, BINS].sum())
+    else:
+        w2_total = int(w2.sum())
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    t_e2e_max = float(te[0])
+
+    if rank == 0:
+        # identical inputs in both arms -> identical integers
+        assert w2_total == binned_total, (w2_total, binned_total)
+        value = binned_total / t_value_max
+        pe_per_s = pair_evals_total / t_value_max
+        # dominant kernel: pa_rdf_fast_kernel (2 launches per step: observed type 1 and 2 per job -> 4)
+        pair_evals_per_s_kernel = pair_evals_rank / (kernel_ms * 1e-3)
+        achieved = pair_evals_per_s_kernel * FP64_OPS_PER_PAIR
+        line = {
+            "metric": METRIC, "value": value, "unit": "binned pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_value_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic cubic box, {natoms} atoms (2 one-atom types), L={L} A, 1 frame per GPU per step, "
+                                   f"references 1 -1 and 2 -1 (all ordered pairs), maxdist_optimize, {BINS}x1 bins",
+                       "pair_evals_per_step_per_gpu": pair_evals_rank / K, "frames_sharding": "frame s*N+r on GPU r, NCCL int64 reduce once",
+                       "l2": "512 MB flush between timed steps; every step works on a different resident frame"},
+            "pair_evals_per_s": pe_per_s,
+            "e2e": {"value": binned_total / t_e2e_max, "unit": "binned pairs/s", "h2d_bytes_per_step": int(st_e.h2d_bytes // K),
+                    "d2h_bytes_per_step": int(st_e.d2h_bytes // K), "ms_per_step": 1e3 * t_e2e_max / K},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved / 1e9, "peak": fp64_rate / 1e9, "unit": "Ginst/s",
+                         "frac": achieved / fp64_rate, "traffic": None,
+                         "note": "algorithmic 26 FP64-pipe instructions per evaluated pair (SURVEY 8d) x pair evaluations / CUDA-event "
+                                 "time of the pair kernels on their stream; peak = DSUB/DMUL issue rate measured live on this GPU "
+                                 "(MEASURED_PEAKS.json has no FP64 entry). HBM is not the bound: 12 B per atom per frame.",
+                         "kernel_ms_per_step": kernel_ms / K,
+                         "hbm_gbs_frame_streaming": (natoms * 12 * K) / (kernel_ms * 1e-3) / 1e9},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            threads = os.cpu_count() or 1
+            nh, fr = cpu_sample_size(threads, 15.0)
+            cb = cpu_reference_run(nh, fr, threads)
+            line["cpu_baseline"] = {"value": cb["binned_per_s"], "unit": "binned pairs/s", "cores": threads, "kind": cb["kind"],
+                                    "pair_evals_per_s": cb["pair_evals_per_s"], "seconds": cb["seconds"],
+                                    "sample": f"{cb['atoms']} atoms x {cb['frames']} frames of the same generator/density, both references "
+                                              "(brute force: per-pair cost independent of N)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -193,7 +193,8 @@ int  pa_session_create(const pa_traj *traj_meta, const pa_job *jobs, int32_t njo
                        const pa_exec *exec, int32_t max_frames, pa_session **out);
 int  pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, int32_t nframes,
                        int32_t step_stride);
-int  pa_session_run(pa_session *s);
+int  pa_session_run(pa_session *s);                                  /* all resident frames   */
+int  pa_session_run_frames(pa_session *s, int32_t first, int32_t count); /* a resident sub-range   */
 int  pa_session_download(pa_session *s, int64_t *const *hists, int64_t *within_bin,
                          int64_t *out_of_bounds, int32_t reset);
 int  pa_session_stats(pa_session *s, pa_stats *stats);

@@ -23,6 +23,16 @@ def job_setup(traj: capi.Trajectory, req: capi.pa_job_request) -> capi.pa_job:
     return job
 
 
+def fp64_issue_rate(device=0) -> float:
+    """Measured FP64-pipe instruction issue rate (DSUB/DMUL chains, no FMA credit) of this GPU."""
+    lib = capi.load()
+    lib.pa_debug_fp64_issue_rate.restype = C.c_int
+    lib.pa_debug_fp64_issue_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    v = C.c_double(0)
+    capi.check(lib.pa_debug_fp64_issue_rate(device, C.byref(v)), "pa_debug_fp64_issue_rate")
+    return v.value
+
+
 def make_exec(device=0, shard_rank=0, shard_count=1, frames_per_batch=0, flags=0) -> capi.pa_exec:
     ex = capi.pa_exec()
     ex.device, ex.shard_rank, ex.shard_count, ex.frames_per_batch, ex.flags = device, shard_rank, shard_count, frames_per_batch, flags
@@ -99,8 +109,11 @@ class Session:
     def upload(self, traj, first_step, nframes, stride=1):
         capi.check(self.lib.pa_session_upload(self.h, traj.ptr, first_step, nframes, stride), "pa_session_upload")
 
-    def run(self):
-        capi.check(self.lib.pa_session_run(self.h), "pa_session_run")
+    def run(self, first=None, count=None):
+        if first is None:
+            capi.check(self.lib.pa_session_run(self.h), "pa_session_run")
+        else:
+            capi.check(self.lib.pa_session_run_frames(self.h, first, 1 if count is None else count), "pa_session_run_frames")
 
     def download(self, reset=False):
         n = len(self.jobs)

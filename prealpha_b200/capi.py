@@ -120,6 +120,7 @@ SIGNATURES = {
                                     C.c_int32, C.POINTER(C.c_void_p)]),
     "pa_session_upload": (C.c_int, [C.c_void_p, C.POINTER(pa_traj), C.c_int32, C.c_int32, C.c_int32]),
     "pa_session_run": (C.c_int, [C.c_void_p]),
+    "pa_session_run_frames": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "pa_session_download": (C.c_int, [C.c_void_p, C.POINTER(_I64P), _I64P, _I64P, C.c_int32]),
     "pa_session_stats": (C.c_int, [C.c_void_p, C.POINTER(pa_stats)]),
     "pa_session_device_accumulators": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), _I64P]),

@@ -25,7 +25,7 @@ std::vector<std::string> tokens_of(const std::string &line)
     std::vector<std::string> out;
     size_t i = 0, n = line.size();
     while (i < n) {
-        while (i < n && (line[i] == ' ' || line[i] == '\t' || line[i] == ',' || line[i] == '\r')) ++i;
+        while (i < n && (line[i] == ' ' || line[i] == '\t' || line[i] == ',' || line[i] == '\r' || line[i] == '\n')) ++i;
         if (i >= n) break;
         if (line[i] == '/') break;
         if (line[i] == '"' || line[i] == '\'') {
@@ -38,7 +38,7 @@ std::vector<std::string> tokens_of(const std::string &line)
             out.push_back(t);
         } else {
             std::string t;
-            while (i < n && line[i] != ' ' && line[i] != '\t' && line[i] != ',' && line[i] != '/' && line[i] != '\r') t += line[i++];
+            while (i < n && line[i] != ' ' && line[i] != '\t' && line[i] != ',' && line[i] != '/' && line[i] != '\r' && line[i] != '\n') t += line[i++];
             out.push_back(t);
         }
     }

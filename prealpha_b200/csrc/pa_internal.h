@@ -70,6 +70,7 @@ struct PaPass {
     PaBox box;
     PaDevJob job;
     int32_t nframes;
+    int32_t frame0;             // first resident frame this launch works on
     int32_t ref_off, nref;      // slot range of the reference type inside a frame
     int32_t obs_off, nobs;
     int32_t same_type;
@@ -87,6 +88,7 @@ struct PaPrepareArgs {
     const PaDevType *types;     // device array
     int32_t ntypes;
     int32_t nframes;
+    int32_t frame0;
     PaPoints pts;
     PaBox box;
     int32_t need_coc;

@@ -49,8 +49,8 @@ __global__ void __launch_bounds__(256) pa_prepare_kernel(PaPrepareArgs a)
     const long long total = (long long)a.nframes * a.pts.M;
     for (long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x; gid < total;
          gid += (long long)gridDim.x * blockDim.x) {
-        const int frame = (int)(gid / a.pts.M);
-        const int slot = (int)(gid - (long long)frame * a.pts.M);
+        const int frame = a.frame0 + (int)(gid / a.pts.M);
+        const int slot = (int)(gid % a.pts.M);
         int t = 0;
         while (t + 1 < a.ntypes && slot >= a.types[t + 1].offset) ++t;
         const PaDevType ty = a.types[t];
@@ -92,10 +92,11 @@ __global__ void __launch_bounds__(256) pa_prepare_kernel(PaPrepareArgs a)
                 }
             }
         }
-        a.pts.px[gid] = p[0]; a.pts.py[gid] = p[1]; a.pts.pz[gid] = p[2];
-        a.pts.wx[gid] = w[0]; a.pts.wy[gid] = w[1]; a.pts.wz[gid] = w[2];
-        a.pts.cx[gid] = c[0]; a.pts.cy[gid] = c[1]; a.pts.cz[gid] = c[2];
-        if (a.need_coc && a.pts.qx) { a.pts.qx[gid] = q[0]; a.pts.qy[gid] = q[1]; a.pts.qz[gid] = q[2]; }
+        const long long o = (long long)frame * a.pts.M + slot;
+        a.pts.px[o] = p[0]; a.pts.py[o] = p[1]; a.pts.pz[o] = p[2];
+        a.pts.wx[o] = w[0]; a.pts.wy[o] = w[1]; a.pts.wz[o] = w[2];
+        a.pts.cx[o] = c[0]; a.pts.cy[o] = c[1]; a.pts.cz[o] = c[2];
+        if (a.need_coc && a.pts.qx) { a.pts.qx[o] = q[0]; a.pts.qy[o] = q[1]; a.pts.qz[o] = q[2]; }
     }
 }
 
@@ -200,7 +201,7 @@ static __device__ __forceinline__ PaItem pa_decode_item(const PaPass &p, long lo
     const int js = (int)(item % p.n_jsplits);
     const long long r = item / p.n_jsplits;
     const int ti = (int)(r % p.n_itiles);
-    it.frame = (int)(r / p.n_itiles);
+    it.frame = p.frame0 + (int)(r / p.n_itiles);
     it.j0 = js * p.jsplit_len;
     it.j1 = min(p.nobs, it.j0 + p.jsplit_len);
     it.i0 = ti;
@@ -256,6 +257,7 @@ __global__ void __launch_bounds__(PA_THREADS) pa_rdf_fast_kernel(PaPass p)
     __syncthreads();
 
     const float scale = p.job.guess_scale;
+    const unsigned long long cut = p.job.cut_bits;
     const float cls_max = (float)(na + 1);
     const int hi_flag = 0x3E100000;                          // hi word of 2^-30: |link_xy|^2 below this -> literal path
     const long long n_items = (long long)p.nframes * p.n_itiles * p.n_jsplits;
@@ -321,11 +323,14 @@ __global__ void __launch_bounds__(PA_THREADS) pa_rdf_fast_kernel(PaPass p)
                     y = fminf(fmaxf(y, 0.0f), cls_max);
                     const int n = __float_as_int(y + 8388608.0f) - 0x4B000000;   // rint(y) in [0, na+1]
                     const unsigned long long db = dbits(d2);
+                    // inside the cutoff the class is min(floor(x), na), so it is n or n+1; beyond the
+                    // cutoff the class jumps to na+1 and the seed says nothing: test the cutoff itself.
+                    const bool inside = db < cut;
                     const int cls = n + (db >= s_thr[n + 1] ? 1 : 0);
                     if (VERIFY) {
                         // invariant of the seed: true class is n or n+1
                         const bool ok = (s_thr[n] <= db) && (n + 2 > na + 2 || db < s_thr[n + 2]);
-                        if (!ok && __double2hiint(s1) >= hi_flag && d2 < 1.0e29) atomicAdd(p.verify_fail, 1u);
+                        if (inside && !ok && __double2hiint(s1) >= hi_flag) atomicAdd(p.verify_fail, 1u);
                     }
                     if (__double2hiint(s1) < hi_flag) {
                         // |link_xy| < 3e-5 A: (anti)parallel to the reference axis, coincident or the
@@ -337,7 +342,7 @@ __global__ void __launch_bounds__(PA_THREADS) pa_rdf_fast_kernel(PaPass p)
                             if (slot < p.exc_cap)
                                 p.exc_list[slot] = make_uint2((unsigned int)(fbase + p.ref_off + i), (unsigned int)(fbase + p.obs_off + j));
                         }
-                    } else if (cls <= na) {
+                    } else if (inside) {
                         atomicAdd(&s_hist[2 * cls], 1u);
                     }
                 }
@@ -564,6 +569,50 @@ int pa_launch_exceptions(const PaPass &p, unsigned int /*count_hint*/, void *str
     pa_exception_kernel<<<148, 128, 0, (cudaStream_t)stream>>>(p);
     pa_exception_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p.exc_count, p.exc_cap);
     return (int)cudaGetLastError();
+}
+
+// FP64-pipe issue rate without FMA credit (independent DSUB/DMUL chains, the pair kernel's mix):
+// the denominator of this path's roofline, measured on the device it runs on.
+__global__ void __launch_bounds__(256) pa_fp64_rate_kernel(double *out, double a, double b, int iters)
+{
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = a + threadIdx.x * 1e-9 + i;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { x[i] = __dsub_rn(x[i], b); x[i] = __dmul_rn(x[i], a); }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += x[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+extern "C" int pa_debug_fp64_issue_rate(int device, double *inst_per_s)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return PA_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PA_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * blocks * threads) != cudaSuccess) return PA_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0);
+        pa_fp64_rate_kernel<<<blocks, threads>>>(d, 1.0000001, 1e-7, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms < best) best = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (err != cudaSuccess) return PA_ERR_CUDA;
+    *inst_per_s = (double)blocks * threads * iters * 16.0 / (best * 1e-3);
+    return 0;
 }
 
 int pa_kernels_selfcheck()

@@ -300,7 +300,15 @@ int pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, in
 
 int pa_session_run(pa_session *s)
 {
-    if (!s || s->nframes < 1) { pa::set_error("pa_session_run: nothing resident"); return PA_ERR_BAD_ARG; }
+    if (!s) return PA_ERR_BAD_ARG;
+    return pa_session_run_frames(s, 0, s->nframes);
+}
+
+int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
+{
+    if (!s || s->nframes < 1 || first < 0 || count < 1 || first + count > s->nframes) {
+        pa::set_error("pa_session_run: frame range not resident"); return PA_ERR_BAD_ARG;
+    }
     PA_CK(cudaSetDevice(s->device));
     const int slot = s->cur;
     PA_CK(cudaStreamWaitEvent(s->s_compute, s->ev_h2d[slot], 0));
@@ -308,7 +316,7 @@ int pa_session_run(pa_session *s)
     PA_CK(cudaEventCreate(&e0)); PA_CK(cudaEventCreate(&e1));
     PA_CK(cudaEventRecord(e0, s->s_compute));
     PaPrepareArgs pa{};
-    pa.types = s->d_types[slot]; pa.ntypes = (int)s->types.size(); pa.nframes = s->nframes;
+    pa.types = s->d_types[slot]; pa.ntypes = (int)s->types.size(); pa.nframes = count; pa.frame0 = first;
     pa.pts = s->pts; pa.box = s->box; pa.need_coc = s->need_coc ? 1 : 0;
     PA_CK((cudaError_t)pa_launch_prepare(pa, s->s_compute));
     s->stats.kernel_launches += 1;
@@ -321,7 +329,7 @@ int pa_session_run(pa_session *s)
         for (int o = o_first; o <= o_last; ++o) {                 // Distribution:727-735
             PaPass p{};
             p.pts = s->pts; p.box = s->box; p.job = js.dj;
-            p.nframes = s->nframes;
+            p.nframes = count; p.frame0 = first;
             p.ref_off = s->types[r].offset; p.nref = s->types[r].nmol;
             p.obs_off = s->types[o].offset; p.nobs = s->types[o].nmol;
             p.same_type = (r == o) ? 1 : 0;
@@ -353,7 +361,7 @@ int pa_session_run(pa_session *s)
     PA_CK(cudaEventRecord(e1, s->s_compute));
     PA_CK(cudaEventRecord(s->ev_done[slot], s->s_compute));
     s->kernel_events.emplace_back(e0, e1);
-    s->stats.frames_done += s->nframes;
+    s->stats.frames_done += count;
     return 0;
 }
 
