@@ -1,0 +1,562 @@
+// pa_cells.cu -- cell-sorted RDF kernel (the fast path for large systems).
+//
+// The brute-force tile kernel (pa_rdf_fast_kernel) must take the minimum over three periodic
+// images per component for every pair because it knows nothing about where the two molecules
+// are.  Here every frame is first sorted into a uniform grid (counting sort, hand-written:
+// count -> scan -> scatter; the grid is finer along x so that runs of x-cells give tiles of
+// almost exactly 256 molecules).  A tile of reference molecules (<= 256, held in registers) is
+// then paired with runs of observed cells, and for each (tile, cell-run) the image shift per
+// component is decided ONCE from the exact bounding boxes:
+//   * "single": one shift s in {-L,0,+L} is strictly closest for every pair of the two boxes
+//     (by a margin far above rounding) -> the pair costs 1 DSUB + 1 DMUL for that component;
+//   * "double": two shifts are possible (boxes straddle L/2) -> 2 DSUB, min of |d|, 1 DMUL;
+//   * cell runs whose closest possible distance is beyond the cutoff are skipped.
+// Nothing about the arithmetic changes: a pair evaluates exactly the candidates
+// fl(fl(p2+s)-p1) that can be the minimum of the reference's 27-image loop (Molecular:1451-1467),
+// so the fp64 result is bit-identical; skipped pairs are pairs the reference evaluates and then
+// discards at `IF (current_distance_squared<maxdist_squared)` (Distribution:783).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "pa_internal.h"
+
+#define PC_THREADS 128
+#define PC_RI 2
+#define PC_TILE (PC_THREADS * PC_RI)
+#define PC_JC 128
+#define PC_MAXG 256
+
+static __device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
+// order-preserving map double -> uint64 (for atomicMin/atomicMax on coordinates)
+static __device__ __forceinline__ unsigned long long okey(double x)
+{
+    const unsigned long long b = dbits(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+static __device__ __forceinline__ double okey_inv(unsigned long long k)
+{
+    return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k));
+}
+
+// ---------------------------------------------------------------------------
+// K1: cell index per molecule, cell population, per-layer exact bounding boxes
+__global__ void __launch_bounds__(256) pa_cell_count_kernel(PaCellGrid g, PaPoints pts, PaBox box, int frame0, int nframes, unsigned int *err)
+{
+    const long long total = (long long)nframes * g.nmol;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(id / g.nmol), m = (int)(id % g.nmol);
+        const long long slot = (long long)(frame0 + f) * pts.M + g.type_off + m;
+        const double p[3] = { pts.px[slot], pts.py[slot], pts.pz[slot] };
+        int c[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            if (!(p[k] >= box.lo[k] && p[k] <= box.hi[k])) { atomicOr(err, 1u); c[k] = 0; continue; }   // NaN / not wrapped
+            int ck = (int)((p[k] - box.lo[k]) * g.inv_w[k]);
+            c[k] = min(g.g[k] - 1, max(0, ck));
+            const long long lay = ((long long)f * 3 + k) * g.gmax + c[k];
+            atomicMin(&g.lay_lo[lay], okey(p[k]));
+            atomicMax(&g.lay_hi[lay], okey(p[k]));
+        }
+        const int cell = (c[2] * g.g[1] + c[1]) * g.g[0] + c[0];
+        g.cid[(long long)f * g.nmol + m] = cell;
+        atomicAdd(&g.cell_start[(long long)f * (g.ncell + 1) + cell + 1], 1);
+    }
+}
+
+// K2: in-place inclusive scan of the populations (cell_start[f][c+1] held counts) -> offsets
+__global__ void __launch_bounds__(1024) pa_cell_scan_kernel(PaCellGrid g)
+{
+    __shared__ int s_part[1024];
+    int *cs = g.cell_start + (long long)blockIdx.x * (g.ncell + 1);
+    const int n = g.ncell, per = (n + 1023) / 1024;
+    const int b = min(n, (int)threadIdx.x * per), e = min(n, b + per);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += cs[i + 1];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = threadIdx.x ? s_part[threadIdx.x - 1] : 0;
+    for (int i = b; i < e; ++i) { run += cs[i + 1]; cs[i + 1] = run; }
+    if (threadIdx.x == 0) cs[0] = 0;
+}
+
+// K3: scatter into cell order (order inside a cell is arbitrary: results are integer sums)
+__global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, PaPoints pts, int frame0, int nframes)
+{
+    const long long total = (long long)nframes * g.nmol;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(id / g.nmol), m = (int)(id % g.nmol);
+        const long long slot = (long long)(frame0 + f) * pts.M + g.type_off + m;
+        const int cell = g.cid[id];
+        const int pos = g.cell_start[(long long)f * (g.ncell + 1) + cell] + atomicAdd(&g.cell_fill[(long long)f * g.ncell + cell], 1);
+        const long long o = (long long)f * g.nmol + pos;
+        g.sx[o] = pts.px[slot]; g.sy[o] = pts.py[slot]; g.sz[o] = pts.pz[slot];
+        g.sorig[o] = m;
+    }
+}
+
+// K4: reference tiles = greedy runs of x-neighbouring cells of one (y,z) row, <= PC_TILE molecules
+// and at most max_run cells wide (so that tile width + cell width stays below L/2).
+__global__ void __launch_bounds__(128) pa_build_tiles_kernel(PaCellGrid g, int nframes, int max_run, PaTile *tiles, unsigned int *ntiles, unsigned int cap)
+{
+    const int rows = g.g[1] * g.g[2], gx = g.g[0];
+    const int id = blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= nframes * rows) return;
+    const int f = id / rows, row = id % rows;
+    const int *cs = g.cell_start + (long long)f * (g.ncell + 1) + (long long)row * gx;
+    int cx = 0;
+    while (cx < gx) {
+        int beg = cs[cx], c1 = cx, cnt = cs[cx + 1] - beg;
+        while (c1 + 1 < gx && (c1 + 1 - cx) < max_run && (cs[c1 + 2] - beg) <= PC_TILE) { ++c1; cnt = cs[c1 + 1] - beg; }
+        // a single over-full cell is split into several tiles
+        for (int off = 0; off < cnt; off += PC_TILE) {
+            const unsigned int t = atomicAdd(ntiles, 1u);
+            if (t < cap) {
+                PaTile tl;
+                tl.frame = f; tl.begin = beg + off; tl.count = min(PC_TILE, cnt - off);
+                tl.cx0 = cx; tl.cx1 = c1; tl.cy = row % g.g[1]; tl.cz = row / g.g[1]; tl.pad = 0;
+                tiles[t] = tl;
+            }
+        }
+        cx = c1 + 1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// per (tile, observed layer, component) image classification
+struct PcLayer { float dmin2; signed char mode, ca, cb, pad; };    // ca/cb: shift code 0,1,2 = -L,0,+L
+
+static __device__ PcLayer pc_classify(double ilo, double ihi, double jlo, double jhi, double L)
+{
+    PcLayer r;
+    const double a = jlo - ihi, b = jhi - ilo;          // p2 - p1 lies in [a, b]
+    const double margin = 1e-9 * L + 1e-12;             // >> rounding of (p2+s)-p1, << any physical scale
+    double mn[3], mx[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double s = (double)(k - 1) * L;
+        const double lo = a + s, hi = b + s;
+        mn[k] = lo > 0.0 ? lo : (hi < 0.0 ? -hi : 0.0);
+        mx[k] = fmax(fabs(lo), fabs(hi));
+    }
+    int best = 0;
+    if (mx[1] < mx[best]) best = 1;
+    if (mx[2] < (best == 0 ? mx[0] : mx[1])) best = 2;
+    const double lim = (best == 0 ? mx[0] : (best == 1 ? mx[1] : mx[2])) + margin;
+    int n = 0, c0 = best, c1 = best;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        if (mn[k] <= lim) { if (n == 0) c0 = k; else c1 = k; ++n; }
+    r.mode = (signed char)n;                             // 1, 2 or 3 (3 = boxes too wide: caller raises the error flag)
+    r.ca = (signed char)c0; r.cb = (signed char)(n >= 2 ? c1 : c0); r.pad = 0;
+    const double d = fmax(0.0, fmin(mn[0], fmin(mn[1], mn[2])) - margin);
+    r.dmin2 = (float)fmin(d * d * (1.0 - 1e-6), 3.0e38);  // rounded down: still a lower bound
+    return r;
+}
+
+template <int MODE>
+static __device__ __forceinline__ double pc_comp_sq(double ja, double jb, double p1)
+{
+    if (MODE == 1) {
+        const double d = __dsub_rn(ja, p1);
+        return __dmul_rn(d, d);
+    } else {
+        // min over the two candidate images of fl(d^2) = fl((the d of smaller magnitude)^2); the
+        // select works on the signed values so that |.| stays an operand modifier of DSETP
+        const double da = __dsub_rn(ja, p1);
+        const double db = __dsub_rn(jb, p1);
+        const double m = fabs(db) < fabs(da) ? db : da;
+        return __dmul_rn(m, m);
+    }
+}
+
+struct PcShared {
+    PcLayer lay[3][PC_MAXG];
+    int work_item;
+};
+
+// Shared-memory class tables: thresholds thr[k] (8-byte stride, k = 0..na+2) and counters cnt[k]
+// (4-byte stride, so that the 32 lanes of an ATOMS spread over all 32 banks).
+static __device__ __forceinline__ double pc_lds_f64(unsigned int addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+static __device__ __forceinline__ unsigned int pc_lds_u32(unsigned int addr)
+{
+    unsigned int v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+static __device__ __forceinline__ void pc_sts_u32(unsigned int addr, unsigned int v)
+{
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+// shared-memory increment (ATOMS.POPC.INC: equal addresses inside the warp are aggregated by the hardware)
+static __device__ __forceinline__ void pc_red(unsigned int addr)
+{
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+struct PcTables {
+    unsigned int thr;       // shared address of thr[0]
+    unsigned int cnt;       // shared address of cnt[0]
+    float s_lo, s_hi;       // (1/step_a)(1 -+ eps): x~ brackets the reference's float32 quotient
+    float r_max;            // clamp of the approximate distance: keeps the class index <= na+1
+    int na;
+    unsigned long long cut;
+};
+
+// VARIANT 0: the class of a pair is floor(sqrt(d2)/step_a) evaluated approximately (top 52 bits of d2,
+//            MUFU.SQRT, two round-down FMAs with the scale shrunk / stretched by eps = 6e-7).  When both
+//            brackets give the same integer the reference's exact float32 chain cannot give another one
+//            (its relative distance to x~ is < 4e-7), so no table is touched.  Otherwise (~1e-3 of the
+//            pairs) the pair takes the rare branch and is decided by the exact fp64 threshold.  Pairs
+//            beyond the cutoff land in counters >= na, which are ignored (valid when the class "inside
+//            the cutoff, a-bin out of range" is empty and the cutoff sits on the boundary of bin na).
+// VARIANT 1: every pair is decided by the exact threshold table and an explicit cutoff test.
+template <int MX, int MY, int MZ, int VARIANT, bool VERIFY>
+static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                                  const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
+                                                  long long jbase, int jb, int je,
+                                                  double sxa, double sxb, double sya, double syb, double sza, double szb,
+                                                  double *s_j, const PcTables &T)
+{
+    const int hi_flag = 0x3E100000;                     // hi word of 2^-30
+    const int na = T.na;
+    const unsigned int cnt_m = T.cnt - 0x4B000000u * 4u;     // counter base minus the float "magic" offset
+    const unsigned int thr_m = T.thr - 0x4B000000u * 8u;
+    const unsigned int trash = T.cnt + (unsigned)(na + 2) * 4u;   // counter nobody reads
+    constexpr int NP = 2 * PC_RI;
+    constexpr int ND = MX + MY + MZ;                    // doubles per staged observed molecule
+    for (int jc = jb; jc < je; jc += PC_JC) {
+        __syncthreads();
+        {
+            const int t = threadIdx.x;                  // PC_JC == PC_THREADS
+            const int j = jc + t;
+            double x = 1.0e15, y = 1.0e15, z = 1.0e15;  // padding: far away, finite in float range
+            if (j < je) { x = go.sx[jbase + j]; y = go.sy[jbase + j]; z = go.sz[jbase + j]; }
+            double *rec = s_j + t * ND;
+            int o = 0;
+            rec[o++] = __dadd_rn(x, sxa); if (MX == 2) rec[o++] = __dadd_rn(x, sxb);
+            rec[o++] = __dadd_rn(y, sya); if (MY == 2) rec[o++] = __dadd_rn(y, syb);
+            rec[o++] = __dadd_rn(z, sza); if (MZ == 2) rec[o++] = __dadd_rn(z, szb);
+        }
+        __syncthreads();
+        const int cnt = min(PC_JC, je - jc);
+        for (int jj = 0; jj < cnt; jj += 2) {
+            // two staged molecules = 2*ND doubles, 16-byte aligned because jj is even
+            double v[2 * ND];
+            {
+                const double2 *rec = reinterpret_cast<const double2 *>(s_j + jj * ND);
+#pragma unroll
+                for (int k = 0; k < ND; ++k) { const double2 w = rec[k]; v[2 * k] = w.x; v[2 * k + 1] = w.y; }
+            }
+            double d2[NP];
+            int s1hi[NP];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const double *w = v + u * ND;
+                const double xa = w[0], xb = w[MX - 1];
+                const double ya = w[MX], yb = w[MX + MY - 1];
+                const double za = w[MX + MY], zb = w[MX + MY + MZ - 1];
+#pragma unroll
+                for (int r = 0; r < PC_RI; ++r) {
+                    const double sx = pc_comp_sq<MX>(xa, xb, p1x[r]);
+                    const double sy = pc_comp_sq<MY>(ya, yb, p1y[r]);
+                    const double sz = pc_comp_sq<MZ>(za, zb, p1z[r]);
+                    const double s1 = __dadd_rn(sx, sy);
+                    s1hi[u * PC_RI + r] = __double2hiint(s1);
+                    d2[u * PC_RI + r] = __dadd_rn(s1, sz);
+                }
+            }
+            unsigned int ca[NP];      // shared address of the counter to increment
+            unsigned int tlo[NP];     // float bits of MAGIC + floor(x~ (1-eps))
+            int slow = 0;
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                const int hi = __double2hiint(d2[q]);
+                const unsigned int lo = (unsigned)__double2loint(d2[q]);
+                // float32 with the top 24 significant bits of d2 (truncated): (hi:lo << 3) - bias
+                const float f = __uint_as_float(__funnelshift_l(lo, (unsigned)hi, 3) + 0x40000000u);
+                float rt;
+                asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(f));
+                rt = fminf(rt, T.r_max);
+                const float t0 = __fmaf_rd(rt, T.s_lo, 8388608.0f);
+                tlo[q] = (unsigned)__float_as_int(t0);
+                if (VARIANT == 0) {
+                    const float t1 = __fmaf_rd(rt, T.s_hi, 8388608.0f);
+                    ca[q] = tlo[q] * 4u + cnt_m;
+                    slow |= (s1hi[q] < hi_flag || t0 != t1) ? (1 << q) : 0;
+                } else {
+                    const double thr = pc_lds_f64(tlo[q] * 8u + thr_m + 8u);                   // thr[n+1]
+                    ca[q] = tlo[q] * 4u + cnt_m + (d2[q] >= thr ? 4u : 0u);
+                    if (!(dbits(d2[q]) < T.cut)) ca[q] = trash;
+                    slow |= (s1hi[q] < hi_flag) ? (1 << q) : 0;
+                }
+            }
+            if (slow) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (!((slow >> q) & 1)) continue;
+                    if (s1hi[q] < hi_flag) {
+                        // |link_xy|^2 < 2^-30: (anti)parallel to the reference axis, coincident, or the molecule
+                        // itself -> literal evaluation by pa_exception_kernel, not binned here
+                        ca[q] = trash;
+                        const int k = (q % PC_RI) * PC_THREADS + threadIdx.x;
+                        const int j = jc + jj + q / PC_RI;
+                        if (k < tl.count && j < je) {
+                            const int io = gi.sorig[(long long)tl.frame * gi.nmol + tl.begin + k];
+                            const int jo = go.sorig[jbase + j];
+                            if (!(p.same_type && io == jo)) {
+                                const unsigned int slot = atomicAdd(p.exc_count, 1u);
+                                const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+                                if (slot < p.exc_cap)
+                                    p.exc_list[slot] = make_uint2((unsigned int)(fb + p.ref_off + io), (unsigned int)(fb + p.obs_off + jo));
+                            }
+                        }
+                    } else if (VARIANT == 0) {
+                        // the two brackets disagree: decide with the exact fp64 threshold thr[n+1]
+                        const double thr = pc_lds_f64(tlo[q] * 8u + thr_m + 8u);
+                        ca[q] = tlo[q] * 4u + cnt_m + (d2[q] >= thr ? 4u : 0u);
+                    }
+                }
+            }
+            if (VERIFY) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    if (s1hi[q] < hi_flag || !(d2[q] < 1e29)) continue;
+                    // exact class by binary search in the table
+                    int lo_k = 0, hi_k = na + 1;
+                    while (lo_k < hi_k) { const int mid = (lo_k + hi_k + 1) >> 1; if (d2[q] >= pc_lds_f64(T.thr + 8u * (unsigned)mid)) lo_k = mid; else hi_k = mid - 1; }
+                    const int got = (int)((ca[q] - T.cnt) / 4u);
+                    const bool ok = lo_k < na ? (got == lo_k) : (got >= na);
+                    if (!ok) atomicAdd(p.verify_fail, 1u);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) pc_red(ca[q]);
+        }
+    }
+}
+
+template <int VARIANT>
+static __device__ void pc_flush(const PaPass &p, const PcTables &T, bool reset)
+{
+    const int na = T.na;
+    unsigned long long within = 0;
+    for (int k = threadIdx.x; k < na + 3; k += blockDim.x) {
+        const unsigned int c = pc_lds_u32(T.cnt + (unsigned)k * 4u);
+        if (c) {
+            if (k < na) { atomicAdd(&p.job.acc[k], (unsigned long long)((long long)c * p.weight)); within += c; }
+            else if (VARIANT == 1 && k == na) atomicAdd(&p.job.acc[na + 1], (unsigned long long)c);   // inside the cutoff, a-bin out of range
+            if (reset) pc_sts_u32(T.cnt + (unsigned)k * 4u, 0u);
+        }
+    }
+    if (within) atomicAdd(&p.job.acc[na], within);
+}
+
+template <int VARIANT, bool VERIFY>
+__global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
+                                                                   const unsigned int *ntiles_ptr, unsigned int tile_cap,
+                                                                   unsigned int *work_counter, int nzg)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int na = p.job.bin_a;
+    double *s_j = reinterpret_cast<double *>(smem_raw);                                   // PC_JC*6 doubles
+    unsigned long long *s_thr = reinterpret_cast<unsigned long long *>(s_j + PC_JC * 6);  // na+3
+    unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_thr + (na + 3));             // na+3 (+1 pad)
+    PcShared *sh = reinterpret_cast<PcShared *>(s_cnt + ((na + 4) & ~1));
+
+    for (int k = threadIdx.x; k < na + 3; k += blockDim.x) {
+        s_thr[k] = p.job.thr_a[k];       // "never" (all ones) is a NaN as a double: every `d2 >= NaN` is false, as required
+        s_cnt[k] = 0u;
+    }
+    __syncthreads();
+
+    PcTables T;
+    T.thr = (unsigned int)__cvta_generic_to_shared(s_thr);
+    T.cnt = (unsigned int)__cvta_generic_to_shared(s_cnt);
+    T.na = na;
+    T.cut = p.job.cut_bits;
+    if (VARIANT == 0) {
+        T.s_lo = p.job.guess_scale * (1.0f - 6.0e-7f);
+        T.s_hi = p.job.guess_scale * (1.0f + 6.0e-7f);
+    } else {
+        T.s_lo = T.s_hi = p.job.guess_scale * (1.0f - 9.5367431640625e-07f);             // floor(x~) <= true class
+    }
+    T.r_max = ((float)na + 1.5f) / p.job.guess_scale;
+    const double cut_d2 = __longlong_as_double((long long)T.cut) * (1.0 + 1e-12);
+    const float cutf = (float)fmin(cut_d2 * (1.0 + 1e-6), 3.0e38);                        // NaN ("never") -> 3e38
+    const unsigned int ntiles = min(*ntiles_ptr, tile_cap);
+    if (*ntiles_ptr > tile_cap && threadIdx.x == 0 && blockIdx.x == 0) atomicOr(p.exc_count + 1, 1u);
+    const long long n_items = (long long)ntiles * nzg;
+    unsigned long long since_flush = 0;
+    const int gx = go.g[0], gy = go.g[1], gz = go.g[2];
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh->work_item = (int)atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const long long item = sh->work_item;
+        if (item >= n_items) break;
+        const PaTile tl = tiles[item / nzg];
+        const int zg = (int)(item % nzg);
+        const int z0 = (int)((long long)gz * zg / nzg), z1 = (int)((long long)gz * (zg + 1) / nzg);
+        if (z0 == z1) continue;
+        // reference molecules of the tile -> registers
+        double p1x[PC_RI], p1y[PC_RI], p1z[PC_RI];
+        const long long ibase = (long long)tl.frame * gi.nmol;
+#pragma unroll
+        for (int r = 0; r < PC_RI; ++r) {
+            const int k = r * PC_THREADS + threadIdx.x;
+            if (k < tl.count) { p1x[r] = gi.sx[ibase + tl.begin + k]; p1y[r] = gi.sy[ibase + tl.begin + k]; p1z[r] = gi.sz[ibase + tl.begin + k]; }
+            else p1x[r] = p1y[r] = p1z[r] = -1.0e15;   // padding: far away, finite in float range
+        }
+        // classification of every observed layer against the tile's bounding box
+        for (int t = threadIdx.x; t < gx + gy + gz; t += blockDim.x) {
+            const int c = t < gx ? 0 : (t < gx + gy ? 1 : 2);
+            const int k = c == 0 ? t : (c == 1 ? t - gx : t - gx - gy);
+            const long long li = ((long long)tl.frame * 3 + c) * gi.gmax, lj = ((long long)tl.frame * 3 + c) * go.gmax;
+            double ilo, ihi;
+            if (c == 0) {
+                ilo = 1e300; ihi = -1e300;
+                for (int q = tl.cx0; q <= tl.cx1; ++q)
+                    if (gi.lay_lo[li + q] <= gi.lay_hi[li + q]) { ilo = fmin(ilo, okey_inv(gi.lay_lo[li + q])); ihi = fmax(ihi, okey_inv(gi.lay_hi[li + q])); }
+            } else {
+                const int q = c == 1 ? tl.cy : tl.cz;
+                ilo = okey_inv(gi.lay_lo[li + q]); ihi = okey_inv(gi.lay_hi[li + q]);
+            }
+            PcLayer cl;
+            if (go.lay_lo[lj + k] > go.lay_hi[lj + k]) { cl.mode = 0; cl.ca = cl.cb = 1; cl.pad = 0; cl.dmin2 = 3.0e38f; }   // empty layer
+            else cl = pc_classify(ilo, ihi, okey_inv(go.lay_lo[lj + k]), okey_inv(go.lay_hi[lj + k]), p.box.L[c]);
+            if (cl.mode == 3) atomicOr(p.exc_count + 1, 1u);                       // boxes too wide: host redoes the call without cells
+            sh->lay[c][k] = cl;
+        }
+        __syncthreads();
+        const unsigned long long item_pairs = (unsigned long long)PC_TILE * (unsigned long long)go.nmol;
+        if (since_flush + item_pairs > 0x7fffffffull) {
+            __syncthreads();
+            pc_flush<VARIANT>(p, T, true);
+            since_flush = 0;
+        }
+        since_flush += item_pairs;
+
+        const long long jbase = (long long)tl.frame * go.nmol;
+        const int *cs = go.cell_start + (long long)tl.frame * (go.ncell + 1);
+        for (int cz = z0; cz < z1; ++cz) {
+            const PcLayer lz = sh->lay[2][cz];
+            if (!(lz.dmin2 < cutf)) continue;
+            for (int cy = 0; cy < gy; ++cy) {
+                const PcLayer ly = sh->lay[1][cy];
+                const float dyz2 = lz.dmin2 + ly.dmin2;
+                if (!(dyz2 < cutf)) continue;
+                const int *row = cs + ((long long)cz * gy + cy) * gx;
+                int cx = 0;
+                while (cx < gx) {
+                    const PcLayer lx = sh->lay[0][cx];
+                    if (!(dyz2 + lx.dmin2 < cutf)) { ++cx; continue; }            // cannot reach the cutoff
+                    int ce = cx;                                                   // extend while the x classification is identical
+                    while (ce + 1 < gx) {
+                        const PcLayer ln = sh->lay[0][ce + 1];
+                        if (ln.mode != lx.mode || ln.ca != lx.ca || ln.cb != lx.cb || !(dyz2 + ln.dmin2 < cutf)) break;
+                        ++ce;
+                    }
+                    const int jb = row[cx], je = row[ce + 1];
+                    cx = ce + 1;
+                    if (jb == je) continue;
+                    const double Lx = p.box.L[0], Ly = p.box.L[1], Lz = p.box.L[2];
+                    const double sxa = (double)(lx.ca - 1) * Lx, sxb = (double)(lx.cb - 1) * Lx;
+                    const double sya = (double)(ly.ca - 1) * Ly, syb = (double)(ly.cb - 1) * Ly;
+                    const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
+                    const int code = (lx.mode >= 2 ? 1 : 0) | (ly.mode >= 2 ? 2 : 0) | (lz.mode >= 2 ? 4 : 0);
+#define PC_SEG(MX_, MY_, MZ_)                                                                                              \
+    pc_segment<MX_, MY_, MZ_, VARIANT, VERIFY>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb,  \
+                                               s_j, T)
+                    switch (code) {
+                    case 0: PC_SEG(1, 1, 1); break;
+                    case 1: PC_SEG(2, 1, 1); break;
+                    case 2: PC_SEG(1, 2, 1); break;
+                    case 3: PC_SEG(2, 2, 1); break;
+                    case 4: PC_SEG(1, 1, 2); break;
+                    case 5: PC_SEG(2, 1, 2); break;
+                    case 6: PC_SEG(1, 2, 2); break;
+                    default: PC_SEG(2, 2, 2); break;
+                    }
+#undef PC_SEG
+                }
+            }
+        }
+    }
+    __syncthreads();
+    pc_flush<VARIANT>(p, T, false);
+}
+
+// ---------------------------------------------------------------------------
+// launch wrappers
+
+int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &box, int frame0, int nframes, unsigned int *err, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)nframes * g.nmol;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    cudaMemsetAsync(g.cell_start, 0, sizeof(int) * (size_t)nframes * (g.ncell + 1), st);
+    cudaMemsetAsync(g.cell_fill, 0, sizeof(int) * (size_t)nframes * g.ncell, st);
+    cudaMemsetAsync(g.lay_lo, 0xff, sizeof(unsigned long long) * (size_t)nframes * 3 * g.gmax, st);
+    cudaMemsetAsync(g.lay_hi, 0x00, sizeof(unsigned long long) * (size_t)nframes * 3 * g.gmax, st);
+    pa_cell_count_kernel<<<blocks, 256, 0, st>>>(g, pts, box, frame0, nframes, err);
+    pa_cell_scan_kernel<<<nframes, 1024, 0, st>>>(g);
+    pa_cell_scatter_kernel<<<blocks, 256, 0, st>>>(g, pts, frame0, nframes);
+    return (int)cudaGetLastError();
+}
+
+int pa_launch_build_tiles(const PaCellGrid &g, int nframes, PaTile *tiles, unsigned int *ntiles, unsigned int cap, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(ntiles, 0, sizeof(unsigned int), st);
+    const int rows = nframes * g.g[1] * g.g[2];
+    // tile width (max_run cells) + one observed cell must stay below L/2: (max_run + 1.1) / gx < 0.5
+    int max_run = (int)(0.45 * g.g[0]) - 1;
+    if (max_run < 1) max_run = 1;
+    pa_build_tiles_kernel<<<(rows + 127) / 128, 128, 0, st>>>(g, nframes, max_run, tiles, ntiles, cap);
+    return (int)cudaGetLastError();
+}
+
+void pa_cell_grid_dims(int nmol, int g[3])
+{
+    // ~100 molecules per (y,z)-isotropic cell, split 4x finer along x: tiles are runs of x-cells
+    int G = (int)cbrt((double)nmol / 100.0);
+    if (G < 5) G = 5;
+    if (G > 64) G = 64;
+    g[1] = g[2] = G;
+    g[0] = 4 * G;
+    if (g[0] > PC_MAXG) g[0] = PC_MAXG;
+}
+
+size_t pa_cells_smem_bytes(int na) { return (size_t)PC_JC * 6 * 8 + (size_t)(na + 3) * 8 + (size_t)(na + 4) * 4 + sizeof(PcShared) + 16; }
+
+int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
+                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = pa_cells_smem_bytes(p.job.bin_a);
+    const bool verify = p.verify_fail != nullptr;
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
+#define PC_LAUNCH(O_, V_)                                                                                       \
+    do {                                                                                                        \
+        int occ = 1;                                                                                            \
+        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
+        pa_rdf_cells_kernel<O_, V_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+    } while (0)
+    if (variant == 1) { if (verify) PC_LAUNCH(1, true); else PC_LAUNCH(1, false); }
+    else { if (verify) PC_LAUNCH(0, true); else PC_LAUNCH(0, false); }
+#undef PC_LAUNCH
+    return (int)cudaGetLastError();
+}

@@ -83,6 +83,21 @@ struct PaPass {
     unsigned int *verify_fail;  // debug counter for the class-guess invariant (may be null)
 };
 
+// Uniform grid of one molecule type for a batch of frames (pa_cells.cu).  Arrays are
+// batch-local: frame index f counts from the first frame the sort was launched on.
+struct PaCellGrid {
+    int32_t g[3], gmax;              // cells per component (x finer than y,z), max of the three
+    int32_t ncell, nmol, type_off, pad_;
+    double inv_w[3];                 // g[k] / L[k]
+    int *cell_start;                 // [nframes][ncell+1] offsets into the sorted arrays
+    int *cell_fill;                  // [nframes][ncell]   scatter cursors
+    int *cid;                        // [nframes][nmol]    cell of every molecule
+    double *sx, *sy, *sz;            // [nframes][nmol]    wrapped positions in cell order
+    int *sorig;                      // [nframes][nmol]    original molecule index
+    unsigned long long *lay_lo, *lay_hi;   // [nframes][3][gmax] exact bounds per cell layer (ordered keys)
+};
+struct PaTile { int32_t frame, begin, count, cx0, cx1, cy, cz, pad; };
+
 // kernel launch wrappers (pa_kernels.cu).  All return cudaError_t as int.
 struct PaPrepareArgs {
     const PaDevType *types;     // device array
@@ -98,6 +113,11 @@ int pa_launch_prepare(const PaPrepareArgs &a, void *stream);
 int pa_launch_rdf_fast(const PaPass &p, int sm_count, void *stream);
 int pa_launch_general(const PaPass &p, int sm_count, void *stream);
 int pa_launch_exceptions(const PaPass &p, unsigned int count, void *stream);
+int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &box, int frame0, int nframes, unsigned int *err, void *stream);
+int pa_launch_build_tiles(const PaCellGrid &g, int nframes, PaTile *tiles, unsigned int *ntiles, unsigned int cap, void *stream);
+int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
+                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream);
+void pa_cell_grid_dims(int nmol, int g[3]);
 int pa_kernels_selfcheck();    // returns 0 when a kernel image for the current device exists
 int pa_rdf_ri(int nref);       // reference molecules per thread the fast kernel will use (tile = 128*RI)
 int pa_general_ri(int nref);

@@ -231,11 +231,12 @@ static __device__ __forceinline__ void pa_stage_j(const PaPass &p, long long fba
 // min over the three images of one component, squared: fl((min_k |(p2+s_k)-p1|)^2)
 static __device__ __forceinline__ double pa_min_image_sq(double jm, double j0, double jp, double p1)
 {
-    const double am = fabs(__dsub_rn(jm, p1));
-    const double a0 = fabs(__dsub_rn(j0, p1));
-    const double ap = fabs(__dsub_rn(jp, p1));
-    double m = a0 < am ? a0 : am;
-    m = ap < m ? ap : m;
+    // selects work on the signed values so that |.| stays an operand modifier of DSETP
+    const double dm = __dsub_rn(jm, p1);
+    const double d0 = __dsub_rn(j0, p1);
+    const double dp = __dsub_rn(jp, p1);
+    double m = fabs(d0) < fabs(dm) ? d0 : dm;
+    m = fabs(dp) < fabs(m) ? dp : m;
     return __dmul_rn(m, m);
 }
 

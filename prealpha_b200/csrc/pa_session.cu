@@ -8,6 +8,7 @@
 // sampled frames can be given to each GPU; integer accumulation makes the sum order-free.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <algorithm>
@@ -37,10 +38,20 @@ struct TypeMeta {
     size_t frame_floats() const { return (size_t)nmol * natoms * 3; }
 };
 
+struct TypeGrid {
+    bool enabled = false;
+    PaCellGrid g{};
+    PaTile *tiles = nullptr;
+    unsigned int *counters = nullptr;   // [0] ntiles, [1] work counter
+    unsigned int tile_cap = 0;
+    bool tiles_ready = false;
+};
+
 struct JobState {
     pa_job job;
     PaDevJob dj;
     bool fast;
+    int cells_variant;   // 0: approximate class + rare exact fix-up, 1: exact table for every pair (see pa_cells.cu)
     size_t acc_off;      // offset (words) inside the accumulator block
     size_t nbins;
     unsigned long long *d_thr_a = nullptr;
@@ -78,6 +89,8 @@ struct pa_session {
     unsigned int *d_exc_count = nullptr;    // [0] count, [1] sticky overflow, [2] verify failures
     pa_stats stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+    std::vector<TypeGrid> grids;            // cell-sorted copies of the types the RDF fast path pairs
+    bool use_cells = false;
 };
 
 namespace {
@@ -258,6 +271,54 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
         d.z_sign = jb.ref_vec[2] > 0 ? 1 : -1;
         d.acc = s->d_acc + js.acc_off;
         js.fast = !s->force_general && pa::job_is_rdf_fast(jb, *traj);
+        {
+            // variant 0 needs: no pair "inside the cutoff with a-bin out of range", and the cutoff within
+            // 3e-7 (relative) of the boundary of bin na, so that the sliver between the two is always
+            // caught by the +-6e-7 brackets of the approximate class.
+            js.cells_variant = 1;
+            if (jb.mode == PA_MODE_PDF && thr_a[jb.bin_a] == thr_a[(size_t)jb.bin_a + 1] && thr_a[(size_t)jb.bin_a + 1] != ~0ull) {
+                double cutd; memcpy(&cutd, &thr_a[(size_t)jb.bin_a + 1], 8);
+                const double xcut = std::sqrt(cutd) / (double)jb.step_a;
+                if (std::fabs(xcut - jb.bin_a) <= 3e-7 * jb.bin_a) js.cells_variant = 0;
+            }
+        }
+    }
+    // cell-sorted path: both partners of a pass need >= 12500 molecules (grid of >= 5^3 cells of ~100)
+    s->grids.resize(traj->ntypes);
+    s->use_cells = !(ex.flags & PA_EXEC_NO_CELLS) && !traj->wrap_trajectory;
+    if (s->use_cells) {
+        for (const JobState &js : s->jobs) {
+            if (!js.fast) continue;
+            const int r = js.job.ref_type - 1;
+            for (int o = 0; o < traj->ntypes; ++o) {
+                if (js.job.obs_type >= 1 && o != js.job.obs_type - 1) continue;
+                if (s->types[r].nmol >= 12500 && s->types[o].nmol >= 12500) { s->grids[r].enabled = true; s->grids[o].enabled = true; }
+            }
+        }
+        for (int t = 0; t < traj->ntypes; ++t) {
+            TypeGrid &tg = s->grids[t];
+            if (!tg.enabled) continue;
+            PaCellGrid &g = tg.g;
+            pa_cell_grid_dims(s->types[t].nmol, g.g);
+            g.gmax = std::max(g.g[0], std::max(g.g[1], g.g[2]));
+            g.ncell = g.g[0] * g.g[1] * g.g[2]; g.nmol = s->types[t].nmol; g.type_off = s->types[t].offset;
+            for (int k = 0; k < 3; ++k) g.inv_w[k] = (double)g.g[k] / s->box.L[k];
+            const size_t nf = (size_t)s->max_frames, nm = (size_t)g.nmol;
+            PA_CK(cudaMalloc(&g.cell_start, sizeof(int) * nf * (g.ncell + 1)));
+            PA_CK(cudaMalloc(&g.cell_fill, sizeof(int) * nf * g.ncell));
+            PA_CK(cudaMalloc(&g.cid, sizeof(int) * nf * nm));
+            PA_CK(cudaMalloc(&g.sx, sizeof(double) * nf * nm));
+            PA_CK(cudaMalloc(&g.sy, sizeof(double) * nf * nm));
+            PA_CK(cudaMalloc(&g.sz, sizeof(double) * nf * nm));
+            PA_CK(cudaMalloc(&g.sorig, sizeof(int) * nf * nm));
+            PA_CK(cudaMalloc(&g.lay_lo, sizeof(unsigned long long) * nf * 3 * g.gmax));
+            PA_CK(cudaMalloc(&g.lay_hi, sizeof(unsigned long long) * nf * 3 * g.gmax));
+            // every cell yields at most one tile plus one extra per 256 molecules
+            tg.tile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.ncell + nm / 256 + 1), 0x7fffffffu);
+            PA_CK(cudaMalloc(&tg.tiles, sizeof(PaTile) * tg.tile_cap));
+            PA_CK(cudaMalloc(&tg.counters, sizeof(unsigned int) * 4));
+            PA_CK(cudaMemset(tg.counters, 0, sizeof(unsigned int) * 4));
+        }
     }
     *out = s;
     return 0;
@@ -320,6 +381,12 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
     pa.pts = s->pts; pa.box = s->box; pa.need_coc = s->need_coc ? 1 : 0;
     PA_CK((cudaError_t)pa_launch_prepare(pa, s->s_compute));
     s->stats.kernel_launches += 1;
+    for (TypeGrid &tg : s->grids) {
+        if (!tg.enabled) continue;
+        PA_CK((cudaError_t)pa_launch_cell_sort(tg.g, s->pts, s->box, first, count, s->d_exc_count + 1, s->s_compute));
+        tg.tiles_ready = false;
+        s->stats.kernel_launches += 3;
+    }
     const long long target_items = (long long)s->sm_count * 16;
     for (JobState &js : s->jobs) {
         const pa_job &jb = js.job;
@@ -347,7 +414,21 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
             p.n_jsplits = (p.nobs + len - 1) / len;
             p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = kExcCap;
             p.verify_fail = s->verify ? s->d_exc_count + 2 : nullptr;
-            if (js.fast) {
+            if (js.fast && s->grids[r].enabled && s->grids[o].enabled) {
+                TypeGrid &gr = s->grids[r];
+                if (!gr.tiles_ready) {
+                    PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, gr.tiles, gr.counters, gr.tile_cap, s->s_compute));
+                    gr.tiles_ready = true;
+                    s->stats.kernel_launches += 1;
+                }
+                const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 230 + 1));
+                long long nzg = (20ll * s->sm_count * 5 + tiles_est - 1) / tiles_est;
+                nzg = std::max<long long>(1, std::min<long long>(nzg, s->grids[o].g.g[2]));
+                PA_CK((cudaError_t)pa_launch_rdf_cells(p, gr.g, s->grids[o].g, gr.tiles, gr.counters, gr.tile_cap, gr.counters + 1,
+                                                       (int)nzg, js.cells_variant, s->sm_count, s->s_compute));
+                PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
+                s->stats.kernel_launches += 3;
+            } else if (js.fast) {
                 PA_CK((cudaError_t)pa_launch_rdf_fast(p, s->sm_count, s->s_compute));
                 PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
                 s->stats.kernel_launches += 3;
@@ -441,6 +522,11 @@ void pa_session_destroy(pa_session *s)
         if (s->ev_done[b]) cudaEventDestroy(s->ev_done[b]);
     }
     for (auto &js : s->jobs) { cudaFree(js.d_thr_a); cudaFree(js.d_thr_b); }
+    for (auto &tg : s->grids) {
+        if (!tg.enabled) continue;
+        cudaFree(tg.g.cell_start); cudaFree(tg.g.cell_fill); cudaFree(tg.g.cid); cudaFree(tg.g.sx); cudaFree(tg.g.sy); cudaFree(tg.g.sz);
+        cudaFree(tg.g.sorig); cudaFree(tg.g.lay_lo); cudaFree(tg.g.lay_hi); cudaFree(tg.tiles); cudaFree(tg.counters);
+    }
     cudaFree(s->d_pts); cudaFree(s->d_acc); cudaFree(s->d_exc); cudaFree(s->d_exc_count);
     if (s->s_compute) cudaStreamDestroy(s->s_compute);
     if (s->s_copy) cudaStreamDestroy(s->s_copy);
@@ -476,7 +562,7 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
     // sampled frames 0, dt, 2dt, ... (Distribution:718); this shard takes k % count == rank
     const int nsamp = (traj->nsteps + dt - 1) / dt;
     const int nlocal = nsamp > ex.shard_rank ? (nsamp - ex.shard_rank + ex.shard_count - 1) / ex.shard_count : 0;
-    for (int attempt = 0; attempt < 2; ++attempt) {
+    for (int attempt = 0; attempt < 3; ++attempt) {
         const int batch = choose_batch(traj, &ex, nlocal);
         pa_session *s = nullptr;
         int rc = pa_session_create(traj, jobs, njobs, &ex, batch, &s);
@@ -501,10 +587,11 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
         }
         cudaEventDestroy(t0); cudaEventDestroy(t1);
         pa_session_destroy(s);
-        if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_FORCE_GENERAL)) {   // exception list overflow
-            ex.flags |= PA_EXEC_FORCE_GENERAL;
-            continue;
-        }
+        // sticky device flag: exception list overflow / boxes too wide for the cell path / non-finite
+        // coordinates.  Redo without cells first, then with the general kernel (always applicable).
+        if (rc == PA_ERR_UNSUPPORTED && getenv("PA_DEBUG")) fprintf(stderr, "[prealpha_b200] attempt %d: %s -> retrying with a more general kernel\n", attempt, pa_last_error());
+        if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_NO_CELLS)) { ex.flags |= PA_EXEC_NO_CELLS; continue; }
+        if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_FORCE_GENERAL)) { ex.flags |= PA_EXEC_FORCE_GENERAL; continue; }
         return rc;
     }
     return PA_ERR_UNSUPPORTED;

@@ -151,6 +151,59 @@ def test_random_systems_against_oracle(case, oracle):
         assert np.array_equal(hists[k], h0), (seed, k)
 
 
+def _big_system(seed, n1, n2, L, nsteps=1, clustered=False, lmp=False):
+    rng = np.random.default_rng(seed)
+    n = n1 + n2
+    if clustered:
+        centres = rng.random((12, 3)) * L
+        pos = centres[rng.integers(0, 12, size=(nsteps, n))] + rng.standard_normal((nsteps, n, 3)) * (L / 14.0)
+        pos[:, : n // 5] = rng.random((nsteps, n // 5, 3)) * L * 1.4 - 0.2 * L          # some uniform background, partly outside the box
+    else:
+        pos = rng.random((nsteps, n, 3)) * L
+    pos = np.round(pos, 4)
+    for s in range(nsteps):                       # planted special pairs (see tests/golden/make_golden.py::case_synth)
+        pos[s, 3, :2] = pos[s, n1 + 5, :2]        # same x,y: link exactly along +-z, different types
+        pos[s, 7, :2] = pos[s, 8, :2]             # same type
+        pos[s, 9] = pos[s, n1 + 9]                # coincident atoms
+        pos[s, 11] = (0.0, L, L / 2)              # on the faces
+        pos[s, 12, 0] = pos[s, 13, 0] + np.round(L / 2, 4)   # |dx| = L/2 (image tie when L/2 is exact)
+        pos[s, 12, 1:] = pos[s, 13, 1:]
+    pos = pos.astype(np.float32)
+    tl = [dict(charge=+1, natoms=1, nmol=n1, elements=["Na"], xyz=pos[:, :n1].reshape(nsteps, n1, 1, 3)),
+          dict(charge=-1, natoms=1, nmol=n2, elements=["Cl"], xyz=pos[:, n1:].reshape(nsteps, n2, 1, 3))]
+    if lmp:
+        lo = np.array([-1.25, 0.333333333333, 2.0]); hi = lo + np.array([L, L * 1.07, L * 0.91])
+        return capi.Trajectory(tl, lo, hi, xyz_format=False)
+    lo32, hi32 = capi.cubic_box_edge(0.0, L)
+    return capi.Trajectory(tl, lo32, hi32)
+
+
+BIG = [("uniform", dict(seed=21, n1=13000, n2=15500, L=80.0)),
+       ("clustered", dict(seed=22, n1=12600, n2=14000, L=76.0, clustered=True)),
+       ("lmp_box_2frames", dict(seed=23, n1=12500, n2=12500, L=70.0, nsteps=2, lmp=True))]
+
+
+@pytest.mark.parametrize("name,kw", BIG, ids=[b[0] for b in BIG])
+def test_cell_sorted_kernel_against_oracle(name, kw, oracle):
+    """The cell-sorted tile kernel (>= 12500 molecules per type) is bit-exact against the oracle and
+    against the brute-force tile kernel, including pairs (anti)parallel to z, coincident atoms, atoms on
+    the box faces and exact image ties."""
+    traj = _big_system(**kw)
+    reqs = [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
+            dict(mode="pdf", ref_type=2, obs_type=2, bin_a=300, bin_b=1, maxdist=17.25),
+            dict(mode="pdf", vec=(0, 0, -1), ref_type=2, obs_type=1, bin_a=64, bin_b=1, maxdist_optimize=True, weigh_charge=True)]
+    pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
+    cells = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY))
+    brute = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY | capi.PA_EXEC_NO_CELLS))
+    assert cells[3].kernel_launches != brute[3].kernel_launches      # the cell path really ran
+    for k, job in enumerate(pjobs):
+        assert np.array_equal(cells[0][k], brute[0][k]) and cells[1][k] == brute[1][k] and cells[2][k] == brute[2][k], (name, k)
+    for k in (1, 2) if name != "lmp_box_2frames" else (1,):          # keep the CPU oracle time bounded
+        h0, w0, o0 = oracle.histogram(traj, pjobs[k])
+        assert np.array_equal(cells[0][k], h0) and (int(cells[1][k]), int(cells[2][k])) == (w0, o0), (name, k)
+    assert int(cells[2].sum()) > 0, "the planted (anti)parallel / coincident pairs must show up as out of bounds"
+
+
 def test_wrap_trajectory_switch(oracle):
     """WRAP_TRAJECTORY = T skips wrap_vector inside the distance routine (Molecular:1442)."""
     rng = np.random.default_rng(11)
