@@ -224,30 +224,39 @@ int pa_write_distribution(const pa_traj *traj, const pa_job *job, int32_t refere
  * beyond NUL); buf must hold >= 32 bytes.  Returns the length written. */
 int pa_format_real4(float value, char *buf);
 
-/* ---- row X: `distance` analysis (Module_Distances) ----------------------- */
+/* ---- row X: `distance` analysis (Module_Distances) -----------------------
+ * Replaces compute_intermolecular_distances / compute_intramolecular_distances
+ * (Distances:976-1091 / 856-974) including the second pass for the standard deviations
+ * and the post-processing of perform_distance_analysis (Distances:1161-1243).
+ * A subjob is one line of the distance input after wildcard expansion
+ * (prepare_subjob, Distances:500-609): the reference atoms indices_1 and the observed
+ * atoms indices_2 as (molecule type, atom index) pairs, both 1-based.
+ * Sums of exp / r^-3 / r^-6 terms are fp64 reductions: the GPU adds them in a fixed tree
+ * order, the reference in loop order, so results agree to ~1e-12 relative, not bitwise
+ * (the reference prints them with 3-4 significant digits). */
 typedef struct pa_dist_subjob {
-    int32_t ref_type, ref_atom;   /* 1-based; molecule type / atom index in molecule */
-    int32_t obs_type, obs_atom;
+    int32_t n_ref, n_obs;
+    const int32_t *ref;           /* [n_ref][2] = (molecule type, atom index)   indices_1       */
+    const int32_t *obs;           /* [n_obs][2]                                  indices_2       */
+    int64_t weight;               /* reference atoms expected per step (Distances:810-845)        */
 } pa_dist_subjob;
 typedef struct pa_dist_job {
-    int32_t intermolecular;       /* 1 = inter, 0 = intra  (Distances:314-320)        */
+    int32_t intermolecular;       /* 1 = "inter", 0 = "intra"  (Distances:314-320)                */
     int32_t nsubjobs;
-    const pa_dist_subjob *subjobs;/* expanded (wildcards resolved) atom pairs,        */
-    const int32_t *subjob_of;     /* [nsubjobs] index of the user-level subjob group  */
-    int32_t ngroups;
-    int32_t nsteps;               /* steps to use (Distances default 1)               */
+    const pa_dist_subjob *subjobs;
+    int32_t nsteps;               /* steps 1..nsteps are used (default 1, Distances:9)            */
     int32_t sampling_interval;
     int32_t calc_exp, calc_ffc, calc_stdev;
-    float   maxdist;              /* REAL4 cutoff                                     */
-    float   exponent;             /* k of exp(-k r)                                   */
+    float   maxdist;              /* REAL4 cutoff; maxdist_squared = maxdist**2 in REAL4          */
+    float   exponent;             /* k of exp(-k r), REAL4                                        */
 } pa_dist_job;
-typedef struct pa_dist_result {   /* per user-level group                              */
-    double closest, closest_stdev;
-    double exp_weighted, exp_stdev;
-    double ffc, ffc_stdev;
-    int64_t weight;
+typedef struct pa_dist_result {   /* list_of_distances(n)%... after post-processing               */
+    double closest_average, closest_stdev;
+    double exponential_average, exponential_stdev, exponential_weight;
+    double ffc_average, ffcexp_average, ffc_weight;
+    int64_t missed_neighbours;
 } pa_dist_result;
-int pa_distance_subjobs(const pa_traj *traj, const pa_dist_job *job, pa_dist_result *results);
+int pa_distance_subjobs(const pa_traj *traj, const pa_dist_job *job, const pa_exec *exec, pa_dist_result *results);
 
 /* ---- file-level drop-in ----------------------------------
  * Runs a general.inp the way `./prealpha general.inp` does for the keywords

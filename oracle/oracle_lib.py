@@ -34,6 +34,7 @@ _SIG = {
     "orc_write_distribution": (C.c_int, [C.POINTER(capi.pa_traj), C.POINTER(capi.pa_job), C.c_int, C.c_char_p,
                                          C.c_char_p, C.POINTER(C.c_float), C.c_float]),
     "orc_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
+    "orc_distance_subjobs": (C.c_int, [C.POINTER(capi.pa_traj), C.POINTER(capi.pa_dist_job), C.POINTER(capi.pa_dist_result)]),
     "orc_read_xyz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_char_p]),
 }
 _lib = None
@@ -88,6 +89,13 @@ def write(traj, job, refnum, prefix, input_name, g, rho):
                                        g.ctypes.data_as(C.POINTER(C.c_float)), rho)
     assert rc == 0, rc
     return g
+
+
+def distance_subjobs(traj, job):
+    res = (capi.pa_dist_result * job.nsubjobs)()
+    rc = load().orc_distance_subjobs(traj.ptr, C.byref(job), res)
+    assert rc == 0
+    return [r.as_dict() for r in res]
 
 
 def format_real4(x) -> str:

@@ -596,3 +596,118 @@ int orc_read_xyz(const char *path, int natoms_total, int nsteps, float *out, cha
     free(line); fclose(f);
     return 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* Row X: compute_intermolecular_distances / compute_intramolecular_distances
+ * (Distances:976-1091 / 856-974), first pass and stdev pass, then the post-processing of
+ * perform_distance_analysis (Distances:1161-1243).  Literal loop order. */
+static float orc_atom_d2(const pa_traj *t, int step, int ty1, int mol1, int at1, int ty2, int mol2, int at2)
+{
+    const pa_type *a = &t->types[ty1], *b = &t->types[ty2];
+    const float *r1 = a->xyz + (((size_t)step * a->nmol + mol1) * a->natoms + at1) * 3;
+    const float *r2 = b->xyz + (((size_t)step * b->nmol + mol2) * b->natoms + at2) * 3;
+    return (float)orc_smallest_atom_distance_squared(t, r1, r2);      /* REAL(4) distance_squared */
+}
+
+static void orc_distance_pass(const pa_traj *t, const pa_dist_job *job, int stdev_run, pa_dist_result *res)
+{
+    const float maxdist_squared = job->maxdist * job->maxdist;
+    for (int step = 0; step < job->nsteps; step += job->sampling_interval) {
+        for (int k = 0; k < job->nsubjobs; ++k) {
+            const pa_dist_subjob *sj = &job->subjobs[k];
+            int64_t localweight = 0, localweight_ffc = 0;
+            double local_closest = 0, local_exponential = 0, weight_exponential = 0, local_exponential_stdev = 0, local_ffc = 0, local_ffcexp = 0;
+            for (int e1 = 0; e1 < sj->n_ref; ++e1) {
+                const int ty1 = sj->ref[2 * e1] - 1, at1 = sj->ref[2 * e1 + 1] - 1;
+                for (int m1 = 0; m1 < t->types[ty1].nmol; ++m1) {
+                    float closest = maxdist_squared;
+                    int valid = 0;
+                    if (stdev_run && job->calc_exp) { local_exponential = 0; weight_exponential = 0; }
+                    for (int e2 = 0; e2 < sj->n_obs; ++e2) {
+                        const int ty2 = sj->obs[2 * e2] - 1, at2 = sj->obs[2 * e2 + 1] - 1;
+                        int m2lo, m2hi;
+                        if (job->intermolecular) { m2lo = 0; m2hi = t->types[ty2].nmol; }
+                        else { if (ty1 != ty2 || at1 == at2) continue; m2lo = m1; m2hi = m1 + 1; }
+                        for (int m2 = m2lo; m2 < m2hi; ++m2) {
+                            if (job->intermolecular && m1 == m2 && ty1 == ty2) continue;
+                            const float d2 = orc_atom_d2(t, step, ty1, m1, at1, ty2, m2, at2);
+                            if (!(d2 < maxdist_squared)) continue;
+                            valid = 1;
+                            if (d2 < closest) closest = d2;
+                            double ef = 0.0;
+                            if (job->calc_exp) {
+                                const float distance = sqrtf(d2);
+                                ef = (double)expf(-job->exponent * distance);
+                                local_exponential = local_exponential + ef * (double)distance;
+                                weight_exponential = weight_exponential + ef;
+                            }
+                            if (job->calc_ffc) {
+                                float ffc;
+                                if (job->intermolecular) { const float distance = sqrtf(d2); ffc = 1.0f / ((distance * distance) * distance); }
+                                else ffc = 1.0f / ((d2 * d2) * d2);
+                                local_ffc = local_ffc + (double)ffc;
+                                localweight_ffc += 1;
+                                if (job->calc_exp) local_ffcexp = local_ffcexp + ef * (double)ffc;
+                            }
+                        }
+                    }
+                    if (valid) {
+                        localweight += 1;
+                        if (stdev_run) {
+                            const double dv = (double)sqrtf(closest) - res[k].closest_average;
+                            local_closest = local_closest + dv * dv;
+                            if (job->calc_exp) {
+                                const double de = local_exponential / weight_exponential - res[k].exponential_average;
+                                local_exponential_stdev = local_exponential_stdev + de * de;
+                            }
+                        } else local_closest = local_closest + (double)sqrtf(closest);
+                    } else res[k].missed_neighbours += 1;     /* also during the stdev pass (Distances:948,1067) */
+                }
+            }
+            const double lw = (double)(float)localweight;
+            if (stdev_run) {
+                res[k].closest_stdev += local_closest / lw;
+                if (job->calc_exp) res[k].exponential_stdev += local_exponential_stdev / lw;
+            } else {
+                res[k].closest_average += local_closest / lw;
+                if (job->calc_exp) { res[k].exponential_average += local_exponential; res[k].exponential_weight += weight_exponential; }
+                if (job->calc_ffc) {
+                    res[k].ffc_average += local_ffc;
+                    if (job->calc_exp) res[k].ffcexp_average += local_ffcexp;
+                    res[k].ffc_weight += (double)(float)localweight_ffc;
+                }
+            }
+        }
+    }
+}
+
+int orc_distance_subjobs(const pa_traj *t, const pa_dist_job *job, pa_dist_result *res)
+{
+    memset(res, 0, sizeof(pa_dist_result) * job->nsubjobs);
+    orc_distance_pass(t, job, 0, res);
+    int nav = (job->nsteps - 1 + job->sampling_interval) / job->sampling_interval;
+    if (nav < 0) nav = 0;
+    const double navf = (double)(float)nav;
+    for (int k = 0; k < job->nsubjobs; ++k) {
+        res[k].closest_average = res[k].closest_average / navf;
+        if (job->calc_exp) res[k].exponential_average = res[k].exponential_average / res[k].exponential_weight;
+        if (job->calc_ffc) {
+            res[k].ffc_average = res[k].ffc_average / res[k].ffc_weight;
+            if (job->calc_exp) res[k].ffcexp_average = res[k].ffcexp_average / res[k].exponential_weight;
+            /* REAL8 ** REAL4 constant: (-1.0/6.0) and (-1.0/3.0) are REAL(4) quotients */
+            const double ex = job->intermolecular ? (double)(-1.0f / 3.0f) : (double)(-1.0f / 6.0f);
+            res[k].ffc_average = pow(res[k].ffc_average, ex);
+            if (job->calc_exp) res[k].ffcexp_average = pow(res[k].ffcexp_average, ex);
+        }
+    }
+    if (job->calc_stdev) {
+        /* the stdev pass of the reference adds to missed_neighbours a second time (Distances:948,1067):
+         * reproduce by letting the pass count again, as the binary's report shows the doubled number */
+        orc_distance_pass(t, job, 1, res);
+        for (int k = 0; k < job->nsubjobs; ++k) {
+            res[k].closest_stdev = sqrt(res[k].closest_stdev / navf);
+            if (job->calc_exp) res[k].exponential_stdev = sqrt(res[k].exponential_stdev / navf);
+        }
+    }
+    return 0;
+}

@@ -88,6 +88,14 @@ def write(traj, job, refnum, prefix, input_name, g, rho):
     return g
 
 
+def distance_subjobs(traj, job, exec_=None):
+    """Row X through the C ABI: list of result dicts, one per subjob."""
+    res = (capi.pa_dist_result * job.nsubjobs)()
+    ex = exec_ if exec_ is not None else make_exec()
+    capi.check(capi.load().pa_distance_subjobs(traj.ptr, C.byref(job), C.byref(ex), res), "pa_distance_subjobs")
+    return [r.as_dict() for r in res]
+
+
 def format_real4(x) -> str:
     buf = C.create_string_buffer(64)
     capi.load().pa_format_real4(float(np.float32(x)), buf)

@@ -84,14 +84,14 @@ class pa_stats(C.Structure):
 
 
 class pa_dist_subjob(C.Structure):
-    _fields_ = [("ref_type", C.c_int32), ("ref_atom", C.c_int32), ("obs_type", C.c_int32), ("obs_atom", C.c_int32)]
+    _fields_ = [("n_ref", C.c_int32), ("n_obs", C.c_int32), ("ref", C.POINTER(C.c_int32)), ("obs", C.POINTER(C.c_int32)),
+                ("weight", C.c_int64)]
 
 
 class pa_dist_job(C.Structure):
     _fields_ = [
-        ("intermolecular", C.c_int32), ("nsubjobs", C.c_int32),
-        ("subjobs", C.POINTER(pa_dist_subjob)), ("subjob_of", C.POINTER(C.c_int32)),
-        ("ngroups", C.c_int32), ("nsteps", C.c_int32), ("sampling_interval", C.c_int32),
+        ("intermolecular", C.c_int32), ("nsubjobs", C.c_int32), ("subjobs", C.POINTER(pa_dist_subjob)),
+        ("nsteps", C.c_int32), ("sampling_interval", C.c_int32),
         ("calc_exp", C.c_int32), ("calc_ffc", C.c_int32), ("calc_stdev", C.c_int32),
         ("maxdist", C.c_float), ("exponent", C.c_float),
     ]
@@ -99,10 +99,14 @@ class pa_dist_job(C.Structure):
 
 class pa_dist_result(C.Structure):
     _fields_ = [
-        ("closest", C.c_double), ("closest_stdev", C.c_double),
-        ("exp_weighted", C.c_double), ("exp_stdev", C.c_double),
-        ("ffc", C.c_double), ("ffc_stdev", C.c_double), ("weight", C.c_int64),
+        ("closest_average", C.c_double), ("closest_stdev", C.c_double),
+        ("exponential_average", C.c_double), ("exponential_stdev", C.c_double), ("exponential_weight", C.c_double),
+        ("ffc_average", C.c_double), ("ffcexp_average", C.c_double), ("ffc_weight", C.c_double),
+        ("missed_neighbours", C.c_int64),
     ]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
 
 
 # symbol -> (restype, argtypes); every entry of include/prealpha_b200.h
@@ -130,7 +134,7 @@ SIGNATURES = {
     "pa_write_distribution": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_job), C.c_int32, C.c_char_p,
                                         C.c_char_p, C.POINTER(C.c_float), C.c_float]),
     "pa_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
-    "pa_distance_subjobs": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_dist_job), C.POINTER(pa_dist_result)]),
+    "pa_distance_subjobs": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_dist_job), C.POINTER(pa_exec), C.POINTER(pa_dist_result)]),
     "pa_run_general_input": (C.c_int, [C.c_char_p, C.POINTER(pa_exec)]),
 }
 

@@ -132,6 +132,8 @@ struct Run {
     std::map<std::string, float> mass_override, charge_override;
     int errors = 0;
     pa_exec exec{};
+    // Distances:288-296: set_defaults() does NOT reset these two, they persist between `distance` lines
+    bool dist_calc_exp = false, dist_calc_ffc = false;
 
     void error(int code, const std::string &msg)
     {
@@ -460,6 +462,218 @@ int perform_distribution(Run &r, const std::string &input_name)     // Distribut
     return 0;
 }
 
+
+// ---- `distance <file>`: Distances:299-802 (input, wildcard expansion), :1093-1159 (report) -------------
+struct DistSubjob {
+    std::vector<int32_t> ref, obs;          // (type, atom) pairs, 1-based
+    long long weight = 0;
+    std::string description, el1, el2;
+};
+
+std::vector<std::array<int, 2>> atoms_of_element(const Run &r, const std::string &el, int only_type /* 1-based or 0 */)
+{
+    std::vector<std::array<int, 2>> v;      // give_indices_of_specific_atoms[_per_molecule]: type-major, then atom order
+    for (size_t t = 0; t < r.types.size(); ++t) {
+        if (only_type && (int)t + 1 != only_type) continue;
+        for (int a = 0; a < r.types[t].natoms; ++a)
+            if (r.types[t].elements[a] == el) v.push_back({ (int)t + 1, a + 1 });
+    }
+    return v;
+}
+
+std::string fortran_e93(double v)           // E9.3 = 0.dddE+ee
+{
+    if (std::isnan(v)) return "      NaN";
+    if (v == 0.0) return "0.000E+00";
+    int e = (int)std::floor(std::log10(std::fabs(v))) + 1;
+    double m = std::fabs(v) / std::pow(10.0, e);
+    long mi = std::lround(m * 1000.0);
+    if (mi >= 1000) { mi = 100; ++e; }
+    if (mi < 100) { mi *= 10; --e; }
+    char buf[32];
+    snprintf(buf, sizeof buf, "%s0.%03ldE%+03d", v < 0 ? "-" : "", mi, e);
+    return buf;
+}
+
+void formatted_distance_output(const std::string &what, double d)   // Distances:1145-1157
+{
+    printf("     %s: ", what.c_str());
+    if (d > 1000.0) printf("%s\n", fortran_e93(d).c_str());
+    else if (d > 1.0) printf("%.3f\n", d);
+    else if (d > 0.01) printf("%5.3f\n", d);
+    else printf("%s\n", fortran_e93(d).c_str());
+}
+
+int perform_distance(Run &r, const std::string &input_name)
+{
+    std::vector<std::string> lines;
+    if (!read_lines(r.path_in + input_name, lines)) { r.error(134, "distance input file '" + r.path_in + input_name + "' not found"); return 134; }
+    std::vector<std::vector<std::string>> toks;
+    for (auto &l : lines) { auto t = tokens_of(l); if (!t.empty()) toks.push_back(t); }
+    if (toks.empty() || toks[0].size() < 2) { r.error(135, "incorrect format in distance input"); return 135; }
+    std::string mode = toks[0][0];
+    if (mode == "intramolecular") mode = "intra";
+    if (mode == "intermolecular") mode = "inter";
+    int nsub = 0;
+    if ((mode != "intra" && mode != "inter") || !parse_int(toks[0][1], nsub)) { r.error(135, "incorrect format in distance input"); return 135; }
+    const bool inter = mode == "inter";
+    const int ntypes = (int)r.types.size();
+    printf(" reading %d user-specified distances...\n", nsub);
+    std::vector<DistSubjob> subs;
+    auto natoms_of = [&](int t) { return (t >= 1 && t <= ntypes) ? r.types[t - 1].natoms : 0; };
+    size_t line = 1;
+    for (int n = 0; n < nsub && line < toks.size(); ++n, ++line) {
+        const auto &tk = toks[line];
+        int a = 0, b = 0, c = 0, d = 0;
+        DistSubjob sj;
+        int wild = -1, t1 = 0, a1 = 0, t2 = 0, a2 = 0;
+        std::string e1, e2;
+        if (inter) {
+            if (tk.size() >= 4 && parse_int(tk[0], a) && parse_int(tk[1], b) && parse_int(tk[2], c) && parse_int(tk[3], d)) {
+                t1 = a; a1 = b; t2 = c; a2 = d;
+                if (a1 < 1 || a1 > natoms_of(t1) || a2 < 1 || a2 > natoms_of(t2)) { r.error(111, "invalid atom index - this line is ignored"); continue; }
+                if (t1 == t2 && r.types[t1 - 1].nmol == 1) { r.error(141, "intermolecular distance needs more than one molecule"); continue; }
+                wild = 0;
+            } else if (tk.size() >= 3 && parse_int(tk[1], b) && parse_int(tk[2], c)) {                 // El type atom -> swapped
+                e1 = tk[0].substr(0, 2);
+                if (c < 1 || c > natoms_of(b)) { r.error(natoms_of(b) ? 111 : 110, "invalid index - this line is ignored"); continue; }
+                if (atoms_of_element(r, e1, 0).empty()) { r.error(136, "no atoms of element '" + e1 + "'"); continue; }
+                printf("  #  NOTICE 140: Swapped reference and observed atoms (wildcard -> specific not allowed).\n");
+                ++r.errors;
+                wild = 1; t1 = b; a1 = c; e2 = e1;
+            } else if (tk.size() >= 3 && parse_int(tk[0], a) && parse_int(tk[1], b)) {                 // type atom El
+                e2 = tk[2].substr(0, 2);
+                if (b < 1 || b > natoms_of(a)) { r.error(natoms_of(a) ? 111 : 110, "invalid index - this line is ignored"); continue; }
+                if (atoms_of_element(r, e2, 0).empty()) { r.error(136, "no atoms of element '" + e2 + "'"); continue; }
+                wild = 1; t1 = a; a1 = b;
+            } else if (tk.size() >= 2) {                                                                // El El
+                e1 = tk[0].substr(0, 2); e2 = tk[1].substr(0, 2);
+                if (atoms_of_element(r, e1, 0).empty() || atoms_of_element(r, e2, 0).empty()) { r.error(136, "no atoms of that element"); continue; }
+                wild = 2;
+            } else break;
+        } else {
+            if (tk.size() >= 3 && parse_int(tk[0], a) && parse_int(tk[1], b) && parse_int(tk[2], c)) {
+                t1 = t2 = a; a1 = b; a2 = c;
+                if (a1 < 1 || a1 > natoms_of(t1) || a2 < 1 || a2 > natoms_of(t1) || a1 == a2) { r.error(natoms_of(t1) ? 111 : 110, "invalid index - this line is ignored"); continue; }
+                wild = 0;
+            } else if (tk.size() >= 3 && parse_int(tk[0], a) && parse_int(tk[2], c)) {                 // type El atom -> swapped
+                e1 = tk[1].substr(0, 2);
+                if (c < 1 || c > natoms_of(a)) { r.error(natoms_of(a) ? 111 : 110, "invalid index - this line is ignored"); continue; }
+                if (atoms_of_element(r, e1, a).empty()) { r.error(136, "no atoms of element '" + e1 + "' in that molecule"); continue; }
+                printf("  #  NOTICE 140: Swapped reference and observed atoms (wildcard -> specific not allowed).\n");
+                ++r.errors;
+                wild = 1; t1 = a; a1 = c; e2 = e1;
+            } else if (tk.size() >= 3 && parse_int(tk[0], a) && parse_int(tk[1], b)) {                 // type atom El
+                e2 = tk[2].substr(0, 2);
+                if (b < 1 || b > natoms_of(a)) { r.error(natoms_of(a) ? 111 : 110, "invalid index - this line is ignored"); continue; }
+                if (atoms_of_element(r, e2, a).empty()) { r.error(136, "no atoms of element '" + e2 + "' in that molecule"); continue; }
+                wild = 1; t1 = a; a1 = b;
+            } else if (tk.size() >= 2) {
+                e1 = tk[0].substr(0, 2); e2 = tk[1].substr(0, 2);
+                bool ok = false;
+                for (int t = 1; t <= ntypes && !ok; ++t) ok = !atoms_of_element(r, e1, t).empty() && !atoms_of_element(r, e2, t).empty();
+                if (!ok) { r.error(136, "no molecule contains both elements"); continue; }
+                wild = 2;
+            } else break;
+        }
+        // prepare_subjob, Distances:500-609
+        char buf[512];
+        if (wild == 0) {
+            sj.ref = { t1, a1 }; sj.obs = { t2, a2 };
+            snprintf(buf, sizeof buf, "Atom #%d in molecule type %d -> atom #%d in molecule type %d", a1, t1, a2, t2);
+            sj.weight = r.types[t1 - 1].nmol;
+        } else if (wild == 1) {
+            sj.ref = { t1, a1 };
+            auto v = atoms_of_element(r, e2, inter ? 0 : t1);
+            for (auto &x : v) { sj.obs.push_back(x[0]); sj.obs.push_back(x[1]); }
+            snprintf(buf, sizeof buf, "Atom #%d in molecule type %d -> %zu %s atoms.", a1, t1, v.size(), e2.c_str());
+            sj.weight = r.types[t1 - 1].nmol;
+        } else {
+            auto v1 = atoms_of_element(r, e1, 0), v2 = atoms_of_element(r, e2, 0);
+            for (auto &x : v1) { sj.ref.push_back(x[0]); sj.ref.push_back(x[1]); }
+            for (auto &x : v2) { sj.obs.push_back(x[0]); sj.obs.push_back(x[1]); }
+            snprintf(buf, sizeof buf, "%zu %s atoms -> %zu %s atoms.", v1.size(), e1.c_str(), v2.size(), e2.c_str());
+            for (auto &x : v1)                                                      // count_wildcard_weights, Distances:810-845
+                for (auto &y : v2) {
+                    if (!inter) { if (x[0] == y[0] && x[1] != y[1]) { sj.weight += r.types[x[0] - 1].nmol; break; } }
+                    else if (x[0] != y[0] || x[1] != y[1]) { sj.weight += r.types[x[0] - 1].nmol; break; }
+                    else if (r.types[x[0] - 1].nmol > 1) { sj.weight += r.types[x[0] - 1].nmol; break; }
+                }
+        }
+        sj.description = buf;
+        sj.el1 = r.types[sj.ref[0] - 1].elements[sj.ref[1] - 1];
+        sj.el2 = r.types[sj.obs[0] - 1].elements[sj.obs[1] - 1];
+        subs.push_back(sj);
+    }
+    printf(" Successfully read %zu/%d custom distance jobs.\n", subs.size(), nsub);
+    if (subs.empty()) { r.error(139, "no valid distance jobs"); return 139; }
+    // keyword block, Distances:366-489; defaults :9-14 and set_defaults :288-296
+    int nsteps = 1, sampling = 1;
+    bool stdev = false;
+    float maxdist = 10.0f, exponent = 1.0f;
+    for (line = 1 + (size_t)nsub; line < toks.size(); ++line) {
+        const auto &tk = toks[line];
+        const std::string &k = tk[0];
+        bool lb; int iv; float fv;
+        if (k == "sampling_interval") { if (tk.size() > 1 && parse_int(tk[1], iv)) sampling = iv; else { r.error(100, "cannot read 'sampling_interval'"); sampling = 1; } }
+        else if (k == "exponent") { if (tk.size() > 1 && parse_real4(tk[1], fv)) exponent = fv; else { r.error(100, "cannot read 'exponent'"); exponent = 1.0f; } }
+        else if (k == "exponential_weight" || k == "weigh_exponential" || k == "calculate_exponential" || k == "average_exponential") {
+            if (tk.size() > 1 && parse_logical(tk[1], lb)) r.dist_calc_exp = lb; else { r.error(100, "cannot read '" + k + "'"); r.dist_calc_exp = false; }
+        } else if (k == "stdev" || k == "standard_deviation" || k == "standarddev") {
+            if (tk.size() > 1 && parse_logical(tk[1], lb)) stdev = lb; else { r.error(100, "cannot read '" + k + "'"); stdev = false; }
+        } else if (k == "ffc_weight" || k == "weigh_ffc" || k == "calculate_ffc" || k == "average_ffc" || k == "ffc" || k == "dhh" || k == "rhh") {
+            if (tk.size() > 1 && parse_logical(tk[1], lb)) r.dist_calc_ffc = lb; else { r.error(100, "cannot read '" + k + "'"); r.dist_calc_ffc = false; }
+        } else if (k == "nsteps") { if (tk.size() > 1 && parse_int(tk[1], iv)) nsteps = iv; else { r.error(100, "cannot read 'nsteps'"); nsteps = 1; } }
+        else if (k == "maxdist" || k == "cutoff") { if (tk.size() > 1 && parse_real4(tk[1], fv)) maxdist = fv; else { r.error(100, "cannot read 'maxdist'"); maxdist = 10.0f; } }
+        else if (k == "maxdist_optimize" || k == "cutoff_optimize") {
+            double lim = r.box_hi[0] - r.box_lo[0];
+            for (int c = 1; c < 3; ++c) lim = std::min(lim, r.box_hi[c] - r.box_lo[c]);
+            maxdist = r.box_given ? (float)(lim / 2.0) : 10.0f;
+        } else if (k == "quit") break;
+    }
+    if (nsteps > r.nsteps) nsteps = r.nsteps;
+    if (nsteps < 1) nsteps = 1;
+    if (sampling < 1) sampling = 1;
+    const int nav = std::max((nsteps - 1 + sampling) / sampling, 0);
+    printf(" Using %d timesteps in intervals of %d for averaging.\n calculating average %smolecular distances.\n", nav, sampling, mode.c_str());
+    std::vector<pa_type> types; pa_traj traj;
+    make_traj(r, types, traj);
+    std::vector<pa_dist_subjob> csj(subs.size());
+    for (size_t i = 0; i < subs.size(); ++i) {
+        csj[i].n_ref = (int)subs[i].ref.size() / 2; csj[i].n_obs = (int)subs[i].obs.size() / 2;
+        csj[i].ref = subs[i].ref.data(); csj[i].obs = subs[i].obs.data(); csj[i].weight = subs[i].weight;
+    }
+    pa_dist_job job{};
+    job.intermolecular = inter ? 1 : 0; job.nsubjobs = (int)csj.size(); job.subjobs = csj.data();
+    job.nsteps = nsteps; job.sampling_interval = sampling;
+    job.calc_exp = r.dist_calc_exp; job.calc_ffc = r.dist_calc_ffc; job.calc_stdev = stdev;
+    job.maxdist = maxdist; job.exponent = exponent;
+    std::vector<pa_dist_result> res(csj.size());
+    const int rc = pa_distance_subjobs(&traj, &job, &r.exec, res.data());
+    if (rc) { r.error(rc, std::string("GPU distance analysis failed: ") + pa_last_error()); return rc; }
+    // report_distances, Distances:1093-1143
+    printf(" Done with %smolecular distance calculation. Results:\n", mode.c_str());
+    for (size_t i = 0; i < subs.size(); ++i) {
+        printf("   Subjob #%zu out of %zu:\n     %s\n", i + 1, subs.size(), subs[i].description.c_str());
+        if (res[i].missed_neighbours > 0) printf("     %lld atoms without neighbour - consider increasing cutoff.\n", (long long)res[i].missed_neighbours);
+        else printf("     Used %lld reference atoms per step.\n", subs[i].weight);
+        formatted_distance_output("average closest distance", res[i].closest_average);
+        if (stdev) formatted_distance_output("standard deviation", res[i].closest_stdev);
+        if (r.dist_calc_exp) {
+            formatted_distance_output("exponentially weighed distance", res[i].exponential_average);
+            if (stdev) formatted_distance_output("standard deviation", res[i].exponential_stdev);
+        }
+        if (r.dist_calc_ffc) {
+            const std::string l = inter ? "d" : "r";
+            formatted_distance_output("FFC distance " + l + subs[i].el1 + subs[i].el2, res[i].ffc_average);
+            formatted_distance_output("exp(-kr) weighed FFC distance " + l + "'" + subs[i].el1 + subs[i].el2, res[i].ffcexp_average);
+            formatted_distance_output("Number of averages for FFC", res[i].ffc_weight);
+        }
+    }
+    printf(" ( reference atom(s) -> observed atom(s) )\n");
+    return 0;
+}
+
 void write_simple_sumrules(Run &r)                            // Distribution:43-67
 {
     const std::string path = r.path_in + "prealpha_simple.inp";
@@ -486,7 +700,7 @@ const char *kOtherModuleKeywords[] = {
     "time_scaling_factor", "error_output", "time_output", "set_threads", "set_threads_simple", "parallel_operation",
     "parallel_execution", "print_atom_masses", "print_atomic_weights", "print_atom_weights", "print_atom_charges",
     "print_dipole_properties", "show_drude_settings", "show_drudes", "drude_temperature", "remove_drude", "remove_core",
-    "dump_slab", "dump_slab_simple", "distance", "distances", "distance_simple", "distances_simple", "DEBUG",
+    "dump_slab", "dump_slab_simple", "distance_simple", "distances_simple", "DEBUG",
 };
 
 }  // namespace
@@ -557,6 +771,10 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             write_simple_sumrules(r);
             printf(" Distribution module invoked.\n");
             perform_distribution(r, "prealpha_simple.inp");
+        } else if (k == "distance" || k == "distances") {                    // Main:3379-3390
+            if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
+            printf(" distance module invoked.\n");
+            perform_distance(r, t[1]);
         } else if (k == "set_prefix") {
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             r.prefix = t[1];
@@ -580,10 +798,3 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
     return r.errors;
 }
 
-// row X is built in a later step of the plan: the entry point exists so that the
-// ABI is stable, and fails loudly instead of silently computing on the host.
-extern "C" int pa_distance_subjobs(const pa_traj *, const pa_dist_job *, pa_dist_result *)
-{
-    pa::set_error("pa_distance_subjobs: not implemented yet");
-    return PA_ERR_UNSUPPORTED;
-}

@@ -274,7 +274,42 @@ def case_synth():
     save("synth", res, types, [lo] * 3, [hi] * 3, jobs, res["coords"], res["elements"], extra=dict(nsteps=np.int64(12)))
 
 
-CASES = {"bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+def case_dist():
+    """K10 of SURVEY 8c (distance module, re-checked) + an intramolecular job.  Only stdout is stored: the
+    inputs are the bmim fixture's coordinates (2 identical steps)."""
+    src = os.path.join(REF, "Example_BMIMTFSI", "trajectory.xyz")
+    wd = tempfile.mkdtemp(prefix="golden_dist_")
+    one = open(src).read()
+    with open(os.path.join(wd, "traj.xyz"), "w") as f:
+        f.write(one * 2)
+    os.makedirs(os.path.join(wd, "out"))
+    with open(os.path.join(wd, "molecular.inp"), "w") as f:
+        f.write(" 2\n 2\n -1 15 512\n +1 25 512\nquit\n")
+    inputs = {
+        "inter.inp": "intermolecular 4\nF H\n2 2 O\n1 3 2 7\nN 1 1\nmaxdist 8.0\nnsteps 2\nstdev T\nffc T\naverage_exponential T\nexponent 1.5\nquit\n",
+        "intra.inp": "intramolecular 4\n2 1 5\n1 F 2\n2 3 H\nC N\nmaxdist 6.0\nnsteps 2\nsampling_interval 1\nstdev T\nffc T\naverage_exponential T\nquit\n",
+        "plain.inp": "inter 2\nO H\n2 1 1 1\ncutoff_optimize\nquit\n",
+    }
+    with open(os.path.join(wd, "general.inp"), "w") as f:
+        f.write(' "traj.xyz"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n cubic_box_edge 0.0 63.9223\n sequential_read F\n')
+        for name in inputs:
+            f.write(f' distance "{name}"\n')
+        f.write(" quit\n")
+    for name, text in inputs.items():
+        with open(os.path.join(wd, name), "w") as f:
+            f.write(text)
+    stdout, wall = orc.run_reference(wd, timeout=7200)
+    shutil.rmtree(wd)
+    assert "average closest distance: 2.658" in stdout and "average closest distance: 3.476" in stdout, stdout[-4000:]
+    d = dict(stdout=np.frombuffer(stdout.encode(), dtype=np.uint8), input_names=np.array(list(inputs)),
+             input_texts=np.array(list(inputs.values())), nsteps=np.int64(2))
+    path = os.path.join(OUT, "dist.npz")
+    np.savez_compressed(path, **d)
+    print(f"wrote {path} ({wall:.0f} s of reference time)")
+    print(stdout[stdout.find("Line 8"):][:6000])
+
+
+CASES = {"dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"
