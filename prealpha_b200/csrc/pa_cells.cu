@@ -220,7 +220,9 @@ struct PcTables {
 //            beyond the cutoff land in counters >= na, which are ignored (valid when the class "inside
 //            the cutoff, a-bin out of range" is empty and the cutoff sits on the boundary of bin na).
 // VARIANT 1: every pair is decided by the exact threshold table and an explicit cutoff test.
-template <int MX, int MY, int MZ, int VARIANT, bool VERIFY>
+// DIAG: the observed run overlaps the tile itself (symmetric pass): only pairs whose observed
+//       molecule comes later in the sorted order than the reference molecule are counted.
+template <int MX, int MY, int MZ, int VARIANT, bool VERIFY, bool DIAG>
 static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                   const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
                                                   long long jbase, int jb, int je,
@@ -300,6 +302,14 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
                     slow |= (s1hi[q] < hi_flag) ? (1 << q) : 0;
                 }
             }
+            if (DIAG) {
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const int ipos = tl.begin + (q % PC_RI) * PC_THREADS + threadIdx.x;
+                    const int jpos = jc + jj + q / PC_RI;
+                    if (!(ipos < jpos)) { ca[q] = trash; slow &= ~(1 << q); }
+                }
+            }
             if (slow) {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
@@ -318,6 +328,12 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
                                 const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
                                 if (slot < p.exc_cap)
                                     p.exc_list[slot] = make_uint2((unsigned int)(fb + p.ref_off + io), (unsigned int)(fb + p.obs_off + jo));
+                                if (p.sym || p.acc2) {
+                                    // the reversed ordered pair (reference j, observed i) is decided literally as well
+                                    const unsigned int slot2 = atomicAdd(p.exc_count2, 1u);
+                                    if (slot2 < p.exc_cap)
+                                        p.exc_list2[slot2] = make_uint2((unsigned int)(fb + p.obs_off + jo), (unsigned int)(fb + p.ref_off + io));
+                                }
                             }
                         }
                     } else if (VARIANT == 0) {
@@ -330,7 +346,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
             if (VERIFY) {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
-                    if (s1hi[q] < hi_flag || !(d2[q] < 1e29)) continue;
+                    if (s1hi[q] < hi_flag || !(d2[q] < 1e29) || ca[q] == trash) continue;
                     // exact class by binary search in the table
                     int lo_k = 0, hi_k = na + 1;
                     while (lo_k < hi_k) { const int mid = (lo_k + hi_k + 1) >> 1; if (d2[q] >= pc_lds_f64(T.thr + 8u * (unsigned)mid)) lo_k = mid; else hi_k = mid - 1; }
@@ -349,19 +365,29 @@ template <int VARIANT>
 static __device__ void pc_flush(const PaPass &p, const PcTables &T, bool reset)
 {
     const int na = T.na;
+    const long long mult = p.sym ? 2 : 1;                // symmetric pass: every unordered pair was seen once
     unsigned long long within = 0;
     for (int k = threadIdx.x; k < na + 3; k += blockDim.x) {
         const unsigned int c = pc_lds_u32(T.cnt + (unsigned)k * 4u);
         if (c) {
-            if (k < na) { atomicAdd(&p.job.acc[k], (unsigned long long)((long long)c * p.weight)); within += c; }
-            else if (VARIANT == 1 && k == na) atomicAdd(&p.job.acc[na + 1], (unsigned long long)c);   // inside the cutoff, a-bin out of range
+            if (k < na) {
+                atomicAdd(&p.job.acc[k], (unsigned long long)((long long)c * p.weight * mult));
+                if (p.acc2) atomicAdd(&p.acc2[k], (unsigned long long)((long long)c * p.weight2));
+                within += c;
+            } else if (VARIANT == 1 && k == na) {                                                   // inside the cutoff, a-bin out of range
+                atomicAdd(&p.job.acc[na + 1], (unsigned long long)((long long)c * mult));
+                if (p.acc2) atomicAdd(&p.acc2[na + 1], (unsigned long long)c);
+            }
             if (reset) pc_sts_u32(T.cnt + (unsigned)k * 4u, 0u);
         }
     }
-    if (within) atomicAdd(&p.job.acc[na], within);
+    if (within) {
+        atomicAdd(&p.job.acc[na], within * (unsigned long long)mult);
+        if (p.acc2) atomicAdd(&p.acc2[na], within);
+    }
 }
 
-template <int VARIANT, bool VERIFY>
+template <int VARIANT, bool VERIFY, bool SYM>
 __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
                                                                    const unsigned int *ntiles_ptr, unsigned int tile_cap,
                                                                    unsigned int *work_counter, int nzg)
@@ -394,7 +420,7 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
     const double cut_d2 = __longlong_as_double((long long)T.cut) * (1.0 + 1e-12);
     const float cutf = (float)fmin(cut_d2 * (1.0 + 1e-6), 3.0e38);                        // NaN ("never") -> 3e38
     const unsigned int ntiles = min(*ntiles_ptr, tile_cap);
-    if (*ntiles_ptr > tile_cap && threadIdx.x == 0 && blockIdx.x == 0) atomicOr(p.exc_count + 1, 1u);
+    if (*ntiles_ptr > tile_cap && threadIdx.x == 0 && blockIdx.x == 0) atomicOr(p.flags + 1, 1u);
     const long long n_items = (long long)ntiles * nzg;
     unsigned long long since_flush = 0;
     const int gx = go.g[0], gy = go.g[1], gz = go.g[2];
@@ -435,7 +461,7 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
             PcLayer cl;
             if (go.lay_lo[lj + k] > go.lay_hi[lj + k]) { cl.mode = 0; cl.ca = cl.cb = 1; cl.pad = 0; cl.dmin2 = 3.0e38f; }   // empty layer
             else cl = pc_classify(ilo, ihi, okey_inv(go.lay_lo[lj + k]), okey_inv(go.lay_hi[lj + k]), p.box.L[c]);
-            if (cl.mode == 3) atomicOr(p.exc_count + 1, 1u);                       // boxes too wide: host redoes the call without cells
+            if (cl.mode == 3) atomicOr(p.flags + 1, 1u);                       // boxes too wide: host redoes the call without cells
             sh->lay[c][k] = cl;
         }
         __syncthreads();
@@ -449,10 +475,15 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
 
         const long long jbase = (long long)tl.frame * go.nmol;
         const int *cs = go.cell_start + (long long)tl.frame * (go.ncell + 1);
+        // symmetric pass: rows (cy,cz) that come before the tile's own row in the sorted order are skipped,
+        // they see this tile as "after" when the roles are reversed
+        const int tile_row = tl.cz * gy + tl.cy, tile_end = tl.begin + tl.count;
         for (int cz = z0; cz < z1; ++cz) {
             const PcLayer lz = sh->lay[2][cz];
             if (!(lz.dmin2 < cutf)) continue;
+            if (SYM && cz < tl.cz) continue;
             for (int cy = 0; cy < gy; ++cy) {
+                if (SYM && cz * gy + cy < tile_row) continue;
                 const PcLayer ly = sh->lay[1][cy];
                 const float dyz2 = lz.dmin2 + ly.dmin2;
                 if (!(dyz2 < cutf)) continue;
@@ -467,16 +498,28 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
                         if (ln.mode != lx.mode || ln.ca != lx.ca || ln.cb != lx.cb || !(dyz2 + ln.dmin2 < cutf)) break;
                         ++ce;
                     }
-                    const int jb = row[cx], je = row[ce + 1];
+                    int jb = row[cx], je = row[ce + 1];
                     cx = ce + 1;
-                    if (jb == je) continue;
+                    int db = 0, de = 0;                                              // part of the run that overlaps the tile itself
+                    if (SYM && cz * gy + cy == tile_row) {
+                        if (je <= tl.begin) continue;                               // entirely before the tile
+                        db = max(jb, tl.begin); de = min(je, tile_end);
+                        jb = max(jb, tile_end);
+                    }
+                    if (jb >= je && db >= de) continue;
                     const double Lx = p.box.L[0], Ly = p.box.L[1], Lz = p.box.L[2];
                     const double sxa = (double)(lx.ca - 1) * Lx, sxb = (double)(lx.cb - 1) * Lx;
                     const double sya = (double)(ly.ca - 1) * Ly, syb = (double)(ly.cb - 1) * Ly;
                     const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
                     const int code = (lx.mode >= 2 ? 1 : 0) | (ly.mode >= 2 ? 2 : 0) | (lz.mode >= 2 ? 4 : 0);
+                    if (SYM && db < de) {
+                        // staging needs an even start so that pairs of records stay 16-byte aligned: start at db & ~1,
+                        // the extra molecule (if any) lies before the tile or inside it and is masked by ipos < jpos
+                        pc_segment<2, 2, 2, VARIANT, VERIFY, true>(p, go, gi, tl, p1x, p1y, p1z, jbase, db, de, sxa, sxb, sya, syb, sza, szb, s_j, T);
+                    }
+                    if (jb >= je) continue;
 #define PC_SEG(MX_, MY_, MZ_)                                                                                              \
-    pc_segment<MX_, MY_, MZ_, VARIANT, VERIFY>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb,  \
+    pc_segment<MX_, MY_, MZ_, VARIANT, VERIFY, false>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb,  \
                                                s_j, T)
                     switch (code) {
                     case 0: PC_SEG(1, 1, 1); break;
@@ -548,15 +591,17 @@ int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
     const size_t smem = pa_cells_smem_bytes(p.job.bin_a);
     const bool verify = p.verify_fail != nullptr;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
-#define PC_LAUNCH(O_, V_)                                                                                       \
+#define PC_LAUNCH2(O_, V_, S_)                                                                                  \
     do {                                                                                                        \
         int occ = 1;                                                                                            \
-        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
-        pa_rdf_cells_kernel<O_, V_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_, S_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
+        pa_rdf_cells_kernel<O_, V_, S_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
     } while (0)
+#define PC_LAUNCH(O_, V_) do { if (p.sym) PC_LAUNCH2(O_, V_, true); else PC_LAUNCH2(O_, V_, false); } while (0)
     if (variant == 1) { if (verify) PC_LAUNCH(1, true); else PC_LAUNCH(1, false); }
     else { if (verify) PC_LAUNCH(0, true); else PC_LAUNCH(0, false); }
+#undef PC_LAUNCH2
 #undef PC_LAUNCH
     return (int)cudaGetLastError();
 }

@@ -77,9 +77,20 @@ struct PaPass {
     int32_t n_itiles, n_jsplits, jsplit_len;
     long long weight;           // +1 or charge of the observed type (weigh_charge)
     // exception list (pairs that need the literal per-pair evaluation)
-    uint2 *exc_list;
-    unsigned int *exc_count;    // [0] appended this pass, [1] sticky overflow flag, [2] verify failures, [3] total processed
+    uint2 *exc_list;            // (reference slot, observed slot) of the pairs to evaluate literally
+    unsigned int *exc_count;    // entries appended to exc_list by this launch
     unsigned int exc_cap;
+    unsigned int *flags;        // [1] sticky error/overflow flag, [2] verify failures, [3] total exception pairs
+    // symmetric / merged passes of the cell kernel (see pa_cells.cu):
+    //   sym:  reference type == observed type and all arithmetic is exact -> every unordered pair is
+    //         evaluated once and counted twice;
+    //   acc2: a second job whose (observed, reference) types are this pass's (reference, observed) types
+    //         with the same bins: d2(i,j) == d2(j,i) bitwise, so the counts are added to both.
+    int32_t sym;
+    unsigned long long *acc2;
+    long long weight2;
+    uint2 *exc_list2;           // reversed pairs (j,i) for the second job (or the same job when sym)
+    unsigned int *exc_count2;
     unsigned int *verify_fail;  // debug counter for the class-guess invariant (may be null)
 };
 

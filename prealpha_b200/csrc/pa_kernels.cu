@@ -557,18 +557,18 @@ int pa_launch_general(const PaPass &p, int sm_count, void *stream)
 }
 
 // bookkeeping after the exception kernel of a pass: sticky overflow flag, running total, reset
-__global__ void pa_exception_finish_kernel(unsigned int *c, unsigned int cap)
+__global__ void pa_exception_finish_kernel(unsigned int *count, unsigned int *flags, unsigned int cap)
 {
-    const unsigned int n = c[0];
-    if (n > cap) c[1] = 1u;
-    c[3] += min(n, cap);
-    c[0] = 0u;
+    const unsigned int n = *count;
+    if (n > cap) flags[1] = 1u;
+    flags[3] += min(n, cap);
+    *count = 0u;
 }
 
 int pa_launch_exceptions(const PaPass &p, unsigned int /*count_hint*/, void *stream)
 {
     pa_exception_kernel<<<148, 128, 0, (cudaStream_t)stream>>>(p);
-    pa_exception_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p.exc_count, p.exc_cap);
+    pa_exception_finish_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(p.exc_count, p.flags, p.exc_cap);
     return (int)cudaGetLastError();
 }
 

@@ -86,11 +86,12 @@ struct pa_session {
     unsigned long long *d_acc = nullptr;
     size_t acc_words = 0;
     uint2 *d_exc = nullptr;
-    unsigned int *d_exc_count = nullptr;    // [0] count, [1] sticky overflow, [2] verify failures
+    unsigned int *d_exc_count = nullptr;    // [0] count, [1] sticky error flag, [2] verify failures, [3] total, [4] count of list 2
     pa_stats stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
     std::vector<TypeGrid> grids;            // cell-sorted copies of the types the RDF fast path pairs
     bool use_cells = false;
+    bool exact_ok = false;                  // resident batch: every coordinate difference is exact in fp64 (see upload)
 };
 
 namespace {
@@ -243,8 +244,8 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     PA_CK(cudaMalloc(&s->d_acc, sizeof(unsigned long long) * words));
     PA_CK(cudaMemset(s->d_acc, 0, sizeof(unsigned long long) * words));
     PA_CK(cudaMalloc(&s->d_exc, sizeof(uint2) * kExcCap));
-    PA_CK(cudaMalloc(&s->d_exc_count, sizeof(unsigned int) * 4));
-    PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 4));
+    PA_CK(cudaMalloc(&s->d_exc_count, sizeof(unsigned int) * 8));
+    PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 8));
     for (int j = 0; j < njobs; ++j) {
         JobState &js = s->jobs[j];
         const pa_job &jb = js.job;
@@ -338,6 +339,15 @@ int pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, in
         PA_CK(cudaEventSynchronize(s->ev_h2d[slot]));
         PA_CK(cudaStreamWaitEvent(s->s_copy, s->ev_done[slot], 0));
     }
+    // Exactness certificate for the symmetric passes of the cell kernel: one-atom molecules (centre of
+    // mass = the float32 coordinate), every coordinate 0 or 2^-17 <= |x| < 2^10, box bounds likewise and
+    // float32-valued.  Then all wrapped positions and image shifts are multiples of 2^-40 below 2^11, every
+    // (p2+s)-p1 needs at most 52 bits and is computed exactly, hence d2(i,j) == d2(j,i) bit for bit.
+    bool exact = s->use_cells && s->box.com_boost;
+    for (int k = 0; k < 3 && exact; ++k) {
+        for (double v : { s->box.lo[k], s->box.hi[k] })
+            if (!((double)(float)v == v && (v == 0.0 || (std::fabs(v) >= 7.62939453125e-06 && std::fabs(v) < 1024.0)))) exact = false;
+    }
     size_t poff = 0;
     for (size_t t = 0; t < s->types.size(); ++t) {
         const TypeMeta &m = s->types[t];
@@ -346,8 +356,19 @@ int pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, in
         if (!ty.xyz || ty.natoms != m.natoms || ty.nmol != m.nmol) { pa::set_error("pa_session_upload: trajectory does not match the session"); return PA_ERR_BAD_ARG; }
         const size_t ff = m.frame_floats();
         float *dst = s->h_pinned[slot] + poff;
-        for (int f = 0; f < nframes; ++f)
-            memcpy(dst + (size_t)f * ff, ty.xyz + (size_t)(first_step + (int64_t)f * step_stride) * ff, ff * sizeof(float));
+        for (int f = 0; f < nframes; ++f) {
+            const float *src = ty.xyz + (size_t)(first_step + (int64_t)f * step_stride) * ff;
+            memcpy(dst + (size_t)f * ff, src, ff * sizeof(float));
+            if (exact) {
+                unsigned int bad = 0;
+                const uint32_t *u = reinterpret_cast<const uint32_t *>(src);
+                for (size_t i = 0; i < ff; ++i) {
+                    const uint32_t a = u[i] & 0x7fffffffu;                     // |x| as bits: 2^-17 = 0x37000000, 2^10 = 0x44800000
+                    bad |= (unsigned)((a != 0u) & ((a < 0x37000000u) | (a >= 0x44800000u)));
+                }
+                if (bad) exact = false;
+            }
+        }
         PA_CK(cudaMemcpyAsync(s->d_raw[slot][t], dst, sizeof(float) * ff * nframes, cudaMemcpyHostToDevice, s->s_copy));
         s->stats.h2d_bytes += (int64_t)(sizeof(float) * ff * nframes);
         poff += ff * (size_t)s->max_frames;
@@ -356,6 +377,7 @@ int pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, in
     s->slot_used[slot] = true;
     s->cur = slot;
     s->nframes = nframes;
+    s->exact_ok = exact;
     return 0;
 }
 
@@ -388,55 +410,107 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         s->stats.kernel_launches += 3;
     }
     const long long target_items = (long long)s->sm_count * 16;
-    for (JobState &js : s->jobs) {
-        const pa_job &jb = js.job;
+    // ---- plan: one pass per (job, observed type), Distribution:727-735 ---------------------------------
+    struct Plan { int job, r, o; bool cells; bool sym; int partner; bool skip; };
+    std::vector<Plan> plan;
+    for (size_t j = 0; j < s->jobs.size(); ++j) {
+        const pa_job &jb = s->jobs[j].job;
         const int r = jb.ref_type - 1;
         const int o_first = jb.obs_type < 1 ? 0 : jb.obs_type - 1;
         const int o_last = jb.obs_type < 1 ? (int)s->types.size() - 1 : jb.obs_type - 1;
-        for (int o = o_first; o <= o_last; ++o) {                 // Distribution:727-735
-            PaPass p{};
-            p.pts = s->pts; p.box = s->box; p.job = js.dj;
-            p.nframes = count; p.frame0 = first;
-            p.ref_off = s->types[r].offset; p.nref = s->types[r].nmol;
-            p.obs_off = s->types[o].offset; p.nobs = s->types[o].nmol;
-            p.same_type = (r == o) ? 1 : 0;
-            p.weight = jb.weigh_charge ? (long long)s->types[o].charge : 1ll;   // Distribution:833-838
-            const int ri = js.fast ? pa_rdf_ri(p.nref) : pa_general_ri(p.nref);
-            const int ti = PA_TILE_THREADS * ri;
-            p.n_itiles = (p.nref + ti - 1) / ti;
-            const long long items0 = (long long)p.nframes * p.n_itiles;
-            const int max_splits = (p.nobs + PA_J_CHUNK - 1) / PA_J_CHUNK;
-            long long want = items0 >= target_items ? 1 : (target_items + items0 - 1) / items0;
-            if (want > max_splits) want = max_splits;
-            int len = (int)((p.nobs + want - 1) / want);
-            len = ((len + PA_J_CHUNK - 1) / PA_J_CHUNK) * PA_J_CHUNK;
-            p.jsplit_len = len;
-            p.n_jsplits = (p.nobs + len - 1) / len;
-            p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = kExcCap;
-            p.verify_fail = s->verify ? s->d_exc_count + 2 : nullptr;
-            if (js.fast && s->grids[r].enabled && s->grids[o].enabled) {
-                TypeGrid &gr = s->grids[r];
-                if (!gr.tiles_ready) {
-                    PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, gr.tiles, gr.counters, gr.tile_cap, s->s_compute));
-                    gr.tiles_ready = true;
-                    s->stats.kernel_launches += 1;
-                }
-                const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 230 + 1));
-                long long nzg = (20ll * s->sm_count * 5 + tiles_est - 1) / tiles_est;
-                nzg = std::max<long long>(1, std::min<long long>(nzg, s->grids[o].g.g[2]));
-                PA_CK((cudaError_t)pa_launch_rdf_cells(p, gr.g, s->grids[o].g, gr.tiles, gr.counters, gr.tile_cap, gr.counters + 1,
-                                                       (int)nzg, js.cells_variant, s->sm_count, s->s_compute));
-                PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
-                s->stats.kernel_launches += 3;
-            } else if (js.fast) {
-                PA_CK((cudaError_t)pa_launch_rdf_fast(p, s->sm_count, s->s_compute));
-                PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
-                s->stats.kernel_launches += 3;
-            } else {
-                PA_CK((cudaError_t)pa_launch_general(p, s->sm_count, s->s_compute));
+        for (int o = o_first; o <= o_last; ++o) {
+            Plan pl{ (int)j, r, o, false, false, -1, false };
+            pl.cells = s->jobs[j].fast && s->grids[r].enabled && s->grids[o].enabled;
+            plan.push_back(pl);
+        }
+    }
+    // When every coordinate difference is exact in fp64 (certificate computed at upload time),
+    // d2(i,j) == d2(j,i) bit for bit: a same-type pass evaluates every unordered pair once, and the pass
+    // (A around B) of one job doubles as the pass (B around A) of another job with the same bins.
+    if (s->exact_ok && !(s->exec.flags & PA_EXEC_NO_SYMMETRY)) {
+        for (size_t a = 0; a < plan.size(); ++a) {
+            Plan &pa_ = plan[a];
+            if (!pa_.cells || pa_.skip) continue;
+            if (pa_.r == pa_.o) { pa_.sym = true; continue; }
+            if (pa_.partner >= 0) continue;
+            for (size_t b2 = a + 1; b2 < plan.size(); ++b2) {
+                Plan &pb = plan[b2];
+                if (!pb.cells || pb.skip || pb.partner >= 0 || pb.r != pa_.o || pb.o != pa_.r) continue;
+                const pa_job &ja = s->jobs[pa_.job].job, &jb2 = s->jobs[pb.job].job;
+                if (ja.bin_a != jb2.bin_a || ja.maxdist != jb2.maxdist || ja.step_a != jb2.step_a ||
+                    s->jobs[pa_.job].cells_variant != s->jobs[pb.job].cells_variant) continue;
+                pa_.partner = (int)b2; pb.skip = true;
+                break;
+            }
+        }
+    }
+    auto fill_pass = [&](PaPass &p, const JobState &js, int r, int o) {
+        const pa_job &jb = js.job;
+        p.pts = s->pts; p.box = s->box; p.job = js.dj;
+        p.nframes = count; p.frame0 = first;
+        p.ref_off = s->types[r].offset; p.nref = s->types[r].nmol;
+        p.obs_off = s->types[o].offset; p.nobs = s->types[o].nmol;
+        p.same_type = (r == o) ? 1 : 0;
+        p.weight = jb.weigh_charge ? (long long)s->types[o].charge : 1ll;   // Distribution:833-838
+        p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = kExcCap / 2; p.flags = s->d_exc_count;
+        p.exc_list2 = s->d_exc + kExcCap / 2; p.exc_count2 = s->d_exc_count + 4;
+        p.verify_fail = s->verify ? s->d_exc_count + 2 : nullptr;
+    };
+    for (const Plan &pl : plan) {
+        const JobState &js = s->jobs[pl.job];
+        const int r = pl.r, o = pl.o;
+        PaPass p{};
+        fill_pass(p, js, r, o);
+        s->stats.pairs_evaluated += (int64_t)p.nframes * ((int64_t)p.nref * p.nobs - (p.same_type ? p.nref : 0));
+        if (pl.skip) continue;                                     // counted by its partner's launch
+        const int ri = js.fast ? pa_rdf_ri(p.nref) : pa_general_ri(p.nref);
+        const int ti = PA_TILE_THREADS * ri;
+        p.n_itiles = (p.nref + ti - 1) / ti;
+        const long long items0 = (long long)p.nframes * p.n_itiles;
+        const int max_splits = (p.nobs + PA_J_CHUNK - 1) / PA_J_CHUNK;
+        long long want = items0 >= target_items ? 1 : (target_items + items0 - 1) / items0;
+        if (want > max_splits) want = max_splits;
+        int len = (int)((p.nobs + want - 1) / want);
+        len = ((len + PA_J_CHUNK - 1) / PA_J_CHUNK) * PA_J_CHUNK;
+        p.jsplit_len = len;
+        p.n_jsplits = (p.nobs + len - 1) / len;
+        if (pl.cells) {
+            TypeGrid &gr = s->grids[r];
+            if (!gr.tiles_ready) {
+                PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, gr.tiles, gr.counters, gr.tile_cap, s->s_compute));
+                gr.tiles_ready = true;
                 s->stats.kernel_launches += 1;
             }
-            s->stats.pairs_evaluated += (int64_t)p.nframes * ((int64_t)p.nref * p.nobs - (p.same_type ? p.nref : 0));
+            PaPass p2{};
+            p.sym = pl.sym ? 1 : 0;
+            if (pl.partner >= 0) {
+                const Plan &pb = plan[pl.partner];
+                fill_pass(p2, s->jobs[pb.job], pb.r, pb.o);
+                p.acc2 = p2.job.acc; p.weight2 = p2.weight;
+                p2.exc_list = p.exc_list2; p2.exc_count = p.exc_count2;     // reversed pairs go through the partner's job
+            }
+            const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 230 + 1));
+            long long nzg = (20ll * s->sm_count * 5 + tiles_est - 1) / tiles_est;
+            nzg = std::max<long long>(1, std::min<long long>(nzg, s->grids[o].g.g[2]));
+            PA_CK((cudaError_t)pa_launch_rdf_cells(p, gr.g, s->grids[o].g, gr.tiles, gr.counters, gr.tile_cap, gr.counters + 1,
+                                                   (int)nzg, js.cells_variant, s->sm_count, s->s_compute));
+            PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
+            s->stats.kernel_launches += 3;
+            if (pl.sym) {                                           // reversed pairs of the same job
+                PaPass ps = p; ps.exc_list = p.exc_list2; ps.exc_count = p.exc_count2;
+                PA_CK((cudaError_t)pa_launch_exceptions(ps, 0, s->s_compute));
+                s->stats.kernel_launches += 2;
+            } else if (pl.partner >= 0) {
+                PA_CK((cudaError_t)pa_launch_exceptions(p2, 0, s->s_compute));
+                s->stats.kernel_launches += 2;
+            }
+        } else if (js.fast) {
+            PA_CK((cudaError_t)pa_launch_rdf_fast(p, s->sm_count, s->s_compute));
+            PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
+            s->stats.kernel_launches += 3;
+        } else {
+            PA_CK((cudaError_t)pa_launch_general(p, s->sm_count, s->s_compute));
+            s->stats.kernel_launches += 1;
         }
     }
     PA_CK(cudaEventRecord(e1, s->s_compute));
@@ -484,7 +558,7 @@ int pa_session_download(pa_session *s, int64_t *const *hists, int64_t *within_bi
     s->stats.pairs_binned = binned;
     if (reset) {
         PA_CK(cudaMemset(s->d_acc, 0, sizeof(unsigned long long) * s->acc_words));
-        PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 4));
+        PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 8));
     }
     if (flags[1]) {
         pa::set_error("exception list overflow: too many pairs (anti)parallel to the reference axis; rerun with PA_EXEC_FORCE_GENERAL");

@@ -191,13 +191,20 @@ def test_cell_sorted_kernel_against_oracle(name, kw, oracle):
     traj = _big_system(**kw)
     reqs = [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
             dict(mode="pdf", ref_type=2, obs_type=2, bin_a=300, bin_b=1, maxdist=17.25),
-            dict(mode="pdf", vec=(0, 0, -1), ref_type=2, obs_type=1, bin_a=64, bin_b=1, maxdist_optimize=True, weigh_charge=True)]
+            dict(mode="pdf", vec=(0, 0, -1), ref_type=2, obs_type=1, bin_a=64, bin_b=1, maxdist_optimize=True, weigh_charge=True),
+            # same bins as job 0 with the roles of the types swapped: its (2 around 1) pass is merged into
+            # job 0's (1 around 2) pass when the arithmetic is provably exact (cubic float32 boxes)
+            dict(mode="pdf", vec=(0, 0, -1), ref_type=2, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True, weigh_charge=True)]
     pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
     cells = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY))
+    nosym = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY | capi.PA_EXEC_NO_SYMMETRY))
     brute = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY | capi.PA_EXEC_NO_CELLS))
     assert cells[3].kernel_launches != brute[3].kernel_launches      # the cell path really ran
+    if name != "lmp_box_2frames":
+        assert cells[3].kernel_launches != nosym[3].kernel_launches  # ... and so did the symmetric / merged passes
     for k, job in enumerate(pjobs):
         assert np.array_equal(cells[0][k], brute[0][k]) and cells[1][k] == brute[1][k] and cells[2][k] == brute[2][k], (name, k)
+        assert np.array_equal(cells[0][k], nosym[0][k]) and cells[1][k] == nosym[1][k] and cells[2][k] == nosym[2][k], (name, k)
     for k in (1, 2) if name != "lmp_box_2frames" else (1,):          # keep the CPU oracle time bounded
         h0, w0, o0 = oracle.histogram(traj, pjobs[k])
         assert np.array_equal(cells[0][k], h0) and (int(cells[1][k]), int(cells[2][k])) == (w0, o0), (name, k)
