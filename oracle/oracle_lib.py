@@ -36,6 +36,7 @@ _SIG = {
     "orc_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
     "orc_distance_subjobs": (C.c_int, [C.POINTER(capi.pa_traj), C.POINTER(capi.pa_dist_job), C.POINTER(capi.pa_dist_result)]),
     "orc_read_xyz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_char_p]),
+    "orc_read_traj": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_char_p]),
 }
 _lib = None
 
@@ -104,10 +105,10 @@ def format_real4(x) -> str:
     return buf.value.decode()
 
 
-def read_xyz(path, natoms_total, nsteps):
+def read_xyz(path, natoms_total, nsteps, header_lines=2):
     out = np.zeros((nsteps, natoms_total, 3), dtype=np.float32)
     el = C.create_string_buffer(natoms_total * 4)
-    rc = load().orc_read_xyz(path.encode(), natoms_total, nsteps, out.ctypes.data_as(C.POINTER(C.c_float)), el)
+    rc = load().orc_read_traj(path.encode(), natoms_total, nsteps, header_lines, out.ctypes.data_as(C.POINTER(C.c_float)), el)
     if rc != 0:
         raise RuntimeError(f"orc_read_xyz({path}) -> {rc}")
     elements = [el.raw[i * 4:i * 4 + 4].split(b"\0")[0].decode() for i in range(natoms_total)]
@@ -175,6 +176,19 @@ def write_xyz(path, elements, frames, fmt="%.5f"):
         n = len(elements)
         for s in range(frames.shape[0]):
             f.write(f"{n}\nstep {s}\n")
+            fr = frames[s]
+            f.write("".join(f"{elements[a]} {fmt % fr[a, 0]} {fmt % fr[a, 1]} {fmt % fr[a, 2]}\n" for a in range(n)))
+
+
+def write_lmp(path, elements, frames, box_lo, box_hi, fmt="%.6f"):
+    """LAMMPS dump with the 9 header lines the reference expects (Molecular:4833-4871)."""
+    with open(path, "w") as f:
+        n = len(elements)
+        for s in range(frames.shape[0]):
+            f.write(f"ITEM: TIMESTEP\n{s * 1000}\nITEM: NUMBER OF ATOMS\n{n}\nITEM: BOX BOUNDS pp pp pp\n")
+            for k in range(3):
+                f.write(f"{float(box_lo[k])!r} {float(box_hi[k])!r}\n")
+            f.write("ITEM: ATOMS element xu yu zu\n")
             fr = frames[s]
             f.write("".join(f"{elements[a]} {fmt % fr[a, 0]} {fmt % fr[a, 1]} {fmt % fr[a, 2]}\n" for a in range(n)))
 

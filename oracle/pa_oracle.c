@@ -569,13 +569,20 @@ int orc_abi_version(void) { return PA_ABI_VERSION; }
  * :5032-5046 (`READ(3,*) element_name, coordinates`): element token, then three
  * REAL(4) items converted decimal->float32 directly (strtof), rest of line ignored.
  * out: [nsteps][natoms_total][3]; elements: [natoms_total][4] from frame 1. */
+int orc_read_traj(const char *path, int natoms_total, int nsteps, int header_lines, float *out, char *elements);
 int orc_read_xyz(const char *path, int natoms_total, int nsteps, float *out, char *elements)
+{
+    return orc_read_traj(path, natoms_total, nsteps, 2, out, elements);
+}
+/* header_lines = 2 (xyz, Molecular:4873) or 9 (lmp, Molecular:4835) */
+int orc_read_traj(const char *path, int natoms_total, int nsteps, int header_lines, float *out, char *elements)
 {
     FILE *f = fopen(path, "r");
     if (!f) return PA_ERR_IO;
     char *line = NULL; size_t cap = 0;
     for (int s = 0; s < nsteps; ++s) {
-        if (getline(&line, &cap, f) < 0 || getline(&line, &cap, f) < 0) { fclose(f); free(line); return 84; }
+        for (int h = 0; h < header_lines; ++h)
+            if (getline(&line, &cap, f) < 0) { fclose(f); free(line); return 84; }
         for (int a = 0; a < natoms_total; ++a) {
             if (getline(&line, &cap, f) < 0) { fclose(f); free(line); return 84; }
             char *p = line;

@@ -91,6 +91,7 @@ struct pa_session {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
     std::vector<TypeGrid> grids;            // cell-sorted copies of the types the RDF fast path pairs
     bool use_cells = false;
+    unsigned int exc_cap = kExcCap;         // entries of the exception list (both halves together)
     bool exact_ok = false;                  // resident batch: every coordinate difference is exact in fp64 (see upload)
 };
 
@@ -152,6 +153,7 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     s->device = ex.device; s->exec = ex;
     s->force_general = (ex.flags & PA_EXEC_FORCE_GENERAL) != 0;
     s->verify = (ex.flags & 0x100) != 0;
+    if (ex.flags & 0x200) s->exc_cap = 2048;          // test hook: tiny exception list to exercise the overflow fallback
     cudaDeviceProp prop;
     PA_CK(cudaGetDeviceProperties(&prop, ex.device));
     s->sm_count = prop.multiProcessorCount;
@@ -452,8 +454,8 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         p.obs_off = s->types[o].offset; p.nobs = s->types[o].nmol;
         p.same_type = (r == o) ? 1 : 0;
         p.weight = jb.weigh_charge ? (long long)s->types[o].charge : 1ll;   // Distribution:833-838
-        p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = kExcCap / 2; p.flags = s->d_exc_count;
-        p.exc_list2 = s->d_exc + kExcCap / 2; p.exc_count2 = s->d_exc_count + 4;
+        p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = s->exc_cap / 2; p.flags = s->d_exc_count;
+        p.exc_list2 = s->d_exc + s->exc_cap / 2; p.exc_count2 = s->d_exc_count + 4;
         p.verify_fail = s->verify ? s->d_exc_count + 2 : nullptr;
     };
     for (const Plan &pl : plan) {

@@ -27,6 +27,7 @@ class Fixture:
         self.files = {str(fn): z[f"file_{i}"].tobytes() for i, fn in enumerate(z["file_names"])}
         self.stdout = z["stdout"].tobytes().decode()
         self.atom_charges = [z[f"atom_charge_{i}"] for i in range(len(self.types))] if "atom_charge_0" in z.files else None
+        self.lmp = "lmp" in z.files
 
     def trajectory(self) -> capi.Trajectory:
         tl, off = [], 0
@@ -38,7 +39,7 @@ class Fixture:
                 d["atom_charge"] = self.atom_charges[ti]
             tl.append(d)
             off += n
-        return capi.Trajectory(tl, self.box_lo, self.box_hi, xyz_format=True)
+        return capi.Trajectory(tl, self.box_lo, self.box_hi, xyz_format=not self.lmp)
 
     def jobs(self):
         """[(job_name, reference_number (1-based within its input file), pa_job_request, (within, oob))]"""
@@ -54,7 +55,7 @@ class Fixture:
         return {fn[len(pre):]: c for fn, c in self.files.items() if fn.startswith(pre)}
 
 
-ALL = ["bmim", "re4", "re4_atoms", "synth"]
+ALL = ["bmim", "re4", "re4_atoms", "synth", "lmp"]
 
 
 def available():

@@ -84,9 +84,7 @@ def run_case(name, traj_path, traj_type, types, nsteps, box, jobs, natoms_total,
             for k, v in expect.items():
                 assert counts[k] == v, (name, k, counts[k], v)
         files = {fn: open(os.path.join(wd, "out", fn), "rb").read() for fn in sorted(os.listdir(os.path.join(wd, "out")))}
-        coords, elements = None, None
-        if traj_type == "xyz":
-            coords, elements = orc.read_xyz(os.path.join(wd, tname), natoms_total, nsteps)
+        coords, elements = orc.read_xyz(os.path.join(wd, tname), natoms_total, nsteps, header_lines=2 if traj_type == "xyz" else 9)
         return dict(stdout=stdout, counts=counts, files=files, texts=texts, coords=coords, elements=elements, wall=wall)
     finally:
         shutil.rmtree(wd, ignore_errors=True)
@@ -309,7 +307,39 @@ def case_dist():
     print(stdout[stdout.find("Line 8"):][:6000])
 
 
-CASES = {"dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+def case_lmp():
+    """LAMMPS-format trajectory: orthorhombic box with full-double bounds read from the file (Molecular:4851-4857),
+    molecules straddling the box, many decimals -> the (i,j)/(j,i) arithmetic is NOT exact here."""
+    rng = np.random.default_rng(4242)
+    nsteps = 11
+    lo = np.array([-3.127893456123, 0.25, 1.0 / 3.0]); hi = lo + np.array([22.71828182845, 25.3141592653, 21.0123456789])
+    types = [(-1, 3, 150), (+1, 1, 90), (+2, 1, 30), (0, 5, 60)]
+    els = [["O", "H", "H"], ["Na"], ["Mg"], ["C", "H", "H", "H", "H"]]
+    frames, elements = [], []
+    for (ch, na, nm), e in zip(types, els):
+        elements += e * nm
+    for s in range(nsteps):
+        fr = []
+        for (ch, na, nm), e in zip(types, els):
+            centre = lo + rng.random((nm, 1, 3)) * (hi - lo) * 1.6 - 0.3 * (hi - lo)
+            fr.append((centre + (rng.random((nm, na, 3)) - 0.5) * 2.4).reshape(-1, 3))
+        frames.append(np.concatenate(fr))
+    frames = np.stack(frames)
+    tmp = tempfile.mkdtemp()
+    p = os.path.join(tmp, "traj.lmp")
+    orc.write_lmp(p, elements, frames, lo, hi)
+    jobs = [
+        ("l1", "pdf", [(Z, 1, -1), (Z, 2, 2), ((0, 0, -1), 4, 1)], dict(maxdist_optimize=True, weigh_charge=True, sampling_interval=1,
+                                                                    bin_count_a=250, bin_count_b=1)),
+        ("l2", "pdf", [((1, 1, 1), 1, 4), (Z, 3, 1)], dict(maxdist="9.5", sampling_interval=2, bin_count_a=20, bin_count_b=15)),
+        ("l3", "cdf", [((1, 0, 1), 2, 1), (Z, 4, -1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=18, bin_count_b=22)),
+    ]
+    res = run_case("lmp", p, "lmp", types, nsteps, None, jobs, len(elements))
+    shutil.rmtree(tmp)
+    save("lmp", res, types, lo, hi, jobs, res["coords"], res["elements"], extra=dict(nsteps=np.int64(nsteps), lmp=np.int64(1)))
+
+
+CASES = {"lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"

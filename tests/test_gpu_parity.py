@@ -225,16 +225,22 @@ def test_wrap_trajectory_switch(oracle):
         assert np.array_equal(hists[k], h0) and (within[k], oob[k]) == (w0, o0)
 
 
-def test_cli_drop_in_end_to_end(oracle, tmp_path):
-    """general.inp -> molecular.inp -> xyz text -> GPU -> output files, compared with the oracle's writers
-    and (for the synth fixture text) with the reference binary's committed files."""
-    fx = fixtures.Fixture("synth")
+@pytest.mark.parametrize("name", ["synth", "lmp"])
+def test_cli_drop_in_end_to_end(name, oracle, tmp_path):
+    """general.inp -> molecular.inp -> xyz / lmp text -> GPU -> output files: byte-identical to what the
+    reference binary wrote for the same inputs (tests/golden), same `within bin` / `out of bounds` lines."""
+    fx = fixtures.Fixture(name)
     wd = tmp_path / "run"
     (wd / "out").mkdir(parents=True)
-    # the fixture coordinates are 5-decimal values: "%.5f" reproduces the original text exactly
-    oracle.write_xyz(str(wd / "syn.xyz"), fx.elements, fx.coords.astype(np.float64))
+    # %.9g round-trips every float32 exactly, so the CLI parses the very coordinates the binary parsed
+    if fx.lmp:
+        oracle.write_lmp(str(wd / "traj.lmp"), fx.elements, fx.coords.astype(np.float64), fx.box_lo, fx.box_hi, fmt="%.9g")
+        tname, box_line = "traj.lmp", ""
+    else:
+        oracle.write_xyz(str(wd / "traj.xyz"), fx.elements, fx.coords.astype(np.float64), fmt="%.9g")
+        tname, box_line = "traj.xyz", f" cubic_box_edge {float(fx.box_lo[0])!r} {float(fx.box_hi[0])!r}\n"
     (wd / "molecular.inp").write_text(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + "quit\n")
-    gen = ' "syn.xyz"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n cubic_box_edge 0.0 30.0\n sequential_read F\n set_threads 8\n'
+    gen = f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n{box_line} sequential_read F\n set_threads 8\n'
     for jn, text in zip(fx.job_names, fx.job_texts):
         (wd / f"{jn}.inp").write_text(text)
         gen += f' set_prefix "{jn}_"\n distribution "{jn}.inp"\n'
@@ -250,3 +256,83 @@ def test_cli_drop_in_end_to_end(oracle, tmp_path):
     assert set(produced) == set(fx.files)
     for fn, content in produced.items():
         assert content == fx.files[fn], fn
+
+
+def test_exception_list_overflow_falls_back(oracle):
+    """A perfect lattice has whole columns of atoms sharing (x,y): every pair of a column is (anti)parallel to
+    z.  With a tiny exception list (test hook 0x200) the fast kernels overflow and the call is redone with
+    the general kernel; the result must not change."""
+    n = 12
+    g = np.arange(n) * 2.0 + 0.5
+    pts = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    rng = np.random.default_rng(3)
+    pts = pts[rng.permutation(len(pts))]
+    half = len(pts) // 2
+    tl = [dict(charge=+1, natoms=1, nmol=half, elements=["Na"], xyz=pts[None, :half].reshape(1, half, 1, 3)),
+          dict(charge=-1, natoms=1, nmol=half, elements=["Cl"], xyz=pts[None, half:].reshape(1, half, 1, 3))]
+    lo, hi = capi.cubic_box_edge(0.0, 24.0)
+    traj = capi.Trajectory(tl, lo, hi)
+    job = api.job_setup(traj, capi.make_request(mode="pdf", ref_type=1, obs_type=-1, bin_a=120, bin_b=1, maxdist_optimize=True, sampling_interval=1))
+    h0, w0, o0 = oracle.histogram(traj, job)
+    assert o0 > 2048
+    normal = api.histogram_multi(traj, [job])
+    tiny = api.histogram_multi(traj, [job], api.make_exec(flags=0x200))
+    for res in (normal, tiny):
+        assert np.array_equal(res[0][0], h0) and (int(res[1][0]), int(res[2][0])) == (w0, o0)
+    assert normal[3].exception_pairs > 0 and tiny[3].exception_pairs == 0      # general kernel: no exception list
+
+
+def test_degenerate_inputs(oracle):
+    rng = np.random.default_rng(8)
+    xyz1 = (rng.random((3, 1, 1, 3)) * 10).astype(np.float32)
+    xyz2 = (rng.random((3, 40, 2, 3)) * 10).astype(np.float32)
+    xyz2[1, 7, 0, 1] = np.nan                                 # a NaN coordinate: never inside the cutoff, nothing crashes
+    tl = [dict(charge=0, natoms=1, nmol=1, elements=["Ar"], xyz=xyz1), dict(charge=0, natoms=2, nmol=40, elements=["N", "N"], xyz=xyz2)]
+    lo, hi = capi.cubic_box_edge(0.0, 10.0)
+    traj = capi.Trajectory(tl, lo, hi)
+    reqs = [dict(mode="pdf", ref_type=1, obs_type=1, bin_a=1, bin_b=1, maxdist_optimize=True),          # one molecule: no pairs at all
+            dict(mode="pdf", ref_type=1, obs_type=2, bin_a=1000, bin_b=1, maxdist=4.99),
+            dict(mode="pdf", ref_type=2, obs_type=-1, bin_a=1, bin_b=1000, maxdist=1e-3),               # cutoff so small that nothing is binned
+            dict(mode="cdf", ref_type=2, obs_type=2, bin_a=1000, bin_b=1, maxdist_optimize=True)]
+    for si in (1, 2, 7):                                      # sampling interval larger than the trajectory: frame 1 only
+        pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=si, **r)) for r in reqs]
+        hists, within, oob, st = api.histogram_multi(traj, pjobs)
+        assert st.frames_done == (3 + si - 1) // si
+        assert within[0] == 0 and oob[0] == 0 and not hists[0].any()
+        for k, job in enumerate(pjobs):
+            h0, w0, o0 = oracle.histogram(traj, job)
+            assert np.array_equal(hists[k], h0) and (int(within[k]), int(oob[k])) == (w0, o0), (si, k)
+
+
+def test_error_codes():
+    import ctypes as C
+    fx = fixtures.Fixture("synth")
+    traj = fx.trajectory()
+    lib = capi.load()
+    job = api.job_setup(traj, fx.jobs()[0][2])
+    hist = np.zeros(job.bin_a * job.bin_b, dtype=np.int64)
+    w, o = C.c_int64(0), C.c_int64(0)
+    bad = capi.pa_job(); C.memmove(C.byref(bad), C.byref(job), C.sizeof(capi.pa_job)); bad.ref_type = 9
+    assert lib.pa_distribution_histogram(traj.ptr, C.byref(bad), hist.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(w), C.byref(o)) == 33
+    bad.ref_type = 1; bad.bin_a = 0
+    assert lib.pa_distribution_histogram(traj.ptr, C.byref(bad), hist.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(w), C.byref(o)) == capi.PA_ERR_BAD_ARG
+    rq = capi.make_request(vec=(0, 0, 0), sampling_interval=1)          # randomised reference vector: undefined in the reference
+    j2 = capi.pa_job()
+    assert lib.pa_job_setup(traj.ptr, C.byref(rq), C.byref(j2)) == capi.PA_ERR_UNSUPPORTED
+    rq = capi.make_request(ref_type=3, sampling_interval=1)
+    assert lib.pa_job_setup(traj.ptr, C.byref(rq), C.byref(j2)) == 33
+
+
+def test_cli_rejects_short_trajectories(oracle, tmp_path):
+    """perform_distribution_analysis refuses trajectories with fewer than 11 steps (error 37, Distribution:1191)."""
+    wd = tmp_path
+    rng = np.random.default_rng(0)
+    oracle.write_xyz(str(wd / "t.xyz"), ["Ar"] * 20, rng.random((5, 20, 3)) * 9.0)
+    (wd / "molecular.inp").write_text(" 5\n 1\n +0 1 20\nquit\n")
+    (wd / "d.inp").write_text("pdf 1\n+0 +0 +1 1 1\nmaxdist_optimize\nquit\n")
+    (wd / "general.inp").write_text(' "t.xyz"\n "molecular.inp"\n "./"\n "./"\n "./"\n cubic_box_edge 0.0 9.0\n distribution "d.inp"\n nonsense_keyword\n quit\n')
+    cli = os.path.join(os.path.dirname(capi.LIB_PATH), "prealpha_b200_cli")
+    p = subprocess.run([cli, "general.inp"], cwd=wd, capture_output=True, timeout=120)
+    out = p.stdout.decode()
+    assert p.returncode == 1 and "ERROR 37" in out and "ERROR 20" in out
+    assert not [f for f in os.listdir(wd) if f.startswith("reference_")]
