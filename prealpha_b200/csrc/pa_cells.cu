@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "pa_internal.h"
+#include "pa_pair_exact.cuh"
 
 #define PC_THREADS 128
 #define PC_RI 2
@@ -541,6 +542,189 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
 }
 
 // ---------------------------------------------------------------------------
+// Cell-sorted GENERAL kernel (2-D pdf, cdf, centre of charge, any reference vector).  Same tiles,
+// same per-run image classification and cutoff pruning as above; a pair inside the cutoff gets the
+// literal evaluation (pa_eval_pair_exact) through its original slots.  With cutoffs well below L/2
+// (the usual 2-D case) almost all cell runs are skipped, which is where the speed-up comes from.
+template <int MODE, bool SMEM_HIST>
+static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                                  const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
+                                                  const int (&iorig)[PC_RI], long long jbase, int jb, int je,
+                                                  double sxa, double sxb, double sya, double syb, double sza, double szb,
+                                                  double *s_j, int *s_jo, unsigned int *s_hist, int nbins,
+                                                  unsigned long long &g_within, unsigned long long &g_oob)
+{
+    const unsigned long long cut = p.job.cut_bits;
+    const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+    for (int jc = jb; jc < je; jc += PC_JC) {
+        __syncthreads();
+        {
+            const int t = threadIdx.x;
+            const int j = jc + t;
+            double x = 1.0e15, y = 1.0e15, z = 1.0e15;
+            int o = -1;
+            if (j < je) { x = go.sx[jbase + j]; y = go.sy[jbase + j]; z = go.sz[jbase + j]; o = go.sorig[jbase + j]; }
+            double *rec = s_j + t * 6;
+            rec[0] = __dadd_rn(x, sxa); rec[1] = __dadd_rn(x, sxb);
+            rec[2] = __dadd_rn(y, sya); rec[3] = __dadd_rn(y, syb);
+            rec[4] = __dadd_rn(z, sza); rec[5] = __dadd_rn(z, szb);
+            s_jo[t] = o;
+        }
+        __syncthreads();
+        const int cnt = min(PC_JC, je - jc);
+        for (int jj = 0; jj < cnt; ++jj) {
+            const double2 *rec = reinterpret_cast<const double2 *>(s_j + jj * 6);
+            const double2 rx = rec[0], ry = rec[1], rz = rec[2];
+#pragma unroll
+            for (int r = 0; r < PC_RI; ++r) {
+                const double sx = pc_comp_sq<MODE>(rx.x, rx.y, p1x[r]);
+                const double sy = pc_comp_sq<MODE>(ry.x, ry.y, p1y[r]);
+                const double sz = pc_comp_sq<MODE>(rz.x, rz.y, p1z[r]);
+                const double d2 = __dadd_rn(__dadd_rn(sx, sy), sz);
+                if (dbits(d2) < cut) {
+                    const int jo = s_jo[jj];
+                    if (iorig[r] < 0 || (p.same_type && iorig[r] == jo)) continue;          // padding lane / Distribution:778
+                    int bin = 0;
+                    const int st = pa_eval_pair_exact(p, fb + p.ref_off + iorig[r], fb + p.obs_off + jo, &bin);
+                    if (SMEM_HIST) {
+                        if (st == 1) atomicAdd(&s_hist[bin], 1u);
+                        else if (st == 2) atomicAdd(&s_hist[nbins], 1u);
+                    } else {
+                        if (st == 1) { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
+                        else if (st == 2) ++g_oob;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <bool SMEM_HIST>
+static __device__ void pg_flush(const PaPass &p, unsigned int *s_hist, int nbins, bool reset)
+{
+    unsigned long long within = 0;
+    for (int k = threadIdx.x; k < nbins + 1; k += blockDim.x) {
+        const unsigned int c = s_hist[k];
+        if (c) {
+            if (k < nbins) { atomicAdd(&p.job.acc[k], (unsigned long long)((long long)c * p.weight)); within += c; }
+            else atomicAdd(&p.job.acc[nbins + 1], (unsigned long long)c);
+            if (reset) s_hist[k] = 0u;
+        }
+    }
+    if (within) atomicAdd(&p.job.acc[nbins], within);
+}
+
+template <bool SMEM_HIST>
+__global__ void __launch_bounds__(PC_THREADS) pa_general_cells_kernel(const __grid_constant__ PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
+                                                                       const unsigned int *ntiles_ptr, unsigned int tile_cap,
+                                                                       unsigned int *work_counter, int nzg)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nbins = p.job.bin_a * p.job.bin_b;
+    double *s_j = reinterpret_cast<double *>(smem_raw);                         // PC_JC*6 doubles
+    int *s_jo = reinterpret_cast<int *>(s_j + PC_JC * 6);                       // PC_JC original indices
+    PcShared *sh = reinterpret_cast<PcShared *>(s_jo + PC_JC);
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(sh + 1);            // nbins+1 (SMEM_HIST)
+    if (SMEM_HIST) for (int k = threadIdx.x; k < nbins + 1; k += blockDim.x) s_hist[k] = 0u;
+    __syncthreads();
+    const double cut_d2 = __longlong_as_double((long long)p.job.cut_bits) * (1.0 + 1e-12);
+    const float cutf = (float)fmin(cut_d2 * (1.0 + 1e-6), 3.0e38);
+    const unsigned int ntiles = min(*ntiles_ptr, tile_cap);
+    if (*ntiles_ptr > tile_cap && threadIdx.x == 0 && blockIdx.x == 0) atomicOr(p.flags + 1, 1u);
+    const long long n_items = (long long)ntiles * nzg;
+    const int gx = go.g[0], gy = go.g[1], gz = go.g[2];
+    unsigned long long g_within = 0, g_oob = 0, since_flush = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) sh->work_item = (int)atomicAdd(work_counter, 1u);
+        __syncthreads();
+        const long long item = sh->work_item;
+        if (item >= n_items) break;
+        const PaTile tl = tiles[item / nzg];
+        const int zg = (int)(item % nzg);
+        const int z0 = (int)((long long)gz * zg / nzg), z1 = (int)((long long)gz * (zg + 1) / nzg);
+        if (z0 == z1) continue;
+        double p1x[PC_RI], p1y[PC_RI], p1z[PC_RI];
+        int iorig[PC_RI];
+        const long long ibase = (long long)tl.frame * gi.nmol;
+#pragma unroll
+        for (int r = 0; r < PC_RI; ++r) {
+            const int k = r * PC_THREADS + threadIdx.x;
+            if (k < tl.count) {
+                p1x[r] = gi.sx[ibase + tl.begin + k]; p1y[r] = gi.sy[ibase + tl.begin + k]; p1z[r] = gi.sz[ibase + tl.begin + k];
+                iorig[r] = gi.sorig[ibase + tl.begin + k];
+            } else { p1x[r] = p1y[r] = p1z[r] = -1.0e15; iorig[r] = -1; }
+        }
+        for (int t = threadIdx.x; t < gx + gy + gz; t += blockDim.x) {
+            const int c = t < gx ? 0 : (t < gx + gy ? 1 : 2);
+            const int k = c == 0 ? t : (c == 1 ? t - gx : t - gx - gy);
+            const long long li = ((long long)tl.frame * 3 + c) * gi.gmax, lj = ((long long)tl.frame * 3 + c) * go.gmax;
+            double ilo, ihi;
+            if (c == 0) {
+                ilo = 1e300; ihi = -1e300;
+                for (int q = tl.cx0; q <= tl.cx1; ++q)
+                    if (gi.lay_lo[li + q] <= gi.lay_hi[li + q]) { ilo = fmin(ilo, okey_inv(gi.lay_lo[li + q])); ihi = fmax(ihi, okey_inv(gi.lay_hi[li + q])); }
+            } else {
+                const int q = c == 1 ? tl.cy : tl.cz;
+                ilo = okey_inv(gi.lay_lo[li + q]); ihi = okey_inv(gi.lay_hi[li + q]);
+            }
+            PcLayer cl;
+            if (go.lay_lo[lj + k] > go.lay_hi[lj + k]) { cl.mode = 0; cl.ca = cl.cb = 1; cl.pad = 0; cl.dmin2 = 3.0e38f; }
+            else cl = pc_classify(ilo, ihi, okey_inv(go.lay_lo[lj + k]), okey_inv(go.lay_hi[lj + k]), p.box.L[c]);
+            if (cl.mode == 3) atomicOr(p.flags + 1, 1u);
+            sh->lay[c][k] = cl;
+        }
+        __syncthreads();
+        if (SMEM_HIST) {
+            const unsigned long long item_pairs = (unsigned long long)PC_TILE * (unsigned long long)go.nmol;
+            if (since_flush + item_pairs > 0x7fffffffull) { __syncthreads(); pg_flush<SMEM_HIST>(p, s_hist, nbins, true); since_flush = 0; }
+            since_flush += item_pairs;
+        }
+        const long long jbase = (long long)tl.frame * go.nmol;
+        const int *cs = go.cell_start + (long long)tl.frame * (go.ncell + 1);
+        for (int cz = z0; cz < z1; ++cz) {
+            const PcLayer lz = sh->lay[2][cz];
+            if (!(lz.dmin2 < cutf)) continue;
+            for (int cy = 0; cy < gy; ++cy) {
+                const PcLayer ly = sh->lay[1][cy];
+                const float dyz2 = lz.dmin2 + ly.dmin2;
+                if (!(dyz2 < cutf)) continue;
+                const int *row = cs + ((long long)cz * gy + cy) * gx;
+                int cx = 0;
+                while (cx < gx) {
+                    const PcLayer lx = sh->lay[0][cx];
+                    if (!(dyz2 + lx.dmin2 < cutf)) { ++cx; continue; }
+                    int ce = cx;
+                    while (ce + 1 < gx) {
+                        const PcLayer ln = sh->lay[0][ce + 1];
+                        if (ln.mode != lx.mode || ln.ca != lx.ca || ln.cb != lx.cb || !(dyz2 + ln.dmin2 < cutf)) break;
+                        ++ce;
+                    }
+                    const int jb = row[cx], je = row[ce + 1];
+                    cx = ce + 1;
+                    if (jb == je) continue;
+                    const double Lx = p.box.L[0], Ly = p.box.L[1], Lz = p.box.L[2];
+                    const double sxa = (double)(lx.ca - 1) * Lx, sxb = (double)(lx.cb - 1) * Lx;
+                    const double sya = (double)(ly.ca - 1) * Ly, syb = (double)(ly.cb - 1) * Ly;
+                    const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
+                    if (lx.mode < 2 && ly.mode < 2 && lz.mode < 2)
+                        pg_segment<1, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, g_within, g_oob);
+                    else
+                        pg_segment<2, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, g_within, g_oob);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (SMEM_HIST) pg_flush<SMEM_HIST>(p, s_hist, nbins, false);
+    else {
+        if (g_within) atomicAdd(&p.job.acc[nbins], g_within);
+        if (g_oob) atomicAdd(&p.job.acc[nbins + 1], g_oob);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // launch wrappers
 
 int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &box, int frame0, int nframes, unsigned int *err, void *stream)
@@ -603,5 +787,25 @@ int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
     else { if (verify) PC_LAUNCH(0, true); else PC_LAUNCH(0, false); }
 #undef PC_LAUNCH2
 #undef PC_LAUNCH
+    return (int)cudaGetLastError();
+}
+
+int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
+                            unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nbins = p.job.bin_a * p.job.bin_b;
+    const bool smem_hist = nbins <= 40000;
+    const size_t smem = (size_t)PC_JC * 6 * 8 + (size_t)PC_JC * 4 + sizeof(PcShared) + (smem_hist ? (size_t)(nbins + 1) * 4 : 0) + 16;
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
+#define PG_LAUNCH(S_)                                                                                           \
+    do {                                                                                                        \
+        int occ = 1;                                                                                            \
+        cudaFuncSetAttribute(pa_general_cells_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_general_cells_kernel<S_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
+        pa_general_cells_kernel<S_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+    } while (0)
+    if (smem_hist) PG_LAUNCH(true); else PG_LAUNCH(false);
+#undef PG_LAUNCH
     return (int)cudaGetLastError();
 }

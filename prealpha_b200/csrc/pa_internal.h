@@ -128,6 +128,8 @@ int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &b
 int pa_launch_build_tiles(const PaCellGrid &g, int nframes, PaTile *tiles, unsigned int *ntiles, unsigned int cap, void *stream);
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
                         unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream);
+int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
+                            unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream);
 void pa_cell_grid_dims(int nmol, int g[3]);
 int pa_kernels_selfcheck();    // returns 0 when a kernel image for the current device exists
 int pa_rdf_ri(int nref);       // reference molecules per thread the fast kernel will use (tile = 128*RI)

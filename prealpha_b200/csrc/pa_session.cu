@@ -291,7 +291,6 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     s->use_cells = !(ex.flags & PA_EXEC_NO_CELLS) && !traj->wrap_trajectory;
     if (s->use_cells) {
         for (const JobState &js : s->jobs) {
-            if (!js.fast) continue;
             const int r = js.job.ref_type - 1;
             for (int o = 0; o < traj->ntypes; ++o) {
                 if (js.job.obs_type >= 1 && o != js.job.obs_type - 1) continue;
@@ -422,7 +421,7 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         const int o_last = jb.obs_type < 1 ? (int)s->types.size() - 1 : jb.obs_type - 1;
         for (int o = o_first; o <= o_last; ++o) {
             Plan pl{ (int)j, r, o, false, false, -1, false };
-            pl.cells = s->jobs[j].fast && s->grids[r].enabled && s->grids[o].enabled;
+            pl.cells = s->grids[r].enabled && s->grids[o].enabled;
             plan.push_back(pl);
         }
     }
@@ -432,12 +431,12 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
     if (s->exact_ok && !(s->exec.flags & PA_EXEC_NO_SYMMETRY)) {
         for (size_t a = 0; a < plan.size(); ++a) {
             Plan &pa_ = plan[a];
-            if (!pa_.cells || pa_.skip) continue;
+            if (!pa_.cells || pa_.skip || !s->jobs[pa_.job].fast) continue;
             if (pa_.r == pa_.o) { pa_.sym = true; continue; }
             if (pa_.partner >= 0) continue;
             for (size_t b2 = a + 1; b2 < plan.size(); ++b2) {
                 Plan &pb = plan[b2];
-                if (!pb.cells || pb.skip || pb.partner >= 0 || pb.r != pa_.o || pb.o != pa_.r) continue;
+                if (!pb.cells || pb.skip || pb.partner >= 0 || pb.r != pa_.o || pb.o != pa_.r || !s->jobs[pb.job].fast) continue;
                 const pa_job &ja = s->jobs[pa_.job].job, &jb2 = s->jobs[pb.job].job;
                 if (ja.bin_a != jb2.bin_a || ja.maxdist != jb2.maxdist || ja.step_a != jb2.step_a ||
                     s->jobs[pa_.job].cells_variant != s->jobs[pb.job].cells_variant) continue;
@@ -476,7 +475,20 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         len = ((len + PA_J_CHUNK - 1) / PA_J_CHUNK) * PA_J_CHUNK;
         p.jsplit_len = len;
         p.n_jsplits = (p.nobs + len - 1) / len;
-        if (pl.cells) {
+        if (pl.cells && !js.fast) {
+            TypeGrid &gr = s->grids[r];
+            if (!gr.tiles_ready) {
+                PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, gr.tiles, gr.counters, gr.tile_cap, s->s_compute));
+                gr.tiles_ready = true;
+                s->stats.kernel_launches += 1;
+            }
+            const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 230 + 1));
+            long long nzg = (20ll * s->sm_count * 5 + tiles_est - 1) / tiles_est;
+            nzg = std::max<long long>(1, std::min<long long>(nzg, s->grids[o].g.g[2]));
+            PA_CK((cudaError_t)pa_launch_general_cells(p, gr.g, s->grids[o].g, gr.tiles, gr.counters, gr.tile_cap, gr.counters + 1,
+                                                       (int)nzg, s->sm_count, s->s_compute));
+            s->stats.kernel_launches += 1;
+        } else if (pl.cells) {
             TypeGrid &gr = s->grids[r];
             if (!gr.tiles_ready) {
                 PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, gr.tiles, gr.counters, gr.tile_cap, s->s_compute));

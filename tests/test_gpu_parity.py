@@ -211,6 +211,30 @@ def test_cell_sorted_kernel_against_oracle(name, kw, oracle):
     assert int(cells[2].sum()) > 0, "the planted (anti)parallel / coincident pairs must show up as out of bounds"
 
 
+@pytest.mark.parametrize("name,kw", BIG[:2] + BIG[2:], ids=[b[0] for b in BIG])
+def test_cell_sorted_general_kernel(name, kw, oracle):
+    """2-D pdf / cdf / centre-of-charge jobs on large systems go through the cell-sorted general kernel
+    (cutoff pruning + literal evaluation of the pairs inside): identical to the brute-force general kernel
+    and to the oracle."""
+    traj = _big_system(**kw)
+    reqs = [dict(mode="pdf", vec=(1, 1, 0), ref_type=1, obs_type=2, bin_a=24, bin_b=12, maxdist=9.0),
+            dict(mode="cdf", vec=(0, 0, 1), ref_type=2, obs_type=-1, bin_a=30, bin_b=30, maxdist=11.5, weigh_charge=True),
+            dict(mode="pdf", vec=(0, 0, 1), ref_type=1, obs_type=1, bin_a=300, bin_b=300, maxdist=8.0),     # 90 000 bins: global atomics
+            dict(mode="pdf", vec=(0, 0, 1), ref_type=2, obs_type=1, bin_a=50, bin_b=1, maxdist=7.0, use_coc=True)]
+    pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
+    cells = api.histogram_multi(traj, pjobs)
+    brute = api.histogram_multi(traj, pjobs, api.make_exec(flags=capi.PA_EXEC_NO_CELLS))
+    assert cells[3].kernel_launches != brute[3].kernel_launches
+    for k in range(len(pjobs)):
+        assert np.array_equal(cells[0][k], brute[0][k]) and cells[1][k] == brute[1][k] and cells[2][k] == brute[2][k], (name, k)
+    if name == "clustered":
+        for k in (0, 1):
+            h0, w0, o0 = oracle.histogram(traj, pjobs[k])
+            assert np.array_equal(cells[0][k], h0) and (int(cells[1][k]), int(cells[2][k])) == (w0, o0), (name, k)
+    if name == "uniform":
+        assert cells[3].kernel_ms < brute[3].kernel_ms      # pruning must pay off at these cutoffs (homogeneous system)
+
+
 def test_wrap_trajectory_switch(oracle):
     """WRAP_TRAJECTORY = T skips wrap_vector inside the distance routine (Molecular:1442)."""
     rng = np.random.default_rng(11)
