@@ -35,6 +35,8 @@ _SIG = {
                                          C.c_char_p, C.POINTER(C.c_float), C.c_float]),
     "orc_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
     "orc_distance_subjobs": (C.c_int, [C.POINTER(capi.pa_traj), C.POINTER(capi.pa_dist_job), C.POINTER(capi.pa_dist_result)]),
+    "orc_wrap_full": (C.c_int, [C.POINTER(capi.pa_traj)]),
+    "orc_unwrap_full": (C.c_int, [C.POINTER(capi.pa_traj)]),
     "orc_read_xyz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_char_p]),
     "orc_read_traj": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_char_p]),
 }
@@ -90,6 +92,18 @@ def write(traj, job, refnum, prefix, input_name, g, rho):
                                        g.ctypes.data_as(C.POINTER(C.c_float)), rho)
     assert rc == 0, rc
     return g
+
+
+def wrap_full(traj):
+    """In-place wrap_full (Molecular:1703): rewrites the float32 coordinates held by `traj`."""
+    assert load().orc_wrap_full(traj.ptr) == 0
+
+
+def unwrap_full(traj):
+    """In-place wrap_full + unwrap_full_SEQUENTIAL twice (Molecular:4806-4816, developers version)."""
+    wrap_full(traj)
+    assert load().orc_unwrap_full(traj.ptr) == 0
+    assert load().orc_unwrap_full(traj.ptr) == 0
 
 
 def distance_subjobs(traj, job):

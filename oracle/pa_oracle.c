@@ -718,3 +718,69 @@ int orc_distance_subjobs(const pa_traj *t, const pa_dist_job *job, pa_dist_resul
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------ */
+/* wrap_full, Molecular:1703-1765: REAL(4) centre of mass; whole molecules are moved by
+ * +-box_size until the centre of mass is inside; coordinates are rewritten in REAL(4). */
+int orc_wrap_full(pa_traj *t)
+{
+    for (int step = 0; step < t->nsteps; ++step)
+        for (int ty = 0; ty < t->ntypes; ++ty) {
+            const pa_type *T = &t->types[ty];
+            for (int m = 0; m < T->nmol; ++m) {
+                double c[3];
+                orc_center_of_mass(t, step, ty, m, c);
+                float *r = (float *)T->xyz + ((size_t)step * T->nmol + m) * (size_t)T->natoms * 3;
+                for (int k = 0; k < 3; ++k) {
+                    float com = (float)c[k];
+                    const double L = t->box_hi[k] - t->box_lo[k];
+                    for (int it = 0; it < 1000; ++it) {
+                        if ((double)com < t->box_lo[k]) {
+                            com = (float)((double)com + L);
+                            for (int a = 0; a < T->natoms; ++a) r[a * 3 + k] = (float)((double)r[a * 3 + k] + L);
+                        } else if ((double)com > t->box_hi[k]) {
+                            com = (float)((double)com - L);
+                            for (int a = 0; a < T->natoms; ++a) r[a * 3 + k] = (float)((double)r[a * 3 + k] - L);
+                        } else break;
+                    }
+                }
+            }
+        }
+    return 0;
+}
+
+/* unwrap_full_SEQUENTIAL, Molecular:1590-1699 (called with WRAP_TRAJECTORY = F). */
+int orc_unwrap_full(pa_traj *t)
+{
+    int nmol_total = 0;
+    for (int ty = 0; ty < t->ntypes; ++ty) nmol_total += t->types[ty].nmol;
+    double *acc = (double *)calloc((size_t)nmol_total * 3, sizeof(double));
+    char *jumped = (char *)calloc((size_t)nmol_total, 1);
+    double thr[3];
+    for (int k = 0; k < 3; ++k) thr[k] = (t->box_hi[k] - t->box_lo[k]) / 2.0;
+    for (int step = 0; step + 1 < t->nsteps; ++step) {
+        int idx = 0;
+        for (int ty = 0; ty < t->ntypes; ++ty) {
+            const pa_type *T = &t->types[ty];
+            for (int m = 0; m < T->nmol; ++m, ++idx) {
+                float *rn = (float *)T->xyz + ((size_t)(step + 1) * T->nmol + m) * (size_t)T->natoms * 3;
+                double *as = acc + (size_t)idx * 3;
+                if (jumped[idx]) {
+                    if ((as[0] * as[0] + as[1] * as[1]) + as[2] * as[2] < 0.001) jumped[idx] = 0;
+                    else for (int a = 0; a < T->natoms; ++a) for (int k = 0; k < 3; ++k) rn[a * 3 + k] = (float)((double)rn[a * 3 + k] + as[k]);
+                }
+                double c1[3], c2[3], link[3];
+                orc_center_of_mass(t, step, ty, m, c1);
+                orc_center_of_mass(t, step + 1, ty, m, c2);
+                (void)orc_smallest_distance_squared(t, c1, c2, link);
+                if (fabs(link[0]) > thr[0] || fabs(link[1]) > thr[1] || fabs(link[2]) > thr[2]) {
+                    for (int a = 0; a < T->natoms; ++a) for (int k = 0; k < 3; ++k) rn[a * 3 + k] = (float)((double)rn[a * 3 + k] + link[k]);
+                    jumped[idx] = 1;
+                    for (int k = 0; k < 3; ++k) as[k] = as[k] + link[k];
+                }
+            }
+        }
+    }
+    free(acc); free(jumped);
+    return 0;
+}

@@ -15,6 +15,7 @@
 #include <sstream>
 #include <chrono>
 #include <array>
+#include <thread>
 #include "pa_internal.h"
 
 namespace {
@@ -258,50 +259,132 @@ bool load_trajectory(Run &r)
     const int header = lmp ? 9 : 2;
     long long natoms_total = 0;
     for (auto &t : r.types) { natoms_total += (long long)t.natoms * t.nmol; t.xyz.assign((size_t)r.nsteps * t.natoms * t.nmol * 3, 0.f); }
-    char *line = nullptr; size_t cap = 0;
-    bool ok = true;
+    // Multi-threaded ingestion: the file is read in large blocks; each block is cut into
+    // whole frames by counting newlines, split among the host threads at line boundaries, and every
+    // thread parses its lines with strtof (decimal -> REAL(4) directly, like the list-directed READ at
+    // Molecular:5042) straight into the [step][mol][atom][3] arrays.  The reference's reader is serial.
+    const long long lines_per_frame = header + natoms_total;
+    std::vector<long long> type_first(r.types.size() + 1, 0);           // first atom line of each type inside a frame
+    for (size_t t = 0; t < r.types.size(); ++t) type_first[t + 1] = type_first[t] + (long long)r.types[t].natoms * r.types[t].nmol;
+    auto parse_atom_line = [&](const char *p, int step, long long a_total, bool first_frame) {
+        size_t t = 0;
+        while (t + 1 < r.types.size() && a_total >= type_first[t + 1]) ++t;
+        HostType &ty = r.types[t];
+        const long long local = a_total - type_first[t];
+        const int m = (int)(local / ty.natoms), a = (int)(local % ty.natoms);
+        while (*p == ' ' || *p == '\t') ++p;
+        const char *e = p;
+        while (*e && *e != ' ' && *e != '\t' && *e != ',' && *e != '\n' && *e != '\r') ++e;
+        if (first_frame && m == 0) ty.elements[a] = std::string(p, (size_t)std::min<ptrdiff_t>(e - p, 2));
+        float *dst = &ty.xyz[(((size_t)step * ty.nmol + m) * ty.natoms + a) * 3];
+        p = e;
+        for (int k = 0; k < 3; ++k) {
+            while (*p == ' ' || *p == '\t' || *p == ',') ++p;
+            char *q; dst[k] = strtof(p, &q); p = q;
+        }
+    };
+    auto parse_header_line = [&](const std::string &ln, int h) {        // frame 1 only, serial
+        if (lmp && h >= 5 && h <= 7) {                                    // box bounds, Molecular:4851-4857
+            auto tk = tokens_of(ln);
+            if (tk.size() < 2 || !parse_real8(tk[0], r.box_lo[h - 5]) || !parse_real8(tk[1], r.box_hi[h - 5])) r.error(71, "cannot read box from lammps header");
+        }
+        if (lmp && h == 8) {
+            auto tk = tokens_of(ln);
+            if (tk.size() < 6 || tk[2] != "element") r.error(53, "lammps trajectory must have 'element' as first column");
+            else if (!(tk[3] == "xu" && tk[4] == "yu" && tk[5] == "zu")) r.error(54, "expected 'xu yu zu' columns");
+        }
+        if (h == (lmp ? 3 : 0)) {
+            auto tk = tokens_of(ln);
+            int n = 0;
+            if (tk.empty() || !parse_int(tk[0], n)) r.error(71, "cannot read number of atoms");
+            else if (n != natoms_total) r.error(10, "number of atoms in trajectory and molecular input differ");
+        }
+    };
+    const unsigned nthreads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    const size_t block_bytes = (size_t)256 << 20;
+    std::vector<char> buf;
+    size_t have = 0;                    // valid bytes in buf
     int steps_read = 0;
-    for (int s = 0; s < r.nsteps && ok; ++s) {
-        for (int h = 0; h < header; ++h) {
-            if (getline(&line, &cap, f) < 0) { ok = false; break; }
-            if (s == 0 && lmp && h >= 5 && h <= 7) {          // box bounds, Molecular:4851-4857
-                auto tk = tokens_of(line);
-                if (tk.size() < 2 || !parse_real8(tk[0], r.box_lo[h - 5]) || !parse_real8(tk[1], r.box_hi[h - 5])) r.error(71, "cannot read box from lammps header");
-            }
-            if (s == 0 && lmp && h == 8) {
-                auto tk = tokens_of(line);
-                if (tk.size() < 6 || tk[2] != "element") r.error(53, "lammps trajectory must have 'element' as first column");
-                else if (!(tk[3] == "xu" && tk[4] == "yu" && tk[5] == "zu")) r.error(54, "expected 'xu yu zu' columns");
-            }
-            if (s == 0 && h == (lmp ? 3 : 0)) {
-                auto tk = tokens_of(line);
-                int n = 0;
-                if (tk.empty() || !parse_int(tk[0], n)) r.error(71, "cannot read number of atoms");
-                else if (n != natoms_total) r.error(10, "number of atoms in trajectory and molecular input differ");
+    bool eof = false;
+    while (steps_read < r.nsteps) {
+        // 1. top up the buffer
+        if (!eof) {
+            if (buf.size() < have + block_bytes + 1) buf.resize(have + block_bytes + 1);
+            const size_t got = fread(buf.data() + have, 1, block_bytes, f);
+            have += got;
+            if (got < block_bytes) { eof = true; if (have && buf[have - 1] != '\n') buf[have++] = '\n'; }
+        }
+        // 2. how many whole frames does it hold?  (count newlines, stop at the last frame boundary)
+        const int want = r.nsteps - steps_read;
+        long long nl = 0; size_t end = 0; int nframes = 0;
+        for (const char *p = buf.data(), *lim = buf.data() + have; p < lim && nframes < want;) {
+            const char *q = (const char *)memchr(p, '\n', (size_t)(lim - p));
+            if (!q) break;
+            ++nl; p = q + 1;
+            if (nl % lines_per_frame == 0) { ++nframes; end = (size_t)(p - buf.data()); }
+        }
+        if (nframes == 0) {
+            if (eof) break;                                               // truncated file: error 84 below
+            continue;                                                     // frame larger than the buffer so far: read more
+        }
+        // 3. frame 1: header lines serially
+        if (steps_read == 0) {
+            const char *p = buf.data();
+            for (int h = 0; h < header; ++h) {
+                const char *q = (const char *)memchr(p, '\n', end - (size_t)(p - buf.data()));
+                parse_header_line(std::string(p, (size_t)(q - p)), h);
+                p = q + 1;
             }
         }
-        if (!ok) break;
-        for (auto &t : r.types) {
-            for (int m = 0; m < t.nmol && ok; ++m)
-                for (int a = 0; a < t.natoms; ++a) {
-                    if (getline(&line, &cap, f) < 0) { ok = false; break; }
-                    char *p = line;
-                    while (*p == ' ' || *p == '\t') ++p;
-                    char *e = p;
-                    while (*e && *e != ' ' && *e != '\t' && *e != ',' && *e != '\n' && *e != '\r') ++e;
-                    if (s == 0 && m == 0) t.elements[a] = std::string(p, (size_t)std::min<ptrdiff_t>(e - p, 2));
-                    float *dst = &t.xyz[(((size_t)s * t.nmol + m) * t.natoms + a) * 3];
-                    p = e;
-                    for (int k = 0; k < 3; ++k) {
-                        while (*p == ' ' || *p == '\t' || *p == ',') ++p;
-                        char *q; dst[k] = strtof(p, &q); p = q;
+        // 4. split [0,end) among the threads at line boundaries, count lines, then parse
+        std::vector<size_t> cut(nthreads + 1, end);
+        cut[0] = 0;
+        for (unsigned t = 1; t < nthreads; ++t) {
+            size_t pos = end / nthreads * t;
+            const char *q = (const char *)memchr(buf.data() + pos, '\n', end - pos);
+            cut[t] = q ? (size_t)(q - buf.data()) + 1 : end;
+        }
+        for (unsigned t = 1; t <= nthreads; ++t) if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+        std::vector<long long> nlines(nthreads, 0);
+        {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nthreads; ++t)
+                th.emplace_back([&, t] {
+                    long long c = 0;
+                    for (const char *p = buf.data() + cut[t], *lim = buf.data() + cut[t + 1]; p < lim;) {
+                        const char *q = (const char *)memchr(p, '\n', (size_t)(lim - p));
+                        if (!q) break;
+                        ++c; p = q + 1;
                     }
-                }
-            if (!ok) break;
+                    nlines[t] = c;
+                });
+            for (auto &x : th) x.join();
         }
-        if (ok) steps_read = s + 1;
+        std::vector<long long> first_line(nthreads + 1, 0);
+        for (unsigned t = 0; t < nthreads; ++t) first_line[t + 1] = first_line[t] + nlines[t];
+        {
+            std::vector<std::thread> th;
+            const int step0 = steps_read;
+            for (unsigned t = 0; t < nthreads; ++t)
+                th.emplace_back([&, t] {
+                    long long ln = first_line[t];
+                    for (const char *p = buf.data() + cut[t], *lim = buf.data() + cut[t + 1]; p < lim; ++ln) {
+                        const char *q = (const char *)memchr(p, '\n', (size_t)(lim - p));
+                        if (!q) break;
+                        const long long in_frame = ln % lines_per_frame;
+                        const int step = step0 + (int)(ln / lines_per_frame);
+                        if (in_frame >= header) parse_atom_line(p, step, in_frame - header, step == 0);
+                        p = q + 1;
+                    }
+                });
+            for (auto &x : th) x.join();
+        }
+        steps_read += nframes;
+        // 5. keep the unparsed tail
+        memmove(buf.data(), buf.data() + end, have - end);
+        have -= end;
     }
-    free(line); fclose(f);
+    fclose(f);
     if (steps_read < r.nsteps) {                                  // Molecular:5003-5009, error 84
         r.error(84, "trajectory is shorter than specified; using " + std::to_string(steps_read) + " steps");
         // re-pack is not needed: arrays are [step][mol][atom][3], truncation just drops the tail
@@ -334,6 +417,109 @@ bool load_trajectory(Run &r)
         }
     }
     return true;
+}
+
+
+// ---- wrap_trajectory / unwrap_trajectory pre-passes ---------------------------------------
+// O(N) per frame scalar work that rewrites the stored REAL(4) coordinates before any analysis
+// (Molecular:4801-4816).  Host threads; molecules are independent.
+
+void host_center_of_mass(const Run &r, const HostType &ty, int step, int mol, bool com_boost, double c[3])   // Molecular:2804-2834
+{
+    const float *p = &ty.xyz[((size_t)step * ty.nmol + mol) * (size_t)ty.natoms * 3];
+    if (com_boost) { c[0] = (double)p[0]; c[1] = (double)p[1]; c[2] = (double)p[2]; return; }
+    (void)r;
+    c[0] = c[1] = c[2] = 0.0;
+    for (int a = 0; a < ty.natoms; ++a)
+        for (int k = 0; k < 3; ++k) { double w = (double)p[a * 3 + k]; w = w * ty.atom_mass[a]; c[k] = c[k] + w; }
+    for (int k = 0; k < 3; ++k) c[k] = c[k] / ty.mass;
+}
+
+template <typename F>
+void parallel_for(int n, F fn)
+{
+    const unsigned nt = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    if (n < 2 || nt < 2) { for (int i = 0; i < n; ++i) fn(i); return; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back([&, t] { for (int i = (int)t; i < n; i += (int)nt) fn(i); });
+    for (auto &x : th) x.join();
+}
+
+bool all_one_atom(const Run &r) { for (auto &t : r.types) if (t.natoms > 1) return false; return true; }
+
+void wrap_full(Run &r)                                          // Molecular:1703-1765
+{
+    const bool boost = all_one_atom(r);
+    parallel_for(r.nsteps, [&](int step) {
+        for (auto &ty : r.types)
+            for (int m = 0; m < ty.nmol; ++m) {
+                double c[3];
+                host_center_of_mass(r, ty, step, m, boost, c);
+                float *p = &ty.xyz[((size_t)step * ty.nmol + m) * (size_t)ty.natoms * 3];
+                for (int k = 0; k < 3; ++k) {
+                    float com = (float)c[k];                                 // REAL :: centre_of_mass(3)
+                    const double L = r.box_hi[k] - r.box_lo[k];
+                    for (int it = 0; it < 1000; ++it) {
+                        if ((double)com < r.box_lo[k]) {
+                            com = (float)((double)com + L);
+                            for (int a = 0; a < ty.natoms; ++a) p[a * 3 + k] = (float)((double)p[a * 3 + k] + L);
+                        } else if ((double)com > r.box_hi[k]) {
+                            com = (float)((double)com - L);
+                            for (int a = 0; a < ty.natoms; ++a) p[a * 3 + k] = (float)((double)p[a * 3 + k] - L);
+                        } else break;
+                    }
+                }
+            }
+    });
+}
+
+// give_smallest_distance_squared with translation (Molecular:1430-1469), WRAP_TRAJECTORY = F
+void host_link_vector(const Run &r, const double c1[3], const double c2[3], double tr[3])
+{
+    double p1[3], p2[3], sh1[3], sh2[3], L[3];
+    for (int k = 0; k < 3; ++k) {
+        L[k] = r.box_hi[k] - r.box_lo[k];
+        p1[k] = c1[k]; p2[k] = c2[k]; sh1[k] = sh2[k] = 0.0;
+        for (int it = 0; it < 1000; ++it) { if (p1[k] < r.box_lo[k]) { p1[k] += L[k]; sh1[k] += L[k]; } else if (p1[k] > r.box_hi[k]) { p1[k] -= L[k]; sh1[k] -= L[k]; } else break; }
+        for (int it = 0; it < 1000; ++it) { if (p2[k] < r.box_lo[k]) { p2[k] += L[k]; sh2[k] += L[k]; } else if (p2[k] > r.box_hi[k]) { p2[k] -= L[k]; sh2[k] -= L[k]; } else break; }
+    }
+    double best = r.max_dist_sq;
+    tr[0] = tr[1] = tr[2] = 0.0;
+    for (int a = -1; a <= 1; ++a) for (int b = -1; b <= 1; ++b) for (int c = -1; c <= 1; ++c) {
+        const double s[3] = { (double)a * L[0], (double)b * L[1], (double)c * L[2] };
+        const double d0 = (p2[0] + s[0]) - p1[0], d1 = (p2[1] + s[1]) - p1[1], d2 = (p2[2] + s[2]) - p1[2];
+        const double clip = (d0 * d0 + d1 * d1) + d2 * d2;
+        if (clip < best) { best = clip; tr[0] = s[0]; tr[1] = s[1]; tr[2] = s[2]; }
+    }
+    for (int k = 0; k < 3; ++k) tr[k] = tr[k] + (sh2[k] - sh1[k]);
+}
+
+void unwrap_full(Run &r)                                        // Molecular:1590-1699
+{
+    const bool boost = all_one_atom(r);
+    double thr[3];
+    for (int k = 0; k < 3; ++k) thr[k] = (r.box_hi[k] - r.box_lo[k]) / 2.0;
+    for (auto &ty : r.types)
+        parallel_for(ty.nmol, [&](int m) {
+            double acc[3] = { 0, 0, 0 };
+            bool jumped = false;
+            for (int step = 0; step + 1 < r.nsteps; ++step) {
+                float *pn = &ty.xyz[((size_t)(step + 1) * ty.nmol + m) * (size_t)ty.natoms * 3];
+                if (jumped) {
+                    if ((acc[0] * acc[0] + acc[1] * acc[1]) + acc[2] * acc[2] < 0.001) jumped = false;
+                    else for (int a = 0; a < ty.natoms; ++a) for (int k = 0; k < 3; ++k) pn[a * 3 + k] = (float)((double)pn[a * 3 + k] + acc[k]);
+                }
+                double c1[3], c2[3], link[3];
+                host_center_of_mass(r, ty, step, m, boost, c1);
+                host_center_of_mass(r, ty, step + 1, m, boost, c2);
+                host_link_vector(r, c1, c2, link);
+                if (std::fabs(link[0]) > thr[0] || std::fabs(link[1]) > thr[1] || std::fabs(link[2]) > thr[2]) {
+                    for (int a = 0; a < ty.natoms; ++a) for (int k = 0; k < 3; ++k) pn[a * 3 + k] = (float)((double)pn[a * 3 + k] + link[k]);
+                    jumped = true;
+                    for (int k = 0; k < 3; ++k) acc[k] = acc[k] + link[k];
+                }
+            }
+        });
 }
 
 struct DistInput {
@@ -744,14 +930,26 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
     }
     if (auto *t = find_switch(body, {"wrap_trajectory"})) if (t->size() > 1 && parse_logical((*t)[1], b)) r.wrap = b;
     if (auto *t = find_switch(body, {"unwrap_trajectory"})) if (t->size() > 1 && parse_logical((*t)[1], b)) r.unwrap = b;
-    if (r.wrap || r.unwrap) {
-        // wrap_full / unwrap_full rewrite the stored float32 coordinates (Molecular:1590-1765); SURVEY 8f-2
-        r.error(0, "wrap_trajectory / unwrap_trajectory pre-passes are not part of this path yet");
-        return r.errors;
+    if (r.unwrap && r.wrap) {                                    // Main:309-313, error 151
+        r.error(151, "wrap_trajectory and unwrap_trajectory are mutually exclusive - both switched off");
+        r.wrap = r.unwrap = false;
     }
+    if (r.unwrap && r.read_sequential) { r.error(152, "unwrap_trajectory needs the whole trajectory in RAM"); r.unwrap = false; }
     if (r.read_sequential) printf(" sequential_read T: frames are streamed in batches anyway; the switch has no effect here.\n");
     if (!read_molecular_input(r)) return r.errors;
     if (!load_trajectory(r)) return r.errors;
+    if ((r.wrap || r.unwrap) && !r.box_given) { r.error(41, "box volume required for wrapping"); return r.errors; }
+    if (r.wrap) {                                                // Molecular:4801-4804
+        printf(" Wrapping centres of mass of each specified molecule into box *now*.\n");
+        wrap_full(r);
+    }
+    if (r.unwrap) {                                              // Molecular:4806-4816 (developers version unwraps twice)
+        printf(" Preparing a clean trajectory before unwrapping...\n");
+        wrap_full(r);
+        printf(" UNwrapping centres of mass of each specified molecule *now*.\n");
+        unwrap_full(r);
+        unwrap_full(r);
+    }
     // body, Main:2882-3666
     int nline = 5;
     for (const auto &t : body) {

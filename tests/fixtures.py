@@ -28,6 +28,8 @@ class Fixture:
         self.stdout = z["stdout"].tobytes().decode()
         self.atom_charges = [z[f"atom_charge_{i}"] for i in range(len(self.types))] if "atom_charge_0" in z.files else None
         self.lmp = "lmp" in z.files
+        self.wrap = "wrap" in z.files
+        self.unwrap = "unwrap" in z.files
 
     def trajectory(self) -> capi.Trajectory:
         tl, off = [], 0
@@ -39,7 +41,13 @@ class Fixture:
                 d["atom_charge"] = self.atom_charges[ti]
             tl.append(d)
             off += n
-        return capi.Trajectory(tl, self.box_lo, self.box_hi, xyz_format=not self.lmp)
+        traj = capi.Trajectory(tl, self.box_lo, self.box_hi, xyz_format=not self.lmp, wrap_trajectory=self.wrap)
+        if self.wrap or self.unwrap:
+            # the reference rewrites the stored float32 coordinates before any analysis (Molecular:4801-4816);
+            # tests apply the oracle's restatement of those pre-passes to the fixture's raw coordinates
+            from oracle import oracle_lib
+            (oracle_lib.wrap_full if self.wrap else oracle_lib.unwrap_full)(traj)
+        return traj
 
     def jobs(self):
         """[(job_name, reference_number (1-based within its input file), pa_job_request, (within, oob))]"""
@@ -55,7 +63,7 @@ class Fixture:
         return {fn[len(pre):]: c for fn, c in self.files.items() if fn.startswith(pre)}
 
 
-ALL = ["bmim", "re4", "re4_atoms", "synth", "lmp"]
+ALL = ["bmim", "re4", "re4_atoms", "synth", "lmp", "lmp_wrap", "lmp_unwrap"]
 
 
 def available():

@@ -45,7 +45,7 @@ def dist_text(mode, refs, **kw):
 
 
 def run_case(name, traj_path, traj_type, types, nsteps, box, jobs, natoms_total, *, expect=None, store_frames=None,
-             lmp_box=None, threads=8, atom_charges=None):
+             lmp_box=None, threads=8, atom_charges=None, switches=()):
     """jobs: list of (jobname, mode, refs, kwargs).  Each job runs under its own set_prefix."""
     wd = tempfile.mkdtemp(prefix=f"golden_{name}_")
     try:
@@ -68,6 +68,8 @@ def run_case(name, traj_path, traj_type, types, nsteps, box, jobs, natoms_total,
             if box is not None:
                 f.write(f" cubic_box_edge {box[0]} {box[1]}\n")
             f.write(f" trajectory_type {traj_type}\n sequential_read F\n parallel_operation T\n set_threads {threads}\n")
+            for sw in switches:
+                f.write(f" {sw}\n")
             for jn, mode, refs, kw in jobs:
                 f.write(f' set_prefix "{jn}_"\n distribution "{jn}.inp"\n')
             f.write(" quit\n")
@@ -335,8 +337,15 @@ def case_lmp():
         ("l3", "cdf", [((1, 0, 1), 2, 1), (Z, 4, -1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=18, bin_count_b=22)),
     ]
     res = run_case("lmp", p, "lmp", types, nsteps, None, jobs, len(elements))
-    shutil.rmtree(tmp)
     save("lmp", res, types, lo, hi, jobs, res["coords"], res["elements"], extra=dict(nsteps=np.int64(nsteps), lmp=np.int64(1)))
+    # the same trajectory with the wrap_trajectory / unwrap_trajectory pre-passes (Molecular:4801-4816)
+    res = run_case("lmp_wrap", p, "lmp", types, nsteps, None, jobs[:2], len(elements), switches=("wrap_trajectory T",))
+    save("lmp_wrap", res, types, lo, hi, jobs[:2], res["coords"], res["elements"],
+         extra=dict(nsteps=np.int64(nsteps), lmp=np.int64(1), wrap=np.int64(1)))
+    res = run_case("lmp_unwrap", p, "lmp", types, nsteps, None, jobs[:2], len(elements), switches=("unwrap_trajectory T",))
+    save("lmp_unwrap", res, types, lo, hi, jobs[:2], res["coords"], res["elements"],
+         extra=dict(nsteps=np.int64(nsteps), lmp=np.int64(1), unwrap=np.int64(1)))
+    shutil.rmtree(tmp)
 
 
 CASES = {"lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
