@@ -44,6 +44,7 @@ extern "C" {
 /* operation modes, Distribution:343-347 ("cdf|cydf", "pdf|podf") */
 #define PA_MODE_CDF 0
 #define PA_MODE_PDF 1
+#define PA_MODE_CHARGE_ARM 2          /* "charge_arm": polar distribution of the charge arm / dipole vector (O(N) per frame) */
 
 /* library-specific failures (negative; prealpha's own codes are >= 0) */
 #define PA_ERR_NO_DEVICE   (-1)  /* no usable CUDA device / kernel image          */
@@ -104,8 +105,9 @@ typedef struct pa_job_request {
     int32_t weigh_charge;      /* logical                                   */
     int32_t use_coc;           /* logical                                   */
     int32_t subtract_uniform;  /* logical (only affects output, row W)      */
-    int32_t maxdist_optimize;  /* 1: maxdist = REAL4(box_limit/2.0)         */
+    int32_t maxdist_optimize;  /* 1: maxdist = REAL4(box_limit/2.0); charge_arm: from the largest arm at step 1 (Distribution:1232-1269) */
     float   maxdist;           /* used when maxdist_optimize == 0           */
+    int32_t normalise_clm;     /* charge_arm only: divide by mass * radius of gyration^2 (Distribution:864-867) */
 } pa_job_request;
 
 /* Fully resolved job: the locals of make_distribution_functions
@@ -120,7 +122,7 @@ typedef struct pa_job {
     int32_t bin_a, bin_b, sampling_interval;
     int32_t weigh_charge, use_coc, subtract_uniform;
     int32_t aligned;                 /* prepare_rotation's `aligned`        */
-    int32_t _pad;
+    int32_t normalise_clm;           /* charge_arm only                     */
 } pa_job;
 
 /* How to run: which device, and which shard of the sampled frames this

@@ -193,6 +193,7 @@ static void orc_prepare_rotation(const double start[3], double rot[9], int *alig
 
 /* Row S: Distribution:353-377 (step sizes), :526-527 (maxdist_optimize),
  * :656 (shift), :665-667 (reference vector, rotation). */
+float orc_charge_arm_maxdist(const pa_traj *t, int ref_type, int normalise_clm);
 int orc_job_setup(const pa_traj *t, const pa_job_request *rq, pa_job *job)
 {
     memset(job, 0, sizeof *job);
@@ -206,7 +207,10 @@ int orc_job_setup(const pa_traj *t, const pa_job_request *rq, pa_job *job)
     job->weigh_charge = rq->weigh_charge; job->use_coc = rq->use_coc;
     job->subtract_uniform = rq->subtract_uniform;
     float maxdist = rq->maxdist;
-    if (rq->maxdist_optimize) {
+    job->normalise_clm = rq->normalise_clm;
+    if (rq->mode == PA_MODE_CHARGE_ARM) {
+        if (rq->maxdist_optimize) maxdist = orc_charge_arm_maxdist(t, rq->ref_type, rq->normalise_clm);
+    } else if (rq->maxdist_optimize) {
         double lim = t->box_hi[0] - t->box_lo[0];                 /* give_box_limit = MINVAL(box_size) */
         for (int k = 1; k < 3; ++k) { double l = t->box_hi[k] - t->box_lo[k]; if (l < lim) lim = l; }
         maxdist = (float)(lim / 2.0);                             /* REAL8/REAL4 -> REAL4 */
@@ -231,6 +235,7 @@ int orc_job_setup(const pa_traj *t, const pa_job_request *rq, pa_job *job)
 
 /* ------------------------------------------------------------------------ */
 /* fill_histogram, Distribution:762-845, for one frame and one observed type. */
+static void orc_fill_histogram_charge_arm(const pa_traj *t, const pa_job *job, int step, int64_t *hist, int64_t *within, int64_t *oob);
 static void orc_fill_histogram(const pa_traj *t, const pa_job *job, int step, int obs_type0,
                                int64_t *hist, int64_t *within, int64_t *oob)
 {
@@ -311,7 +316,9 @@ int orc_distribution_histogram_shard(const pa_traj *t, const pa_job *job, int sh
         for (int k = 0; k < nsamp; ++k) {
             if (k % shard_count != shard_rank) continue;
             int step = k * dt;
-            if (job->obs_type < 1) {
+            if (job->mode == PA_MODE_CHARGE_ARM) {
+                orc_fill_histogram_charge_arm(t, job, step, hl, &wl, &ol);
+            } else if (job->obs_type < 1) {
                 for (int ot = 0; ot < t->ntypes; ++ot) orc_fill_histogram(t, job, step, ot, hl, &wl, &ol);
             } else {
                 orc_fill_histogram(t, job, step, job->obs_type - 1, hl, &wl, &ol);
@@ -380,11 +387,17 @@ int orc_transfer_histogram(const pa_traj *t, const pa_job *job, const int64_t *h
             if (job->mode == PA_MODE_CDF) chunk_volume = chunk_area * job->step_b;   /* :958 */
             else {
                 float b = (float)ib * job->step_b;
-                chunk_volume = chunk_area * (cosf(b - job->step_b) - cosf(b));       /* :962 */
+                if (job->mode == PA_MODE_CHARGE_ARM) chunk_volume = cosf(b - job->step_b) - cosf(b);    /* :967 */
+                else chunk_volume = chunk_area * (cosf(b - job->step_b) - cosf(b));  /* :962 */
             }
             size_t idx = (size_t)(ib - 1) * na + (ia - 1);
             g[idx] = g[idx] / chunk_volume;                                          /* :972 */
         }
+    }
+    if (job->mode == PA_MODE_CHARGE_ARM) {                                           /* :976, SUM in array element order */
+        float sum = 0.0f;
+        for (size_t i = 0; i < (size_t)na * nb; ++i) sum = sum + g[i];
+        for (size_t i = 0; i < (size_t)na * nb; ++i) g[i] = g[i] / sum;
     }
     *ideal_density_out = ideal_density;
     return rc;
@@ -466,7 +479,11 @@ int orc_write_distribution(const pa_traj *t, const pa_job *job, int reference_nu
     snprintf(header, sizeof header, "reference vector %+d %+d %+d, ", job->ref_xyz[0], job->ref_xyz[1], job->ref_xyz[2]);
     /* TRIM(headerline) drops the trailing blank before the next piece is appended (:1029,:1034) */
     size_t hl = strlen(header); while (hl && header[hl - 1] == ' ') header[--hl] = 0;
-    if (job->obs_type < 1) {
+    if (job->mode == PA_MODE_CHARGE_ARM) {                                           /* :1008-1024 */
+        const char *what = reference_charge != 0 ? "charge_arm" : "dipole_moment";
+        snprintf(base + strlen(base), sizeof base - strlen(base), "%s%s_type_%d", job->normalise_clm ? "CLM-normalised_" : "", what, job->ref_type);
+        snprintf(header + hl, sizeof header - hl, " %s for molecule type %d,", reference_charge != 0 ? "charge arm" : "dipole moment", job->ref_type);
+    } else if (job->obs_type < 1) {
         snprintf(base + strlen(base), sizeof base - strlen(base), "all_around_%d", job->ref_type);
         snprintf(header + hl, sizeof header - hl, " all molecules around type %d,", job->ref_type);
     } else {
@@ -482,6 +499,29 @@ int orc_write_distribution(const pa_traj *t, const pa_job *job, int reference_nu
         snprintf(mainname, sizeof mainname, "%s%s_cdf", base, job->weigh_charge ? "_xcharge" : "");
         strcat(header, " cylindrical distribution function");
         unitline = "a(perpendicular_distance) b(collinear_distance) g(a,b)";
+    } else if (job->mode == PA_MODE_CHARGE_ARM) {                                    /* :1112-1139 */
+        shift_b = 0.0f;
+        char trace_name[2200];
+        snprintf(trace_name, sizeof trace_name, "%s_rdf", base);
+        snprintf(mainname, sizeof mainname, "%s%s_pdf", base, job->subtract_uniform ? "_-trace" : "");
+        FILE *ft = fopen(trace_name, "w");
+        if (!ft) return 26;
+        fprintf(ft, "%s radial distribution function (trace of pdf)\n", header);
+        fprintf(ft, "distance g(r)\n");
+        for (int ia = 1; ia <= na; ++ia) {
+            float trace = 0.0f;
+            for (int ib = 0; ib < nb; ++ib) trace = trace + g[(size_t)ib * na + (ia - 1)];
+            trace = trace / (float)nb;
+            float a = (float)ia * job->step_a;
+            a = a - 0.5f * job->step_a;
+            float rowt[2] = { a, trace };
+            orc_write_reals(ft, rowt, 2);
+            if (job->subtract_uniform)
+                for (int ib = 0; ib < nb; ++ib) g[(size_t)ib * na + (ia - 1)] = g[(size_t)ib * na + (ia - 1)] - trace;
+        }
+        fclose(ft);
+        unitline = "a(distance) b(polar_angle) g(a,b)";
+        strcat(header, " polar distribution function");
     } else {
         shift_b = 0.0f;
         char trace_name[2200];
@@ -533,7 +573,7 @@ int orc_write_distribution(const pa_traj *t, const pa_job *job, int reference_nu
         unitline = "a(distance) b(polar_angle) g(a,b)";
         strcat(header, " polar distribution function");
     }
-    if (job->weigh_charge) strcat(header, ", weighed by charge");
+    if (job->weigh_charge && job->mode != PA_MODE_CHARGE_ARM) strcat(header, ", weighed by charge");
     f3 = fopen(mainname, "w");
     if (!f3) return 26;
     fprintf(f3, "Output in this file is based on the input file '%s':\n", input_file_name);
@@ -542,7 +582,7 @@ int orc_write_distribution(const pa_traj *t, const pa_job *job, int reference_nu
         for (int ib = 1; ib <= nb; ++ib) {
             float a = ((float)ia * job->step_a) - 0.5f * job->step_a;
             float b = (((float)ib * job->step_b) - 0.5f * job->step_b) - shift_b;
-            if (job->mode == PA_MODE_PDF) b = (float)((double)b * ORC_DEGREES);
+            if (job->mode != PA_MODE_CDF) b = (float)((double)b * ORC_DEGREES);
             float row[3] = { a, b, g[(size_t)(ib - 1) * na + (ia - 1)] };
             orc_write_reals(f3, row, 3);
         }
@@ -783,4 +823,78 @@ int orc_unwrap_full(pa_traj *t)
     }
     free(acc); free(jumped);
     return 0;
+}
+
+/* ------------------------------------------------------------------------ */
+/* charge_arm mode.  charge_arm(): Molecular:2926-2937; compute_squared_radius_of_gyration:
+ * Molecular:945-972; optimise_charge_arm: Distribution:1232-1269; fill_histogram_charge_arm:
+ * Distribution:847-895. */
+static void orc_charge_arm_vec(const pa_traj *t, int step, int type, int mol, double out[3])
+{
+    const pa_type *ty = &t->types[type];
+    const float *r = ty->xyz + ((size_t)step * ty->nmol + mol) * (size_t)ty->natoms * 3;
+    double qd[3] = { 0, 0, 0 };
+    for (int a = 0; a < ty->natoms; ++a)
+        for (int k = 0; k < 3; ++k) { double w = (double)r[a * 3 + k]; w = w * ty->atom_charge[a]; qd[k] = qd[k] + w; }
+    if (ty->charge == 0) { out[0] = qd[0]; out[1] = qd[1]; out[2] = qd[2]; return; }
+    double c[3];
+    orc_center_of_mass(t, step, type, mol, c);
+    for (int k = 0; k < 3; ++k) {
+        const double ca = qd[k] / (double)ty->realcharge;
+        out[k] = (double)ty->realcharge * (ca - c[k]);
+    }
+}
+
+static double orc_rgy_sq(const pa_traj *t, int step, int type, int mol)
+{
+    const pa_type *ty = &t->types[type];
+    const float *r = ty->xyz + ((size_t)step * ty->nmol + mol) * (size_t)ty->natoms * 3;
+    double c[3], rgy = 0.0;
+    orc_center_of_mass(t, step, type, mol, c);
+    for (int a = 0; a < ty->natoms; ++a) {
+        double d[3];
+        for (int k = 0; k < 3; ++k) d[k] = (double)r[a * 3 + k] - c[k];
+        const double d2 = (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2];
+        rgy = rgy + ty->atom_mass[a] * d2;
+    }
+    return rgy / ty->mass;
+}
+
+/* optimise_charge_arm (first time step only): returns the REAL(4) maxdist */
+float orc_charge_arm_maxdist(const pa_traj *t, int ref_type, int normalise_clm)
+{
+    const int ty = ref_type - 1;
+    float maxdist = 0.0f;
+    for (int m = 0; m < t->types[ty].nmol; ++m) {
+        double v[3];
+        orc_charge_arm_vec(t, 0, ty, m, v);
+        float chargearm = (float)sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+        if (normalise_clm) chargearm = (float)((double)chargearm / (t->types[ty].mass * orc_rgy_sq(t, 0, ty, m)));
+        if (chargearm > maxdist) maxdist = chargearm;
+    }
+    if (normalise_clm) { maxdist = maxdist * 100000.0f; maxdist = (float)(int)ceilf(maxdist); maxdist = maxdist / 100000.0f; }
+    else { maxdist = maxdist * 10.0f; maxdist = (float)(int)ceilf(maxdist); maxdist = maxdist / 10.0f; }
+    if (maxdist < 0.0f) maxdist = 10.0f;
+    return maxdist;
+}
+
+static void orc_fill_histogram_charge_arm(const pa_traj *t, const pa_job *job, int step, int64_t *hist, int64_t *within, int64_t *oob)
+{
+    const int ty = job->ref_type - 1;
+    for (int m = 0; m < t->types[ty].nmol; ++m) {
+        double link[3];
+        orc_charge_arm_vec(t, step, ty, m, link);
+        if (job->normalise_clm) {
+            const double den = t->types[ty].mass * orc_rgy_sq(t, step, ty, m);
+            for (int k = 0; k < 3; ++k) link[k] = link[k] / den;
+        }
+        const float a = (float)sqrt((link[0] * link[0] + link[1] * link[1]) + link[2] * link[2]);
+        if (a < 1E-8f) { *oob += 1; continue; }
+        for (int k = 0; k < 3; ++k) link[k] = link[k] / (double)a;
+        const double dot = ((0.0 + link[0] * job->ref_vec[0]) + link[1] * job->ref_vec[1]) + link[2] * job->ref_vec[2];
+        const float b = (float)acos(dot);
+        const int ia = orc_plus1(orc_int_of_float(a / job->step_a)), ib = orc_plus1(orc_int_of_float(b / job->step_b));
+        if (ia > 0 && ia <= job->bin_a && ib > 0 && ib <= job->bin_b) { *within += 1; hist[(size_t)(ib - 1) * job->bin_a + (ia - 1)] += 1; }
+        else *oob += 1;
+    }
 }

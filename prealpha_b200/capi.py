@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libprealpha_b200.so")
 
 PA_MODE_CDF = 0
 PA_MODE_PDF = 1
+PA_MODE_CHARGE_ARM = 2
 PA_ERR_NO_DEVICE = -1
 PA_ERR_CUDA = -2
 PA_ERR_BAD_ARG = -3
@@ -50,7 +51,7 @@ class pa_job_request(C.Structure):
         ("mode", C.c_int32), ("ref_xyz", C.c_int32 * 3), ("ref_type", C.c_int32), ("obs_type", C.c_int32),
         ("bin_a", C.c_int32), ("bin_b", C.c_int32), ("sampling_interval", C.c_int32),
         ("weigh_charge", C.c_int32), ("use_coc", C.c_int32), ("subtract_uniform", C.c_int32),
-        ("maxdist_optimize", C.c_int32), ("maxdist", C.c_float),
+        ("maxdist_optimize", C.c_int32), ("maxdist", C.c_float), ("normalise_clm", C.c_int32),
     ]
 
 
@@ -61,7 +62,7 @@ class pa_job(C.Structure):
         ("maxdist", C.c_float), ("step_a", C.c_float), ("step_b", C.c_float), ("shift", C.c_float),
         ("bin_a", C.c_int32), ("bin_b", C.c_int32), ("sampling_interval", C.c_int32),
         ("weigh_charge", C.c_int32), ("use_coc", C.c_int32), ("subtract_uniform", C.c_int32),
-        ("aligned", C.c_int32), ("_pad", C.c_int32),
+        ("aligned", C.c_int32), ("normalise_clm", C.c_int32),
     ]
 
 
@@ -263,9 +264,10 @@ def cubic_box_edge(lo: float, hi: float):
 
 def make_request(mode="pdf", vec=(0, 0, 1), ref_type=1, obs_type=1, bin_a=100, bin_b=100, sampling_interval=10,
                  weigh_charge=False, use_coc=False, subtract_uniform=False, maxdist_optimize=False,
-                 maxdist=10.0) -> pa_job_request:
+                 maxdist=10.0, normalise_clm=False) -> pa_job_request:
     r = pa_job_request()
-    r.mode = PA_MODE_PDF if mode in ("pdf", "podf", PA_MODE_PDF) else PA_MODE_CDF
+    r.mode = PA_MODE_CHARGE_ARM if mode in ("charge_arm", PA_MODE_CHARGE_ARM) else (PA_MODE_PDF if mode in ("pdf", "podf", PA_MODE_PDF) else PA_MODE_CDF)
+    r.normalise_clm = int(normalise_clm)
     for k in range(3):
         r.ref_xyz[k] = int(vec[k])
     r.ref_type, r.obs_type = int(ref_type), int(obs_type)

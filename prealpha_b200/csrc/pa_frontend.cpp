@@ -526,7 +526,7 @@ struct DistInput {
     int mode = PA_MODE_PDF;
     std::vector<std::array<int, 5>> refs;
     int sampling_interval = 10, bin_a = 100, bin_b = 100;        // Distribution:9-16
-    bool subtract_uniform = false, weigh_charge = false, use_coc = false, maxdist_optimize = false;
+    bool subtract_uniform = false, weigh_charge = false, use_coc = false, maxdist_optimize = false, normalise_clm = false;
     float maxdist = 10.0f;
 };
 
@@ -542,7 +542,7 @@ int read_distribution_input(Run &r, const std::string &name, DistInput &d)
     if (mode == "podf") mode = "pdf";
     if (mode == "cdf") d.mode = PA_MODE_CDF;
     else if (mode == "pdf") d.mode = PA_MODE_PDF;
-    else if (mode == "charge_arm") { r.error(0, "charge_arm mode is outside the accelerated path (O(N) per frame; see DESIGN.md)"); return PA_ERR_UNSUPPORTED; }
+    else if (mode == "charge_arm") d.mode = PA_MODE_CHARGE_ARM;
     else { r.error(99, "incorrect format in distribution input"); return 99; }
     int nref = 0;
     if (toks[0].size() < 2 || !parse_int(toks[0][1], nref) || nref < 0 || (int)toks.size() < 1 + nref) { r.error(99, "incorrect format in distribution input"); return 99; }
@@ -550,8 +550,9 @@ int read_distribution_input(Run &r, const std::string &name, DistInput &d)
     for (int n = 0; n < nref; ++n) {
         std::array<int, 5> v{};
         const auto &tk = toks[1 + n];
-        bool ok = tk.size() >= 5;
-        for (int k = 0; ok && k < 5; ++k) ok = parse_int(tk[k], v[k]);
+        const int nfields = d.mode == PA_MODE_CHARGE_ARM ? 4 : 5;            // Distribution:427-445: charge_arm references have no observed type
+        bool ok = (int)tk.size() >= nfields;
+        for (int k = 0; ok && k < nfields; ++k) ok = parse_int(tk[k], v[k]);
         if (!ok) { r.error(99, "incorrect format in distribution input"); return 99; }
         if (v[3] > ntypes || v[3] < 1 || v[4] > ntypes) { r.error(33, "molecule type index does not exist"); return 33; }
         d.refs.push_back(v);
@@ -569,9 +570,19 @@ int read_distribution_input(Run &r, const std::string &name, DistInput &d)
             d.maxdist_optimize = false;
             float v; if (tk.size() > 1 && parse_real4(tk[1], v)) d.maxdist = v; else { r.error(100, "cannot read 'maxdist'"); d.maxdist = 10.0f; }
         } else if (k == "maxdist_optimize" || k == "maxdist_optimise") d.maxdist_optimize = true;
-        else if (k == "subtract_uniform") { if (d.mode == PA_MODE_PDF) want_log(d.subtract_uniform, false); }
-        else if (k == "weigh_charge") want_log(d.weigh_charge, false);
-        else if (k == "use_coc" || k == "use_COC" || k == "center_of_charge" || k == "centre_of_charge") want_log(d.use_coc, false);
+        else if (k == "subtract_uniform") {
+            if (d.mode != PA_MODE_CDF) want_log(d.subtract_uniform, false);
+            else printf("   subtract_uniform is only available for polar distribution functions.\n");
+        } else if (k == "weigh_charge") {
+            if (d.mode == PA_MODE_CHARGE_ARM) printf(" charge weighing not available for charge_arm analysis.\n");
+            else want_log(d.weigh_charge, false);
+        } else if (k == "normalise_CLM" || k == "normalise_charge_arm" || k == "normalize_CLM" || k == "normalize_charge_arm" || k == "normalise_clm") {
+            if (d.mode == PA_MODE_CHARGE_ARM) want_log(d.normalise_clm, false);
+            else printf(" The charge lever moment normalisation is only available for charge_arm analysis.\n");
+        } else if (k == "use_coc" || k == "use_COC" || k == "center_of_charge" || k == "centre_of_charge") {
+            if (d.mode == PA_MODE_CHARGE_ARM) printf(" center_of_charge not available for charge_arm analysis.\n");
+            else want_log(d.use_coc, false);
+        }
         else if (k == "quit") break;
         if (d.bin_a < 1) { d.bin_a = 1; r.error(104, "bin count out of range"); } else if (d.bin_a > 1000) { d.bin_a = 1000; r.error(104, "bin count out of range"); }
         if (d.bin_b < 1) { d.bin_b = 1; r.error(104, "bin count out of range"); } else if (d.bin_b > 1000) { d.bin_b = 1000; r.error(104, "bin count out of range"); }
@@ -615,7 +626,13 @@ int perform_distribution(Run &r, const std::string &input_name)     // Distribut
         rq.ref_type = d.refs[n][3]; rq.obs_type = d.refs[n][4];
         rq.bin_a = d.bin_a; rq.bin_b = d.bin_b; rq.sampling_interval = d.sampling_interval;
         rq.weigh_charge = d.weigh_charge; rq.use_coc = d.use_coc; rq.subtract_uniform = d.subtract_uniform;
-        rq.maxdist_optimize = d.maxdist_optimize; rq.maxdist = d.maxdist;
+        rq.maxdist_optimize = d.maxdist_optimize; rq.maxdist = d.maxdist; rq.normalise_clm = d.normalise_clm;
+        if (d.mode == PA_MODE_CHARGE_ARM) {                       // Distribution:1205-1207 (check_charges, Molecular:191-202)
+            const HostType &h = r.types[rq.ref_type - 1];
+            bool any = false;
+            for (double q : h.atom_charge) if (std::fabs((float)q) > 0.001f) { any = true; break; }
+            if (!any) r.error(127, "something is wrong with the atomic charges of this molecule type index");
+        }
         rc = pa_job_setup(&traj, &rq, &jobs[n]);
         if (rc) { r.error(rc, pa_last_error()); return rc; }
     }
@@ -872,6 +889,20 @@ void write_simple_sumrules(Run &r)                            // Distribution:43
     if (r.verbose) printf(" File 'prealpha_simple.inp' written.\n");
 }
 
+void write_simple_charge_arm(Run &r, bool normalise)          // Distribution:69-96
+{
+    const std::string path = r.path_in + "prealpha_simple.inp";
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) { r.error(46, "cannot write '" + path + "'"); return; }
+    fprintf(f, "charge_arm %zu\n", r.types.size());
+    for (size_t n = 1; n <= r.types.size(); ++n) fprintf(f, "+0 +0 +1 %zu\n", n);
+    fprintf(f, "maxdist_optimize\nsubtract_uniform F\nsampling_interval 1\nbin_count_a 100\nbin_count_b 100\n");
+    if (normalise) fprintf(f, "normalise_clm T\n");
+    fprintf(f, "quit\n");
+    fclose(f);
+    if (r.verbose) printf(" File 'prealpha_simple.inp' written.\n");
+}
+
 const char *kOtherModuleKeywords[] = {
     "show_settings", "print_atomic_masses", "print_atomic_charges", "print_dipole_statistics", "show_drude",
     "switch_to_com", "barycentric", "barycenter", "barycentre", "dump_snapshot", "dump_snapshot_simple", "dump_split",
@@ -968,6 +999,13 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
             write_simple_sumrules(r);
             printf(" Distribution module invoked.\n");
+            perform_distribution(r, "prealpha_simple.inp");
+        } else if (k == "charge_arm_simple" || k == "clm_simple" || k == "CLM_simple" || k == "charge_lever_moment_simple") {   // Main:3518-3535
+            const bool clm = k != "charge_arm_simple";
+            printf(" Distribution module invoked - simple mode:\n");
+            printf(clm ? " CLM distribution. Requires charges to be initialised.\n (charge arm with charge lever moment correction)\n"
+                       : " Charge Arm distribution. Requires charges to be initialised.\n");
+            write_simple_charge_arm(r, clm);
             perform_distribution(r, "prealpha_simple.inp");
         } else if (k == "distance" || k == "distances") {                    // Main:3379-3390
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }

@@ -173,6 +173,44 @@ void pa::build_thr_b(const pa_job &job, std::vector<double> &thr)
     }
 }
 
+// charge_arm mode: a-class of the squared arm length S: INT(REAL4(SQRT(S))/step_a), clamped to
+// [0, bin_a] (bin_a = out of range); lengths below 1E-8 are out of bounds before binning
+// (Distribution:861-866), reported through tiny_bits = smallest S with REAL4(SQRT(S)) >= 1E-8.
+static int charge_arm_class_of(const pa_job &job, double S)
+{
+    const float a = (float)std::sqrt(S);
+    const int ia = int_of_float_x86(a / job.step_a);
+    return (ia < 0 || ia >= job.bin_a) ? job.bin_a : ia;
+}
+
+void pa::build_thr_charge_arm(const pa_job &job, std::vector<unsigned long long> &thr, unsigned long long &tiny_bits)
+{
+    const int na = job.bin_a;
+    const unsigned long long inf_bits = 0x7ff0000000000000ull, never = ~0ull;
+    thr.assign((size_t)na + 3, never);
+    thr[0] = 0;
+    {   // smallest S with !(a < 1E-8)
+        unsigned long long lo = 0, hi = inf_bits;      // a(lo) < 1E-8 <= a(hi)
+        while (hi - lo > 1) {
+            const unsigned long long mid = lo + (hi - lo) / 2;
+            if ((float)std::sqrt(double_of(mid)) < 1E-8f) lo = mid; else hi = mid;
+        }
+        tiny_bits = hi;
+    }
+    // INT(a/step_a) is monotone in S for step_a > 0; for step_a <= 0 or NaN every length is out of range.
+    if (!(job.step_a > 0.0f)) { for (int k = 1; k <= na; ++k) thr[k] = 0; return; }
+    for (int k = 1; k <= na; ++k) {
+        if (charge_arm_class_of(job, double_of(inf_bits)) < k) { thr[k] = never; continue; }
+        unsigned long long lo = thr[k - 1] == never ? inf_bits : thr[k - 1], hi = inf_bits;
+        if (charge_arm_class_of(job, double_of(lo)) >= k) { thr[k] = lo; continue; }
+        while (hi - lo > 1) {
+            const unsigned long long mid = lo + (hi - lo) / 2;
+            if (charge_arm_class_of(job, double_of(mid)) >= k) hi = mid; else lo = mid;
+        }
+        thr[k] = hi;
+    }
+}
+
 // The RDF fast kernel decides the a-bin only and sends pairs whose link vector is within
 // |link_xy|^2 < 2^-30 A^2 of the z axis to the literal evaluation.  That is sufficient when the
 // b-dimension has a single bin, the reference vector is +-z, the link vector is the
@@ -187,6 +225,63 @@ bool pa::job_is_rdf_fast(const pa_job &job, const pa_traj &traj)
     return true;
 }
 
+// charge_arm helpers on the host (first time step only, for optimise_charge_arm, Distribution:1232-1269)
+namespace {
+
+void host_com(const pa_traj &t, const pa_type &ty, const float *r, double c[3])       // Molecular:2804-2833
+{
+    if (t.com_boost) { c[0] = (double)r[0]; c[1] = (double)r[1]; c[2] = (double)r[2]; return; }
+    c[0] = c[1] = c[2] = 0.0;
+    for (int a = 0; a < ty.natoms; ++a)
+        for (int k = 0; k < 3; ++k) { double w = (double)r[a * 3 + k]; w = w * ty.atom_mass[a]; c[k] = c[k] + w; }
+    for (int k = 0; k < 3; ++k) c[k] = c[k] / ty.mass;
+}
+
+void host_charge_arm(const pa_traj &t, const pa_type &ty, const float *r, double out[3])   // Molecular:2926-2937
+{
+    double qd[3] = { 0.0, 0.0, 0.0 };
+    for (int a = 0; a < ty.natoms; ++a)
+        for (int k = 0; k < 3; ++k) { double w = (double)r[a * 3 + k]; w = w * ty.atom_charge[a]; qd[k] = qd[k] + w; }
+    if (ty.charge == 0) { out[0] = qd[0]; out[1] = qd[1]; out[2] = qd[2]; return; }
+    double c[3];
+    host_com(t, ty, r, c);
+    for (int k = 0; k < 3; ++k) { const double ca = qd[k] / (double)ty.realcharge; out[k] = (double)ty.realcharge * (ca - c[k]); }
+}
+
+double host_rgy_sq(const pa_traj &t, const pa_type &ty, const float *r)                   // Molecular:945-972
+{
+    double c[3], rgy = 0.0;
+    host_com(t, ty, r, c);
+    for (int a = 0; a < ty.natoms; ++a) {
+        const double dx = (double)r[a * 3] - c[0], dy = (double)r[a * 3 + 1] - c[1], dz = (double)r[a * 3 + 2] - c[2];
+        const double d2 = (dx * dx + dy * dy) + dz * dz;
+        rgy = rgy + ty.atom_mass[a] * d2;
+    }
+    return rgy / ty.mass;
+}
+
+float charge_arm_maxdist(const pa_traj &t, int type, bool clm)
+{
+    const pa_type &ty = t.types[type];
+    float maxdist = 0.0f;
+    for (int m = 0; m < ty.nmol; ++m) {
+        const float *r = ty.xyz + (size_t)m * ty.natoms * 3;
+        double v[3];
+        host_charge_arm(t, ty, r, v);
+        float arm = (float)std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+        if (clm) arm = (float)((double)arm / (ty.mass * host_rgy_sq(t, ty, r)));
+        if (arm > maxdist) maxdist = arm;
+    }
+    const float scale = clm ? 100000.0f : 10.0f;                                          // :1256-1264
+    maxdist = maxdist * scale;
+    maxdist = (float)int_of_float_x86(std::ceil(maxdist));
+    maxdist = maxdist / scale;
+    if (maxdist < 0.0f) maxdist = 10.0f;
+    return maxdist;
+}
+
+}  // namespace
+
 // ---------------------------------------------------------------------------
 extern "C" {
 
@@ -194,7 +289,7 @@ int pa_job_setup(const pa_traj *traj, const pa_job_request *rq, pa_job *job)
 {
     if (!traj || !rq || !job) return PA_ERR_BAD_ARG;
     memset(job, 0, sizeof *job);
-    if (rq->mode != PA_MODE_PDF && rq->mode != PA_MODE_CDF) { pa::set_error("unknown operation mode (error 99)"); return PA_E_DIST_INPUT_FORMAT; }
+    if (rq->mode != PA_MODE_PDF && rq->mode != PA_MODE_CDF && rq->mode != PA_MODE_CHARGE_ARM) { pa::set_error("unknown operation mode (error 99)"); return PA_E_DIST_INPUT_FORMAT; }
     if (rq->ref_type < 1 || rq->ref_type > traj->ntypes || rq->obs_type > traj->ntypes) {
         pa::set_error("molecule type index out of range (error 33)");           // Distribution:415-427
         return PA_E_TYPE_INVALID;
@@ -206,9 +301,18 @@ int pa_job_setup(const pa_traj *traj, const pa_job_request *rq, pa_job *job)
     job->sampling_interval = rq->sampling_interval;
     job->weigh_charge = rq->weigh_charge ? 1 : 0;
     job->use_coc = rq->use_coc ? 1 : 0;
-    job->subtract_uniform = (rq->subtract_uniform && rq->mode == PA_MODE_PDF) ? 1 : 0;
+    job->subtract_uniform = (rq->subtract_uniform && rq->mode != PA_MODE_CDF) ? 1 : 0;
+    job->normalise_clm = (rq->normalise_clm && rq->mode == PA_MODE_CHARGE_ARM) ? 1 : 0;
     float maxdist = rq->maxdist;
-    if (rq->maxdist_optimize) {                                                   // Distribution:526-534
+    if (rq->mode == PA_MODE_CHARGE_ARM) {
+        if (rq->maxdist_optimize) {
+            const pa_type &ty = traj->types[rq->ref_type - 1];
+            if (!ty.xyz || traj->nsteps < 1 || !ty.atom_mass || !ty.atom_charge) {
+                pa::set_error("charge_arm maxdist_optimize needs the first time step, masses and charges"); return PA_ERR_BAD_ARG;
+            }
+            maxdist = charge_arm_maxdist(*traj, rq->ref_type - 1, job->normalise_clm != 0);
+        }
+    } else if (rq->maxdist_optimize) {                                                   // Distribution:526-534
         double lim = traj->box_hi[0] - traj->box_lo[0];
         for (int k = 1; k < 3; ++k) lim = std::min(lim, traj->box_hi[k] - traj->box_lo[k]);
         maxdist = (float)(lim / 2.0);
@@ -231,6 +335,7 @@ int pa_job_setup(const pa_traj *traj, const pa_job_request *rq, pa_job *job)
         return PA_ERR_UNSUPPORTED;
     }
     if (job->sampling_interval < 1) { pa::set_error("sampling_interval < 1"); return PA_ERR_BAD_ARG; }
+    if (rq->mode == PA_MODE_CHARGE_ARM && maxdist < 0.0f) { pa::set_error("charge_arm: negative maxdist"); return PA_ERR_UNSUPPORTED; }
     normalize3(job->ref_vec);                                                     // Distribution:665-667
     prepare_rotation_to_z(job->ref_vec, job->rot, &job->aligned);
     return 0;
@@ -281,11 +386,17 @@ int pa_transfer_histogram(const pa_traj *traj, const pa_job *job, const int64_t 
                 chunk_volume = chunk_area * job->step_b;                          // :958
             } else {
                 const float b = (float)ib * job->step_b;
-                chunk_volume = chunk_area * (cosf(b - job->step_b) - cosf(b));    // :962
+                if (job->mode == PA_MODE_CHARGE_ARM) chunk_volume = cosf(b - job->step_b) - cosf(b);   // :967
+                else chunk_volume = chunk_area * (cosf(b - job->step_b) - cosf(b));                   // :962
             }
             float &v = g[(size_t)(ib - 1) * na + (ia - 1)];
             v = v / chunk_volume;                                                 // :972
         }
+    }
+    if (job->mode == PA_MODE_CHARGE_ARM) {                                        // :976 (SUM in array element order)
+        float sum = 0.0f;
+        for (size_t i = 0; i < n; ++i) sum = sum + g[i];
+        for (size_t i = 0; i < n; ++i) g[i] = g[i] / sum;
     }
     *ideal_density_out = rho;
     return rc;
@@ -365,7 +476,13 @@ extern "C" int pa_write_distribution(const pa_traj *traj, const pa_job *job, int
     std::string base = std::string(path_prefix) + "reference_" + std::to_string(reference_number) + "_";   // :1004
     snprintf(tmp, sizeof tmp, "reference vector %+d %+d %+d, ", job->ref_xyz[0], job->ref_xyz[1], job->ref_xyz[2]);
     std::string header = tmp;
-    if (job->obs_type < 1) {                                                      // :1025-1036
+    const bool arm = job->mode == PA_MODE_CHARGE_ARM;
+    if (arm) {                                                                    // :1008-1024
+        base += std::string(job->normalise_clm ? "CLM-normalised_" : "") + (ref_charge != 0 ? "charge_arm" : "dipole_moment") +
+                "_type_" + std::to_string(job->ref_type);
+        header = rtrim(header) + (ref_charge != 0 ? " charge arm" : " dipole moment") + " for molecule type " +
+                 std::to_string(job->ref_type) + ",";
+    } else if (job->obs_type < 1) {                                               // :1025-1036
         base += "all_around_" + std::to_string(job->ref_type);
         header = rtrim(header) + " all molecules around type " + std::to_string(job->ref_type) + ", ";
     } else {
@@ -381,6 +498,26 @@ extern "C" int pa_write_distribution(const pa_traj *traj, const pa_job *job, int
         main_name = base + xc + "_cdf";
         header = rtrim(header) + " cylindrical distribution function";
         unitline = "a(perpendicular_distance) b(collinear_distance) g(a,b)";
+    } else if (arm) {                                                             // :1112-1139
+        shift_b = 0.0f;
+        const std::string trace_name = base + "_rdf";
+        main_name = base + (job->subtract_uniform ? "_-trace" : "") + "_pdf";
+        FILE *ft = fopen(trace_name.c_str(), "w");
+        if (!ft) { pa::set_error("cannot open output file " + trace_name + " (error 26)"); return 26; }
+        fprintf(ft, "%s radial distribution function (trace of pdf)\ndistance g(r)\n", rtrim(header).c_str());
+        for (int ia = 1; ia <= na; ++ia) {
+            float trace = 0.0f;
+            for (int ib = 0; ib < nb; ++ib) trace = trace + g[(size_t)ib * na + (ia - 1)];
+            trace = trace / (float)nb;
+            float a = (float)ia * job->step_a;
+            a = a - 0.5f * job->step_a;
+            write_reals(ft, { a, trace });
+            if (job->subtract_uniform)
+                for (int ib = 0; ib < nb; ++ib) g[(size_t)ib * na + (ia - 1)] = g[(size_t)ib * na + (ia - 1)] - trace;
+        }
+        fclose(ft);
+        unitline = "a(distance) b(polar_angle) g(a,b)";
+        header = rtrim(header) + " polar distribution function";
     } else {                                                                      // :1048-1111
         shift_b = 0.0f;
         const std::string trace_name = base + "_rdf" + xc;
@@ -423,7 +560,7 @@ extern "C" int pa_write_distribution(const pa_traj *traj, const pa_job *job, int
         unitline = "a(distance) b(polar_angle) g(a,b)";
         header = rtrim(header) + " polar distribution function";
     }
-    if (job->weigh_charge) header = rtrim(header) + ", weighed by charge";        // :1143
+    if (job->weigh_charge && !arm) header = rtrim(header) + ", weighed by charge";   // :1143
     FILE *f = fopen(main_name.c_str(), "w");
     if (!f) { pa::set_error("cannot open output file " + main_name + " (error 26)"); return 26; }
     fprintf(f, "Output in this file is based on the input file '%s':\n%s\n%s\n", input_file_name, rtrim(header).c_str(), unitline.c_str());
@@ -431,7 +568,7 @@ extern "C" int pa_write_distribution(const pa_traj *traj, const pa_job *job, int
         for (int ib = 1; ib <= nb; ++ib) {                                        // :1147-1154
             const float a = ((float)ia * job->step_a) - 0.5f * job->step_a;
             float b = (((float)ib * job->step_b) - 0.5f * job->step_b) - shift_b;
-            if (job->mode == PA_MODE_PDF) b = (float)((double)b * kDegrees);
+            if (job->mode != PA_MODE_CDF) b = (float)((double)b * kDegrees);
             write_reals(f, { a, b, g[(size_t)(ib - 1) * na + (ia - 1)] });
         }
     fclose(f);

@@ -131,6 +131,16 @@ int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
 int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
                             unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream);
 void pa_cell_grid_dims(int nmol, int g[3]);
+// charge_arm mode (O(N) per frame): one thread per reference molecule and frame
+struct PaChargeArmArgs {
+    const PaDevType *types;     // device array (raw coordinates of the resident batch)
+    int32_t type;               // reference type, 0-based
+    int32_t frame0, nframes;
+    int32_t normalise_clm, com_boost;
+    PaDevJob job;               // thr_a = classes of the squared arm length, thr_b as for pdf
+    unsigned long long tiny_bits;   // smallest squared length whose REAL(4) length is >= 1E-8
+};
+int pa_launch_charge_arm(const PaChargeArmArgs &a, void *stream);
 int pa_kernels_selfcheck();    // returns 0 when a kernel image for the current device exists
 int pa_rdf_ri(int nref);       // reference molecules per thread the fast kernel will use (tile = 128*RI)
 int pa_general_ri(int nref);
@@ -145,6 +155,7 @@ namespace pa {
 // class tables, see PaDevJob
 void build_thr_a(const pa_job &job, double max_dist_sq, std::vector<unsigned long long> &thr);
 void build_thr_b(const pa_job &job, std::vector<double> &thr);
+void build_thr_charge_arm(const pa_job &job, std::vector<unsigned long long> &thr, unsigned long long &tiny_bits);
 int  a_class_of(const pa_job &job, double max_dist_sq, double d2);   // reference arithmetic
 int  b_class_of(const pa_job &job, double dot);
 bool job_is_rdf_fast(const pa_job &job, const pa_traj &traj);

@@ -387,6 +387,79 @@ __global__ void __launch_bounds__(128) pa_exception_kernel(const __grid_constant
 }
 
 // ---------------------------------------------------------------------------
+// charge_arm mode: fill_histogram_charge_arm (Distribution:847-895) with charge_arm()
+// (Molecular:2926-2937) and compute_squared_radius_of_gyration (Molecular:945-972).
+__global__ void __launch_bounds__(128) pa_charge_arm_kernel(PaChargeArmArgs a)
+{
+    const PaDevType ty = a.types[a.type];
+    const long long total = (long long)a.nframes * ty.nmol;
+    const int na = a.job.bin_a, nb = a.job.bin_b, nbins = na * nb;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int frame = a.frame0 + (int)(id / ty.nmol), mol = (int)(id % ty.nmol);
+        const float *r = ty.xyz + ((size_t)frame * ty.nmol + mol) * (size_t)ty.natoms * 3;
+        double qd[3] = { 0.0, 0.0, 0.0 }, c[3] = { 0.0, 0.0, 0.0 }, link[3];
+        for (int at = 0; at < ty.natoms; ++at) {
+            const double q = ty.atom_charge[at], m = ty.atom_mass[at];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double x = (double)r[at * 3 + k];
+                qd[k] = __dadd_rn(qd[k], __dmul_rn(x, q));
+                c[k] = __dadd_rn(c[k], __dmul_rn(x, m));
+            }
+        }
+        if (a.com_boost) { c[0] = (double)r[0]; c[1] = (double)r[1]; c[2] = (double)r[2]; }   // Molecular:2810-2817
+        else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) c[k] = __ddiv_rn(c[k], ty.mass);
+        }
+        if (ty.charge == 0) { link[0] = qd[0]; link[1] = qd[1]; link[2] = qd[2]; }
+        else {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) link[k] = __dmul_rn(ty.realcharge, __dsub_rn(__ddiv_rn(qd[k], ty.realcharge), c[k]));
+        }
+        if (a.normalise_clm) {
+            double rgy = 0.0;
+            for (int at = 0; at < ty.natoms; ++at) {
+                const double dx = __dsub_rn((double)r[at * 3 + 0], c[0]), dy = __dsub_rn((double)r[at * 3 + 1], c[1]), dz = __dsub_rn((double)r[at * 3 + 2], c[2]);
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                rgy = __dadd_rn(rgy, __dmul_rn(ty.atom_mass[at], d2));
+            }
+            rgy = __ddiv_rn(rgy, ty.mass);
+            const double den = __dmul_rn(ty.mass, rgy);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) link[k] = __ddiv_rn(link[k], den);
+        }
+        const double S = __dadd_rn(__dadd_rn(__dmul_rn(link[0], link[0]), __dmul_rn(link[1], link[1])), __dmul_rn(link[2], link[2]));
+        const unsigned long long sb = dbits(S);
+        bool oob = !(sb >= a.tiny_bits) || !(S == S);              // a < 1E-8 (or NaN)
+        int ia = 0, ib = 0;
+        if (!oob) {
+            int lo = 0, hi = na;                                   // class in [0, na]; na = binpos_a out of range
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (a.job.thr_a[mid] <= sb) lo = mid; else hi = mid - 1; }
+            ia = lo;
+            const double af = (double)__double2float_rn(__dsqrt_rn(S));
+            const double lx = __ddiv_rn(link[0], af), ly = __ddiv_rn(link[1], af), lz = __ddiv_rn(link[2], af);
+            const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(lx, a.job.ref_vec[0])), __dmul_rn(ly, a.job.ref_vec[1])), __dmul_rn(lz, a.job.ref_vec[2]));
+            if (!(dot >= -1.0 && dot <= 1.0)) oob = true;
+            else {
+                int l2 = 0, h2 = nb;
+                while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (dot <= a.job.thr_b[mid]) l2 = mid; else h2 = mid - 1; }
+                ib = l2;
+            }
+            if (ia >= na || ib >= nb) oob = true;
+        }
+        if (oob) atomicAdd(&a.job.acc[nbins + 1], 1ull);
+        else { atomicAdd(&a.job.acc[ib * na + ia], 1ull); atomicAdd(&a.job.acc[nbins], 1ull); }
+    }
+}
+
+int pa_launch_charge_arm(const PaChargeArmArgs &a, void *stream)
+{
+    pa_charge_arm_kernel<<<148 * 4, 128, 0, (cudaStream_t)stream>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // launch wrappers
 
 static int pa_grid_for(long long n_items, int sm_count, int ctas_per_sm)

@@ -56,6 +56,7 @@ struct JobState {
     size_t nbins;
     unsigned long long *d_thr_a = nullptr;
     double *d_thr_b = nullptr;
+    unsigned long long tiny_bits = 0;   // charge_arm only
 };
 
 constexpr unsigned int kExcCap = 4u << 20;
@@ -181,10 +182,11 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
             delete s; pa::set_error("molecule type index out of range (error 33)"); return PA_E_TYPE_INVALID;
         }
         if (jb.bin_a < 1 || jb.bin_a > 1000 || jb.bin_b < 1 || jb.bin_b > 1000 || jb.sampling_interval < 1 ||
-            (jb.mode != PA_MODE_PDF && jb.mode != PA_MODE_CDF)) {
-            delete s; pa::set_error("invalid job (bins 1..1000, sampling_interval >= 1, mode cdf|pdf)"); return PA_ERR_BAD_ARG;
+            (jb.mode != PA_MODE_PDF && jb.mode != PA_MODE_CDF && jb.mode != PA_MODE_CHARGE_ARM)) {
+            delete s; pa::set_error("invalid job (bins 1..1000, sampling_interval >= 1, mode cdf|pdf|charge_arm)"); return PA_ERR_BAD_ARG;
         }
         s->types[jb.ref_type - 1].needed = true;
+        if (jb.mode == PA_MODE_CHARGE_ARM) continue;                // intramolecular: no observed types
         if (jb.obs_type < 1) for (auto &m : s->types) m.needed = true;
         else s->types[jb.obs_type - 1].needed = true;
         if (jb.use_coc) s->need_coc = true;
@@ -253,10 +255,11 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
         const pa_job &jb = js.job;
         std::vector<unsigned long long> thr_a;
         std::vector<double> thr_b;
-        pa::build_thr_a(jb, traj->max_dist_sq, thr_a);
+        if (jb.mode == PA_MODE_CHARGE_ARM) pa::build_thr_charge_arm(jb, thr_a, js.tiny_bits);
+        else pa::build_thr_a(jb, traj->max_dist_sq, thr_a);
         PA_CK(cudaMalloc(&js.d_thr_a, sizeof(unsigned long long) * thr_a.size()));
         PA_CK(cudaMemcpy(js.d_thr_a, thr_a.data(), sizeof(unsigned long long) * thr_a.size(), cudaMemcpyHostToDevice));
-        if (jb.mode == PA_MODE_PDF) {
+        if (jb.mode != PA_MODE_CDF) {
             pa::build_thr_b(jb, thr_b);
             PA_CK(cudaMalloc(&js.d_thr_b, sizeof(double) * thr_b.size()));
             PA_CK(cudaMemcpy(js.d_thr_b, thr_b.data(), sizeof(double) * thr_b.size(), cudaMemcpyHostToDevice));
@@ -273,7 +276,7 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
         d.guess_scale = 1.0f / jb.step_a;
         d.z_sign = jb.ref_vec[2] > 0 ? 1 : -1;
         d.acc = s->d_acc + js.acc_off;
-        js.fast = !s->force_general && pa::job_is_rdf_fast(jb, *traj);
+        js.fast = !s->force_general && pa::job_is_rdf_fast(jb, *traj);   // false for cdf and charge_arm
         {
             // variant 0 needs: no pair "inside the cutoff with a-bin out of range", and the cutoff within
             // 3e-7 (relative) of the boundary of bin na, so that the sliver between the two is always
@@ -292,6 +295,7 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     if (s->use_cells) {
         for (const JobState &js : s->jobs) {
             const int r = js.job.ref_type - 1;
+            if (js.job.mode == PA_MODE_CHARGE_ARM) continue;
             for (int o = 0; o < traj->ntypes; ++o) {
                 if (js.job.obs_type >= 1 && o != js.job.obs_type - 1) continue;
                 if (s->types[r].nmol >= 12500 && s->types[o].nmol >= 12500) { s->grids[r].enabled = true; s->grids[o].enabled = true; }
@@ -417,6 +421,16 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
     for (size_t j = 0; j < s->jobs.size(); ++j) {
         const pa_job &jb = s->jobs[j].job;
         const int r = jb.ref_type - 1;
+        if (jb.mode == PA_MODE_CHARGE_ARM) {                        // fill_histogram_charge_arm, Distribution:847-895
+            PaChargeArmArgs ca{};
+            ca.types = s->d_types[slot]; ca.type = r; ca.frame0 = first; ca.nframes = count;
+            ca.normalise_clm = jb.normalise_clm; ca.com_boost = s->box.com_boost;
+            ca.job = s->jobs[j].dj; ca.tiny_bits = s->jobs[j].tiny_bits;
+            PA_CK((cudaError_t)pa_launch_charge_arm(ca, s->s_compute));
+            s->stats.kernel_launches += 1;
+            s->stats.pairs_evaluated += (int64_t)count * s->types[r].nmol;   // molecules, not pairs, in this mode
+            continue;
+        }
         const int o_first = jb.obs_type < 1 ? 0 : jb.obs_type - 1;
         const int o_last = jb.obs_type < 1 ? (int)s->types.size() - 1 : jb.obs_type - 1;
         for (int o = o_first; o <= o_last; ++o) {

@@ -48,15 +48,18 @@ def parse_distribution_input(text: str, ntypes: int, box_limit: float | None = N
     head = _tokens(lines[0])
     mode = head[0]
     mode = {"cydf": "cdf", "podf": "pdf"}.get(mode, mode)
-    if mode not in ("cdf", "pdf"):
-        raise ValueError(99 if mode != "charge_arm" else -4)
+    if mode not in ("cdf", "pdf", "charge_arm"):
+        raise ValueError(99)
     nref = int(head[1])
     refs = []
+    ncol = 4 if mode == "charge_arm" else 5                      # Distribution:409 / :434
     for k in range(nref):
         t = _tokens(lines[1 + k])
-        v = [int(x) for x in t[:5]]
-        if len(v) < 5:
+        v = [int(x) for x in t[:ncol]]
+        if len(v) < ncol:
             raise ValueError(99)
+        if ncol == 4:
+            v.append(v[3])
         if v[3] > ntypes or v[3] < 1 or v[4] > ntypes:
             raise ValueError(33)
         refs.append(v)
@@ -83,12 +86,17 @@ def parse_distribution_input(text: str, ntypes: int, box_limit: float | None = N
                 # pa_job_setup does the same REAL(4) arithmetic from the box in pa_traj.
                 kw["maxdist_optimize"] = True
             elif key == "subtract_uniform":
-                if mode == "pdf":
+                if mode in ("pdf", "charge_arm"):
                     kw["subtract_uniform"] = _logical(t[1])
             elif key == "weigh_charge":
-                kw["weigh_charge"] = _logical(t[1])
+                if mode != "charge_arm":
+                    kw["weigh_charge"] = _logical(t[1])
             elif key in ("use_coc", "use_COC", "center_of_charge", "centre_of_charge"):
-                kw["use_coc"] = _logical(t[1])
+                if mode != "charge_arm":
+                    kw["use_coc"] = _logical(t[1])
+            elif key in ("normalise_CLM", "normalise_charge_arm", "normalize_CLM", "normalize_charge_arm", "normalise_clm"):
+                if mode == "charge_arm":
+                    kw["normalise_clm"] = _logical(t[1])
             elif key == "quit":
                 break
         except (IndexError, ValueError):
@@ -102,7 +110,8 @@ def parse_distribution_input(text: str, ntypes: int, box_limit: float | None = N
                                       bin_b=kw["bin_count_b"], sampling_interval=kw["sampling_interval"],
                                       weigh_charge=kw["weigh_charge"], use_coc=kw["use_coc"],
                                       subtract_uniform=kw["subtract_uniform"],
-                                      maxdist_optimize=kw["maxdist_optimize"], maxdist=kw["maxdist"]))
+                                      maxdist_optimize=kw["maxdist_optimize"], maxdist=kw["maxdist"],
+                                      normalise_clm=kw.get("normalise_clm", False)))
     return reqs
 
 

@@ -63,7 +63,7 @@ class Fixture:
         return {fn[len(pre):]: c for fn, c in self.files.items() if fn.startswith(pre)}
 
 
-ALL = ["bmim", "re4", "re4_atoms", "synth", "lmp", "lmp_wrap", "lmp_unwrap"]
+ALL = ["bmim", "re4", "re4_atoms", "synth", "lmp", "lmp_wrap", "lmp_unwrap", "charge_arm"]
 
 
 def available():

@@ -31,7 +31,10 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 def dist_text(mode, refs, **kw):
     lines = [f"{mode} {len(refs)}"]
     for vec, rt, ot in refs:
-        lines.append(f"{vec[0]:+d} {vec[1]:+d} {vec[2]:+d} {rt} {ot}")
+        if mode == "charge_arm":
+            lines.append(f"{vec[0]:+d} {vec[1]:+d} {vec[2]:+d} {rt}")
+        else:
+            lines.append(f"{vec[0]:+d} {vec[1]:+d} {vec[2]:+d} {rt} {ot}")
     for k, v in kw.items():
         if k == "maxdist_optimize":
             if v:
@@ -348,7 +351,46 @@ def case_lmp():
     shutil.rmtree(tmp)
 
 
-CASES = {"lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+def case_charge_arm():
+    """charge_arm mode (Distribution:847-895, 1232-1269) on the BMIM / NTf2 frame with the atomic charges of the
+    bmim fixture, plus 64 neutral three-site molecules appended to exercise the dipole-moment branch."""
+    src = os.path.join(REF, "Example_BMIMTFSI", "trajectory.xyz")
+    tmp = tempfile.mkdtemp()
+    traj = os.path.join(tmp, "traj.xyz")
+    rng = np.random.default_rng(2024)
+    lines = open(src).read().splitlines()
+    nwater = 64
+    centre = rng.uniform(0.0, 63.9223, size=(nwater, 1, 3))
+    water = centre + np.concatenate([np.zeros((nwater, 1, 3)), rng.normal(0.0, 0.6, size=(nwater, 2, 3))], axis=1)
+    water[5, 1:] = water[5, :1]                                  # one molecule with a vanishing dipole moment (a < 1E-8)
+    body = lines[2:2 + 20480] + [f"{el} {x:.5f} {y:.5f} {z:.5f}" for mol in water for el, (x, y, z) in zip("OHH", mol)]
+    natoms = 20480 + 3 * nwater
+    one = f"{natoms}\ncharge_arm fixture\n" + "\n".join(body) + "\n"
+    with open(traj, "w") as f:
+        f.write(one * 11)
+    types = [(-1, 15, 512), (+1, 25, 512), (0, 3, nwater)]
+    charges = []
+    for ch, na, _ in types[:2]:
+        q = rng.integers(-12, 13, size=na) / 16.0
+        q[-1] += ch - q.sum()
+        charges.append(q)
+    charges.append(np.array([-0.8125, 0.40625, 0.40625]))
+    jobs = [
+        ("ca1", "charge_arm", [(Z, 1, 1), ((1, 1, 0), 2, 2), ((0, 1, 0), 3, 3)],
+         dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=30, bin_count_b=20)),
+        ("ca2", "charge_arm", [((0, 0, -1), 2, 2), ((2, -1, 1), 1, 1), (Z, 3, 3)],
+         dict(maxdist_optimize=True, normalise_CLM=True, subtract_uniform=True, sampling_interval=1, bin_count_a=12, bin_count_b=9)),
+        ("ca3", "charge_arm", [(Z, 2, 2)], dict(maxdist="13.1", sampling_interval=5, bin_count_a=13, bin_count_b=1)),
+    ]
+    res = run_case("charge_arm", traj, "xyz", types, 11, ("0.0", "63.9223"), jobs, natoms, atom_charges=charges)
+    shutil.rmtree(tmp)
+    lo, hi = np.float32(0.0), np.float32(63.9223)
+    save("charge_arm", res, types, [lo] * 3, [hi] * 3, jobs, res["coords"][:1], res["elements"],
+         extra=dict(nsteps=np.int64(11), replicate=np.int64(11), atom_charge_0=charges[0], atom_charge_1=charges[1],
+                    atom_charge_2=charges[2]))
+
+
+CASES = {"charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"

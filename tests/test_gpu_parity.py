@@ -249,7 +249,7 @@ def test_wrap_trajectory_switch(oracle):
         assert np.array_equal(hists[k], h0) and (within[k], oob[k]) == (w0, o0)
 
 
-@pytest.mark.parametrize("name", ["synth", "lmp", "lmp_wrap", "lmp_unwrap"])
+@pytest.mark.parametrize("name", ["synth", "lmp", "lmp_wrap", "lmp_unwrap", "charge_arm"])
 def test_cli_drop_in_end_to_end(name, oracle, tmp_path):
     """general.inp -> molecular.inp -> xyz / lmp text -> GPU -> output files: byte-identical to what the
     reference binary wrote for the same inputs (tests/golden), same `within bin` / `out of bounds` lines."""
@@ -263,7 +263,11 @@ def test_cli_drop_in_end_to_end(name, oracle, tmp_path):
     else:
         oracle.write_xyz(str(wd / "traj.xyz"), fx.elements, fx.coords.astype(np.float64), fmt="%.9g")
         tname, box_line = "traj.xyz", f" cubic_box_edge {float(fx.box_lo[0])!r} {float(fx.box_hi[0])!r}\n"
-    (wd / "molecular.inp").write_text(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + "quit\n")
+    charges = ""
+    if fx.atom_charges is not None:
+        charges = f"atomic_charges {sum(len(q) for q in fx.atom_charges)}\n" + "".join(
+            f" {ti + 1} {ai + 1} {float(v)!r}\n" for ti, q in enumerate(fx.atom_charges) for ai, v in enumerate(q))
+    (wd / "molecular.inp").write_text(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + charges + "quit\n")
     switch = " wrap_trajectory T\n" if fx.wrap else (" unwrap_trajectory T\n" if fx.unwrap else "")
     gen = f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n{box_line}{switch} sequential_read F\n set_threads 8\n'
     for jn, text in zip(fx.job_names, fx.job_texts):
