@@ -261,6 +261,21 @@ typedef struct pa_dist_result {   /* list_of_distances(n)%... after post-process
 } pa_dist_result;
 int pa_distance_subjobs(const pa_traj *traj, const pa_dist_job *job, const pa_exec *exec, pa_dist_result *results);
 
+/* ---- contact distances --------------------------------------
+ * Replaces contact_distance / print_distances (Debug:586-623) for one molecule
+ * type at one time step: give_intramolecular_distances (Molecular:1271-1292) and
+ * give_intermolecular_contact_distance (Molecular:1295-1367), both built on
+ * give_smallest_atom_distance_squared (Molecular:1380-1427).  The intermolecular
+ * search is the reference's O(N_atoms(type) * N_atoms(all)) brute force; the
+ * results are the REAL(4) values the reference prints with F0.3.
+ * timestep and type are 1-based; the caller applies check_timestep (Debug:46-56). */
+typedef struct pa_contact_result {
+    float largest_intramolecular, smallest_intramolecular, smallest_intermolecular;
+    int32_t pad_;
+    int64_t pairs_evaluated;      /* atom pairs of the intermolecular search */
+} pa_contact_result;
+int pa_contact_distance(const pa_traj *traj, int32_t timestep, int32_t type, const pa_exec *exec, pa_contact_result *result);
+
 /* ---- file-level drop-in ----------------------------------
  * Runs a general.inp the way `./prealpha general.inp` does for the keywords
  * of this path (Main:103-357 header, Main:2882-3666 body; unknown keywords

@@ -35,6 +35,7 @@ _SIG = {
                                          C.c_char_p, C.POINTER(C.c_float), C.c_float]),
     "orc_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
     "orc_distance_subjobs": (C.c_int, [C.POINTER(capi.pa_traj), C.POINTER(capi.pa_dist_job), C.POINTER(capi.pa_dist_result)]),
+    "orc_contact_distance": (C.c_int, [C.POINTER(capi.pa_traj), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "orc_wrap_full": (C.c_int, [C.POINTER(capi.pa_traj)]),
     "orc_unwrap_full": (C.c_int, [C.POINTER(capi.pa_traj)]),
     "orc_read_xyz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_char_p]),
@@ -111,6 +112,14 @@ def distance_subjobs(traj, job):
     rc = load().orc_distance_subjobs(traj.ptr, C.byref(job), res)
     assert rc == 0
     return [r.as_dict() for r in res]
+
+
+def contact_distance(traj, timestep, type_, nthreads=0):
+    """(largest intramolecular, smallest intramolecular, smallest intermolecular) as float32 (Debug:586-623)."""
+    out = (C.c_float * 3)()
+    rc = load().orc_contact_distance(traj.ptr, timestep, type_, nthreads or (os.cpu_count() or 1), out)
+    assert rc == 0, rc
+    return tuple(np.float32(v) for v in out)
 
 
 def format_real4(x) -> str:
@@ -218,7 +227,9 @@ def write_case(workdir, traj_name, types, nsteps, box, dist_inputs, threads=8, e
         f.write("quit\n")
     with open(os.path.join(workdir, "general.inp"), "w") as f:
         f.write(f' "{traj_name}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n')
-        f.write(f" cubic_box_edge {box[0]} {box[1]}\n sequential_read F\n parallel_operation T\n set_threads {threads}\n")
+        if box is not None:
+            f.write(f" cubic_box_edge {box[0]} {box[1]}\n")
+        f.write(f" sequential_read F\n parallel_operation T\n set_threads {threads}\n")
         for line in extra_general:
             f.write(f" {line}\n")
         for name in dist_inputs:

@@ -656,6 +656,48 @@ static float orc_atom_d2(const pa_traj *t, int step, int ty1, int mol1, int at1,
     return (float)orc_smallest_atom_distance_squared(t, r1, r2);      /* REAL(4) distance_squared */
 }
 
+/* contact_distance -> print_distances, Debug:586-623: give_intramolecular_distances (Molecular:1271-1292)
+ * and give_intermolecular_contact_distance (Molecular:1295-1367; note the EXIT at :1355 -- within the type
+ * under study only molecules with a lower index than the current one are visited).  OpenMP over the outer
+ * molecule loop here as in the reference (min is order independent).
+ * out = { largest intramolecular, smallest intramolecular, smallest intermolecular }. */
+int orc_contact_distance(const pa_traj *t, int timestep, int type, int nthreads, float out[3])
+{
+    if (timestep < 1 || timestep > t->nsteps || type < 1 || type > t->ntypes) return PA_ERR_BAD_ARG;
+    const int step = timestep - 1, ty1 = type - 1;
+    const pa_type *a = &t->types[ty1];
+    float smallest = (float)t->max_dist_sq, largest = 0.0f;
+    for (int m = 0; m < a->nmol; ++m)
+        for (int a1 = 0; a1 + 1 < a->natoms; ++a1)
+            for (int a2 = a1 + 1; a2 < a->natoms; ++a2) {
+                const float cur = orc_atom_d2(t, step, ty1, m, a1, ty1, m, a2);
+                if (cur > largest) largest = cur;
+                if (cur < smallest) smallest = cur;
+            }
+    out[0] = sqrtf(largest); out[1] = sqrtf(smallest);
+    float inter = (float)t->max_dist_sq;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel num_threads(nthreads)
+    {
+        float local = (float)t->max_dist_sq;
+#pragma omp for schedule(dynamic, 1)
+        for (int m1 = 0; m1 < a->nmol; ++m1)
+            for (int a1 = 0; a1 < a->natoms; ++a1)
+                for (int ty2 = 0; ty2 < t->ntypes; ++ty2)
+                    for (int m2 = 0; m2 < t->types[ty2].nmol; ++m2) {
+                        if (ty2 == ty1 && m2 == m1) break;
+                        for (int a2 = 0; a2 < t->types[ty2].natoms; ++a2) {
+                            const float cur = orc_atom_d2(t, step, ty1, m1, a1, ty2, m2, a2);
+                            if (cur < local) local = cur;
+                        }
+                    }
+#pragma omp critical
+        if (local < inter) inter = local;
+    }
+    out[2] = sqrtf(inter);
+    return 0;
+}
+
 static void orc_distance_pass(const pa_traj *t, const pa_dist_job *job, int stdev_run, pa_dist_result *res)
 {
     const float maxdist_squared = job->maxdist * job->maxdist;

@@ -96,6 +96,16 @@ def distance_subjobs(traj, job, exec_=None):
     return [r.as_dict() for r in res]
 
 
+def contact_distance(traj, timestep, type_, exec_=None):
+    """contact_distance (Debug:586-623) for one molecule type at one time step (both 1-based):
+    (largest intramolecular, smallest intramolecular, smallest intermolecular) as float32, plus the pair count."""
+    res = capi.pa_contact_result()
+    ex = exec_ if exec_ is not None else make_exec()
+    capi.check(capi.load().pa_contact_distance(traj.ptr, timestep, type_, C.byref(ex), C.byref(res)), "pa_contact_distance")
+    return (np.float32(res.largest_intramolecular), np.float32(res.smallest_intramolecular),
+            np.float32(res.smallest_intermolecular)), int(res.pairs_evaluated)
+
+
 def format_real4(x) -> str:
     buf = C.create_string_buffer(64)
     capi.load().pa_format_real4(float(np.float32(x)), buf)

@@ -111,6 +111,13 @@ class pa_dist_result(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class pa_contact_result(C.Structure):
+    _fields_ = [
+        ("largest_intramolecular", C.c_float), ("smallest_intramolecular", C.c_float), ("smallest_intermolecular", C.c_float),
+        ("pad_", C.c_int32), ("pairs_evaluated", C.c_int64),
+    ]
+
+
 # symbol -> (restype, argtypes); every entry of include/prealpha_b200.h
 _I64P = C.POINTER(C.c_int64)
 SIGNATURES = {
@@ -137,6 +144,7 @@ SIGNATURES = {
                                         C.c_char_p, C.POINTER(C.c_float), C.c_float]),
     "pa_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
     "pa_distance_subjobs": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_dist_job), C.POINTER(pa_exec), C.POINTER(pa_dist_result)]),
+    "pa_contact_distance": (C.c_int, [C.POINTER(pa_traj), C.c_int32, C.c_int32, C.POINTER(pa_exec), C.POINTER(pa_contact_result)]),
     "pa_run_general_input": (C.c_int, [C.c_char_p, C.POINTER(pa_exec)]),
 }
 

@@ -298,3 +298,212 @@ done:
     for (int k = 0; k < job->nsubjobs; ++k) { cudaFree(d_ref[k]); cudaFree(d_obs[k]); cudaFree(d_first[k]); cudaFree(d_out[k]); }
     return rc;
 }
+
+// ---------------------------------------------------------------------------
+// contact distances: contact_distance / print_distances, Debug:586-623.
+//
+// One frame.  All atoms are wrapped once (wrap_vector, as give_smallest_atom_distance_squared does
+// for both atoms of every call) into one SoA table in type / molecule / atom order.  The
+// intermolecular search keeps the reference's evaluation order -- the atom of the molecule type
+// under study is always pos_1, and within the same type only molecules with a LOWER index are
+// visited (the EXIT at Molecular:1355 leaves the molecule loop) -- because (p2+s)-p1 and (p1+s)-p2
+// can round differently.  Minima / maxima are taken on the fp64 squared distance; the REAL(4)
+// rounding and the clip to maximum_distance_squared are monotone and applied once at the end.
+namespace {
+
+#define PC_THREADS 128
+#define PC_CHUNK 128
+
+struct PcArgs {
+    const double *x, *y, *z;            // wrapped positions of all atoms of the frame
+    int n_all;
+    int t_begin, t_end;                 // atom index range of the molecule type under study
+    int natoms;                         // atoms per molecule of that type
+    int jsplit;                         // observed atoms per blockIdx.y
+    double L[3];
+    unsigned long long *out;            // [0] min inter, [1] min intra, [2] max intra (bit patterns of doubles >= 0)
+};
+
+__global__ void pa_contact_wrap_kernel(const float *xyz, int n, int first, double3 lo, double3 hi, double3 L,
+                                       double *x, double *y, double *z)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double l[3] = { lo.x, lo.y, lo.z }, h[3] = { hi.x, hi.y, hi.z }, len[3] = { L.x, L.y, L.z };
+    double p[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        double v = (double)xyz[(size_t)i * 3 + k];
+        for (int it = 0; it < 1000; ++it) {                       // wrap_vector, Molecular:1560-1586
+            if (v < l[k]) v = __dadd_rn(v, len[k]);
+            else if (v > h[k]) v = __dsub_rn(v, len[k]);
+            else break;
+        }
+        p[k] = v;
+    }
+    x[first + i] = p[0]; y[first + i] = p[1]; z[first + i] = p[2];
+}
+
+__device__ __forceinline__ double pc_component(double xm, double x0, double xp, double xi)
+{
+    const double dm = __dsub_rn(xm, xi), d0 = __dsub_rn(x0, xi), dp = __dsub_rn(xp, xi);
+    double m = fabs(d0) < fabs(dm) ? d0 : dm;
+    m = fabs(dp) < fabs(m) ? dp : m;
+    return __dmul_rn(m, m);
+}
+
+__global__ void __launch_bounds__(PC_THREADS) pa_contact_inter_kernel(PcArgs a)
+{
+    __shared__ double sj[9][PC_CHUNK];
+    __shared__ unsigned long long smin;
+    const int i = a.t_begin + blockIdx.x * PC_THREADS + threadIdx.x;
+    const bool live = i < a.t_end;
+    const double xi = live ? a.x[i] : 0.0, yi = live ? a.y[i] : 0.0, zi = live ? a.z[i] : 0.0;
+    // observed atoms allowed for this reference atom: everything outside [excl_lo, t_end)
+    const int excl_lo = live ? a.t_begin + ((i - a.t_begin) / a.natoms) * a.natoms : 0;
+    const int j_begin = blockIdx.y * a.jsplit, j_end = min(a.n_all, j_begin + a.jsplit);
+    double best = __longlong_as_double(0x7ff0000000000000ll);
+    if (threadIdx.x == 0) smin = 0x7ff0000000000000ull;
+    __syncthreads();
+    for (int j0 = j_begin; j0 < j_end; j0 += PC_CHUNK) {
+        __syncthreads();
+        {
+            const int j = j0 + threadIdx.x;
+            double px = 1e300, py = 1e300, pz = 1e300;                 // padding: never the minimum
+            if (j < j_end) { px = a.x[j]; py = a.y[j]; pz = a.z[j]; }
+            sj[0][threadIdx.x] = __dadd_rn(px, -a.L[0]); sj[1][threadIdx.x] = px; sj[2][threadIdx.x] = __dadd_rn(px, a.L[0]);
+            sj[3][threadIdx.x] = __dadd_rn(py, -a.L[1]); sj[4][threadIdx.x] = py; sj[5][threadIdx.x] = __dadd_rn(py, a.L[1]);
+            sj[6][threadIdx.x] = __dadd_rn(pz, -a.L[2]); sj[7][threadIdx.x] = pz; sj[8][threadIdx.x] = __dadd_rn(pz, a.L[2]);
+        }
+        __syncthreads();
+        const int nj = min(PC_CHUNK, j_end - j0);
+        // chunk entirely allowed for every thread of this CTA?  (block-uniform test on the CTA's exclusion hull)
+        const int cta_lo = a.t_begin + ((blockIdx.x * PC_THREADS) / a.natoms) * a.natoms;
+        const bool clean = (j0 + nj <= cta_lo) || (j0 >= a.t_end);
+        if (clean) {
+#pragma unroll 4
+            for (int jj = 0; jj < nj; ++jj) {
+                const double s = __dadd_rn(__dadd_rn(pc_component(sj[0][jj], sj[1][jj], sj[2][jj], xi),
+                                                     pc_component(sj[3][jj], sj[4][jj], sj[5][jj], yi)),
+                                           pc_component(sj[6][jj], sj[7][jj], sj[8][jj], zi));
+                best = s < best ? s : best;
+            }
+        } else {
+            for (int jj = 0; jj < nj; ++jj) {
+                const int j = j0 + jj;
+                if (j >= excl_lo && j < a.t_end) continue;              // same molecule, or same type with a higher index
+                const double s = __dadd_rn(__dadd_rn(pc_component(sj[0][jj], sj[1][jj], sj[2][jj], xi),
+                                                     pc_component(sj[3][jj], sj[4][jj], sj[5][jj], yi)),
+                                           pc_component(sj[6][jj], sj[7][jj], sj[8][jj], zi));
+                best = s < best ? s : best;
+            }
+        }
+    }
+    if (live && best == best) atomicMin(&smin, (unsigned long long)__double_as_longlong(best));
+    __syncthreads();
+    if (threadIdx.x == 0) atomicMin(&a.out[0], smin);
+}
+
+__global__ void pa_contact_intra_kernel(PcArgs a)
+{
+    const int mol = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nmol = (a.t_end - a.t_begin) / a.natoms;
+    if (mol >= nmol) return;
+    const int base = a.t_begin + mol * a.natoms;
+    double lo = __longlong_as_double(0x7ff0000000000000ll), hi = 0.0;
+    bool any = false;
+    for (int a1 = 0; a1 + 1 < a.natoms; ++a1) {                         // Molecular:1281-1289
+        const double xi = a.x[base + a1], yi = a.y[base + a1], zi = a.z[base + a1];
+        for (int a2 = a1 + 1; a2 < a.natoms; ++a2) {
+            const double xj = a.x[base + a2], yj = a.y[base + a2], zj = a.z[base + a2];
+            const double s = __dadd_rn(__dadd_rn(pc_component(__dadd_rn(xj, -a.L[0]), xj, __dadd_rn(xj, a.L[0]), xi),
+                                                 pc_component(__dadd_rn(yj, -a.L[1]), yj, __dadd_rn(yj, a.L[1]), yi)),
+                                       pc_component(__dadd_rn(zj, -a.L[2]), zj, __dadd_rn(zj, a.L[2]), zi));
+            lo = s < lo ? s : lo; hi = s > hi ? s : hi; any = true;
+        }
+    }
+    if (any) {
+        atomicMin(&a.out[1], (unsigned long long)__double_as_longlong(lo));
+        atomicMax(&a.out[2], (unsigned long long)__double_as_longlong(hi));
+    }
+}
+
+}  // namespace
+
+extern "C" int pa_contact_distance(const pa_traj *traj, int32_t timestep, int32_t type, const pa_exec *exec, pa_contact_result *result)
+{
+    if (!traj || !result || timestep < 1 || timestep > traj->nsteps) { pa::set_error("bad argument (time step out of range: error 57)"); return PA_ERR_BAD_ARG; }
+    if (type < 1 || type > traj->ntypes) { pa::set_error("molecule type index out of range (error 33)"); return PA_E_TYPE_INVALID; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); pa::set_error("no CUDA device (this path has no CPU fallback)"); return PA_ERR_NO_DEVICE; }
+    const int device = exec ? exec->device : 0;
+    if (cudaSetDevice(device) != cudaSuccess || pa_kernels_selfcheck() != 0) { cudaGetLastError(); pa::set_error("no sm_100a kernel image for this device"); return PA_ERR_NO_DEVICE; }
+    int rc = 0;
+    const int nt = traj->ntypes;
+    std::vector<int> first(nt + 1, 0);
+    for (int t = 0; t < nt; ++t) {
+        const long long n = (long long)traj->types[t].nmol * traj->types[t].natoms;
+        if (first[t] + n > 0x7fffffffll) { pa::set_error("too many atoms"); return PA_ERR_BAD_ARG; }
+        first[t + 1] = first[t] + (int)n;
+    }
+    const int n_all = first[nt];
+    double *d_pos = nullptr;
+    float *d_raw = nullptr;
+    unsigned long long *d_out = nullptr;
+    unsigned long long h_out[3] = { 0x7ff0000000000000ull, 0x7ff0000000000000ull, 0ull };
+    memset(result, 0, sizeof *result);
+    {
+        size_t max_raw = 1;
+        for (int t = 0; t < nt; ++t) max_raw = std::max(max_raw, (size_t)(first[t + 1] - first[t]) * 3);
+        PD_CK(cudaMalloc(&d_pos, sizeof(double) * 3 * (size_t)std::max(n_all, 1)));
+        PD_CK(cudaMalloc(&d_raw, sizeof(float) * max_raw));
+        PD_CK(cudaMalloc(&d_out, sizeof h_out));
+        PD_CK(cudaMemcpy(d_out, h_out, sizeof h_out, cudaMemcpyHostToDevice));
+        double *x = d_pos, *y = d_pos + n_all, *z = d_pos + 2 * (size_t)n_all;
+        const double3 lo = make_double3(traj->box_lo[0], traj->box_lo[1], traj->box_lo[2]);
+        const double3 hi = make_double3(traj->box_hi[0], traj->box_hi[1], traj->box_hi[2]);
+        const double3 L = make_double3(traj->box_hi[0] - traj->box_lo[0], traj->box_hi[1] - traj->box_lo[1], traj->box_hi[2] - traj->box_lo[2]);
+        for (int t = 0; t < nt; ++t) {
+            const int n = first[t + 1] - first[t];
+            if (n < 1) continue;
+            if (!traj->types[t].xyz) { pa::set_error("coordinates missing"); rc = PA_ERR_BAD_ARG; goto done; }
+            PD_CK(cudaMemcpy(d_raw, traj->types[t].xyz + (size_t)(timestep - 1) * n * 3, sizeof(float) * (size_t)n * 3, cudaMemcpyHostToDevice));
+            pa_contact_wrap_kernel<<<(n + 255) / 256, 256>>>(d_raw, n, first[t], lo, hi, L, x, y, z);
+            PD_CK(cudaGetLastError());
+        }
+        PcArgs a{};
+        a.x = x; a.y = y; a.z = z; a.n_all = n_all;
+        a.t_begin = first[type - 1]; a.t_end = first[type]; a.natoms = traj->types[type - 1].natoms;
+        a.L[0] = L.x; a.L[1] = L.y; a.L[2] = L.z; a.out = d_out;
+        const int n_ref = a.t_end - a.t_begin;
+        if (n_ref > 0) {
+            const int bx = (n_ref + PC_THREADS - 1) / PC_THREADS;
+            int splits = std::max(1, (148 * 8 + bx - 1) / bx);
+            const int max_splits = std::max(1, (n_all + PC_CHUNK - 1) / PC_CHUNK);
+            splits = std::min(std::min(splits, max_splits), 65535);
+            a.jsplit = (((n_all + splits - 1) / splits + PC_CHUNK - 1) / PC_CHUNK) * PC_CHUNK;
+            splits = (n_all + a.jsplit - 1) / a.jsplit;
+            pa_contact_inter_kernel<<<dim3(bx, splits), PC_THREADS>>>(a);
+            PD_CK(cudaGetLastError());
+            const int nmol = traj->types[type - 1].nmol;
+            pa_contact_intra_kernel<<<(nmol + 127) / 128, 128>>>(a);
+            PD_CK(cudaGetLastError());
+        }
+        PD_CK(cudaMemcpy(h_out, d_out, sizeof h_out, cudaMemcpyDeviceToHost));
+        auto finish = [&](unsigned long long bits, bool is_min) {
+            double m; memcpy(&m, &bits, 8);
+            float v = is_min ? (float)traj->max_dist_sq : 0.0f;            // smallest=maximum_distance_squared / largest=0.0
+            const float c = (float)(m < traj->max_dist_sq ? m : traj->max_dist_sq);   // REAL(4) function result, Molecular:1400,1418
+            if (is_min ? (c < v) : (c > v)) v = c;
+            return sqrtf(v);
+        };
+        result->smallest_intermolecular = finish(h_out[0], true);
+        result->smallest_intramolecular = finish(h_out[1], true);
+        result->largest_intramolecular = (h_out[1] == 0x7ff0000000000000ull && h_out[2] == 0) ? 0.0f : finish(h_out[2], false);
+        const long long nm = traj->types[type - 1].nmol, na = a.natoms;
+        result->pairs_evaluated = (long long)n_ref * (n_all - n_ref) + na * na * (nm * (nm - 1) / 2);
+    }
+done:
+    cudaFree(d_pos); cudaFree(d_raw); cudaFree(d_out);
+    return rc;
+}

@@ -889,6 +889,45 @@ void write_simple_sumrules(Run &r)                            // Distribution:43
     if (r.verbose) printf(" File 'prealpha_simple.inp' written.\n");
 }
 
+std::string fortran_f0_3(float v)                             // F0.3: no leading zero for |v| < 1
+{
+    char buf[64];
+    snprintf(buf, sizeof buf, "%.3f", (double)v);
+    std::string t = buf;
+    if (t.rfind("0.", 0) == 0) t.erase(0, 1);
+    else if (t.rfind("-0.", 0) == 0) t.erase(1, 1);
+    return t;
+}
+
+int perform_contact_distance(Run &r, int timestep, int type_in)       // Debug:586-623
+{
+    const int ntypes = (int)r.types.size();
+    if (type_in > ntypes) { r.error(33, "molecule type index does not exist"); return 33; }
+    std::vector<pa_type> types; pa_traj traj;
+    make_traj(r, types, traj);
+    auto print_distances = [&](int type) -> int {
+        pa_contact_result res{};
+        const int rc = pa_contact_distance(&traj, timestep, type, &r.exec, &res);
+        if (rc) { r.error(rc, std::string("GPU contact distance failed: ") + pa_last_error()); return rc; }
+        const char *ind = type_in < 1 ? "  " : "";
+        printf("%s   Largest intramolecular distance:  %s\n", ind, fortran_f0_3(res.largest_intramolecular).c_str());
+        printf("%s   Smallest intramolecular distance: %s\n", ind, fortran_f0_3(res.smallest_intramolecular).c_str());
+        printf("%s   Smallest intermolecular distance: %s\n", ind, fortran_f0_3(res.smallest_intermolecular).c_str());
+        return 0;
+    };
+    if (type_in < 1) {
+        printf(" Calculating intra- and intermolecular contact distances at timestep %d for all molecule types.\n", timestep);
+        for (int t = 1; t <= ntypes; ++t) {
+            printf("   Molecule type index %d out of %d.\n", t, ntypes);
+            const int rc = print_distances(t);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    printf(" Calculating intra- and intermolecular contact distances for molecule type %d at timestep %d.\n", type_in, timestep);
+    return print_distances(type_in);
+}
+
 void write_simple_charge_arm(Run &r, bool normalise)          // Distribution:69-96
 {
     const std::string path = r.path_in + "prealpha_simple.inp";
@@ -907,7 +946,7 @@ const char *kOtherModuleKeywords[] = {
     "show_settings", "print_atomic_masses", "print_atomic_charges", "print_dipole_statistics", "show_drude",
     "switch_to_com", "barycentric", "barycenter", "barycentre", "dump_snapshot", "dump_snapshot_simple", "dump_split",
     "dump_split_simple", "dump_single", "dump_cut", "dump_dimers", "dump_neighbour_traj", "dump_example",
-    "dump_example_simple", "dump_full_gro", "dump_full_gro_simple", "contact_distance", "contact_distance_simple",
+    "dump_example_simple", "dump_full_gro", "dump_full_gro_simple", 
     "remove_drudes", "remove_drudes_simple", "remove_cores", "remove_cores_simple", "drude_temp", "drude_temp_simple",
     "temperature", "temperature_simple", "gyradius", "gyradius_simple", "jump_velocity", "jump_velocity_simple",
     "convert", "convert_simple", "convert_coc", "convert_coc_simple", "unwrap_full", "unwrap_full_simple",
@@ -1007,6 +1046,13 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
                        : " Charge Arm distribution. Requires charges to be initialised.\n");
             write_simple_charge_arm(r, clm);
             perform_distribution(r, "prealpha_simple.inp");
+        } else if (k == "contact_distance" || k == "contact_distance_simple") {   // Main:3066-3086
+            if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
+            int step = 1, type = -1;
+            if (k == "contact_distance" && !(t.size() > 2 && parse_int(t[1], step) && parse_int(t[2], type))) { r.error(19, "cannot read general input line"); break; }
+            if (step < 1) { r.error(57, "timestep out of range"); step = 1; }                 // check_timestep, Debug:46-56
+            else if (step > r.nsteps) { r.error(57, "timestep out of range"); step = r.nsteps; }
+            perform_contact_distance(r, step, type);
         } else if (k == "distance" || k == "distances") {                    // Main:3379-3390
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             printf(" distance module invoked.\n");

@@ -312,9 +312,7 @@ def case_dist():
     print(stdout[stdout.find("Line 8"):][:6000])
 
 
-def case_lmp():
-    """LAMMPS-format trajectory: orthorhombic box with full-double bounds read from the file (Molecular:4851-4857),
-    molecules straddling the box, many decimals -> the (i,j)/(j,i) arithmetic is NOT exact here."""
+def _lmp_system():
     rng = np.random.default_rng(4242)
     nsteps = 11
     lo = np.array([-3.127893456123, 0.25, 1.0 / 3.0]); hi = lo + np.array([22.71828182845, 25.3141592653, 21.0123456789])
@@ -330,6 +328,13 @@ def case_lmp():
             fr.append((centre + (rng.random((nm, na, 3)) - 0.5) * 2.4).reshape(-1, 3))
         frames.append(np.concatenate(fr))
     frames = np.stack(frames)
+    return types, elements, frames, lo, hi, nsteps
+
+
+def case_lmp():
+    """LAMMPS-format trajectory: orthorhombic box with full-double bounds read from the file (Molecular:4851-4857),
+    molecules straddling the box, many decimals -> the (i,j)/(j,i) arithmetic is NOT exact here."""
+    types, elements, frames, lo, hi, nsteps = _lmp_system()
     tmp = tempfile.mkdtemp()
     p = os.path.join(tmp, "traj.lmp")
     orc.write_lmp(p, elements, frames, lo, hi)
@@ -349,6 +354,25 @@ def case_lmp():
     save("lmp_unwrap", res, types, lo, hi, jobs[:2], res["coords"], res["elements"],
          extra=dict(nsteps=np.int64(nsteps), lmp=np.int64(1), unwrap=np.int64(1)))
     shutil.rmtree(tmp)
+
+
+def case_contact():
+    """contact_distance (Debug:586-623) on the lmp fixture's trajectory: only the binary's stdout is stored, the
+    coordinates are those of lmp.npz.  Covers all-types / single-type calls, the time-step clamp (error 57),
+    one-atom types (no intramolecular pair) and atoms outside the box."""
+    types, elements, frames, lo, hi, nsteps = _lmp_system()
+    wd = tempfile.mkdtemp(prefix="golden_contact_")
+    orc.write_lmp(os.path.join(wd, "traj.lmp"), elements, frames, lo, hi)
+    keywords = ["contact_distance 1 -1", "contact_distance 7 4", "contact_distance_simple", "contact_distance 99 1",
+                "contact_distance 0 2"]
+    orc.write_case(wd, "traj.lmp", types, nsteps, None, {}, threads=8, extra_general=["trajectory_type lmp"] + keywords)
+    stdout, wall = orc.run_reference(wd, timeout=7200)
+    shutil.rmtree(wd)
+    d = dict(stdout=np.frombuffer(stdout.encode(), dtype=np.uint8), keywords=np.array(keywords))
+    path = os.path.join(OUT, "contact.npz")
+    np.savez_compressed(path, **d)
+    print(f"wrote {path} ({wall:.0f} s of reference time)")
+    print(stdout[stdout.find("contact_distance") - 20:][:5000])
 
 
 def case_charge_arm():
@@ -390,7 +414,7 @@ def case_charge_arm():
                     atom_charge_2=charges[2]))
 
 
-CASES = {"charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+CASES = {"contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"
