@@ -889,6 +889,39 @@ void write_simple_sumrules(Run &r)                            // Distribution:43
     if (r.verbose) printf(" File 'prealpha_simple.inp' written.\n");
 }
 
+// write_simple_intramolecular_distances / write_simple_intermolecular_distances, Distances:178-284.  The
+// intermolecular variant sets both_available from F alone (the reference tests "F" twice, Distances:252-253).
+bool write_simple_distances(Run &r, bool inter)
+{
+    const std::string path = r.path_in + "prealpha_simple.inp";
+    FILE *f = fopen(path.c_str(), "w");
+    if (!f) { r.error(46, "cannot write '" + path + "'"); return false; }
+    bool h_av = false, f_av = false, both = false;
+    if (inter) {
+        h_av = atoms_of_element(r, "H", 0).size() > 1;
+        f_av = atoms_of_element(r, "F", 0).size() > 1;
+        // give_number_of_specific_atoms counts atoms per molecule type summed over types, not instances
+        both = f_av;
+    } else {
+        for (size_t t = 0; t < r.types.size(); ++t) {
+            const size_t nh = atoms_of_element(r, "H", (int)t + 1).size(), nf = atoms_of_element(r, "F", (int)t + 1).size();
+            if (nh > 1) h_av = true;
+            if (nf > 1) f_av = true;
+            if (nh > 1 && nf > 1) both = true;
+        }
+    }
+    const int n = (h_av ? 1 : 0) + (f_av ? 1 : 0) + (both ? 2 : 0);
+    fprintf(f, "%s %d\n", inter ? "inter" : "intra", n);
+    if (n == 0) { fclose(f); return false; }
+    if (h_av) fprintf(f, "H H\n");
+    if (f_av) fprintf(f, "F F\n");
+    if (both) fprintf(f, "H F\nF H\n");
+    fprintf(f, "exponential_weight T\nffc T\nstdev T\nnsteps %d\ncutoff_optimize\nquit\n", r.nsteps > 10 ? 10 : r.nsteps);
+    fclose(f);
+    if (r.verbose) printf(" File 'prealpha_simple.inp' written.\n");
+    return true;
+}
+
 std::string fortran_f0_3(float v)                             // F0.3: no leading zero for |v| < 1
 {
     char buf[64];
@@ -1053,6 +1086,14 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             if (step < 1) { r.error(57, "timestep out of range"); step = 1; }                 // check_timestep, Debug:46-56
             else if (step > r.nsteps) { r.error(57, "timestep out of range"); step = r.nsteps; }
             perform_contact_distance(r, step, type);
+        } else if (k == "distance_simple" || k == "distances_simple") {      // Main:3394-3409
+            printf(" Calculating, where possible, intra- and intermolecular distances for H and F.\n");
+            for (int inter = 0; inter < 2; ++inter) {
+                if (write_simple_distances(r, inter != 0)) {
+                    printf(" %smolecular distance calculation, simple mode:\n", inter ? "Inter" : "Intra");
+                    perform_distance(r, "prealpha_simple.inp");
+                } else printf(" Can't do %smolecular distances. Do manually if necessary.\n", inter ? "inter" : "intra");
+            }
         } else if (k == "distance" || k == "distances") {                    // Main:3379-3390
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             printf(" distance module invoked.\n");

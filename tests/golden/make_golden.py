@@ -331,6 +331,24 @@ def _lmp_system():
     return types, elements, frames, lo, hi, nsteps
 
 
+def case_dist_simple():
+    """`distance_simple` (Main:3394-3409, Distances:178-284) on two steps of the bmim frame: stdout only."""
+    src = os.path.join(REF, "Example_BMIMTFSI", "trajectory.xyz")
+    wd = tempfile.mkdtemp(prefix="golden_dist_simple_")
+    one = open(src).read()
+    with open(os.path.join(wd, "traj.xyz"), "w") as f:
+        f.write(one * 2)
+    orc.write_case(wd, "traj.xyz", [(-1, 15, 512), (+1, 25, 512)], 2, ("0.0", "63.9223"), {}, threads=8,
+                   extra_general=["distance_simple"])
+    stdout, wall = orc.run_reference(wd, timeout=7200)
+    simple = open(os.path.join(wd, "prealpha_simple.inp")).read()
+    shutil.rmtree(wd)
+    path = os.path.join(OUT, "dist_simple.npz")
+    np.savez_compressed(path, stdout=np.frombuffer(stdout.encode(), dtype=np.uint8), simple_inp=np.array(simple))
+    print(f"wrote {path} ({wall:.0f} s of reference time)")
+    print(stdout[stdout.find("distance_simple") - 20:][:6000])
+
+
 def case_lmp():
     """LAMMPS-format trajectory: orthorhombic box with full-double bounds read from the file (Molecular:4851-4857),
     molecules straddling the box, many decimals -> the (i,j)/(j,i) arithmetic is NOT exact here."""
@@ -414,7 +432,7 @@ def case_charge_arm():
                     atom_charge_2=charges[2]))
 
 
-CASES = {"contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+CASES = {"dist_simple": case_dist_simple, "contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"

@@ -188,3 +188,22 @@ def test_contact_distance_cli_matches_reference_stdout(oracle, tmp_path):
     assert p.returncode >= 0, out[-3000:]          # not killed by a signal; warnings make the exit status non-zero
     assert _contact_lines(out) == _contact_lines(stdout), out[-3000:]
     assert "Encountered 2 errors/warnings globally." in out
+
+
+@pytest.mark.gpu
+def test_distance_simple_cli_matches_reference_stdout(oracle, tmp_path):
+    """`distance_simple` (Main:3394-3409): the generated prealpha_simple.inp files (intra, then inter with the
+    reference's F-only `both_available` test) and both report blocks equal the binary's."""
+    z = np.load(os.path.join(fixtures.GOLDEN, "dist_simple.npz"))
+    stdout, simple = z["stdout"].tobytes().decode(), str(z["simple_inp"])
+    fx, _ = _bmim_two_steps()
+    wd = tmp_path / "run"
+    (wd / "out").mkdir(parents=True)
+    oracle.write_xyz(str(wd / "traj.xyz"), fx.elements, fx.coords.astype(np.float64), fmt="%.4f")
+    oracle.write_case(str(wd), "traj.xyz", fx.types, 2, ("0.0", "63.9223"), {}, extra_general=["distance_simple"])
+    cli = os.path.join(os.path.dirname(capi.LIB_PATH), "prealpha_b200_cli")
+    p = subprocess.run([cli, "general.inp"], cwd=wd, capture_output=True, timeout=900)
+    out = p.stdout.decode()
+    blocks = _ref_report_blocks(out)
+    assert len(blocks) == 2 and blocks == _ref_report_blocks(stdout), out[-3000:]
+    assert (wd / "prealpha_simple.inp").read_text() == simple          # the last one written: intermolecular
