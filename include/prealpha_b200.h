@@ -141,6 +141,7 @@ typedef struct pa_exec {
 #define PA_EXEC_FORCE_GENERAL  1   /* use the general (2-D capable) kernel even for RDF jobs */
 #define PA_EXEC_NO_CELLS       2   /* disable the cell-sorted tile path (brute force tiles)   */
 #define PA_EXEC_NO_SYMMETRY    4   /* evaluate every ordered pair even when (i,j)/(j,i) are provably bit-identical */
+#define PA_EXEC_NO_F32         8   /* cell kernel: approximate classes from fp64 differences only (no float32 segments) */
 
 /* Per-call statistics (all optional outputs). */
 typedef struct pa_stats {

@@ -27,6 +27,7 @@ PA_ERR_IO = -5
 PA_EXEC_FORCE_GENERAL = 1
 PA_EXEC_NO_CELLS = 2
 PA_EXEC_NO_SYMMETRY = 4
+PA_EXEC_NO_F32 = 8
 
 
 class pa_type(C.Structure):

@@ -175,9 +175,13 @@ static __device__ __forceinline__ double pc_comp_sq(double ja, double jb, double
     }
 }
 
-struct PcShared {
+struct PcShared {           // general kernel
     PcLayer lay[3][PC_MAXG];
     int work_item;
+};
+struct PcSharedR {          // RDF kernel (its layer table is sized at launch)
+    int work_item;
+    unsigned int t2_bits;    // float bits of the largest squared distance of a tile molecule from the tile origin
 };
 
 // Shared-memory class tables: thresholds thr[k] (8-byte stride, k = 0..na+2) and counters cnt[k]
@@ -203,6 +207,8 @@ static __device__ __forceinline__ void pc_red(unsigned int addr)
 {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
 }
+// (A variant predicated on "counter is read at flush time" was measured: 402 ms instead of 314 ms per 1M-atom frame --
+// partially active ATOMS.POPC.INC are slower than full warps that hit ignored counters.)
 
 struct PcTables {
     unsigned int thr;       // shared address of thr[0]
@@ -211,6 +217,10 @@ struct PcTables {
     float r_max;            // clamp of the approximate distance: keeps the class index <= na+1
     int na;
     unsigned long long cut;
+    // float32 segments (see pc_segment_f32)
+    float f_lo, f_hi;       // (1/step_a)(1 -+ 8e-7)
+    float pad_x;            // local x of padded observed molecules: beyond the cutoff for every tile molecule
+    unsigned int cnt_pad;   // byte offset of the counter window used by padded reference slots
 };
 
 // VARIANT 0: the class of a pair is floor(sqrt(d2)/step_a) evaluated approximately (top 52 bits of d2,
@@ -362,6 +372,207 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
     }
 }
 
+
+// ---------------------------------------------------------------------------
+// float32 segments (VARIANT 0 only, all three components in "single image" mode).
+//
+// The approximate class of a pair is computed entirely in float32 from LOCAL coordinates about the tile
+// origin O (T = largest distance of a tile molecule from O, measured per tile):
+//     xi~ = fl32(xi - O),  xj~ = fl32(fl64(xj + s) - O),  d~ = fl32(xj~ - xi~),
+//     d2~ = fma(dz~,dz~, fma(dy~,dy~, fl32(dx~*dx~))),   r~ = sqrt.approx(d2~),
+// two reference molecules per instruction (sm_100 packed FADD2 / FMUL2 / FFMA2).
+// With u = 2^-24: |d~_k - d_k| <= u(|xi_k-O_k| + |xj~_k| + |d~_k|) <= u(2|d_k| + 2T_k)(1+o(1)), and
+// | |d~| - |d| | <= |d~ - d| <= 2u(r + |T|): a relative error of 2u = 1.2e-7 in r plus the absolute term
+// a = 2u|T|.  On top come the three roundings of d2~ (1.5u = 0.9e-7 in r), sqrt.approx (2^-23 = 1.2e-7), the
+// two roundings inside the scale factor (1.2e-7) and the reference's own float32 chain
+// fl(fl(sqrtf(fl(d2)))/step_a), which deviates from sqrt(d2)/step_a by 2.5u = 1.5e-7.
+//   * far runs (boxes >= 2|T| apart): a <= u r, total 6.6e-7 relative, inside the +-8e-7 brackets;
+//   * NEAR runs: the brackets are evaluated at r~ -+ a (one more FADD2, whose rounding adds u): 6.6e-7.
+// A pair whose brackets disagree, or whose |link_xy|^2 may be below 2^-30, is re-evaluated from the staged
+// fp64 values exactly as pc_segment does, so results stay bit-identical.  Padded slots (tile tail, chunk
+// tail) need no clamp: padded observed molecules sit at local (pad_x,0,0), beyond the cutoff for every
+// tile molecule, and padded reference slots count into a shifted window of the counter array that is
+// never read.
+static __device__ __forceinline__ unsigned long long pc_pack(float lo, float hi)
+{
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+static __device__ __forceinline__ float pc_lo(unsigned long long v) { return __uint_as_float((unsigned int)v); }
+static __device__ __forceinline__ float pc_hi(unsigned long long v) { return __uint_as_float((unsigned int)(v >> 32)); }
+static __device__ __forceinline__ unsigned long long pc_sub2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+static __device__ __forceinline__ unsigned long long pc_add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+static __device__ __forceinline__ unsigned long long pc_mul2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+static __device__ __forceinline__ unsigned long long pc_fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+static __device__ __forceinline__ unsigned long long pc_fma2_rm(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long d;
+    asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
+static __device__ __forceinline__ float4 pc_lds_f32x4(unsigned int addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+
+// exact decision for one pair of a float32 segment (cold: ~1e-3 of the pairs)
+template <bool ZCOL>
+static __device__ __noinline__ unsigned int pc_f32_exact(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                                         unsigned int rec_addr, double x1, double y1, double z1, int k, int j, long long jbase,
+                                                         unsigned int tlo, unsigned int thi, unsigned int cnt_m, unsigned int trash)
+{
+    const int hi_flag = 0x3E100000;                     // hi word of 2^-30
+    const double ex = pc_comp_sq<1>(pc_lds_f64(rec_addr), 0.0, x1);
+    const double ey = pc_comp_sq<1>(pc_lds_f64(rec_addr + 8u), 0.0, y1);
+    const double ez = pc_comp_sq<1>(pc_lds_f64(rec_addr + 16u), 0.0, z1);
+    const double e1 = __dadd_rn(ex, ey);
+    const double e2 = __dadd_rn(e1, ez);
+    if (ZCOL && __double2hiint(e1) < hi_flag) {
+        // |link_xy|^2 < 2^-30: literal evaluation by pa_exception_kernel, not binned here
+        const int io = gi.sorig[(long long)tl.frame * gi.nmol + tl.begin + k];
+        const int jo = go.sorig[jbase + j];
+        if (!(p.same_type && io == jo)) {
+            const unsigned int slot = atomicAdd(p.exc_count, 1u);
+            const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+            if (slot < p.exc_cap)
+                p.exc_list[slot] = make_uint2((unsigned int)(fb + p.ref_off + io), (unsigned int)(fb + p.obs_off + jo));
+            if (p.sym || p.acc2) {
+                const unsigned int slot2 = atomicAdd(p.exc_count2, 1u);
+                if (slot2 < p.exc_cap)
+                    p.exc_list2[slot2] = make_uint2((unsigned int)(fb + p.obs_off + jo), (unsigned int)(fb + p.ref_off + io));
+            }
+        }
+        return trash;
+    }
+    // exact class inside the brackets [n_lo, n_hi] (n_hi = n_lo + 1 except next to r = 0 in NEAR runs)
+    // (thresholds from global memory: the float32 launch keeps no copy of the table in shared memory)
+    unsigned int n = max(tlo, 0x4B000000u);
+    while (n < thi && e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (n - 0x4B000000u + 1u)))) ++n;
+    return n * 4u + cnt_m;
+}
+
+template <bool ZCOL, bool NEAR, bool VERIFY>
+static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                                      const float (&xf)[PC_RI], const float (&yf)[PC_RI], const float (&zf)[PC_RI],
+                                                      const unsigned int (&cb)[PC_RI],
+                                                      const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
+                                                      double ox, double oy, double oz,
+                                                      long long jbase, int jb, int je, double sxa, double sya, double sza,
+                                                      double *s_j, float4 *s_jf, const PcTables &T, float near_a)
+{
+    static_assert(PC_RI == 2, "the packed float32 loop pairs the two reference molecules of a thread");
+    const unsigned long long X01 = pc_pack(xf[0], xf[1]), Y01 = pc_pack(yf[0], yf[1]), Z01 = pc_pack(zf[0], zf[1]);
+    const unsigned long long F2 = pc_pack(p.f32_lo, p.f32_hi), M2 = pc_pack(8388608.0f, 8388608.0f), A2 = pc_pack(-near_a, near_a);
+    const float zthr = 2.0e-9f;                         // 2^-30 plus the float32 error of dx~^2 + dy~^2 near the axis
+    const int na = T.na;
+    const unsigned int cnt_m = T.cnt - 0x4B000000u * 4u;
+    const unsigned int trash = T.cnt + (unsigned)(na + 2) * 4u;
+    const unsigned int a_jf = (unsigned int)__cvta_generic_to_shared(s_jf), a_j = (unsigned int)__cvta_generic_to_shared(s_j);
+    constexpr int NP = 2 * PC_RI;
+    for (int jc = jb; jc < je; jc += PC_JC) {
+        __syncthreads();
+        {
+            const int t = threadIdx.x;
+            const int j = jc + t;
+            double x = 1.0e15, y = 1.0e15, z = 1.0e15;
+            float4 f = make_float4(T.pad_x, 0.0f, 0.0f, 0.0f);
+            if (j < je) {
+                x = __dadd_rn(go.sx[jbase + j], sxa); y = __dadd_rn(go.sy[jbase + j], sya); z = __dadd_rn(go.sz[jbase + j], sza);
+                f.x = __double2float_rn(__dsub_rn(x, ox)); f.y = __double2float_rn(__dsub_rn(y, oy)); f.z = __double2float_rn(__dsub_rn(z, oz));
+            }
+            s_j[t * 3 + 0] = x; s_j[t * 3 + 1] = y; s_j[t * 3 + 2] = z;
+            s_jf[t] = f;
+        }
+        __syncthreads();
+        const int cnt = min(PC_JC, je - jc);
+        const unsigned int a_end = a_jf + (unsigned)cnt * 16u;
+        for (unsigned int aj = a_jf; aj < a_end; aj += 32u) {
+            const float4 w0 = pc_lds_f32x4(aj), w1 = pc_lds_f32x4(aj + 16u);
+            unsigned int ca[NP], tlo[NP], thi[NP];
+            float s1[NP];
+            bool slow = false;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                // both reference molecules of the thread at once (packed float32 pairs, sm_100 FADD2 / FMUL2 / FFMA2)
+                const float4 w = u ? w1 : w0;
+                const unsigned long long dx = pc_sub2(pc_pack(w.x, w.x), X01), dy = pc_sub2(pc_pack(w.y, w.y), Y01), dz = pc_sub2(pc_pack(w.z, w.z), Z01);
+                const unsigned long long s1p = pc_fma2(dy, dy, pc_mul2(dx, dx));
+                const unsigned long long d2p = pc_fma2(dz, dz, s1p);
+#pragma unroll
+                for (int r = 0; r < PC_RI; ++r) {
+                    const int q = u * PC_RI + r;
+                    float rt;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(r ? pc_hi(d2p) : pc_lo(d2p)));
+                    unsigned long long rr = pc_pack(rt, rt);
+                    if (NEAR) rr = pc_add2(rr, A2);                               // (r~ - a, r~ + a)
+                    const unsigned long long tt = pc_fma2_rm(rr, F2, M2);        // (MAGIC + floor(lo bracket), MAGIC + floor(hi bracket))
+                    tlo[q] = __float_as_uint(pc_lo(tt)); thi[q] = __float_as_uint(pc_hi(tt));
+                    s1[q] = r ? pc_hi(s1p) : pc_lo(s1p);
+                    slow |= tlo[q] != thi[q];
+                    if (ZCOL) slow |= s1[q] < zthr;
+                    ca[q] = tlo[q] * 4u + cb[r];
+                }
+            }
+            if (__any_sync(0xffffffffu, slow)) {                                  // warp-uniform: ~15% of the iterations
+                const int jj = (int)((aj - a_jf) >> 4);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const int r = q % PC_RI, u = q / PC_RI;
+                    const int k = r * PC_THREADS + threadIdx.x;
+                    const int j = jc + jj + u;
+                    const bool need = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && k < tl.count && j < je;   // not for padded slots
+                    if (!__any_sync(0xffffffffu, need)) continue;
+                    if (need)
+                        ca[q] = pc_f32_exact<ZCOL>(p, go, gi, tl, a_j + (unsigned)(jj + u) * 24u, p1x[r], p1y[r], p1z[r], k, j, jbase,
+                                                   tlo[q], thi[q], cnt_m, trash);
+                }
+            }
+            if (VERIFY) {
+                const int jj = (int)((aj - a_jf) >> 4);
+#pragma unroll
+                for (int q = 0; q < NP; ++q) {
+                    const int r = q % PC_RI, u = q / PC_RI;
+                    if (r * PC_THREADS + threadIdx.x >= tl.count || jc + jj + u >= je || ca[q] == trash) continue;
+                    const double *rec = s_j + (jj + u) * 3;
+                    const double e1 = __dadd_rn(pc_comp_sq<1>(rec[0], rec[0], p1x[r]), pc_comp_sq<1>(rec[1], rec[1], p1y[r]));
+                    const double e2 = __dadd_rn(e1, pc_comp_sq<1>(rec[2], rec[2], p1z[r]));
+                    int lo_k = 0, hi_k = na + 1;
+                    while (lo_k < hi_k) { const int mid = (lo_k + hi_k + 1) >> 1; if (e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + mid))) lo_k = mid; else hi_k = mid - 1; }
+                    const int got = (int)((ca[q] - T.cnt) / 4u);
+                    const bool ok = (__double2hiint(e1) >= 0x3E100000) && (lo_k < na ? (got == lo_k) : (got >= na));
+                    if (!ok) atomicAdd(p.verify_fail, 1u);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < NP; ++q) pc_red(ca[q]);
+        }
+    }
+}
+
 template <int VARIANT>
 static __device__ void pc_flush(const PaPass &p, const PcTables &T, bool reset)
 {
@@ -388,22 +599,28 @@ static __device__ void pc_flush(const PaPass &p, const PcTables &T, bool reset)
     }
 }
 
-template <int VARIANT, bool VERIFY, bool SYM>
-__global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
+// PART 0: every run in one launch.  PART 1 / PART 2: the float32-eligible runs (far, single image) and all other
+// runs as two launches over the same work items, so that each gets its own register allocation.
+template <int VARIANT, bool VERIFY, bool SYM, int PART>
+__global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
                                                                    const unsigned int *ntiles_ptr, unsigned int tile_cap,
                                                                    unsigned int *work_counter, int nzg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int na = p.job.bin_a;
-    double *s_j = reinterpret_cast<double *>(smem_raw);                                   // PC_JC*6 doubles
-    unsigned long long *s_thr = reinterpret_cast<unsigned long long *>(s_j + PC_JC * 6);  // na+3
-    unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_thr + (na + 3));             // na+3 (+1 pad)
-    PcShared *sh = reinterpret_cast<PcShared *>(s_cnt + ((na + 4) & ~1));
+    const bool f32_on = VARIANT == 0 && PART != 0 && p.f32_cnt > 0;       // PART 0 is launched only when float32 segments are off
+    const int ncnt = (f32_on && PART == 1) ? p.f32_cnt + na + 8 : na + 3;                                // counters (see pc_segment_f32)
+    // PART 1 (float32 runs only): 3 staged doubles per molecule and no threshold table (read from global when needed)
+    double *s_j = reinterpret_cast<double *>(smem_raw);                                   // PC_JC*6 doubles (PART 1: *3)
+    float4 *s_jf = reinterpret_cast<float4 *>(s_j + PC_JC * (PART == 1 ? 3 : 6));         // PC_JC float4
+    unsigned long long *s_thr = reinterpret_cast<unsigned long long *>(s_jf + PC_JC);     // na+3 (PART 1: none)
+    unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_thr + (PART == 1 ? 0 : na + 3));   // ncnt (+1 pad)
+    PcSharedR *sh = reinterpret_cast<PcSharedR *>(s_cnt + ((ncnt + 1) & ~1));
+    PcLayer *lay = reinterpret_cast<PcLayer *>(sh + 1);                                   // gx+gy+gz entries: x layers, y layers, z layers
 
-    for (int k = threadIdx.x; k < na + 3; k += blockDim.x) {
+    for (int k = threadIdx.x; k < (PART == 1 ? 0 : na + 3); k += blockDim.x)
         s_thr[k] = p.job.thr_a[k];       // "never" (all ones) is a NaN as a double: every `d2 >= NaN` is false, as required
-        s_cnt[k] = 0u;
-    }
+    for (int k = threadIdx.x; k < ncnt; k += blockDim.x) s_cnt[k] = 0u;
     __syncthreads();
 
     PcTables T;
@@ -418,6 +635,10 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
         T.s_lo = T.s_hi = p.job.guess_scale * (1.0f - 9.5367431640625e-07f);             // floor(x~) <= true class
     }
     T.r_max = ((float)na + 1.5f) / p.job.guess_scale;
+    T.f_lo = p.f32_lo; T.f_hi = p.f32_hi;
+    const float t2max = 32.0f;                                                            // largest |T| a float32 tile may have
+    T.pad_x = p.job.maxdist * 1.001f + 3.0f * t2max;
+    T.cnt_pad = (unsigned)(na + 8) * 4u;
     const double cut_d2 = __longlong_as_double((long long)T.cut) * (1.0 + 1e-12);
     const float cutf = (float)fmin(cut_d2 * (1.0 + 1e-6), 3.0e38);                        // NaN ("never") -> 3e38
     const unsigned int ntiles = min(*ntiles_ptr, tile_cap);
@@ -428,7 +649,7 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) sh->work_item = (int)atomicAdd(work_counter, 1u);
+        if (threadIdx.x == 0) { sh->work_item = (int)atomicAdd(work_counter, 1u); sh->t2_bits = 0u; }
         __syncthreads();
         const long long item = sh->work_item;
         if (item >= n_items) break;
@@ -444,6 +665,29 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
             const int k = r * PC_THREADS + threadIdx.x;
             if (k < tl.count) { p1x[r] = gi.sx[ibase + tl.begin + k]; p1y[r] = gi.sy[ibase + tl.begin + k]; p1z[r] = gi.sz[ibase + tl.begin + k]; }
             else p1x[r] = p1y[r] = p1z[r] = -1.0e15;   // padding: far away, finite in float range
+        }
+        // float32 segments: local coordinates about the centre of the tile's cells
+        float xf[PC_RI], yf[PC_RI], zf[PC_RI];
+        unsigned int cb[PC_RI];
+        const double ox = p.box.lo[0] + 0.5 * (double)(tl.cx0 + tl.cx1 + 1) / gi.inv_w[0];
+        const double oy = p.box.lo[1] + ((double)tl.cy + 0.5) / gi.inv_w[1];
+        const double oz = p.box.lo[2] + ((double)tl.cz + 0.5) / gi.inv_w[2];
+        if (f32_on) {
+            float t2 = 0.0f;
+#pragma unroll
+            for (int r = 0; r < PC_RI; ++r) {
+                const bool live = r * PC_THREADS + threadIdx.x < tl.count;
+                xf[r] = live ? __double2float_rn(__dsub_rn(p1x[r], ox)) : 0.0f;
+                yf[r] = live ? __double2float_rn(__dsub_rn(p1y[r], oy)) : 0.0f;
+                zf[r] = live ? __double2float_rn(__dsub_rn(p1z[r], oz)) : 0.0f;
+                cb[r] = T.cnt - 0x4B000000u * 4u + (live ? 0u : T.cnt_pad);
+                t2 = fmaxf(t2, __fmaf_ru(zf[r], zf[r], __fmaf_ru(yf[r], yf[r], __fmul_ru(xf[r], xf[r]))));
+            }
+            t2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(t2)));
+            if ((threadIdx.x & 31) == 0) atomicMax(&sh->t2_bits, __float_as_uint(t2));
+        } else {
+#pragma unroll
+            for (int r = 0; r < PC_RI; ++r) { xf[r] = yf[r] = zf[r] = 0.0f; cb[r] = 0u; }
         }
         // classification of every observed layer against the tile's bounding box
         for (int t = threadIdx.x; t < gx + gy + gz; t += blockDim.x) {
@@ -463,7 +707,7 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
             if (go.lay_lo[lj + k] > go.lay_hi[lj + k]) { cl.mode = 0; cl.ca = cl.cb = 1; cl.pad = 0; cl.dmin2 = 3.0e38f; }   // empty layer
             else cl = pc_classify(ilo, ihi, okey_inv(go.lay_lo[lj + k]), okey_inv(go.lay_hi[lj + k]), p.box.L[c]);
             if (cl.mode == 3) atomicOr(p.flags + 1, 1u);                       // boxes too wide: host redoes the call without cells
-            sh->lay[c][k] = cl;
+            lay[(c == 0 ? 0 : (c == 1 ? gx : gx + gy)) + k] = cl;
         }
         __syncthreads();
         const unsigned long long item_pairs = (unsigned long long)PC_TILE * (unsigned long long)go.nmol;
@@ -473,6 +717,12 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
             since_flush = 0;
         }
         since_flush += item_pairs;
+        // float32 eligibility of this tile: |T| <= t2max; runs must then be at least 2|T| away (rounded up)
+        const float tile_t2 = __uint_as_float(sh->t2_bits);
+        const bool tile_f32 = f32_on && tile_t2 <= t2max * t2max;
+        if (PART == 1 && !tile_f32) continue;
+        const float rmin2 = 4.0f * tile_t2 * 1.0001f + 1.0e-3f;
+        const float near_a = 1.25e-7f * sqrtf(tile_t2) + 1.0e-12f;       // 2u|T| (u = 2^-24), rounded up
 
         const long long jbase = (long long)tl.frame * go.nmol;
         const int *cs = go.cell_start + (long long)tl.frame * (go.ncell + 1);
@@ -480,27 +730,35 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
         // they see this tile as "after" when the roles are reversed
         const int tile_row = tl.cz * gy + tl.cy, tile_end = tl.begin + tl.count;
         for (int cz = z0; cz < z1; ++cz) {
-            const PcLayer lz = sh->lay[2][cz];
+            const PcLayer lz = lay[gx + gy + cz];
             if (!(lz.dmin2 < cutf)) continue;
             if (SYM && cz < tl.cz) continue;
             for (int cy = 0; cy < gy; ++cy) {
                 if (SYM && cz * gy + cy < tile_row) continue;
-                const PcLayer ly = sh->lay[1][cy];
+                const PcLayer ly = lay[gx + cy];
                 const float dyz2 = lz.dmin2 + ly.dmin2;
                 if (!(dyz2 < cutf)) continue;
                 const int *row = cs + ((long long)cz * gy + cy) * gx;
                 int cx = 0;
                 while (cx < gx) {
-                    const PcLayer lx = sh->lay[0][cx];
+                    const PcLayer lx = lay[cx];
                     if (!(dyz2 + lx.dmin2 < cutf)) { ++cx; continue; }            // cannot reach the cutoff
+                    // float32 segment: all components single-image, boxes >= 2|T| apart; zcol: the link vector of a
+                    // pair of this run can be (anti)parallel to z
+                    const bool far = tile_f32;                                     // every single-image run of a float32 tile
+                    const bool nearr = !(dyz2 + lx.dmin2 >= rmin2);                // closer than 2|T|: brackets get the absolute term
+                    const bool zcol = !(lx.dmin2 + ly.dmin2 > 1.0e-6f);
                     int ce = cx;                                                   // extend while the x classification is identical
                     while (ce + 1 < gx) {
-                        const PcLayer ln = sh->lay[0][ce + 1];
+                        const PcLayer ln = lay[ce + 1];
                         if (ln.mode != lx.mode || ln.ca != lx.ca || ln.cb != lx.cb || !(dyz2 + ln.dmin2 < cutf)) break;
+                        if (tile_f32 && (!(dyz2 + ln.dmin2 >= rmin2) != nearr || !(ln.dmin2 + ly.dmin2 > 1.0e-6f) != zcol)) break;
                         ++ce;
                     }
                     int jb = row[cx], je = row[ce + 1];
                     cx = ce + 1;
+                    if (PART == 1 && !(far && lx.mode == 1 && ly.mode == 1 && lz.mode == 1)) continue;
+                    if (PART == 2 && far && lx.mode == 1 && ly.mode == 1 && lz.mode == 1) continue;
                     int db = 0, de = 0;                                              // part of the run that overlaps the tile itself
                     if (SYM && cz * gy + cy == tile_row) {
                         if (je <= tl.begin) continue;                               // entirely before the tile
@@ -513,12 +771,20 @@ __global__ void __launch_bounds__(PC_THREADS) pa_rdf_cells_kernel(PaPass p, PaCe
                     const double sya = (double)(ly.ca - 1) * Ly, syb = (double)(ly.cb - 1) * Ly;
                     const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
                     const int code = (lx.mode >= 2 ? 1 : 0) | (ly.mode >= 2 ? 2 : 0) | (lz.mode >= 2 ? 4 : 0);
-                    if (SYM && db < de) {
+                    if (PART != 1 && SYM && db < de) {
                         // staging needs an even start so that pairs of records stay 16-byte aligned: start at db & ~1,
                         // the extra molecule (if any) lies before the tile or inside it and is masked by ipos < jpos
                         pc_segment<2, 2, 2, VARIANT, VERIFY, true>(p, go, gi, tl, p1x, p1y, p1z, jbase, db, de, sxa, sxb, sya, syb, sza, szb, s_j, T);
                     }
                     if (jb >= je) continue;
+                    if (VARIANT == 0 && PART == 1 && far && code == 0) {
+#define PC_F32(Z_, N_) pc_segment_f32<Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_j, s_jf, T, near_a)
+                        if (nearr) { if (zcol) PC_F32(true, true); else PC_F32(false, true); }
+                        else { if (zcol) PC_F32(true, false); else PC_F32(false, false); }
+#undef PC_F32
+                        continue;
+                    }
+                    if (PART == 1) continue;
 #define PC_SEG(MX_, MY_, MZ_)                                                                                              \
     pc_segment<MX_, MY_, MZ_, VARIANT, VERIFY, false>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb,  \
                                                s_j, T)
@@ -637,7 +903,7 @@ __global__ void __launch_bounds__(PC_THREADS) pa_general_cells_kernel(const __gr
 
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) sh->work_item = (int)atomicAdd(work_counter, 1u);
+        if (threadIdx.x == 0) { sh->work_item = (int)atomicAdd(work_counter, 1u); }
         __syncthreads();
         const long long item = sh->work_item;
         if (item >= n_items) break;
@@ -766,25 +1032,37 @@ void pa_cell_grid_dims(int nmol, int g[3])
     if (g[0] > PC_MAXG) g[0] = PC_MAXG;
 }
 
-size_t pa_cells_smem_bytes(int na) { return (size_t)PC_JC * 6 * 8 + (size_t)(na + 3) * 8 + (size_t)(na + 4) * 4 + sizeof(PcShared) + 16; }
+size_t pa_cells_smem_bytes(int na, int f32_cnt, int nlayers)   // f32_cnt > 0: the PART 1 launch
+{
+    const int ncnt = f32_cnt > 0 ? f32_cnt + na + 8 : na + 3;
+    return (size_t)PC_JC * (f32_cnt > 0 ? 3 : 6) * 8 + (size_t)PC_JC * 16 + (f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 2) * 4 +
+           sizeof(PcSharedR) + (size_t)nlayers * sizeof(PcLayer) + 16;
+}
 
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
                         unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = pa_cells_smem_bytes(p.job.bin_a);
+    const size_t smem = pa_cells_smem_bytes(p.job.bin_a, variant == 0 ? p.f32_cnt : 0, go.g[0] + go.g[1] + go.g[2]);
+    const size_t smem0 = pa_cells_smem_bytes(p.job.bin_a, 0, go.g[0] + go.g[1] + go.g[2]);
     const bool verify = p.verify_fail != nullptr;
-    cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
-#define PC_LAUNCH2(O_, V_, S_)                                                                                  \
+#define PC_LAUNCH3(O_, V_, S_, P_, SMEM_)                                                                        \
     do {                                                                                                        \
         int occ = 1;                                                                                            \
-        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_, S_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
-        pa_rdf_cells_kernel<O_, V_, S_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+        cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);                                             \
+        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_, S_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_, S_, P_>, PC_THREADS, (SMEM_)) != cudaSuccess || occ < 1) occ = 1; \
+        pa_rdf_cells_kernel<O_, V_, S_, P_><<<sm_count * occ, PC_THREADS, (SMEM_), st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+    } while (0)
+#define PC_LAUNCH2(O_, V_, S_)                                                                                  \
+    do {                                                                                                        \
+        if (O_ == 0 && p.f32_cnt > 0) { PC_LAUNCH3(O_, V_, S_, 1, smem); PC_LAUNCH3(O_, V_, S_, 2, smem0); }    \
+        else PC_LAUNCH3(O_, V_, S_, 0, smem0);                                                                  \
     } while (0)
 #define PC_LAUNCH(O_, V_) do { if (p.sym) PC_LAUNCH2(O_, V_, true); else PC_LAUNCH2(O_, V_, false); } while (0)
     if (variant == 1) { if (verify) PC_LAUNCH(1, true); else PC_LAUNCH(1, false); }
     else { if (verify) PC_LAUNCH(0, true); else PC_LAUNCH(0, false); }
+#undef PC_LAUNCH3
 #undef PC_LAUNCH2
 #undef PC_LAUNCH
     return (int)cudaGetLastError();

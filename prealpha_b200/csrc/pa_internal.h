@@ -92,6 +92,9 @@ struct PaPass {
     uint2 *exc_list2;           // reversed pairs (j,i) for the second job (or the same job when sym)
     unsigned int *exc_count2;
     unsigned int *verify_fail;  // debug counter for the class-guess invariant (may be null)
+    int32_t f32_cnt;            // > 0: float32 segments enabled in the cell kernel, counters needed for any reachable class
+    int32_t f32_pad_;
+    float f32_lo, f32_hi;       // (1/step_a)(1 -+ 8e-7), adjacent so that they load as one packed pair
 };
 
 // Uniform grid of one molecule type for a batch of frames (pa_cells.cu).  Arrays are

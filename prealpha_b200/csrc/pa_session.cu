@@ -51,6 +51,7 @@ struct JobState {
     pa_job job;
     PaDevJob dj;
     bool fast;
+    int f32_cnt = 0;     // > 0: float32 segments of the cell kernel enabled (counter classes needed), see pa_cells.cu
     int cells_variant;   // 0: approximate class + rare exact fix-up, 1: exact table for every pair (see pa_cells.cu)
     size_t acc_off;      // offset (words) inside the accumulator block
     size_t nbins;
@@ -287,6 +288,15 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
                 const double xcut = std::sqrt(cutd) / (double)jb.step_a;
                 if (std::fabs(xcut - jb.bin_a) <= 3e-7 * jb.bin_a) js.cells_variant = 0;
             }
+            js.f32_cnt = 0;
+            if (js.cells_variant == 0 && !(ex.flags & PA_EXEC_NO_F32)) {
+                // classes a float32 segment can produce: any pair of a single-image run is closer than the box
+                // diagonal; padded observed molecules sit at maxdist*1.001 + 96 (+32 for the tile radius)
+                const double diag = std::sqrt(s->box.L[0] * s->box.L[0] + s->box.L[1] * s->box.L[1] + s->box.L[2] * s->box.L[2]);
+                const double far = std::max(diag, (double)jb.maxdist * 1.001 + 128.0);
+                const double ncl = far * (double)d.guess_scale * 1.00001 + 4.0;
+                if (ncl + jb.bin_a + 8 <= 12288.0) js.f32_cnt = (int)ncl;
+            }
         }
     }
     // cell-sorted path: both partners of a pass need >= 12500 molecules (grid of >= 5^3 cells of ~100)
@@ -470,6 +480,16 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = s->exc_cap / 2; p.flags = s->d_exc_count;
         p.exc_list2 = s->d_exc + s->exc_cap / 2; p.exc_count2 = s->d_exc_count + 4;
         p.verify_fail = s->verify ? s->d_exc_count + 2 : nullptr;
+        p.f32_cnt = js.f32_cnt; p.f32_pad_ = 0;
+        {
+            // brackets of the float32 segments: the largest float <= (1-eps)/step_a and the smallest float >= (1+eps)/step_a,
+            // computed in double so that the scale factor itself carries no rounding towards the inside (eps = 6e-7)
+            const double inv = 1.0 / (double)jb.step_a;
+            float lo = (float)(inv * (1.0 - 6.0e-7)), hi = (float)(inv * (1.0 + 6.0e-7));
+            if ((double)lo > inv * (1.0 - 6.0e-7)) lo = std::nextafterf(lo, 0.0f);
+            if ((double)hi < inv * (1.0 + 6.0e-7)) hi = std::nextafterf(hi, INFINITY);
+            p.f32_lo = lo; p.f32_hi = hi;
+        }
     };
     for (const Plan &pl : plan) {
         const JobState &js = s->jobs[pl.job];
@@ -523,7 +543,7 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
             PA_CK((cudaError_t)pa_launch_rdf_cells(p, gr.g, s->grids[o].g, gr.tiles, gr.counters, gr.tile_cap, gr.counters + 1,
                                                    (int)nzg, js.cells_variant, s->sm_count, s->s_compute));
             PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
-            s->stats.kernel_launches += 3;
+            s->stats.kernel_launches += 3 + ((js.cells_variant == 0 && js.f32_cnt > 0) ? 1 : 0);   // float32 runs and the rest are two launches
             if (pl.sym) {                                           // reversed pairs of the same job
                 PaPass ps = p; ps.exc_list = p.exc_list2; ps.exc_count = p.exc_count2;
                 PA_CK((cudaError_t)pa_launch_exceptions(ps, 0, s->s_compute));
