@@ -218,7 +218,7 @@ struct PcTables {
     int na;
     unsigned long long cut;
     // float32 segments (see pc_segment_f32)
-    float f_lo, f_hi;       // (1/step_a)(1 -+ 8e-7)
+    float f_lo, f_hi;       // (1/step_a)(1 -+ 6e-7), rounded outwards
     float pad_x;            // local x of padded observed molecules: beyond the cutoff for every tile molecule
     unsigned int cnt_pad;   // byte offset of the counter window used by padded reference slots
 };
@@ -383,11 +383,12 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
 // two reference molecules per instruction (sm_100 packed FADD2 / FMUL2 / FFMA2).
 // With u = 2^-24: |d~_k - d_k| <= u(|xi_k-O_k| + |xj~_k| + |d~_k|) <= u(2|d_k| + 2T_k)(1+o(1)), and
 // | |d~| - |d| | <= |d~ - d| <= 2u(r + |T|): a relative error of 2u = 1.2e-7 in r plus the absolute term
-// a = 2u|T|.  On top come the three roundings of d2~ (1.5u = 0.9e-7 in r), sqrt.approx (2^-23 = 1.2e-7), the
-// two roundings inside the scale factor (1.2e-7) and the reference's own float32 chain
-// fl(fl(sqrtf(fl(d2)))/step_a), which deviates from sqrt(d2)/step_a by 2.5u = 1.5e-7.
-//   * far runs (boxes >= 2|T| apart): a <= u r, total 6.6e-7 relative, inside the +-8e-7 brackets;
-//   * NEAR runs: the brackets are evaluated at r~ -+ a (one more FADD2, whose rounding adds u): 6.6e-7.
+// a = 2u|T|.  On top come the three roundings of d2~ (1.5u = 0.9e-7 in r), sqrt.approx (2^-23 = 1.2e-7) and the
+// reference's own float32 chain fl(fl(sqrtf(fl(d2)))/step_a), which deviates from sqrt(d2)/step_a by
+// 2.5u = 1.5e-7.  The bracket factors (1 -+ 6e-7)/step_a are computed by the host in double and rounded
+// outwards (PaPass::f32_lo/f32_hi), and the FFMA.RM is a single rounding, so the scale adds nothing.
+//   * far runs (boxes >= 2|T| apart): a <= u r = 0.6e-7, total 5.4e-7 relative, inside the +-6e-7 brackets;
+//   * NEAR runs: the brackets are evaluated at r~ -+ a (one more FADD2, whose rounding adds u): 5.4e-7.
 // A pair whose brackets disagree, or whose |link_xy|^2 may be below 2^-30, is re-evaluated from the staged
 // fp64 values exactly as pc_segment does, so results stay bit-identical.  Padded slots (tile tail, chunk
 // tail) need no clamp: padded observed molecules sit at local (pad_x,0,0), beyond the cutoff for every

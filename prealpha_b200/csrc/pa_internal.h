@@ -94,7 +94,7 @@ struct PaPass {
     unsigned int *verify_fail;  // debug counter for the class-guess invariant (may be null)
     int32_t f32_cnt;            // > 0: float32 segments enabled in the cell kernel, counters needed for any reachable class
     int32_t f32_pad_;
-    float f32_lo, f32_hi;       // (1/step_a)(1 -+ 8e-7), adjacent so that they load as one packed pair
+    float f32_lo, f32_hi;       // (1 -+ 6e-7)/step_a rounded outwards; adjacent so that they load as one packed pair
 };
 
 // Uniform grid of one molecule type for a batch of frames (pa_cells.cu).  Arrays are
