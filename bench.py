@@ -74,6 +74,11 @@ class ClockSampler:
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            # nvidia-smi's own start-up (driver attach) can stall CUDA calls for a few hundred ms: wait for its first
+            # sample so that this happens before the timed region, not inside it
+            t_end = time.time() + 8.0
+            while not self.rows and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.05)
         except Exception:
             self.proc = None
 
@@ -258,11 +263,14 @@ def main():
         time.sleep(0.3)
     barrier()
     t0 = time.perf_counter()
+    step_marks = []
     for s in range(K):
         flush.zero_()                      # L2 flush between timed iterations (torch stream)
         torch.cuda.synchronize()
+        step_marks.append(time.perf_counter() - t0)
         sess.run(W + s, 1)                 # prepare + pair kernels on the session's compute stream
     ptr, nwords = sess.device_accumulators()   # synchronises the compute stream
+    step_marks.append(time.perf_counter() - t0)
     if world > 1:
         class _Acc:   # zero-copy view of the session's int64 accumulators for NCCL
             __cuda_array_interface__ = {"shape": (nwords,), "typestr": "<i8", "data": (ptr, False), "version": 2}
@@ -270,6 +278,8 @@ def main():
         dist.reduce(acc, dst=0, op=dist.ReduceOp.SUM)      # integer bin counts combined once over NVLink
     barrier()
     t_value = time.perf_counter() - t0
+    if rank == 0:
+        print("[bench] value arm: step boundaries (s) " + " ".join(f"{m:.3f}" for m in step_marks) + f" end {t_value:.3f}", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     hists, within, oob = sess.download()
     st1 = sess.stats()

@@ -440,40 +440,54 @@ static __device__ __forceinline__ float4 pc_lds_f32x4(unsigned int addr)
     return v;
 }
 
-// exact decision for one pair of a float32 segment (cold: ~1e-3 of the pairs)
+// Exact decisions of the float32 segments are deferred: a flagged pair (~1e-3 of the pairs, usually one lane of
+// the warp) is appended to a 32-entry queue of its warp and the queue is drained with one entry per lane, so
+// the fp64 re-evaluation runs at full lane occupancy instead of stalling 31 idle lanes on every hit.
+//   entry: bits 0-8 reference index inside the tile, 9-15 observed index inside the staged chunk,
+//          16-23 n_hi - n_lo, 32-63 float bits of MAGIC + n_lo
+#define PC_QCAP 32
 template <bool ZCOL>
-static __device__ __noinline__ unsigned int pc_f32_exact(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
-                                                         unsigned int rec_addr, double x1, double y1, double z1, int k, int j, long long jbase,
-                                                         unsigned int tlo, unsigned int thi, unsigned int cnt_m, unsigned int trash)
+static __device__ __noinline__ void pc_f32_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                                 const unsigned long long *queue, int count, unsigned int a_j, long long jbase, int jc,
+                                                 unsigned int cnt_m)
 {
-    const int hi_flag = 0x3E100000;                     // hi word of 2^-30
-    const double ex = pc_comp_sq<1>(pc_lds_f64(rec_addr), 0.0, x1);
-    const double ey = pc_comp_sq<1>(pc_lds_f64(rec_addr + 8u), 0.0, y1);
-    const double ez = pc_comp_sq<1>(pc_lds_f64(rec_addr + 16u), 0.0, z1);
-    const double e1 = __dadd_rn(ex, ey);
-    const double e2 = __dadd_rn(e1, ez);
-    if (ZCOL && __double2hiint(e1) < hi_flag) {
-        // |link_xy|^2 < 2^-30: literal evaluation by pa_exception_kernel, not binned here
-        const int io = gi.sorig[(long long)tl.frame * gi.nmol + tl.begin + k];
-        const int jo = go.sorig[jbase + j];
-        if (!(p.same_type && io == jo)) {
-            const unsigned int slot = atomicAdd(p.exc_count, 1u);
-            const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
-            if (slot < p.exc_cap)
-                p.exc_list[slot] = make_uint2((unsigned int)(fb + p.ref_off + io), (unsigned int)(fb + p.obs_off + jo));
-            if (p.sym || p.acc2) {
-                const unsigned int slot2 = atomicAdd(p.exc_count2, 1u);
-                if (slot2 < p.exc_cap)
-                    p.exc_list2[slot2] = make_uint2((unsigned int)(fb + p.obs_off + jo), (unsigned int)(fb + p.ref_off + io));
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    if (lane < count) {
+        const unsigned long long ent = queue[lane];
+        const int k = (int)(ent & 511u), jl = (int)((ent >> 9) & 127u);
+        const unsigned int tlo = (unsigned int)(ent >> 32), thi = tlo + (unsigned int)((ent >> 16) & 255u);
+        const long long iref = (long long)tl.frame * gi.nmol + tl.begin + k;
+        const unsigned int rec = a_j + (unsigned)jl * 24u;
+        const double ex = pc_comp_sq<1>(pc_lds_f64(rec), 0.0, gi.sx[iref]);
+        const double ey = pc_comp_sq<1>(pc_lds_f64(rec + 8u), 0.0, gi.sy[iref]);
+        const double ez = pc_comp_sq<1>(pc_lds_f64(rec + 16u), 0.0, gi.sz[iref]);
+        const double e1 = __dadd_rn(ex, ey);
+        const double e2 = __dadd_rn(e1, ez);
+        if (ZCOL && __double2hiint(e1) < 0x3E100000) {
+            // |link_xy|^2 < 2^-30: literal evaluation by pa_exception_kernel, not binned here
+            const int io = gi.sorig[iref];
+            const int jo = go.sorig[jbase + jc + jl];
+            if (!(p.same_type && io == jo)) {
+                const unsigned int slot = atomicAdd(p.exc_count, 1u);
+                const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+                if (slot < p.exc_cap)
+                    p.exc_list[slot] = make_uint2((unsigned int)(fb + p.ref_off + io), (unsigned int)(fb + p.obs_off + jo));
+                if (p.sym || p.acc2) {
+                    const unsigned int slot2 = atomicAdd(p.exc_count2, 1u);
+                    if (slot2 < p.exc_cap)
+                        p.exc_list2[slot2] = make_uint2((unsigned int)(fb + p.obs_off + jo), (unsigned int)(fb + p.ref_off + io));
+                }
             }
+        } else {
+            // exact class inside the brackets [n_lo, n_hi] (n_hi = n_lo + 1 except next to r = 0 in NEAR runs);
+            // thresholds from global memory: the float32 launch keeps no copy of the table in shared memory
+            unsigned int n = max(tlo, 0x4B000000u);
+            while (n < thi && e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (n - 0x4B000000u + 1u)))) ++n;
+            pc_red(n * 4u + cnt_m);
         }
-        return trash;
     }
-    // exact class inside the brackets [n_lo, n_hi] (n_hi = n_lo + 1 except next to r = 0 in NEAR runs)
-    // (thresholds from global memory: the float32 launch keeps no copy of the table in shared memory)
-    unsigned int n = max(tlo, 0x4B000000u);
-    while (n < thi && e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (n - 0x4B000000u + 1u)))) ++n;
-    return n * 4u + cnt_m;
+    __syncwarp();
 }
 
 template <bool ZCOL, bool NEAR, bool VERIFY>
@@ -483,9 +497,12 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                                                       const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
                                                       double ox, double oy, double oz,
                                                       long long jbase, int jb, int je, double sxa, double sya, double sza,
-                                                      double *s_j, float4 *s_jf, const PcTables &T, float near_a)
+                                                      double *s_j, float4 *s_jf, const PcTables &T, float near_a, unsigned long long *queue)
 {
     static_assert(PC_RI == 2, "the packed float32 loop pairs the two reference molecules of a thread");
+    static_assert(PC_TILE <= 512 && PC_JC <= 128, "queue entry layout");
+    int qn = 0;                                         // entries in this warp's queue (warp-uniform)
+    const unsigned int lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     const unsigned long long X01 = pc_pack(xf[0], xf[1]), Y01 = pc_pack(yf[0], yf[1]), Z01 = pc_pack(zf[0], zf[1]);
     const unsigned long long F2 = pc_pack(p.f32_lo, p.f32_hi), M2 = pc_pack(8388608.0f, 8388608.0f), A2 = pc_pack(-near_a, near_a);
     const float zthr = 2.0e-9f;                         // 2^-30 plus the float32 error of dx~^2 + dy~^2 near the axis
@@ -493,7 +510,8 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
     const unsigned int cnt_m = T.cnt - 0x4B000000u * 4u;
     const unsigned int trash = T.cnt + (unsigned)(na + 2) * 4u;
     const unsigned int a_jf = (unsigned int)__cvta_generic_to_shared(s_jf), a_j = (unsigned int)__cvta_generic_to_shared(s_j);
-    constexpr int NP = 2 * PC_RI;
+    constexpr int NU = 2;                               // staged molecules per iteration (4 measured slower)
+    constexpr int NP = NU * PC_RI;
     for (int jc = jb; jc < je; jc += PC_JC) {
         __syncthreads();
         {
@@ -511,15 +529,17 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
         __syncthreads();
         const int cnt = min(PC_JC, je - jc);
         const unsigned int a_end = a_jf + (unsigned)cnt * 16u;
-        for (unsigned int aj = a_jf; aj < a_end; aj += 32u) {
-            const float4 w0 = pc_lds_f32x4(aj), w1 = pc_lds_f32x4(aj + 16u);
+        for (unsigned int aj = a_jf; aj < a_end; aj += 16u * NU) {
+            float4 wv[NU];
+#pragma unroll
+            for (int u = 0; u < NU; ++u) wv[u] = pc_lds_f32x4(aj + 16u * u);
             unsigned int ca[NP], tlo[NP], thi[NP];
             float s1[NP];
             bool slow = false;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < NU; ++u) {
                 // both reference molecules of the thread at once (packed float32 pairs, sm_100 FADD2 / FMUL2 / FFMA2)
-                const float4 w = u ? w1 : w0;
+                const float4 w = wv[u];
                 const unsigned long long dx = pc_sub2(pc_pack(w.x, w.x), X01), dy = pc_sub2(pc_pack(w.y, w.y), Y01), dz = pc_sub2(pc_pack(w.z, w.z), Z01);
                 const unsigned long long s1p = pc_fma2(dy, dy, pc_mul2(dx, dx));
                 const unsigned long long d2p = pc_fma2(dz, dz, s1p);
@@ -538,18 +558,23 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                     ca[q] = tlo[q] * 4u + cb[r];
                 }
             }
-            if (__any_sync(0xffffffffu, slow)) {                                  // warp-uniform: ~15% of the iterations
+            if (__any_sync(0xffffffffu, slow)) {                                  // warp-uniform: ~10% of the iterations
                 const int jj = (int)((aj - a_jf) >> 4);
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     const int r = q % PC_RI, u = q / PC_RI;
                     const int k = r * PC_THREADS + threadIdx.x;
-                    const int j = jc + jj + u;
-                    const bool need = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && k < tl.count && j < je;   // not for padded slots
-                    if (!__any_sync(0xffffffffu, need)) continue;
-                    if (need)
-                        ca[q] = pc_f32_exact<ZCOL>(p, go, gi, tl, a_j + (unsigned)(jj + u) * 24u, p1x[r], p1y[r], p1z[r], k, j, jbase,
-                                                   tlo[q], thi[q], cnt_m, trash);
+                    const bool need = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && k < tl.count && jc + jj + u < je;   // not for padded slots
+                    const unsigned int m = __ballot_sync(0xffffffffu, need);
+                    if (m == 0u) continue;
+                    const int add = __popc(m);
+                    if (qn + add > PC_QCAP) { pc_f32_drain<ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }
+                    if (need) {
+                        queue[qn + __popc(m & lane_lt)] = ((unsigned long long)tlo[q] << 32) | ((unsigned long long)min(thi[q] - tlo[q], 255u) << 16) |
+                                                          ((unsigned long long)(jj + u) << 9) | (unsigned long long)k;
+                        ca[q] = trash;                                            // counted by the drain
+                    }
+                    qn += add;
                 }
             }
             if (VERIFY) {
@@ -571,6 +596,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
 #pragma unroll
             for (int q = 0; q < NP; ++q) pc_red(ca[q]);
         }
+        if (qn > 0) { pc_f32_drain<ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }   // before the chunk is overwritten
     }
 }
 
@@ -618,6 +644,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_thr + (PART == 1 ? 0 : na + 3));   // ncnt (+1 pad)
     PcSharedR *sh = reinterpret_cast<PcSharedR *>(s_cnt + ((ncnt + 1) & ~1));
     PcLayer *lay = reinterpret_cast<PcLayer *>(sh + 1);                                   // gx+gy+gz entries: x layers, y layers, z layers
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(lay + (go.g[0] + go.g[1] + go.g[2])) + (threadIdx.x >> 5) * PC_QCAP;   // PART 1: per warp
 
     for (int k = threadIdx.x; k < (PART == 1 ? 0 : na + 3); k += blockDim.x)
         s_thr[k] = p.job.thr_a[k];       // "never" (all ones) is a NaN as a double: every `d2 >= NaN` is false, as required
@@ -779,7 +806,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     }
                     if (jb >= je) continue;
                     if (VARIANT == 0 && PART == 1 && far && code == 0) {
-#define PC_F32(Z_, N_) pc_segment_f32<Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_j, s_jf, T, near_a)
+#define PC_F32(Z_, N_) pc_segment_f32<Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_j, s_jf, T, near_a, queue)
                         if (nearr) { if (zcol) PC_F32(true, true); else PC_F32(false, true); }
                         else { if (zcol) PC_F32(true, false); else PC_F32(false, false); }
 #undef PC_F32
@@ -1037,7 +1064,7 @@ size_t pa_cells_smem_bytes(int na, int f32_cnt, int nlayers)   // f32_cnt > 0: t
 {
     const int ncnt = f32_cnt > 0 ? f32_cnt + na + 8 : na + 3;
     return (size_t)PC_JC * (f32_cnt > 0 ? 3 : 6) * 8 + (size_t)PC_JC * 16 + (f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 2) * 4 +
-           sizeof(PcSharedR) + (size_t)nlayers * sizeof(PcLayer) + 16;
+           sizeof(PcSharedR) + (size_t)nlayers * sizeof(PcLayer) + (f32_cnt > 0 ? (size_t)(PC_THREADS / 32) * PC_QCAP * 8 : 0) + 16;
 }
 
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
