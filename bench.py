@@ -320,6 +320,11 @@ def main():
     if rank == 0:
         # identical inputs in both arms -> identical integers
         assert w2_total == binned_total, (w2_total, binned_total)
+        # size-independent property of the synthetic workload: uniform points, cutoff L/2 -> the binned fraction of all
+        # ordered pairs is the sphere / cube volume ratio pi/6 (statistical scatter ~1e-6 at 1e12 pairs per frame)
+        if n_half == N_PER_TYPE:
+            frac_binned = binned_total / pair_evals_total
+            assert abs(frac_binned - np.pi / 6.0) < 1.0e-4, f"binned fraction {frac_binned} is not pi/6: counts are wrong"
         value = binned_total / t_value_max
         pe_per_s = pair_evals_total / t_value_max
         # dominant kernel: pa_rdf_fast_kernel (2 launches per step: observed type 1 and 2 per job -> 4)

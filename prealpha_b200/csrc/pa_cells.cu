@@ -785,8 +785,10 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     }
                     int jb = row[cx], je = row[ce + 1];
                     cx = ce + 1;
-                    if (PART == 1 && !(far && lx.mode == 1 && ly.mode == 1 && lz.mode == 1)) continue;
-                    if (PART == 2 && far && lx.mode == 1 && ly.mode == 1 && lz.mode == 1) continue;
+                    // float32-eligible runs belong to the PART 1 launch -- except the part of a run that overlaps the tile
+                    // itself in a symmetric pass (db..de below), which always takes the fp64 segment of PART 0 / 2
+                    const bool f32run = far && lx.mode == 1 && ly.mode == 1 && lz.mode == 1;
+                    if (PART == 1 && !f32run) continue;
                     int db = 0, de = 0;                                              // part of the run that overlaps the tile itself
                     if (SYM && cz * gy + cy == tile_row) {
                         if (je <= tl.begin) continue;                               // entirely before the tile
@@ -805,6 +807,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                         pc_segment<2, 2, 2, VARIANT, VERIFY, true>(p, go, gi, tl, p1x, p1y, p1z, jbase, db, de, sxa, sxb, sya, syb, sza, szb, s_j, T);
                     }
                     if (jb >= je) continue;
+                    if (PART == 2 && f32run) continue;                              // counted by the PART 1 launch
                     if (VARIANT == 0 && PART == 1 && far && code == 0) {
 #define PC_F32(Z_, N_) pc_segment_f32<Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_j, s_jf, T, near_a, queue)
                         if (nearr) { if (zcol) PC_F32(true, true); else PC_F32(false, true); }

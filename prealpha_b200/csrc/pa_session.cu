@@ -11,6 +11,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <chrono>
+#include <mutex>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -66,6 +68,31 @@ constexpr unsigned int kExcCap = 4u << 20;
 
 void pa::set_error(const std::string &msg) { g_last_error = msg; }
 
+// Page-locking host memory costs tens to hundreds of milliseconds per call; the staging buffers of the last
+// sessions are kept (at most 4 buffers, 1 GiB in total) and handed to the next session that asks for the same size.
+namespace {
+struct PinnedEntry { void *ptr; size_t bytes; };
+std::mutex g_pool_mutex;
+std::vector<PinnedEntry> g_pinned_pool;
+
+void *pinned_pool_take(size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (size_t i = 0; i < g_pinned_pool.size(); ++i)
+        if (g_pinned_pool[i].bytes == bytes) { void *p = g_pinned_pool[i].ptr; g_pinned_pool.erase(g_pinned_pool.begin() + i); return p; }
+    return nullptr;
+}
+
+void pinned_pool_give(void *ptr, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    size_t total = bytes;
+    for (const PinnedEntry &e : g_pinned_pool) total += e.bytes;
+    if (g_pinned_pool.size() >= 4 || total > (size_t(1) << 30)) { cudaFreeHost(ptr); return; }
+    g_pinned_pool.push_back({ ptr, bytes });
+}
+}  // namespace
+
 struct pa_session {
     int device = 0, sm_count = 148;
     pa_exec exec{};
@@ -81,6 +108,7 @@ struct pa_session {
     bool slot_used[2] = { false, false };
     std::vector<float *> d_raw[2];
     float *h_pinned[2] = { nullptr, nullptr };
+    size_t h_pinned_bytes[2] = { 0, 0 };
     size_t pinned_floats = 0;
     PaDevType *d_types[2] = { nullptr, nullptr };
     double *d_pts = nullptr;
@@ -219,7 +247,9 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
         for (int t = 0; t < traj->ntypes; ++t)
             if (s->types[t].needed)
                 PA_CK(cudaMalloc(&s->d_raw[b][t], sizeof(float) * s->types[t].frame_floats() * (size_t)s->max_frames));
-        PA_CK(cudaMallocHost(&s->h_pinned[b], sizeof(float) * std::max<size_t>(pinned, 1)));
+        s->h_pinned_bytes[b] = sizeof(float) * std::max<size_t>(pinned, 1);
+        s->h_pinned[b] = static_cast<float *>(pinned_pool_take(s->h_pinned_bytes[b]));
+        if (!s->h_pinned[b]) PA_CK(cudaMallocHost(&s->h_pinned[b], s->h_pinned_bytes[b]));
         PA_CK(cudaMalloc(&s->d_types[b], sizeof(PaDevType) * traj->ntypes));
         int rc = upload_types_table(s, b);
         if (rc) return rc;
@@ -638,7 +668,7 @@ void pa_session_destroy(pa_session *s)
     for (auto &m : s->types) { cudaFree(m.d_mass); cudaFree(m.d_charge); }
     for (int b = 0; b < 2; ++b) {
         for (float *p : s->d_raw[b]) cudaFree(p);
-        if (s->h_pinned[b]) cudaFreeHost(s->h_pinned[b]);
+        if (s->h_pinned[b]) pinned_pool_give(s->h_pinned[b], s->h_pinned_bytes[b]);
         cudaFree(s->d_types[b]);
         if (s->ev_h2d[b]) cudaEventDestroy(s->ev_h2d[b]);
         if (s->ev_done[b]) cudaEventDestroy(s->ev_done[b]);
@@ -687,8 +717,14 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
     for (int attempt = 0; attempt < 3; ++attempt) {
         const int batch = choose_batch(traj, &ex, nlocal);
         pa_session *s = nullptr;
+        const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
+        const auto w0 = std::chrono::steady_clock::now();
+        auto lap = [&](const char *what) {
+            if (dbg_t) fprintf(stderr, "[prealpha_b200] %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
+        };
         int rc = pa_session_create(traj, jobs, njobs, &ex, batch, &s);
         if (rc) return rc;
+        lap("create");
         cudaEvent_t t0, t1;
         cudaEventCreate(&t0); cudaEventCreate(&t1);
         cudaEventRecord(t0, s->s_compute);
@@ -698,9 +734,11 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
             rc = pa_session_upload(s, traj, first + done * stride, n, stride);
             if (rc == 0) rc = pa_session_run(s);
         }
+        lap("enqueued");
         if (rc == 0) rc = pa_session_download(s, hists, within_bin, out_of_bounds, 0);
         cudaEventRecord(t1, s->s_compute);
         cudaEventSynchronize(t1);
+        lap("download");
         if (stats) {
             pa_session_stats(s, stats);
             float ms = 0.f;
@@ -709,6 +747,7 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
         }
         cudaEventDestroy(t0); cudaEventDestroy(t1);
         pa_session_destroy(s);
+        lap("destroy");
         // sticky device flag: exception list overflow / boxes too wide for the cell path / non-finite
         // coordinates.  Redo without cells first, then with the general kernel (always applicable).
         if (rc == PA_ERR_UNSUPPORTED && getenv("PA_DEBUG")) fprintf(stderr, "[prealpha_b200] attempt %d: %s -> retrying with a more general kernel\n", attempt, pa_last_error());

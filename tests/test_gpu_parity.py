@@ -211,6 +211,27 @@ def test_cell_sorted_kernel_against_oracle(name, kw, oracle):
     assert int(cells[2].sum()) > 0, "the planted (anti)parallel / coincident pairs must show up as out of bounds"
 
 
+def test_cell_sorted_float32_segments_large_box(oracle):
+    """A box that is large compared with a tile (L/2 = 58 A vs 40 A tiles): the tile's own cell run is a single-image,
+    float32-eligible run, so the symmetric pass splits it between the fp64 launch (pairs inside the tile) and the
+    float32 launch (the rest).  All launch combinations must give the same integers as the brute-force kernel, and
+    the oracle agrees on the cross-type job."""
+    traj = _big_system(seed=31, n1=40000, n2=12800, L=116.0)
+    reqs = [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
+            dict(mode="pdf", vec=(0, 0, -1), ref_type=2, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
+            dict(mode="pdf", ref_type=2, obs_type=1, bin_a=400, bin_b=1, maxdist_optimize=True)]
+    pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
+    runs = {f: api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY | f))
+            for f in (0, capi.PA_EXEC_NO_F32, capi.PA_EXEC_NO_SYMMETRY, capi.PA_EXEC_NO_F32 | capi.PA_EXEC_NO_SYMMETRY, capi.PA_EXEC_NO_CELLS)}
+    assert runs[0][3].kernel_launches > runs[capi.PA_EXEC_NO_F32][3].kernel_launches      # the float32 launches really ran
+    ref = runs[capi.PA_EXEC_NO_CELLS]
+    for f, got in runs.items():
+        for k in range(len(pjobs)):
+            assert np.array_equal(got[0][k], ref[0][k]) and got[1][k] == ref[1][k] and got[2][k] == ref[2][k], (f, k)
+    h0, w0, o0 = oracle.histogram(traj, pjobs[2])
+    assert np.array_equal(ref[0][2], h0) and (int(ref[1][2]), int(ref[2][2])) == (w0, o0)
+
+
 @pytest.mark.parametrize("name,kw", BIG[:2] + BIG[2:], ids=[b[0] for b in BIG])
 def test_cell_sorted_general_kernel(name, kw, oracle):
     """2-D pdf / cdf / centre-of-charge jobs on large systems go through the cell-sorted general kernel
