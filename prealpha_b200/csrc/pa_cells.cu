@@ -446,7 +446,7 @@ static __device__ __forceinline__ float4 pc_lds_f32x4(unsigned int addr)
 //   entry: bits 0-8 reference index inside the tile, 9-15 observed index inside the staged chunk,
 //          16-23 n_hi - n_lo, 32-63 float bits of MAGIC + n_lo
 #define PC_QCAP 32
-template <bool ZCOL>
+template <int MX, int MY, int MZ, bool ZCOL>
 static __device__ __noinline__ void pc_f32_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                  const unsigned long long *queue, int count, unsigned int a_j, long long jbase, int jc,
                                                  unsigned int cnt_m)
@@ -458,10 +458,11 @@ static __device__ __noinline__ void pc_f32_drain(const PaPass &p, const PaCellGr
         const int k = (int)(ent & 511u), jl = (int)((ent >> 9) & 127u);
         const unsigned int tlo = (unsigned int)(ent >> 32), thi = tlo + (unsigned int)((ent >> 16) & 255u);
         const long long iref = (long long)tl.frame * gi.nmol + tl.begin + k;
-        const unsigned int rec = a_j + (unsigned)jl * 24u;
-        const double ex = pc_comp_sq<1>(pc_lds_f64(rec), 0.0, gi.sx[iref]);
-        const double ey = pc_comp_sq<1>(pc_lds_f64(rec + 8u), 0.0, gi.sy[iref]);
-        const double ez = pc_comp_sq<1>(pc_lds_f64(rec + 16u), 0.0, gi.sz[iref]);
+        constexpr int ND = MX + MY + MZ;                 // staged doubles per observed molecule, laid out as in pc_segment
+        const unsigned int rec = a_j + (unsigned)jl * (8u * ND);
+        const double ex = pc_comp_sq<MX>(pc_lds_f64(rec), pc_lds_f64(rec + 8u * (MX - 1)), gi.sx[iref]);
+        const double ey = pc_comp_sq<MY>(pc_lds_f64(rec + 8u * MX), pc_lds_f64(rec + 8u * (MX + MY - 1)), gi.sy[iref]);
+        const double ez = pc_comp_sq<MZ>(pc_lds_f64(rec + 8u * (MX + MY)), pc_lds_f64(rec + 8u * (MX + MY + MZ - 1)), gi.sz[iref]);
         const double e1 = __dadd_rn(ex, ey);
         const double e2 = __dadd_rn(e1, ez);
         if (ZCOL && __double2hiint(e1) < 0x3E100000) {
@@ -490,16 +491,27 @@ static __device__ __noinline__ void pc_f32_drain(const PaPass &p, const PaCellGr
     __syncwarp();
 }
 
-template <bool ZCOL, bool NEAR, bool VERIFY>
+// per-half minimum of two packed pairs
+static __device__ __forceinline__ unsigned long long pc_min2(unsigned long long a, unsigned long long b)
+{
+    return pc_pack(fminf(pc_lo(a), pc_lo(b)), fminf(pc_hi(a), pc_hi(b)));
+}
+
+// MX/MY/MZ: 1 = single image, 2 = two candidate images for that component (at most one component; its second
+// candidate travels in the .w lane of the staged float4, and the squared component is the smaller of the two squares)
+template <int MX, int MY, int MZ, bool ZCOL, bool NEAR, bool VERIFY>
 static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                       const float (&xf)[PC_RI], const float (&yf)[PC_RI], const float (&zf)[PC_RI],
                                                       const unsigned int (&cb)[PC_RI],
                                                       const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
                                                       double ox, double oy, double oz,
-                                                      long long jbase, int jb, int je, double sxa, double sya, double sza,
+                                                      long long jbase, int jb, int je,
+                                                      double sxa, double sxb, double sya, double syb, double sza, double szb,
                                                       double *s_j, float4 *s_jf, const PcTables &T, float near_a, unsigned long long *queue)
 {
     static_assert(PC_RI == 2, "the packed float32 loop pairs the two reference molecules of a thread");
+    static_assert(MX + MY + MZ <= 4, "at most one component with two candidate images");
+    constexpr int ND = MX + MY + MZ;
     static_assert(PC_TILE <= 512 && PC_JC <= 128, "queue entry layout");
     int qn = 0;                                         // entries in this warp's queue (warp-uniform)
     const unsigned int lane_lt = (1u << (threadIdx.x & 31)) - 1u;
@@ -517,13 +529,23 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
         {
             const int t = threadIdx.x;
             const int j = jc + t;
-            double x = 1.0e15, y = 1.0e15, z = 1.0e15;
-            float4 f = make_float4(T.pad_x, 0.0f, 0.0f, 0.0f);
+            double x = 1.0e15, y = 1.0e15, z = 1.0e15, b2 = 1.0e15;      // b2: second candidate of the two-image component
+            float4 f = make_float4(T.pad_x, 0.0f, 0.0f, MX == 2 ? T.pad_x : 0.0f);
             if (j < je) {
-                x = __dadd_rn(go.sx[jbase + j], sxa); y = __dadd_rn(go.sy[jbase + j], sya); z = __dadd_rn(go.sz[jbase + j], sza);
+                const double gx0 = go.sx[jbase + j], gy0 = go.sy[jbase + j], gz0 = go.sz[jbase + j];
+                x = __dadd_rn(gx0, sxa); y = __dadd_rn(gy0, sya); z = __dadd_rn(gz0, sza);
                 f.x = __double2float_rn(__dsub_rn(x, ox)); f.y = __double2float_rn(__dsub_rn(y, oy)); f.z = __double2float_rn(__dsub_rn(z, oz));
+                if (MX == 2) { b2 = __dadd_rn(gx0, sxb); f.w = __double2float_rn(__dsub_rn(b2, ox)); }
+                if (MY == 2) { b2 = __dadd_rn(gy0, syb); f.w = __double2float_rn(__dsub_rn(b2, oy)); }
+                if (MZ == 2) { b2 = __dadd_rn(gz0, szb); f.w = __double2float_rn(__dsub_rn(b2, oz)); }
             }
-            s_j[t * 3 + 0] = x; s_j[t * 3 + 1] = y; s_j[t * 3 + 2] = z;
+            {
+                double *rec = s_j + t * ND;                               // same layout as pc_segment
+                int o = 0;
+                rec[o++] = x; if (MX == 2) rec[o++] = b2;
+                rec[o++] = y; if (MY == 2) rec[o++] = b2;
+                rec[o++] = z; if (MZ == 2) rec[o++] = b2;
+            }
             s_jf[t] = f;
         }
         __syncthreads();
@@ -541,8 +563,23 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                 // both reference molecules of the thread at once (packed float32 pairs, sm_100 FADD2 / FMUL2 / FFMA2)
                 const float4 w = wv[u];
                 const unsigned long long dx = pc_sub2(pc_pack(w.x, w.x), X01), dy = pc_sub2(pc_pack(w.y, w.y), Y01), dz = pc_sub2(pc_pack(w.z, w.z), Z01);
-                const unsigned long long s1p = pc_fma2(dy, dy, pc_mul2(dx, dx));
-                const unsigned long long d2p = pc_fma2(dz, dz, s1p);
+                unsigned long long s1p, d2p;
+                if (MX == 2) {
+                    const unsigned long long db = pc_sub2(pc_pack(w.w, w.w), X01);
+                    s1p = pc_fma2(dy, dy, pc_min2(pc_mul2(dx, dx), pc_mul2(db, db)));
+                    d2p = pc_fma2(dz, dz, s1p);
+                } else if (MY == 2) {
+                    const unsigned long long db = pc_sub2(pc_pack(w.w, w.w), Y01);
+                    s1p = pc_add2(pc_mul2(dx, dx), pc_min2(pc_mul2(dy, dy), pc_mul2(db, db)));
+                    d2p = pc_fma2(dz, dz, s1p);
+                } else if (MZ == 2) {
+                    const unsigned long long db = pc_sub2(pc_pack(w.w, w.w), Z01);
+                    s1p = pc_fma2(dy, dy, pc_mul2(dx, dx));
+                    d2p = pc_add2(s1p, pc_min2(pc_mul2(dz, dz), pc_mul2(db, db)));
+                } else {
+                    s1p = pc_fma2(dy, dy, pc_mul2(dx, dx));
+                    d2p = pc_fma2(dz, dz, s1p);
+                }
 #pragma unroll
                 for (int r = 0; r < PC_RI; ++r) {
                     const int q = u * PC_RI + r;
@@ -568,7 +605,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                     const unsigned int m = __ballot_sync(0xffffffffu, need);
                     if (m == 0u) continue;
                     const int add = __popc(m);
-                    if (qn + add > PC_QCAP) { pc_f32_drain<ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }
+                    if (qn + add > PC_QCAP) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }
                     if (need) {
                         queue[qn + __popc(m & lane_lt)] = ((unsigned long long)tlo[q] << 32) | ((unsigned long long)min(thi[q] - tlo[q], 255u) << 16) |
                                                           ((unsigned long long)(jj + u) << 9) | (unsigned long long)k;
@@ -583,9 +620,9 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                 for (int q = 0; q < NP; ++q) {
                     const int r = q % PC_RI, u = q / PC_RI;
                     if (r * PC_THREADS + threadIdx.x >= tl.count || jc + jj + u >= je || ca[q] == trash) continue;
-                    const double *rec = s_j + (jj + u) * 3;
-                    const double e1 = __dadd_rn(pc_comp_sq<1>(rec[0], rec[0], p1x[r]), pc_comp_sq<1>(rec[1], rec[1], p1y[r]));
-                    const double e2 = __dadd_rn(e1, pc_comp_sq<1>(rec[2], rec[2], p1z[r]));
+                    const double *rec = s_j + (jj + u) * ND;
+                    const double e1 = __dadd_rn(pc_comp_sq<MX>(rec[0], rec[MX - 1], p1x[r]), pc_comp_sq<MY>(rec[MX], rec[MX + MY - 1], p1y[r]));
+                    const double e2 = __dadd_rn(e1, pc_comp_sq<MZ>(rec[MX + MY], rec[MX + MY + MZ - 1], p1z[r]));
                     int lo_k = 0, hi_k = na + 1;
                     while (lo_k < hi_k) { const int mid = (lo_k + hi_k + 1) >> 1; if (e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + mid))) lo_k = mid; else hi_k = mid - 1; }
                     const int got = (int)((ca[q] - T.cnt) / 4u);
@@ -596,7 +633,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
 #pragma unroll
             for (int q = 0; q < NP; ++q) pc_red(ca[q]);
         }
-        if (qn > 0) { pc_f32_drain<ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }   // before the chunk is overwritten
+        if (qn > 0) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }   // before the chunk is overwritten
     }
 }
 
@@ -637,9 +674,9 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     const int na = p.job.bin_a;
     const bool f32_on = VARIANT == 0 && PART != 0 && p.f32_cnt > 0;       // PART 0 is launched only when float32 segments are off
     const int ncnt = (f32_on && PART == 1) ? p.f32_cnt + na + 8 : na + 3;                                // counters (see pc_segment_f32)
-    // PART 1 (float32 runs only): 3 staged doubles per molecule and no threshold table (read from global when needed)
-    double *s_j = reinterpret_cast<double *>(smem_raw);                                   // PC_JC*6 doubles (PART 1: *3)
-    float4 *s_jf = reinterpret_cast<float4 *>(s_j + PC_JC * (PART == 1 ? 3 : 6));         // PC_JC float4
+    // PART 1 (float32 runs only): at most 4 staged doubles per molecule and no threshold table (read from global when needed)
+    double *s_j = reinterpret_cast<double *>(smem_raw);                                   // PC_JC*6 doubles (PART 1: *4)
+    float4 *s_jf = reinterpret_cast<float4 *>(s_j + PC_JC * (PART == 1 ? 4 : 6));         // PC_JC float4
     unsigned long long *s_thr = reinterpret_cast<unsigned long long *>(s_jf + PC_JC);     // na+3 (PART 1: none)
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_thr + (PART == 1 ? 0 : na + 3));   // ncnt (+1 pad)
     PcSharedR *sh = reinterpret_cast<PcSharedR *>(s_cnt + ((ncnt + 1) & ~1));
@@ -787,7 +824,10 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     cx = ce + 1;
                     // float32-eligible runs belong to the PART 1 launch -- except the part of a run that overlaps the tile
                     // itself in a symmetric pass (db..de below), which always takes the fp64 segment of PART 0 / 2
-                    const bool f32run = far && lx.mode == 1 && ly.mode == 1 && lz.mode == 1;
+                    // (all components single image, or -- far runs only -- exactly one component with two candidates)
+                    const int dcode = (lx.mode >= 2 ? 1 : 0) | (ly.mode >= 2 ? 2 : 0) | (lz.mode >= 2 ? 4 : 0);
+                    const bool f32run = far && lx.mode <= 2 && ly.mode <= 2 && lz.mode <= 2 &&
+                                        (dcode == 0 || (!nearr && (dcode == 4 || ((dcode == 1 || dcode == 2) && !zcol))));
                     if (PART == 1 && !f32run) continue;
                     int db = 0, de = 0;                                              // part of the run that overlaps the tile itself
                     if (SYM && cz * gy + cy == tile_row) {
@@ -808,10 +848,15 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     }
                     if (jb >= je) continue;
                     if (PART == 2 && f32run) continue;                              // counted by the PART 1 launch
-                    if (VARIANT == 0 && PART == 1 && far && code == 0) {
-#define PC_F32(Z_, N_) pc_segment_f32<Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_j, s_jf, T, near_a, queue)
-                        if (nearr) { if (zcol) PC_F32(true, true); else PC_F32(false, true); }
-                        else { if (zcol) PC_F32(true, false); else PC_F32(false, false); }
+                    if (VARIANT == 0 && PART == 1 && f32run) {
+#define PC_F32(MX_, MY_, MZ_, Z_, N_) pc_segment_f32<MX_, MY_, MZ_, Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, \
+                                                                                    sxa, sxb, sya, syb, sza, szb, s_j, s_jf, T, near_a, queue)
+                        if (dcode == 0) {
+                            if (nearr) { if (zcol) PC_F32(1, 1, 1, true, true); else PC_F32(1, 1, 1, false, true); }
+                            else { if (zcol) PC_F32(1, 1, 1, true, false); else PC_F32(1, 1, 1, false, false); }
+                        } else if (dcode == 1) PC_F32(2, 1, 1, false, false);
+                        else if (dcode == 2) PC_F32(1, 2, 1, false, false);
+                        else { if (zcol) PC_F32(1, 1, 2, true, false); else PC_F32(1, 1, 2, false, false); }
 #undef PC_F32
                         continue;
                     }
@@ -1066,7 +1111,7 @@ void pa_cell_grid_dims(int nmol, int g[3])
 size_t pa_cells_smem_bytes(int na, int f32_cnt, int nlayers)   // f32_cnt > 0: the PART 1 launch
 {
     const int ncnt = f32_cnt > 0 ? f32_cnt + na + 8 : na + 3;
-    return (size_t)PC_JC * (f32_cnt > 0 ? 3 : 6) * 8 + (size_t)PC_JC * 16 + (f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 2) * 4 +
+    return (size_t)PC_JC * (f32_cnt > 0 ? 4 : 6) * 8 + (size_t)PC_JC * 16 + (f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 2) * 4 +
            sizeof(PcSharedR) + (size_t)nlayers * sizeof(PcLayer) + (f32_cnt > 0 ? (size_t)(PC_THREADS / 32) * PC_QCAP * 8 : 0) + 16;
 }
 
