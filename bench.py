@@ -189,7 +189,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "binned pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",     # results are defined by the reference's fp64 arithmetic; float32 only brackets the class
         "config": {"workload": f"synthetic cubic box (same generator and density as the 1M-atom case), {2 * n_half} atoms x {frames} frames, "
                                "references 1 -1 and 2 -1, maxdist_optimize, 1000x1 bins; brute force, cost per pair independent of N"},
         "pair_evals_per_s": sum(r["pair_evals_per_s"] * r["seconds"] for r in res) / sec,
@@ -327,13 +327,14 @@ def main():
             assert abs(frac_binned - np.pi / 6.0) < 1.0e-4, f"binned fraction {frac_binned} is not pi/6: counts are wrong"
         value = binned_total / t_value_max
         pe_per_s = pair_evals_total / t_value_max
-        # dominant kernel: pa_rdf_fast_kernel (2 launches per step: observed type 1 and 2 per job -> 4)
+        # dominant kernel: pa_rdf_cells_kernel<0,*,*,1> (float32 launch of the cell-sorted RDF kernel; 3 launches per step:
+        # two symmetric same-type passes and the merged cross-type pass), 95 % of the GPU time (profiles/r1h_launches_bench_1M.csv)
         pair_evals_per_s_kernel = pair_evals_rank / (kernel_ms * 1e-3)
         achieved = pair_evals_per_s_kernel * FP64_OPS_PER_PAIR
         line = {
             "metric": METRIC, "value": value, "unit": "binned pairs/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": 1e3 * t_value_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": "synthetic",     # results are defined by the reference's fp64 arithmetic; float32 only brackets the class
             "config": {"workload": f"synthetic cubic box, {natoms} atoms (2 one-atom types), L={L} A, 1 frame per GPU per step, "
                                    f"references 1 -1 and 2 -1 (all ordered pairs), maxdist_optimize, {BINS}x1 bins",
                        "pair_evals_per_step_per_gpu": pair_evals_rank / K, "frames_sharding": "frame s*N+r on GPU r, NCCL int64 reduce once",
@@ -343,10 +344,16 @@ def main():
                     "d2h_bytes_per_step": int(st_e.d2h_bytes // K), "ms_per_step": 1e3 * t_e2e_max / K},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved / 1e9, "peak": fp64_rate / 1e9, "unit": "Ginst/s",
-                         "frac": achieved / fp64_rate, "traffic": None,
+                         "frac": achieved / fp64_rate,
+                         # dram__bytes_read+write of the merged cross-type launch (500k x 500k molecules) in the ncu --set full
+                         # capture profiles/r1h_ncu_full_pa_rdf_cells_kernel.csv: 24.36 MB + 3 KB = the 24 B per sorted molecule it must read
+                         "traffic": 24.37e6 if n_half == N_PER_TYPE else None,
                          "note": "algorithmic 26 FP64-pipe instructions per evaluated pair (SURVEY 8d) x pair evaluations / CUDA-event "
                                  "time of the pair kernels on their stream; peak = DSUB/DMUL issue rate measured live on this GPU "
-                                 "(MEASURED_PEAKS.json has no FP64 entry). HBM is not the bound: 12 B per atom per frame.",
+                                 "(MEASURED_PEAKS.json has no FP64 entry). frac > 1 because the kernels prune by cells, evaluate "
+                                 "symmetric pairs once and bracket the class in packed float32 (exact fp64 only for ~1e-3 of the pairs); "
+                                 "the launch itself is bound by issue slots (71 %) and shared-memory atomics (68 % of LSU wavefronts), "
+                                 "see profiles/README.md. HBM is not the bound: 12 B per atom per frame.",
                          "kernel_ms_per_step": kernel_ms / K,
                          "hbm_gbs_frame_streaming": (natoms * 12 * K) / (kernel_ms * 1e-3) / 1e9},
             "clocks": clocks,
