@@ -1,3 +1,5 @@
+"""Debug helper: the end-to-end C-ABI call of bench.py on 4 frames of the 1M-atom workload, with and without the float32
+launch (PA_EXEC_NO_F32 = 8); prints wall time, kernel time and counters.  PA_DEBUG_TIMING=1 adds the host phases."""
 import time, sys, numpy as np
 sys.path.insert(0, "/root/repo")
 import bench
