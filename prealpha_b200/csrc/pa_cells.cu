@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, PaPo
         const long long o = (long long)f * g.nmol + pos;
         g.sx[o] = pts.px[slot]; g.sy[o] = pts.py[slot]; g.sz[o] = pts.pz[slot];
         g.sorig[o] = m;
+        g.sflag[o] = (pts.wx[slot] != 0.0 || pts.wy[slot] != 0.0 || pts.wz[slot] != 0.0) ? 1 : 0;
     }
 }
 
@@ -888,16 +889,60 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
 // same per-run image classification and cutoff pruning as above; a pair inside the cutoff gets the
 // literal evaluation (pa_eval_pair_exact) through its original slots.  With cutoffs well below L/2
 // (the usual 2-D case) almost all cell runs are skipped, which is where the speed-up comes from.
+// Pairs inside the cutoff are not evaluated where they are found (a quarter of the lanes at a time) but appended
+// to a queue of their warp -- entry = (reference index inside the tile, observed index inside the staged chunk) --
+// and drained with one entry per lane.  An entry whose two molecules were not moved by wrap_vector, in a run with
+// one possible image per component, needs no global data: translation + wrapshift is the run's image shift, so
+// the reference's link vector (translation + com_obs) - com_ref (Distribution:786-792) is bit for bit the
+// difference fl(p2+s) - p1 already staged, and the bin follows from pa_bin_from_link.  Everything else (centre of
+// charge, wrapped molecules, two candidate images, m >= maximum_distance_squared) takes pa_eval_pair_exact.
+#define PG_QCAP 64
+template <int MODE, bool SMEM_HIST>
+static __device__ __noinline__ void pg_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                             const unsigned int *queue, int count, const double *s_j, const int *s_jo,
+                                             long long jbase, int jc, unsigned int *s_hist, int nbins,
+                                             unsigned long long &g_within, unsigned long long &g_oob)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+    for (int base = 0; base < count; base += 32) {
+        if (base + lane >= count) continue;
+        const unsigned int ent = queue[base + lane];
+        const int k = (int)(ent & 0xffffu), jl = (int)(ent >> 16);
+        const long long iref = (long long)tl.frame * gi.nmol + tl.begin + k;
+        const int io = gi.sorig[iref], jo = s_jo[jl];
+        int bin = 0, st;
+        bool fast = false;
+        if (MODE == 1 && !p.job.use_coc && !p.box.wrap_trajectory && gi.sflag[iref] == 0 && go.sflag[jbase + jc + jl] == 0) {
+            const double *rec = s_j + jl * 6;
+            const double link[3] = { __dsub_rn(rec[0], gi.sx[iref]), __dsub_rn(rec[2], gi.sy[iref]), __dsub_rn(rec[4], gi.sz[iref]) };
+            const double m = __dadd_rn(__dadd_rn(__dmul_rn(link[0], link[0]), __dmul_rn(link[1], link[1])), __dmul_rn(link[2], link[2]));
+            if (m < p.box.max_dist_sq) { st = pa_bin_from_link(p, m, link, &bin); fast = true; }
+        }
+        if (!fast) st = pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
+        if (SMEM_HIST) {
+            if (st == 1) atomicAdd(&s_hist[bin], 1u);
+            else if (st == 2) atomicAdd(&s_hist[nbins], 1u);
+        } else {
+            if (st == 1) { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
+            else if (st == 2) ++g_oob;
+        }
+    }
+    __syncwarp();
+}
+
 template <int MODE, bool SMEM_HIST>
 static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                   const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
                                                   const int (&iorig)[PC_RI], long long jbase, int jb, int je,
                                                   double sxa, double sxb, double sya, double syb, double sza, double szb,
-                                                  double *s_j, int *s_jo, unsigned int *s_hist, int nbins,
+                                                  double *s_j, int *s_jo, unsigned int *s_hist, int nbins, unsigned int *queue,
                                                   unsigned long long &g_within, unsigned long long &g_oob)
 {
     const unsigned long long cut = p.job.cut_bits;
-    const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+    const unsigned int lane_lt = (1u << (threadIdx.x & 31)) - 1u;
+    int qn = 0;                                          // entries in this warp's queue (warp-uniform)
     for (int jc = jb; jc < je; jc += PC_JC) {
         __syncthreads();
         {
@@ -917,27 +962,24 @@ static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellG
         for (int jj = 0; jj < cnt; ++jj) {
             const double2 *rec = reinterpret_cast<const double2 *>(s_j + jj * 6);
             const double2 rx = rec[0], ry = rec[1], rz = rec[2];
+            const int jo = s_jo[jj];
 #pragma unroll
             for (int r = 0; r < PC_RI; ++r) {
                 const double sx = pc_comp_sq<MODE>(rx.x, rx.y, p1x[r]);
                 const double sy = pc_comp_sq<MODE>(ry.x, ry.y, p1y[r]);
                 const double sz = pc_comp_sq<MODE>(rz.x, rz.y, p1z[r]);
                 const double d2 = __dadd_rn(__dadd_rn(sx, sy), sz);
-                if (dbits(d2) < cut) {
-                    const int jo = s_jo[jj];
-                    if (iorig[r] < 0 || (p.same_type && iorig[r] == jo)) continue;          // padding lane / Distribution:778
-                    int bin = 0;
-                    const int st = pa_eval_pair_exact(p, fb + p.ref_off + iorig[r], fb + p.obs_off + jo, &bin);
-                    if (SMEM_HIST) {
-                        if (st == 1) atomicAdd(&s_hist[bin], 1u);
-                        else if (st == 2) atomicAdd(&s_hist[nbins], 1u);
-                    } else {
-                        if (st == 1) { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
-                        else if (st == 2) ++g_oob;
-                    }
-                }
+                // inside the cutoff, not a padding lane, not the molecule itself (Distribution:778)
+                const bool need = dbits(d2) < cut && iorig[r] >= 0 && !(p.same_type && iorig[r] == jo);
+                const unsigned int m = __ballot_sync(0xffffffffu, need);
+                if (m == 0u) continue;
+                const int add = __popc(m);
+                if (qn + add > PG_QCAP) { pg_drain<MODE, SMEM_HIST>(p, go, gi, tl, queue, qn, s_j, s_jo, jbase, jc, s_hist, nbins, g_within, g_oob); qn = 0; }
+                if (need) queue[qn + __popc(m & lane_lt)] = ((unsigned int)jj << 16) | (unsigned int)(r * PC_THREADS + threadIdx.x);
+                qn += add;
             }
         }
+        if (qn > 0) { pg_drain<MODE, SMEM_HIST>(p, go, gi, tl, queue, qn, s_j, s_jo, jbase, jc, s_hist, nbins, g_within, g_oob); qn = 0; }   // before the chunk is overwritten
     }
 }
 
@@ -957,7 +999,7 @@ static __device__ void pg_flush(const PaPass &p, unsigned int *s_hist, int nbins
 }
 
 template <bool SMEM_HIST>
-__global__ void __launch_bounds__(PC_THREADS) pa_general_cells_kernel(const __grid_constant__ PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
+__global__ void __launch_bounds__(PC_THREADS, 5) pa_general_cells_kernel(const __grid_constant__ PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
                                                                        const unsigned int *ntiles_ptr, unsigned int tile_cap,
                                                                        unsigned int *work_counter, int nzg)
 {
@@ -966,7 +1008,8 @@ __global__ void __launch_bounds__(PC_THREADS) pa_general_cells_kernel(const __gr
     double *s_j = reinterpret_cast<double *>(smem_raw);                         // PC_JC*6 doubles
     int *s_jo = reinterpret_cast<int *>(s_j + PC_JC * 6);                       // PC_JC original indices
     PcShared *sh = reinterpret_cast<PcShared *>(s_jo + PC_JC);
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(sh + 1);            // nbins+1 (SMEM_HIST)
+    unsigned int *queue = reinterpret_cast<unsigned int *>(sh + 1) + (threadIdx.x >> 5) * PG_QCAP;   // per warp
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(sh + 1) + (PC_THREADS / 32) * PG_QCAP;   // nbins+1 (SMEM_HIST)
     if (SMEM_HIST) for (int k = threadIdx.x; k < nbins + 1; k += blockDim.x) s_hist[k] = 0u;
     __syncthreads();
     const double cut_d2 = __longlong_as_double((long long)p.job.cut_bits) * (1.0 + 1e-12);
@@ -1051,9 +1094,9 @@ __global__ void __launch_bounds__(PC_THREADS) pa_general_cells_kernel(const __gr
                     const double sya = (double)(ly.ca - 1) * Ly, syb = (double)(ly.cb - 1) * Ly;
                     const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
                     if (lx.mode < 2 && ly.mode < 2 && lz.mode < 2)
-                        pg_segment<1, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, g_within, g_oob);
+                        pg_segment<1, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, queue, g_within, g_oob);
                     else
-                        pg_segment<2, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, g_within, g_oob);
+                        pg_segment<2, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, queue, g_within, g_oob);
                 }
             }
         }
@@ -1149,8 +1192,11 @@ int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellG
 {
     cudaStream_t st = (cudaStream_t)stream;
     const int nbins = p.job.bin_a * p.job.bin_b;
-    const bool smem_hist = nbins <= 40000;
-    const size_t smem = (size_t)PC_JC * 6 * 8 + (size_t)PC_JC * 4 + sizeof(PcShared) + (smem_hist ? (size_t)(nbins + 1) * 4 : 0) + 16;
+    // a shared-memory histogram only while it leaves room for >= 6 CTAs per SM (occupancy matters more to this
+    // latency-bound kernel than the atomics: larger histograms take 64-bit atomics in L2)
+    const bool smem_hist = nbins <= 6000;
+    const size_t smem = (size_t)PC_JC * 6 * 8 + (size_t)PC_JC * 4 + sizeof(PcShared) + (size_t)(PC_THREADS / 32) * PG_QCAP * 4 +
+                        (smem_hist ? (size_t)(nbins + 1) * 4 : 0) + 16;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
 #define PG_LAUNCH(S_)                                                                                           \
     do {                                                                                                        \

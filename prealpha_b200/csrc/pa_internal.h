@@ -108,6 +108,7 @@ struct PaCellGrid {
     int *cid;                        // [nframes][nmol]    cell of every molecule
     double *sx, *sy, *sz;            // [nframes][nmol]    wrapped positions in cell order
     int *sorig;                      // [nframes][nmol]    original molecule index
+    unsigned char *sflag;            // [nframes][nmol]    1: the centre of mass was moved by wrap_vector (w != 0)
     unsigned long long *lay_lo, *lay_hi;   // [nframes][3][gmax] exact bounds per cell layer (ordered keys)
 };
 struct PaTile { int32_t frame, begin, count, cx0, cx1, cy, cz, pad; };

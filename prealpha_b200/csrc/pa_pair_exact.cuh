@@ -17,6 +17,48 @@ static __device__ __forceinline__ int pa_int_of_float_x86(float x)
 static __device__ __forceinline__ int pa_plus1_wrap(int v) { return (int)((unsigned)v + 1u); }
 
 // ---------------------------------------------------------------------------
+// Bin of a pair inside the cutoff from its separable minimum m (fp64) and its link vector (row F,
+// Distribution:796-827).  Shared by the literal evaluation below and by the in-register path of the
+// cell-sorted general kernel, so both produce the same bits by construction.
+// returns 1 = binned (index in *bin), 2 = out of bounds.
+static __device__ __forceinline__ int pa_bin_from_link(const PaPass &p, double m, const double (&link)[3], int *bin)
+{
+    const int na = p.job.bin_a, nb = p.job.bin_b;
+    int ia, ib;
+    if (p.job.mode == PA_MODE_CDF) {                         // Distribution:796-809, Angles:104-115
+        const double *R = p.job.rot;
+        const double rx = __dadd_rn(__dadd_rn(__dmul_rn(link[0], R[0]), __dmul_rn(link[1], R[1])), __dmul_rn(link[2], R[2]));
+        const double ry = __dadd_rn(__dadd_rn(__dmul_rn(link[0], R[3]), __dmul_rn(link[1], R[4])), __dmul_rn(link[2], R[5]));
+        const double rz = __dadd_rn(__dadd_rn(__dmul_rn(link[0], R[6]), __dmul_rn(link[1], R[7])), __dmul_rn(link[2], R[8]));
+        const float a = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry))));
+        const float b = __double2float_rn(rz);
+        ia = pa_plus1_wrap(pa_int_of_float_x86(__fdiv_rn(a, p.job.step_a)));
+        const float bs = __fadd_rn(b, p.job.shift);
+        ib = pa_plus1_wrap(pa_int_of_float_x86(__fdiv_rn(bs, p.job.step_b)));
+        if (ib == 1 && bs < 0.0f) ib = 0;
+    } else {                                                 // Distribution:812-827
+        // a-class from the threshold table (binary search: no assumption on the seed)
+        const unsigned long long db = pa_dbits(m);
+        int lo = 0, hi = na + 1;                             // class in [lo, hi]
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.job.thr_a[mid] <= db) lo = mid; else hi = mid - 1; }
+        ia = lo + 1;                                         // class na -> binpos_a = na+1 (out of bounds)
+        const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(link[0], link[0]), __dmul_rn(link[1], link[1])), __dmul_rn(link[2], link[2])));
+        const double lx = __ddiv_rn(link[0], len), ly = __ddiv_rn(link[1], len), lz = __ddiv_rn(link[2], len);
+        const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(lx, p.job.ref_vec[0])), __dmul_rn(ly, p.job.ref_vec[1])),
+                                     __dmul_rn(lz, p.job.ref_vec[2]));
+        if (!(dot >= -1.0 && dot <= 1.0)) ib = -1;           // ACOS -> NaN -> INT() = INT_MIN -> binpos_b < 1
+        else {
+            // thr_b[k] (k=1..nb) = largest dot with INT(REAL4(ACOS(dot))/step_b) >= k, decreasing in k
+            int l2 = 0, h2 = nb;
+            while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (dot <= p.job.thr_b[mid]) l2 = mid; else h2 = mid - 1; }
+            ib = l2 + 1;
+        }
+    }
+    if (ia > 0 && ia <= na && ib > 0 && ib <= nb) { *bin = (ib - 1) * na + (ia - 1); return 1; }
+    return 2;
+}
+
+// ---------------------------------------------------------------------------
 // literal per-pair evaluation (rows D + F), used by the general and the exception kernel.
 // returns 0 = beyond cutoff (not counted), 1 = binned (index in *bin), 2 = out of bounds.
 static __device__ __noinline__ int pa_eval_pair_exact(const PaPass &p, long long i_abs, long long j_abs, int *bin)
@@ -71,39 +113,7 @@ static __device__ __noinline__ int pa_eval_pair_exact(const PaPass &p, long long
             link[c] = __dsub_rn(__dadd_rn(tr, c2[c]), c1[c]);                             // Distribution:786-792
         }
     }
-    const int na = p.job.bin_a, nb = p.job.bin_b;
-    int ia, ib;
-    if (p.job.mode == PA_MODE_CDF) {                         // Distribution:796-809, Angles:104-115
-        const double *R = p.job.rot;
-        const double rx = __dadd_rn(__dadd_rn(__dmul_rn(link[0], R[0]), __dmul_rn(link[1], R[1])), __dmul_rn(link[2], R[2]));
-        const double ry = __dadd_rn(__dadd_rn(__dmul_rn(link[0], R[3]), __dmul_rn(link[1], R[4])), __dmul_rn(link[2], R[5]));
-        const double rz = __dadd_rn(__dadd_rn(__dmul_rn(link[0], R[6]), __dmul_rn(link[1], R[7])), __dmul_rn(link[2], R[8]));
-        const float a = __double2float_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(rx, rx), __dmul_rn(ry, ry))));
-        const float b = __double2float_rn(rz);
-        ia = pa_plus1_wrap(pa_int_of_float_x86(__fdiv_rn(a, p.job.step_a)));
-        const float bs = __fadd_rn(b, p.job.shift);
-        ib = pa_plus1_wrap(pa_int_of_float_x86(__fdiv_rn(bs, p.job.step_b)));
-        if (ib == 1 && bs < 0.0f) ib = 0;
-    } else {                                                 // Distribution:812-827
-        // a-class from the threshold table (binary search: no assumption on the seed)
-        const unsigned long long db = pa_dbits(m);
-        int lo = 0, hi = na + 1;                             // class in [lo, hi]
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.job.thr_a[mid] <= db) lo = mid; else hi = mid - 1; }
-        ia = lo + 1;                                         // class na -> binpos_a = na+1 (out of bounds)
-        const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(link[0], link[0]), __dmul_rn(link[1], link[1])), __dmul_rn(link[2], link[2])));
-        const double lx = __ddiv_rn(link[0], len), ly = __ddiv_rn(link[1], len), lz = __ddiv_rn(link[2], len);
-        const double dot = __dadd_rn(__dadd_rn(__dadd_rn(0.0, __dmul_rn(lx, p.job.ref_vec[0])), __dmul_rn(ly, p.job.ref_vec[1])),
-                                     __dmul_rn(lz, p.job.ref_vec[2]));
-        if (!(dot >= -1.0 && dot <= 1.0)) ib = -1;           // ACOS -> NaN -> INT() = INT_MIN -> binpos_b < 1
-        else {
-            // thr_b[k] (k=1..nb) = largest dot with INT(REAL4(ACOS(dot))/step_b) >= k, decreasing in k
-            int l2 = 0, h2 = nb;
-            while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (dot <= p.job.thr_b[mid]) l2 = mid; else h2 = mid - 1; }
-            ib = l2 + 1;
-        }
-    }
-    if (ia > 0 && ia <= na && ib > 0 && ib <= nb) { *bin = (ib - 1) * na + (ia - 1); return 1; }
-    return 2;
+    return pa_bin_from_link(p, m, link, bin);
 }
 
 

@@ -357,6 +357,7 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
             PA_CK(cudaMalloc(&g.sy, sizeof(double) * nf * nm));
             PA_CK(cudaMalloc(&g.sz, sizeof(double) * nf * nm));
             PA_CK(cudaMalloc(&g.sorig, sizeof(int) * nf * nm));
+            PA_CK(cudaMalloc(&g.sflag, nf * nm));
             PA_CK(cudaMalloc(&g.lay_lo, sizeof(unsigned long long) * nf * 3 * g.gmax));
             PA_CK(cudaMalloc(&g.lay_hi, sizeof(unsigned long long) * nf * 3 * g.gmax));
             // every cell yields at most one tile plus one extra per 256 molecules
@@ -677,7 +678,7 @@ void pa_session_destroy(pa_session *s)
     for (auto &tg : s->grids) {
         if (!tg.enabled) continue;
         cudaFree(tg.g.cell_start); cudaFree(tg.g.cell_fill); cudaFree(tg.g.cid); cudaFree(tg.g.sx); cudaFree(tg.g.sy); cudaFree(tg.g.sz);
-        cudaFree(tg.g.sorig); cudaFree(tg.g.lay_lo); cudaFree(tg.g.lay_hi); cudaFree(tg.tiles); cudaFree(tg.counters);
+        cudaFree(tg.g.sorig); cudaFree(tg.g.sflag); cudaFree(tg.g.lay_lo); cudaFree(tg.g.lay_hi); cudaFree(tg.tiles); cudaFree(tg.counters);
     }
     cudaFree(s->d_pts); cudaFree(s->d_acc); cudaFree(s->d_exc); cudaFree(s->d_exc_count);
     if (s->s_compute) cudaStreamDestroy(s->s_compute);
