@@ -354,6 +354,12 @@ def main():
                                  "symmetric pairs once and bracket the class in packed float32 (exact fp64 only for ~1e-3 of the pairs); "
                                  "the launch itself is bound by issue slots (71 %) and shared-memory atomics (68 % of LSU wavefronts), "
                                  "see profiles/README.md. HBM is not the bound: 12 B per atom per frame.",
+                         # second bound named by the north star: shared-memory atomics.  Every pair the kernels evaluate after cell
+                         # pruning issues one ATOMS.POPC.INC: 4.50e11 per 1M-atom frame (ncu, smsp__inst_executed_op_shared_atom x 32
+                         # summed over the launches of a frame, profiles/r1h_ncu_full_pa_rdf_cells_kernel.csv); peak = the r^2-distributed
+                         # 1000-bin histogram microbenchmark, profiles/microbench_r1.json
+                         "smem_atomics": ({"achieved": 4.50e11 * K / (kernel_ms * 1e-3), "peak": 4.2e12, "unit": "atomics/s",
+                                           "frac": 4.50e11 * K / (kernel_ms * 1e-3) / 4.2e12} if n_half == N_PER_TYPE else None),
                          "kernel_ms_per_step": kernel_ms / K,
                          "hbm_gbs_frame_streaming": (natoms * 12 * K) / (kernel_ms * 1e-3) / 1e9},
             "clocks": clocks,
