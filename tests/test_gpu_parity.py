@@ -211,6 +211,32 @@ def test_cell_sorted_kernel_against_oracle(name, kw, oracle):
     assert int(cells[2].sum()) > 0, "the planted (anti)parallel / coincident pairs must show up as out of bounds"
 
 
+def test_full_size_frame_launch_combinations_agree():
+    """BASELINE's full size (1M atoms in one frame, both references, 1000 bins, cutoff L/2) is far beyond the oracle's
+    reach; what can be checked at that size are properties: every kernel combination (float32 launch on/off,
+    symmetric + merged passes on/off) must give the same integers, the histogram must sum to `within bin`, every
+    ordered pair is either binned, beyond the cutoff or out of bounds, and for uniform points the binned fraction is
+    the sphere / cube volume ratio pi/6."""
+    import bench
+    n_half, L = bench.N_PER_TYPE, float(bench.L_BOX)
+    frames = np.stack([bench.synth_frame(0, 2 * n_half, L)])
+    traj = bench.make_traj(frames, n_half, L)
+    jobs = bench.make_jobs(traj)
+    runs = {f: api.histogram_multi(traj, jobs, api.make_exec(flags=f))
+            for f in (0, capi.PA_EXEC_NO_F32, capi.PA_EXEC_NO_F32 | capi.PA_EXEC_NO_SYMMETRY)}
+    ref = runs[capi.PA_EXEC_NO_F32 | capi.PA_EXEC_NO_SYMMETRY]
+    for f, got in runs.items():
+        for k in range(len(jobs)):
+            assert np.array_equal(got[0][k], ref[0][k]) and got[1][k] == ref[1][k] and got[2][k] == ref[2][k], (f, k)
+    hists, within, oob, st = runs[0]
+    for k in range(len(jobs)):
+        assert int(hists[k].sum()) == int(within[k])
+    pairs = 2 * n_half * (2 * n_half - 1)
+    assert st.pairs_evaluated == pairs
+    assert abs(float(within.sum()) / pairs - np.pi / 6.0) < 1.0e-4
+    assert int(oob.sum()) < 1000          # only links (anti)parallel to z within 3e-8 rad can be out of bounds
+
+
 def test_cell_sorted_float32_segments_large_box(oracle):
     """A box that is large compared with a tile (L/2 = 58 A vs 40 A tiles): the tile's own cell run is a single-image,
     float32-eligible run, so the symmetric pass splits it between the fp64 launch (pairs inside the tile) and the
