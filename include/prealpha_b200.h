@@ -277,6 +277,32 @@ typedef struct pa_contact_result {
 } pa_contact_result;
 int pa_contact_distance(const pa_traj *traj, int32_t timestep, int32_t type, const pa_exec *exec, pa_contact_result *result);
 
+/* ---- neighbour pairs -----------------------------------------
+ * The distance test that the cluster and speciation analyses run for every pair
+ * of listed atoms: give_smallest_atom_distance_squared(...) < squared cutoff in
+ * REAL(4) (Cluster:1094-1100 with one cutoff per pass; Speciation:1407-1431 with
+ * one cutoff per (acceptor atom, donor atom) combination).  Returns every
+ * qualifying pair of atom instances, sorted by (ia, ib) = the order in which the
+ * reference's nested loops meet them, so that the sequential bookkeeping
+ * (cluster merging, species clipboard) can replay them on the host.
+ * Instances are (molecule type, molecule index, atom index) triples, 1-based. */
+typedef struct pa_neigh_request {
+    int32_t timestep;            /* 1-based                                                     */
+    int32_t n_a, n_b;            /* atom instances in list a (outer loop) and b (inner loop)    */
+    const int32_t *a, *b;        /* [n][3]                                                      */
+    const int32_t *a_class;      /* optional [n_a], 0-based row of cutoff_sq (NULL: row 0)      */
+    const int32_t *b_class;      /* optional [n_b], 0-based column of cutoff_sq (NULL: col 0)   */
+    int32_t n_class_a, n_class_b;
+    const float *cutoff_sq;      /* [n_class_a][n_class_b] REAL(4) squared cutoffs              */
+    int32_t same_list;           /* 1: b is a; each unordered pair once, ib > ia (Cluster:1092) */
+    int32_t skip_same_molecule;  /* 1: atoms of one molecule are never paired (Speciation:1407) */
+} pa_neigh_request;
+typedef struct pa_neigh_pair { int32_t ia, ib; } pa_neigh_pair;   /* 0-based positions in the lists */
+/* Writes at most `capacity` pairs; *count is the number found (call again with a larger buffer when
+ * it exceeds capacity).  *tests = distance tests carried out. */
+int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *req, const pa_exec *exec,
+                       pa_neigh_pair *out, int64_t capacity, int64_t *count, int64_t *tests);
+
 /* ---- file-level drop-in ----------------------------------
  * Runs a general.inp the way `./prealpha general.inp` does for the keywords
  * of this path (Main:103-357 header, Main:2882-3666 body; unknown keywords

@@ -36,6 +36,8 @@ _SIG = {
     "orc_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
     "orc_distance_subjobs": (C.c_int, [C.POINTER(capi.pa_traj), C.POINTER(capi.pa_dist_job), C.POINTER(capi.pa_dist_result)]),
     "orc_contact_distance": (C.c_int, [C.POINTER(capi.pa_traj), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "orc_neighbour_pairs": (C.c_int, [C.POINTER(capi.pa_traj), C.POINTER(capi.pa_neigh_request), C.POINTER(capi.pa_neigh_pair),
+                                      C.c_int64, _I64P]),
     "orc_wrap_full": (C.c_int, [C.POINTER(capi.pa_traj)]),
     "orc_unwrap_full": (C.c_int, [C.POINTER(capi.pa_traj)]),
     "orc_read_xyz": (C.c_int, [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_char_p]),
@@ -120,6 +122,14 @@ def contact_distance(traj, timestep, type_, nthreads=0):
     rc = load().orc_contact_distance(traj.ptr, timestep, type_, nthreads or (os.cpu_count() or 1), out)
     assert rc == 0, rc
     return tuple(np.float32(v) for v in out)
+
+
+def neighbour_pairs(traj, rq, capacity=1 << 22):
+    out = np.zeros((capacity, 2), dtype=np.int32)
+    count = C.c_int64(0)
+    rc = load().orc_neighbour_pairs(traj.ptr, C.byref(rq), out.ctypes.data_as(C.POINTER(capi.pa_neigh_pair)), capacity, C.byref(count))
+    assert rc == 0 and count.value <= capacity, (rc, count.value)
+    return out[:count.value]
 
 
 def format_real4(x) -> str:

@@ -698,6 +698,31 @@ int orc_contact_distance(const pa_traj *t, int timestep, int type, int nthreads,
     return 0;
 }
 
+/* Neighbour test of the cluster / speciation analyses (Cluster:1092-1100, Speciation:1407-1431): literal double
+ * loop over two lists of atom instances, REAL(4) give_smallest_atom_distance_squared < REAL(4) squared cutoff.
+ * Pairs come out in loop order (ia outer, ib inner). */
+int orc_neighbour_pairs(const pa_traj *t, const pa_neigh_request *rq, pa_neigh_pair *out, int64_t capacity, int64_t *count)
+{
+    if (rq->timestep < 1 || rq->timestep > t->nsteps) return PA_ERR_BAD_ARG;
+    const int step = rq->timestep - 1;
+    int64_t n = 0;
+    for (int ia = 0; ia < rq->n_a; ++ia) {
+        const int ty1 = rq->a[3 * ia] - 1, m1 = rq->a[3 * ia + 1] - 1, a1 = rq->a[3 * ia + 2] - 1;
+        const int row = (rq->a_class ? rq->a_class[ia] : 0) * rq->n_class_b;
+        for (int ib = rq->same_list ? ia + 1 : 0; ib < rq->n_b; ++ib) {
+            const int ty2 = rq->b[3 * ib] - 1, m2 = rq->b[3 * ib + 1] - 1, a2 = rq->b[3 * ib + 2] - 1;
+            if (rq->skip_same_molecule && ty1 == ty2 && m1 == m2) continue;
+            const float cut = rq->cutoff_sq[row + (rq->b_class ? rq->b_class[ib] : 0)];
+            if (orc_atom_d2(t, step, ty1, m1, a1, ty2, m2, a2) < cut) {
+                if (n < capacity) { out[n].ia = ia; out[n].ib = ib; }
+                ++n;
+            }
+        }
+    }
+    *count = n;
+    return 0;
+}
+
 static void orc_distance_pass(const pa_traj *t, const pa_dist_job *job, int stdev_run, pa_dist_result *res)
 {
     const float maxdist_squared = job->maxdist * job->maxdist;

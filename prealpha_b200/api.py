@@ -106,6 +106,19 @@ def contact_distance(traj, timestep, type_, exec_=None):
             np.float32(res.smallest_intermolecular)), int(res.pairs_evaluated)
 
 
+def neighbour_pairs(traj, rq, capacity=1 << 20, exec_=None):
+    """pa_neighbour_pairs: int32 array [count][2] of (ia, ib), sorted in the reference's loop order, and the number of tests."""
+    ex = exec_ if exec_ is not None else make_exec()
+    while True:
+        out = np.zeros((max(capacity, 1), 2), dtype=np.int32)
+        count, tests = C.c_int64(0), C.c_int64(0)
+        capi.check(capi.load().pa_neighbour_pairs(traj.ptr, C.byref(rq), C.byref(ex), out.ctypes.data_as(C.POINTER(capi.pa_neigh_pair)),
+                                                  capacity, C.byref(count), C.byref(tests)), "pa_neighbour_pairs")
+        if count.value <= capacity:
+            return out[:count.value], tests.value
+        capacity = int(count.value)
+
+
 def format_real4(x) -> str:
     buf = C.create_string_buffer(64)
     capi.load().pa_format_real4(float(np.float32(x)), buf)

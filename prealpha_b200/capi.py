@@ -119,6 +119,41 @@ class pa_contact_result(C.Structure):
     ]
 
 
+class pa_neigh_request(C.Structure):
+    _fields_ = [
+        ("timestep", C.c_int32), ("n_a", C.c_int32), ("n_b", C.c_int32),
+        ("a", C.POINTER(C.c_int32)), ("b", C.POINTER(C.c_int32)),
+        ("a_class", C.POINTER(C.c_int32)), ("b_class", C.POINTER(C.c_int32)),
+        ("n_class_a", C.c_int32), ("n_class_b", C.c_int32),
+        ("cutoff_sq", C.POINTER(C.c_float)),
+        ("same_list", C.c_int32), ("skip_same_molecule", C.c_int32),
+    ]
+
+
+class pa_neigh_pair(C.Structure):
+    _fields_ = [("ia", C.c_int32), ("ib", C.c_int32)]
+
+
+def make_neigh_request(timestep, a, b, cutoff_sq, a_class=None, b_class=None, same_list=False, skip_same_molecule=False):
+    """a, b: int arrays [n][3] of (molecule type, molecule index, atom index), 1-based; cutoff_sq: float32 scalar or matrix.
+    Returns (request, keepalive)."""
+    a = np.ascontiguousarray(a, dtype=np.int32).reshape(-1, 3)
+    b = a if same_list else np.ascontiguousarray(b, dtype=np.int32).reshape(-1, 3)
+    cut = np.ascontiguousarray(np.atleast_2d(np.asarray(cutoff_sq, dtype=np.float32)))
+    keep = [a, b, cut]
+    rq = pa_neigh_request()
+    rq.timestep, rq.n_a, rq.n_b = int(timestep), a.shape[0], b.shape[0]
+    rq.a = a.ctypes.data_as(C.POINTER(C.c_int32)); rq.b = b.ctypes.data_as(C.POINTER(C.c_int32))
+    for name, arr in (("a_class", a_class), ("b_class", b_class)):
+        if arr is not None:
+            arr = np.ascontiguousarray(arr, dtype=np.int32); keep.append(arr)
+            setattr(rq, name, arr.ctypes.data_as(C.POINTER(C.c_int32)))
+    rq.n_class_a, rq.n_class_b = cut.shape
+    rq.cutoff_sq = cut.ctypes.data_as(C.POINTER(C.c_float))
+    rq.same_list, rq.skip_same_molecule = int(bool(same_list)), int(bool(skip_same_molecule))
+    return rq, keep
+
+
 # symbol -> (restype, argtypes); every entry of include/prealpha_b200.h
 _I64P = C.POINTER(C.c_int64)
 SIGNATURES = {
@@ -146,6 +181,8 @@ SIGNATURES = {
     "pa_format_real4": (C.c_int, [C.c_float, C.c_char_p]),
     "pa_distance_subjobs": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_dist_job), C.POINTER(pa_exec), C.POINTER(pa_dist_result)]),
     "pa_contact_distance": (C.c_int, [C.POINTER(pa_traj), C.c_int32, C.c_int32, C.POINTER(pa_exec), C.POINTER(pa_contact_result)]),
+    "pa_neighbour_pairs": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_neigh_request), C.POINTER(pa_exec), C.POINTER(pa_neigh_pair),
+                                     C.c_int64, _I64P, _I64P]),
     "pa_run_general_input": (C.c_int, [C.c_char_p, C.POINTER(pa_exec)]),
 }
 

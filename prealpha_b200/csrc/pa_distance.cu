@@ -15,6 +15,7 @@
 #include <cmath>
 #include <vector>
 #include <string>
+#include <algorithm>
 #include "pa_internal.h"
 
 namespace {
@@ -505,5 +506,201 @@ extern "C" int pa_contact_distance(const pa_traj *traj, int32_t timestep, int32_
     }
 done:
     cudaFree(d_pos); cudaFree(d_raw); cudaFree(d_out);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------
+// neighbour pairs: the REAL(4) test give_smallest_atom_distance_squared(...) < cutoff**2 of the
+// cluster / speciation analyses (Cluster:1094-1100, Speciation:1407-1431) for every pair of two atom lists.
+// Brute force like the reference (every a-instance against every b-instance, observed atoms staged as
+// (x-L, x, x+L) triples); qualifying pairs are appended with one atomic per warp and sorted on the host into
+// the order of the reference's nested loops.
+namespace {
+
+struct PnArgs {
+    const double *x, *y, *z;            // wrapped positions of all atoms of the frame
+    const int *ia_atom, *ib_atom;       // global atom index of every instance
+    const int *ia_mol, *ib_mol;         // global molecule id of every instance (skip_same_molecule)
+    const int *a_class, *b_class;       // may be null
+    const float *cutoff_sq;
+    int n_a, n_b, n_class_b;
+    int same_list, skip_same_molecule;
+    int jsplit;
+    double L[3], mds;
+    int2 *out;
+    unsigned long long capacity;
+    unsigned long long *count;
+};
+
+__global__ void __launch_bounds__(PC_THREADS) pa_neighbour_kernel(PnArgs a)
+{
+    __shared__ double sj[9][PC_CHUNK];
+    __shared__ int s_mol[PC_CHUNK], s_cls[PC_CHUNK];
+    const int ia = blockIdx.x * PC_THREADS + threadIdx.x;
+    const bool live = ia < a.n_a;
+    double xi = 0.0, yi = 0.0, zi = 0.0;
+    int moli = -1, rowi = 0;
+    if (live) {
+        const int at = a.ia_atom[ia];
+        xi = a.x[at]; yi = a.y[at]; zi = a.z[at];
+        moli = a.ia_mol[ia];
+        rowi = (a.a_class ? a.a_class[ia] : 0) * a.n_class_b;
+    }
+    const int lane = threadIdx.x & 31;
+    const int j_begin = blockIdx.y * a.jsplit, j_end = min(a.n_b, j_begin + a.jsplit);
+    for (int j0 = j_begin; j0 < j_end; j0 += PC_CHUNK) {
+        __syncthreads();
+        {
+            const int j = j0 + threadIdx.x;
+            double px = 1e300, py = 1e300, pz = 1e300;
+            int mol = -2, cls = 0;
+            if (j < j_end) {
+                const int at = a.ib_atom[j];
+                px = a.x[at]; py = a.y[at]; pz = a.z[at];
+                mol = a.ib_mol[j]; cls = a.b_class ? a.b_class[j] : 0;
+            }
+            sj[0][threadIdx.x] = __dadd_rn(px, -a.L[0]); sj[1][threadIdx.x] = px; sj[2][threadIdx.x] = __dadd_rn(px, a.L[0]);
+            sj[3][threadIdx.x] = __dadd_rn(py, -a.L[1]); sj[4][threadIdx.x] = py; sj[5][threadIdx.x] = __dadd_rn(py, a.L[1]);
+            sj[6][threadIdx.x] = __dadd_rn(pz, -a.L[2]); sj[7][threadIdx.x] = pz; sj[8][threadIdx.x] = __dadd_rn(pz, a.L[2]);
+            s_mol[threadIdx.x] = mol; s_cls[threadIdx.x] = cls;
+        }
+        __syncthreads();
+        const int nj = min(PC_CHUNK, j_end - j0);
+        for (int jj = 0; jj < nj; ++jj) {
+            const int j = j0 + jj;
+            bool hit = false;
+            if (live && !(a.same_list && j <= ia) && !(a.skip_same_molecule && s_mol[jj] == moli)) {
+                const double s = __dadd_rn(__dadd_rn(pc_component(sj[0][jj], sj[1][jj], sj[2][jj], xi),
+                                                     pc_component(sj[3][jj], sj[4][jj], sj[5][jj], yi)),
+                                           pc_component(sj[6][jj], sj[7][jj], sj[8][jj], zi));
+                // REAL(4) function result (Molecular:1400,1418) against the REAL(4) squared cutoff
+                hit = __double2float_rn(s < a.mds ? s : a.mds) < a.cutoff_sq[rowi + s_cls[jj]];
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, hit);
+            if (m == 0u) continue;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.count, (unsigned long long)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (hit) {
+                const unsigned long long slot = base + __popc(m & ((1u << lane) - 1u));
+                if (slot < a.capacity) a.out[slot] = make_int2(ia, j);
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *rq, const pa_exec *exec,
+                                  pa_neigh_pair *out, int64_t capacity, int64_t *count, int64_t *tests)
+{
+    if (!traj || !rq || !count || capacity < 0 || (capacity > 0 && !out) || rq->n_a < 0 || rq->n_b < 0 || !rq->cutoff_sq ||
+        rq->n_class_a < 1 || rq->n_class_b < 1 || (rq->n_a > 0 && !rq->a) || (rq->n_b > 0 && !rq->b)) {
+        pa::set_error("bad argument"); return PA_ERR_BAD_ARG;
+    }
+    if (rq->timestep < 1 || rq->timestep > traj->nsteps) { pa::set_error("time step out of range (error 57)"); return PA_ERR_BAD_ARG; }
+    const int nt = traj->ntypes;
+    std::vector<int> first(nt + 1, 0), first_mol(nt + 1, 0);
+    for (int t = 0; t < nt; ++t) {
+        const long long n = (long long)traj->types[t].nmol * traj->types[t].natoms;
+        if (first[t] + n > 0x7fffffffll) { pa::set_error("too many atoms"); return PA_ERR_BAD_ARG; }
+        first[t + 1] = first[t] + (int)n;
+        first_mol[t + 1] = first_mol[t] + traj->types[t].nmol;
+    }
+    // instance lists -> global atom / molecule indices (host; validates the triples: errors 110 / 111 / 33)
+    std::vector<int> h_at[2], h_mol[2];
+    for (int side = 0; side < 2; ++side) {
+        const int n = side ? rq->n_b : rq->n_a;
+        const int32_t *lst = side ? rq->b : rq->a;
+        const int32_t *cls = side ? rq->b_class : rq->a_class;
+        h_at[side].resize(n); h_mol[side].resize(n);
+        for (int i = 0; i < n; ++i) {
+            const int ty = lst[3 * i], mol = lst[3 * i + 1], at = lst[3 * i + 2];
+            if (ty < 1 || ty > nt) { pa::set_error("invalid molecule type in atom list (error 33)"); return PA_E_TYPE_INVALID; }
+            if (mol < 1 || mol > traj->types[ty - 1].nmol) { pa::set_error("invalid molecule index in atom list (error 110)"); return 110; }
+            if (at < 1 || at > traj->types[ty - 1].natoms) { pa::set_error("invalid atom index in atom list (error 111)"); return 111; }
+            if (cls && (cls[i] < 0 || cls[i] >= (side ? rq->n_class_b : rq->n_class_a))) { pa::set_error("cutoff class out of range"); return PA_ERR_BAD_ARG; }
+            h_at[side][i] = first[ty - 1] + (mol - 1) * traj->types[ty - 1].natoms + (at - 1);
+            h_mol[side][i] = first_mol[ty - 1] + (mol - 1);
+        }
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); pa::set_error("no CUDA device (this path has no CPU fallback)"); return PA_ERR_NO_DEVICE; }
+    const int device = exec ? exec->device : 0;
+    if (cudaSetDevice(device) != cudaSuccess || pa_kernels_selfcheck() != 0) { cudaGetLastError(); pa::set_error("no sm_100a kernel image for this device"); return PA_ERR_NO_DEVICE; }
+    *count = 0;
+    if (tests) *tests = 0;
+    if (rq->n_a == 0 || rq->n_b == 0) return 0;
+    int rc = 0;
+    const int n_all = first[nt];
+    double *d_pos = nullptr;
+    float *d_raw = nullptr, *d_cut = nullptr;
+    int *d_idx = nullptr;
+    int2 *d_out = nullptr;
+    unsigned long long *d_count = nullptr, h_count = 0;
+    {
+        size_t max_raw = 1;
+        for (int t = 0; t < nt; ++t) max_raw = std::max(max_raw, (size_t)(first[t + 1] - first[t]) * 3);
+        PD_CK(cudaMalloc(&d_pos, sizeof(double) * 3 * (size_t)std::max(n_all, 1)));
+        PD_CK(cudaMalloc(&d_raw, sizeof(float) * max_raw));
+        double *x = d_pos, *y = d_pos + n_all, *z = d_pos + 2 * (size_t)n_all;
+        const double3 lo = make_double3(traj->box_lo[0], traj->box_lo[1], traj->box_lo[2]);
+        const double3 hi = make_double3(traj->box_hi[0], traj->box_hi[1], traj->box_hi[2]);
+        const double3 L = make_double3(traj->box_hi[0] - traj->box_lo[0], traj->box_hi[1] - traj->box_lo[1], traj->box_hi[2] - traj->box_lo[2]);
+        for (int t = 0; t < nt; ++t) {
+            const int n = first[t + 1] - first[t];
+            if (n < 1) continue;
+            if (!traj->types[t].xyz) { pa::set_error("coordinates missing"); rc = PA_ERR_BAD_ARG; goto done; }
+            PD_CK(cudaMemcpy(d_raw, traj->types[t].xyz + (size_t)(rq->timestep - 1) * n * 3, sizeof(float) * (size_t)n * 3, cudaMemcpyHostToDevice));
+            pa_contact_wrap_kernel<<<(n + 255) / 256, 256>>>(d_raw, n, first[t], lo, hi, L, x, y, z);
+            PD_CK(cudaGetLastError());
+        }
+        // index block: [a atoms][a mols][a classes][b atoms][b mols][b classes]
+        const size_t na = (size_t)rq->n_a, nb = (size_t)rq->n_b;
+        PD_CK(cudaMalloc(&d_idx, sizeof(int) * 3 * (na + nb)));
+        PD_CK(cudaMemcpy(d_idx, h_at[0].data(), sizeof(int) * na, cudaMemcpyHostToDevice));
+        PD_CK(cudaMemcpy(d_idx + na, h_mol[0].data(), sizeof(int) * na, cudaMemcpyHostToDevice));
+        if (rq->a_class) PD_CK(cudaMemcpy(d_idx + 2 * na, rq->a_class, sizeof(int) * na, cudaMemcpyHostToDevice));
+        PD_CK(cudaMemcpy(d_idx + 3 * na, h_at[1].data(), sizeof(int) * nb, cudaMemcpyHostToDevice));
+        PD_CK(cudaMemcpy(d_idx + 3 * na + nb, h_mol[1].data(), sizeof(int) * nb, cudaMemcpyHostToDevice));
+        if (rq->b_class) PD_CK(cudaMemcpy(d_idx + 3 * na + 2 * nb, rq->b_class, sizeof(int) * nb, cudaMemcpyHostToDevice));
+        const size_t ncut = (size_t)rq->n_class_a * rq->n_class_b;
+        PD_CK(cudaMalloc(&d_cut, sizeof(float) * ncut));
+        PD_CK(cudaMemcpy(d_cut, rq->cutoff_sq, sizeof(float) * ncut, cudaMemcpyHostToDevice));
+        PD_CK(cudaMalloc(&d_out, sizeof(int2) * (size_t)std::max<int64_t>(capacity, 1)));
+        PD_CK(cudaMalloc(&d_count, sizeof(unsigned long long)));
+        PD_CK(cudaMemset(d_count, 0, sizeof(unsigned long long)));
+        PnArgs a{};
+        a.x = x; a.y = y; a.z = z;
+        a.ia_atom = d_idx; a.ia_mol = d_idx + na; a.a_class = rq->a_class ? d_idx + 2 * na : nullptr;
+        a.ib_atom = d_idx + 3 * na; a.ib_mol = d_idx + 3 * na + nb; a.b_class = rq->b_class ? d_idx + 3 * na + 2 * nb : nullptr;
+        a.cutoff_sq = d_cut; a.n_a = rq->n_a; a.n_b = rq->n_b; a.n_class_b = rq->n_class_b;
+        a.same_list = rq->same_list ? 1 : 0; a.skip_same_molecule = rq->skip_same_molecule ? 1 : 0;
+        a.L[0] = L.x; a.L[1] = L.y; a.L[2] = L.z; a.mds = traj->max_dist_sq;
+        a.out = d_out; a.capacity = (unsigned long long)capacity; a.count = d_count;
+        const int bx = (rq->n_a + PC_THREADS - 1) / PC_THREADS;
+        int splits = std::max(1, (148 * 8 + bx - 1) / bx);
+        splits = std::min(std::min(splits, std::max(1, (rq->n_b + PC_CHUNK - 1) / PC_CHUNK)), 65535);
+        a.jsplit = (((rq->n_b + splits - 1) / splits + PC_CHUNK - 1) / PC_CHUNK) * PC_CHUNK;
+        splits = (rq->n_b + a.jsplit - 1) / a.jsplit;
+        pa_neighbour_kernel<<<dim3(bx, splits), PC_THREADS>>>(a);
+        PD_CK(cudaGetLastError());
+        PD_CK(cudaMemcpy(&h_count, d_count, sizeof h_count, cudaMemcpyDeviceToHost));
+        *count = (int64_t)h_count;
+        const size_t ncopy = (size_t)std::min<unsigned long long>(h_count, (unsigned long long)capacity);
+        if (ncopy > 0) {
+            static_assert(sizeof(pa_neigh_pair) == sizeof(int2), "layout");
+            PD_CK(cudaMemcpy(out, d_out, sizeof(int2) * ncopy, cudaMemcpyDeviceToHost));
+            if (h_count <= (unsigned long long)capacity)       // complete list: the order of the reference's nested loops
+                std::sort(out, out + ncopy, [](const pa_neigh_pair &p, const pa_neigh_pair &q) { return p.ia != q.ia ? p.ia < q.ia : p.ib < q.ib; });
+        }
+        if (tests) {
+            long long t = (long long)rq->n_a * rq->n_b;
+            if (rq->same_list) t = (long long)rq->n_a * (rq->n_a - 1) / 2;
+            *tests = t;                                         // upper bound when skip_same_molecule removes pairs
+        }
+    }
+done:
+    cudaFree(d_pos); cudaFree(d_raw); cudaFree(d_cut); cudaFree(d_idx); cudaFree(d_out); cudaFree(d_count);
     return rc;
 }

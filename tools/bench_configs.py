@@ -63,11 +63,33 @@ def c5(natoms=4_000_000, maxdist=40.0):
     run(f"C5_4M_atoms_2D_maxdist{int(maxdist)}", traj, jobs, "1 frame, reference type 1 around all, 200x90 distance-angle bins")
 
 
+def neigh(natoms=100_000, cutoff=3.0):
+    """8f-4 primitive: all-atom neighbour pairs below `cutoff` in a 100k-atom box (what one frame of a GLOBAL cluster
+    analysis tests, Cluster:1092-1100), host lists in, sorted pair list out."""
+    rng = np.random.default_rng(3)
+    L = round((natoms / 0.05) ** (1 / 3), 4)
+    lo, hi = capi.cubic_box_edge(0.0, L)
+    half = natoms // 2
+    tl = [dict(charge=+1, natoms=1, nmol=half, elements=["Na"], xyz=np.round(rng.random((1, half, 1, 3)) * L, 5).astype(np.float32)),
+          dict(charge=-1, natoms=1, nmol=half, elements=["Cl"], xyz=np.round(rng.random((1, half, 1, 3)) * L, 5).astype(np.float32))]
+    traj = capi.Trajectory(tl, lo, hi)
+    inst = np.array([(t, m, 1) for t in (1, 2) for m in range(1, half + 1)], dtype=np.int32)
+    rq, keep = capi.make_neigh_request(1, a=inst, b=None, cutoff_sq=np.float32(cutoff) ** 2, same_list=True)
+    api.neighbour_pairs(traj, rq, capacity=1 << 22)                      # warm-up
+    t0 = time.perf_counter()
+    pairs, tests = api.neighbour_pairs(traj, rq, capacity=1 << 22)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"config": "neighbour_pairs_100k_atoms", "note": f"all-atom list against itself, cutoff {cutoff} A, sorted pair list on the host",
+                      "seconds_e2e": dt, "distance_tests": int(tests), "tests_per_s_e2e": tests / dt, "pairs_found": int(len(pairs))}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c3", "c5"]
     if "c3" in which:
         c3()
     if "c5" in which:
         c5()
+    if "neigh" in which:
+        neigh()
     if "c5big" in which:
         c5(maxdist=140.0)
