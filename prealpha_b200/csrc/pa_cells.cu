@@ -11,7 +11,10 @@
 //     (by a margin far above rounding) -> the pair costs 1 DSUB + 1 DMUL for that component;
 //   * "double": two shifts are possible (boxes straddle L/2) -> 2 DSUB, min of |d|, 1 DMUL;
 //   * cell runs whose closest possible distance is beyond the cutoff are skipped.
-// Nothing about the arithmetic changes: a pair evaluates exactly the candidates
+// Most runs are then classified in packed float32 from tile-local coordinates (pc_segment_f32: rigorous
+// +-6e-7 class brackets, exact fp64 decision for the pairs the brackets leave open), which removes the
+// FP64 pipe from the inner loop without changing a count.
+// Nothing about the fp64 arithmetic changes: a pair evaluates exactly the candidates
 // fl(fl(p2+s)-p1) that can be the minimum of the reference's 27-image loop (Molecular:1451-1467),
 // so the fp64 result is bit-identical; skipped pairs are pairs the reference evaluates and then
 // discards at `IF (current_distance_squared<maxdist_squared)` (Distribution:783).
@@ -219,7 +222,6 @@ struct PcTables {
     int na;
     unsigned long long cut;
     // float32 segments (see pc_segment_f32)
-    float f_lo, f_hi;       // (1/step_a)(1 -+ 6e-7), rounded outwards
     float pad_x;            // local x of padded observed molecules: beyond the cutoff for every tile molecule
     unsigned int cnt_pad;   // byte offset of the counter window used by padded reference slots
 };
@@ -701,7 +703,6 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
         T.s_lo = T.s_hi = p.job.guess_scale * (1.0f - 9.5367431640625e-07f);             // floor(x~) <= true class
     }
     T.r_max = ((float)na + 1.5f) / p.job.guess_scale;
-    T.f_lo = p.f32_lo; T.f_hi = p.f32_hi;
     const float t2max = 32.0f;                                                            // largest |T| a float32 tile may have
     T.pad_x = p.job.maxdist * 1.001f + 3.0f * t2max;
     T.cnt_pad = (unsigned)(na + 8) * 4u;
