@@ -902,6 +902,7 @@ template <int MODE, bool SMEM_HIST>
 static __device__ __noinline__ void pg_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                              const unsigned int *queue, int count, const double *s_j, const int *s_jo,
                                              long long jbase, int jc, unsigned int *s_hist, int nbins,
+                                             const unsigned long long *thr_a, const double *thr_b,
                                              unsigned long long &g_within, unsigned long long &g_oob)
 {
     __syncwarp();
@@ -919,7 +920,7 @@ static __device__ __noinline__ void pg_drain(const PaPass &p, const PaCellGrid &
             const double *rec = s_j + jl * 6;
             const double link[3] = { __dsub_rn(rec[0], gi.sx[iref]), __dsub_rn(rec[2], gi.sy[iref]), __dsub_rn(rec[4], gi.sz[iref]) };
             const double m = __dadd_rn(__dadd_rn(__dmul_rn(link[0], link[0]), __dmul_rn(link[1], link[1])), __dmul_rn(link[2], link[2]));
-            if (m < p.box.max_dist_sq) { st = pa_bin_from_link(p, m, link, &bin); fast = true; }
+            if (m < p.box.max_dist_sq) { st = pa_bin_from_link(p, m, link, &bin, thr_a, thr_b); fast = true; }
         }
         if (!fast) st = pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
         if (SMEM_HIST) {
@@ -939,13 +940,22 @@ static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellG
                                                   const int (&iorig)[PC_RI], long long jbase, int jb, int je,
                                                   double sxa, double sxb, double sya, double syb, double sza, double szb,
                                                   double *s_j, int *s_jo, unsigned int *s_hist, int nbins, unsigned int *queue,
+                                                  const unsigned long long *thr_a, const double *thr_b, int &parity,
                                                   unsigned long long &g_within, unsigned long long &g_oob)
 {
+    // The staging area is double buffered (s_j0 / s_jo0 hold two chunks): chunk g goes to buffer g & 1 and there is ONE
+    // barrier per chunk, after the staging.  A warp restages a buffer only after the barrier of the chunk in between,
+    // which every warp passes only after it has finished (evaluated and drained) the chunk that used the buffer before;
+    // so warps may be one chunk apart and a long drain in one warp no longer stalls the other three.
+    double *const s_j0 = s_j;
+    int *const s_jo0 = s_jo;
     const unsigned long long cut = p.job.cut_bits;
     const unsigned int lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     int qn = 0;                                          // entries in this warp's queue (warp-uniform)
     for (int jc = jb; jc < je; jc += PC_JC) {
-        __syncthreads();
+        s_j = s_j0 + (parity & 1) * (PC_JC * 6);
+        s_jo = s_jo0 + (parity & 1) * PC_JC;
+        ++parity;
         {
             const int t = threadIdx.x;
             const int j = jc + t;
@@ -975,12 +985,12 @@ static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellG
                 const unsigned int m = __ballot_sync(0xffffffffu, need);
                 if (m == 0u) continue;
                 const int add = __popc(m);
-                if (qn + add > PG_QCAP) { pg_drain<MODE, SMEM_HIST>(p, go, gi, tl, queue, qn, s_j, s_jo, jbase, jc, s_hist, nbins, g_within, g_oob); qn = 0; }
+                if (qn + add > PG_QCAP) { pg_drain<MODE, SMEM_HIST>(p, go, gi, tl, queue, qn, s_j, s_jo, jbase, jc, s_hist, nbins, thr_a, thr_b, g_within, g_oob); qn = 0; }
                 if (need) queue[qn + __popc(m & lane_lt)] = ((unsigned int)jj << 16) | (unsigned int)(r * PC_THREADS + threadIdx.x);
                 qn += add;
             }
         }
-        if (qn > 0) { pg_drain<MODE, SMEM_HIST>(p, go, gi, tl, queue, qn, s_j, s_jo, jbase, jc, s_hist, nbins, g_within, g_oob); qn = 0; }   // before the chunk is overwritten
+        if (qn > 0) { pg_drain<MODE, SMEM_HIST>(p, go, gi, tl, queue, qn, s_j, s_jo, jbase, jc, s_hist, nbins, thr_a, thr_b, g_within, g_oob); qn = 0; }   // before the chunk is overwritten
     }
 }
 
@@ -1006,11 +1016,21 @@ __global__ void __launch_bounds__(PC_THREADS, 5) pa_general_cells_kernel(const _
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbins = p.job.bin_a * p.job.bin_b;
-    double *s_j = reinterpret_cast<double *>(smem_raw);                         // PC_JC*6 doubles
-    int *s_jo = reinterpret_cast<int *>(s_j + PC_JC * 6);                       // PC_JC original indices
-    PcShared *sh = reinterpret_cast<PcShared *>(s_jo + PC_JC);
+    double *s_j = reinterpret_cast<double *>(smem_raw);                         // 2 x PC_JC*6 doubles (double buffered)
+    int *s_jo = reinterpret_cast<int *>(s_j + 2 * PC_JC * 6);                   // 2 x PC_JC original indices
+    PcShared *sh = reinterpret_cast<PcShared *>(s_jo + 2 * PC_JC);
+    int parity = 0;
     unsigned int *queue = reinterpret_cast<unsigned int *>(sh + 1) + (threadIdx.x >> 5) * PG_QCAP;   // per warp
-    unsigned int *s_hist = reinterpret_cast<unsigned int *>(sh + 1) + (PC_THREADS / 32) * PG_QCAP;   // nbins+1 (SMEM_HIST)
+    // class tables of the job in shared memory (pdf: thr_a[bin_a+3], thr_b[bin_b+1]; <= 16 KB), searched by every drained pair
+    unsigned long long *s_thr_a = reinterpret_cast<unsigned long long *>(
+        (reinterpret_cast<uintptr_t>(reinterpret_cast<unsigned int *>(sh + 1) + (PC_THREADS / 32) * PG_QCAP) + 7) & ~uintptr_t(7));
+    const int n_thr_a = p.job.mode == PA_MODE_PDF ? p.job.bin_a + 3 : 0, n_thr_b = p.job.mode == PA_MODE_PDF ? p.job.bin_b + 1 : 0;
+    double *s_thr_b = reinterpret_cast<double *>(s_thr_a + n_thr_a);
+    for (int k = threadIdx.x; k < n_thr_a; k += blockDim.x) s_thr_a[k] = p.job.thr_a[k];
+    for (int k = threadIdx.x; k < n_thr_b; k += blockDim.x) s_thr_b[k] = p.job.thr_b[k];
+    const unsigned long long *thr_a = n_thr_a ? s_thr_a : p.job.thr_a;
+    const double *thr_b = n_thr_b ? s_thr_b : p.job.thr_b;
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(s_thr_b + n_thr_b);   // nbins+1 (SMEM_HIST)
     if (SMEM_HIST) for (int k = threadIdx.x; k < nbins + 1; k += blockDim.x) s_hist[k] = 0u;
     __syncthreads();
     const double cut_d2 = __longlong_as_double((long long)p.job.cut_bits) * (1.0 + 1e-12);
@@ -1095,9 +1115,9 @@ __global__ void __launch_bounds__(PC_THREADS, 5) pa_general_cells_kernel(const _
                     const double sya = (double)(ly.ca - 1) * Ly, syb = (double)(ly.cb - 1) * Ly;
                     const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
                     if (lx.mode < 2 && ly.mode < 2 && lz.mode < 2)
-                        pg_segment<1, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, queue, g_within, g_oob);
+                        pg_segment<1, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, queue, thr_a, thr_b, parity, g_within, g_oob);
                     else
-                        pg_segment<2, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, queue, g_within, g_oob);
+                        pg_segment<2, SMEM_HIST>(p, go, gi, tl, p1x, p1y, p1z, iorig, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, s_j, s_jo, s_hist, nbins, queue, thr_a, thr_b, parity, g_within, g_oob);
                 }
             }
         }
@@ -1196,8 +1216,9 @@ int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellG
     // a shared-memory histogram only while it leaves room for >= 6 CTAs per SM (occupancy matters more to this
     // latency-bound kernel than the atomics: larger histograms take 64-bit atomics in L2)
     const bool smem_hist = nbins <= 6000;
-    const size_t smem = (size_t)PC_JC * 6 * 8 + (size_t)PC_JC * 4 + sizeof(PcShared) + (size_t)(PC_THREADS / 32) * PG_QCAP * 4 +
-                        (smem_hist ? (size_t)(nbins + 1) * 4 : 0) + 16;
+    const size_t smem = 2 * ((size_t)PC_JC * 6 * 8 + (size_t)PC_JC * 4) + sizeof(PcShared) + (size_t)(PC_THREADS / 32) * PG_QCAP * 4 +
+                        (p.job.mode == PA_MODE_PDF ? (size_t)(p.job.bin_a + 3 + p.job.bin_b + 1) * 8 : 0) +
+                        (smem_hist ? (size_t)(nbins + 1) * 4 : 0) + 24;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
 #define PG_LAUNCH(S_)                                                                                           \
     do {                                                                                                        \

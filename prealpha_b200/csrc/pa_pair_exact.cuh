@@ -21,7 +21,9 @@ static __device__ __forceinline__ int pa_plus1_wrap(int v) { return (int)((unsig
 // Distribution:796-827).  Shared by the literal evaluation below and by the in-register path of the
 // cell-sorted general kernel, so both produce the same bits by construction.
 // returns 1 = binned (index in *bin), 2 = out of bounds.
-static __device__ __forceinline__ int pa_bin_from_link(const PaPass &p, double m, const double (&link)[3], int *bin)
+// thr_a / thr_b: the job's class tables (global memory) or a copy of them in shared memory.
+static __device__ __forceinline__ int pa_bin_from_link(const PaPass &p, double m, const double (&link)[3], int *bin,
+                                                       const unsigned long long *thr_a, const double *thr_b)
 {
     const int na = p.job.bin_a, nb = p.job.bin_b;
     int ia, ib;
@@ -37,10 +39,12 @@ static __device__ __forceinline__ int pa_bin_from_link(const PaPass &p, double m
         ib = pa_plus1_wrap(pa_int_of_float_x86(__fdiv_rn(bs, p.job.step_b)));
         if (ib == 1 && bs < 0.0f) ib = 0;
     } else {                                                 // Distribution:812-827
-        // a-class from the threshold table (binary search: no assumption on the seed)
+        // a-class = largest k with thr_a[k] <= m (as bit patterns): a float32 estimate of SQRT(m)/step_a seeds the
+        // search, the monotone table decides (the result does not depend on the seed)
         const unsigned long long db = pa_dbits(m);
-        int lo = 0, hi = na + 1;                             // class in [lo, hi]
-        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (p.job.thr_a[mid] <= db) lo = mid; else hi = mid - 1; }
+        int lo = min(max((int)(__fsqrt_rn(__double2float_rn(m)) * p.job.guess_scale), 0), na + 1);
+        while (lo < na + 1 && thr_a[lo + 1] <= db) ++lo;
+        while (lo > 0 && thr_a[lo] > db) --lo;
         ia = lo + 1;                                         // class na -> binpos_a = na+1 (out of bounds)
         const double len = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(link[0], link[0]), __dmul_rn(link[1], link[1])), __dmul_rn(link[2], link[2])));
         const double lx = __ddiv_rn(link[0], len), ly = __ddiv_rn(link[1], len), lz = __ddiv_rn(link[2], len);
@@ -49,8 +53,10 @@ static __device__ __forceinline__ int pa_bin_from_link(const PaPass &p, double m
         if (!(dot >= -1.0 && dot <= 1.0)) ib = -1;           // ACOS -> NaN -> INT() = INT_MIN -> binpos_b < 1
         else {
             // thr_b[k] (k=1..nb) = largest dot with INT(REAL4(ACOS(dot))/step_b) >= k, decreasing in k
-            int l2 = 0, h2 = nb;
-            while (l2 < h2) { const int mid = (l2 + h2 + 1) >> 1; if (dot <= p.job.thr_b[mid]) l2 = mid; else h2 = mid - 1; }
+            // largest k with dot <= thr_b[k], seeded by a float32 acos (again: the table decides)
+            int l2 = min(max((int)(acosf(__double2float_rn(dot)) / p.job.step_b), 0), nb);
+            while (l2 < nb && dot <= thr_b[l2 + 1]) ++l2;
+            while (l2 > 0 && !(dot <= thr_b[l2])) --l2;
             ib = l2 + 1;
         }
     }
@@ -113,7 +119,7 @@ static __device__ __noinline__ int pa_eval_pair_exact(const PaPass &p, long long
             link[c] = __dsub_rn(__dadd_rn(tr, c2[c]), c1[c]);                             // Distribution:786-792
         }
     }
-    return pa_bin_from_link(p, m, link, bin);
+    return pa_bin_from_link(p, m, link, bin, p.job.thr_a, p.job.thr_b);
 }
 
 
