@@ -916,7 +916,7 @@ static __device__ __noinline__ void pg_drain(const PaPass &p, const PaCellGrid &
         const int io = gi.sorig[iref], jo = s_jo[jl];
         int bin = 0, st;
         bool fast = false;
-        if (MODE == 1 && !p.job.use_coc && !p.box.wrap_trajectory && gi.sflag[iref] == 0 && go.sflag[jbase + jc + jl] == 0) {
+        if (MODE == 1 && !p.job.use_coc && gi.sflag[iref] == 0 && go.sflag[jbase + jc + jl] == 0) {
             const double *rec = s_j + jl * 6;
             const double link[3] = { __dsub_rn(rec[0], gi.sx[iref]), __dsub_rn(rec[2], gi.sy[iref]), __dsub_rn(rec[4], gi.sz[iref]) };
             const double m = __dadd_rn(__dadd_rn(__dmul_rn(link[0], link[0]), __dmul_rn(link[1], link[1])), __dmul_rn(link[2], link[2]));

@@ -331,7 +331,9 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     }
     // cell-sorted path: both partners of a pass need >= 12500 molecules (grid of >= 5^3 cells of ~100)
     s->grids.resize(traj->ntypes);
-    s->use_cells = !(ex.flags & PA_EXEC_NO_CELLS) && !traj->wrap_trajectory;
+    // (with wrap_trajectory the positions are used as they are: the grid then needs every centre of mass inside the box,
+    //  which pa_cell_count_kernel checks -- otherwise the sticky flag sends the call to the brute-force kernels)
+    s->use_cells = !(ex.flags & PA_EXEC_NO_CELLS);
     if (s->use_cells) {
         for (const JobState &js : s->jobs) {
             const int r = js.job.ref_type - 1;

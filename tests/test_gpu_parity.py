@@ -298,6 +298,33 @@ def test_wrap_trajectory_switch(oracle):
         assert np.array_equal(hists[k], h0) and (within[k], oob[k]) == (w0, o0)
 
 
+@pytest.mark.parametrize("outside", [False, True])
+def test_wrap_trajectory_with_cell_sorted_kernels(outside):
+    """wrap_trajectory T on a large system: the cell-sorted kernels apply as long as every centre of mass lies inside the
+    box (float32 and general kernels alike); with molecules outside the box the call must fall back to the brute-force
+    kernels by itself.  Both must equal the brute-force result (which the small-system test pins on the oracle)."""
+    rng = np.random.default_rng(41)
+    n1, n2, L = 14000, 13000, 81.0
+    pos = np.round(rng.random((1, n1 + n2, 3)) * L, 4)
+    if outside:
+        pos[0, 5] = (-0.5, 10.0, 10.0); pos[0, n1 + 7] = (40.0, L + 0.25, 3.0)
+    pos = pos.astype(np.float32)
+    tl = [dict(charge=+1, natoms=1, nmol=n1, elements=["Na"], xyz=pos[:, :n1].reshape(1, n1, 1, 3)),
+          dict(charge=-1, natoms=1, nmol=n2, elements=["Cl"], xyz=pos[:, n1:].reshape(1, n2, 1, 3))]
+    lo, hi = capi.cubic_box_edge(0.0, L)
+    traj = capi.Trajectory(tl, lo, hi, wrap_trajectory=True)
+    reqs = [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=800, bin_b=1, maxdist_optimize=True),
+            dict(mode="pdf", vec=(1, 0, 1), ref_type=2, obs_type=1, bin_a=30, bin_b=18, maxdist=9.5),
+            dict(mode="cdf", vec=(0, 0, 1), ref_type=1, obs_type=2, bin_a=25, bin_b=25, maxdist=8.0)]
+    pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
+    cells = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY))
+    brute = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY | capi.PA_EXEC_NO_CELLS))
+    for k in range(len(pjobs)):
+        assert np.array_equal(cells[0][k], brute[0][k]) and cells[1][k] == brute[1][k] and cells[2][k] == brute[2][k], k
+    if not outside:
+        assert cells[3].kernel_launches != brute[3].kernel_launches      # the cell path really ran
+
+
 @pytest.mark.parametrize("name", ["synth", "lmp", "lmp_wrap", "lmp_unwrap", "charge_arm"])
 def test_cli_drop_in_end_to_end(name, oracle, tmp_path):
     """general.inp -> molecular.inp -> xyz / lmp text -> GPU -> output files: byte-identical to what the
