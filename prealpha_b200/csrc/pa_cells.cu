@@ -12,7 +12,7 @@
 //   * "double": two shifts are possible (boxes straddle L/2) -> 2 DSUB, min of |d|, 1 DMUL;
 //   * cell runs whose closest possible distance is beyond the cutoff are skipped.
 // Most runs are then classified in packed float32 from tile-local coordinates (pc_segment_f32: rigorous
-// +-6e-7 class brackets, exact fp64 decision for the pairs the brackets leave open), which removes the
+// class brackets 5.5e-7 + delta wide, exact fp64 decision for the pairs the brackets leave open), which removes the
 // FP64 pipe from the inner loop without changing a count.
 // Nothing about the fp64 arithmetic changes: a pair evaluates exactly the candidates
 // fl(fl(p2+s)-p1) that can be the minimum of the reference's 27-image loop (Molecular:1451-1467),
@@ -221,18 +221,22 @@ struct PcTables {
     float r_max;            // clamp of the approximate distance: keeps the class index <= na+1
     int na;
     unsigned long long cut;
+    unsigned int special;   // shared address of the counter for "inside the cutoff, a-bin out of range" decided by an exact path (VARIANT 0)
     // float32 segments (see pc_segment_f32)
     float pad_x;            // local x of padded observed molecules: beyond the cutoff for every tile molecule
     unsigned int cnt_pad;   // byte offset of the counter window used by padded reference slots
 };
 
 // VARIANT 0: the class of a pair is floor(sqrt(d2)/step_a) evaluated approximately (top 52 bits of d2,
-//            MUFU.SQRT, two round-down FMAs with the scale shrunk / stretched by eps = 6e-7).  When both
+//            MUFU.SQRT, two round-down FMAs with the scale shrunk / stretched by eps = 5.5e-7 + delta_top).  When both
 //            brackets give the same integer the reference's exact float32 chain cannot give another one
-//            (its relative distance to x~ is < 4e-7), so no table is touched.  Otherwise (~1e-3 of the
-//            pairs) the pair takes the rare branch and is decided by the exact fp64 threshold.  Pairs
-//            beyond the cutoff land in counters >= na, which are ignored (valid when the class "inside
-//            the cutoff, a-bin out of range" is empty and the cutoff sits on the boundary of bin na).
+//            (its relative distance to x~ is < 5.1e-7), so no table is touched.  Otherwise (~2e-3 of the
+//            pairs) the pair takes the rare branch and is decided by the exact fp64 thresholds.  Pairs
+//            beyond the cutoff land in counters >= na, which are ignored.  Valid when the cutoff sits
+//            within delta_top <= 3e-7 of the boundary of bin na (pa_session.cu): the brackets are wider than
+//            the error budget by delta_top, so every pair that close to the boundary reaches the exact branch, which
+//            tells the last bin, "inside the cutoff, a-bin out of range" (counter T.special, counted
+//            out of bounds at flush time) and "beyond the cutoff" apart.
 // VARIANT 1: every pair is decided by the exact threshold table and an explicit cutoff test.
 // DIAG: the observed run overlaps the tile itself (symmetric pass): only pairs whose observed
 //       molecule comes later in the sorted order than the reference molecule are counted.
@@ -351,9 +355,12 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
                             }
                         }
                     } else if (VARIANT == 0) {
-                        // the two brackets disagree: decide with the exact fp64 threshold thr[n+1]
+                        // the two brackets disagree: decide with the exact fp64 threshold thr[n+1]; next to the cutoff the
+                        // outcome can also be "inside the cutoff, a-bin out of range" (class na) or "beyond the cutoff"
                         const double thr = pc_lds_f64(tlo[q] * 8u + thr_m + 8u);
-                        ca[q] = tlo[q] * 4u + cnt_m + (d2[q] >= thr ? 4u : 0u);
+                        const unsigned int n = tlo[q] + (d2[q] >= thr ? 1u : 0u);
+                        ca[q] = n * 4u + cnt_m;
+                        if (n == 0x4B000000u + (unsigned)na) ca[q] = dbits(d2[q]) < T.cut ? T.special : trash;
                     }
                 }
             }
@@ -365,7 +372,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
                     int lo_k = 0, hi_k = na + 1;
                     while (lo_k < hi_k) { const int mid = (lo_k + hi_k + 1) >> 1; if (d2[q] >= pc_lds_f64(T.thr + 8u * (unsigned)mid)) lo_k = mid; else hi_k = mid - 1; }
                     const int got = (int)((ca[q] - T.cnt) / 4u);
-                    const bool ok = lo_k < na ? (got == lo_k) : (got >= na);
+                    const bool ok = lo_k < na ? (got == lo_k) : (VARIANT == 0 && lo_k == na ? ca[q] == T.special : (got >= na && ca[q] != T.special));
                     if (!ok) atomicAdd(p.verify_fail, 1u);
                 }
             }
@@ -388,9 +395,11 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
 // | |d~| - |d| | <= |d~ - d| <= 2u(r + |T|): a relative error of 2u = 1.2e-7 in r plus the absolute term
 // a = 2u|T|.  On top come the three roundings of d2~ (1.5u = 0.9e-7 in r), sqrt.approx (2^-23 = 1.2e-7) and the
 // reference's own float32 chain fl(fl(sqrtf(fl(d2)))/step_a), which deviates from sqrt(d2)/step_a by
-// 2.5u = 1.5e-7.  The bracket factors (1 -+ 6e-7)/step_a are computed by the host in double and rounded
+// 2.5u = 1.5e-7.  The bracket factors (1 -+ eps)/step_a are computed by the host in double and rounded
 // outwards (PaPass::f32_lo/f32_hi), and the FFMA.RM is a single rounding, so the scale adds nothing.
-//   * far runs (boxes >= 2|T| apart): a <= u r = 0.6e-7, total 5.4e-7 relative, inside the +-6e-7 brackets;
+//   * far runs (boxes >= 2|T| apart): a <= u r = 0.6e-7, total 5.4e-7 relative; eps = 5.5e-7 + delta_top because the
+//     cutoff may sit delta_top <= 3e-7 off the boundary of the last bin (either side): every pair that close to the boundary
+//     must reach the exact path, which also knows the class "inside the cutoff, a-bin out of range";
 //   * NEAR runs: the brackets are evaluated at r~ -+ a (one more FADD2, whose rounding adds u): 5.4e-7.
 // A pair whose brackets disagree, or whose |link_xy|^2 may be below 2^-30, is re-evaluated from the staged
 // fp64 values exactly as pc_segment does, so results stay bit-identical.  Padded slots (tile tail, chunk
@@ -452,7 +461,7 @@ static __device__ __forceinline__ float4 pc_lds_f32x4(unsigned int addr)
 template <int MX, int MY, int MZ, bool ZCOL>
 static __device__ __noinline__ void pc_f32_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                  const unsigned long long *queue, int count, unsigned int a_j, long long jbase, int jc,
-                                                 unsigned int cnt_m)
+                                                 unsigned int cnt_m, int na, unsigned long long cut, unsigned int special)
 {
     __syncwarp();
     const int lane = threadIdx.x & 31;
@@ -487,8 +496,12 @@ static __device__ __noinline__ void pc_f32_drain(const PaPass &p, const PaCellGr
             // exact class inside the brackets [n_lo, n_hi] (n_hi = n_lo + 1 except next to r = 0 in NEAR runs);
             // thresholds from global memory: the float32 launch keeps no copy of the table in shared memory
             unsigned int n = max(tlo, 0x4B000000u);
-            while (n < thi && e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (n - 0x4B000000u + 1u)))) ++n;
-            pc_red(n * 4u + cnt_m);
+            const unsigned int n_end = min(thi, 0x4B000000u + (unsigned)na + 1u);   // class na + 1 = beyond the cutoff; the table has na + 3 entries
+            while (n < n_end && e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (n - 0x4B000000u + 1u)))) ++n;
+            const unsigned int cls = n - 0x4B000000u;
+            if (cls < (unsigned)na) pc_red(n * 4u + cnt_m);
+            else if (cls == (unsigned)na && dbits(e2) < cut) pc_red(special);      // inside the cutoff, a-bin out of range
+            // else: beyond the cutoff, not counted
         }
     }
     __syncwarp();
@@ -604,11 +617,14 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                 for (int q = 0; q < NP; ++q) {
                     const int r = q % PC_RI, u = q / PC_RI;
                     const int k = r * PC_THREADS + threadIdx.x;
-                    const bool need = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && k < tl.count && jc + jj + u < je;   // not for padded slots
+                    // not for padded slots, and not when even the lower bracket is beyond the cutoff (class > na: never counted,
+                    // and the threshold table ends at class na + 2)
+                    const bool need = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && tlo[q] <= 0x4B000000u + (unsigned)na &&
+                                      k < tl.count && jc + jj + u < je;
                     const unsigned int m = __ballot_sync(0xffffffffu, need);
                     if (m == 0u) continue;
                     const int add = __popc(m);
-                    if (qn + add > PC_QCAP) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }
+                    if (qn + add > PC_QCAP) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m, na, T.cut, T.special); qn = 0; }
                     if (need) {
                         queue[qn + __popc(m & lane_lt)] = ((unsigned long long)tlo[q] << 32) | ((unsigned long long)min(thi[q] - tlo[q], 255u) << 16) |
                                                           ((unsigned long long)(jj + u) << 9) | (unsigned long long)k;
@@ -629,14 +645,14 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                     int lo_k = 0, hi_k = na + 1;
                     while (lo_k < hi_k) { const int mid = (lo_k + hi_k + 1) >> 1; if (e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + mid))) lo_k = mid; else hi_k = mid - 1; }
                     const int got = (int)((ca[q] - T.cnt) / 4u);
-                    const bool ok = (__double2hiint(e1) >= 0x3E100000) && (lo_k < na ? (got == lo_k) : (got >= na));
+                    const bool ok = (__double2hiint(e1) >= 0x3E100000) && (lo_k < na ? (got == lo_k) : (got >= na && lo_k != na));   // class na is always queued
                     if (!ok) atomicAdd(p.verify_fail, 1u);
                 }
             }
 #pragma unroll
             for (int q = 0; q < NP; ++q) pc_red(ca[q]);
         }
-        if (qn > 0) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m); qn = 0; }   // before the chunk is overwritten
+        if (qn > 0) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m, na, T.cut, T.special); qn = 0; }   // before the chunk is overwritten
     }
 }
 
@@ -664,6 +680,14 @@ static __device__ void pc_flush(const PaPass &p, const PcTables &T, bool reset)
         atomicAdd(&p.job.acc[na], within * (unsigned long long)mult);
         if (p.acc2) atomicAdd(&p.acc2[na], within);
     }
+    if (VARIANT == 0 && threadIdx.x == 0) {                                                          // class na found by an exact path
+        const unsigned int c = pc_lds_u32(T.special);
+        if (c) {
+            atomicAdd(&p.job.acc[na + 1], (unsigned long long)((long long)c * mult));
+            if (p.acc2) atomicAdd(&p.acc2[na + 1], (unsigned long long)c);
+            if (reset) pc_sts_u32(T.special, 0u);
+        }
+    }
 }
 
 // PART 0: every run in one launch.  PART 1 / PART 2: the float32-eligible runs (far, single image) and all other
@@ -676,7 +700,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int na = p.job.bin_a;
     const bool f32_on = VARIANT == 0 && PART != 0 && p.f32_cnt > 0;       // PART 0 is launched only when float32 segments are off
-    const int ncnt = (f32_on && PART == 1) ? p.f32_cnt + na + 8 : na + 3;                                // counters (see pc_segment_f32)
+    const int ncnt = ((f32_on && PART == 1) ? p.f32_cnt + na + 8 : na + 3) + 1;                          // counters (see pc_segment_f32) + the class-na counter
     // PART 1 (float32 runs only): at most 4 staged doubles per molecule and no threshold table (read from global when needed)
     double *s_j = reinterpret_cast<double *>(smem_raw);                                   // PC_JC*6 doubles (PART 1: *4)
     float4 *s_jf = reinterpret_cast<float4 *>(s_j + PC_JC * (PART == 1 ? 4 : 6));         // PC_JC float4
@@ -697,12 +721,13 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     T.na = na;
     T.cut = p.job.cut_bits;
     if (VARIANT == 0) {
-        T.s_lo = p.job.guess_scale * (1.0f - 6.0e-7f);
-        T.s_hi = p.job.guess_scale * (1.0f + 6.0e-7f);
+        T.s_lo = p.job.guess_scale * (1.0f - p.eps64);
+        T.s_hi = p.job.guess_scale * (1.0f + p.eps64);
     } else {
         T.s_lo = T.s_hi = p.job.guess_scale * (1.0f - 9.5367431640625e-07f);             // floor(x~) <= true class
     }
     T.r_max = ((float)na + 1.5f) / p.job.guess_scale;
+    T.special = T.cnt + (unsigned)(ncnt - 1) * 4u;
     const float t2max = 32.0f;                                                            // largest |T| a float32 tile may have
     T.pad_x = p.job.maxdist * 1.001f + 3.0f * t2max;
     T.cnt_pad = (unsigned)(na + 8) * 4u;
@@ -1174,7 +1199,7 @@ void pa_cell_grid_dims(int nmol, int g[3])
 
 size_t pa_cells_smem_bytes(int na, int f32_cnt, int nlayers)   // f32_cnt > 0: the PART 1 launch
 {
-    const int ncnt = f32_cnt > 0 ? f32_cnt + na + 8 : na + 3;
+    const int ncnt = (f32_cnt > 0 ? f32_cnt + na + 8 : na + 3) + 1;
     return (size_t)PC_JC * (f32_cnt > 0 ? 4 : 6) * 8 + (size_t)PC_JC * 16 + (f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 2) * 4 +
            sizeof(PcSharedR) + (size_t)nlayers * sizeof(PcLayer) + (f32_cnt > 0 ? (size_t)(PC_THREADS / 32) * PC_QCAP * 8 : 0) + 16;
 }

@@ -93,8 +93,8 @@ struct PaPass {
     unsigned int *exc_count2;
     unsigned int *verify_fail;  // debug counter for the class-guess invariant (may be null)
     int32_t f32_cnt;            // > 0: float32 segments enabled in the cell kernel, counters needed for any reachable class
-    int32_t f32_pad_;
-    float f32_lo, f32_hi;       // (1 -+ 6e-7)/step_a rounded outwards; adjacent so that they load as one packed pair
+    float eps64;                // half-width of the class brackets of the fp64-difference segments (variant 0)
+    float f32_lo, f32_hi;       // (1 -+ eps)/step_a rounded outwards (eps: pa_session.cu); adjacent so that they load as one packed pair
 };
 
 // Uniform grid of one molecule type for a batch of frames (pa_cells.cu).  Arrays are

@@ -53,6 +53,7 @@ struct JobState {
     pa_job job;
     PaDevJob dj;
     bool fast;
+    double delta_top = 0.0;   // relative distance of the cutoff / the start of class na from the boundary of bin na (variant 0)
     int f32_cnt = 0;     // > 0: float32 segments of the cell kernel enabled (counter classes needed), see pa_cells.cu
     int cells_variant;   // 0: approximate class + rare exact fix-up, 1: exact table for every pair (see pa_cells.cu)
     size_t acc_off;      // offset (words) inside the accumulator block
@@ -309,14 +310,17 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
         d.acc = s->d_acc + js.acc_off;
         js.fast = !s->force_general && pa::job_is_rdf_fast(jb, *traj);   // false for cdf and charge_arm
         {
-            // variant 0 needs: no pair "inside the cutoff with a-bin out of range", and the cutoff within
-            // 3e-7 (relative) of the boundary of bin na, so that the sliver between the two is always
-            // caught by the +-6e-7 brackets of the approximate class.
+            // variant 0 needs the cutoff within 3e-7 (relative) of the boundary of bin na (REAL(4) step_a * bin_a is
+            // maxdist up to a few float32 roundings): the class brackets are wider than the error budget by the actual
+            // distance (delta_top), so every pair within that distance of the boundary -- binned in the last bin, "inside the cutoff with a-bin out
+            // of range", or beyond the cutoff -- is decided by the exact fp64 path, whichever side the cutoff lies on.
             js.cells_variant = 1;
-            if (jb.mode == PA_MODE_PDF && thr_a[jb.bin_a] == thr_a[(size_t)jb.bin_a + 1] && thr_a[(size_t)jb.bin_a + 1] != ~0ull) {
-                double cutd; memcpy(&cutd, &thr_a[(size_t)jb.bin_a + 1], 8);
-                const double xcut = std::sqrt(cutd) / (double)jb.step_a;
-                if (std::fabs(xcut - jb.bin_a) <= 3e-7 * jb.bin_a) js.cells_variant = 0;
+            js.delta_top = 0.0;
+            if (jb.mode == PA_MODE_PDF && thr_a[(size_t)jb.bin_a + 1] != ~0ull) {
+                double cutd, nad; memcpy(&cutd, &thr_a[(size_t)jb.bin_a + 1], 8); memcpy(&nad, &thr_a[(size_t)jb.bin_a], 8);
+                const double xcut = std::sqrt(cutd) / (double)jb.step_a, xna = std::sqrt(nad) / (double)jb.step_a;   // thr_a[na] <= cut
+                const double delta = std::max(std::fabs(xcut - jb.bin_a), std::fabs(xna - jb.bin_a)) / jb.bin_a;
+                if (delta <= 3e-7) { js.cells_variant = 0; js.delta_top = delta; }
             }
             js.f32_cnt = 0;
             if (js.cells_variant == 0 && !(ex.flags & PA_EXEC_NO_F32)) {
@@ -513,14 +517,19 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         p.exc_list = s->d_exc; p.exc_count = s->d_exc_count; p.exc_cap = s->exc_cap / 2; p.flags = s->d_exc_count;
         p.exc_list2 = s->d_exc + s->exc_cap / 2; p.exc_count2 = s->d_exc_count + 4;
         p.verify_fail = s->verify ? s->d_exc_count + 2 : nullptr;
-        p.f32_cnt = js.f32_cnt; p.f32_pad_ = 0;
+        p.f32_cnt = js.f32_cnt;
         {
             // brackets of the float32 segments: the largest float <= (1-eps)/step_a and the smallest float >= (1+eps)/step_a,
-            // computed in double so that the scale factor itself carries no rounding towards the inside (eps = 6e-7)
+            // computed in double so that the scale factor itself carries no rounding towards the inside; eps = error budget
+            // 5.4e-7 (pa_cells.cu) + the distance of the cutoff from the boundary of the last bin + 0.1e-7
+            const double eps = 5.5e-7 + js.delta_top;
             const double inv = 1.0 / (double)jb.step_a;
-            float lo = (float)(inv * (1.0 - 6.0e-7)), hi = (float)(inv * (1.0 + 6.0e-7));
-            if ((double)lo > inv * (1.0 - 6.0e-7)) lo = std::nextafterf(lo, 0.0f);
-            if ((double)hi < inv * (1.0 + 6.0e-7)) hi = std::nextafterf(hi, INFINITY);
+            float lo = (float)(inv * (1.0 - eps)), hi = (float)(inv * (1.0 + eps));
+            if ((double)lo > inv * (1.0 - eps)) lo = std::nextafterf(lo, 0.0f);
+            if ((double)hi < inv * (1.0 + eps)) hi = std::nextafterf(hi, INFINITY);
+            // fp64-difference segments: truncation of d2 to 24 bits 0.6e-7, sqrt.approx 1.2e-7, reference chain 1.5e-7,
+            // three float32 roundings inside the in-kernel scale factors 1.8e-7 = 5.1e-7
+            p.eps64 = (float)(5.5e-7 + js.delta_top);
             p.f32_lo = lo; p.f32_hi = hi;
         }
     };

@@ -298,6 +298,76 @@ def test_wrap_trajectory_switch(oracle):
         assert np.array_equal(hists[k], h0) and (within[k], oob[k]) == (w0, o0)
 
 
+def test_cutoff_off_the_last_bin_boundary(oracle):
+    """maxdist = 44.0 with 1000 bins: REAL(4) step_a * 1000 is below maxdist, so the reference has pairs "inside the
+    cutoff with a-bin out of range" (counted out of bounds, Distribution:829-831); maxdist = 46.5 has none.  Both take the
+    approximate-class kernels, whose exact branch must tell the three outcomes apart.  A lattice with spacing chosen
+    so that many pairs sit exactly in that sliver makes the case visible."""
+    L = 88.0
+    n_side = 25                                             # 25^3 = 15625 sites per type, spacing 3.52 A
+    g = (np.arange(n_side, dtype=np.float64) + 0.25) * (L / n_side)
+    lat = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(1, -1, 3)
+    rng = np.random.default_rng(61)
+    a = np.round(lat + rng.normal(0.0, 0.02, size=lat.shape), 4).astype(np.float32)
+    # type 2: every site displaced by a vector of length ~ 44.0 (just below / above the cutoff), so that thousands of
+    # pairs have d within 1e-6 relative of maxdist
+    u = rng.normal(size=lat.shape); u /= np.linalg.norm(u, axis=-1, keepdims=True)
+    r = 44.0 * (1.0 + rng.uniform(-4e-7, 4e-7, size=lat.shape[:2] + (1,)))
+    b = (np.mod(lat + u * r, L)).astype(np.float32)
+    tl = [dict(charge=+1, natoms=1, nmol=a.shape[1], elements=["Na"], xyz=a.reshape(1, -1, 1, 3)),
+          dict(charge=-1, natoms=1, nmol=b.shape[1], elements=["Cl"], xyz=b.reshape(1, -1, 1, 3))]
+    lo, hi = capi.cubic_box_edge(0.0, L)
+    traj = capi.Trajectory(tl, lo, hi)
+    reqs = [dict(mode="pdf", ref_type=1, obs_type=2, bin_a=1000, bin_b=1, maxdist_optimize=True),
+            dict(mode="pdf", ref_type=2, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True)]
+    pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
+    assert pjobs[0].maxdist == 44.0
+    runs = {f: api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY | f)) for f in (0, capi.PA_EXEC_NO_F32, capi.PA_EXEC_NO_CELLS)}
+    assert runs[0][3].kernel_launches > runs[capi.PA_EXEC_NO_F32][3].kernel_launches      # approximate-class + float32 launches ran
+    ref = runs[capi.PA_EXEC_NO_CELLS]
+    for f, got in runs.items():
+        for k in range(len(pjobs)):
+            assert np.array_equal(got[0][k], ref[0][k]) and got[1][k] == ref[1][k] and got[2][k] == ref[2][k], (f, k)
+    h0, w0, o0 = oracle.histogram(traj, pjobs[0])
+    assert np.array_equal(ref[0][0], h0) and (int(ref[1][0]), int(ref[2][0])) == (w0, o0)
+    assert o0 > 0, "the construction must produce pairs inside the cutoff whose a-bin is out of range"
+
+
+@pytest.mark.parametrize("case", ["molecules", "dense_and_sparse", "orthorhombic"])
+def test_float32_segments_on_inexact_coordinates(case):
+    """(The cutoff 46.5 A / 1000 bins is one for which REAL(4) step_a * bin_a reaches the cutoff, i.e. the approximate-class
+    variant of the cell kernel applies; e.g. 44.0 A does not, and then every pair takes the exact table.)
+    Float32 segments where nothing about the coordinates is special: centres of mass of two-atom molecules (arbitrary
+    doubles), types of very different density (small and large cells, tiles wider than the float32 limit), and an
+    orthorhombic box with full-double bounds.  The float32 launch, the fp64-only cell kernel and the brute-force kernel
+    must agree bit for bit (VERIFY re-derives every class from the fp64 table inside the kernels)."""
+    rng = np.random.default_rng({"molecules": 51, "dense_and_sparse": 52, "orthorhombic": 53}[case])
+    if case == "molecules":
+        L, specs = 93.0, [(+1, 2, 20000), (-1, 1, 18000)]
+    elif case == "dense_and_sparse":
+        L, specs = 93.0, [(+1, 1, 70000), (-1, 1, 14800)]
+    else:
+        L, specs = 100.0, [(+1, 1, 27000), (-1, 1, 25000)]      # shortest edge 93 A -> cutoff 46.5 A as in the other cases
+    lo = np.array([0.0, 0.0, 0.0]); hi = np.array([L, L, L])
+    if case == "orthorhombic":
+        lo = np.array([-3.3333333333, 1.25, 0.1]); hi = lo + np.array([L, L * 1.11, L * 0.93])
+    tl = []
+    for ch, na, nm in specs:
+        c = lo + rng.random((1, nm, 1, 3)) * (hi - lo)
+        xyz = c + (rng.normal(0.0, 0.45, size=(1, nm, na, 3)) if na > 1 else 0.0)
+        tl.append(dict(charge=ch, natoms=na, nmol=nm, elements=["N"] * na, xyz=np.round(xyz, 5).astype(np.float32)))
+    traj = capi.Trajectory(tl, lo, hi, xyz_format=(case != "orthorhombic"))
+    reqs = [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
+            dict(mode="pdf", vec=(0, 0, -1), ref_type=2, obs_type=1, bin_a=333, bin_b=1, maxdist_optimize=True)]
+    pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
+    runs = {f: api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY | f)) for f in (0, capi.PA_EXEC_NO_F32, capi.PA_EXEC_NO_CELLS)}
+    assert runs[0][3].kernel_launches > runs[capi.PA_EXEC_NO_F32][3].kernel_launches      # the float32 launches really ran
+    ref = runs[capi.PA_EXEC_NO_CELLS]
+    for f, got in runs.items():
+        for k in range(len(pjobs)):
+            assert np.array_equal(got[0][k], ref[0][k]) and got[1][k] == ref[1][k] and got[2][k] == ref[2][k], (case, f, k)
+
+
 @pytest.mark.parametrize("outside", [False, True])
 def test_wrap_trajectory_with_cell_sorted_kernels(outside):
     """wrap_trajectory T on a large system: the cell-sorted kernels apply as long as every centre of mass lies inside the
