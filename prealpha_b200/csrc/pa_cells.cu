@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(1024) pa_cell_scan_kernel(PaCellGrid g)
 }
 
 // K3: scatter into cell order (order inside a cell is arbitrary: results are integer sums)
-__global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, PaPoints pts, int frame0, int nframes)
+__global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, PaPoints pts, PaBox box, int frame0, int nframes)
 {
     const long long total = (long long)nframes * g.nmol;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
@@ -98,7 +98,13 @@ __global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, PaPo
         const int cell = g.cid[id];
         const int pos = g.cell_start[(long long)f * (g.ncell + 1) + cell] + atomicAdd(&g.cell_fill[(long long)f * g.ncell + cell], 1);
         const long long o = (long long)f * g.nmol + pos;
-        g.sx[o] = pts.px[slot]; g.sy[o] = pts.py[slot]; g.sz[o] = pts.pz[slot];
+        // A position outside the box (not wrapped: wrap_trajectory, or beyond 1000 wrap moves) or NaN has already raised
+        // the sticky flag in pa_cell_count_kernel and the whole call will be redone without cells; the pair kernels still
+        // run, so such a position is clamped into the box here to keep every distance below the box diagonal (the
+        // float32 segments size their counter window by that bound).  fmax / fmin return the non-NaN operand.
+        g.sx[o] = fmin(fmax(pts.px[slot], box.lo[0]), box.hi[0]);
+        g.sy[o] = fmin(fmax(pts.py[slot], box.lo[1]), box.hi[1]);
+        g.sz[o] = fmin(fmax(pts.pz[slot], box.lo[2]), box.hi[2]);
         g.sorig[o] = m;
         g.sflag[o] = (pts.wx[slot] != 0.0 || pts.wy[slot] != 0.0 || pts.wz[slot] != 0.0) ? 1 : 0;
     }
@@ -1170,7 +1176,7 @@ int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &b
     cudaMemsetAsync(g.lay_hi, 0x00, sizeof(unsigned long long) * (size_t)nframes * 3 * g.gmax, st);
     pa_cell_count_kernel<<<blocks, 256, 0, st>>>(g, pts, box, frame0, nframes, err);
     pa_cell_scan_kernel<<<nframes, 1024, 0, st>>>(g);
-    pa_cell_scatter_kernel<<<blocks, 256, 0, st>>>(g, pts, frame0, nframes);
+    pa_cell_scatter_kernel<<<blocks, 256, 0, st>>>(g, pts, box, frame0, nframes);
     return (int)cudaGetLastError();
 }
 

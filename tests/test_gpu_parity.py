@@ -368,21 +368,26 @@ def test_float32_segments_on_inexact_coordinates(case):
             assert np.array_equal(got[0][k], ref[0][k]) and got[1][k] == ref[1][k] and got[2][k] == ref[2][k], (case, f, k)
 
 
+@pytest.mark.parametrize("wrap", [True, False])
 @pytest.mark.parametrize("outside", [False, True])
-def test_wrap_trajectory_with_cell_sorted_kernels(outside):
+def test_wrap_trajectory_with_cell_sorted_kernels(outside, wrap):
     """wrap_trajectory T on a large system: the cell-sorted kernels apply as long as every centre of mass lies inside the
-    box (float32 and general kernels alike); with molecules outside the box the call must fall back to the brute-force
-    kernels by itself.  Both must equal the brute-force result (which the small-system test pins on the oracle)."""
+    box (float32 and general kernels alike); with molecules outside the box -- slightly, absurdly far, or NaN -- the call
+    must fall back to the brute-force kernels by itself, and the cell kernels that run before the flag is read must stay
+    inside their tables.  Same without wrap_trajectory, where wrap_vector gives up after 1000 moves.  Both must equal
+    the brute-force result (which the small-system tests pin on the oracle)."""
     rng = np.random.default_rng(41)
     n1, n2, L = 14000, 13000, 81.0
     pos = np.round(rng.random((1, n1 + n2, 3)) * L, 4)
     if outside:
         pos[0, 5] = (-0.5, 10.0, 10.0); pos[0, n1 + 7] = (40.0, L + 0.25, 3.0)
+        pos[0, 6] = (1.0e7, 20.0, 20.0)                    # absurdly far (also after 1000 wrap moves): must not send a kernel out of its tables
+        pos[0, n1 + 8] = (np.nan, 1.0, 1.0)
     pos = pos.astype(np.float32)
     tl = [dict(charge=+1, natoms=1, nmol=n1, elements=["Na"], xyz=pos[:, :n1].reshape(1, n1, 1, 3)),
           dict(charge=-1, natoms=1, nmol=n2, elements=["Cl"], xyz=pos[:, n1:].reshape(1, n2, 1, 3))]
     lo, hi = capi.cubic_box_edge(0.0, L)
-    traj = capi.Trajectory(tl, lo, hi, wrap_trajectory=True)
+    traj = capi.Trajectory(tl, lo, hi, wrap_trajectory=wrap)
     reqs = [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=800, bin_b=1, maxdist_optimize=True),
             dict(mode="pdf", vec=(1, 0, 1), ref_type=2, obs_type=1, bin_a=30, bin_b=18, maxdist=9.5),
             dict(mode="cdf", vec=(0, 0, 1), ref_type=1, obs_type=2, bin_a=25, bin_b=25, maxdist=8.0)]
@@ -393,6 +398,8 @@ def test_wrap_trajectory_with_cell_sorted_kernels(outside):
         assert np.array_equal(cells[0][k], brute[0][k]) and cells[1][k] == brute[1][k] and cells[2][k] == brute[2][k], k
     if not outside:
         assert cells[3].kernel_launches != brute[3].kernel_launches      # the cell path really ran
+    else:
+        assert wrap or int(cells[1].sum()) > 0
 
 
 @pytest.mark.parametrize("name", ["synth", "lmp", "lmp_wrap", "lmp_unwrap", "charge_arm"])
