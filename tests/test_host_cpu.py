@@ -34,6 +34,37 @@ def test_struct_layout_matches_header_sizes():
     assert C.sizeof(capi.pa_exec) == 24
 
 
+def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):
+    """Every struct of include/prealpha_b200.h: sizeof and the offset of its last field, printed by a C program compiled
+    against the header, equal what the ctypes mirror in prealpha_b200/capi.py lays out."""
+    import subprocess
+    structs = {"pa_type": "xyz", "pa_traj": "wrap_trajectory", "pa_job_request": "normalise_clm", "pa_job": "normalise_clm",
+               "pa_exec": None, "pa_stats": None, "pa_dist_subjob": "weight", "pa_dist_job": "exponent", "pa_dist_result": "missed_neighbours",
+               "pa_contact_result": "pairs_evaluated", "pa_neigh_request": "skip_same_molecule", "pa_neigh_pair": "ib"}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "prealpha_b200.h"', "int main(void) {"]
+    for name, last in structs.items():
+        off = f"(long)offsetof({name}, {last})" if last else "-1L"
+        lines.append(f'  printf("{name} %zu %ld\\n", sizeof({name}), {off});')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines) + "\n")
+    exe = tmp_path / "layout"
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    subprocess.check_call(["gcc", "-std=c11", "-I", inc, str(src), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)]).decode().split("\n")
+    seen = 0
+    for row in out:
+        if not row.strip():
+            continue
+        name, size, off = row.split()
+        ct = getattr(capi, name)
+        assert C.sizeof(ct) == int(size), name
+        if int(off) >= 0:
+            assert getattr(ct, structs[name]).offset == int(off), name
+        seen += 1
+    assert seen == len(structs)
+
+
 @pytest.mark.parametrize("name", fixtures.available())
 def test_job_setup_matches_oracle_bitwise(name, oracle):
     fx = fixtures.Fixture(name)
