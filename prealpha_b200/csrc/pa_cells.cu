@@ -836,6 +836,10 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                 const PcLayer ly = lay[gx + cy];
                 const float dyz2 = lz.dmin2 + ly.dmin2;
                 if (!(dyz2 < cutf)) continue;
+                // PART 2 has nothing to do in a row whose y and z layers are single-image, at least 2|T| away and not in the
+                // tile's own xy column: every run there is float32-eligible whatever its x class (nearr and zcol are false)
+                if (PART == 2 && tile_f32 && ly.mode == 1 && lz.mode == 1 && dyz2 >= rmin2 && ly.dmin2 > 1.0e-6f &&
+                    !(SYM && cz * gy + cy == tile_row)) continue;
                 const int *row = cs + ((long long)cz * gy + cy) * gx;
                 int cx = 0;
                 while (cx < gx) {
