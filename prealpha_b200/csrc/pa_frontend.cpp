@@ -54,6 +54,57 @@ bool parse_int(const std::string &s, int &v)
     v = (int)x;
     return true;
 }
+// Decimal text -> REAL(4), correctly rounded like strtof (what the list-directed READ of the reference produces,
+// Molecular:5042), for the coordinates of a trajectory line.  Fast path: [+-]digits[.digits][(e|E)[+-]digits] with at
+// most 15 significant digits and a decimal exponent within +-22.  Then the digits are an integer m < 2^53 and 10^|e| is
+// exact in double, so d = m * 10^e (or m / 10^-e) is the correctly rounded double of the decimal value, and rounding d
+// to float32 equals rounding the decimal value directly unless d sits exactly on the midpoint between two floats
+// (d is the nearest double and the midpoint is a double, so value and d lie on the same side of it otherwise).
+// Midpoints, tiny magnitudes (float32 subnormals), long digit strings, large exponents, inf / nan / hex and anything
+// else unusual go to strtof.  *end receives the first unparsed character, as with strtof.
+float parse_coordinate(const char *p, const char **end)
+{
+    static const double pow10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16,
+                                      1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
+    const char *q = p;
+    bool neg = false;
+    if (*q == '+' || *q == '-') { neg = (*q == '-'); ++q; }
+    unsigned long long m = 0;
+    int ndig = 0, nsig = 0, e10 = 0;
+    bool ok = true;
+    while (*q >= '0' && *q <= '9') { if (nsig || *q != '0') { if (++nsig > 15) ok = false; else m = m * 10 + (unsigned)(*q - '0'); } ++ndig; ++q; }
+    if (*q == '.') {
+        ++q;
+        while (*q >= '0' && *q <= '9') { if (nsig || *q != '0') { if (++nsig > 15) ok = false; else m = m * 10 + (unsigned)(*q - '0'); } --e10; ++ndig; ++q; }
+    }
+    if (ndig == 0 || *q == 'x' || *q == 'X') ok = false;      // nothing numeric, or a hexadecimal constant: strtof decides
+    if (ok && (*q == 'e' || *q == 'E')) {
+        const char *x = q + 1;
+        bool eneg = false;
+        if (*x == '+' || *x == '-') { eneg = (*x == '-'); ++x; }
+        if (*x >= '0' && *x <= '9') {
+            int ev = 0;
+            while (*x >= '0' && *x <= '9') { if (ev < 10000) ev = ev * 10 + (*x - '0'); ++x; }
+            e10 += eneg ? -ev : ev;
+            q = x;
+        }
+    }
+    if (ok && e10 >= -22 && e10 <= 22) {
+        double d = (double)m;
+        d = e10 < 0 ? d / pow10[-e10] : d * pow10[e10];
+        unsigned long long bits; memcpy(&bits, &d, 8);
+        if ((bits & 0x1FFFFFFFull) != 0x10000000ull && (d == 0.0 || d > 1e-30)) {
+            *end = q;
+            const float f = (float)d;
+            return neg ? -f : f;
+        }
+    }
+    char *e;
+    const float f = strtof(p, &e);
+    *end = e;
+    return f;
+}
+
 bool parse_real4(const std::string &s, float &v)      // decimal -> REAL(4) directly
 {
     std::string t = s;
@@ -255,13 +306,17 @@ bool load_trajectory(Run &r)
     const std::string path = r.path_traj + r.traj_file;
     FILE *f = fopen(path.c_str(), "r");
     if (!f) { r.error(9, "trajectory file '" + path + "' not found"); return false; }
+    const auto t_load0 = std::chrono::steady_clock::now();
+    const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
+    double t_read = 0, t_count = 0, t_parse = 0;
+    auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const bool lmp = (r.traj_type == "lmp");
     const int header = lmp ? 9 : 2;
     long long natoms_total = 0;
     for (auto &t : r.types) { natoms_total += (long long)t.natoms * t.nmol; t.xyz.assign((size_t)r.nsteps * t.natoms * t.nmol * 3, 0.f); }
     // Multi-threaded ingestion: the file is read in large blocks; each block is cut into
     // whole frames by counting newlines, split among the host threads at line boundaries, and every
-    // thread parses its lines with strtof (decimal -> REAL(4) directly, like the list-directed READ at
+    // thread parses its lines with parse_coordinate (decimal -> REAL(4) directly, bit-identical to strtof, like the list-directed READ at
     // Molecular:5042) straight into the [step][mol][atom][3] arrays.  The reference's reader is serial.
     const long long lines_per_frame = header + natoms_total;
     std::vector<long long> type_first(r.types.size() + 1, 0);           // first atom line of each type inside a frame
@@ -280,7 +335,7 @@ bool load_trajectory(Run &r)
         p = e;
         for (int k = 0; k < 3; ++k) {
             while (*p == ' ' || *p == '\t' || *p == ',') ++p;
-            char *q; dst[k] = strtof(p, &q); p = q;
+            const char *q; dst[k] = parse_coordinate(p, &q); p = q;
         }
     };
     auto parse_header_line = [&](const std::string &ln, int h) {        // frame 1 only, serial
@@ -301,19 +356,21 @@ bool load_trajectory(Run &r)
         }
     };
     const unsigned nthreads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-    const size_t block_bytes = (size_t)256 << 20;
+    const size_t block_bytes = (size_t)64 << 20;
     std::vector<char> buf;
     size_t have = 0;                    // valid bytes in buf
     int steps_read = 0;
     bool eof = false;
     while (steps_read < r.nsteps) {
         // 1. top up the buffer
+        double t0 = now_s();
         if (!eof) {
             if (buf.size() < have + block_bytes + 1) buf.resize(have + block_bytes + 1);
             const size_t got = fread(buf.data() + have, 1, block_bytes, f);
             have += got;
             if (got < block_bytes) { eof = true; if (have && buf[have - 1] != '\n') buf[have++] = '\n'; }
         }
+        t_read += now_s() - t0; t0 = now_s();
         // 2. how many whole frames does it hold?  (count newlines, stop at the last frame boundary)
         const int want = r.nsteps - steps_read;
         long long nl = 0; size_t end = 0; int nframes = 0;
@@ -327,6 +384,7 @@ bool load_trajectory(Run &r)
             if (eof) break;                                               // truncated file: error 84 below
             continue;                                                     // frame larger than the buffer so far: read more
         }
+        t_count += now_s() - t0; t0 = now_s();
         // 3. frame 1: header lines serially
         if (steps_read == 0) {
             const char *p = buf.data();
@@ -379,12 +437,14 @@ bool load_trajectory(Run &r)
                 });
             for (auto &x : th) x.join();
         }
+        t_parse += now_s() - t0;
         steps_read += nframes;
         // 5. keep the unparsed tail
         memmove(buf.data(), buf.data() + end, have - end);
         have -= end;
     }
     fclose(f);
+    if (dbg_t) fprintf(stderr, "[prealpha_b200] ingestion: read %.3f s, frame cut %.3f s, parse %.3f s\n", t_read, t_count, t_parse);
     if (steps_read < r.nsteps) {                                  // Molecular:5003-5009, error 84
         r.error(84, "trajectory is shorter than specified; using " + std::to_string(steps_read) + " steps");
         // re-pack is not needed: arrays are [step][mol][atom][3], truncation just drops the tail
@@ -415,6 +475,11 @@ bool load_trajectory(Run &r)
             for (int a = 0; a < t.natoms; ++a) sum = sum + t.atom_charge[a];
             if (std::fabs(sum - (double)(float)t.charge) > (double)0.001f) { r.error(126, "sum of atomic charges differs from formal charge"); t.realcharge = (float)sum; }
         }
+    }
+    if (r.verbose) {
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load0).count();
+        printf(" reading the trajectory...done (%d steps of %lld atoms in %.3f s: %.1f million atoms/s on the host threads).\n",
+               r.nsteps, natoms_total, sec, sec > 0 ? (double)r.nsteps * (double)natoms_total / sec * 1e-6 : 0.0);
     }
     return true;
 }
@@ -993,6 +1058,15 @@ const char *kOtherModuleKeywords[] = {
 };
 
 }  // namespace
+
+// test hook: the trajectory readers' decimal -> REAL(4) conversion (must equal strtof bit for bit)
+extern "C" float pa_debug_parse_coordinate(const char *s, int32_t *consumed)
+{
+    const char *e = s;
+    const float f = parse_coordinate(s, &e);
+    if (consumed) *consumed = (int32_t)(e - s);
+    return f;
+}
 
 extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec *exec)
 {

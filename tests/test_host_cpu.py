@@ -216,3 +216,52 @@ def test_distribution_input_parser():
     assert reqs[0].maxdist == 12.5 and reqs[0].maxdist_optimize == 0
     with pytest.raises(ValueError):
         inputs.parse_distribution_input("pdf 1\n0 0 1 3 1\n", ntypes=2)
+
+
+def test_fast_coordinate_parser_equals_strtof():
+    """The trajectory readers convert decimal text to REAL(4) with a fast path (exact integer mantissa x exact power of ten
+    in double, then one rounding to float32) that must agree with libc's correctly rounded strtof bit for bit, including
+    how many characters it consumes: random decimals of every length, exponents, signs, zeros, strings on and next to
+    float32 rounding midpoints (where the fast path must defer to strtof), overflow / underflow, and non-numeric tokens."""
+    import ctypes.util
+    from decimal import Decimal, getcontext
+    getcontext().prec = 60
+    lib = capi.load()
+    fn = lib.pa_debug_parse_coordinate
+    fn.restype, fn.argtypes = C.c_float, [C.c_char_p, C.POINTER(C.c_int32)]
+    libc = C.CDLL(ctypes.util.find_library("c"))
+    libc.strtof.restype, libc.strtof.argtypes = C.c_float, [C.c_char_p, C.POINTER(C.c_char_p)]
+    rng = np.random.default_rng(99)
+    cases = ["0", "-0", "0.0", "-0.0", "+1", "1.", ".5", "-.5", ".", "-", "+", "", "1e", "1e+", "1E5", "1e-5", "1.5D0", "12,3", "7abc",
+             "0x1p3", "0X10", "inf", "-inf", "nan", "NaN", "infinity", "1e38", "3.4028235e38", "3.4028236e38", "3.5e38", "1e39", "1e-37", "1e-38",
+             "1.17549435e-38", "1e-40", "1e-45", "7e-46", "1e-50", "123456789012345", "1234567890123456", "0.000000000000000000001",
+             "00000123.4500000", "1e22", "1e23", "1e-22", "1e-23", "9007199254740993", "16777217", "16777216.5", "33554433", "0.1", "0.3",
+             "271.4418", "63.9223", "-12.34567", "1.0000000596046448", "1.00000005960464477539062", "1.00000005960464477539063", "1.00000005960464477539061"]
+    for nd in range(1, 19):                                              # random digit strings with a point somewhere
+        for _ in range(1500):
+            digits = "".join(rng.choice(list("0123456789"), size=nd))
+            k = int(rng.integers(0, nd + 1))
+            s = digits[:k] + "." + digits[k:]
+            if rng.random() < 0.3:
+                s += f"e{int(rng.integers(-30, 31))}"
+            cases.append(("-" if rng.random() < 0.5 else "") + s)
+    for _ in range(4000):                                                # exact float32 midpoints and their decimal neighbours
+        f = np.float32(10.0 ** rng.uniform(-6, 6) * rng.uniform(1, 10))
+        g = np.nextafter(f, np.float32(np.inf), dtype=np.float32)
+        mid = (Decimal(float(f)) + Decimal(float(g))) / 2
+        txt = format(mid, "f")
+        cases.append(txt)
+        for digits in (9, 12, 15, 17):
+            q = Decimal(1).scaleb(-digits)
+            cases += [format(mid.quantize(q), "f"), format(mid.quantize(q) + q, "f"), format(mid.quantize(q) - q, "f")]
+    for s in cases:
+        b = s.encode()
+        n = C.c_int32(-1)
+        got = np.float32(fn(b, C.byref(n)))
+        endp = C.c_char_p()
+        buf = C.create_string_buffer(b)
+        exp = np.float32(libc.strtof(buf, C.byref(endp)))
+        consumed = C.cast(endp, C.c_void_p).value - C.addressof(buf)
+        assert got.tobytes() == exp.tobytes() or (np.isnan(got) and np.isnan(exp)), (s, got, exp)
+        assert n.value == consumed, (s, n.value, consumed)
+    assert len(cases) > 40000
