@@ -277,6 +277,10 @@ typedef struct pa_contact_result {
 } pa_contact_result;
 int pa_contact_distance(const pa_traj *traj, int32_t timestep, int32_t type, const pa_exec *exec, pa_contact_result *result);
 
+/* Page-locked staging buffers of finished sessions are kept for the next call of the same size (at most four buffers,
+ * 1 GiB); pa_trim() gives them back to the system. */
+void pa_trim(void);
+
 /* ---- neighbour pairs -----------------------------------------
  * The distance test that the cluster and speciation analyses run for every pair
  * of listed atoms: give_smallest_atom_distance_squared(...) < squared cutoff in

@@ -160,6 +160,7 @@ SIGNATURES = {
     "pa_abi_version": (C.c_int, []),
     "pa_last_error": (C.c_char_p, []),
     "pa_device_count": (C.c_int, []),
+    "pa_trim": (None, []),
     "pa_job_setup": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_job_request), C.POINTER(pa_job)]),
     "pa_distribution_histogram": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_job), _I64P, _I64P, _I64P]),
     "pa_distribution_histogram_multi": (C.c_int, [C.POINTER(pa_traj), C.POINTER(pa_job), C.c_int32,

@@ -147,6 +147,13 @@ int upload_types_table(pa_session *s, int slot)
 extern "C" {
 
 int pa_abi_version(void) { return PA_ABI_VERSION; }
+
+void pa_trim(void)
+{
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (const PinnedEntry &e : g_pinned_pool) cudaFreeHost(e.ptr);
+    g_pinned_pool.clear();
+}
 const char *pa_last_error(void) { return g_last_error.c_str(); }
 
 int pa_device_count(void)
