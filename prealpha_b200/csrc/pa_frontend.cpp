@@ -177,6 +177,7 @@ struct Run {
     std::string traj_file, mol_file, path_traj, path_in, path_out, prefix;
     std::string traj_type = "lmp";
     bool box_given = false, read_sequential = false, wrap = false, unwrap = false, extra_velocity = false;
+    bool stream = false;          // sequential_read T and nothing in general.inp needs the whole trajectory in RAM
     bool verbose = true, custom_charges = false;
     double box_lo[3] = {0, 0, 0}, box_hi[3] = {0, 0, 0}, max_dist_sq = 0.0;
     int nsteps = 0;
@@ -301,23 +302,40 @@ float element_mass(Run &r, const std::string &el)
 
 // Trajectory: header pass over frame 1 (elements -> masses / charges, Molecular:4827-4949) and
 // body (Molecular:4951-5063): `READ(3,*) element_name, coordinates` per atom, REAL(4) items.
-bool load_trajectory(Run &r)
+//
+// Multi-threaded ingestion: the file is read in large blocks; each block is cut into
+// whole frames by counting newlines, split among the host threads at line boundaries, and every
+// thread parses its lines with parse_coordinate (decimal -> REAL(4) directly, bit-identical to strtof,
+// like the list-directed READ at Molecular:5042) straight into [frame][mol][atom][3] arrays.  The
+// reference's reader is serial.  TrajStream keeps the position between calls, so the same code loads
+// the whole trajectory (sequential_read F) or streams it batch by batch (sequential_read T).
+struct TrajStream {
+    FILE *f = nullptr;
+    std::vector<char> buf;
+    size_t have = 0;                    // valid bytes in buf
+    bool eof = false;
+    int frames_done = 0;                // frames parsed so far = index of the next frame
+    double t_read = 0, t_count = 0, t_parse = 0;
+    ~TrajStream() { if (f) fclose(f); }
+};
+
+bool open_stream(Run &r, TrajStream &ts)
 {
     const std::string path = r.path_traj + r.traj_file;
-    FILE *f = fopen(path.c_str(), "r");
-    if (!f) { r.error(9, "trajectory file '" + path + "' not found"); return false; }
-    const auto t_load0 = std::chrono::steady_clock::now();
-    const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
-    double t_read = 0, t_count = 0, t_parse = 0;
+    ts.f = fopen(path.c_str(), "r");
+    if (!ts.f) { r.error(9, "trajectory file '" + path + "' not found"); return false; }
+    return true;
+}
+
+// Parses up to `want` further frames into dst[type] ([local frame][mol][atom][3], local frame 0 = first frame of this
+// call); returns the number of frames parsed (< want at the end of the file).
+int read_frames(Run &r, TrajStream &ts, int want_frames, const std::vector<float *> &dst)
+{
     auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const bool lmp = (r.traj_type == "lmp");
     const int header = lmp ? 9 : 2;
     long long natoms_total = 0;
-    for (auto &t : r.types) { natoms_total += (long long)t.natoms * t.nmol; t.xyz.assign((size_t)r.nsteps * t.natoms * t.nmol * 3, 0.f); }
-    // Multi-threaded ingestion: the file is read in large blocks; each block is cut into
-    // whole frames by counting newlines, split among the host threads at line boundaries, and every
-    // thread parses its lines with parse_coordinate (decimal -> REAL(4) directly, bit-identical to strtof, like the list-directed READ at
-    // Molecular:5042) straight into the [step][mol][atom][3] arrays.  The reference's reader is serial.
+    for (auto &t : r.types) natoms_total += (long long)t.natoms * t.nmol;
     const long long lines_per_frame = header + natoms_total;
     std::vector<long long> type_first(r.types.size() + 1, 0);           // first atom line of each type inside a frame
     for (size_t t = 0; t < r.types.size(); ++t) type_first[t + 1] = type_first[t] + (long long)r.types[t].natoms * r.types[t].nmol;
@@ -331,11 +349,11 @@ bool load_trajectory(Run &r)
         const char *e = p;
         while (*e && *e != ' ' && *e != '\t' && *e != ',' && *e != '\n' && *e != '\r') ++e;
         if (first_frame && m == 0) ty.elements[a] = std::string(p, (size_t)std::min<ptrdiff_t>(e - p, 2));
-        float *dst = &ty.xyz[(((size_t)step * ty.nmol + m) * ty.natoms + a) * 3];
+        float *out = dst[t] + (((size_t)step * ty.nmol + m) * ty.natoms + a) * 3;
         p = e;
         for (int k = 0; k < 3; ++k) {
             while (*p == ' ' || *p == '\t' || *p == ',') ++p;
-            const char *q; dst[k] = parse_coordinate(p, &q); p = q;
+            const char *q; out[k] = parse_coordinate(p, &q); p = q;
         }
     };
     auto parse_header_line = [&](const std::string &ln, int h) {        // frame 1 only, serial
@@ -357,36 +375,40 @@ bool load_trajectory(Run &r)
     };
     const unsigned nthreads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
     const size_t block_bytes = (size_t)64 << 20;
-    std::vector<char> buf;
-    size_t have = 0;                    // valid bytes in buf
+    std::vector<char> &buf = ts.buf;
     int steps_read = 0;
-    bool eof = false;
-    while (steps_read < r.nsteps) {
-        // 1. top up the buffer
+    while (steps_read < want_frames) {
+        // 1. top up the buffer (only when it does not already hold a whole frame)
         double t0 = now_s();
-        if (!eof) {
-            if (buf.size() < have + block_bytes + 1) buf.resize(have + block_bytes + 1);
-            const size_t got = fread(buf.data() + have, 1, block_bytes, f);
-            have += got;
-            if (got < block_bytes) { eof = true; if (have && buf[have - 1] != '\n') buf[have++] = '\n'; }
-        }
-        t_read += now_s() - t0; t0 = now_s();
-        // 2. how many whole frames does it hold?  (count newlines, stop at the last frame boundary)
-        const int want = r.nsteps - steps_read;
+        const int want = want_frames - steps_read;
         long long nl = 0; size_t end = 0; int nframes = 0;
-        for (const char *p = buf.data(), *lim = buf.data() + have; p < lim && nframes < want;) {
-            const char *q = (const char *)memchr(p, '\n', (size_t)(lim - p));
-            if (!q) break;
-            ++nl; p = q + 1;
-            if (nl % lines_per_frame == 0) { ++nframes; end = (size_t)(p - buf.data()); }
+        auto count_frames = [&] {
+            nl = 0; end = 0; nframes = 0;
+            for (const char *p = buf.data(), *lim = buf.data() + ts.have; p < lim && nframes < want;) {
+                const char *q = (const char *)memchr(p, '\n', (size_t)(lim - p));
+                if (!q) break;
+                ++nl; p = q + 1;
+                if (nl % lines_per_frame == 0) { ++nframes; end = (size_t)(p - buf.data()); }
+            }
+        };
+        if (ts.have > 0) count_frames();
+        ts.t_count += now_s() - t0; t0 = now_s();
+        if (nframes < want && !ts.eof) {
+            if (buf.size() < ts.have + block_bytes + 1) buf.resize(ts.have + block_bytes + 1);
+            const size_t got = fread(buf.data() + ts.have, 1, block_bytes, ts.f);
+            ts.have += got;
+            if (got < block_bytes) { ts.eof = true; if (ts.have && buf[ts.have - 1] != '\n') buf[ts.have++] = '\n'; }
+            ts.t_read += now_s() - t0; t0 = now_s();
+            // 2. how many whole frames does it hold?  (count newlines, stop at the last frame boundary)
+            count_frames();
+            ts.t_count += now_s() - t0; t0 = now_s();
         }
         if (nframes == 0) {
-            if (eof) break;                                               // truncated file: error 84 below
+            if (ts.eof) break;                                            // truncated file: the caller reports error 84
             continue;                                                     // frame larger than the buffer so far: read more
         }
-        t_count += now_s() - t0; t0 = now_s();
-        // 3. frame 1: header lines serially
-        if (steps_read == 0) {
+        // 3. very first frame of the file: header lines serially
+        if (ts.frames_done == 0) {
             const char *p = buf.data();
             for (int h = 0; h < header; ++h) {
                 const char *q = (const char *)memchr(p, '\n', end - (size_t)(p - buf.data()));
@@ -423,6 +445,7 @@ bool load_trajectory(Run &r)
         {
             std::vector<std::thread> th;
             const int step0 = steps_read;
+            const bool file_start = ts.frames_done == 0;
             for (unsigned t = 0; t < nthreads; ++t)
                 th.emplace_back([&, t] {
                     long long ln = first_line[t];
@@ -431,21 +454,37 @@ bool load_trajectory(Run &r)
                         if (!q) break;
                         const long long in_frame = ln % lines_per_frame;
                         const int step = step0 + (int)(ln / lines_per_frame);
-                        if (in_frame >= header) parse_atom_line(p, step, in_frame - header, step == 0);
+                        if (in_frame >= header) parse_atom_line(p, step, in_frame - header, file_start && step == 0);
                         p = q + 1;
                     }
                 });
             for (auto &x : th) x.join();
         }
-        t_parse += now_s() - t0;
+        ts.t_parse += now_s() - t0;
         steps_read += nframes;
+        ts.frames_done += nframes;
         // 5. keep the unparsed tail
-        memmove(buf.data(), buf.data() + end, have - end);
-        have -= end;
+        memmove(buf.data(), buf.data() + end, ts.have - end);
+        ts.have -= end;
     }
-    fclose(f);
-    if (dbg_t) fprintf(stderr, "[prealpha_b200] ingestion: read %.3f s, frame cut %.3f s, parse %.3f s\n", t_read, t_count, t_parse);
-    if (steps_read < r.nsteps) {                                  // Molecular:5003-5009, error 84
+    return steps_read;
+}
+
+// sequential_read F: the whole trajectory; sequential_read T: frame 1 only (elements, masses, box) -- the analyses
+// then stream the file themselves (perform_distribution_streaming).
+bool load_trajectory(Run &r)
+{
+    TrajStream ts;
+    if (!open_stream(r, ts)) return false;
+    const auto t_load0 = std::chrono::steady_clock::now();
+    const bool lmp = (r.traj_type == "lmp");
+    long long natoms_total = 0;
+    const int want = r.stream ? std::min(r.nsteps, 1) : r.nsteps;
+    std::vector<float *> dst;
+    for (auto &t : r.types) { natoms_total += (long long)t.natoms * t.nmol; t.xyz.assign((size_t)want * t.natoms * t.nmol * 3, 0.f); dst.push_back(t.xyz.data()); }
+    const int steps_read = read_frames(r, ts, want, dst);
+    if (getenv("PA_DEBUG_TIMING")) fprintf(stderr, "[prealpha_b200] ingestion: read %.3f s, frame cut %.3f s, parse %.3f s\n", ts.t_read, ts.t_count, ts.t_parse);
+    if (steps_read < want) {                                      // Molecular:5003-5009, error 84
         r.error(84, "trajectory is shorter than specified; using " + std::to_string(steps_read) + " steps");
         // re-pack is not needed: arrays are [step][mol][atom][3], truncation just drops the tail
         for (auto &t : r.types) t.xyz.resize((size_t)steps_read * t.natoms * t.nmol * 3);
@@ -479,7 +518,7 @@ bool load_trajectory(Run &r)
     if (r.verbose) {
         const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_load0).count();
         printf(" reading the trajectory...done (%d steps of %lld atoms in %.3f s: %.1f million atoms/s on the host threads).\n",
-               r.nsteps, natoms_total, sec, sec > 0 ? (double)r.nsteps * (double)natoms_total / sec * 1e-6 : 0.0);
+               steps_read, natoms_total, sec, sec > 0 ? (double)steps_read * (double)natoms_total / sec * 1e-6 : 0.0);
     }
     return true;
 }
@@ -675,6 +714,66 @@ void make_traj(Run &r, std::vector<pa_type> &types, pa_traj &t)
     t.wrap_trajectory = r.wrap ? 1 : 0;
 }
 
+// sequential_read T: the trajectory never sits in host memory as a whole.  Batches of frames are parsed from the file
+// (read_frames) into a staging array, handed to a session (pinned copy + cudaMemcpyAsync on its copy stream) and
+// evaluated while the host threads already parse the next batch; the sampled frames of a batch are picked by the
+// stride of pa_session_upload.  The kernel ladder of pa_distribution_histogram_multi (cells -> brute force ->
+// general kernel when a sticky device flag asks for it) is repeated here by re-reading the file.
+int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, std::vector<int64_t *> &hp,
+                        std::vector<int64_t> &within, std::vector<int64_t> &oob, pa_stats *st)
+{
+    const int dt = jobs[0].sampling_interval;
+    long long floats_per_frame = 0;
+    for (auto &t : r.types) floats_per_frame += (long long)t.natoms * t.nmol * 3;
+    int B = (int)std::max<long long>(1, std::min<long long>(256, ((long long)256 << 20) / std::max<long long>(1, floats_per_frame * 4)));
+    if (const char *e = getenv("PA_STREAM_BATCH")) B = std::max(1, std::min(256, atoi(e)));      // test hook: frames per batch
+    pa_exec ex = r.exec;
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        TrajStream ts;
+        if (!open_stream(r, ts)) return PA_ERR_IO;
+        pa_session *s = nullptr;
+        int rc = pa_session_create(&meta, jobs.data(), (int)jobs.size(), &ex, (B + dt - 1) / dt, &s);
+        if (rc) return rc;
+        std::vector<std::vector<float>> batch(r.types.size());
+        std::vector<pa_type> vt(meta.types, meta.types + meta.ntypes);
+        std::vector<float *> dst;
+        for (size_t t = 0; t < r.types.size(); ++t) {
+            batch[t].assign((size_t)B * r.types[t].natoms * r.types[t].nmol * 3, 0.f);
+            dst.push_back(batch[t].data());
+            vt[t].xyz = batch[t].data();
+        }
+        pa_traj view = meta;
+        view.types = vt.data();
+        int g0 = 0;                                               // global index of the first frame of the batch
+        bool short_file = false;
+        while (g0 < r.nsteps && rc == 0) {
+            const int want = std::min(B, r.nsteps - g0);
+            const int n = read_frames(r, ts, want, dst);
+            if (n > 0) {
+                const int first = (dt - g0 % dt) % dt;            // sampled frames are the global multiples of dt (Distribution:718)
+                if (first < n) {
+                    view.nsteps = n;
+                    rc = pa_session_upload(s, &view, first, (n - first + dt - 1) / dt, dt);
+                    if (rc == 0) rc = pa_session_run(s);
+                }
+                g0 += n;
+            }
+            if (n < want) { short_file = true; break; }
+        }
+        if (rc == 0) rc = pa_session_download(s, hp.data(), within.data(), oob.data(), 0);
+        if (st) pa_session_stats(s, st);
+        pa_session_destroy(s);
+        if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_NO_CELLS)) { ex.flags |= PA_EXEC_NO_CELLS; continue; }
+        if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_FORCE_GENERAL)) { ex.flags |= PA_EXEC_FORCE_GENERAL; continue; }
+        if (rc == 0 && short_file) {                              // Molecular:5003-5009
+            r.error(84, "trajectory is shorter than specified; using " + std::to_string(g0) + " steps");
+            r.nsteps = g0;
+        }
+        return rc;
+    }
+    return PA_ERR_UNSUPPORTED;
+}
+
 int perform_distribution(Run &r, const std::string &input_name)     // Distribution:1187-1228
 {
     if (r.nsteps < 11) { r.error(37, "trajectory is too short for the distribution analysis (< 11 steps)"); return 37; }
@@ -709,9 +808,11 @@ int perform_distribution(Run &r, const std::string &input_name)     // Distribut
     std::vector<int64_t> within(jobs.size()), oob(jobs.size());
     pa_stats st{};
     const auto t0 = std::chrono::steady_clock::now();
-    rc = pa_distribution_histogram_multi(&traj, jobs.data(), (int)jobs.size(), &r.exec, hp.data(), within.data(), oob.data(), &st);
+    if (r.stream) rc = histogram_streaming(r, traj, jobs, hp, within, oob, &st);
+    else rc = pa_distribution_histogram_multi(&traj, jobs.data(), (int)jobs.size(), &r.exec, hp.data(), within.data(), oob.data(), &st);
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { r.error(rc, std::string("GPU histogram failed: ") + pa_last_error()); return rc; }
+    traj.nsteps = r.nsteps;                                   // (a streamed file may have turned out shorter: error 84)
     printf("   ### B200 execution (distribution function): %lld frames, %lld pair evaluations, %lld kernel launches\n",
            (long long)st.frames_done, (long long)st.pairs_evaluated, (long long)st.kernel_launches);
     printf("   ### End of accelerated section, took %.3f seconds (kernels %.3f ms)\n", sec, st.kernel_ms);
@@ -1112,7 +1213,19 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
         r.wrap = r.unwrap = false;
     }
     if (r.unwrap && r.read_sequential) { r.error(152, "unwrap_trajectory needs the whole trajectory in RAM"); r.unwrap = false; }
-    if (r.read_sequential) printf(" sequential_read T: frames are streamed in batches anyway; the switch has no effect here.\n");
+    if (r.read_sequential) {
+        // the distribution analysis streams the file batch by batch; the other analyses of this program (distance,
+        // contact_distance) and the wrap / unwrap pre-passes work on the trajectory in RAM
+        r.stream = !r.wrap && !r.unwrap;
+        for (const auto &t : body) {
+            if (t.empty()) continue;
+            if (t[0] == "quit" || t[0] == "exit") break;
+            if (t[0] == "distance" || t[0] == "distances" || t[0] == "distance_simple" || t[0] == "distances_simple" ||
+                t[0] == "contact_distance" || t[0] == "contact_distance_simple") r.stream = false;
+        }
+        printf(r.stream ? " sequential_read T: the distribution analysis streams the trajectory from the file, batch by batch.\n"
+                        : " sequential_read T: this input needs the whole trajectory in RAM; it is loaded once.\n");
+    }
     if (!read_molecular_input(r)) return r.errors;
     if (!load_trajectory(r)) return r.errors;
     if ((r.wrap || r.unwrap) && !r.box_given) { r.error(41, "box volume required for wrapping"); return r.errors; }

@@ -402,8 +402,9 @@ def test_wrap_trajectory_with_cell_sorted_kernels(outside, wrap):
         assert wrap or int(cells[1].sum()) > 0
 
 
-@pytest.mark.parametrize("name", ["synth", "lmp", "lmp_wrap", "lmp_unwrap", "charge_arm"])
-def test_cli_drop_in_end_to_end(name, oracle, tmp_path):
+@pytest.mark.parametrize("name,stream", [("synth", False), ("lmp", False), ("lmp_wrap", False), ("lmp_unwrap", False), ("charge_arm", False),
+                                         ("synth", True), ("lmp", True), ("charge_arm", True)])
+def test_cli_drop_in_end_to_end(name, stream, oracle, tmp_path):
     """general.inp -> molecular.inp -> xyz / lmp text -> GPU -> output files: byte-identical to what the
     reference binary wrote for the same inputs (tests/golden), same `within bin` / `out of bounds` lines."""
     fx = fixtures.Fixture(name)
@@ -422,16 +423,20 @@ def test_cli_drop_in_end_to_end(name, oracle, tmp_path):
             f" {ti + 1} {ai + 1} {float(v)!r}\n" for ti, q in enumerate(fx.atom_charges) for ai, v in enumerate(q))
     (wd / "molecular.inp").write_text(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + charges + "quit\n")
     switch = " wrap_trajectory T\n" if fx.wrap else (" unwrap_trajectory T\n" if fx.unwrap else "")
-    gen = f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n{box_line}{switch} sequential_read F\n set_threads 8\n'
+    gen = f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n{box_line}{switch} sequential_read {"T" if stream else "F"}\n set_threads 8\n'
     for jn, text in zip(fx.job_names, fx.job_texts):
         (wd / f"{jn}.inp").write_text(text)
         gen += f' set_prefix "{jn}_"\n distribution "{jn}.inp"\n'
     gen += " gyradius -1 1 1\n quit\n"
     (wd / "general.inp").write_text(gen)
     cli = os.path.join(os.path.dirname(capi.LIB_PATH), "prealpha_b200_cli")
-    p = subprocess.run([cli, "general.inp"], cwd=wd, capture_output=True, timeout=600)
+    env = dict(os.environ)
+    if stream:
+        env["PA_STREAM_BATCH"] = "3"          # sequential_read T: stream the file three frames at a time
+    p = subprocess.run([cli, "general.inp"], cwd=wd, capture_output=True, timeout=600, env=env)
     out = p.stdout.decode()
     assert p.returncode == 0, out[-3000:] + p.stderr.decode()[-2000:]
+    assert ("streams the trajectory from the file" in out) == stream
     counts = oracle.parse_within(out)
     assert counts == fx.counts
     produced = {fn: (wd / "out" / fn).read_bytes() for fn in os.listdir(wd / "out")}
