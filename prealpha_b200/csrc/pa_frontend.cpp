@@ -726,6 +726,7 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
     long long floats_per_frame = 0;
     for (auto &t : r.types) floats_per_frame += (long long)t.natoms * t.nmol * 3;
     int B = (int)std::max<long long>(1, std::min<long long>(256, ((long long)256 << 20) / std::max<long long>(1, floats_per_frame * 4)));
+    B = (int)std::min<long long>(B, std::max<long long>(1, ((long long)r.nsteps + 7) / 8));       // at least ~8 batches: parsing overlaps the kernels
     if (const char *e = getenv("PA_STREAM_BATCH")) B = std::max(1, std::min(256, atoi(e)));      // test hook: frames per batch
     pa_exec ex = r.exec;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -1176,6 +1177,11 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
     if (exec) r.exec = *exec;
     if (r.exec.shard_count < 1) r.exec.shard_count = 1;
     r.general_path = general_inp_path;
+    // CUDA context creation and the load of the kernel image take ~1 s in a fresh process: start them now, on a helper
+    // thread, so that they overlap with reading the input files and the trajectory instead of delaying the first analysis
+    const int warm_device = r.exec.device;
+    std::thread warm([warm_device] { if (pa_device_count() > 0 && cudaSetDevice(warm_device) == cudaSuccess) { cudaFree(nullptr); pa_kernels_selfcheck(); } });
+    struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } warm_joiner{ warm };
     std::vector<std::string> lines;
     if (!read_lines(r.general_path, lines)) { r.error(5, "general input file '" + r.general_path + "' not found"); return r.errors; }
     std::vector<std::vector<std::string>> toks;        // non-blank records, list-directed READ skips blank ones
