@@ -265,3 +265,57 @@ def test_fast_coordinate_parser_equals_strtof():
         assert got.tobytes() == exp.tobytes() or (np.isnan(got) and np.isnan(exp)), (s, got, exp)
         assert n.value == consumed, (s, n.value, consumed)
     assert len(cases) > 40000
+
+
+def _run_general_inp(workdir):
+    """pa_run_general_input in a subprocess (its report goes to the C stdout); returns (error count, stdout)."""
+    import subprocess, sys
+    code = ("import sys, ctypes as C; sys.path.insert(0, %r); from prealpha_b200 import capi, api; "
+            "rc = capi.load().pa_run_general_input(b'general.inp', C.byref(api.make_exec())); print('RC', rc)" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], cwd=workdir, capture_output=True, timeout=300)
+    out = p.stdout.decode()
+    assert p.returncode == 0, out + p.stderr.decode()
+    return int(out.rsplit("RC", 1)[1]), out
+
+
+def _write_small_case(wd, nsteps_declared=12, nsteps_written=12, natoms_line=None, body=""):
+    rng = np.random.default_rng(3)
+    n = 24
+    with open(wd / "traj.xyz", "w") as f:
+        for s in range(nsteps_written):
+            f.write(f"{natoms_line if natoms_line is not None else n}\nstep {s}\n")
+            for a in range(n):
+                x = rng.random(3) * 12.0
+                f.write(f"{'Na' if a < 12 else 'Cl'} {x[0]:.4f} {x[1]:.4f} {x[2]:.4f}\n")
+    (wd / "molecular.inp").write_text(f" {nsteps_declared}\n 2\n +1 1 12\n -1 1 12\nquit\n")
+    (wd / "general.inp").write_text(' "traj.xyz"\n "molecular.inp"\n "./"\n "./"\n "./"\n cubic_box_edge 0.0 12.0\n trajectory_type xyz\n'
+                                    ' sequential_read F\n' + body + " quit\n")
+
+
+def test_general_inp_host_logic_without_gpu(tmp_path):
+    """The drop-in front end up to the point where a kernel would be needed: header, switches, molecular.inp, threaded
+    trajectory reader, keyword dispatch and the reference's warning counter -- all host code, so it runs here."""
+    wd = tmp_path / "ok"; wd.mkdir()
+    _write_small_case(wd, body=" set_prefix test_\n gyradius -1 1 1\n this_keyword_does_not_exist 1\n #comment\n")
+    rc, out = _run_general_inp(wd)
+    assert "reading the trajectory...done (12 steps of 24 atoms" in out
+    assert "belongs to a prealpha module outside the accelerated path" in out          # gyradius
+    assert "ERROR 20" in out and rc == 1 and "Encountered 1 errors/warnings globally." in out
+    # fewer steps in the file than molecular.inp declares: error 84, the shorter trajectory is used (Molecular:5003-5009)
+    wd = tmp_path / "short"; wd.mkdir()
+    _write_small_case(wd, nsteps_declared=15, nsteps_written=12)
+    rc, out = _run_general_inp(wd)
+    assert "ERROR 84" in out and "using 12 steps" in out and rc == 1
+    # atom count of the trajectory header differs from molecular.inp: error 10
+    wd = tmp_path / "natoms"; wd.mkdir()
+    _write_small_case(wd, natoms_line=25)
+    rc, out = _run_general_inp(wd)
+    assert "ERROR 10" in out
+    # a compute keyword without a GPU must fail loudly (and only then), never fall back
+    if api.device_count() == 0:
+        wd = tmp_path / "compute"; wd.mkdir()
+        (wd / "rdf.inp").write_text("pdf 1\n+0 +0 +1 1 2\nmaxdist_optimize\nsampling_interval 1\nbin_count_a 10\nbin_count_b 1\nquit\n")
+        _write_small_case(wd, body=' distribution "rdf.inp"\n')
+        rc, out = _run_general_inp(wd)
+        assert "GPU histogram failed" in out and "no CPU fallback" in out and rc >= 1
+        assert not any(f.startswith("reference_") for f in os.listdir(wd))
