@@ -356,10 +356,10 @@ def main():
                                  "see profiles/README.md. HBM is not the bound: 12 B per atom per frame.",
                          # second bound named by the north star: shared-memory atomics.  Every pair the kernels evaluate after cell
                          # pruning issues one ATOMS.POPC.INC: 4.50e11 per 1M-atom frame (ncu, smsp__inst_executed_op_shared_atom x 32
-                         # summed over the launches of a frame, profiles/r1h_ncu_full_pa_rdf_cells_kernel.csv); peak = the r^2-distributed
-                         # 1000-bin histogram microbenchmark, profiles/microbench_r1.json
-                         "smem_atomics": ({"achieved": 4.50e11 * K / (kernel_ms * 1e-3), "peak": 4.2e12, "unit": "atomics/s",
-                                           "frac": 4.50e11 * K / (kernel_ms * 1e-3) / 4.2e12} if n_half == N_PER_TYPE else None),
+                         # summed over the launches of a frame, profiles/r1h_ncu_full_pa_rdf_cells_kernel.csv); peak = warp-wide
+                         # red.shared.add.u32 to 32 different counters of a 128-class window, profiles/microbench2_r1.json
+                         "smem_atomics": ({"achieved": 4.50e11 * K / (kernel_ms * 1e-3), "peak": 2.2e12, "unit": "atomics/s",
+                                           "frac": 4.50e11 * K / (kernel_ms * 1e-3) / 2.2e12} if n_half == N_PER_TYPE else None),
                          "kernel_ms_per_step": kernel_ms / K,
                          "hbm_gbs_frame_streaming": (natoms * 12 * K) / (kernel_ms * 1e-3) / 1e9},
             "clocks": clocks,

@@ -104,6 +104,38 @@ __global__ void k_mix_packed(float *out, float a, float b)
     out[blockIdx.x * blockDim.x + threadIdx.x] = __uint_as_float(acc);
 }
 
+
+// Shared-memory atomics of the pair kernels: the 32 lanes of a warp hit ~32 different counters inside a window of 128
+// classes (one observed molecule against 32 reference molecules).  LAYOUT 0: counters at a 4-byte stride as in
+// pa_cells.cu (different classes collide in a bank: ~3 wavefronts per ATOMS); LAYOUT 1: one counter per class AND lane
+// ([class][32], 128 KB for 1000 classes): every lane its own bank, one wavefront per instruction.  Same index stream.
+constexpr int ITERS_A = 4096;
+template <int LAYOUT>
+__global__ void k_atoms_layout(unsigned int *out, int nbins, int window, unsigned int seed)
+{
+    extern __shared__ unsigned int h[];
+    const int nwords = LAYOUT ? nbins * 32 : nbins;
+    for (int k = threadIdx.x; k < nwords; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    unsigned int s = seed ^ (blockIdx.x * 9781u + threadIdx.x * 6271u + 1u);
+    unsigned int sw = seed ^ (blockIdx.x * 7919u + (threadIdx.x >> 5) * 104729u + 7u);      // warp-uniform stream: window position
+    const int lane = threadIdx.x & 31;
+    unsigned int acc = 0;
+    for (int it = 0; it < ITERS_A; ++it) {
+        sw = sw * 1664525u + 1013904223u;
+        const int base = (int)(((unsigned long long)(sw >> 8) * (unsigned)(nbins - window)) >> 24);   // warp-uniform window position (cheap)
+        s = s * 1664525u + 1013904223u;
+        const int bin = base + (int)((s >> 8) & (unsigned)(window - 1));                              // window must be a power of two
+        const unsigned int addr = LAYOUT ? (unsigned)(bin * 32 + lane) : (unsigned)bin;
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(h + addr)) : "memory");
+        acc += bin;
+    }
+    __syncthreads();
+    unsigned int t = acc;
+    for (int k = threadIdx.x; k < nwords; k += blockDim.x) t += h[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
 template <typename F>
 static double time_ms(F launch, int reps = 5)
 {
@@ -140,7 +172,15 @@ int main(int argc, char **argv)
     const double npairs = (double)threads * blocks * ITERS * 4.0;
     const double t_ms = time_ms([&] { k_mix_scalar<<<blocks, threads>>>(fout, 7.37f, 7.38f); });
     const double t_mp = time_ms([&] { k_mix_packed<<<blocks, threads>>>(fout, 7.37f, 7.38f); });
+    // shared atomics: 128-thread CTAs; layout 0 at the occupancy of the pair kernel (6 CTAs/SM), layout 1 with one 128 KB
+    // histogram per SM shared by a 1024-thread CTA
+    unsigned int *uout; CK(cudaMalloc(&uout, sizeof(unsigned int) * 1024 * sms * 8));
+    CK(cudaFuncSetAttribute(k_atoms_layout<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 1000 * 32 * 4));
+    const double t_a0 = time_ms([&] { k_atoms_layout<0><<<sms * 6, 128, 1000 * 4>>>(uout, 1000, 128, 12345u); });
+    const double t_a1 = time_ms([&] { k_atoms_layout<1><<<sms, 768, 1000 * 32 * 4>>>(uout, 1000, 128, 12345u); });
+    const double n_a0 = (double)sms * 6 * 128 * ITERS_A, n_a1 = (double)sms * 768 * ITERS_A;
     printf("{\"gpu\": \"%s\", \"sms\": %d,\n", p.name, sms);
+    printf(" \"smem_atomics_4byte_stride_per_s\": %.4e, \"smem_atomics_lane_private_banks_per_s\": %.4e,\n", n_a0 / (t_a0 * 1e-3), n_a1 / (t_a1 * 1e-3));
     printf(" \"ffma_inst_per_s\": %.4e, \"ffma_rm_inst_per_s\": %.4e,\n", n / (t_ffma * 1e-3), n / (t_frm * 1e-3));
     printf(" \"ffma2_inst_per_s\": %.4e, \"ffma2_rm_inst_per_s\": %.4e, \"fadd2_inst_per_s\": %.4e,\n", n / (t_p0 * 1e-3), n / (t_p1 * 1e-3), n / (t_p2 * 1e-3));
     printf(" \"ffma2_with_1_lop3_inst_per_s\": %.4e, \"ffma2_with_2_lop3_inst_per_s\": %.4e, \"ffma2_with_1_imad_inst_per_s\": %.4e,\n",
