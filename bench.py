@@ -189,7 +189,7 @@ def run_reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "binned pairs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",     # results are defined by the reference's fp64 arithmetic; float32 only brackets the class
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",     # the reference computes in fp64 (27 images per pair)
         "config": {"workload": f"synthetic cubic box (same generator and density as the 1M-atom case), {2 * n_half} atoms x {frames} frames, "
                                "references 1 -1 and 2 -1, maxdist_optimize, 1000x1 bins; brute force, cost per pair independent of N"},
         "pair_evals_per_s": sum(r["pair_evals_per_s"] * r["seconds"] for r in res) / sec,
@@ -205,13 +205,44 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------
+def _traffic_from_profiles():
+    """dram bytes (read + write) per launch of the dominant kernel, from the committed ncu --set full capture of THIS
+    round's kernels (profiles/r2_traffic.json, written by tools/ncu_summary.py); None when no capture is committed."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_per_launch"]), t.get("source")
+    except Exception:
+        return None, None
+
+
+def make_c5(natoms: int, maxdist: float):
+    """BASELINE config 5: one 4M-atom frame, 200x90 distance-angle histogram (`pdf` with 90 angle bins)."""
+    from prealpha_b200 import api, capi
+    L = round((natoms / 0.05) ** (1.0 / 3.0), 3)
+    g = np.random.Generator(np.random.Philox(key=[12345, 5_000_000]))
+    frame = np.round(g.random((natoms, 3)) * L, 5).astype(np.float32)
+    half = natoms // 2
+    lo, hi = capi.cubic_box_edge(0.0, L)
+    types = [dict(charge=+1, natoms=1, nmol=half, elements=["Na"], xyz=frame[:half].reshape(1, half, 1, 3)),
+             dict(charge=-1, natoms=1, nmol=half, elements=["Cl"], xyz=frame[half:].reshape(1, half, 1, 3))]
+    traj = capi.Trajectory(types, lo, hi, xyz_format=True)
+    jobs = [api.job_setup(traj, capi.make_request(mode="pdf", vec=(0, 0, 1), ref_type=1, obs_type=-1, bin_a=200, bin_b=90,
+                                                  maxdist=maxdist, sampling_interval=1))]
+    return traj, jobs, L
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
+    ap.add_argument("--config", default="c4", choices=["c4", "c5"],
+                    help="c4 (default, the BASELINE metric): 1M-atom RDF, one frame per GPU per step (weak scaling over frames); "
+                         "c5: ONE 4M-atom frame, 200x90 distance-angle histogram, tile shards over the GPUs (strong scaling)")
     ap.add_argument("--atoms-per-type", type=int, default=N_PER_TYPE, help="debug: smaller box (not a valid bench line)")
+    ap.add_argument("--c5-maxdist", type=float, default=40.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--flags", type=int, default=0)
     args = ap.parse_args()
@@ -233,14 +264,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     W, K = max(args.warmup, 3), args.steps
-    n_half = args.atoms_per_type
-    natoms = 2 * n_half
-    L = float(L_BOX) if n_half == N_PER_TYPE else round((natoms / 0.05) ** (1.0 / 3.0), 4)
-    # frames: step s of rank r is global frame s*world + r (frames sharded round-robin over the GPUs)
-    frames = np.stack([synth_frame(s * world + rank, natoms, L) for s in range(W + K)])
-    traj = make_traj(frames, n_half, L)
-    jobs = make_jobs(traj)
-    ex = api.make_exec(device=local, flags=args.flags)
+    c5 = args.config == "c5"
 
     def barrier():
         torch.cuda.synchronize()
@@ -248,27 +272,52 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident arm (`value`): all W+K frames uploaded before the timed region -------------
-    sess = api.Session(traj, jobs, max_frames=W + K, exec_=ex)
-    sess.upload(traj, 0, W + K)
-    flush = torch.empty(512 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")    # > 126 MB L2
+    if c5:
+        # strong scaling: every rank holds the SAME frame and takes tile shard `rank` of `world` (pa_exec.tile_shard_*)
+        natoms = 4_000_000 if args.atoms_per_type == N_PER_TYPE else 2 * args.atoms_per_type
+        traj1, jobs, L = make_c5(natoms, args.c5_maxdist)
+        n_half = natoms // 2
+        frames_of = lambda s: 0                                   # noqa: E731  (one resident frame, re-run every step)
+        nres = 1
+        traj = traj1
+        ex = api.make_exec(device=local, flags=args.flags, tile_shard_rank=rank, tile_shard_count=world)
+    else:
+        n_half = args.atoms_per_type
+        natoms = 2 * n_half
+        L = float(L_BOX) if n_half == N_PER_TYPE else round((natoms / 0.05) ** (1.0 / 3.0), 4)
+        # frames: step s of rank r is global frame s*world + r (frames sharded round-robin over the GPUs)
+        frames = np.stack([synth_frame(s * world + rank, natoms, L) for s in range(W + K)])
+        traj = make_traj(frames, n_half, L)
+        jobs = make_jobs(traj)
+        frames_of = lambda s: s                                   # noqa: E731
+        nres = W + K
+        ex = api.make_exec(device=local, flags=args.flags)
+
+    # ---- device-resident arm (`value`): all frames uploaded before the timed region -------------------
+    sess = api.Session(traj, jobs, max_frames=nres, exec_=ex)
+    sess.upload(traj, 0, nres)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")    # 256 MB > 126 MB of L2
     for s in range(W):
-        sess.run(s, 1)
+        flush.zero_()                      # also warms torch's fill kernel: no cold launch inside the timed region
+        torch.cuda.synchronize()
+        sess.run(frames_of(s), 1)
     sess.download(reset=True)
     st0 = sess.stats()
     fp64_rate = api.fp64_issue_rate(local)
+    atomic_rate = api.smem_atomic_rate(local)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    flush.zero_()
     barrier()
     t0 = time.perf_counter()
     step_marks = []
     for s in range(K):
-        flush.zero_()                      # L2 flush between timed iterations (torch stream)
+        flush.zero_()                      # L2 flush between timed iterations (0.04 ms of HBM writes on torch's stream)
         torch.cuda.synchronize()
         step_marks.append(time.perf_counter() - t0)
-        sess.run(W + s, 1)                 # prepare + pair kernels on the session's compute stream
+        sess.run(frames_of(W + s), 1)      # prepare + sort + pair kernels on the session's compute stream
     ptr, nwords = sess.device_accumulators()   # synchronises the compute stream
     step_marks.append(time.perf_counter() - t0)
     if world > 1:
@@ -280,36 +329,56 @@ def main():
     t_value = time.perf_counter() - t0
     if rank == 0:
         print("[bench] value arm: step boundaries (s) " + " ".join(f"{m:.3f}" for m in step_marks) + f" end {t_value:.3f}", file=sys.stderr)
+        gaps = np.diff(step_marks)
+        if len(gaps) > 2 and gaps[0] > 1.5 * np.median(gaps[1:]):
+            print(f"[bench] WARNING: first timed step took {gaps[0]:.3f} s against a median of {np.median(gaps[1:]):.3f} s", file=sys.stderr)
     clocks = sampler.stop() if rank == 0 else None
     hists, within, oob = sess.download()
     st1 = sess.stats()
-    kernel_ms = st1.kernel_ms - st0.kernel_ms
-    launches = st1.kernel_launches - st0.kernel_launches
-    pair_evals_rank = st1.pairs_evaluated - st0.pairs_evaluated
     sess.close()
-    # local (pre-reduce) binned count of this rank: rank 0 holds the reduced sum when world > 1
-    tv = torch.tensor([t_value, kernel_ms], dtype=torch.float64, device="cuda")
-    pe = torch.tensor([float(pair_evals_rank)], dtype=torch.float64, device="cuda")
+    d = lambda name: getattr(st1, name) - getattr(st0, name)      # noqa: E731
+    kernel_ms, launches, pair_evals_rank = d("kernel_ms"), d("kernel_launches"), d("pairs_evaluated")
+    tv = torch.tensor([t_value, kernel_ms, d("dominant_ms")], dtype=torch.float64, device="cuda")
+    pe = torch.tensor([float(pair_evals_rank), float(d("cell_pair_evals")), float(d("smem_atomics")), float(d("unique_pairs_counted")),
+                       float(d("dominant_pair_evals")), float(d("dominant_atomics")), float(d("dominant_launches")), float(launches)],
+                      dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tv, op=dist.ReduceOp.MAX)
         dist.all_reduce(pe, op=dist.ReduceOp.SUM)
-    t_value_max, kernel_ms_max = float(tv[0]), float(tv[1])
+    t_value_max, kernel_ms_max, dominant_ms_max = (float(x) for x in tv)
     binned_total = int(within.sum())           # rank 0: whole job (after the reduce)
     pair_evals_total = float(pe[0])
 
     # ---- end-to-end arm: host buffers through the C ABI, H2D/D2H inside the timed region --------------
-    e2e_traj = make_traj(frames[W:], n_half, L)
-    e2e_jobs = make_jobs(e2e_traj)
-    api.histogram_multi(make_traj(frames[:1], n_half, L), e2e_jobs, api.make_exec(device=local, frames_per_batch=1, flags=args.flags))  # warm
+    if c5:
+        e2e_traj, e2e_jobs, e2e_steps = traj, jobs, K
+    else:
+        e2e_traj = make_traj(frames[W:], n_half, L)
+        e2e_jobs = make_jobs(e2e_traj)
+        e2e_steps = 1
+    mk = lambda: api.make_exec(device=local, frames_per_batch=1, flags=args.flags,                       # noqa: E731
+                               tile_shard_rank=rank if c5 else 0, tile_shard_count=world if c5 else 1)
+    warm_traj = traj if c5 else make_traj(frames[:1], n_half, L)
+    api.histogram_multi(warm_traj, e2e_jobs, mk())        # warm: context, module load, page-locked staging (kept in the library's pool)
     barrier()
     t0 = time.perf_counter()
-    h2, w2, o2, st_e = api.histogram_multi(e2e_traj, e2e_jobs, api.make_exec(device=local, frames_per_batch=1, flags=args.flags))
-    if world > 1:
-        acc2 = torch.from_numpy(np.concatenate([np.concatenate([h2[k], w2[k:k + 1], o2[k:k + 1]]) for k in range(len(e2e_jobs))])).cuda()
-        dist.reduce(acc2, dst=0, op=dist.ReduceOp.SUM)
-        w2_total = int(acc2.cpu().numpy().reshape(len(e2e_jobs), -1)[:, BINS].sum())
-    else:
-        w2_total = int(w2.sum())
+    h2d = d2h = 0
+    w2_total = 0
+    for _ in range(e2e_steps):
+        h2, w2, o2, st_e = api.histogram_multi(e2e_traj, e2e_jobs, mk())
+        h2d += st_e.h2d_bytes
+        d2h += st_e.d2h_bytes
+        if world > 1:
+            acc2 = torch.from_numpy(np.concatenate([np.concatenate([h2[k], w2[k:k + 1], o2[k:k + 1]]) for k in range(len(e2e_jobs))])).cuda()
+            dist.reduce(acc2, dst=0, op=dist.ReduceOp.SUM)
+            nb = [int(j.bin_a) * int(j.bin_b) for j in e2e_jobs]
+            flat = acc2.cpu().numpy()
+            off = 0
+            for k in range(len(e2e_jobs)):
+                w2_total += int(flat[off + nb[k]])
+                off += nb[k] + 2
+        else:
+            w2_total += int(w2.sum())
     barrier()
     t_e2e = time.perf_counter() - t0
     te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
@@ -322,46 +391,76 @@ def main():
         assert w2_total == binned_total, (w2_total, binned_total)
         # size-independent property of the synthetic workload: uniform points, cutoff L/2 -> the binned fraction of all
         # ordered pairs is the sphere / cube volume ratio pi/6 (statistical scatter ~1e-6 at 1e12 pairs per frame)
-        if n_half == N_PER_TYPE:
+        if not c5 and n_half == N_PER_TYPE:
             frac_binned = binned_total / pair_evals_total
             assert abs(frac_binned - np.pi / 6.0) < 1.0e-4, f"binned fraction {frac_binned} is not pi/6: counts are wrong"
+        if c5:
+            # uniform points, cutoff sphere inside the box: binned fraction = (4/3) pi r^3 / L^3 (up to the ~1e-5 of pairs
+            # whose link is (anti)parallel to the axis)
+            expect = 4.0 / 3.0 * np.pi * args.c5_maxdist ** 3 / L ** 3
+            frac_binned = binned_total / pair_evals_total
+            assert abs(frac_binned / expect - 1.0) < 2.0e-3, (frac_binned, expect)
         value = binned_total / t_value_max
-        pe_per_s = pair_evals_total / t_value_max
-        # dominant kernel: pa_rdf_cells_kernel<0,*,*,1> (float32 launch of the cell-sorted RDF kernel; 3 launches per step:
-        # two symmetric same-type passes and the merged cross-type pass), 95 % of the GPU time (profiles/r1h_launches_bench_1M.csv)
-        pair_evals_per_s_kernel = pair_evals_rank / (kernel_ms * 1e-3)
-        achieved = pair_evals_per_s_kernel * FP64_OPS_PER_PAIR
+        cell_evals, atomics, unique, dom_evals, dom_atomics, dom_launches, launches_all = (float(x) for x in pe[1:])
+        traffic, traffic_src = _traffic_from_profiles()
+        if c5:
+            # general cell-sorted kernel: latency / issue bound; reported against the FP64 issue rate of the
+            # literal per-binned-pair evaluation is not meaningful, so the line carries the pair-evaluation rate only
+            roofline = {"bound": "issue", "achieved": cell_evals / (kernel_ms_max * 1e-3) if cell_evals else None,
+                        "peak": None, "unit": "pair evaluations/s", "frac": None, "traffic": None,
+                        "kernel_ms_per_step": kernel_ms_max / K,
+                        "note": "pa_general_cells_kernel: drain-latency bound (ncu: issue slots ~50 % busy); no hardware peak is claimed for it"}
+        else:
+            # dominant kernel: pa_rdf_cells_kernel<0,*,*,1> (float32 launch of the cell-sorted RDF kernel; 3 launches per step:
+            # two symmetric same-type passes and the merged cross-type pass).  Its binding resource is the shared-memory
+            # atomic unit (one ATOMS.POPC.INC per evaluated pair of a live iteration): both the atomics and the peak are
+            # measured in THIS run -- the kernels count their own atomics (pa_stats.dominant_atomics) and the time of
+            # exactly those launches is taken with CUDA events on their stream (pa_stats.dominant_ms).
+            dom_s = dominant_ms_max * 1e-3
+            roofline = {
+                "bound": "smem_atomics", "kernel": "pa_rdf_cells_kernel<0,*,*,1> (float32 launch)",
+                "achieved": dom_atomics / world / dom_s if dom_s else None, "peak": atomic_rate, "unit": "atomics/s",
+                "frac": (dom_atomics / world / dom_s / atomic_rate) if dom_s else None,
+                "useful_frac": (unique / world / (kernel_ms_max * 1e-3) / atomic_rate),
+                "traffic": traffic, "traffic_source": traffic_src,
+                "ms_per_launch": dominant_ms_max * world / dom_launches if dom_launches else None,
+                "launches_per_step": dom_launches / world / K, "share_of_kernel_time": dominant_ms_max / kernel_ms_max,
+                "atomics_per_step_per_gpu": atomics / world / K, "pair_evals_after_pruning_per_step_per_gpu": cell_evals / world / K,
+                "unique_pairs_counted_per_step_per_gpu": unique / world / K,
+                "kernel_ms_per_step": kernel_ms_max / K,
+                "algorithmic_fp64_frac": pair_evals_rank / (kernel_ms * 1e-3) * FP64_OPS_PER_PAIR / fp64_rate,
+                "fp64_issue_rate_measured": fp64_rate,
+                "hbm_gbs_frame_streaming": (natoms * 12 * K) / (kernel_ms_max * 1e-3) / 1e9,
+                "note": "frac = shared-memory atomics issued by the float32 launches (counted by the kernel itself) / CUDA-event "
+                        "time of those launches / live-measured rate of warp-wide red.shared.add.u32 to 32 different counters "
+                        "(pa_debug_smem_atomic_rate, same kernel as pa_microbench2). useful_frac = pairs that landed in a bin, "
+                        "each evaluated once, / total pair-kernel time / the same peak. algorithmic_fp64_frac = SURVEY 8d's 26 "
+                        "FP64-pipe instructions x ordered reference pairs / kernel time / measured DSUB-DMUL issue rate: > 1 "
+                        "because cells prune, symmetric pairs are evaluated once and the class is bracketed in packed float32 "
+                        "(exact fp64 only for ~1e-3 of the pairs) -- a bookkeeping figure, not a hardware fraction. HBM is not "
+                        "the bound: 12 B per atom per frame.",
+            }
         line = {
-            "metric": METRIC, "value": value, "unit": "binned pairs/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": 1e3 * t_value_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",     # results are defined by the reference's fp64 arithmetic; float32 only brackets the class
-            "config": {"workload": f"synthetic cubic box, {natoms} atoms (2 one-atom types), L={L} A, 1 frame per GPU per step, "
-                                   f"references 1 -1 and 2 -1 (all ordered pairs), maxdist_optimize, {BINS}x1 bins",
-                       "pair_evals_per_step_per_gpu": pair_evals_rank / K, "frames_sharding": "frame s*N+r on GPU r, NCCL int64 reduce once",
-                       "l2": "512 MB flush between timed steps; every step works on a different resident frame"},
-            "pair_evals_per_s": pe_per_s,
-            "e2e": {"value": binned_total / t_e2e_max, "unit": "binned pairs/s", "h2d_bytes_per_step": int(st_e.h2d_bytes // K),
-                    "d2h_bytes_per_step": int(st_e.d2h_bytes // K), "ms_per_step": 1e3 * t_e2e_max / K},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "achieved": achieved / 1e9, "peak": fp64_rate / 1e9, "unit": "Ginst/s",
-                         "frac": achieved / fp64_rate,
-                         # dram__bytes_read+write of the merged cross-type launch (500k x 500k molecules) in the ncu --set full
-                         # capture profiles/r1h_ncu_full_pa_rdf_cells_kernel.csv: 24.36 MB + 3 KB = the 24 B per sorted molecule it must read
-                         "traffic": 24.37e6 if n_half == N_PER_TYPE else None,
-                         "note": "algorithmic 26 FP64-pipe instructions per evaluated pair (SURVEY 8d) x pair evaluations / CUDA-event "
-                                 "time of the pair kernels on their stream; peak = DSUB/DMUL issue rate measured live on this GPU "
-                                 "(MEASURED_PEAKS.json has no FP64 entry). frac > 1 because the kernels prune by cells, evaluate "
-                                 "symmetric pairs once and bracket the class in packed float32 (exact fp64 only for ~1e-3 of the pairs); "
-                                 "the launch itself is bound by issue slots (71 %) and shared-memory atomics (68 % of LSU wavefronts), "
-                                 "see profiles/README.md. HBM is not the bound: 12 B per atom per frame.",
-                         # second bound named by the north star: shared-memory atomics.  Every pair the kernels evaluate after cell
-                         # pruning issues one ATOMS.POPC.INC: 4.50e11 per 1M-atom frame (ncu, smsp__inst_executed_op_shared_atom x 32
-                         # summed over the launches of a frame, profiles/r1h_ncu_full_pa_rdf_cells_kernel.csv); peak = warp-wide
-                         # red.shared.add.u32 to 32 different counters of a 128-class window, profiles/microbench2_r1.json
-                         "smem_atomics": ({"achieved": 4.50e11 * K / (kernel_ms * 1e-3), "peak": 2.2e12, "unit": "atomics/s",
-                                           "frac": 4.50e11 * K / (kernel_ms * 1e-3) / 2.2e12} if n_half == N_PER_TYPE else None),
-                         "kernel_ms_per_step": kernel_ms / K,
-                         "hbm_gbs_frame_streaming": (natoms * 12 * K) / (kernel_ms * 1e-3) / 1e9},
+            "metric": METRIC if not c5 else "binned atom-pairs/s, 4M-atom 2-D distance-angle histogram (BASELINE config 5), tile shards over the GPUs",
+            "value": value, "unit": "binned pairs/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": 1e3 * t_value_max / K, "higher_is_better": True, "scaling": "strong" if c5 else "weak", "vs_baseline": None,
+            # results are defined by the reference's fp64 arithmetic; packed float32 only brackets the class
+            "dtype": "f64 (f32-bracketed class, exact f64 fix-up)" if not c5 else "f64", "data": "synthetic",
+            "config": ({"workload": f"synthetic cubic box, {natoms} atoms (2 one-atom types), L={L} A, ONE frame, reference type 1 around all, "
+                                    f"pdf 200x90 bins, maxdist {args.c5_maxdist} A; every GPU holds the frame and takes tile shard r of N "
+                                    "(i-range split), NCCL int64 reduce once",
+                        "l2": "256 MB flush between timed steps"} if c5 else
+                       {"workload": f"synthetic cubic box, {natoms} atoms (2 one-atom types), L={L} A, 1 frame per GPU per step, "
+                                    f"references 1 -1 and 2 -1 (all ordered pairs), maxdist_optimize, {BINS}x1 bins",
+                        "pair_evals_per_step_per_gpu": pair_evals_rank / K, "frames_sharding": "frame s*N+r on GPU r, NCCL int64 reduce once",
+                        "l2": "256 MB flush between timed steps; every step works on a different resident frame"}),
+            "pair_evals_per_s": pair_evals_total / t_value_max,
+            "e2e": {"value": w2_total / t_e2e_max, "unit": "binned pairs/s", "h2d_bytes_per_step": int(h2d // K),
+                    "d2h_bytes_per_step": int(d2h // K), "ms_per_step": 1e3 * t_e2e_max / K,
+                    "note": "pa_distribution_histogram_multi with host buffers: memcpy into page-locked staging, cudaMemcpyAsync, "
+                            "kernels, D2H of the bins; the page-locked buffers come from the library's pool (allocated by the warm-up call)"},
+            "gpu_launches": int(launches_all),
+            "roofline": roofline,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define PA_ABI_VERSION 1
+#define PA_ABI_VERSION 2
 
 /* operation modes, Distribution:343-347 ("cdf|cydf", "pdf|podf") */
 #define PA_MODE_CDF 0
@@ -125,17 +125,33 @@ typedef struct pa_job {
     int32_t normalise_clm;           /* charge_arm only                     */
 } pa_job;
 
-/* How to run: which device, and which shard of the sampled frames this
- * process owns (frames are independent units: Distribution:717-718 runs them
- * SCHEDULE(STATIC,1) over threads; here shard r of n takes sampled frame k
- * when k % n == r).  Histograms of different shards add (integers). */
+/* How to run: which device(s), and which shard of the work this process owns.
+ * Frames are independent units (Distribution:717-718 runs them SCHEDULE(STATIC,1)
+ * over OpenMP threads); here frame shard r of n takes sampled frame k when
+ * k % n == r.  A single huge frame gives that loop no parallelism, so a second,
+ * independent split exists below the frame: tile shard r of n takes the work
+ * items (tile of reference molecules, slab of observed cells) w with w % n == r
+ * (cell-sorted kernels) or the tiles of reference molecules t with t % n == r
+ * (brute-force kernels).  Histograms of different shards add (integers), in
+ * any combination of the two splits.
+ * ndevices > 1 (one-shot entry points and the file-level drop-in): the call
+ * itself drives devices device .. device+ndevices-1 with one host thread each --
+ * the analogue of `set_threads` (Main:3313-3330) for the parallel region
+ * Distribution:704-753 -- sharding frames when there are at least ndevices
+ * sampled frames and tiles otherwise, and combines the int64 accumulators on
+ * `device` with one ncclReduce over NVLink (peer copies + an add kernel when
+ * libnccl cannot be loaded).  ndevices < 0: all usable devices.  The caller's
+ * shard_* / tile_shard_* then describe this process's share of a larger job
+ * and are subdivided further. */
 typedef struct pa_exec {
-    int32_t device;            /* CUDA ordinal                              */
-    int32_t shard_rank;        /* 0..shard_count-1                          */
-    int32_t shard_count;       /* >= 1                                      */
+    int32_t device;            /* CUDA ordinal (first device when ndevices > 1) */
+    int32_t shard_rank;        /* frame shard 0..shard_count-1              */
+    int32_t shard_count;       /* >= 1 (0 is read as 1)                     */
     int32_t frames_per_batch;  /* 0 = choose                                */
     int32_t flags;             /* PA_EXEC_*                                 */
-    int32_t _pad;
+    int32_t tile_shard_rank;   /* tile shard 0..tile_shard_count-1          */
+    int32_t tile_shard_count;  /* >= 1 (0 is read as 1)                     */
+    int32_t ndevices;          /* 0/1: one device; N: N devices; <0: all    */
 } pa_exec;
 
 #define PA_EXEC_FORCE_GENERAL  1   /* use the general (2-D capable) kernel even for RDF jobs */
@@ -153,6 +169,14 @@ typedef struct pa_stats {
     int64_t h2d_bytes, d2h_bytes;
     double  kernel_ms;         /* CUDA-event time of the pair kernels on their stream         */
     double  total_ms;          /* CUDA-event time upload..download                            */
+    /* counted by the cell-sorted RDF kernels themselves (0 when another kernel did the work): */
+    int64_t cell_pair_evals;   /* pair distances actually evaluated after cell pruning, each unordered pair of a
+                                  symmetric / merged pass once                                */
+    int64_t smem_atomics;      /* shared-memory atomic increments issued (lanes)              */
+    int64_t unique_pairs_counted; /* pairs that landed in a bin, each evaluated pair once     */
+    int64_t dominant_launches; /* launches of the float32 cell-sorted RDF kernel (the dominant kernel of large RDF jobs) */
+    double  dominant_ms;       /* CUDA-event time of those launches alone                     */
+    int64_t dominant_pair_evals, dominant_atomics;   /* their share of cell_pair_evals / smem_atomics */
 } pa_stats;
 
 /* ---- library ---------------------------------------------------------- */

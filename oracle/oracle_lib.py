@@ -80,6 +80,17 @@ def histogram(traj: capi.Trajectory, job: capi.pa_job, nthreads=0, shard=(0, 1))
     return hist, w.value, o.value
 
 
+def histogram_frame(traj: capi.Trajectory, job: capi.pa_job, step=0, nthreads=0):
+    """One frame, OpenMP over blocks of reference molecules (same loop body and integers as `histogram`;
+    for frames of the benchmark's size, where the frame loop offers no parallelism)."""
+    hist = np.zeros(job.bin_a * job.bin_b, dtype=np.int64)
+    w, o = C.c_int64(0), C.c_int64(0)
+    rc = load().orc_distribution_histogram_frame(traj.ptr, C.byref(job), step, nthreads,
+                                                 hist.ctypes.data_as(_I64P), C.byref(w), C.byref(o))
+    assert rc == 0
+    return hist, w.value, o.value
+
+
 def transfer(traj, job, hist, within, oob, verbose=1):
     g = np.zeros(job.bin_a * job.bin_b, dtype=np.float32)
     rho = C.c_float(0)

@@ -236,14 +236,23 @@ int orc_job_setup(const pa_traj *t, const pa_job_request *rq, pa_job *job)
 /* ------------------------------------------------------------------------ */
 /* fill_histogram, Distribution:762-845, for one frame and one observed type. */
 static void orc_fill_histogram_charge_arm(const pa_traj *t, const pa_job *job, int step, int64_t *hist, int64_t *within, int64_t *oob);
+static void orc_fill_histogram_range(const pa_traj *t, const pa_job *job, int step, int obs_type0, int i_begin, int i_end,
+                                     int64_t *hist, int64_t *within, int64_t *oob);
 static void orc_fill_histogram(const pa_traj *t, const pa_job *job, int step, int obs_type0,
                                int64_t *hist, int64_t *within, int64_t *oob)
 {
+    orc_fill_histogram_range(t, job, step, obs_type0, 0, t->types[job->ref_type - 1].nmol, hist, within, oob);
+}
+/* the same loop nest for the reference molecules i_begin <= i < i_end (0-based): the iterations of the outer loop
+ * (Distribution:773) are independent and the results are integer sums, so any partition of it adds up to the whole */
+static void orc_fill_histogram_range(const pa_traj *t, const pa_job *job, int step, int obs_type0, int i_begin, int i_end,
+                                     int64_t *hist, int64_t *within, int64_t *oob)
+{
     const int ref0 = job->ref_type - 1;
     const float maxdist_squared = job->maxdist * job->maxdist;    /* maxdist**2, :659 */
-    const int nref = t->types[ref0].nmol, nobs = t->types[obs_type0].nmol;
+    const int nobs = t->types[obs_type0].nmol;
     const int w = job->weigh_charge ? t->types[obs_type0].charge : 1;
-    for (int i = 0; i < nref; ++i) {
+    for (int i = i_begin; i < i_end; ++i) {
         double cref[3];
         orc_center_of_mass(t, step, ref0, i, cref);
         for (int j = 0; j < nobs; ++j) {
@@ -322,6 +331,50 @@ int orc_distribution_histogram_shard(const pa_traj *t, const pa_job *job, int sh
                 for (int ot = 0; ot < t->ntypes; ++ot) orc_fill_histogram(t, job, step, ot, hl, &wl, &ol);
             } else {
                 orc_fill_histogram(t, job, step, job->obs_type - 1, hl, &wl, &ol);
+            }
+        }
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+        {
+            for (size_t i = 0; i < nb; ++i) hist[i] += hl[i];
+            within += wl; oob += ol;
+        }
+        free(hl);
+    }
+    *within_bin = within; *out_of_bounds = oob;
+    return 0;
+}
+
+/* ONE frame (0-based step), OpenMP over blocks of reference molecules instead of over frames: same loop body, same
+ * integers, but a single huge frame (the 1M-atom benchmark frame) uses every host core.  The reference itself has no
+ * such mode (its parallel loop is over time steps, Distribution:717); this exists so that the tests can pin the GPU
+ * path on frames of the benchmark's size. */
+int orc_distribution_histogram_frame(const pa_traj *t, const pa_job *job, int step, int nthreads,
+                                     int64_t *hist, int64_t *within_bin, int64_t *out_of_bounds)
+{
+    const size_t nb = (size_t)job->bin_a * job->bin_b;
+    memset(hist, 0, nb * sizeof(int64_t));
+    int64_t within = 0, oob = 0;
+    if (step < 0 || step >= t->nsteps || job->mode == PA_MODE_CHARGE_ARM) return -3;
+    const int nref = t->types[job->ref_type - 1].nmol;
+    const int block = 16, nblocks = (nref + block - 1) / block;
+#ifdef _OPENMP
+    if (nthreads < 1) nthreads = omp_get_max_threads();
+#pragma omp parallel num_threads(nthreads)
+#endif
+    {
+        int64_t *hl = (int64_t *)calloc(nb, sizeof(int64_t));
+        int64_t wl = 0, ol = 0;
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 1)
+#endif
+        for (int b = 0; b < nblocks; ++b) {
+            const int i0 = b * block, i1 = (i0 + block < nref) ? i0 + block : nref;
+            if (job->obs_type < 1) {
+                for (int ot = 0; ot < t->ntypes; ++ot) orc_fill_histogram_range(t, job, step, ot, i0, i1, hl, &wl, &ol);
+            } else {
+                orc_fill_histogram_range(t, job, step, job->obs_type - 1, i0, i1, hl, &wl, &ol);
             }
         }
 #ifdef _OPENMP

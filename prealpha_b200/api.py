@@ -33,9 +33,22 @@ def fp64_issue_rate(device=0) -> float:
     return v.value
 
 
-def make_exec(device=0, shard_rank=0, shard_count=1, frames_per_batch=0, flags=0) -> capi.pa_exec:
+def smem_atomic_rate(device=0) -> float:
+    """Shared-memory atomic increments per second with the pair kernels' access pattern (32 different counters per
+    warp instruction), measured live on `device`: the roofline denominator of the cell-sorted RDF kernels."""
+    lib = capi.load()
+    lib.pa_debug_smem_atomic_rate.restype = C.c_int
+    lib.pa_debug_smem_atomic_rate.argtypes = [C.c_int, C.POINTER(C.c_double)]
+    v = C.c_double(0)
+    capi.check(lib.pa_debug_smem_atomic_rate(device, C.byref(v)), "pa_debug_smem_atomic_rate")
+    return v.value
+
+
+def make_exec(device=0, shard_rank=0, shard_count=1, frames_per_batch=0, flags=0, tile_shard_rank=0, tile_shard_count=1,
+              ndevices=0) -> capi.pa_exec:
     ex = capi.pa_exec()
     ex.device, ex.shard_rank, ex.shard_count, ex.frames_per_batch, ex.flags = device, shard_rank, shard_count, frames_per_batch, flags
+    ex.tile_shard_rank, ex.tile_shard_count, ex.ndevices = tile_shard_rank, tile_shard_count, ndevices
     return ex
 
 

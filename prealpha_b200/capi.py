@@ -70,7 +70,8 @@ class pa_job(C.Structure):
 class pa_exec(C.Structure):
     _fields_ = [
         ("device", C.c_int32), ("shard_rank", C.c_int32), ("shard_count", C.c_int32),
-        ("frames_per_batch", C.c_int32), ("flags", C.c_int32), ("_pad", C.c_int32),
+        ("frames_per_batch", C.c_int32), ("flags", C.c_int32),
+        ("tile_shard_rank", C.c_int32), ("tile_shard_count", C.c_int32), ("ndevices", C.c_int32),
     ]
 
 
@@ -80,6 +81,9 @@ class pa_stats(C.Structure):
         ("kernel_launches", C.c_int64), ("exception_pairs", C.c_int64),
         ("h2d_bytes", C.c_int64), ("d2h_bytes", C.c_int64),
         ("kernel_ms", C.c_double), ("total_ms", C.c_double),
+        ("cell_pair_evals", C.c_int64), ("smem_atomics", C.c_int64), ("unique_pairs_counted", C.c_int64),
+        ("dominant_launches", C.c_int64), ("dominant_ms", C.c_double),
+        ("dominant_pair_evals", C.c_int64), ("dominant_atomics", C.c_int64),
     ]
 
     def as_dict(self):
@@ -211,7 +215,7 @@ def load():
                 f"{LIB_PATH} is not built. Run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a). There is no CPU fallback for this path.")
         _lib = bind(C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL))
-        if _lib.pa_abi_version() != 1:
+        if _lib.pa_abi_version() != 2:
             raise RuntimeError("prealpha_b200 ABI mismatch")
     return _lib
 

@@ -29,6 +29,12 @@
 #define PC_JC 128
 #define PC_MAXG 256
 
+// Reference molecule r (0..PC_RI-1) of this thread inside its tile: every warp owns 32*PC_RI consecutive molecules of
+// the tile's sorted order, i.e. a compact slab of the tile (the tile is a run of x-cells), so that "every pair of this
+// warp with observed molecule j is beyond the cutoff" is a common, warp-uniform event that skips the class computation
+// and the shared-memory atomics (pc_segment_f32).
+static __device__ __forceinline__ int pc_kidx(int r) { return (int)(threadIdx.x >> 5) * (32 * PC_RI) + r * 32 + (int)(threadIdx.x & 31); }
+
 static __device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
 // order-preserving map double -> uint64 (for atomicMin/atomicMax on coordinates)
 static __device__ __forceinline__ unsigned long long okey(double x)
@@ -251,7 +257,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
                                                   const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
                                                   long long jbase, int jb, int je,
                                                   double sxa, double sxb, double sya, double syb, double sza, double szb,
-                                                  double *s_j, const PcTables &T)
+                                                  double *s_j, const PcTables &T, unsigned int &it_all, unsigned int &it_live)
 {
     const int hi_flag = 0x3E100000;                     // hi word of 2^-30
     const int na = T.na;
@@ -275,6 +281,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
         }
         __syncthreads();
         const int cnt = min(PC_JC, je - jc);
+        it_all += (unsigned)((cnt + 1) / 2); it_live += (unsigned)((cnt + 1) / 2);   // statistics: no iteration is skipped here
         for (int jj = 0; jj < cnt; jj += 2) {
             // two staged molecules = 2*ND doubles, 16-byte aligned because jj is even
             double v[2 * ND];
@@ -329,7 +336,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
             if (DIAG) {
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
-                    const int ipos = tl.begin + (q % PC_RI) * PC_THREADS + threadIdx.x;
+                    const int ipos = tl.begin + pc_kidx(q % PC_RI);
                     const int jpos = jc + jj + q / PC_RI;
                     if (!(ipos < jpos)) { ca[q] = trash; slow &= ~(1 << q); }
                 }
@@ -342,7 +349,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
                         // |link_xy|^2 < 2^-30: (anti)parallel to the reference axis, coincident, or the molecule
                         // itself -> literal evaluation by pa_exception_kernel, not binned here
                         ca[q] = trash;
-                        const int k = (q % PC_RI) * PC_THREADS + threadIdx.x;
+                        const int k = pc_kidx(q % PC_RI);
                         const int j = jc + jj + q / PC_RI;
                         if (k < tl.count && j < je) {
                             const int io = gi.sorig[(long long)tl.frame * gi.nmol + tl.begin + k];
@@ -529,7 +536,8 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                                                       double ox, double oy, double oz,
                                                       long long jbase, int jb, int je,
                                                       double sxa, double sxb, double sya, double syb, double sza, double szb,
-                                                      double *s_j, float4 *s_jf, const PcTables &T, float near_a, unsigned long long *queue)
+                                                      double *s_j, float4 *s_jf, const PcTables &T, float near_a, unsigned long long *queue,
+                                                      float dead_d2, unsigned int &it_all, unsigned int &it_live)
 {
     static_assert(PC_RI == 2, "the packed float32 loop pairs the two reference molecules of a thread");
     static_assert(MX + MY + MZ <= 4, "at most one component with two candidate images");
@@ -572,6 +580,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
         }
         __syncthreads();
         const int cnt = min(PC_JC, je - jc);
+        it_all += (unsigned)((cnt + NU - 1) / NU);
         const unsigned int a_end = a_jf + (unsigned)cnt * 16u;
         for (unsigned int aj = a_jf; aj < a_end; aj += 16u * NU) {
             float4 wv[NU];
@@ -579,6 +588,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
             for (int u = 0; u < NU; ++u) wv[u] = pc_lds_f32x4(aj + 16u * u);
             unsigned int ca[NP], tlo[NP], thi[NP];
             float s1[NP];
+            unsigned long long s1q[NU], d2q[NU];
             bool slow = false;
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
@@ -602,6 +612,34 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                     s1p = pc_fma2(dy, dy, pc_mul2(dx, dx));
                     d2p = pc_fma2(dz, dz, s1p);
                 }
+                s1q[u] = s1p; d2q[u] = d2p;
+            }
+            // Warp-uniform skip: when every pair of this iteration (4 per lane: the warp's slab of the tile against two
+            // observed molecules) has d2~ >= dead_d2, every lower class bracket is > na -- such a pair is never counted
+            // and never queued (see `need` below) -- so the square roots, brackets and atomics are skipped altogether.
+            {
+                const float m01 = fminf(fminf(pc_lo(d2q[0]), pc_hi(d2q[0])), fminf(pc_lo(d2q[NU - 1]), pc_hi(d2q[NU - 1])));
+                if (__all_sync(0xffffffffu, m01 >= dead_d2)) {
+                    if (VERIFY) {
+                        const int jj = (int)((aj - a_jf) >> 4);
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            const int r = q % PC_RI, u = q / PC_RI;
+                            if (pc_kidx(r) >= tl.count || jc + jj + u >= je) continue;
+                            const double *rec = s_j + (jj + u) * ND;
+                            const double e1 = __dadd_rn(pc_comp_sq<MX>(rec[0], rec[MX - 1], p1x[r]), pc_comp_sq<MY>(rec[MX], rec[MX + MY - 1], p1y[r]));
+                            const double e2 = __dadd_rn(e1, pc_comp_sq<MZ>(rec[MX + MY], rec[MX + MY + MZ - 1], p1z[r]));
+                            // must be "beyond the cutoff": class na + 1
+                            if (!(e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (na + 1))))) atomicAdd(p.verify_fail, 1u);
+                        }
+                    }
+                    continue;
+                }
+            }
+            ++it_live;
+#pragma unroll
+            for (int u = 0; u < NU; ++u) {
+                const unsigned long long s1p = s1q[u], d2p = d2q[u];
 #pragma unroll
                 for (int r = 0; r < PC_RI; ++r) {
                     const int q = u * PC_RI + r;
@@ -622,7 +660,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     const int r = q % PC_RI, u = q / PC_RI;
-                    const int k = r * PC_THREADS + threadIdx.x;
+                    const int k = pc_kidx(r);
                     // not for padded slots, and not when even the lower bracket is beyond the cutoff (class > na: never counted,
                     // and the threshold table ends at class na + 2)
                     const bool need = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && tlo[q] <= 0x4B000000u + (unsigned)na &&
@@ -644,7 +682,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     const int r = q % PC_RI, u = q / PC_RI;
-                    if (r * PC_THREADS + threadIdx.x >= tl.count || jc + jj + u >= je || ca[q] == trash) continue;
+                    if (pc_kidx(r) >= tl.count || jc + jj + u >= je || ca[q] == trash) continue;
                     const double *rec = s_j + (jj + u) * ND;
                     const double e1 = __dadd_rn(pc_comp_sq<MX>(rec[0], rec[MX - 1], p1x[r]), pc_comp_sq<MY>(rec[MX], rec[MX + MY - 1], p1y[r]));
                     const double e2 = __dadd_rn(e1, pc_comp_sq<MZ>(rec[MX + MY], rec[MX + MY + MZ - 1], p1z[r]));
@@ -685,6 +723,7 @@ static __device__ void pc_flush(const PaPass &p, const PcTables &T, bool reset)
     if (within) {
         atomicAdd(&p.job.acc[na], within * (unsigned long long)mult);
         if (p.acc2) atomicAdd(&p.acc2[na], within);
+        if (p.kstats) atomicAdd(p.kstats + 2, within);               // pairs counted, each evaluated once
     }
     if (VARIANT == 0 && threadIdx.x == 0) {                                                          // class na found by an exact path
         const unsigned int c = pc_lds_u32(T.special);
@@ -744,12 +783,16 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     const long long n_items = (long long)ntiles * nzg;
     unsigned long long since_flush = 0;
     const int gx = go.g[0], gy = go.g[1], gz = go.g[2];
+    // statistics (warp-uniform): loop iterations (4 pair evaluations per lane each) and those that issued their atomics
+    unsigned int it_all = 0, it_live = 0;
+    unsigned long long st_all = 0, st_live = 0;
 
     for (;;) {
+        st_all += it_all; st_live += it_live; it_all = it_live = 0;
         __syncthreads();
         if (threadIdx.x == 0) { sh->work_item = (int)atomicAdd(work_counter, 1u); sh->t2_bits = 0u; }
         __syncthreads();
-        const long long item = sh->work_item;
+        const long long item = (long long)sh->work_item * p.tshard_count + p.tshard_rank;   // tile shard: items w with w % count == rank
         if (item >= n_items) break;
         const PaTile tl = tiles[item / nzg];
         const int zg = (int)(item % nzg);
@@ -758,10 +801,12 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
         // reference molecules of the tile -> registers
         double p1x[PC_RI], p1y[PC_RI], p1z[PC_RI];
         const long long ibase = (long long)tl.frame * gi.nmol;
+        double q1x[PC_RI], q1y[PC_RI], q1z[PC_RI];         // padded slots: a copy of the tile's last molecule (float32 segments)
 #pragma unroll
         for (int r = 0; r < PC_RI; ++r) {
-            const int k = r * PC_THREADS + threadIdx.x;
-            if (k < tl.count) { p1x[r] = gi.sx[ibase + tl.begin + k]; p1y[r] = gi.sy[ibase + tl.begin + k]; p1z[r] = gi.sz[ibase + tl.begin + k]; }
+            const int k = pc_kidx(r), kk = min(k, tl.count - 1);
+            q1x[r] = gi.sx[ibase + tl.begin + kk]; q1y[r] = gi.sy[ibase + tl.begin + kk]; q1z[r] = gi.sz[ibase + tl.begin + kk];
+            if (k < tl.count) { p1x[r] = q1x[r]; p1y[r] = q1y[r]; p1z[r] = q1z[r]; }
             else p1x[r] = p1y[r] = p1z[r] = -1.0e15;   // padding: far away, finite in float range
         }
         // float32 segments: local coordinates about the centre of the tile's cells
@@ -774,10 +819,12 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
             float t2 = 0.0f;
 #pragma unroll
             for (int r = 0; r < PC_RI; ++r) {
-                const bool live = r * PC_THREADS + threadIdx.x < tl.count;
-                xf[r] = live ? __double2float_rn(__dsub_rn(p1x[r], ox)) : 0.0f;
-                yf[r] = live ? __double2float_rn(__dsub_rn(p1y[r], oy)) : 0.0f;
-                zf[r] = live ? __double2float_rn(__dsub_rn(p1z[r], oz)) : 0.0f;
+                // padded slots sit on the tile's last molecule (so that they do not spoil the warp-uniform "beyond the
+                // cutoff" test) and count into the shifted counter window
+                const bool live = pc_kidx(r) < tl.count;
+                xf[r] = __double2float_rn(__dsub_rn(q1x[r], ox));
+                yf[r] = __double2float_rn(__dsub_rn(q1y[r], oy));
+                zf[r] = __double2float_rn(__dsub_rn(q1z[r], oz));
                 cb[r] = T.cnt - 0x4B000000u * 4u + (live ? 0u : T.cnt_pad);
                 t2 = fmaxf(t2, __fmaf_ru(zf[r], zf[r], __fmaf_ru(yf[r], yf[r], __fmul_ru(xf[r], xf[r]))));
             }
@@ -821,6 +868,10 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
         if (PART == 1 && !tile_f32) continue;
         const float rmin2 = 4.0f * tile_t2 * 1.0001f + 1.0e-3f;
         const float near_a = 1.25e-7f * sqrtf(tile_t2) + 1.0e-12f;       // 2u|T| (u = 2^-24), rounded up
+        // d2~ from which the lower bracket floor((sqrt.approx(d2~) - a) * f32_lo) is certainly > na (sqrt.approx: 2^-22 relative)
+        const float dead_r = __fadd_ru(p.dead_r, near_a);
+        float dead_d2 = __fmul_ru(__fmul_ru(dead_r, dead_r), 1.000001f);
+        asm volatile("" : "+f"(dead_d2));                                 // keep it in a register: ptxas otherwise recomputes it per iteration
 
         const long long jbase = (long long)tl.frame * go.nmol;
         const int *cs = go.cell_start + (long long)tl.frame * (go.ncell + 1);
@@ -881,13 +932,13 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     if (PART != 1 && SYM && db < de) {
                         // staging needs an even start so that pairs of records stay 16-byte aligned: start at db & ~1,
                         // the extra molecule (if any) lies before the tile or inside it and is masked by ipos < jpos
-                        pc_segment<2, 2, 2, VARIANT, VERIFY, true>(p, go, gi, tl, p1x, p1y, p1z, jbase, db, de, sxa, sxb, sya, syb, sza, szb, s_j, T);
+                        pc_segment<2, 2, 2, VARIANT, VERIFY, true>(p, go, gi, tl, p1x, p1y, p1z, jbase, db, de, sxa, sxb, sya, syb, sza, szb, s_j, T, it_all, it_live);
                     }
                     if (jb >= je) continue;
                     if (PART == 2 && f32run) continue;                              // counted by the PART 1 launch
                     if (VARIANT == 0 && PART == 1 && f32run) {
 #define PC_F32(MX_, MY_, MZ_, Z_, N_) pc_segment_f32<MX_, MY_, MZ_, Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, \
-                                                                                    sxa, sxb, sya, syb, sza, szb, s_j, s_jf, T, near_a, queue)
+                                                                                    sxa, sxb, sya, syb, sza, szb, s_j, s_jf, T, near_a, queue, dead_d2, it_all, it_live)
                         if (dcode == 0) {
                             if (nearr) { if (zcol) PC_F32(1, 1, 1, true, true); else PC_F32(1, 1, 1, false, true); }
                             else { if (zcol) PC_F32(1, 1, 1, true, false); else PC_F32(1, 1, 1, false, false); }
@@ -900,7 +951,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     if (PART == 1) continue;
 #define PC_SEG(MX_, MY_, MZ_)                                                                                              \
     pc_segment<MX_, MY_, MZ_, VARIANT, VERIFY, false>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb,  \
-                                               s_j, T)
+                                               s_j, T, it_all, it_live)
                     switch (code) {
                     case 0: PC_SEG(1, 1, 1); break;
                     case 1: PC_SEG(2, 1, 1); break;
@@ -918,6 +969,12 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     }
     __syncthreads();
     pc_flush<VARIANT>(p, T, false);
+    if (p.kstats && (threadIdx.x & 31) == 0) {
+        st_all += it_all; st_live += it_live;
+        unsigned long long *ks = p.kstats + (PART == 1 ? 0 : 4);    // the float32 launch is accounted separately
+        if (st_all) atomicAdd(ks + 0, st_all * 128ull);             // pair evaluations (lanes x 4 per iteration)
+        if (st_live) atomicAdd(ks + 1, st_live * 128ull);           // shared-memory atomics issued (one per evaluated pair of a live iteration)
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1080,7 +1137,7 @@ __global__ void __launch_bounds__(PC_THREADS, 5) pa_general_cells_kernel(const _
         __syncthreads();
         if (threadIdx.x == 0) { sh->work_item = (int)atomicAdd(work_counter, 1u); }
         __syncthreads();
-        const long long item = sh->work_item;
+        const long long item = (long long)sh->work_item * p.tshard_count + p.tshard_rank;   // tile shard: items w with w % count == rank
         if (item >= n_items) break;
         const PaTile tl = tiles[item / nzg];
         const int zg = (int)(item % nzg);
@@ -1215,7 +1272,8 @@ size_t pa_cells_smem_bytes(int na, int f32_cnt, int nlayers)   // f32_cnt > 0: t
 }
 
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
-                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream)
+                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream,
+                        void *ev_f32_begin, void *ev_f32_end)
 {
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = pa_cells_smem_bytes(p.job.bin_a, variant == 0 ? p.f32_cnt : 0, go.g[0] + go.g[1] + go.g[2]);
@@ -1231,7 +1289,12 @@ int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
     } while (0)
 #define PC_LAUNCH2(O_, V_, S_)                                                                                  \
     do {                                                                                                        \
-        if (O_ == 0 && p.f32_cnt > 0) { PC_LAUNCH3(O_, V_, S_, 1, smem); PC_LAUNCH3(O_, V_, S_, 2, smem0); }    \
+        if (O_ == 0 && p.f32_cnt > 0) {                                                                         \
+            if (ev_f32_begin) cudaEventRecord((cudaEvent_t)ev_f32_begin, st);                                   \
+            PC_LAUNCH3(O_, V_, S_, 1, smem);                                                                    \
+            if (ev_f32_end) cudaEventRecord((cudaEvent_t)ev_f32_end, st);                                       \
+            PC_LAUNCH3(O_, V_, S_, 2, smem0);                                                                   \
+        }                                                                                                       \
         else PC_LAUNCH3(O_, V_, S_, 0, smem0);                                                                  \
     } while (0)
 #define PC_LAUNCH(O_, V_) do { if (p.sym) PC_LAUNCH2(O_, V_, true); else PC_LAUNCH2(O_, V_, false); } while (0)

@@ -809,8 +809,21 @@ int perform_distribution(Run &r, const std::string &input_name)     // Distribut
     std::vector<int64_t> within(jobs.size()), oob(jobs.size());
     pa_stats st{};
     const auto t0 = std::chrono::steady_clock::now();
+    pa_exec ex = r.exec;
+    if (ex.ndevices < 0) {
+        // "all usable devices" is a default, not an order: a job below ~2e11 pair evaluations finishes on one GPU before
+        // the other contexts and the communicators exist
+        double evals = 0.0;
+        for (const pa_job &jb : jobs) {
+            if (jb.mode == PA_MODE_CHARGE_ARM) continue;
+            double nobs = 0.0;
+            for (size_t t = 0; t < r.types.size(); ++t) if (jb.obs_type < 1 || (int)t == jb.obs_type - 1) nobs += r.types[t].nmol;
+            evals += (double)r.types[jb.ref_type - 1].nmol * nobs * ((r.nsteps + jb.sampling_interval - 1) / jb.sampling_interval);
+        }
+        if (evals < 2.0e11 || pa_device_count() - ex.device < 2) ex.ndevices = 1;
+    }
     if (r.stream) rc = histogram_streaming(r, traj, jobs, hp, within, oob, &st);
-    else rc = pa_distribution_histogram_multi(&traj, jobs.data(), (int)jobs.size(), &r.exec, hp.data(), within.data(), oob.data(), &st);
+    else rc = pa_distribution_histogram_multi(&traj, jobs.data(), (int)jobs.size(), &ex, hp.data(), within.data(), oob.data(), &st);
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { r.error(rc, std::string("GPU histogram failed: ") + pa_last_error()); return rc; }
     traj.nsteps = r.nsteps;                                   // (a streamed file may have turned out shorter: error 84)

@@ -95,6 +95,11 @@ struct PaPass {
     int32_t f32_cnt;            // > 0: float32 segments enabled in the cell kernel, counters needed for any reachable class
     float eps64;                // half-width of the class brackets of the fp64-difference segments (variant 0)
     float f32_lo, f32_hi;       // (1 -+ eps)/step_a rounded outwards (eps: pa_session.cu); adjacent so that they load as one packed pair
+    int32_t tshard_rank, tshard_count;   // tile shard of this device (pa_exec.tile_shard_*): work item w is taken when w % count == rank
+    float dead_r;               // (bin_a + 1)/f32_lo rounded up: from this approximate distance on, the lower class bracket is beyond the cutoff
+    unsigned long long *kstats; // device counters of the cell kernels (8 words, may be null): [0] pair evaluations after cell pruning
+                                // and [1] shared-memory atomics issued by the float32 launches, [4] / [5] the same for the other
+                                // launches, [2] pairs counted into bins (each evaluated once)
 };
 
 // Uniform grid of one molecule type for a batch of frames (pa_cells.cu).  Arrays are
@@ -131,7 +136,8 @@ int pa_launch_exceptions(const PaPass &p, unsigned int count, void *stream);
 int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &box, int frame0, int nframes, unsigned int *err, void *stream);
 int pa_launch_build_tiles(const PaCellGrid &g, int nframes, PaTile *tiles, unsigned int *ntiles, unsigned int cap, void *stream);
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
-                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream);
+                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream,
+                        void *ev_f32_begin, void *ev_f32_end);   // optional CUDA events around the float32 launch (the dominant kernel)
 int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
                             unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream);
 void pa_cell_grid_dims(int nmol, int g[3]);

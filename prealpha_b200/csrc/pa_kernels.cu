@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(PA_THREADS) pa_rdf_fast_kernel(PaPass p)
     unsigned long long since_flush = 0;
     constexpr int TI = PA_THREADS * RI;
 
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // tile shard r of n takes the items w with w % n == r (pa_exec.tile_shard_*)
+    for (long long item = (long long)blockIdx.x * p.tshard_count + p.tshard_rank; item < n_items; item += (long long)gridDim.x * p.tshard_count) {
         const PaItem it = pa_decode_item(p, item);
         const long long fbase = (long long)it.frame * p.pts.M;
         const int i0 = it.i0 * TI;
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(PA_THREADS) pa_general_kernel(const __grid_con
     constexpr int TI = PA_THREADS * RI;
     unsigned long long g_within = 0, g_oob = 0;               // !SMEM_HIST: per-thread counters
 
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    // tile shard r of n takes the items w with w % n == r (pa_exec.tile_shard_*)
+    for (long long item = (long long)blockIdx.x * p.tshard_count + p.tshard_rank; item < n_items; item += (long long)gridDim.x * p.tshard_count) {
         const PaItem it = pa_decode_item(p, item);
         const long long fbase = (long long)it.frame * p.pts.M;
         const int i0 = it.i0 * TI;
@@ -465,7 +467,7 @@ int pa_launch_charge_arm(const PaChargeArmArgs &a, void *stream)
 static int pa_grid_for(long long n_items, int sm_count, int ctas_per_sm)
 {
     long long g = (long long)sm_count * ctas_per_sm;
-    if (n_items < g) g = n_items;
+    if (n_items < g) g = n_items;                            // (a tile shard owns about n_items / tshard_count of them: a few idle CTAs at most)
     if (g < 1) g = 1;
     return (int)g;
 }
@@ -589,6 +591,59 @@ extern "C" int pa_debug_fp64_issue_rate(int device, double *inst_per_s)
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
     if (err != cudaSuccess) return PA_ERR_CUDA;
     *inst_per_s = (double)blocks * threads * iters * 16.0 / (best * 1e-3);
+    return 0;
+}
+
+// Shared-memory atomic rate with the access pattern of the cell-sorted RDF kernels: every lane of a warp increments a
+// different 4-byte counter inside a 128-class window of a 1000-class histogram (one observed molecule against 32 reference
+// molecules), 128-thread CTAs at the pair kernel's occupancy.  The second denominator of this path's roofline, measured
+// on the device it runs on (same kernel as prealpha_b200/csrc/pa_microbench2.cu, layout 0).
+__global__ void __launch_bounds__(128) pa_smem_atomic_rate_kernel(unsigned int *out, int nbins, int window, int iters, unsigned int seed)
+{
+    extern __shared__ unsigned int h[];
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) h[k] = 0;
+    __syncthreads();
+    unsigned int s = seed ^ (blockIdx.x * 9781u + threadIdx.x * 6271u + 1u);
+    unsigned int sw = seed ^ (blockIdx.x * 7919u + (threadIdx.x >> 5) * 104729u + 7u);      // warp-uniform stream: window position
+    unsigned int acc = 0;
+    for (int it = 0; it < iters; ++it) {
+        sw = sw * 1664525u + 1013904223u;
+        const int base = (int)(((unsigned long long)(sw >> 8) * (unsigned)(nbins - window)) >> 24);
+        s = s * 1664525u + 1013904223u;
+        const int bin = base + (int)((s >> 8) & (unsigned)(window - 1));
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(h + bin)) : "memory");
+        acc += bin;
+    }
+    __syncthreads();
+    unsigned int t = acc;
+    for (int k = threadIdx.x; k < nbins; k += blockDim.x) t += h[k];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = t;
+}
+
+extern "C" int pa_debug_smem_atomic_rate(int device, double *atomics_per_s)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return PA_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PA_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 6, threads = 128, iters = 8192, nbins = 1000;
+    unsigned int *d = nullptr;
+    if (cudaMalloc(&d, sizeof(unsigned int) * blocks * threads) != cudaSuccess) return PA_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; ++r) {
+        cudaEventRecord(e0);
+        pa_smem_atomic_rate_kernel<<<blocks, threads, nbins * 4>>>(d, nbins, 128, iters, 12345u);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms < best) best = ms;
+    }
+    const cudaError_t err = cudaGetLastError();
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    if (err != cudaSuccess) return PA_ERR_CUDA;
+    *atomics_per_s = (double)blocks * threads * iters / (best * 1e-3);
     return 0;
 }
 

@@ -1,6 +1,8 @@
 // prealpha_b200 -- command-line drop-in for `./prealpha general.inp` on the distribution path.
 // Mirrors PROGRAM PREALPHA (Main:3843-3915): every argument is a general input file; without
-// arguments "general.inp" is used (SETTINGS:73).  Options: --device N.
+// arguments "general.inp" is used (SETTINGS:73).  Options: --device N (first device), --devices N | -g N | -g all
+// (how many GPUs one analysis may use; default: all usable devices for large jobs, see pa_exec.ndevices;
+// environment PREALPHA_B200_DEVICES has the same meaning).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -13,9 +15,14 @@ int main(int argc, char **argv)
     pa_exec ex;
     memset(&ex, 0, sizeof ex);
     ex.shard_count = 1;
+    ex.tile_shard_count = 1;
+    ex.ndevices = -1;                                            // all usable devices, for jobs that are worth it
+    auto parse_devices = [](const char *v) { return (!strcmp(v, "all") || !strcmp(v, "0")) ? -1 : atoi(v); };
+    if (const char *e = getenv("PREALPHA_B200_DEVICES")) ex.ndevices = parse_devices(e);
     std::vector<std::string> inputs;
     for (int i = 1; i < argc; ++i) {
         if (!strcmp(argv[i], "--device") && i + 1 < argc) ex.device = atoi(argv[++i]);
+        else if ((!strcmp(argv[i], "--devices") || !strcmp(argv[i], "-g")) && i + 1 < argc) ex.ndevices = parse_devices(argv[++i]);
         else inputs.push_back(argv[i]);
     }
     if (inputs.empty()) inputs.push_back("general.inp");

@@ -13,6 +13,8 @@
 #include <cmath>
 #include <chrono>
 #include <mutex>
+#include <thread>
+#include <dlfcn.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -118,8 +120,10 @@ struct pa_session {
     size_t acc_words = 0;
     uint2 *d_exc = nullptr;
     unsigned int *d_exc_count = nullptr;    // [0] count, [1] sticky error flag, [2] verify failures, [3] total, [4] count of list 2
+    unsigned long long *d_kstats = nullptr; // counters of the cell kernels, see PaPass::kstats
     pa_stats stats{};
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> kernel_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> f32_events;     // around every float32 launch of the cell-sorted RDF kernel
     std::vector<TypeGrid> grids;            // cell-sorted copies of the types the RDF fast path pairs
     bool use_cells = false;
     unsigned int exc_cap = kExcCap;         // entries of the exception list (both halves together)
@@ -144,15 +148,22 @@ int upload_types_table(pa_session *s, int slot)
 
 }  // namespace
 
+int pa_multi_device_histogram(const pa_traj *traj, const pa_job *jobs, int32_t njobs, pa_exec ex,
+                              int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, pa_stats *stats);
+void pa_multi_device_trim();
+
 extern "C" {
 
 int pa_abi_version(void) { return PA_ABI_VERSION; }
 
 void pa_trim(void)
 {
-    std::lock_guard<std::mutex> lock(g_pool_mutex);
-    for (const PinnedEntry &e : g_pinned_pool) cudaFreeHost(e.ptr);
-    g_pinned_pool.clear();
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        for (const PinnedEntry &e : g_pinned_pool) cudaFreeHost(e.ptr);
+        g_pinned_pool.clear();
+    }
+    pa_multi_device_trim();
 }
 const char *pa_last_error(void) { return g_last_error.c_str(); }
 
@@ -168,6 +179,10 @@ int pa_device_count(void)
     return ok;
 }
 
+// Every failure path of the set-up below returns through pa_session_create, which destroys the partially built
+// session (pa_session_destroy tolerates null members), so no device buffer, pinned buffer, stream or event leaks.
+static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job *jobs, int32_t njobs, const pa_exec &ex, int32_t max_frames);
+
 int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, const pa_exec *exec,
                       int32_t max_frames, pa_session **out)
 {
@@ -175,6 +190,8 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     pa_exec ex{};
     if (exec) ex = *exec;
     if (ex.shard_count < 1) ex.shard_count = 1;
+    if (ex.tile_shard_count < 1) ex.tile_shard_count = 1;
+    if (ex.tile_shard_rank < 0 || ex.tile_shard_rank >= ex.tile_shard_count) { pa::set_error("bad tile shard"); return PA_ERR_BAD_ARG; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
         cudaGetLastError();
@@ -188,6 +205,14 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
         return PA_ERR_NO_DEVICE;
     }
     pa_session *s = new pa_session();
+    const int rc = session_create_impl(s, traj, jobs, njobs, ex, max_frames);
+    if (rc) { pa_session_destroy(s); return rc; }
+    *out = s;
+    return 0;
+}
+
+static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job *jobs, int32_t njobs, const pa_exec &ex, int32_t max_frames)
+{
     s->device = ex.device; s->exec = ex;
     s->force_general = (ex.flags & PA_EXEC_FORCE_GENERAL) != 0;
     s->verify = (ex.flags & 0x100) != 0;
@@ -206,7 +231,7 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     int64_t off = 0;
     for (int t = 0; t < traj->ntypes; ++t) {
         const pa_type &ty = traj->types[t];
-        if (ty.natoms < 1 || ty.nmol < 1) { delete s; pa::set_error("molecule type with natoms/nmol < 1"); return PA_ERR_BAD_ARG; }
+        if (ty.natoms < 1 || ty.nmol < 1) { pa::set_error("molecule type with natoms/nmol < 1"); return PA_ERR_BAD_ARG; }
         TypeMeta &m = s->types[t];
         m.charge = ty.charge; m.natoms = ty.natoms; m.nmol = ty.nmol; m.offset = (int32_t)off;
         m.mass = ty.mass; m.realcharge = (double)ty.realcharge; m.needed = false;
@@ -216,11 +241,11 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     for (int j = 0; j < njobs; ++j) {
         const pa_job &jb = jobs[j];
         if (jb.ref_type < 1 || jb.ref_type > traj->ntypes || jb.obs_type > traj->ntypes) {
-            delete s; pa::set_error("molecule type index out of range (error 33)"); return PA_E_TYPE_INVALID;
+            pa::set_error("molecule type index out of range (error 33)"); return PA_E_TYPE_INVALID;
         }
         if (jb.bin_a < 1 || jb.bin_a > 1000 || jb.bin_b < 1 || jb.bin_b > 1000 || jb.sampling_interval < 1 ||
             (jb.mode != PA_MODE_PDF && jb.mode != PA_MODE_CDF && jb.mode != PA_MODE_CHARGE_ARM)) {
-            delete s; pa::set_error("invalid job (bins 1..1000, sampling_interval >= 1, mode cdf|pdf|charge_arm)"); return PA_ERR_BAD_ARG;
+            pa::set_error("invalid job (bins 1..1000, sampling_interval >= 1, mode cdf|pdf|charge_arm)"); return PA_ERR_BAD_ARG;
         }
         s->types[jb.ref_type - 1].needed = true;
         if (jb.mode == PA_MODE_CHARGE_ARM) continue;                // intramolecular: no observed types
@@ -289,6 +314,8 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
     PA_CK(cudaMalloc(&s->d_exc, sizeof(uint2) * kExcCap));
     PA_CK(cudaMalloc(&s->d_exc_count, sizeof(unsigned int) * 8));
     PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 8));
+    PA_CK(cudaMalloc(&s->d_kstats, sizeof(unsigned long long) * 8));
+    PA_CK(cudaMemset(s->d_kstats, 0, sizeof(unsigned long long) * 8));
     for (int j = 0; j < njobs; ++j) {
         JobState &js = s->jobs[j];
         const pa_job &jb = js.job;
@@ -380,7 +407,9 @@ int pa_session_create(const pa_traj *traj, const pa_job *jobs, int32_t njobs, co
             PA_CK(cudaMemset(tg.counters, 0, sizeof(unsigned int) * 4));
         }
     }
-    *out = s;
+    // the table uploads and memsets above ran on the legacy default stream, which does not synchronise with the
+    // session's non-blocking streams: make sure all of them have landed before the first kernel can start
+    PA_CK(cudaDeviceSynchronize());
     return 0;
 }
 
@@ -476,6 +505,7 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         const pa_job &jb = s->jobs[j].job;
         const int r = jb.ref_type - 1;
         if (jb.mode == PA_MODE_CHARGE_ARM) {                        // fill_histogram_charge_arm, Distribution:847-895
+            if (s->exec.tile_shard_rank != 0) continue;             // O(N) per frame: the first tile shard does it
             PaChargeArmArgs ca{};
             ca.types = s->d_types[slot]; ca.type = r; ca.frame0 = first; ca.nframes = count;
             ca.normalise_clm = jb.normalise_clm; ca.com_boost = s->box.com_boost;
@@ -538,14 +568,21 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
             // three float32 roundings inside the in-kernel scale factors 1.8e-7 = 5.1e-7
             p.eps64 = (float)(5.5e-7 + js.delta_top);
             p.f32_lo = lo; p.f32_hi = hi;
+            // approximate distance from which floor(r~ * f32_lo) > bin_a even after the 2^-22 relative error of sqrt.approx
+            const double dead = ((double)jb.bin_a + 1.0) / (double)lo * (1.0 + 1.0e-6);
+            p.dead_r = (float)dead;
+            if ((double)p.dead_r < dead) p.dead_r = std::nextafterf(p.dead_r, INFINITY);
         }
+        p.tshard_rank = s->exec.tile_shard_rank; p.tshard_count = s->exec.tile_shard_count;
+        p.kstats = s->d_kstats;
     };
     for (const Plan &pl : plan) {
         const JobState &js = s->jobs[pl.job];
         const int r = pl.r, o = pl.o;
         PaPass p{};
         fill_pass(p, js, r, o);
-        s->stats.pairs_evaluated += (int64_t)p.nframes * ((int64_t)p.nref * p.nobs - (p.same_type ? p.nref : 0));
+        if (s->exec.tile_shard_rank == 0)                           // the statistics of all tile shards add up to the whole
+            s->stats.pairs_evaluated += (int64_t)p.nframes * ((int64_t)p.nref * p.nobs - (p.same_type ? p.nref : 0));
         if (pl.skip) continue;                                     // counted by its partner's launch
         const int ri = js.fast ? pa_rdf_ri(p.nref) : pa_general_ri(p.nref);
         const int ti = PA_TILE_THREADS * ri;
@@ -589,8 +626,13 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
             const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 230 + 1));
             long long nzg = (20ll * s->sm_count * 5 + tiles_est - 1) / tiles_est;
             nzg = std::max<long long>(1, std::min<long long>(nzg, s->grids[o].g.g[2]));
+            cudaEvent_t f0 = nullptr, f1 = nullptr;
+            if (js.cells_variant == 0 && js.f32_cnt > 0) {
+                PA_CK(cudaEventCreate(&f0)); PA_CK(cudaEventCreate(&f1));
+                s->f32_events.emplace_back(f0, f1);
+            }
             PA_CK((cudaError_t)pa_launch_rdf_cells(p, gr.g, s->grids[o].g, gr.tiles, gr.counters, gr.tile_cap, gr.counters + 1,
-                                                   (int)nzg, js.cells_variant, s->sm_count, s->s_compute));
+                                                   (int)nzg, js.cells_variant, s->sm_count, s->s_compute, f0, f1));
             PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
             s->stats.kernel_launches += 3 + ((js.cells_variant == 0 && js.f32_cnt > 0) ? 1 : 0);   // float32 runs and the rest are two launches
             if (pl.sym) {                                           // reversed pairs of the same job
@@ -629,6 +671,18 @@ int pa_session_stats(pa_session *s, pa_stats *st)
         cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
     }
     s->kernel_events.clear();
+    for (auto &ev : s->f32_events) {
+        float ms = 0.f;
+        PA_CK(cudaEventElapsedTime(&ms, ev.first, ev.second));
+        s->stats.dominant_ms += ms; s->stats.dominant_launches += 1;
+        cudaEventDestroy(ev.first); cudaEventDestroy(ev.second);
+    }
+    s->f32_events.clear();
+    unsigned long long ks[8];
+    PA_CK(cudaMemcpy(ks, s->d_kstats, sizeof ks, cudaMemcpyDeviceToHost));
+    s->stats.cell_pair_evals = (int64_t)(ks[0] + ks[4]); s->stats.smem_atomics = (int64_t)(ks[1] + ks[5]);
+    s->stats.unique_pairs_counted = (int64_t)ks[2];
+    s->stats.dominant_pair_evals = (int64_t)ks[0]; s->stats.dominant_atomics = (int64_t)ks[1];
     *st = s->stats;
     return 0;
 }
@@ -654,8 +708,10 @@ int pa_session_download(pa_session *s, int64_t *const *hists, int64_t *within_bi
     }
     s->stats.pairs_binned = binned;
     if (reset) {
-        PA_CK(cudaMemset(s->d_acc, 0, sizeof(unsigned long long) * s->acc_words));
-        PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 8));
+        // stream-ordered with the kernels of the next run (a plain cudaMemset runs on the legacy default stream, which
+        // the non-blocking compute stream does not wait for)
+        PA_CK(cudaMemsetAsync(s->d_acc, 0, sizeof(unsigned long long) * s->acc_words, s->s_compute));
+        PA_CK(cudaMemsetAsync(s->d_exc_count, 0, sizeof(unsigned int) * 8, s->s_compute));
     }
     if (flags[1]) {
         pa::set_error("exception list overflow: too many pairs (anti)parallel to the reference axis; rerun with PA_EXEC_FORCE_GENERAL");
@@ -684,6 +740,7 @@ void pa_session_destroy(pa_session *s)
     if (s->s_compute) cudaStreamSynchronize(s->s_compute);
     if (s->s_copy) cudaStreamSynchronize(s->s_copy);
     for (auto &ev : s->kernel_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    for (auto &ev : s->f32_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &m : s->types) { cudaFree(m.d_mass); cudaFree(m.d_charge); }
     for (int b = 0; b < 2; ++b) {
         for (float *p : s->d_raw[b]) cudaFree(p);
@@ -698,7 +755,7 @@ void pa_session_destroy(pa_session *s)
         cudaFree(tg.g.cell_start); cudaFree(tg.g.cell_fill); cudaFree(tg.g.cid); cudaFree(tg.g.sx); cudaFree(tg.g.sy); cudaFree(tg.g.sz);
         cudaFree(tg.g.sorig); cudaFree(tg.g.sflag); cudaFree(tg.g.lay_lo); cudaFree(tg.g.lay_hi); cudaFree(tg.tiles); cudaFree(tg.counters);
     }
-    cudaFree(s->d_pts); cudaFree(s->d_acc); cudaFree(s->d_exc); cudaFree(s->d_exc_count);
+    cudaFree(s->d_pts); cudaFree(s->d_acc); cudaFree(s->d_exc); cudaFree(s->d_exc_count); cudaFree(s->d_kstats);
     if (s->s_compute) cudaStreamDestroy(s->s_compute);
     if (s->s_copy) cudaStreamDestroy(s->s_copy);
     delete s;
@@ -718,19 +775,13 @@ static int choose_batch(const pa_traj *traj, const pa_exec *ex, int nsamp_local)
     return (int)b;
 }
 
-int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int32_t njobs, const pa_exec *exec,
-                                    int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, pa_stats *stats)
+// This process's share of the work on ONE device (ex is already sharded): create a session, stream the frames through
+// it and leave the results in its device accumulators.  A sticky device flag (exception list overflow / boxes too wide
+// for the cell path / non-finite coordinates) sends the share through the kernel ladder cells -> brute force -> general
+// kernel; every rung gives the same integers, so different devices may end on different rungs.
+static int run_share_on_device(const pa_traj *traj, const pa_job *jobs, int32_t njobs, pa_exec ex, pa_session **out, float *total_ms)
 {
-    if (!traj || !jobs || njobs < 1) { pa::set_error("bad argument"); return PA_ERR_BAD_ARG; }
-    pa_exec ex{};
-    if (exec) ex = *exec;
-    if (ex.shard_count < 1) ex.shard_count = 1;
-    if (ex.shard_rank < 0 || ex.shard_rank >= ex.shard_count) { pa::set_error("bad shard"); return PA_ERR_BAD_ARG; }
     const int dt = jobs[0].sampling_interval;
-    for (int j = 1; j < njobs; ++j)
-        if (jobs[j].sampling_interval != dt) { pa::set_error("jobs of one call must share sampling_interval"); return PA_ERR_BAD_ARG; }
-    if (dt < 1) { pa::set_error("sampling_interval < 1"); return PA_ERR_BAD_ARG; }
-    // sampled frames 0, dt, 2dt, ... (Distribution:718); this shard takes k % count == rank
     const int nsamp = (traj->nsteps + dt - 1) / dt;
     const int nlocal = nsamp > ex.shard_rank ? (nsamp - ex.shard_rank + ex.shard_count - 1) / ex.shard_count : 0;
     for (int attempt = 0; attempt < 3; ++attempt) {
@@ -739,7 +790,7 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
         const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
         const auto w0 = std::chrono::steady_clock::now();
         auto lap = [&](const char *what) {
-            if (dbg_t) fprintf(stderr, "[prealpha_b200] %-10s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
+            if (dbg_t) fprintf(stderr, "[prealpha_b200] dev %d %-10s %8.2f ms\n", ex.device, what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count());
         };
         int rc = pa_session_create(traj, jobs, njobs, &ex, batch, &s);
         if (rc) return rc;
@@ -754,21 +805,14 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
             if (rc == 0) rc = pa_session_run(s);
         }
         lap("enqueued");
-        if (rc == 0) rc = pa_session_download(s, hists, within_bin, out_of_bounds, 0);
+        if (rc == 0) rc = pa_session_download(s, nullptr, nullptr, nullptr, 0);      // waits, and reads the sticky flags
         cudaEventRecord(t1, s->s_compute);
         cudaEventSynchronize(t1);
-        lap("download");
-        if (stats) {
-            pa_session_stats(s, stats);
-            float ms = 0.f;
-            cudaEventElapsedTime(&ms, t0, t1);
-            stats->total_ms = ms;
-        }
+        lap("finished");
+        if (total_ms) { *total_ms = 0.f; cudaEventElapsedTime(total_ms, t0, t1); }
         cudaEventDestroy(t0); cudaEventDestroy(t1);
+        if (rc == 0) { *out = s; return 0; }
         pa_session_destroy(s);
-        lap("destroy");
-        // sticky device flag: exception list overflow / boxes too wide for the cell path / non-finite
-        // coordinates.  Redo without cells first, then with the general kernel (always applicable).
         if (rc == PA_ERR_UNSUPPORTED && getenv("PA_DEBUG")) fprintf(stderr, "[prealpha_b200] attempt %d: %s -> retrying with a more general kernel\n", attempt, pa_last_error());
         if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_NO_CELLS)) { ex.flags |= PA_EXEC_NO_CELLS; continue; }
         if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_FORCE_GENERAL)) { ex.flags |= PA_EXEC_FORCE_GENERAL; continue; }
@@ -776,6 +820,206 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
     }
     return PA_ERR_UNSUPPORTED;
 }
+
+int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int32_t njobs, const pa_exec *exec,
+                                    int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, pa_stats *stats)
+{
+    if (!traj || !jobs || njobs < 1) { pa::set_error("bad argument"); return PA_ERR_BAD_ARG; }
+    pa_exec ex{};
+    if (exec) ex = *exec;
+    if (ex.shard_count < 1) ex.shard_count = 1;
+    if (ex.tile_shard_count < 1) ex.tile_shard_count = 1;
+    if (ex.shard_rank < 0 || ex.shard_rank >= ex.shard_count || ex.tile_shard_rank < 0 || ex.tile_shard_rank >= ex.tile_shard_count) {
+        pa::set_error("bad shard"); return PA_ERR_BAD_ARG;
+    }
+    const int dt = jobs[0].sampling_interval;
+    for (int j = 1; j < njobs; ++j)
+        if (jobs[j].sampling_interval != dt) { pa::set_error("jobs of one call must share sampling_interval"); return PA_ERR_BAD_ARG; }
+    if (dt < 1) { pa::set_error("sampling_interval < 1"); return PA_ERR_BAD_ARG; }
+    if (ex.ndevices > 1 || ex.ndevices < 0)
+        return pa_multi_device_histogram(traj, jobs, njobs, ex, hists, within_bin, out_of_bounds, stats);
+    pa_session *s = nullptr;
+    float total_ms = 0.f;
+    int rc = run_share_on_device(traj, jobs, njobs, ex, &s, &total_ms);
+    if (rc) return rc;
+    rc = pa_session_download(s, hists, within_bin, out_of_bounds, 0);
+    if (stats) { pa_session_stats(s, stats); stats->total_ms = total_ms; }
+    pa_session_destroy(s);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------
+// several devices inside one call (pa_exec.ndevices): the parallel region of iterate_timesteps_parallelised
+// (Distribution:704-753) with one host thread per GPU instead of one per core, and the CRITICAL-section merge of the
+// private histograms (Distribution:745-751) as ONE ncclReduce(sum) of the int64 accumulators over NVLink.
+namespace {
+
+__global__ void pa_acc_add_kernel(unsigned long long *dst, const unsigned long long *src, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
+// NCCL is loaded at run time (libnccl.so.2 is in the image; a process that already uses NCCL, e.g. through
+// torch.distributed, shares its copy), so that single-GPU users need no NCCL at all.
+struct NcclApi {
+    void *lib = nullptr;
+    int (*CommInitAll)(void **, int, const int *) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void *, void *, size_t, int, int, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+std::mutex g_nccl_mutex;
+NcclApi g_nccl;
+bool g_nccl_tried = false;
+struct CommSet { std::vector<int> devs; std::vector<void *> comms; };
+std::vector<CommSet> g_comm_cache;
+
+const NcclApi &nccl_api()
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (g_nccl_tried) return g_nccl;
+    g_nccl_tried = true;
+    if (getenv("PA_NO_NCCL")) return g_nccl;                 // test hook: exercise the peer-copy path
+    for (const char *name : { "libnccl.so.2", "libnccl.so" }) {
+        g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) return g_nccl;
+    g_nccl.CommInitAll = (int (*)(void **, int, const int *))dlsym(g_nccl.lib, "ncclCommInitAll");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GroupStart = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
+    g_nccl.Reduce = (int (*)(const void *, void *, size_t, int, int, int, void *, cudaStream_t))dlsym(g_nccl.lib, "ncclReduce");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.GroupStart && g_nccl.GroupEnd && g_nccl.Reduce;
+    return g_nccl;
+}
+
+// communicators are expensive to create (hundreds of ms): one set per device list, kept until pa_trim()
+std::vector<void *> nccl_comms_for(const std::vector<int> &devs)
+{
+    const NcclApi &api = nccl_api();
+    if (!api.ok) return {};
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    for (const CommSet &c : g_comm_cache) if (c.devs == devs) return c.comms;
+    CommSet c;
+    c.devs = devs; c.comms.assign(devs.size(), nullptr);
+    if (api.CommInitAll(c.comms.data(), (int)devs.size(), devs.data()) != 0) return {};
+    g_comm_cache.push_back(c);
+    return c.comms;
+}
+
+}  // namespace
+
+void pa_multi_device_trim()
+{
+    std::lock_guard<std::mutex> lock(g_nccl_mutex);
+    if (g_nccl.ok)
+        for (CommSet &c : g_comm_cache)
+            for (void *comm : c.comms) if (comm) g_nccl.CommDestroy(comm);
+    g_comm_cache.clear();
+}
+
+int pa_multi_device_histogram(const pa_traj *traj, const pa_job *jobs, int32_t njobs, pa_exec ex,
+                              int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, pa_stats *stats)
+{
+    const int usable = pa_device_count();
+    int n = ex.ndevices < 0 ? usable - ex.device : ex.ndevices;
+    if (usable < 1) { pa::set_error("no CUDA device (this path has no CPU fallback)"); return PA_ERR_NO_DEVICE; }
+    if (n < 1 || ex.device < 0 || ex.device + n > usable) { pa::set_error("pa_exec.device/ndevices: not that many usable devices"); return PA_ERR_BAD_ARG; }
+    ex.ndevices = 1;
+    if (n == 1) return pa_distribution_histogram_multi(traj, jobs, njobs, &ex, hists, within_bin, out_of_bounds, stats);
+    const int dt = jobs[0].sampling_interval;
+    const int nsamp = (traj->nsteps + dt - 1) / dt;
+    const int nlocal = nsamp > ex.shard_rank ? (nsamp - ex.shard_rank + ex.shard_count - 1) / ex.shard_count : 0;
+    // enough frames: every device takes whole frames (no replicated per-frame work); otherwise the frames are few and
+    // huge, and the devices split the work items of each frame
+    const bool by_frames = nlocal >= n;
+    std::vector<int> devs(n);
+    for (int d = 0; d < n; ++d) devs[d] = ex.device + d;
+    // communicators are created while the kernels run
+    std::vector<void *> comms;
+    std::thread comm_thread([&] { comms = nccl_comms_for(devs); });
+    std::vector<pa_session *> sess(n, nullptr);
+    std::vector<int> rcs(n, 0);
+    std::vector<float> total_ms(n, 0.f);
+    std::vector<std::string> errs(n);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < n; ++d) {
+        workers.emplace_back([&, d] {
+            pa_exec e = ex;
+            e.device = devs[d];
+            if (by_frames) { e.shard_rank = ex.shard_rank + ex.shard_count * d; e.shard_count = ex.shard_count * n; }
+            else { e.tile_shard_rank = ex.tile_shard_rank + ex.tile_shard_count * d; e.tile_shard_count = ex.tile_shard_count * n; }
+            rcs[d] = run_share_on_device(traj, jobs, njobs, e, &sess[d], &total_ms[d]);
+            if (rcs[d]) errs[d] = pa_last_error();
+        });
+    }
+    for (auto &w : workers) w.join();
+    comm_thread.join();
+    int rc = 0;
+    for (int d = 0; d < n && rc == 0; ++d) if (rcs[d]) { rc = rcs[d]; pa::set_error("device " + std::to_string(devs[d]) + ": " + errs[d]); }
+    // ---- combine the integer accumulators on the first device ------------------------------------------------
+    const size_t words = rc == 0 ? sess[0]->acc_words : 0;
+    bool reduced = false;
+    if (rc == 0 && !comms.empty()) {
+        const NcclApi &api = nccl_api();
+        int nrc = api.GroupStart();
+        for (int d = 0; d < n && nrc == 0; ++d) {
+            cudaSetDevice(devs[d]);
+            nrc = api.Reduce(sess[d]->d_acc, sess[d]->d_acc, words, /*ncclUint64*/ 5, /*ncclSum*/ 0, 0, comms[d], sess[d]->s_compute);
+        }
+        const int erc = api.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        for (int d = 0; d < n; ++d) { cudaSetDevice(devs[d]); cudaStreamSynchronize(sess[d]->s_compute); }
+        if (nrc == 0) reduced = true;
+        else if (getenv("PA_DEBUG")) fprintf(stderr, "[prealpha_b200] ncclReduce failed (%s): falling back to peer copies\n", api.GetErrorString ? api.GetErrorString(nrc) : "?");
+    }
+    if (rc == 0 && !reduced) {
+        // peer copies + add kernel (libnccl not loadable): device d's accumulators are copied to a scratch buffer on the
+        // first device and added there; 16 KB per job, so the serial order does not matter
+        cudaSetDevice(devs[0]);
+        unsigned long long *scratch = nullptr;
+        if (cudaMalloc(&scratch, sizeof(unsigned long long) * words) != cudaSuccess) { pa::set_error("cudaMalloc (reduce scratch)"); rc = PA_ERR_CUDA; }
+        for (int d = 1; d < n && rc == 0; ++d) {
+            if (cudaMemcpyPeerAsync(scratch, devs[0], sess[d]->d_acc, devs[d], sizeof(unsigned long long) * words, sess[0]->s_compute) != cudaSuccess) {
+                pa::set_error("cudaMemcpyPeerAsync"); rc = PA_ERR_CUDA; break;
+            }
+            pa_acc_add_kernel<<<(unsigned)std::min<size_t>((words + 255) / 256, 1184), 256, 0, sess[0]->s_compute>>>(sess[0]->d_acc, scratch, words);
+        }
+        if (rc == 0 && cudaStreamSynchronize(sess[0]->s_compute) != cudaSuccess) { pa::set_error("peer reduce"); rc = PA_ERR_CUDA; }
+        cudaFree(scratch);
+    }
+    if (rc == 0) rc = pa_session_download(sess[0], hists, within_bin, out_of_bounds, 0);
+    if (rc == 0 && stats) {
+        pa_stats sum{};
+        for (int d = 0; d < n; ++d) {
+            pa_stats st{};
+            pa_session_stats(sess[d], &st);
+            sum.pairs_evaluated += st.pairs_evaluated;
+            sum.frames_done = by_frames ? sum.frames_done + st.frames_done : st.frames_done;
+            sum.kernel_launches += st.kernel_launches; sum.exception_pairs += st.exception_pairs;
+            sum.h2d_bytes += st.h2d_bytes; sum.d2h_bytes += st.d2h_bytes;
+            sum.kernel_ms = std::max(sum.kernel_ms, st.kernel_ms);
+            sum.total_ms = std::max(sum.total_ms, (double)total_ms[d]);
+            sum.cell_pair_evals += st.cell_pair_evals; sum.smem_atomics += st.smem_atomics; sum.unique_pairs_counted += st.unique_pairs_counted;
+            sum.dominant_launches += st.dominant_launches; sum.dominant_ms = std::max(sum.dominant_ms, st.dominant_ms);
+            sum.dominant_pair_evals += st.dominant_pair_evals; sum.dominant_atomics += st.dominant_atomics;
+        }
+        sum.pairs_binned = 0;
+        for (int j = 0; j < njobs; ++j) if (within_bin) sum.pairs_binned += within_bin[j];
+        *stats = sum;
+    }
+    for (int d = 0; d < n; ++d) if (sess[d]) pa_session_destroy(sess[d]);
+    return rc;
+}
+
+extern "C" {
 
 int pa_distribution_histogram(const pa_traj *traj, const pa_job *job, int64_t *hist, int64_t *within_bin, int64_t *out_of_bounds)
 {

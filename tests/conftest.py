@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "big: full-size parity cases (minutes of host CPU for the oracle); part of -m gpu")
 
 
 @pytest.fixture(scope="session")

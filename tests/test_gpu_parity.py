@@ -79,6 +79,37 @@ def test_frame_shards_add_up(oracle):
             assert np.array_equal(acc[k], full[0][k]) and w[k] == full[1][k]
 
 
+def test_tile_shards_add_up(oracle):
+    """The split below the frame (pa_exec.tile_shard_*: work items of ONE frame dealt out to several GPUs) adds up to the
+    oracle's histogram for every kernel family: brute-force RDF, brute-force general (2-D, cdf), charge_arm (first shard
+    only), and -- combined with frame shards -- for any combination of the two splits."""
+    fx = fixtures.Fixture("synth")
+    traj = fx.trajectory()
+    pjobs = [api.job_setup(traj, rq) for _, _, rq, _ in fx.jobs()]
+    pjobs = [j for j in pjobs if j.sampling_interval == pjobs[0].sampling_interval]
+    full = api.histogram_multi(traj, pjobs)
+    for k, job in enumerate(pjobs):
+        h0, w0, o0 = oracle.histogram(traj, job)
+        assert np.array_equal(full[0][k], h0) and (int(full[1][k]), int(full[2][k])) == (w0, o0)
+    for fcount, tcount in ((1, 2), (1, 5), (2, 3)):
+        acc = [np.zeros_like(h) for h in full[0]]
+        w = np.zeros(len(pjobs), dtype=np.int64)
+        o = np.zeros(len(pjobs), dtype=np.int64)
+        evals = 0
+        for fr in range(fcount):
+            for tr in range(tcount):
+                h, wi, oo, st = api.histogram_multi(traj, pjobs, api.make_exec(shard_rank=fr, shard_count=fcount,
+                                                                               tile_shard_rank=tr, tile_shard_count=tcount))
+                for k in range(len(pjobs)):
+                    acc[k] += h[k]
+                w += wi
+                o += oo
+                evals += st.pairs_evaluated
+        for k in range(len(pjobs)):
+            assert np.array_equal(acc[k], full[0][k]) and w[k] == full[1][k] and o[k] == full[2][k], (fcount, tcount, k)
+        assert evals == full[3].pairs_evaluated
+
+
 def test_small_batches_and_sessions(oracle):
     fx = fixtures.Fixture("re4_atoms")
     traj = fx.trajectory()
@@ -209,6 +240,18 @@ def test_cell_sorted_kernel_against_oracle(name, kw, oracle):
         h0, w0, o0 = oracle.histogram(traj, pjobs[k])
         assert np.array_equal(cells[0][k], h0) and (int(cells[1][k]), int(cells[2][k])) == (w0, o0), (name, k)
     assert int(cells[2].sum()) > 0, "the planted (anti)parallel / coincident pairs must show up as out of bounds"
+    if name == "uniform":                                            # tile shards of the cell-sorted launches add up as well
+        acc = [np.zeros_like(h) for h in cells[0]]
+        w = np.zeros(len(pjobs), dtype=np.int64)
+        o = np.zeros(len(pjobs), dtype=np.int64)
+        for tr in range(3):
+            h, wi, oo, _ = api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY, tile_shard_rank=tr, tile_shard_count=3))
+            for k in range(len(pjobs)):
+                acc[k] += h[k]
+            w += wi
+            o += oo
+        for k in range(len(pjobs)):
+            assert np.array_equal(acc[k], cells[0][k]) and w[k] == cells[1][k] and o[k] == cells[2][k], (name, k)
 
 
 def test_full_size_frame_launch_combinations_agree():

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(capi.SIGNATURES), (declared ^ set(capi.SIGNATURES))
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pa_abi_version() == 1
+    assert lib.pa_abi_version() == 2
 
 
 def test_struct_layout_matches_header_sizes():
@@ -31,7 +31,7 @@ def test_struct_layout_matches_header_sizes():
     assert C.sizeof(capi.pa_type) == 56
     assert C.sizeof(capi.pa_traj) == 16 + 48 + 8 + 8
     assert C.sizeof(capi.pa_job) == 4 * 6 + 24 + 72 + 16 + 8 * 4
-    assert C.sizeof(capi.pa_exec) == 24
+    assert C.sizeof(capi.pa_exec) == 32
 
 
 def test_ctypes_structs_match_the_header_as_compiled_by_gcc(tmp_path):
