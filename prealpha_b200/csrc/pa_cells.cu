@@ -23,17 +23,24 @@
 #include "pa_internal.h"
 #include "pa_pair_exact.cuh"
 
-#define PC_THREADS 128
+// RDF kernel: every WARP is autonomous -- it owns a tile of 32*PC_RI reference molecules (a compact slab of one row of
+// cells), takes its own work items, classifies the observed cell layers against ITS bounding box, stages observed
+// molecules into its own slice of shared memory and never meets a CTA-wide barrier inside the work loop; only the
+// class counters (and the threshold table) are shared by the warps of a CTA.
+#define PC_WARPS 4
+#define PC_THREADS (32 * PC_WARPS)
 #define PC_RI 2
-#define PC_TILE (PC_THREADS * PC_RI)
-#define PC_JC 128
+#define PC_TILE (32 * PC_RI)
+#define PC_JC 32                    // observed molecules staged per chunk: one per lane
 #define PC_MAXG 256
+// general (2-D) kernel: CTA-wide tiles
+#define PG_THREADS 128
+#define PG_RI 2
+#define PC_GTILE (PG_THREADS * PG_RI)
+#define PG_JC 128
 
-// Reference molecule r (0..PC_RI-1) of this thread inside its tile: every warp owns 32*PC_RI consecutive molecules of
-// the tile's sorted order, i.e. a compact slab of the tile (the tile is a run of x-cells), so that "every pair of this
-// warp with observed molecule j is beyond the cutoff" is a common, warp-uniform event that skips the class computation
-// and the shared-memory atomics (pc_segment_f32).
-static __device__ __forceinline__ int pc_kidx(int r) { return (int)(threadIdx.x >> 5) * (32 * PC_RI) + r * 32 + (int)(threadIdx.x & 31); }
+// Reference molecule r (0..PC_RI-1) of this lane inside its warp's tile (consecutive in the row's sorted order).
+static __device__ __forceinline__ int pc_kidx(int r) { return r * 32 + (int)(threadIdx.x & 31); }
 
 static __device__ __forceinline__ unsigned long long dbits(double x) { return (unsigned long long)__double_as_longlong(x); }
 // order-preserving map double -> uint64 (for atomicMin/atomicMax on coordinates)
@@ -116,31 +123,71 @@ __global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, PaPo
     }
 }
 
-// K4: reference tiles = greedy runs of x-neighbouring cells of one (y,z) row, <= PC_TILE molecules
-// and at most max_run cells wide (so that tile width + cell width stays below L/2).
-__global__ void __launch_bounds__(128) pa_build_tiles_kernel(PaCellGrid g, int nframes, int max_run, PaTile *tiles, unsigned int *ntiles, unsigned int cap)
+// K4: reference tiles.  Two kinds, both numbered deterministically (count per row -> exclusive scan -> fill), because
+// tile shards on different GPUs (pa_exec.tile_shard_*) must agree on which tile is which:
+//   CHUNKS = false: greedy runs of x-neighbouring cells of one (y,z) row, <= PC_GTILE molecules and at most max_run cells
+//                   wide (so that tile width + cell width stays below L/2) -- the general kernel's tiles;
+//   CHUNKS = true:  consecutive PC_TILE-molecule pieces of a row's sorted order (x-cell ascending), cut without regard
+//                   to cell boundaries -- one warp's worth of reference molecules of the RDF kernel, a compact slab.
+template <bool CHUNKS, bool FILL>
+__global__ void __launch_bounds__(128) pa_build_tiles_kernel(PaCellGrid g, int nframes, int max_run, PaTile *tiles, int *row_off, unsigned int cap)
 {
     const int rows = g.g[1] * g.g[2], gx = g.g[0];
     const int id = blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= nframes * rows) return;
     const int f = id / rows, row = id % rows;
     const int *cs = g.cell_start + (long long)f * (g.ncell + 1) + (long long)row * gx;
-    int cx = 0;
-    while (cx < gx) {
-        int beg = cs[cx], c1 = cx, cnt = cs[cx + 1] - beg;
-        while (c1 + 1 < gx && (c1 + 1 - cx) < max_run && (cs[c1 + 2] - beg) <= PC_TILE) { ++c1; cnt = cs[c1 + 1] - beg; }
-        // a single over-full cell is split into several tiles
-        for (int off = 0; off < cnt; off += PC_TILE) {
-            const unsigned int t = atomicAdd(ntiles, 1u);
-            if (t < cap) {
+    unsigned int t = FILL ? (unsigned int)row_off[id] : 0u;
+    int n = 0;
+    if (CHUNKS) {
+        const int beg = cs[0], cnt = cs[gx] - beg;
+        for (int off = 0; off < cnt; off += PC_TILE, ++n) {
+            if (FILL && t + n < cap) {
                 PaTile tl;
                 tl.frame = f; tl.begin = beg + off; tl.count = min(PC_TILE, cnt - off);
-                tl.cx0 = cx; tl.cx1 = c1; tl.cy = row % g.g[1]; tl.cz = row / g.g[1]; tl.pad = 0;
-                tiles[t] = tl;
+                tl.cx0 = 0; tl.cx1 = gx - 1; tl.cy = row % g.g[1]; tl.cz = row / g.g[1]; tl.pad = 0;
+                tiles[t + n] = tl;
             }
         }
-        cx = c1 + 1;
+    } else {
+        int cx = 0;
+        while (cx < gx) {
+            int beg = cs[cx], c1 = cx, cnt = cs[cx + 1] - beg;
+            while (c1 + 1 < gx && (c1 + 1 - cx) < max_run && (cs[c1 + 2] - beg) <= PC_GTILE) { ++c1; cnt = cs[c1 + 1] - beg; }
+            // a single over-full cell is split into several tiles
+            for (int off = 0; off < cnt; off += PC_GTILE, ++n) {
+                if (FILL && t + n < cap) {
+                    PaTile tl;
+                    tl.frame = f; tl.begin = beg + off; tl.count = min(PC_GTILE, cnt - off);
+                    tl.cx0 = cx; tl.cx1 = c1; tl.cy = row % g.g[1]; tl.cz = row / g.g[1]; tl.pad = 0;
+                    tiles[t + n] = tl;
+                }
+            }
+            cx = c1 + 1;
+        }
     }
+    if (!FILL) row_off[id] = n;
+}
+
+// exclusive scan of row_off[0..n) in place (one block), total -> *ntiles
+__global__ void __launch_bounds__(1024) pa_tile_scan_kernel(int *row_off, int n, unsigned int *ntiles)
+{
+    __shared__ int s_part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = min(n, (int)threadIdx.x * per), e = min(n, b + per);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += row_off[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = threadIdx.x ? s_part[threadIdx.x - 1] : 0;
+    for (int i = b; i < e; ++i) { const int c = row_off[i]; row_off[i] = run; run += c; }
+    if (threadIdx.x == 1023) *ntiles = (unsigned int)s_part[1023];
 }
 
 // ---------------------------------------------------------------------------
@@ -195,11 +242,6 @@ struct PcShared {           // general kernel
     PcLayer lay[3][PC_MAXG];
     int work_item;
 };
-struct PcSharedR {          // RDF kernel (its layer table is sized at launch)
-    int work_item;
-    unsigned int t2_bits;    // float bits of the largest squared distance of a tile molecule from the tile origin
-};
-
 // Shared-memory class tables: thresholds thr[k] (8-byte stride, k = 0..na+2) and counters cnt[k]
 // (4-byte stride, so that the 32 lanes of an ATOMS spread over all 32 banks).
 static __device__ __forceinline__ double pc_lds_f64(unsigned int addr)
@@ -267,9 +309,9 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
     constexpr int NP = 2 * PC_RI;
     constexpr int ND = MX + MY + MZ;                    // doubles per staged observed molecule
     for (int jc = jb; jc < je; jc += PC_JC) {
-        __syncthreads();
+        __syncwarp();
         {
-            const int t = threadIdx.x;                  // PC_JC == PC_THREADS
+            const int t = threadIdx.x & 31;             // PC_JC == 32: one staged molecule per lane, in the warp's own buffer
             const int j = jc + t;
             double x = 1.0e15, y = 1.0e15, z = 1.0e15;  // padding: far away, finite in float range
             if (j < je) { x = go.sx[jbase + j]; y = go.sy[jbase + j]; z = go.sz[jbase + j]; }
@@ -279,7 +321,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
             rec[o++] = __dadd_rn(y, sya); if (MY == 2) rec[o++] = __dadd_rn(y, syb);
             rec[o++] = __dadd_rn(z, sza); if (MZ == 2) rec[o++] = __dadd_rn(z, szb);
         }
-        __syncthreads();
+        __syncwarp();
         const int cnt = min(PC_JC, je - jc);
         it_all += (unsigned)((cnt + 1) / 2); it_live += (unsigned)((cnt + 1) / 2);   // statistics: no iteration is skipped here
         for (int jj = 0; jj < cnt; jj += 2) {
@@ -528,7 +570,7 @@ static __device__ __forceinline__ unsigned long long pc_min2(unsigned long long 
 
 // MX/MY/MZ: 1 = single image, 2 = two candidate images for that component (at most one component; its second
 // candidate travels in the .w lane of the staged float4, and the squared component is the smaller of the two squares)
-template <int MX, int MY, int MZ, bool ZCOL, bool NEAR, bool VERIFY>
+template <int MX, int MY, int MZ, bool ZCOL, bool NEAR, bool VERIFY, bool DEADSKIP>
 static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                       const float (&xf)[PC_RI], const float (&yf)[PC_RI], const float (&zf)[PC_RI],
                                                       const unsigned int (&cb)[PC_RI],
@@ -543,6 +585,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
     static_assert(MX + MY + MZ <= 4, "at most one component with two candidate images");
     constexpr int ND = MX + MY + MZ;
     static_assert(PC_TILE <= 512 && PC_JC <= 128, "queue entry layout");
+    static_assert(PC_JC == 32, "one staged molecule per lane");
     int qn = 0;                                         // entries in this warp's queue (warp-uniform)
     const unsigned int lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     const unsigned long long X01 = pc_pack(xf[0], xf[1]), Y01 = pc_pack(yf[0], yf[1]), Z01 = pc_pack(zf[0], zf[1]);
@@ -553,11 +596,12 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
     const unsigned int trash = T.cnt + (unsigned)(na + 2) * 4u;
     const unsigned int a_jf = (unsigned int)__cvta_generic_to_shared(s_jf), a_j = (unsigned int)__cvta_generic_to_shared(s_j);
     constexpr int NU = 2;                               // staged molecules per iteration (4 measured slower)
+    static_assert(NU == 2, "the warp-uniform skip test and the statistics assume two staged molecules per iteration");
     constexpr int NP = NU * PC_RI;
     for (int jc = jb; jc < je; jc += PC_JC) {
-        __syncthreads();
+        __syncwarp();
         {
-            const int t = threadIdx.x;
+            const int t = threadIdx.x & 31;
             const int j = jc + t;
             double x = 1.0e15, y = 1.0e15, z = 1.0e15, b2 = 1.0e15;      // b2: second candidate of the two-image component
             float4 f = make_float4(T.pad_x, 0.0f, 0.0f, MX == 2 ? T.pad_x : 0.0f);
@@ -578,7 +622,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
             }
             s_jf[t] = f;
         }
-        __syncthreads();
+        __syncwarp();
         const int cnt = min(PC_JC, je - jc);
         it_all += (unsigned)((cnt + NU - 1) / NU);
         const unsigned int a_end = a_jf + (unsigned)cnt * 16u;
@@ -617,7 +661,7 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
             // Warp-uniform skip: when every pair of this iteration (4 per lane: the warp's slab of the tile against two
             // observed molecules) has d2~ >= dead_d2, every lower class bracket is > na -- such a pair is never counted
             // and never queued (see `need` below) -- so the square roots, brackets and atomics are skipped altogether.
-            {
+            if (DEADSKIP) {
                 const float m01 = fminf(fminf(pc_lo(d2q[0]), pc_hi(d2q[0])), fminf(pc_lo(d2q[NU - 1]), pc_hi(d2q[NU - 1])));
                 if (__all_sync(0xffffffffu, m01 >= dead_d2)) {
                     if (VERIFY) {
@@ -735,25 +779,88 @@ static __device__ void pc_flush(const PaPass &p, const PcTables &T, bool reset)
     }
 }
 
-// PART 0: every run in one launch.  PART 1 / PART 2: the float32-eligible runs (far, single image) and all other
-// runs as two launches over the same work items, so that each gets its own register allocation.
-template <int VARIANT, bool VERIFY, bool SYM, int PART>
+// The same flush by ONE warp while the other warps of the CTA keep counting: every counter is fetched and zeroed with
+// an atomic exchange, so no increment is lost or seen twice.  Used before the 32-bit counters could wrap.
+static __device__ __forceinline__ unsigned int pc_exch_u32(unsigned int addr)
+{
+    unsigned int v;
+    asm volatile("atom.shared.exch.b32 %0, [%1], 0;" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+template <int VARIANT>
+static __device__ __noinline__ void pc_flush_warp(const PaPass &p, const PcTables &T)
+{
+    const int na = T.na, lane = threadIdx.x & 31;
+    const long long mult = p.sym ? 2 : 1;
+    unsigned long long within = 0;
+    for (int k = lane; k < na + 3; k += 32) {
+        if (k >= na && !(VARIANT == 1 && k == na)) continue;                                        // ignored classes
+        const unsigned int c = pc_exch_u32(T.cnt + (unsigned)k * 4u);
+        if (!c) continue;
+        if (k < na) {
+            atomicAdd(&p.job.acc[k], (unsigned long long)((long long)c * p.weight * mult));
+            if (p.acc2) atomicAdd(&p.acc2[k], (unsigned long long)((long long)c * p.weight2));
+            within += c;
+        } else {
+            atomicAdd(&p.job.acc[na + 1], (unsigned long long)((long long)c * mult));
+            if (p.acc2) atomicAdd(&p.acc2[na + 1], (unsigned long long)c);
+        }
+    }
+    if (within) {
+        atomicAdd(&p.job.acc[na], within * (unsigned long long)mult);
+        if (p.acc2) atomicAdd(&p.acc2[na], within);
+        if (p.kstats) atomicAdd(p.kstats + 2, within);
+    }
+    if (VARIANT == 0 && lane == 0) {
+        const unsigned int c = pc_exch_u32(T.special);
+        if (c) {
+            atomicAdd(&p.job.acc[na + 1], (unsigned long long)((long long)c * mult));
+            if (p.acc2) atomicAdd(&p.acc2[na + 1], (unsigned long long)c);
+        }
+    }
+    __syncwarp();
+}
+
+// warp-wide minimum / maximum of a double (all lanes receive the result)
+static __device__ __forceinline__ double pc_warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+static __device__ __forceinline__ double pc_warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// PART 0: every run in one launch.  PART 1 / PART 2: the float32-eligible runs (single image or one two-image
+// component) and all other runs as two launches over the same work items, so that each gets its own register allocation.
+// DEADSKIP (PART 1): warp-uniform skip of iterations whose pairs are all beyond the cutoff (see pc_segment_f32).
+template <int VARIANT, bool VERIFY, bool SYM, int PART, bool DEADSKIP>
 __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
                                                                    const unsigned int *ntiles_ptr, unsigned int tile_cap,
                                                                    unsigned int *work_counter, int nzg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int na = p.job.bin_a;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool f32_on = VARIANT == 0 && PART != 0 && p.f32_cnt > 0;       // PART 0 is launched only when float32 segments are off
     const int ncnt = ((f32_on && PART == 1) ? p.f32_cnt + na + 8 : na + 3) + 1;                          // counters (see pc_segment_f32) + the class-na counter
-    // PART 1 (float32 runs only): at most 4 staged doubles per molecule and no threshold table (read from global when needed)
-    double *s_j = reinterpret_cast<double *>(smem_raw);                                   // PC_JC*6 doubles (PART 1: *4)
-    float4 *s_jf = reinterpret_cast<float4 *>(s_j + PC_JC * (PART == 1 ? 4 : 6));         // PC_JC float4
-    unsigned long long *s_thr = reinterpret_cast<unsigned long long *>(s_jf + PC_JC);     // na+3 (PART 1: none)
+    const int nlay = go.g[0] + go.g[1] + go.g[2];
+    // CTA-wide: threshold table (PART 1 reads it from global memory when needed) and the class counters
+    unsigned long long *s_thr = reinterpret_cast<unsigned long long *>(smem_raw);          // na+3 (PART 1: none)
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_thr + (PART == 1 ? 0 : na + 3));   // ncnt (+1 pad)
-    PcSharedR *sh = reinterpret_cast<PcSharedR *>(s_cnt + ((ncnt + 1) & ~1));
-    PcLayer *lay = reinterpret_cast<PcLayer *>(sh + 1);                                   // gx+gy+gz entries: x layers, y layers, z layers
-    unsigned long long *queue = reinterpret_cast<unsigned long long *>(lay + (go.g[0] + go.g[1] + go.g[2])) + (threadIdx.x >> 5) * PC_QCAP;   // PART 1: per warp
+    // per warp (16-byte aligned slices): staged observed molecules as doubles (PC_JC*6, PART 1: *4) and as local float4,
+    // the layer classification of the warp's tile (x layers, y layers, z layers) and the queue of deferred exact decisions
+    constexpr int NDMAX = PART == 1 ? 4 : 6;
+    const size_t warp_bytes = (size_t)PC_JC * NDMAX * 8 + (size_t)PC_JC * 16 + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15) + (size_t)PC_QCAP * 8;
+    unsigned char *wbase = smem_raw + ((((size_t)(PART == 1 ? 0 : na + 3) * 8 + (size_t)(ncnt + 1) * 4) + 15) & ~(size_t)15) + (size_t)warp * warp_bytes;
+    double *s_j = reinterpret_cast<double *>(wbase);
+    float4 *s_jf = reinterpret_cast<float4 *>(s_j + PC_JC * NDMAX);
+    PcLayer *lay = reinterpret_cast<PcLayer *>(s_jf + PC_JC);
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lay) + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15));
 
     for (int k = threadIdx.x; k < (PART == 1 ? 0 : na + 3); k += blockDim.x)
         s_thr[k] = p.job.thr_a[k];       // "never" (all ones) is a NaN as a double: every `d2 >= NaN` is false, as required
@@ -781,7 +888,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     const unsigned int ntiles = min(*ntiles_ptr, tile_cap);
     if (*ntiles_ptr > tile_cap && threadIdx.x == 0 && blockIdx.x == 0) atomicOr(p.flags + 1, 1u);
     const long long n_items = (long long)ntiles * nzg;
-    unsigned long long since_flush = 0;
+    unsigned long long since_flush = 0;                       // this warp's increments since its own last flush
     const int gx = go.g[0], gy = go.g[1], gz = go.g[2];
     // statistics (warp-uniform): loop iterations (4 pair evaluations per lane each) and those that issued their atomics
     unsigned int it_all = 0, it_live = 0;
@@ -789,19 +896,21 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
 
     for (;;) {
         st_all += it_all; st_live += it_live; it_all = it_live = 0;
-        __syncthreads();
-        if (threadIdx.x == 0) { sh->work_item = (int)atomicAdd(work_counter, 1u); sh->t2_bits = 0u; }
-        __syncthreads();
-        const long long item = (long long)sh->work_item * p.tshard_count + p.tshard_rank;   // tile shard: items w with w % count == rank
+        __syncwarp();
+        unsigned int w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        const long long item = (long long)w * p.tshard_count + p.tshard_rank;   // tile shard: items w with w % count == rank
         if (item >= n_items) break;
         const PaTile tl = tiles[item / nzg];
         const int zg = (int)(item % nzg);
         const int z0 = (int)((long long)gz * zg / nzg), z1 = (int)((long long)gz * (zg + 1) / nzg);
         if (z0 == z1) continue;
-        // reference molecules of the tile -> registers
+        // reference molecules of the tile -> registers; padded slots are a copy of the tile's last molecule for the
+        // float32 coordinates (so that they never decide a warp-uniform test) and far away for the fp64 segments
         double p1x[PC_RI], p1y[PC_RI], p1z[PC_RI];
+        double q1x[PC_RI], q1y[PC_RI], q1z[PC_RI];
         const long long ibase = (long long)tl.frame * gi.nmol;
-        double q1x[PC_RI], q1y[PC_RI], q1z[PC_RI];         // padded slots: a copy of the tile's last molecule (float32 segments)
 #pragma unroll
         for (int r = 0; r < PC_RI; ++r) {
             const int k = pc_kidx(r), kk = min(k, tl.count - 1);
@@ -809,61 +918,58 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
             if (k < tl.count) { p1x[r] = q1x[r]; p1y[r] = q1y[r]; p1z[r] = q1z[r]; }
             else p1x[r] = p1y[r] = p1z[r] = -1.0e15;   // padding: far away, finite in float range
         }
-        // float32 segments: local coordinates about the centre of the tile's cells
+        // exact bounding box of the tile (padded slots repeat a real molecule, so they do not widen it)
+        double blox = q1x[0], bloy = q1y[0], bloz = q1z[0], bhix = q1x[0], bhiy = q1y[0], bhiz = q1z[0];
+#pragma unroll
+        for (int r = 1; r < PC_RI; ++r) {
+            blox = fmin(blox, q1x[r]); bhix = fmax(bhix, q1x[r]);
+            bloy = fmin(bloy, q1y[r]); bhiy = fmax(bhiy, q1y[r]);
+            bloz = fmin(bloz, q1z[r]); bhiz = fmax(bhiz, q1z[r]);
+        }
+        blox = pc_warp_min(blox); bloy = pc_warp_min(bloy); bloz = pc_warp_min(bloz);
+        bhix = pc_warp_max(bhix); bhiy = pc_warp_max(bhiy); bhiz = pc_warp_max(bhiz);
+        // float32 segments: local coordinates about the centre of the tile's bounding box
         float xf[PC_RI], yf[PC_RI], zf[PC_RI];
         unsigned int cb[PC_RI];
-        const double ox = p.box.lo[0] + 0.5 * (double)(tl.cx0 + tl.cx1 + 1) / gi.inv_w[0];
-        const double oy = p.box.lo[1] + ((double)tl.cy + 0.5) / gi.inv_w[1];
-        const double oz = p.box.lo[2] + ((double)tl.cz + 0.5) / gi.inv_w[2];
+        const double ox = 0.5 * (blox + bhix), oy = 0.5 * (bloy + bhiy), oz = 0.5 * (bloz + bhiz);
+        float tile_t2 = 0.0f;
         if (f32_on) {
-            float t2 = 0.0f;
 #pragma unroll
             for (int r = 0; r < PC_RI; ++r) {
-                // padded slots sit on the tile's last molecule (so that they do not spoil the warp-uniform "beyond the
-                // cutoff" test) and count into the shifted counter window
                 const bool live = pc_kidx(r) < tl.count;
                 xf[r] = __double2float_rn(__dsub_rn(q1x[r], ox));
                 yf[r] = __double2float_rn(__dsub_rn(q1y[r], oy));
                 zf[r] = __double2float_rn(__dsub_rn(q1z[r], oz));
-                cb[r] = T.cnt - 0x4B000000u * 4u + (live ? 0u : T.cnt_pad);
-                t2 = fmaxf(t2, __fmaf_ru(zf[r], zf[r], __fmaf_ru(yf[r], yf[r], __fmul_ru(xf[r], xf[r]))));
+                cb[r] = T.cnt - 0x4B000000u * 4u + (live ? 0u : T.cnt_pad);      // padded slots count into a window nobody reads
+                tile_t2 = fmaxf(tile_t2, __fmaf_ru(zf[r], zf[r], __fmaf_ru(yf[r], yf[r], __fmul_ru(xf[r], xf[r]))));
             }
-            t2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(t2)));
-            if ((threadIdx.x & 31) == 0) atomicMax(&sh->t2_bits, __float_as_uint(t2));
+            tile_t2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(tile_t2)));
         } else {
 #pragma unroll
             for (int r = 0; r < PC_RI; ++r) { xf[r] = yf[r] = zf[r] = 0.0f; cb[r] = 0u; }
         }
         // classification of every observed layer against the tile's bounding box
-        for (int t = threadIdx.x; t < gx + gy + gz; t += blockDim.x) {
+        __syncwarp();
+        for (int t = lane; t < nlay; t += 32) {
             const int c = t < gx ? 0 : (t < gx + gy ? 1 : 2);
             const int k = c == 0 ? t : (c == 1 ? t - gx : t - gx - gy);
-            const long long li = ((long long)tl.frame * 3 + c) * gi.gmax, lj = ((long long)tl.frame * 3 + c) * go.gmax;
-            double ilo, ihi;
-            if (c == 0) {
-                ilo = 1e300; ihi = -1e300;
-                for (int q = tl.cx0; q <= tl.cx1; ++q)
-                    if (gi.lay_lo[li + q] <= gi.lay_hi[li + q]) { ilo = fmin(ilo, okey_inv(gi.lay_lo[li + q])); ihi = fmax(ihi, okey_inv(gi.lay_hi[li + q])); }
-            } else {
-                const int q = c == 1 ? tl.cy : tl.cz;
-                ilo = okey_inv(gi.lay_lo[li + q]); ihi = okey_inv(gi.lay_hi[li + q]);
-            }
+            const long long lj = ((long long)tl.frame * 3 + c) * go.gmax;
             PcLayer cl;
             if (go.lay_lo[lj + k] > go.lay_hi[lj + k]) { cl.mode = 0; cl.ca = cl.cb = 1; cl.pad = 0; cl.dmin2 = 3.0e38f; }   // empty layer
-            else cl = pc_classify(ilo, ihi, okey_inv(go.lay_lo[lj + k]), okey_inv(go.lay_hi[lj + k]), p.box.L[c]);
+            else cl = pc_classify(c == 0 ? blox : (c == 1 ? bloy : bloz), c == 0 ? bhix : (c == 1 ? bhiy : bhiz),
+                                  okey_inv(go.lay_lo[lj + k]), okey_inv(go.lay_hi[lj + k]), c == 0 ? p.box.L[0] : (c == 1 ? p.box.L[1] : p.box.L[2]));
             if (cl.mode == 3) atomicOr(p.flags + 1, 1u);                       // boxes too wide: host redoes the call without cells
-            lay[(c == 0 ? 0 : (c == 1 ? gx : gx + gy)) + k] = cl;
+            lay[t] = cl;
         }
-        __syncthreads();
+        __syncwarp();
+        // 32-bit shared counters: the CTA's warps together add at most PC_WARPS * 2^28 between two flushes of any one of them
         const unsigned long long item_pairs = (unsigned long long)PC_TILE * (unsigned long long)go.nmol;
-        if (since_flush + item_pairs > 0x7fffffffull) {
-            __syncthreads();
-            pc_flush<VARIANT>(p, T, true);
+        if (since_flush + item_pairs > (0x7fffffffull / PC_WARPS)) {
+            pc_flush_warp<VARIANT>(p, T);
             since_flush = 0;
         }
         since_flush += item_pairs;
         // float32 eligibility of this tile: |T| <= t2max; runs must then be at least 2|T| away (rounded up)
-        const float tile_t2 = __uint_as_float(sh->t2_bits);
         const bool tile_f32 = f32_on && tile_t2 <= t2max * t2max;
         if (PART == 1 && !tile_f32) continue;
         const float rmin2 = 4.0f * tile_t2 * 1.0001f + 1.0e-3f;
@@ -937,7 +1043,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     if (jb >= je) continue;
                     if (PART == 2 && f32run) continue;                              // counted by the PART 1 launch
                     if (VARIANT == 0 && PART == 1 && f32run) {
-#define PC_F32(MX_, MY_, MZ_, Z_, N_) pc_segment_f32<MX_, MY_, MZ_, Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, \
+#define PC_F32(MX_, MY_, MZ_, Z_, N_) pc_segment_f32<MX_, MY_, MZ_, Z_, N_, VERIFY, DEADSKIP>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, \
                                                                                     sxa, sxb, sya, syb, sza, szb, s_j, s_jf, T, near_a, queue, dead_d2, it_all, it_live)
                         if (dcode == 0) {
                             if (nearr) { if (zcol) PC_F32(1, 1, 1, true, true); else PC_F32(1, 1, 1, false, true); }
@@ -967,14 +1073,14 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
             }
         }
     }
-    __syncthreads();
-    pc_flush<VARIANT>(p, T, false);
-    if (p.kstats && (threadIdx.x & 31) == 0) {
+    if (p.kstats && lane == 0) {
         st_all += it_all; st_live += it_live;
         unsigned long long *ks = p.kstats + (PART == 1 ? 0 : 4);    // the float32 launch is accounted separately
         if (st_all) atomicAdd(ks + 0, st_all * 128ull);             // pair evaluations (lanes x 4 per iteration)
         if (st_live) atomicAdd(ks + 1, st_live * 128ull);           // shared-memory atomics issued (one per evaluated pair of a live iteration)
     }
+    __syncthreads();
+    pc_flush<VARIANT>(p, T, false);
 }
 
 // ---------------------------------------------------------------------------
@@ -1028,8 +1134,8 @@ static __device__ __noinline__ void pg_drain(const PaPass &p, const PaCellGrid &
 
 template <int MODE, bool SMEM_HIST>
 static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
-                                                  const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
-                                                  const int (&iorig)[PC_RI], long long jbase, int jb, int je,
+                                                  const double (&p1x)[PG_RI], const double (&p1y)[PG_RI], const double (&p1z)[PG_RI],
+                                                  const int (&iorig)[PG_RI], long long jbase, int jb, int je,
                                                   double sxa, double sxb, double sya, double syb, double sza, double szb,
                                                   double *s_j, int *s_jo, unsigned int *s_hist, int nbins, unsigned int *queue,
                                                   const unsigned long long *thr_a, const double *thr_b, int &parity,
@@ -1044,9 +1150,9 @@ static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellG
     const unsigned long long cut = p.job.cut_bits;
     const unsigned int lane_lt = (1u << (threadIdx.x & 31)) - 1u;
     int qn = 0;                                          // entries in this warp's queue (warp-uniform)
-    for (int jc = jb; jc < je; jc += PC_JC) {
-        s_j = s_j0 + (parity & 1) * (PC_JC * 6);
-        s_jo = s_jo0 + (parity & 1) * PC_JC;
+    for (int jc = jb; jc < je; jc += PG_JC) {
+        s_j = s_j0 + (parity & 1) * (PG_JC * 6);
+        s_jo = s_jo0 + (parity & 1) * PG_JC;
         ++parity;
         {
             const int t = threadIdx.x;
@@ -1061,13 +1167,13 @@ static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellG
             s_jo[t] = o;
         }
         __syncthreads();
-        const int cnt = min(PC_JC, je - jc);
+        const int cnt = min(PG_JC, je - jc);
         for (int jj = 0; jj < cnt; ++jj) {
             const double2 *rec = reinterpret_cast<const double2 *>(s_j + jj * 6);
             const double2 rx = rec[0], ry = rec[1], rz = rec[2];
             const int jo = s_jo[jj];
 #pragma unroll
-            for (int r = 0; r < PC_RI; ++r) {
+            for (int r = 0; r < PG_RI; ++r) {
                 const double sx = pc_comp_sq<MODE>(rx.x, rx.y, p1x[r]);
                 const double sy = pc_comp_sq<MODE>(ry.x, ry.y, p1y[r]);
                 const double sz = pc_comp_sq<MODE>(rz.x, rz.y, p1z[r]);
@@ -1078,7 +1184,7 @@ static __device__ __forceinline__ void pg_segment(const PaPass &p, const PaCellG
                 if (m == 0u) continue;
                 const int add = __popc(m);
                 if (qn + add > PG_QCAP) { pg_drain<MODE, SMEM_HIST>(p, go, gi, tl, queue, qn, s_j, s_jo, jbase, jc, s_hist, nbins, thr_a, thr_b, g_within, g_oob); qn = 0; }
-                if (need) queue[qn + __popc(m & lane_lt)] = ((unsigned int)jj << 16) | (unsigned int)(r * PC_THREADS + threadIdx.x);
+                if (need) queue[qn + __popc(m & lane_lt)] = ((unsigned int)jj << 16) | (unsigned int)(r * PG_THREADS + threadIdx.x);
                 qn += add;
             }
         }
@@ -1102,20 +1208,20 @@ static __device__ void pg_flush(const PaPass &p, unsigned int *s_hist, int nbins
 }
 
 template <bool SMEM_HIST>
-__global__ void __launch_bounds__(PC_THREADS, 5) pa_general_cells_kernel(const __grid_constant__ PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
+__global__ void __launch_bounds__(PG_THREADS, 5) pa_general_cells_kernel(const __grid_constant__ PaPass p, PaCellGrid gi, PaCellGrid go, const PaTile *tiles,
                                                                        const unsigned int *ntiles_ptr, unsigned int tile_cap,
                                                                        unsigned int *work_counter, int nzg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nbins = p.job.bin_a * p.job.bin_b;
-    double *s_j = reinterpret_cast<double *>(smem_raw);                         // 2 x PC_JC*6 doubles (double buffered)
-    int *s_jo = reinterpret_cast<int *>(s_j + 2 * PC_JC * 6);                   // 2 x PC_JC original indices
-    PcShared *sh = reinterpret_cast<PcShared *>(s_jo + 2 * PC_JC);
+    double *s_j = reinterpret_cast<double *>(smem_raw);                         // 2 x PG_JC*6 doubles (double buffered)
+    int *s_jo = reinterpret_cast<int *>(s_j + 2 * PG_JC * 6);                   // 2 x PG_JC original indices
+    PcShared *sh = reinterpret_cast<PcShared *>(s_jo + 2 * PG_JC);
     int parity = 0;
     unsigned int *queue = reinterpret_cast<unsigned int *>(sh + 1) + (threadIdx.x >> 5) * PG_QCAP;   // per warp
     // class tables of the job in shared memory (pdf: thr_a[bin_a+3], thr_b[bin_b+1]; <= 16 KB), searched by every drained pair
     unsigned long long *s_thr_a = reinterpret_cast<unsigned long long *>(
-        (reinterpret_cast<uintptr_t>(reinterpret_cast<unsigned int *>(sh + 1) + (PC_THREADS / 32) * PG_QCAP) + 7) & ~uintptr_t(7));
+        (reinterpret_cast<uintptr_t>(reinterpret_cast<unsigned int *>(sh + 1) + (PG_THREADS / 32) * PG_QCAP) + 7) & ~uintptr_t(7));
     const int n_thr_a = p.job.mode == PA_MODE_PDF ? p.job.bin_a + 3 : 0, n_thr_b = p.job.mode == PA_MODE_PDF ? p.job.bin_b + 1 : 0;
     double *s_thr_b = reinterpret_cast<double *>(s_thr_a + n_thr_a);
     for (int k = threadIdx.x; k < n_thr_a; k += blockDim.x) s_thr_a[k] = p.job.thr_a[k];
@@ -1143,12 +1249,12 @@ __global__ void __launch_bounds__(PC_THREADS, 5) pa_general_cells_kernel(const _
         const int zg = (int)(item % nzg);
         const int z0 = (int)((long long)gz * zg / nzg), z1 = (int)((long long)gz * (zg + 1) / nzg);
         if (z0 == z1) continue;
-        double p1x[PC_RI], p1y[PC_RI], p1z[PC_RI];
-        int iorig[PC_RI];
+        double p1x[PG_RI], p1y[PG_RI], p1z[PG_RI];
+        int iorig[PG_RI];
         const long long ibase = (long long)tl.frame * gi.nmol;
 #pragma unroll
-        for (int r = 0; r < PC_RI; ++r) {
-            const int k = r * PC_THREADS + threadIdx.x;
+        for (int r = 0; r < PG_RI; ++r) {
+            const int k = r * PG_THREADS + threadIdx.x;
             if (k < tl.count) {
                 p1x[r] = gi.sx[ibase + tl.begin + k]; p1y[r] = gi.sy[ibase + tl.begin + k]; p1z[r] = gi.sz[ibase + tl.begin + k];
                 iorig[r] = gi.sorig[ibase + tl.begin + k];
@@ -1175,7 +1281,7 @@ __global__ void __launch_bounds__(PC_THREADS, 5) pa_general_cells_kernel(const _
         }
         __syncthreads();
         if (SMEM_HIST) {
-            const unsigned long long item_pairs = (unsigned long long)PC_TILE * (unsigned long long)go.nmol;
+            const unsigned long long item_pairs = (unsigned long long)PC_GTILE * (unsigned long long)go.nmol;
             if (since_flush + item_pairs > 0x7fffffffull) { __syncthreads(); pg_flush<SMEM_HIST>(p, s_hist, nbins, true); since_flush = 0; }
             since_flush += item_pairs;
         }
@@ -1241,15 +1347,23 @@ int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &b
     return (int)cudaGetLastError();
 }
 
-int pa_launch_build_tiles(const PaCellGrid &g, int nframes, PaTile *tiles, unsigned int *ntiles, unsigned int cap, void *stream)
+int pa_launch_build_tiles(const PaCellGrid &g, int nframes, bool chunks, PaTile *tiles, unsigned int *ntiles, int *row_off, unsigned int cap, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    cudaMemsetAsync(ntiles, 0, sizeof(unsigned int), st);
     const int rows = nframes * g.g[1] * g.g[2];
     // tile width (max_run cells) + one observed cell must stay below L/2: (max_run + 1.1) / gx < 0.5
     int max_run = (int)(0.45 * g.g[0]) - 1;
     if (max_run < 1) max_run = 1;
-    pa_build_tiles_kernel<<<(rows + 127) / 128, 128, 0, st>>>(g, nframes, max_run, tiles, ntiles, cap);
+    const int blocks = (rows + 127) / 128;
+    if (chunks) {
+        pa_build_tiles_kernel<true, false><<<blocks, 128, 0, st>>>(g, nframes, max_run, tiles, row_off, cap);
+        pa_tile_scan_kernel<<<1, 1024, 0, st>>>(row_off, rows, ntiles);
+        pa_build_tiles_kernel<true, true><<<blocks, 128, 0, st>>>(g, nframes, max_run, tiles, row_off, cap);
+    } else {
+        pa_build_tiles_kernel<false, false><<<blocks, 128, 0, st>>>(g, nframes, max_run, tiles, row_off, cap);
+        pa_tile_scan_kernel<<<1, 1024, 0, st>>>(row_off, rows, ntiles);
+        pa_build_tiles_kernel<false, true><<<blocks, 128, 0, st>>>(g, nframes, max_run, tiles, row_off, cap);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -1267,8 +1381,10 @@ void pa_cell_grid_dims(int nmol, int g[3])
 size_t pa_cells_smem_bytes(int na, int f32_cnt, int nlayers)   // f32_cnt > 0: the PART 1 launch
 {
     const int ncnt = (f32_cnt > 0 ? f32_cnt + na + 8 : na + 3) + 1;
-    return (size_t)PC_JC * (f32_cnt > 0 ? 4 : 6) * 8 + (size_t)PC_JC * 16 + (f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 2) * 4 +
-           sizeof(PcSharedR) + (size_t)nlayers * sizeof(PcLayer) + (f32_cnt > 0 ? (size_t)(PC_THREADS / 32) * PC_QCAP * 8 : 0) + 16;
+    const size_t cta = ((f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 1) * 4 + 15) & ~(size_t)15;
+    const size_t warp = (size_t)PC_JC * (f32_cnt > 0 ? 4 : 6) * 8 + (size_t)PC_JC * 16 + (((size_t)nlayers * sizeof(PcLayer) + 15) & ~(size_t)15) +
+                        (size_t)PC_QCAP * 8;
+    return cta + (size_t)PC_WARPS * warp + 16;
 }
 
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
@@ -1279,28 +1395,28 @@ int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
     const size_t smem = pa_cells_smem_bytes(p.job.bin_a, variant == 0 ? p.f32_cnt : 0, go.g[0] + go.g[1] + go.g[2]);
     const size_t smem0 = pa_cells_smem_bytes(p.job.bin_a, 0, go.g[0] + go.g[1] + go.g[2]);
     const bool verify = p.verify_fail != nullptr;
-#define PC_LAUNCH3(O_, V_, S_, P_, SMEM_)                                                                        \
+#define PC_LAUNCH4(O_, V_, S_, P_, D_, SMEM_)                                                                   \
     do {                                                                                                        \
         int occ = 1;                                                                                            \
         cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);                                             \
-        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_, S_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_, S_, P_>, PC_THREADS, (SMEM_)) != cudaSuccess || occ < 1) occ = 1; \
-        pa_rdf_cells_kernel<O_, V_, S_, P_><<<sm_count * occ, PC_THREADS, (SMEM_), st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_, S_, P_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_, S_, P_, D_>, PC_THREADS, (SMEM_)) != cudaSuccess || occ < 1) occ = 1; \
+        pa_rdf_cells_kernel<O_, V_, S_, P_, D_><<<sm_count * occ, PC_THREADS, (SMEM_), st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
     } while (0)
 #define PC_LAUNCH2(O_, V_, S_)                                                                                  \
     do {                                                                                                        \
         if (O_ == 0 && p.f32_cnt > 0) {                                                                         \
             if (ev_f32_begin) cudaEventRecord((cudaEvent_t)ev_f32_begin, st);                                   \
-            PC_LAUNCH3(O_, V_, S_, 1, smem);                                                                    \
+            if (p.deadskip) PC_LAUNCH4(O_, V_, S_, 1, true, smem); else PC_LAUNCH4(O_, V_, S_, 1, false, smem); \
             if (ev_f32_end) cudaEventRecord((cudaEvent_t)ev_f32_end, st);                                       \
-            PC_LAUNCH3(O_, V_, S_, 2, smem0);                                                                   \
+            PC_LAUNCH4(O_, V_, S_, 2, false, smem0);                                                            \
         }                                                                                                       \
-        else PC_LAUNCH3(O_, V_, S_, 0, smem0);                                                                  \
+        else PC_LAUNCH4(O_, V_, S_, 0, false, smem0);                                                           \
     } while (0)
 #define PC_LAUNCH(O_, V_) do { if (p.sym) PC_LAUNCH2(O_, V_, true); else PC_LAUNCH2(O_, V_, false); } while (0)
     if (variant == 1) { if (verify) PC_LAUNCH(1, true); else PC_LAUNCH(1, false); }
     else { if (verify) PC_LAUNCH(0, true); else PC_LAUNCH(0, false); }
-#undef PC_LAUNCH3
+#undef PC_LAUNCH4
 #undef PC_LAUNCH2
 #undef PC_LAUNCH
     return (int)cudaGetLastError();
@@ -1314,7 +1430,7 @@ int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellG
     // a shared-memory histogram only while it leaves room for >= 6 CTAs per SM (occupancy matters more to this
     // latency-bound kernel than the atomics: larger histograms take 64-bit atomics in L2)
     const bool smem_hist = nbins <= 6000;
-    const size_t smem = 2 * ((size_t)PC_JC * 6 * 8 + (size_t)PC_JC * 4) + sizeof(PcShared) + (size_t)(PC_THREADS / 32) * PG_QCAP * 4 +
+    const size_t smem = 2 * ((size_t)PG_JC * 6 * 8 + (size_t)PG_JC * 4) + sizeof(PcShared) + (size_t)(PG_THREADS / 32) * PG_QCAP * 4 +
                         (p.job.mode == PA_MODE_PDF ? (size_t)(p.job.bin_a + 3 + p.job.bin_b + 1) * 8 : 0) +
                         (smem_hist ? (size_t)(nbins + 1) * 4 : 0) + 24;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
@@ -1322,8 +1438,8 @@ int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellG
     do {                                                                                                        \
         int occ = 1;                                                                                            \
         cudaFuncSetAttribute(pa_general_cells_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_general_cells_kernel<S_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
-        pa_general_cells_kernel<S_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_general_cells_kernel<S_>, PG_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
+        pa_general_cells_kernel<S_><<<sm_count * occ, PG_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
     } while (0)
     if (smem_hist) PG_LAUNCH(true); else PG_LAUNCH(false);
 #undef PG_LAUNCH

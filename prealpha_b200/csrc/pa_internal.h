@@ -96,6 +96,7 @@ struct PaPass {
     float eps64;                // half-width of the class brackets of the fp64-difference segments (variant 0)
     float f32_lo, f32_hi;       // (1 -+ eps)/step_a rounded outwards (eps: pa_session.cu); adjacent so that they load as one packed pair
     int32_t tshard_rank, tshard_count;   // tile shard of this device (pa_exec.tile_shard_*): work item w is taken when w % count == rank
+    int32_t deadskip;           // 1: float32 launch skips iterations whose pairs are all beyond the cutoff (debug flag 0x400 clears it)
     float dead_r;               // (bin_a + 1)/f32_lo rounded up: from this approximate distance on, the lower class bracket is beyond the cutoff
     unsigned long long *kstats; // device counters of the cell kernels (8 words, may be null): [0] pair evaluations after cell pruning
                                 // and [1] shared-memory atomics issued by the float32 launches, [4] / [5] the same for the other
@@ -134,7 +135,9 @@ int pa_launch_rdf_fast(const PaPass &p, int sm_count, void *stream);
 int pa_launch_general(const PaPass &p, int sm_count, void *stream);
 int pa_launch_exceptions(const PaPass &p, unsigned int count, void *stream);
 int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &box, int frame0, int nframes, unsigned int *err, void *stream);
-int pa_launch_build_tiles(const PaCellGrid &g, int nframes, PaTile *tiles, unsigned int *ntiles, unsigned int cap, void *stream);
+// chunks = false: cell-aligned tiles of <= 256 molecules (general kernel); true: 64-molecule pieces of the rows (RDF kernel,
+// one per warp); row_off: scratch of nframes * g[1] * g[2] ints
+int pa_launch_build_tiles(const PaCellGrid &g, int nframes, bool chunks, PaTile *tiles, unsigned int *ntiles, int *row_off, unsigned int cap, void *stream);
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
                         unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream,
                         void *ev_f32_begin, void *ev_f32_end);   // optional CUDA events around the float32 launch (the dominant kernel)

@@ -45,10 +45,13 @@ struct TypeMeta {
 struct TypeGrid {
     bool enabled = false;
     PaCellGrid g{};
-    PaTile *tiles = nullptr;
-    unsigned int *counters = nullptr;   // [0] ntiles, [1] work counter
-    unsigned int tile_cap = 0;
-    bool tiles_ready = false;
+    // two deterministic tile lists (pa_cells.cu): cell-aligned CTA tiles of the general kernel and 64-molecule warp tiles
+    // of the RDF kernel
+    PaTile *tiles = nullptr, *wtiles = nullptr;
+    unsigned int *counters = nullptr;   // [0] ntiles, [1] work counter, [2] number of warp tiles
+    unsigned int tile_cap = 0, wtile_cap = 0;
+    bool tiles_ready = false, wtiles_ready = false;
+    int *row_off = nullptr;             // scratch of the tile builder: one int per (frame, row of cells)
 };
 
 struct JobState {
@@ -403,6 +406,10 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
             // every cell yields at most one tile plus one extra per 256 molecules
             tg.tile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.ncell + nm / 256 + 1), 0x7fffffffu);
             PA_CK(cudaMalloc(&tg.tiles, sizeof(PaTile) * tg.tile_cap));
+            // warp tiles: every row of cells yields at most one partial piece plus one per 64 molecules
+            tg.wtile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.g[1] * g.g[2] + nm / 64 + 1), 0x7fffffffu);
+            PA_CK(cudaMalloc(&tg.wtiles, sizeof(PaTile) * tg.wtile_cap));
+            PA_CK(cudaMalloc(&tg.row_off, sizeof(int) * (nf * (size_t)g.g[1] * g.g[2] + 1)));
             PA_CK(cudaMalloc(&tg.counters, sizeof(unsigned int) * 4));
             PA_CK(cudaMemset(tg.counters, 0, sizeof(unsigned int) * 4));
         }
@@ -494,7 +501,7 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
     for (TypeGrid &tg : s->grids) {
         if (!tg.enabled) continue;
         PA_CK((cudaError_t)pa_launch_cell_sort(tg.g, s->pts, s->box, first, count, s->d_exc_count + 1, s->s_compute));
-        tg.tiles_ready = false;
+        tg.tiles_ready = tg.wtiles_ready = false;
         s->stats.kernel_launches += 3;
     }
     const long long target_items = (long long)s->sm_count * 16;
@@ -574,6 +581,7 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
             if ((double)p.dead_r < dead) p.dead_r = std::nextafterf(p.dead_r, INFINITY);
         }
         p.tshard_rank = s->exec.tile_shard_rank; p.tshard_count = s->exec.tile_shard_count;
+        p.deadskip = (s->exec.flags & 0x400) ? 0 : 1;               // debug flag: float32 launch without the warp-uniform skip
         p.kstats = s->d_kstats;
     };
     for (const Plan &pl : plan) {
@@ -598,9 +606,9 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         if (pl.cells && !js.fast) {
             TypeGrid &gr = s->grids[r];
             if (!gr.tiles_ready) {
-                PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, gr.tiles, gr.counters, gr.tile_cap, s->s_compute));
+                PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, false, gr.tiles, gr.counters, gr.row_off, gr.tile_cap, s->s_compute));
                 gr.tiles_ready = true;
-                s->stats.kernel_launches += 1;
+                s->stats.kernel_launches += 3;
             }
             const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 230 + 1));
             long long nzg = (20ll * s->sm_count * 5 + tiles_est - 1) / tiles_est;
@@ -610,10 +618,10 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
             s->stats.kernel_launches += 1;
         } else if (pl.cells) {
             TypeGrid &gr = s->grids[r];
-            if (!gr.tiles_ready) {
-                PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, gr.tiles, gr.counters, gr.tile_cap, s->s_compute));
-                gr.tiles_ready = true;
-                s->stats.kernel_launches += 1;
+            if (!gr.wtiles_ready) {
+                PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, true, gr.wtiles, gr.counters + 2, gr.row_off, gr.wtile_cap, s->s_compute));
+                gr.wtiles_ready = true;
+                s->stats.kernel_launches += 3;
             }
             PaPass p2{};
             p.sym = pl.sym ? 1 : 0;
@@ -623,15 +631,16 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
                 p.acc2 = p2.job.acc; p.weight2 = p2.weight;
                 p2.exc_list = p.exc_list2; p2.exc_count = p.exc_count2;     // reversed pairs go through the partner's job
             }
-            const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 230 + 1));
-            long long nzg = (20ll * s->sm_count * 5 + tiles_est - 1) / tiles_est;
+            // work items = (warp tile, slab of observed z-layers): enough of them for ~40 per resident warp
+            const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 60 + (long long)gr.g.g[1] * gr.g.g[2]));
+            long long nzg = (40ll * s->sm_count * 24 + tiles_est - 1) / tiles_est;
             nzg = std::max<long long>(1, std::min<long long>(nzg, s->grids[o].g.g[2]));
             cudaEvent_t f0 = nullptr, f1 = nullptr;
             if (js.cells_variant == 0 && js.f32_cnt > 0) {
                 PA_CK(cudaEventCreate(&f0)); PA_CK(cudaEventCreate(&f1));
                 s->f32_events.emplace_back(f0, f1);
             }
-            PA_CK((cudaError_t)pa_launch_rdf_cells(p, gr.g, s->grids[o].g, gr.tiles, gr.counters, gr.tile_cap, gr.counters + 1,
+            PA_CK((cudaError_t)pa_launch_rdf_cells(p, gr.g, s->grids[o].g, gr.wtiles, gr.counters + 2, gr.wtile_cap, gr.counters + 1,
                                                    (int)nzg, js.cells_variant, s->sm_count, s->s_compute, f0, f1));
             PA_CK((cudaError_t)pa_launch_exceptions(p, 0, s->s_compute));
             s->stats.kernel_launches += 3 + ((js.cells_variant == 0 && js.f32_cnt > 0) ? 1 : 0);   // float32 runs and the rest are two launches
@@ -753,7 +762,7 @@ void pa_session_destroy(pa_session *s)
     for (auto &tg : s->grids) {
         if (!tg.enabled) continue;
         cudaFree(tg.g.cell_start); cudaFree(tg.g.cell_fill); cudaFree(tg.g.cid); cudaFree(tg.g.sx); cudaFree(tg.g.sy); cudaFree(tg.g.sz);
-        cudaFree(tg.g.sorig); cudaFree(tg.g.sflag); cudaFree(tg.g.lay_lo); cudaFree(tg.g.lay_hi); cudaFree(tg.tiles); cudaFree(tg.counters);
+        cudaFree(tg.g.sorig); cudaFree(tg.g.sflag); cudaFree(tg.g.lay_lo); cudaFree(tg.g.lay_hi); cudaFree(tg.tiles); cudaFree(tg.wtiles); cudaFree(tg.row_off); cudaFree(tg.counters);
     }
     cudaFree(s->d_pts); cudaFree(s->d_acc); cudaFree(s->d_exc); cudaFree(s->d_exc_count); cudaFree(s->d_kstats);
     if (s->s_compute) cudaStreamDestroy(s->s_compute);

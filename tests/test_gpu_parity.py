@@ -566,3 +566,45 @@ def test_cli_rejects_short_trajectories(oracle, tmp_path):
     out = p.stdout.decode()
     assert p.returncode == 1 and "ERROR 37" in out and "ERROR 20" in out
     assert not [f for f in os.listdir(wd) if f.startswith("reference_")]
+
+
+@pytest.mark.parametrize("no_nccl", [False, True], ids=["nccl_reduce", "peer_copy_reduce"])
+def test_multi_device_call_matches_single_device(no_nccl, tmp_path):
+    """pa_exec.ndevices: one call drives several GPUs (one host thread each) and combines the int64 accumulators on the
+    first device with ncclReduce (or peer copies + add when NCCL is switched off).  Frames >= devices: frame shards;
+    a single frame: tile shards.  Same integers as one device either way.  Needs >= 2 GPUs (skipped on a 1-GPU box);
+    run in a subprocess because the NCCL switch is read once per process."""
+    if api.device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import fixtures
+from prealpha_b200 import api, capi
+from test_gpu_parity import _big_system
+nd = api.device_count()
+fx = fixtures.Fixture("re4")
+traj = fx.trajectory()
+pjobs = [api.job_setup(traj, rq) for _, _, rq, _ in fx.jobs()[:2]]
+one = api.histogram_multi(traj, pjobs)
+for n in sorted({2, nd, -1}):
+    many = api.histogram_multi(traj, pjobs, api.make_exec(ndevices=n))
+    for k in range(len(pjobs)):
+        assert np.array_equal(one[0][k], many[0][k]) and one[1][k] == many[1][k] and one[2][k] == many[2][k], (n, k)
+    assert many[3].frames_done == one[3].frames_done and many[3].pairs_evaluated == one[3].pairs_evaluated
+# one frame: the devices split the work items of the frame (cell-sorted kernels)
+traj = _big_system(seed=21, n1=13000, n2=15500, L=80.0)
+pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, mode="pdf", ref_type=1, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True)),
+         api.job_setup(traj, capi.make_request(sampling_interval=1, mode="pdf", vec=(1, 1, 0), ref_type=2, obs_type=1, bin_a=24, bin_b=12, maxdist=9.0))]
+one = api.histogram_multi(traj, pjobs)
+many = api.histogram_multi(traj, pjobs, api.make_exec(ndevices=nd))
+for k in range(len(pjobs)):
+    assert np.array_equal(one[0][k], many[0][k]) and one[1][k] == many[1][k] and one[2][k] == many[2][k], k
+assert many[3].frames_done == 1 and many[3].pairs_evaluated == one[3].pairs_evaluated
+print("ok")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ)
+    if no_nccl:
+        env["PA_NO_NCCL"] = "1"
+    out = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
