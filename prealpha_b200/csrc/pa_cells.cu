@@ -20,6 +20,7 @@
 // discards at `IF (current_distance_squared<maxdist_squared)` (Distribution:783).
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <algorithm>
 #include "pa_internal.h"
 #include "pa_pair_exact.cuh"
 
@@ -101,25 +102,71 @@ __global__ void __launch_bounds__(1024) pa_cell_scan_kernel(PaCellGrid g)
     if (threadIdx.x == 0) cs[0] = 0;
 }
 
-// K3: scatter into cell order (order inside a cell is arbitrary: results are integer sums)
-__global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, PaPoints pts, PaBox box, int frame0, int nframes)
+// K3a: scatter the molecule indices into cell order.  The position inside a cell comes from an atomic cursor, i.e. it
+// differs from run to run (and from GPU to GPU) ...
+__global__ void __launch_bounds__(256) pa_cell_scatter_kernel(PaCellGrid g, int nframes)
 {
     const long long total = (long long)nframes * g.nmol;
     for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
         const int f = (int)(id / g.nmol), m = (int)(id % g.nmol);
-        const long long slot = (long long)(frame0 + f) * pts.M + g.type_off + m;
         const int cell = g.cid[id];
         const int pos = g.cell_start[(long long)f * (g.ncell + 1) + cell] + atomicAdd(&g.cell_fill[(long long)f * g.ncell + cell], 1);
-        const long long o = (long long)f * g.nmol + pos;
+        g.sorig[(long long)f * g.nmol + pos] = m;
+    }
+}
+
+// K3b: ... so every cell is put into ascending molecule index (one warp per cell, rank sort: the rank of an entry is the
+// number of smaller entries).  The sorted order of a frame is then a function of the frame alone, which is what lets
+// tile shards on different GPUs -- whose warp tiles are pieces of this order -- agree on which molecules a tile holds.
+// Output goes to g.cid (free after K3a).  A cell with more than PC_MAX_CELL molecules (the grid is useless for such a
+// frame) raises the sticky flag: the host redoes the call without cells.
+#define PC_MAX_CELL 4096
+__global__ void __launch_bounds__(256) pa_cell_order_kernel(PaCellGrid g, int nframes, unsigned int *err)
+{
+    const int lane = threadIdx.x & 31;
+    const long long ncells = (long long)nframes * g.ncell;
+    for (long long c = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5; c < ncells; c += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int f = (int)(c / g.ncell), cell = (int)(c % g.ncell);
+        const int *cs = g.cell_start + (long long)f * (g.ncell + 1);
+        const int beg = cs[cell], n = cs[cell + 1] - beg;
+        const int *src = g.sorig + (long long)f * g.nmol + beg;
+        int *dst = g.cid + (long long)f * g.nmol + beg;
+        if (n <= 32) {
+            const int v = lane < n ? src[lane] : 0x7fffffff;
+            int rank = 0;
+            for (int k = 0; k < n; ++k) rank += (__shfl_sync(0xffffffffu, v, k) < v) ? 1 : 0;
+            if (lane < n) dst[rank] = v;
+        } else if (n <= PC_MAX_CELL) {
+            for (int i = lane; i < n; i += 32) {
+                const int v = src[i];
+                int rank = 0;
+                for (int k = 0; k < n; ++k) rank += (src[k] < v) ? 1 : 0;
+                dst[rank] = v;
+            }
+        } else {
+            if (lane == 0) atomicOr(err, 1u);
+            for (int i = lane; i < n; i += 32) dst[i] = src[i];
+        }
+    }
+}
+
+// K3c: gather the positions into the sorted order
+__global__ void __launch_bounds__(256) pa_cell_gather_kernel(PaCellGrid g, PaPoints pts, PaBox box, int frame0, int nframes)
+{
+    const long long total = (long long)nframes * g.nmol;
+    for (long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x; id < total; id += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(id / g.nmol);
+        const int m = g.cid[id];
+        const long long slot = (long long)(frame0 + f) * pts.M + g.type_off + m;
         // A position outside the box (not wrapped: wrap_trajectory, or beyond 1000 wrap moves) or NaN has already raised
         // the sticky flag in pa_cell_count_kernel and the whole call will be redone without cells; the pair kernels still
         // run, so such a position is clamped into the box here to keep every distance below the box diagonal (the
         // float32 segments size their counter window by that bound).  fmax / fmin return the non-NaN operand.
-        g.sx[o] = fmin(fmax(pts.px[slot], box.lo[0]), box.hi[0]);
-        g.sy[o] = fmin(fmax(pts.py[slot], box.lo[1]), box.hi[1]);
-        g.sz[o] = fmin(fmax(pts.pz[slot], box.lo[2]), box.hi[2]);
-        g.sorig[o] = m;
-        g.sflag[o] = (pts.wx[slot] != 0.0 || pts.wy[slot] != 0.0 || pts.wz[slot] != 0.0) ? 1 : 0;
+        g.sx[id] = fmin(fmax(pts.px[slot], box.lo[0]), box.hi[0]);
+        g.sy[id] = fmin(fmax(pts.py[slot], box.lo[1]), box.hi[1]);
+        g.sz[id] = fmin(fmax(pts.pz[slot], box.lo[2]), box.hi[2]);
+        g.sorig[id] = m;
+        g.sflag[id] = (pts.wx[slot] != 0.0 || pts.wy[slot] != 0.0 || pts.wz[slot] != 0.0) ? 1 : 0;
     }
 }
 
@@ -507,56 +554,78 @@ static __device__ __forceinline__ float4 pc_lds_f32x4(unsigned int addr)
     return v;
 }
 
-// Exact decisions of the float32 segments are deferred: a flagged pair (~1e-3 of the pairs, usually one lane of
-// the warp) is appended to a 32-entry queue of its warp and the queue is drained with one entry per lane, so
-// the fp64 re-evaluation runs at full lane occupancy instead of stalling 31 idle lanes on every hit.
-//   entry: bits 0-8 reference index inside the tile, 9-15 observed index inside the staged chunk,
-//          16-23 n_hi - n_lo, 32-63 float bits of MAGIC + n_lo
+// Exact decisions of the float32 segments are deferred: a lane with a flagged pair (~1e-3 of the pairs) appends ONE
+// entry for its iteration to a 32-entry queue of its warp, and the queue is drained with one entry per lane, so the fp64
+// re-evaluation runs at full lane occupancy instead of stalling 31 idle lanes on every hit.  An entry is self-contained
+// (sorted positions of the two observed molecules of the iteration, source lane, which of the 4 pairs), the drain reads
+// the coordinates from global memory and decides the class from the fp64 threshold table alone, so entries survive
+// refills of the staging buffer and a drain only happens when the queue is full or the run ends.
+//   entry: bits 0-23 sorted position of observed molecule u = 0, 24-47 of u = 1, 48-52 source lane,
+//          53-56 mask of the pairs to decide (bit u * PC_RI + r)
 #define PC_QCAP 32
+#define PC_FBUF 128                 // staged (compacted) observed molecules per warp
+template <int MX, int MY, int MZ>
+static __device__ __forceinline__ void pc_exact_pair(const PaCellGrid &go, const PaCellGrid &gi, long long jslot, long long islot,
+                                                     double sxa, double sxb, double sya, double syb, double sza, double szb,
+                                                     double &e1, double &e2)
+{
+    const double gx0 = go.sx[jslot], gy0 = go.sy[jslot], gz0 = go.sz[jslot];
+    const double ex = pc_comp_sq<MX>(__dadd_rn(gx0, sxa), __dadd_rn(gx0, sxb), gi.sx[islot]);
+    const double ey = pc_comp_sq<MY>(__dadd_rn(gy0, sya), __dadd_rn(gy0, syb), gi.sy[islot]);
+    const double ez = pc_comp_sq<MZ>(__dadd_rn(gz0, sza), __dadd_rn(gz0, szb), gi.sz[islot]);
+    e1 = __dadd_rn(ex, ey);
+    e2 = __dadd_rn(e1, ez);
+}
+// exact class of d2 from the fp64 threshold table (global memory: the float32 launch keeps no copy in shared memory):
+// the largest k <= na + 1 with thr_a[k] <= d2 (class na = inside the cutoff with the a-bin out of range, na + 1 = beyond)
+static __device__ __forceinline__ int pc_exact_class(const PaPass &p, double d2, int na)
+{
+    int n = (int)fmin(sqrt(d2) * (double)p.job.guess_scale, (double)(na + 1));
+    while (n > 0 && !(d2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + n)))) --n;
+    while (n <= na && d2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + n + 1))) ++n;
+    return n;
+}
 template <int MX, int MY, int MZ, bool ZCOL>
 static __device__ __noinline__ void pc_f32_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
-                                                 const unsigned long long *queue, int count, unsigned int a_j, long long jbase, int jc,
-                                                 unsigned int cnt_m, int na, unsigned long long cut, unsigned int special)
+                                                 const unsigned long long *queue, int count, long long jbase,
+                                                 double sxa, double sxb, double sya, double syb, double sza, double szb,
+                                                 unsigned int cnt0, int na, unsigned long long cut, unsigned int special)
 {
     __syncwarp();
     const int lane = threadIdx.x & 31;
     if (lane < count) {
         const unsigned long long ent = queue[lane];
-        const int k = (int)(ent & 511u), jl = (int)((ent >> 9) & 127u);
-        const unsigned int tlo = (unsigned int)(ent >> 32), thi = tlo + (unsigned int)((ent >> 16) & 255u);
-        const long long iref = (long long)tl.frame * gi.nmol + tl.begin + k;
-        constexpr int ND = MX + MY + MZ;                 // staged doubles per observed molecule, laid out as in pc_segment
-        const unsigned int rec = a_j + (unsigned)jl * (8u * ND);
-        const double ex = pc_comp_sq<MX>(pc_lds_f64(rec), pc_lds_f64(rec + 8u * (MX - 1)), gi.sx[iref]);
-        const double ey = pc_comp_sq<MY>(pc_lds_f64(rec + 8u * MX), pc_lds_f64(rec + 8u * (MX + MY - 1)), gi.sy[iref]);
-        const double ez = pc_comp_sq<MZ>(pc_lds_f64(rec + 8u * (MX + MY)), pc_lds_f64(rec + 8u * (MX + MY + MZ - 1)), gi.sz[iref]);
-        const double e1 = __dadd_rn(ex, ey);
-        const double e2 = __dadd_rn(e1, ez);
-        if (ZCOL && __double2hiint(e1) < 0x3E100000) {
-            // |link_xy|^2 < 2^-30: literal evaluation by pa_exception_kernel, not binned here
-            const int io = gi.sorig[iref];
-            const int jo = go.sorig[jbase + jc + jl];
-            if (!(p.same_type && io == jo)) {
-                const unsigned int slot = atomicAdd(p.exc_count, 1u);
-                const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
-                if (slot < p.exc_cap)
-                    p.exc_list[slot] = make_uint2((unsigned int)(fb + p.ref_off + io), (unsigned int)(fb + p.obs_off + jo));
-                if (p.sym || p.acc2) {
-                    const unsigned int slot2 = atomicAdd(p.exc_count2, 1u);
-                    if (slot2 < p.exc_cap)
-                        p.exc_list2[slot2] = make_uint2((unsigned int)(fb + p.obs_off + jo), (unsigned int)(fb + p.ref_off + io));
+        const int src = (int)((ent >> 48) & 31u);
+        unsigned int mask = (unsigned int)((ent >> 53) & 15u);
+        while (mask) {
+            const int q = __ffs((int)mask) - 1;
+            mask &= mask - 1u;
+            const int r = q % PC_RI, u = q / PC_RI;
+            const long long jpos = (long long)((ent >> (24 * u)) & 0xffffffull);
+            const long long iref = (long long)tl.frame * gi.nmol + tl.begin + r * 32 + src;
+            double e1, e2;
+            pc_exact_pair<MX, MY, MZ>(go, gi, jbase + jpos, iref, sxa, sxb, sya, syb, sza, szb, e1, e2);
+            if (ZCOL && __double2hiint(e1) < 0x3E100000) {
+                // |link_xy|^2 < 2^-30: literal evaluation by pa_exception_kernel, not binned here
+                const int io = gi.sorig[iref];
+                const int jo = go.sorig[jbase + jpos];
+                if (!(p.same_type && io == jo)) {
+                    const unsigned int slot = atomicAdd(p.exc_count, 1u);
+                    const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+                    if (slot < p.exc_cap)
+                        p.exc_list[slot] = make_uint2((unsigned int)(fb + p.ref_off + io), (unsigned int)(fb + p.obs_off + jo));
+                    if (p.sym || p.acc2) {
+                        const unsigned int slot2 = atomicAdd(p.exc_count2, 1u);
+                        if (slot2 < p.exc_cap)
+                            p.exc_list2[slot2] = make_uint2((unsigned int)(fb + p.obs_off + jo), (unsigned int)(fb + p.ref_off + io));
+                    }
                 }
+            } else {
+                const int cls = pc_exact_class(p, e2, na);
+                if (cls < na) pc_red(cnt0 + (unsigned)cls * 4u);
+                else if (cls == na && dbits(e2) < cut) pc_red(special);          // inside the cutoff, a-bin out of range
+                // else: beyond the cutoff, not counted
             }
-        } else {
-            // exact class inside the brackets [n_lo, n_hi] (n_hi = n_lo + 1 except next to r = 0 in NEAR runs);
-            // thresholds from global memory: the float32 launch keeps no copy of the table in shared memory
-            unsigned int n = max(tlo, 0x4B000000u);
-            const unsigned int n_end = min(thi, 0x4B000000u + (unsigned)na + 1u);   // class na + 1 = beyond the cutoff; the table has na + 3 entries
-            while (n < n_end && e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (n - 0x4B000000u + 1u)))) ++n;
-            const unsigned int cls = n - 0x4B000000u;
-            if (cls < (unsigned)na) pc_red(n * 4u + cnt_m);
-            else if (cls == (unsigned)na && dbits(e2) < cut) pc_red(special);      // inside the cutoff, a-bin out of range
-            // else: beyond the cutoff, not counted
         }
     }
     __syncwarp();
@@ -569,70 +638,107 @@ static __device__ __forceinline__ unsigned long long pc_min2(unsigned long long 
 }
 
 // MX/MY/MZ: 1 = single image, 2 = two candidate images for that component (at most one component; its second
-// candidate travels in the .w lane of the staged float4, and the squared component is the smaller of the two squares)
-template <int MX, int MY, int MZ, bool ZCOL, bool NEAR, bool VERIFY, bool DEADSKIP>
+// candidate travels in the .w lane of the staged float4, and the squared component is the smaller of the two squares).
+//
+// Staging compacts: a lane converts one observed molecule of the run to local float32 coordinates and keeps it only if
+// it can reach the tile at all -- with h = the tile's half extents about its origin (exact maxima of the |local float
+// coordinates| of its molecules), every tile molecule i has |xj~ - xi~| >= g_x := max(0, |xj~| - h_x) (rounded down), and
+// because rounding is monotone the d2~ the loop would compute for (i, j) is >= the same chain of operations evaluated
+// on (g_x, g_y, g_z).  If that bound is >= dead_d2 (lower class bracket beyond the cutoff even after sqrt.approx's error
+// and the NEAR term) no pair of j with this tile is ever counted or queued, and j is dropped.  The survivors are
+// appended to the warp's buffer (ballot + popc), so the pair loop only ever sees molecules with something to count:
+// for a cutoff of L/2 this removes the ~15 % of the evaluated pairs (and their atomics) that the cell-level pruning
+// must leave in.
+template <int MX, int MY, int MZ, bool ZCOL, bool NEAR, bool VERIFY>
 static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                       const float (&xf)[PC_RI], const float (&yf)[PC_RI], const float (&zf)[PC_RI],
                                                       const unsigned int (&cb)[PC_RI],
-                                                      const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
+                                                      float hx, float hy, float hz,
                                                       double ox, double oy, double oz,
                                                       long long jbase, int jb, int je,
                                                       double sxa, double sxb, double sya, double syb, double sza, double szb,
-                                                      double *s_j, float4 *s_jf, const PcTables &T, float near_a, unsigned long long *queue,
+                                                      float4 *s_jf, int *s_jidx, const PcTables &T, float near_a, unsigned long long *queue,
                                                       float dead_d2, unsigned int &it_all, unsigned int &it_live)
 {
     static_assert(PC_RI == 2, "the packed float32 loop pairs the two reference molecules of a thread");
     static_assert(MX + MY + MZ <= 4, "at most one component with two candidate images");
-    constexpr int ND = MX + MY + MZ;
-    static_assert(PC_TILE <= 512 && PC_JC <= 128, "queue entry layout");
-    static_assert(PC_JC == 32, "one staged molecule per lane");
     int qn = 0;                                         // entries in this warp's queue (warp-uniform)
-    const unsigned int lane_lt = (1u << (threadIdx.x & 31)) - 1u;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lane_lt = (1u << lane) - 1u;
     const unsigned long long X01 = pc_pack(xf[0], xf[1]), Y01 = pc_pack(yf[0], yf[1]), Z01 = pc_pack(zf[0], zf[1]);
     const unsigned long long F2 = pc_pack(p.f32_lo, p.f32_hi), M2 = pc_pack(8388608.0f, 8388608.0f), A2 = pc_pack(-near_a, near_a);
     const float zthr = 2.0e-9f;                         // 2^-30 plus the float32 error of dx~^2 + dy~^2 near the axis
     const int na = T.na;
-    const unsigned int cnt_m = T.cnt - 0x4B000000u * 4u;
     const unsigned int trash = T.cnt + (unsigned)(na + 2) * 4u;
-    const unsigned int a_jf = (unsigned int)__cvta_generic_to_shared(s_jf), a_j = (unsigned int)__cvta_generic_to_shared(s_j);
+    const unsigned int a_jf = (unsigned int)__cvta_generic_to_shared(s_jf);
+    const long long ibase = (long long)tl.frame * gi.nmol + tl.begin;
     constexpr int NU = 2;                               // staged molecules per iteration (4 measured slower)
-    static_assert(NU == 2, "the warp-uniform skip test and the statistics assume two staged molecules per iteration");
+    static_assert(NU == 2, "queue entries and statistics assume two staged molecules per iteration");
     constexpr int NP = NU * PC_RI;
-    for (int jc = jb; jc < je; jc += PC_JC) {
-        __syncwarp();
+    int fill = 0;                                       // molecules in the warp's buffer (warp-uniform)
+    for (int jc = jb; jc < je; jc += 32) {
+        // ---- stage: one candidate per lane, keep the ones that can reach the tile -------------------------------
         {
-            const int t = threadIdx.x & 31;
-            const int j = jc + t;
-            double x = 1.0e15, y = 1.0e15, z = 1.0e15, b2 = 1.0e15;      // b2: second candidate of the two-image component
-            float4 f = make_float4(T.pad_x, 0.0f, 0.0f, MX == 2 ? T.pad_x : 0.0f);
+            const int j = jc + lane;
+            bool live = false;
+            float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             if (j < je) {
                 const double gx0 = go.sx[jbase + j], gy0 = go.sy[jbase + j], gz0 = go.sz[jbase + j];
-                x = __dadd_rn(gx0, sxa); y = __dadd_rn(gy0, sya); z = __dadd_rn(gz0, sza);
-                f.x = __double2float_rn(__dsub_rn(x, ox)); f.y = __double2float_rn(__dsub_rn(y, oy)); f.z = __double2float_rn(__dsub_rn(z, oz));
-                if (MX == 2) { b2 = __dadd_rn(gx0, sxb); f.w = __double2float_rn(__dsub_rn(b2, ox)); }
-                if (MY == 2) { b2 = __dadd_rn(gy0, syb); f.w = __double2float_rn(__dsub_rn(b2, oy)); }
-                if (MZ == 2) { b2 = __dadd_rn(gz0, szb); f.w = __double2float_rn(__dsub_rn(b2, oz)); }
+                f.x = __double2float_rn(__dsub_rn(__dadd_rn(gx0, sxa), ox));
+                f.y = __double2float_rn(__dsub_rn(__dadd_rn(gy0, sya), oy));
+                f.z = __double2float_rn(__dsub_rn(__dadd_rn(gz0, sza), oz));
+                if (MX == 2) f.w = __double2float_rn(__dsub_rn(__dadd_rn(gx0, sxb), ox));
+                if (MY == 2) f.w = __double2float_rn(__dsub_rn(__dadd_rn(gy0, syb), oy));
+                if (MZ == 2) f.w = __double2float_rn(__dsub_rn(__dadd_rn(gz0, szb), oz));
+                // lower bound of the d2~ of any pair (tile molecule, j): same operations as the pair loop below
+                float g1 = fmaxf(__fsub_rd(fabsf(f.x), hx), 0.0f), g2 = fmaxf(__fsub_rd(fabsf(f.y), hy), 0.0f), g3 = fmaxf(__fsub_rd(fabsf(f.z), hz), 0.0f);
+                float bound;
+                if (MX == 2) {
+                    g1 = fminf(g1, fmaxf(__fsub_rd(fabsf(f.w), hx), 0.0f));
+                    bound = __fmaf_rn(g3, g3, __fmaf_rn(g2, g2, __fmul_rn(g1, g1)));
+                } else if (MY == 2) {
+                    g2 = fminf(g2, fmaxf(__fsub_rd(fabsf(f.w), hy), 0.0f));
+                    bound = __fmaf_rn(g3, g3, __fadd_rn(__fmul_rn(g1, g1), __fmul_rn(g2, g2)));
+                } else if (MZ == 2) {
+                    g3 = fminf(g3, fmaxf(__fsub_rd(fabsf(f.w), hz), 0.0f));
+                    bound = __fadd_rn(__fmaf_rn(g2, g2, __fmul_rn(g1, g1)), __fmul_rn(g3, g3));
+                } else {
+                    bound = __fmaf_rn(g3, g3, __fmaf_rn(g2, g2, __fmul_rn(g1, g1)));
+                }
+                live = !(bound >= dead_d2);
+                if (VERIFY && !live) {
+                    // a dropped molecule must be beyond the cutoff (class na + 1) for every molecule of the tile
+#pragma unroll 1
+                    for (int k = 0; k < tl.count; ++k) {
+                        double e1, e2;
+                        pc_exact_pair<MX, MY, MZ>(go, gi, jbase + j, ibase + k, sxa, sxb, sya, syb, sza, szb, e1, e2);
+                        if (!(e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (na + 1))))) atomicAdd(p.verify_fail, 1u);
+                    }
+                }
             }
-            {
-                double *rec = s_j + t * ND;                               // same layout as pc_segment
-                int o = 0;
-                rec[o++] = x; if (MX == 2) rec[o++] = b2;
-                rec[o++] = y; if (MY == 2) rec[o++] = b2;
-                rec[o++] = z; if (MZ == 2) rec[o++] = b2;
+            const unsigned int m = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const int pos = fill + __popc(m & lane_lt);
+                s_jf[pos] = f;
+                s_jidx[pos] = j;
             }
-            s_jf[t] = f;
+            fill += __popc(m);
+        }
+        if (!(fill > PC_FBUF - 32 || (jc + 32 >= je && fill > 0))) continue;
+        // ---- evaluate the buffer ---------------------------------------------------------------------------------
+        if ((fill & 1) && lane == 0) {                   // odd count: one padded slot, beyond the cutoff for every tile molecule
+            s_jf[fill] = make_float4(T.pad_x, 0.0f, 0.0f, MX == 2 ? T.pad_x : 0.0f);
+            s_jidx[fill] = 0;
         }
         __syncwarp();
-        const int cnt = min(PC_JC, je - jc);
-        it_all += (unsigned)((cnt + NU - 1) / NU);
-        const unsigned int a_end = a_jf + (unsigned)cnt * 16u;
+        it_all += (unsigned)((fill + NU - 1) / NU); it_live += (unsigned)((fill + NU - 1) / NU);
+        const unsigned int a_end = a_jf + (unsigned)fill * 16u;
         for (unsigned int aj = a_jf; aj < a_end; aj += 16u * NU) {
             float4 wv[NU];
 #pragma unroll
             for (int u = 0; u < NU; ++u) wv[u] = pc_lds_f32x4(aj + 16u * u);
             unsigned int ca[NP], tlo[NP], thi[NP];
             float s1[NP];
-            unsigned long long s1q[NU], d2q[NU];
             bool slow = false;
 #pragma unroll
             for (int u = 0; u < NU; ++u) {
@@ -656,34 +762,6 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                     s1p = pc_fma2(dy, dy, pc_mul2(dx, dx));
                     d2p = pc_fma2(dz, dz, s1p);
                 }
-                s1q[u] = s1p; d2q[u] = d2p;
-            }
-            // Warp-uniform skip: when every pair of this iteration (4 per lane: the warp's slab of the tile against two
-            // observed molecules) has d2~ >= dead_d2, every lower class bracket is > na -- such a pair is never counted
-            // and never queued (see `need` below) -- so the square roots, brackets and atomics are skipped altogether.
-            if (DEADSKIP) {
-                const float m01 = fminf(fminf(pc_lo(d2q[0]), pc_hi(d2q[0])), fminf(pc_lo(d2q[NU - 1]), pc_hi(d2q[NU - 1])));
-                if (__all_sync(0xffffffffu, m01 >= dead_d2)) {
-                    if (VERIFY) {
-                        const int jj = (int)((aj - a_jf) >> 4);
-#pragma unroll
-                        for (int q = 0; q < NP; ++q) {
-                            const int r = q % PC_RI, u = q / PC_RI;
-                            if (pc_kidx(r) >= tl.count || jc + jj + u >= je) continue;
-                            const double *rec = s_j + (jj + u) * ND;
-                            const double e1 = __dadd_rn(pc_comp_sq<MX>(rec[0], rec[MX - 1], p1x[r]), pc_comp_sq<MY>(rec[MX], rec[MX + MY - 1], p1y[r]));
-                            const double e2 = __dadd_rn(e1, pc_comp_sq<MZ>(rec[MX + MY], rec[MX + MY + MZ - 1], p1z[r]));
-                            // must be "beyond the cutoff": class na + 1
-                            if (!(e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + (na + 1))))) atomicAdd(p.verify_fail, 1u);
-                        }
-                    }
-                    continue;
-                }
-            }
-            ++it_live;
-#pragma unroll
-            for (int u = 0; u < NU; ++u) {
-                const unsigned long long s1p = s1q[u], d2p = d2q[u];
 #pragma unroll
                 for (int r = 0; r < PC_RI; ++r) {
                     const int q = u * PC_RI + r;
@@ -701,23 +779,25 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
             }
             if (__any_sync(0xffffffffu, slow)) {                                  // warp-uniform: ~10% of the iterations
                 const int jj = (int)((aj - a_jf) >> 4);
+                unsigned int need = 0u;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     const int r = q % PC_RI, u = q / PC_RI;
-                    const int k = pc_kidx(r);
-                    // not for padded slots, and not when even the lower bracket is beyond the cutoff (class > na: never counted,
-                    // and the threshold table ends at class na + 2)
-                    const bool need = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && tlo[q] <= 0x4B000000u + (unsigned)na &&
-                                      k < tl.count && jc + jj + u < je;
-                    const unsigned int m = __ballot_sync(0xffffffffu, need);
-                    if (m == 0u) continue;
+                    // not for padded slots, and not when even the lower bracket is beyond the cutoff (class > na: never counted)
+                    const bool nq = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && tlo[q] <= 0x4B000000u + (unsigned)na &&
+                                    pc_kidx(r) < tl.count && jj + u < fill;
+                    if (nq) { need |= 1u << q; ca[q] = trash; }                   // counted by the drain
+                }
+                const unsigned int m = __ballot_sync(0xffffffffu, need != 0u);
+                if (m != 0u) {
                     const int add = __popc(m);
-                    if (qn + add > PC_QCAP) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m, na, T.cut, T.special); qn = 0; }
-                    if (need) {
-                        queue[qn + __popc(m & lane_lt)] = ((unsigned long long)tlo[q] << 32) | ((unsigned long long)min(thi[q] - tlo[q], 255u) << 16) |
-                                                          ((unsigned long long)(jj + u) << 9) | (unsigned long long)k;
-                        ca[q] = trash;                                            // counted by the drain
+                    if (qn + add > PC_QCAP) {
+                        pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, jbase, sxa, sxb, sya, syb, sza, szb, T.cnt, na, T.cut, T.special);
+                        qn = 0;
                     }
+                    if (need)
+                        queue[qn + __popc(m & lane_lt)] = (unsigned long long)(unsigned int)s_jidx[jj] | ((unsigned long long)(unsigned int)s_jidx[jj + 1] << 24) |
+                                                          ((unsigned long long)lane << 48) | ((unsigned long long)need << 53);
                     qn += add;
                 }
             }
@@ -726,10 +806,9 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
                     const int r = q % PC_RI, u = q / PC_RI;
-                    if (pc_kidx(r) >= tl.count || jc + jj + u >= je || ca[q] == trash) continue;
-                    const double *rec = s_j + (jj + u) * ND;
-                    const double e1 = __dadd_rn(pc_comp_sq<MX>(rec[0], rec[MX - 1], p1x[r]), pc_comp_sq<MY>(rec[MX], rec[MX + MY - 1], p1y[r]));
-                    const double e2 = __dadd_rn(e1, pc_comp_sq<MZ>(rec[MX + MY], rec[MX + MY + MZ - 1], p1z[r]));
+                    if (pc_kidx(r) >= tl.count || jj + u >= fill || ca[q] == trash) continue;
+                    double e1, e2;
+                    pc_exact_pair<MX, MY, MZ>(go, gi, jbase + s_jidx[jj + u], ibase + pc_kidx(r), sxa, sxb, sya, syb, sza, szb, e1, e2);
                     int lo_k = 0, hi_k = na + 1;
                     while (lo_k < hi_k) { const int mid = (lo_k + hi_k + 1) >> 1; if (e2 >= __longlong_as_double((long long)__ldg(p.job.thr_a + mid))) lo_k = mid; else hi_k = mid - 1; }
                     const int got = (int)((ca[q] - T.cnt) / 4u);
@@ -740,8 +819,10 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
 #pragma unroll
             for (int q = 0; q < NP; ++q) pc_red(ca[q]);
         }
-        if (qn > 0) { pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, a_j, jbase, jc, cnt_m, na, T.cut, T.special); qn = 0; }   // before the chunk is overwritten
+        fill = 0;
+        __syncwarp();                                    // the buffer is refilled by the next staging step
     }
+    if (qn > 0) pc_f32_drain<MX, MY, MZ, ZCOL>(p, go, gi, tl, queue, qn, jbase, sxa, sxb, sya, syb, sza, szb, T.cnt, na, T.cut, T.special);   // the shifts belong to this run
 }
 
 template <int VARIANT>
@@ -837,8 +918,14 @@ static __device__ __forceinline__ double pc_warp_max(double v)
 
 // PART 0: every run in one launch.  PART 1 / PART 2: the float32-eligible runs (single image or one two-image
 // component) and all other runs as two launches over the same work items, so that each gets its own register allocation.
-// DEADSKIP (PART 1): warp-uniform skip of iterations whose pairs are all beyond the cutoff (see pc_segment_f32).
-template <int VARIANT, bool VERIFY, bool SYM, int PART, bool DEADSKIP>
+static __host__ __device__ __forceinline__ size_t pc_warp_bytes(bool part1, int nlay)
+{
+    // per warp (16-byte aligned slices): PART 1: staged local float4 (PC_FBUF) + their sorted positions + queue of deferred
+    // exact decisions; other parts: staged doubles (PC_JC * 6); both: layer classification of the warp's tile
+    const size_t stage = part1 ? (size_t)PC_FBUF * 16 + (size_t)PC_FBUF * 4 + (size_t)PC_QCAP * 8 : (size_t)PC_JC * 6 * 8;
+    return stage + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15);
+}
+template <int VARIANT, bool VERIFY, bool SYM, int PART>
 __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
                                                                    const unsigned int *ntiles_ptr, unsigned int tile_cap,
                                                                    unsigned int *work_counter, int nzg)
@@ -852,15 +939,13 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
     // CTA-wide: threshold table (PART 1 reads it from global memory when needed) and the class counters
     unsigned long long *s_thr = reinterpret_cast<unsigned long long *>(smem_raw);          // na+3 (PART 1: none)
     unsigned int *s_cnt = reinterpret_cast<unsigned int *>(s_thr + (PART == 1 ? 0 : na + 3));   // ncnt (+1 pad)
-    // per warp (16-byte aligned slices): staged observed molecules as doubles (PC_JC*6, PART 1: *4) and as local float4,
-    // the layer classification of the warp's tile (x layers, y layers, z layers) and the queue of deferred exact decisions
-    constexpr int NDMAX = PART == 1 ? 4 : 6;
-    const size_t warp_bytes = (size_t)PC_JC * NDMAX * 8 + (size_t)PC_JC * 16 + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15) + (size_t)PC_QCAP * 8;
-    unsigned char *wbase = smem_raw + ((((size_t)(PART == 1 ? 0 : na + 3) * 8 + (size_t)(ncnt + 1) * 4) + 15) & ~(size_t)15) + (size_t)warp * warp_bytes;
-    double *s_j = reinterpret_cast<double *>(wbase);
-    float4 *s_jf = reinterpret_cast<float4 *>(s_j + PC_JC * NDMAX);
-    PcLayer *lay = reinterpret_cast<PcLayer *>(s_jf + PC_JC);
-    unsigned long long *queue = reinterpret_cast<unsigned long long *>(reinterpret_cast<unsigned char *>(lay) + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15));
+    unsigned char *wbase = smem_raw + ((((size_t)(PART == 1 ? 0 : na + 3) * 8 + (size_t)(ncnt + 1) * 4) + 15) & ~(size_t)15) +
+                           (size_t)warp * pc_warp_bytes(PART == 1, nlay);
+    double *s_j = reinterpret_cast<double *>(wbase);                                       // PART 0 / 2
+    float4 *s_jf = reinterpret_cast<float4 *>(wbase);                                      // PART 1
+    int *s_jidx = reinterpret_cast<int *>(s_jf + PC_FBUF);
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(s_jidx + PC_FBUF);
+    PcLayer *lay = reinterpret_cast<PcLayer *>(wbase + (PART == 1 ? (size_t)PC_FBUF * 20 + (size_t)PC_QCAP * 8 : (size_t)PC_JC * 6 * 8));
 
     for (int k = threadIdx.x; k < (PART == 1 ? 0 : na + 3); k += blockDim.x)
         s_thr[k] = p.job.thr_a[k];       // "never" (all ones) is a NaN as a double: every `d2 >= NaN` is false, as required
@@ -932,7 +1017,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
         float xf[PC_RI], yf[PC_RI], zf[PC_RI];
         unsigned int cb[PC_RI];
         const double ox = 0.5 * (blox + bhix), oy = 0.5 * (bloy + bhiy), oz = 0.5 * (bloz + bhiz);
-        float tile_t2 = 0.0f;
+        float tile_t2 = 0.0f, hx = 0.0f, hy = 0.0f, hz = 0.0f;
         if (f32_on) {
 #pragma unroll
             for (int r = 0; r < PC_RI; ++r) {
@@ -942,8 +1027,13 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                 zf[r] = __double2float_rn(__dsub_rn(q1z[r], oz));
                 cb[r] = T.cnt - 0x4B000000u * 4u + (live ? 0u : T.cnt_pad);      // padded slots count into a window nobody reads
                 tile_t2 = fmaxf(tile_t2, __fmaf_ru(zf[r], zf[r], __fmaf_ru(yf[r], yf[r], __fmul_ru(xf[r], xf[r]))));
+                hx = fmaxf(hx, fabsf(xf[r])); hy = fmaxf(hy, fabsf(yf[r])); hz = fmaxf(hz, fabsf(zf[r]));
             }
             tile_t2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(tile_t2)));
+            // half extents of the tile in local float32 coordinates (non-negative floats order like their bit patterns)
+            hx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hx)));
+            hy = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hy)));
+            hz = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hz)));
         } else {
 #pragma unroll
             for (int r = 0; r < PC_RI; ++r) { xf[r] = yf[r] = zf[r] = 0.0f; cb[r] = 0u; }
@@ -976,8 +1066,7 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
         const float near_a = 1.25e-7f * sqrtf(tile_t2) + 1.0e-12f;       // 2u|T| (u = 2^-24), rounded up
         // d2~ from which the lower bracket floor((sqrt.approx(d2~) - a) * f32_lo) is certainly > na (sqrt.approx: 2^-22 relative)
         const float dead_r = __fadd_ru(p.dead_r, near_a);
-        float dead_d2 = __fmul_ru(__fmul_ru(dead_r, dead_r), 1.000001f);
-        asm volatile("" : "+f"(dead_d2));                                 // keep it in a register: ptxas otherwise recomputes it per iteration
+        const float dead_d2 = __fmul_ru(__fmul_ru(dead_r, dead_r), 1.000001f);
 
         const long long jbase = (long long)tl.frame * go.nmol;
         const int *cs = go.cell_start + (long long)tl.frame * (go.ncell + 1);
@@ -1043,8 +1132,8 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_ke
                     if (jb >= je) continue;
                     if (PART == 2 && f32run) continue;                              // counted by the PART 1 launch
                     if (VARIANT == 0 && PART == 1 && f32run) {
-#define PC_F32(MX_, MY_, MZ_, Z_, N_) pc_segment_f32<MX_, MY_, MZ_, Z_, N_, VERIFY, DEADSKIP>(p, go, gi, tl, xf, yf, zf, cb, p1x, p1y, p1z, ox, oy, oz, jbase, jb, je, \
-                                                                                    sxa, sxb, sya, syb, sza, szb, s_j, s_jf, T, near_a, queue, dead_d2, it_all, it_live)
+#define PC_F32(MX_, MY_, MZ_, Z_, N_) pc_segment_f32<MX_, MY_, MZ_, Z_, N_, VERIFY>(p, go, gi, tl, xf, yf, zf, cb, hx, hy, hz, ox, oy, oz, jbase, jb, je, \
+                                                                                    sxa, sxb, sya, syb, sza, szb, s_jf, s_jidx, T, near_a, queue, dead_d2, it_all, it_live)
                         if (dcode == 0) {
                             if (nearr) { if (zcol) PC_F32(1, 1, 1, true, true); else PC_F32(1, 1, 1, false, true); }
                             else { if (zcol) PC_F32(1, 1, 1, true, false); else PC_F32(1, 1, 1, false, false); }
@@ -1343,7 +1432,10 @@ int pa_launch_cell_sort(const PaCellGrid &g, const PaPoints &pts, const PaBox &b
     cudaMemsetAsync(g.lay_hi, 0x00, sizeof(unsigned long long) * (size_t)nframes * 3 * g.gmax, st);
     pa_cell_count_kernel<<<blocks, 256, 0, st>>>(g, pts, box, frame0, nframes, err);
     pa_cell_scan_kernel<<<nframes, 1024, 0, st>>>(g);
-    pa_cell_scatter_kernel<<<blocks, 256, 0, st>>>(g, pts, box, frame0, nframes);
+    pa_cell_scatter_kernel<<<blocks, 256, 0, st>>>(g, nframes);
+    const long long order_threads = (long long)nframes * g.ncell * 32;
+    pa_cell_order_kernel<<<(int)std::min<long long>((order_threads + 255) / 256, 148 * 16), 256, 0, st>>>(g, nframes, err);
+    pa_cell_gather_kernel<<<blocks, 256, 0, st>>>(g, pts, box, frame0, nframes);
     return (int)cudaGetLastError();
 }
 
@@ -1382,9 +1474,7 @@ size_t pa_cells_smem_bytes(int na, int f32_cnt, int nlayers)   // f32_cnt > 0: t
 {
     const int ncnt = (f32_cnt > 0 ? f32_cnt + na + 8 : na + 3) + 1;
     const size_t cta = ((f32_cnt > 0 ? 0 : (size_t)(na + 3) * 8) + (size_t)(ncnt + 1) * 4 + 15) & ~(size_t)15;
-    const size_t warp = (size_t)PC_JC * (f32_cnt > 0 ? 4 : 6) * 8 + (size_t)PC_JC * 16 + (((size_t)nlayers * sizeof(PcLayer) + 15) & ~(size_t)15) +
-                        (size_t)PC_QCAP * 8;
-    return cta + (size_t)PC_WARPS * warp + 16;
+    return cta + (size_t)PC_WARPS * pc_warp_bytes(f32_cnt > 0, nlayers) + 16;
 }
 
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
@@ -1395,28 +1485,28 @@ int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
     const size_t smem = pa_cells_smem_bytes(p.job.bin_a, variant == 0 ? p.f32_cnt : 0, go.g[0] + go.g[1] + go.g[2]);
     const size_t smem0 = pa_cells_smem_bytes(p.job.bin_a, 0, go.g[0] + go.g[1] + go.g[2]);
     const bool verify = p.verify_fail != nullptr;
-#define PC_LAUNCH4(O_, V_, S_, P_, D_, SMEM_)                                                                   \
+#define PC_LAUNCH3(O_, V_, S_, P_, SMEM_)                                                                        \
     do {                                                                                                        \
         int occ = 1;                                                                                            \
         cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);                                             \
-        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_, S_, P_, D_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)); \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_, S_, P_, D_>, PC_THREADS, (SMEM_)) != cudaSuccess || occ < 1) occ = 1; \
-        pa_rdf_cells_kernel<O_, V_, S_, P_, D_><<<sm_count * occ, PC_THREADS, (SMEM_), st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+        cudaFuncSetAttribute(pa_rdf_cells_kernel<O_, V_, S_, P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_rdf_cells_kernel<O_, V_, S_, P_>, PC_THREADS, (SMEM_)) != cudaSuccess || occ < 1) occ = 1; \
+        pa_rdf_cells_kernel<O_, V_, S_, P_><<<sm_count * occ, PC_THREADS, (SMEM_), st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
     } while (0)
 #define PC_LAUNCH2(O_, V_, S_)                                                                                  \
     do {                                                                                                        \
         if (O_ == 0 && p.f32_cnt > 0) {                                                                         \
             if (ev_f32_begin) cudaEventRecord((cudaEvent_t)ev_f32_begin, st);                                   \
-            if (p.deadskip) PC_LAUNCH4(O_, V_, S_, 1, true, smem); else PC_LAUNCH4(O_, V_, S_, 1, false, smem); \
+            PC_LAUNCH3(O_, V_, S_, 1, smem);                                                                    \
             if (ev_f32_end) cudaEventRecord((cudaEvent_t)ev_f32_end, st);                                       \
-            PC_LAUNCH4(O_, V_, S_, 2, false, smem0);                                                            \
+            PC_LAUNCH3(O_, V_, S_, 2, smem0);                                                                   \
         }                                                                                                       \
-        else PC_LAUNCH4(O_, V_, S_, 0, false, smem0);                                                           \
+        else PC_LAUNCH3(O_, V_, S_, 0, smem0);                                                                  \
     } while (0)
 #define PC_LAUNCH(O_, V_) do { if (p.sym) PC_LAUNCH2(O_, V_, true); else PC_LAUNCH2(O_, V_, false); } while (0)
     if (variant == 1) { if (verify) PC_LAUNCH(1, true); else PC_LAUNCH(1, false); }
     else { if (verify) PC_LAUNCH(0, true); else PC_LAUNCH(0, false); }
-#undef PC_LAUNCH4
+#undef PC_LAUNCH3
 #undef PC_LAUNCH2
 #undef PC_LAUNCH
     return (int)cudaGetLastError();

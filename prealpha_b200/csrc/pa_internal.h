@@ -96,7 +96,7 @@ struct PaPass {
     float eps64;                // half-width of the class brackets of the fp64-difference segments (variant 0)
     float f32_lo, f32_hi;       // (1 -+ eps)/step_a rounded outwards (eps: pa_session.cu); adjacent so that they load as one packed pair
     int32_t tshard_rank, tshard_count;   // tile shard of this device (pa_exec.tile_shard_*): work item w is taken when w % count == rank
-    int32_t deadskip;           // 1: float32 launch skips iterations whose pairs are all beyond the cutoff (debug flag 0x400 clears it)
+    int32_t pad0_;
     float dead_r;               // (bin_a + 1)/f32_lo rounded up: from this approximate distance on, the lower class bracket is beyond the cutoff
     unsigned long long *kstats; // device counters of the cell kernels (8 words, may be null): [0] pair evaluations after cell pruning
                                 // and [1] shared-memory atomics issued by the float32 launches, [4] / [5] the same for the other

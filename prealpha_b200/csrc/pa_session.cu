@@ -366,7 +366,9 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
                 const double diag = std::sqrt(s->box.L[0] * s->box.L[0] + s->box.L[1] * s->box.L[1] + s->box.L[2] * s->box.L[2]);
                 const double far = std::max(diag, (double)jb.maxdist * 1.001 + 128.0);
                 const double ncl = far * (double)d.guess_scale * 1.00001 + 4.0;
-                if (ncl + jb.bin_a + 8 <= 12288.0) js.f32_cnt = (int)ncl;
+                bool small = true;                                  // queue entries of the float32 launch hold sorted positions in 24 bits
+                for (int t = 0; t < traj->ntypes; ++t) if (traj->types[t].nmol >= (1 << 24)) small = false;
+                if (ncl + jb.bin_a + 8 <= 12288.0 && small) js.f32_cnt = (int)ncl;
             }
         }
     }
@@ -502,7 +504,7 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         if (!tg.enabled) continue;
         PA_CK((cudaError_t)pa_launch_cell_sort(tg.g, s->pts, s->box, first, count, s->d_exc_count + 1, s->s_compute));
         tg.tiles_ready = tg.wtiles_ready = false;
-        s->stats.kernel_launches += 3;
+        s->stats.kernel_launches += 5;
     }
     const long long target_items = (long long)s->sm_count * 16;
     // ---- plan: one pass per (job, observed type), Distribution:727-735 ---------------------------------
@@ -581,7 +583,6 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
             if ((double)p.dead_r < dead) p.dead_r = std::nextafterf(p.dead_r, INFINITY);
         }
         p.tshard_rank = s->exec.tile_shard_rank; p.tshard_count = s->exec.tile_shard_count;
-        p.deadskip = (s->exec.flags & 0x400) ? 0 : 1;               // debug flag: float32 launch without the warp-uniform skip
         p.kstats = s->d_kstats;
     };
     for (const Plan &pl : plan) {

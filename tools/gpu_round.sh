@@ -14,10 +14,9 @@ fi
 timeout 600 python bench.py --steps 6 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 cat gpurun_out/${TAG}_bench.json | cut -c1-2600
 tail -3 gpurun_out/${TAG}_bench.err
-timeout 600 python bench.py --steps 4 --warmup 3 --no-cpu-baseline --flags 1024 > gpurun_out/${TAG}_bench_nodeadskip.json 2> gpurun_out/${TAG}_bench_nodeadskip.err; echo "bench(no deadskip) rc=$?"
 python - <<PY
 import json
-for n in ("bench", "bench_nodeadskip"):
+for n in ("bench",):
     try:
         d = json.load(open("gpurun_out/${TAG}_%s.json" % n)); r = d["roofline"]
         print(n, "ms/step %.1f value %.3e e2e %.3e frac %.3f useful %.3f atomics/step %.3e evals/step %.3e dom_ms %.1f" % (d["ms_per_step"], d["value"], d["e2e"]["value"], r["frac"], r["useful_frac"], r["atomics_per_step_per_gpu"], r["pair_evals_after_pruning_per_step_per_gpu"], r["ms_per_launch"]))
