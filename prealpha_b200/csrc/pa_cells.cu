@@ -29,6 +29,9 @@
 // molecules into its own slice of shared memory and never meets a CTA-wide barrier inside the work loop; only the
 // class counters (and the threshold table) are shared by the warps of a CTA.
 #define PC_WARPS 4
+#ifndef PC_MINB
+#define PC_MINB 6                   // resident CTAs per SM the float32 launch is compiled for (80 registers per thread)
+#endif
 #define PC_THREADS (32 * PC_WARPS)
 #define PC_RI 2
 #define PC_TILE (32 * PC_RI)
@@ -490,7 +493,7 @@ static __device__ __forceinline__ void pc_segment(const PaPass &p, const PaCellG
 //
 // The approximate class of a pair is computed entirely in float32 from LOCAL coordinates about the tile
 // origin O (T = largest distance of a tile molecule from O, measured per tile):
-//     xi~ = fl32(xi - O),  xj~ = fl32(fl64(xj + s) - O),  d~ = fl32(xj~ - xi~),
+//     xi~ = fl32(xi - O),  xj~ = fl32(fl64(xj + fl64(s - O))),  d~ = fl32(xj~ - xi~),
 //     d2~ = fma(dz~,dz~, fma(dy~,dy~, fl32(dx~*dx~))),   r~ = sqrt.approx(d2~),
 // two reference molecules per instruction (sm_100 packed FADD2 / FMUL2 / FFMA2).
 // With u = 2^-24: |d~_k - d_k| <= u(|xi_k-O_k| + |xj~_k| + |d~_k|) <= u(2|d_k| + 2T_k)(1+o(1)), and
@@ -675,21 +678,31 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
     constexpr int NU = 2;                               // staged molecules per iteration (4 measured slower)
     static_assert(NU == 2, "queue entries and statistics assume two staged molecules per iteration");
     constexpr int NP = NU * PC_RI;
+    const unsigned int tlim = 0x4B000000u + (unsigned)na;
+    // pairs (bit u * PC_RI + r) whose reference slot r holds a real molecule of the tile
+    const unsigned int kmask = (pc_kidx(0) < tl.count ? 0x5u : 0u) | (pc_kidx(1) < tl.count ? 0xAu : 0u);
     int fill = 0;                                       // molecules in the warp's buffer (warp-uniform)
+    // local coordinate of an observed molecule: fl32(fl64(xj + c)) with c = fl64(s - O), image shift and tile origin folded
+    // into one constant per run (the two fp64 roundings, < 1.3e-13 A together, are far inside the float32 budget)
+    const double cxa = __dsub_rn(sxa, ox), cya = __dsub_rn(sya, oy), cza = __dsub_rn(sza, oz);
+    const double cb2 = MX == 2 ? __dsub_rn(sxb, ox) : (MY == 2 ? __dsub_rn(syb, oy) : __dsub_rn(szb, oz));   // second candidate of the two-image component
+    // the candidates of a staging step are loaded one step ahead (the global-memory latency overlaps the compaction
+    // and the pair loop of the step before)
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    if (jb + lane < je) { nx = go.sx[jbase + jb + lane]; ny = go.sy[jbase + jb + lane]; nz = go.sz[jbase + jb + lane]; }
     for (int jc = jb; jc < je; jc += 32) {
         // ---- stage: one candidate per lane, keep the ones that can reach the tile -------------------------------
         {
             const int j = jc + lane;
             bool live = false;
             float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            const double gx0 = nx, gy0 = ny, gz0 = nz;
+            if (j + 32 < je) { nx = go.sx[jbase + j + 32]; ny = go.sy[jbase + j + 32]; nz = go.sz[jbase + j + 32]; }
             if (j < je) {
-                const double gx0 = go.sx[jbase + j], gy0 = go.sy[jbase + j], gz0 = go.sz[jbase + j];
-                f.x = __double2float_rn(__dsub_rn(__dadd_rn(gx0, sxa), ox));
-                f.y = __double2float_rn(__dsub_rn(__dadd_rn(gy0, sya), oy));
-                f.z = __double2float_rn(__dsub_rn(__dadd_rn(gz0, sza), oz));
-                if (MX == 2) f.w = __double2float_rn(__dsub_rn(__dadd_rn(gx0, sxb), ox));
-                if (MY == 2) f.w = __double2float_rn(__dsub_rn(__dadd_rn(gy0, syb), oy));
-                if (MZ == 2) f.w = __double2float_rn(__dsub_rn(__dadd_rn(gz0, szb), oz));
+                f.x = __double2float_rn(__dadd_rn(gx0, cxa));
+                f.y = __double2float_rn(__dadd_rn(gy0, cya));
+                f.z = __double2float_rn(__dadd_rn(gz0, cza));
+                if (MX == 2 || MY == 2 || MZ == 2) f.w = __double2float_rn(__dadd_rn(MX == 2 ? gx0 : (MY == 2 ? gy0 : gz0), cb2));
                 // lower bound of the d2~ of any pair (tile molecule, j): same operations as the pair loop below
                 float g1 = fmaxf(__fsub_rd(fabsf(f.x), hx), 0.0f), g2 = fmaxf(__fsub_rd(fabsf(f.y), hy), 0.0f), g3 = fmaxf(__fsub_rd(fabsf(f.z), hz), 0.0f);
                 float bound;
@@ -782,12 +795,13 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
                 unsigned int need = 0u;
 #pragma unroll
                 for (int q = 0; q < NP; ++q) {
-                    const int r = q % PC_RI, u = q / PC_RI;
-                    // not for padded slots, and not when even the lower bracket is beyond the cutoff (class > na: never counted)
-                    const bool nq = (tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && tlo[q] <= 0x4B000000u + (unsigned)na &&
-                                    pc_kidx(r) < tl.count && jj + u < fill;
-                    if (nq) { need |= 1u << q; ca[q] = trash; }                   // counted by the drain
+                    // not when even the lower bracket is beyond the cutoff (class > na: never counted; this also covers the
+                    // padded observed slot, which sits beyond the cutoff), and not for padded reference slots (kmask)
+                    if ((tlo[q] != thi[q] || (ZCOL && s1[q] < zthr)) && tlo[q] <= tlim) need |= 1u << q;
                 }
+                need &= kmask;
+#pragma unroll
+                for (int q = 0; q < NP; ++q) if (need & (1u << q)) ca[q] = trash;   // counted by the drain
                 const unsigned int m = __ballot_sync(0xffffffffu, need != 0u);
                 if (m != 0u) {
                     const int add = __popc(m);
@@ -926,7 +940,7 @@ static __host__ __device__ __forceinline__ size_t pc_warp_bytes(bool part1, int 
     return stage + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15);
 }
 template <int VARIANT, bool VERIFY, bool SYM, int PART>
-__global__ void __launch_bounds__(PC_THREADS, PART == 1 ? 6 : 0) pa_rdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
+__global__ void __launch_bounds__(PC_THREADS, PART == 1 ? PC_MINB : 0) pa_rdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
                                                                    const unsigned int *ntiles_ptr, unsigned int tile_cap,
                                                                    unsigned int *work_counter, int nzg)
 {
