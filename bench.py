@@ -332,7 +332,6 @@ def main():
         gaps = np.diff(step_marks)
         if len(gaps) > 2 and gaps[0] > 1.5 * np.median(gaps[1:]):
             print(f"[bench] WARNING: first timed step took {gaps[0]:.3f} s against a median of {np.median(gaps[1:]):.3f} s", file=sys.stderr)
-    clocks = sampler.stop() if rank == 0 else None
     hists, within, oob = sess.download()
     st1 = sess.stats()
     sess.close()
@@ -381,6 +380,9 @@ def main():
             w2_total += int(w2.sum())
     barrier()
     t_e2e = time.perf_counter() - t0
+    # the sampler runs through both timed regions: stopping nvidia-smi detaches it from the driver, which can stall
+    # CUDA calls of this process for a few hundred ms -- not something to have between the two arms
+    clocks = sampler.stop() if rank == 0 else None
     te = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -29,6 +29,10 @@
 // molecules into its own slice of shared memory and never meets a CTA-wide barrier inside the work loop; only the
 // class counters (and the threshold table) are shared by the warps of a CTA.
 #define PC_WARPS 4
+#ifndef PC_PREFETCH
+#define PC_PREFETCH 0               // float32 launch: load the candidates of the next staging step one step ahead (measured:
+                                    // 212 ms instead of 203 ms per 1M-atom frame -- the six extra registers cost more than the latency)
+#endif
 #ifndef PC_MINB
 #define PC_MINB 6                   // resident CTAs per SM the float32 launch is compiled for (80 registers per thread)
 #endif
@@ -688,16 +692,23 @@ static __device__ __forceinline__ void pc_segment_f32(const PaPass &p, const PaC
     const double cb2 = MX == 2 ? __dsub_rn(sxb, ox) : (MY == 2 ? __dsub_rn(syb, oy) : __dsub_rn(szb, oz));   // second candidate of the two-image component
     // the candidates of a staging step are loaded one step ahead (the global-memory latency overlaps the compaction
     // and the pair loop of the step before)
+#if PC_PREFETCH
     double nx = 0.0, ny = 0.0, nz = 0.0;
     if (jb + lane < je) { nx = go.sx[jbase + jb + lane]; ny = go.sy[jbase + jb + lane]; nz = go.sz[jbase + jb + lane]; }
+#endif
     for (int jc = jb; jc < je; jc += 32) {
         // ---- stage: one candidate per lane, keep the ones that can reach the tile -------------------------------
         {
             const int j = jc + lane;
             bool live = false;
             float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#if PC_PREFETCH
             const double gx0 = nx, gy0 = ny, gz0 = nz;
             if (j + 32 < je) { nx = go.sx[jbase + j + 32]; ny = go.sy[jbase + j + 32]; nz = go.sz[jbase + j + 32]; }
+#else
+            double gx0 = 0.0, gy0 = 0.0, gz0 = 0.0;
+            if (j < je) { gx0 = go.sx[jbase + j]; gy0 = go.sy[jbase + j]; gz0 = go.sz[jbase + j]; }
+#endif
             if (j < je) {
                 f.x = __double2float_rn(__dadd_rn(gx0, cxa));
                 f.y = __double2float_rn(__dadd_rn(gy0, cya));

@@ -99,6 +99,76 @@ void pinned_pool_give(void *ptr, size_t bytes)
 }
 }  // namespace
 
+// Device memory of finished sessions is kept as well (exact-size blocks, at most 4 GiB per process): a one-shot call
+// allocates ~40 buffers and frees them again, and cudaFree synchronises the device -- tens to hundreds of milliseconds
+// per call that repeated analyses of same-shaped trajectories need not pay.  pa_trim() returns everything.
+namespace {
+struct DevBlock { void *ptr; size_t bytes; int dev; };
+std::mutex g_dev_mutex;
+std::vector<DevBlock> g_dev_pool;
+std::vector<DevBlock> g_dev_live;
+size_t g_dev_pool_bytes = 0;
+
+cudaError_t pool_malloc_raw(void **out, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (bytes == 0) bytes = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        for (size_t i = 0; i < g_dev_pool.size(); ++i)
+            if (g_dev_pool[i].dev == dev && g_dev_pool[i].bytes == bytes) {
+                *out = g_dev_pool[i].ptr;
+                g_dev_live.push_back(g_dev_pool[i]);
+                g_dev_pool_bytes -= bytes;
+                g_dev_pool.erase(g_dev_pool.begin() + i);
+                return cudaSuccess;
+            }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {
+        // out of memory with blocks parked in the pool: give them back and try once more
+        cudaGetLastError();
+        std::vector<DevBlock> drop;
+        { std::lock_guard<std::mutex> lock(g_dev_mutex); drop.swap(g_dev_pool); g_dev_pool_bytes = 0; }
+        for (const DevBlock &b : drop) { cudaSetDevice(b.dev); cudaFree(b.ptr); }
+        cudaSetDevice(dev);
+        e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) return e;
+    }
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    g_dev_live.push_back({ *out, bytes, dev });
+    return cudaSuccess;
+}
+template <typename T> cudaError_t pool_malloc(T **out, size_t bytes) { return pool_malloc_raw(reinterpret_cast<void **>(out), bytes); }
+
+void pool_free(void *ptr)
+{
+    if (!ptr) return;
+    DevBlock b{ ptr, 0, 0 };
+    bool keep = false;
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mutex);
+        for (size_t i = 0; i < g_dev_live.size(); ++i)
+            if (g_dev_live[i].ptr == ptr) { b = g_dev_live[i]; g_dev_live.erase(g_dev_live.begin() + i); break; }
+        if (b.bytes && g_dev_pool.size() < 512 && g_dev_pool_bytes + b.bytes <= (size_t(4) << 30)) {
+            g_dev_pool.push_back(b); g_dev_pool_bytes += b.bytes; keep = true;
+        }
+    }
+    if (!keep) cudaFree(ptr);
+}
+
+void pool_trim()
+{
+    std::vector<DevBlock> drop;
+    { std::lock_guard<std::mutex> lock(g_dev_mutex); drop.swap(g_dev_pool); g_dev_pool_bytes = 0; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    for (const DevBlock &b : drop) { cudaSetDevice(b.dev); cudaFree(b.ptr); }
+    cudaSetDevice(dev);
+}
+}  // namespace
+
 struct pa_session {
     int device = 0, sm_count = 148;
     pa_exec exec{};
@@ -166,6 +236,7 @@ void pa_trim(void)
         for (const PinnedEntry &e : g_pinned_pool) cudaFreeHost(e.ptr);
         g_pinned_pool.clear();
     }
+    pool_trim();
     pa_multi_device_trim();
 }
 const char *pa_last_error(void) { return g_last_error.c_str(); }
@@ -270,8 +341,8 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
     for (int t = 0; t < traj->ntypes; ++t) {
         TypeMeta &m = s->types[t];
         const pa_type &ty = traj->types[t];
-        PA_CK(cudaMalloc(&m.d_mass, sizeof(double) * m.natoms));
-        PA_CK(cudaMalloc(&m.d_charge, sizeof(double) * m.natoms));
+        PA_CK(pool_malloc(&m.d_mass, sizeof(double) * m.natoms));
+        PA_CK(pool_malloc(&m.d_charge, sizeof(double) * m.natoms));
         std::vector<double> zeros(m.natoms, 0.0);
         PA_CK(cudaMemcpy(m.d_mass, ty.atom_mass ? ty.atom_mass : zeros.data(), sizeof(double) * m.natoms, cudaMemcpyHostToDevice));
         PA_CK(cudaMemcpy(m.d_charge, ty.atom_charge ? ty.atom_charge : zeros.data(), sizeof(double) * m.natoms, cudaMemcpyHostToDevice));
@@ -282,18 +353,18 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
         s->d_raw[b].assign(traj->ntypes, nullptr);
         for (int t = 0; t < traj->ntypes; ++t)
             if (s->types[t].needed)
-                PA_CK(cudaMalloc(&s->d_raw[b][t], sizeof(float) * s->types[t].frame_floats() * (size_t)s->max_frames));
+                PA_CK(pool_malloc(&s->d_raw[b][t], sizeof(float) * s->types[t].frame_floats() * (size_t)s->max_frames));
         s->h_pinned_bytes[b] = sizeof(float) * std::max<size_t>(pinned, 1);
         s->h_pinned[b] = static_cast<float *>(pinned_pool_take(s->h_pinned_bytes[b]));
         if (!s->h_pinned[b]) PA_CK(cudaMallocHost(&s->h_pinned[b], s->h_pinned_bytes[b]));
-        PA_CK(cudaMalloc(&s->d_types[b], sizeof(PaDevType) * traj->ntypes));
+        PA_CK(pool_malloc(&s->d_types[b], sizeof(PaDevType) * traj->ntypes));
         int rc = upload_types_table(s, b);
         if (rc) return rc;
     }
     // points SoA
     const size_t nslots = (size_t)s->max_frames * (size_t)s->M;
     const int narr = s->need_coc ? 12 : 9;
-    PA_CK(cudaMalloc(&s->d_pts, sizeof(double) * nslots * narr));
+    PA_CK(pool_malloc(&s->d_pts, sizeof(double) * nslots * narr));
     double *b0 = s->d_pts;
     s->pts.px = b0; s->pts.py = b0 + nslots; s->pts.pz = b0 + 2 * nslots;
     s->pts.wx = b0 + 3 * nslots; s->pts.wy = b0 + 4 * nslots; s->pts.wz = b0 + 5 * nslots;
@@ -312,12 +383,12 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
         words += js.nbins + 2;
     }
     s->acc_words = words;
-    PA_CK(cudaMalloc(&s->d_acc, sizeof(unsigned long long) * words));
+    PA_CK(pool_malloc(&s->d_acc, sizeof(unsigned long long) * words));
     PA_CK(cudaMemset(s->d_acc, 0, sizeof(unsigned long long) * words));
-    PA_CK(cudaMalloc(&s->d_exc, sizeof(uint2) * kExcCap));
-    PA_CK(cudaMalloc(&s->d_exc_count, sizeof(unsigned int) * 8));
+    PA_CK(pool_malloc(&s->d_exc, sizeof(uint2) * kExcCap));
+    PA_CK(pool_malloc(&s->d_exc_count, sizeof(unsigned int) * 8));
     PA_CK(cudaMemset(s->d_exc_count, 0, sizeof(unsigned int) * 8));
-    PA_CK(cudaMalloc(&s->d_kstats, sizeof(unsigned long long) * 8));
+    PA_CK(pool_malloc(&s->d_kstats, sizeof(unsigned long long) * 8));
     PA_CK(cudaMemset(s->d_kstats, 0, sizeof(unsigned long long) * 8));
     for (int j = 0; j < njobs; ++j) {
         JobState &js = s->jobs[j];
@@ -326,11 +397,11 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
         std::vector<double> thr_b;
         if (jb.mode == PA_MODE_CHARGE_ARM) pa::build_thr_charge_arm(jb, thr_a, js.tiny_bits);
         else pa::build_thr_a(jb, traj->max_dist_sq, thr_a);
-        PA_CK(cudaMalloc(&js.d_thr_a, sizeof(unsigned long long) * thr_a.size()));
+        PA_CK(pool_malloc(&js.d_thr_a, sizeof(unsigned long long) * thr_a.size()));
         PA_CK(cudaMemcpy(js.d_thr_a, thr_a.data(), sizeof(unsigned long long) * thr_a.size(), cudaMemcpyHostToDevice));
         if (jb.mode != PA_MODE_CDF) {
             pa::build_thr_b(jb, thr_b);
-            PA_CK(cudaMalloc(&js.d_thr_b, sizeof(double) * thr_b.size()));
+            PA_CK(pool_malloc(&js.d_thr_b, sizeof(double) * thr_b.size()));
             PA_CK(cudaMemcpy(js.d_thr_b, thr_b.data(), sizeof(double) * thr_b.size(), cudaMemcpyHostToDevice));
         }
         PaDevJob &d = js.dj;
@@ -395,24 +466,24 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
             g.ncell = g.g[0] * g.g[1] * g.g[2]; g.nmol = s->types[t].nmol; g.type_off = s->types[t].offset;
             for (int k = 0; k < 3; ++k) g.inv_w[k] = (double)g.g[k] / s->box.L[k];
             const size_t nf = (size_t)s->max_frames, nm = (size_t)g.nmol;
-            PA_CK(cudaMalloc(&g.cell_start, sizeof(int) * nf * (g.ncell + 1)));
-            PA_CK(cudaMalloc(&g.cell_fill, sizeof(int) * nf * g.ncell));
-            PA_CK(cudaMalloc(&g.cid, sizeof(int) * nf * nm));
-            PA_CK(cudaMalloc(&g.sx, sizeof(double) * nf * nm));
-            PA_CK(cudaMalloc(&g.sy, sizeof(double) * nf * nm));
-            PA_CK(cudaMalloc(&g.sz, sizeof(double) * nf * nm));
-            PA_CK(cudaMalloc(&g.sorig, sizeof(int) * nf * nm));
-            PA_CK(cudaMalloc(&g.sflag, nf * nm));
-            PA_CK(cudaMalloc(&g.lay_lo, sizeof(unsigned long long) * nf * 3 * g.gmax));
-            PA_CK(cudaMalloc(&g.lay_hi, sizeof(unsigned long long) * nf * 3 * g.gmax));
+            PA_CK(pool_malloc(&g.cell_start, sizeof(int) * nf * (g.ncell + 1)));
+            PA_CK(pool_malloc(&g.cell_fill, sizeof(int) * nf * g.ncell));
+            PA_CK(pool_malloc(&g.cid, sizeof(int) * nf * nm));
+            PA_CK(pool_malloc(&g.sx, sizeof(double) * nf * nm));
+            PA_CK(pool_malloc(&g.sy, sizeof(double) * nf * nm));
+            PA_CK(pool_malloc(&g.sz, sizeof(double) * nf * nm));
+            PA_CK(pool_malloc(&g.sorig, sizeof(int) * nf * nm));
+            PA_CK(pool_malloc(&g.sflag, nf * nm));
+            PA_CK(pool_malloc(&g.lay_lo, sizeof(unsigned long long) * nf * 3 * g.gmax));
+            PA_CK(pool_malloc(&g.lay_hi, sizeof(unsigned long long) * nf * 3 * g.gmax));
             // every cell yields at most one tile plus one extra per 256 molecules
             tg.tile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.ncell + nm / 256 + 1), 0x7fffffffu);
-            PA_CK(cudaMalloc(&tg.tiles, sizeof(PaTile) * tg.tile_cap));
+            PA_CK(pool_malloc(&tg.tiles, sizeof(PaTile) * tg.tile_cap));
             // warp tiles: every row of cells yields at most one partial piece plus one per 64 molecules
             tg.wtile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.g[1] * g.g[2] + nm / 64 + 1), 0x7fffffffu);
-            PA_CK(cudaMalloc(&tg.wtiles, sizeof(PaTile) * tg.wtile_cap));
-            PA_CK(cudaMalloc(&tg.row_off, sizeof(int) * (nf * (size_t)g.g[1] * g.g[2] + 1)));
-            PA_CK(cudaMalloc(&tg.counters, sizeof(unsigned int) * 4));
+            PA_CK(pool_malloc(&tg.wtiles, sizeof(PaTile) * tg.wtile_cap));
+            PA_CK(pool_malloc(&tg.row_off, sizeof(int) * (nf * (size_t)g.g[1] * g.g[2] + 1)));
+            PA_CK(pool_malloc(&tg.counters, sizeof(unsigned int) * 4));
             PA_CK(cudaMemset(tg.counters, 0, sizeof(unsigned int) * 4));
         }
     }
@@ -751,21 +822,21 @@ void pa_session_destroy(pa_session *s)
     if (s->s_copy) cudaStreamSynchronize(s->s_copy);
     for (auto &ev : s->kernel_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
     for (auto &ev : s->f32_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-    for (auto &m : s->types) { cudaFree(m.d_mass); cudaFree(m.d_charge); }
+    for (auto &m : s->types) { pool_free(m.d_mass); pool_free(m.d_charge); }
     for (int b = 0; b < 2; ++b) {
-        for (float *p : s->d_raw[b]) cudaFree(p);
+        for (float *p : s->d_raw[b]) pool_free(p);
         if (s->h_pinned[b]) pinned_pool_give(s->h_pinned[b], s->h_pinned_bytes[b]);
-        cudaFree(s->d_types[b]);
+        pool_free(s->d_types[b]);
         if (s->ev_h2d[b]) cudaEventDestroy(s->ev_h2d[b]);
         if (s->ev_done[b]) cudaEventDestroy(s->ev_done[b]);
     }
-    for (auto &js : s->jobs) { cudaFree(js.d_thr_a); cudaFree(js.d_thr_b); }
+    for (auto &js : s->jobs) { pool_free(js.d_thr_a); pool_free(js.d_thr_b); }
     for (auto &tg : s->grids) {
         if (!tg.enabled) continue;
-        cudaFree(tg.g.cell_start); cudaFree(tg.g.cell_fill); cudaFree(tg.g.cid); cudaFree(tg.g.sx); cudaFree(tg.g.sy); cudaFree(tg.g.sz);
-        cudaFree(tg.g.sorig); cudaFree(tg.g.sflag); cudaFree(tg.g.lay_lo); cudaFree(tg.g.lay_hi); cudaFree(tg.tiles); cudaFree(tg.wtiles); cudaFree(tg.row_off); cudaFree(tg.counters);
+        pool_free(tg.g.cell_start); pool_free(tg.g.cell_fill); pool_free(tg.g.cid); pool_free(tg.g.sx); pool_free(tg.g.sy); pool_free(tg.g.sz);
+        pool_free(tg.g.sorig); pool_free(tg.g.sflag); pool_free(tg.g.lay_lo); pool_free(tg.g.lay_hi); pool_free(tg.tiles); pool_free(tg.wtiles); pool_free(tg.row_off); pool_free(tg.counters);
     }
-    cudaFree(s->d_pts); cudaFree(s->d_acc); cudaFree(s->d_exc); cudaFree(s->d_exc_count); cudaFree(s->d_kstats);
+    pool_free(s->d_pts); pool_free(s->d_acc); pool_free(s->d_exc); pool_free(s->d_exc_count); pool_free(s->d_kstats);
     if (s->s_compute) cudaStreamDestroy(s->s_compute);
     if (s->s_copy) cudaStreamDestroy(s->s_copy);
     delete s;

@@ -1,20 +1,27 @@
 #!/bin/bash
-# A/B on the GPU box: bench with the shipped build, then rebuild pa_cells.o with EXTRA flags and bench again.
-# usage: tools/gpu_ab.sh TAG "EXTRA flags"
-TAG=$1; EXTRA=$2
+# A/B on the GPU box: bench with the shipped build, then for every further argument rebuild pa_cells.o with those EXTRA
+# flags and bench again.  usage: tools/gpu_ab.sh TAG "EXTRA flags 1" ["EXTRA flags 2" ...]
+TAG=$1; shift
 mkdir -p gpurun_out
-PA_DEBUG_TIMING=1 timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_A.json 2> gpurun_out/${TAG}_A.err; echo "A rc=$?"
-tail -30 gpurun_out/${TAG}_A.err
 cp prealpha_b200/libprealpha_b200.so /tmp/lib_A.so
-( cd prealpha_b200/csrc && touch pa_cells.cu && make -s EXTRA="$EXTRA" 2>&1 | grep -i error )
-timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_B.json 2> gpurun_out/${TAG}_B.err; echo "B rc=$?"
+run() { timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_$1.json 2> gpurun_out/${TAG}_$1.err; echo "$1 rc=$?"; }
+run A
+n=0
+for EXTRA in "$@"; do
+  n=$((n+1))
+  ( cd prealpha_b200/csrc && touch pa_cells.cu && make -s EXTRA="$EXTRA" 2>&1 | grep -v "^$" | grep -v "warning\|plus1_wrap\|\^\|Remark" | head -5 )
+  ls -la prealpha_b200/libprealpha_b200.so | cut -c20-80
+  run V$n
+done
 cp /tmp/lib_A.so prealpha_b200/libprealpha_b200.so
-python - <<PY
-import json
-for n in ("A", "B"):
+python - "$@" <<PY
+import json, sys
+names = ["A"] + ["V%d" % (i + 1) for i in range(len(sys.argv) - 1)]
+flags = ["(shipped)"] + sys.argv[1:]
+for n, f in zip(names, flags):
     try:
         d = json.load(open("gpurun_out/${TAG}_%s.json" % n)); r = d["roofline"]
-        print(n, "ms/step %.1f value %.3e e2e %.3e (%.1f ms) frac %.3f useful %.3f atomics/step %.3e dom_ms %.1f" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["ms_per_step"], r["frac"], r["useful_frac"], r["atomics_per_step_per_gpu"], r["ms_per_launch"]))
+        print(n, f, "ms/step %.1f value %.3e e2e %.3e (%.1f ms) frac %.3f useful %.3f atomics/step %.3e dom_ms %.1f" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["ms_per_step"], r["frac"], r["useful_frac"], r["atomics_per_step_per_gpu"], r["ms_per_launch"]))
     except Exception as e:
-        print(n, "unreadable", e)
+        print(n, f, "unreadable", e)
 PY
