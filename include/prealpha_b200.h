@@ -259,9 +259,9 @@ int pa_format_real4(float value, char *buf);
  * A subjob is one line of the distance input after wildcard expansion
  * (prepare_subjob, Distances:500-609): the reference atoms indices_1 and the observed
  * atoms indices_2 as (molecule type, atom index) pairs, both 1-based.
- * Sums of exp / r^-3 / r^-6 terms are fp64 reductions: the GPU adds them in a fixed tree
- * order, the reference in loop order, so results agree to ~1e-12 relative, not bitwise
- * (the reference prints them with 3-4 significant digits). */
+ * The GPU evaluates the minimum-image distances and returns those below the cutoff in the
+ * reference's loop order; the sums of exp / r^-3 / r^-6 terms are then formed on the host as
+ * the same sequential chain of REAL(8) additions, so every result is bit-identical. */
 typedef struct pa_dist_subjob {
     int32_t n_ref, n_obs;
     const int32_t *ref;           /* [n_ref][2] = (molecule type, atom index)   indices_1       */

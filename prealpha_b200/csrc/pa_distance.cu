@@ -5,10 +5,10 @@
 //   step -> subjob -> reference atom index -> reference molecule -> observed atom index -> observed molecule
 // around give_smallest_atom_distance_squared (Molecular:1380-1427: both atoms are always wrapped,
 // then the 27-image loop).  Here one warp owns one reference atom instance (atom index x molecule)
-// and its lanes stride over the observed atom instances; per instance the closest squared distance
-// (float32, exact) and the fp64 partial sums are written out, and the host finishes in the
-// reference's loop order (sum over reference atoms, averages, stdev pass from the same per-atom
-// values, FFC powers -- Distances:1188-1235).
+// and its lanes take 32 consecutive observed atom instances of the reference's loop order at a time;
+// the squared distances below the cutoff come back in loop order and the host replays the reference's
+// sequential accumulation on them (sums over pairs, over reference atoms, averages, stdev pass, FFC
+// powers -- Distances:1188-1235), which makes every REAL(8) result bit-identical to the reference's.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -33,11 +33,7 @@ namespace {
 
 struct PdType { const float *xyz; int natoms, nmol; };          // one frame: [mol][atom][3]
 struct PdEntry { int type, atom; };                               // 0-based
-struct PdOut {                                                    // per reference atom instance
-    float closest_d2; int valid;
-    double sum_exp_d, sum_exp, sum_ffc, sum_ffcexp;
-    long long nffc;
-};
+struct PdOut;                                                     // (unused: the sums are formed on the host, in the reference's order)
 struct PdArgs {
     const PdType *types;
     const PdEntry *ref, *obs;
@@ -82,82 +78,67 @@ __device__ __forceinline__ float pd_distance_squared(const PdArgs &a, const doub
     return __double2float_rn(m < a.mds ? m : a.mds);
 }
 
-struct PdAcc {
-    float closest; int valid; double se_d, se, sf, sfe; long long nf;
-};
-
-__device__ __forceinline__ void pd_pair(const PdArgs &a, float d2, PdAcc &c)
+// One warp per reference atom instance; its lanes take 32 consecutive observed instances of the reference's loop order
+// (observed atom index, then observed molecule) at a time.  The squared distances below the cutoff are the only thing the
+// sums of the reference depend on, so the kernel hands them back IN LOOP ORDER (ballot + popc compaction keeps the order
+// inside a group of 32) and the host replays the reference's sequential fp64 accumulation on them -- bit for bit, because
+// it is the same chain of additions with the same libm expf.  Pass 1 (WRITE = false) counts, pass 2 writes at the offsets
+// the host derived from the counts.
+template <bool WRITE>
+__global__ void __launch_bounds__(128) pa_distance_kernel(PdArgs a, int inst0, int ninst, int *count, const long long *offset, float *list)
 {
-    if (!(d2 < a.maxdist_sq)) return;
-    c.valid = 1;
-    if (d2 < c.closest) c.closest = d2;
-    double ef = 0.0;
-    float distance = 0.f;
-    if (a.calc_exp || (a.calc_ffc && a.intermolecular)) distance = __fsqrt_rn(d2);
-    if (a.calc_exp) {
-        // exp of a REAL(4): the reference calls expf; correctly rounded here via fp64 exp
-        ef = (double)__double2float_rn(exp((double)(-__fmul_rn(a.exponent, distance))));
-        c.se_d = __dadd_rn(c.se_d, __dmul_rn(ef, (double)distance));
-        c.se = __dadd_rn(c.se, ef);
-    }
-    if (a.calc_ffc) {
-        float ffc;
-        if (a.intermolecular) ffc = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(distance, distance), distance));   // 1/r^3
-        else ffc = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(d2, d2), d2));                                      // 1/(r^2)^3
-        c.sf = __dadd_rn(c.sf, (double)ffc);
-        c.nf += 1;
-        if (a.calc_exp) c.sfe = __dadd_rn(c.sfe, __dmul_rn(ef, (double)ffc));
-    }
-}
-
-__global__ void __launch_bounds__(128) pa_distance_kernel(PdArgs a)
-{
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= a.n_inst) return;
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= ninst) return;
+    const int inst = inst0 + w;
+    const unsigned int lane_lt = (1u << lane) - 1u;
     // reference instance -> (entry, molecule)
     int e1 = 0;
-    while (e1 + 1 < a.n_ref && warp >= a.ref_first[e1 + 1]) ++e1;
-    const int m1 = warp - a.ref_first[e1];
+    while (e1 + 1 < a.n_ref && inst >= a.ref_first[e1 + 1]) ++e1;
+    const int m1 = inst - a.ref_first[e1];
     const PdEntry r = a.ref[e1];
     double p1[3];
     pd_load_wrapped(a, r.type, m1, r.atom, p1);
-    PdAcc c; c.closest = a.maxdist_sq; c.valid = 0; c.se_d = c.se = c.sf = c.sfe = 0.0; c.nf = 0;
+    int cnt = 0;
+    float *out = WRITE ? list + offset[w] : nullptr;
     if (a.intermolecular) {
         for (int e2 = 0; e2 < a.n_obs; ++e2) {
             const PdEntry o = a.obs[e2];
             const int nmol = a.types[o.type].nmol;
-            for (int m2 = lane; m2 < nmol; m2 += 32) {
-                if (m2 == m1 && o.type == r.type) continue;                  // Distances:1014
-                double p2[3];
-                pd_load_wrapped(a, o.type, m2, o.atom, p2);
-                pd_pair(a, pd_distance_squared(a, p1, p2), c);
+            for (int base = 0; base < nmol; base += 32) {
+                const int m2 = base + lane;
+                bool valid = false;
+                float d2 = 0.f;
+                if (m2 < nmol && !(m2 == m1 && o.type == r.type)) {          // Distances:1014
+                    double p2[3];
+                    pd_load_wrapped(a, o.type, m2, o.atom, p2);
+                    d2 = pd_distance_squared(a, p1, p2);
+                    valid = d2 < a.maxdist_sq;
+                }
+                const unsigned int m = __ballot_sync(0xffffffffu, valid);
+                if (WRITE && valid) out[cnt + __popc(m & lane_lt)] = d2;
+                cnt += __popc(m);
             }
         }
     } else {
-        for (int e2 = lane; e2 < a.n_obs; e2 += 32) {
-            const PdEntry o = a.obs[e2];
-            if (o.type != r.type || o.atom == r.atom) continue;              // Distances:891-893
-            double p2[3];
-            pd_load_wrapped(a, o.type, m1, o.atom, p2);
-            pd_pair(a, pd_distance_squared(a, p1, p2), c);
+        for (int base = 0; base < a.n_obs; base += 32) {
+            const int e2 = base + lane;
+            bool valid = false;
+            float d2 = 0.f;
+            if (e2 < a.n_obs) {
+                const PdEntry o = a.obs[e2];
+                if (o.type == r.type && o.atom != r.atom) {                   // Distances:891-893
+                    double p2[3];
+                    pd_load_wrapped(a, o.type, m1, o.atom, p2);
+                    d2 = pd_distance_squared(a, p1, p2);
+                    valid = d2 < a.maxdist_sq;
+                }
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, valid);
+            if (WRITE && valid) out[cnt + __popc(m & lane_lt)] = d2;
+            cnt += __popc(m);
         }
     }
-    // fixed-order warp reduction (deterministic)
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-        const float oc = __shfl_down_sync(0xffffffffu, c.closest, off);
-        const int ov = __shfl_down_sync(0xffffffffu, c.valid, off);
-        c.closest = fminf(c.closest, oc); c.valid |= ov;
-        c.se_d = __dadd_rn(c.se_d, __shfl_down_sync(0xffffffffu, c.se_d, off));
-        c.se = __dadd_rn(c.se, __shfl_down_sync(0xffffffffu, c.se, off));
-        c.sf = __dadd_rn(c.sf, __shfl_down_sync(0xffffffffu, c.sf, off));
-        c.sfe = __dadd_rn(c.sfe, __shfl_down_sync(0xffffffffu, c.sfe, off));
-        c.nf += __shfl_down_sync(0xffffffffu, c.nf, off);
-    }
-    if (lane == 0) {
-        PdOut o; o.closest_d2 = c.closest; o.valid = c.valid; o.sum_exp_d = c.se_d; o.sum_exp = c.se; o.sum_ffc = c.sf; o.sum_ffcexp = c.sfe; o.nffc = c.nf;
-        a.out[warp] = o;
-    }
+    if (!WRITE && lane == 0) count[w] = cnt;
 }
 
 }  // namespace
@@ -186,10 +167,16 @@ extern "C" int pa_distance_subjobs(const pa_traj *traj, const pa_dist_job *job, 
     std::vector<PdEntry *> d_ref(job->nsubjobs, nullptr), d_obs(job->nsubjobs, nullptr);
     std::vector<int *> d_first(job->nsubjobs, nullptr);
     std::vector<std::vector<int>> first(job->nsubjobs);
-    std::vector<PdOut *> d_out(job->nsubjobs, nullptr);
     std::vector<int> ninst(job->nsubjobs, 0);
-    // per (step, subjob) per-instance records, kept for the stdev pass
-    std::vector<std::vector<std::vector<PdOut>>> recs;
+    int *d_count = nullptr;
+    long long *d_offset = nullptr;
+    float *d_list = nullptr;
+    size_t list_cap = 0;
+    int max_inst = 0;
+    // per (step, subjob): for every reference atom instance, in loop order, the squared distances below the cutoff in
+    // loop order (lists[...] concatenated, counts[...] per instance)
+    struct StepRec { std::vector<int> counts; std::vector<float> d2; };
+    std::vector<std::vector<StepRec>> recs;
     std::vector<PdType> h_types(nt);
     {
         for (int t = 0; t < nt; ++t) {
@@ -209,14 +196,17 @@ extern "C" int pa_distance_subjobs(const pa_traj *traj, const pa_dist_job *job, 
             }
             for (int e = 0; e < sj.n_obs; ++e) { ho[e].type = sj.obs[2 * e] - 1; ho[e].atom = sj.obs[2 * e + 1] - 1; }
             ninst[k] = first[k][sj.n_ref];
+            max_inst = std::max(max_inst, ninst[k]);
             PD_CK(cudaMalloc(&d_ref[k], sizeof(PdEntry) * sj.n_ref));
             PD_CK(cudaMalloc(&d_obs[k], sizeof(PdEntry) * sj.n_obs));
             PD_CK(cudaMalloc(&d_first[k], sizeof(int) * (sj.n_ref + 1)));
-            PD_CK(cudaMalloc(&d_out[k], sizeof(PdOut) * ninst[k]));
             PD_CK(cudaMemcpy(d_ref[k], hr.data(), sizeof(PdEntry) * sj.n_ref, cudaMemcpyHostToDevice));
             PD_CK(cudaMemcpy(d_obs[k], ho.data(), sizeof(PdEntry) * sj.n_obs, cudaMemcpyHostToDevice));
             PD_CK(cudaMemcpy(d_first[k], first[k].data(), sizeof(int) * (sj.n_ref + 1), cudaMemcpyHostToDevice));
         }
+        PD_CK(cudaMalloc(&d_count, sizeof(int) * std::max(max_inst, 1)));
+        PD_CK(cudaMalloc(&d_offset, sizeof(long long) * std::max(max_inst, 1)));
+        std::vector<long long> h_off(std::max(max_inst, 1));
         for (int step = 0; step < nsteps; step += job->sampling_interval) {
             for (int t = 0; t < nt; ++t) {
                 const size_t n = (size_t)traj->types[t].nmol * traj->types[t].natoms * 3;
@@ -231,47 +221,107 @@ extern "C" int pa_distance_subjobs(const pa_traj *traj, const pa_dist_job *job, 
                 a.maxdist_sq = job->maxdist * job->maxdist; a.exponent = job->exponent;
                 for (int c = 0; c < 3; ++c) { a.lo[c] = traj->box_lo[c]; a.hi[c] = traj->box_hi[c]; a.L[c] = traj->box_hi[c] - traj->box_lo[c]; }
                 a.mds = traj->max_dist_sq;
-                a.out = d_out[k];
+                a.out = nullptr;
+                StepRec &rec = recs.back()[k];
+                rec.counts.resize(ninst[k]);
                 const int blocks = (ninst[k] + 3) / 4;
-                pa_distance_kernel<<<blocks, 128>>>(a);
+                pa_distance_kernel<false><<<blocks, 128>>>(a, 0, ninst[k], d_count, nullptr, nullptr);
                 PD_CK(cudaGetLastError());
-                recs.back()[k].resize(ninst[k]);
-                PD_CK(cudaMemcpy(recs.back()[k].data(), d_out[k], sizeof(PdOut) * ninst[k], cudaMemcpyDeviceToHost));
+                PD_CK(cudaMemcpy(rec.counts.data(), d_count, sizeof(int) * ninst[k], cudaMemcpyDeviceToHost));
+                long long total = 0;
+                for (int i = 0; i < ninst[k]; ++i) total += rec.counts[i];
+                rec.d2.resize((size_t)total);
+                // pass 2 in pieces of at most 64 Mi list entries (256 MB)
+                const long long piece = (long long)64 << 20;
+                int i0 = 0;
+                long long done = 0;
+                while (i0 < ninst[k]) {
+                    int i1 = i0;
+                    long long n = 0;
+                    while (i1 < ninst[k] && (i1 == i0 || n + rec.counts[i1] <= piece)) { h_off[i1 - i0] = n; n += rec.counts[i1]; ++i1; }
+                    if ((size_t)n > list_cap) {
+                        if (d_list) cudaFree(d_list);
+                        d_list = nullptr;
+                        list_cap = (size_t)std::max<long long>(n, 1 << 20);
+                        PD_CK(cudaMalloc(&d_list, sizeof(float) * list_cap));
+                    }
+                    if (n > 0) {
+                        PD_CK(cudaMemcpy(d_offset, h_off.data(), sizeof(long long) * (i1 - i0), cudaMemcpyHostToDevice));
+                        pa_distance_kernel<true><<<(i1 - i0 + 3) / 4, 128>>>(a, i0, i1 - i0, nullptr, d_offset, d_list);
+                        PD_CK(cudaGetLastError());
+                        PD_CK(cudaMemcpy(rec.d2.data() + done, d_list, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost));
+                    }
+                    done += n;
+                    i0 = i1;
+                }
             }
         }
     }
-    // host: the reference's accumulation over reference atoms, steps, and its post-processing
+    // host: the reference's loop nest (Distances:1000-1075 / 880-960) over the squared distances the kernel kept, in the
+    // same order, with the same REAL(4) / REAL(8) expressions -- every sum is the same chain of additions
     {
         int nav = (job->nsteps - 1 + job->sampling_interval) / job->sampling_interval;
         if (nav < 0) nav = 0;
         const double navf = (double)(float)nav;
+        const float maxdist_squared = job->maxdist * job->maxdist;
         memset(results, 0, sizeof(pa_dist_result) * job->nsubjobs);
         for (int pass = 0; pass < (job->calc_stdev ? 2 : 1); ++pass) {
+            const bool stdev_run = pass == 1;
             for (size_t s = 0; s < recs.size(); ++s)
                 for (int k = 0; k < job->nsubjobs; ++k) {
                     pa_dist_result &r = results[k];
-                    int localweight = 0; long long lw_ffc = 0;
-                    double local_closest = 0, local_exp = 0, w_exp = 0, local_exp_stdev = 0, local_ffc = 0, local_ffcexp = 0;
-                    for (const PdOut &o : recs[s][k]) {
-                        if (o.valid) {
-                            ++localweight;
-                            const double cd = (double)sqrtf(o.closest_d2);
-                            if (pass == 1) {
-                                local_closest = local_closest + (cd - r.closest_average) * (cd - r.closest_average);
-                                if (job->calc_exp) { const double de = o.sum_exp_d / o.sum_exp - r.exponential_average; local_exp_stdev = local_exp_stdev + de * de; }
-                            } else local_closest = local_closest + cd;
-                        } else r.missed_neighbours += 1;
-                        local_exp = local_exp + o.sum_exp_d; w_exp = w_exp + o.sum_exp;
-                        local_ffc = local_ffc + o.sum_ffc; local_ffcexp = local_ffcexp + o.sum_ffcexp; lw_ffc += o.nffc;
+                    const StepRec &rec = recs[s][k];
+                    int localweight = 0; long long localweight_ffc = 0;
+                    double local_closest = 0, local_exponential = 0, weight_exponential = 0, local_exponential_stdev = 0, local_ffc = 0, local_ffcexp = 0;
+                    size_t pos = 0;
+                    for (int i = 0; i < ninst[k]; ++i) {
+                        float closest = maxdist_squared;
+                        const int n = rec.counts[i];
+                        if (stdev_run && job->calc_exp) { local_exponential = 0; weight_exponential = 0; }
+                        for (int q = 0; q < n; ++q) {
+                            const float d2 = rec.d2[pos + q];
+                            if (d2 < closest) closest = d2;
+                            double ef = 0.0;
+                            if (job->calc_exp) {
+                                const float distance = sqrtf(d2);
+                                ef = (double)expf(-job->exponent * distance);
+                                local_exponential = local_exponential + ef * (double)distance;
+                                weight_exponential = weight_exponential + ef;
+                            }
+                            if (job->calc_ffc) {
+                                float ffc;
+                                if (job->intermolecular) { const float distance = sqrtf(d2); ffc = 1.0f / ((distance * distance) * distance); }
+                                else ffc = 1.0f / ((d2 * d2) * d2);
+                                local_ffc = local_ffc + (double)ffc;
+                                localweight_ffc += 1;
+                                if (job->calc_exp) local_ffcexp = local_ffcexp + ef * (double)ffc;
+                            }
+                        }
+                        pos += (size_t)n;
+                        if (n > 0) {
+                            localweight += 1;
+                            if (stdev_run) {
+                                const double dv = (double)sqrtf(closest) - r.closest_average;
+                                local_closest = local_closest + dv * dv;
+                                if (job->calc_exp) {
+                                    const double de = local_exponential / weight_exponential - r.exponential_average;
+                                    local_exponential_stdev = local_exponential_stdev + de * de;
+                                }
+                            } else local_closest = local_closest + (double)sqrtf(closest);
+                        } else r.missed_neighbours += 1;                   // also during the stdev pass (Distances:948,1067)
                     }
                     const double lw = (double)(float)localweight;
-                    if (pass == 1) {
+                    if (stdev_run) {
                         r.closest_stdev += local_closest / lw;
-                        if (job->calc_exp) r.exponential_stdev += local_exp_stdev / lw;
+                        if (job->calc_exp) r.exponential_stdev += local_exponential_stdev / lw;
                     } else {
                         r.closest_average += local_closest / lw;
-                        if (job->calc_exp) { r.exponential_average += local_exp; r.exponential_weight += w_exp; }
-                        if (job->calc_ffc) { r.ffc_average += local_ffc; if (job->calc_exp) r.ffcexp_average += local_ffcexp; r.ffc_weight += (double)(float)lw_ffc; }
+                        if (job->calc_exp) { r.exponential_average += local_exponential; r.exponential_weight += weight_exponential; }
+                        if (job->calc_ffc) {
+                            r.ffc_average += local_ffc;
+                            if (job->calc_exp) r.ffcexp_average += local_ffcexp;
+                            r.ffc_weight += (double)(float)localweight_ffc;
+                        }
                     }
                 }
             for (int k = 0; k < job->nsubjobs; ++k) {
@@ -295,8 +345,8 @@ extern "C" int pa_distance_subjobs(const pa_traj *traj, const pa_dist_job *job, 
     }
 done:
     for (float *p : d_xyz) cudaFree(p);
-    cudaFree(d_types);
-    for (int k = 0; k < job->nsubjobs; ++k) { cudaFree(d_ref[k]); cudaFree(d_obs[k]); cudaFree(d_first[k]); cudaFree(d_out[k]); }
+    cudaFree(d_types); cudaFree(d_count); cudaFree(d_offset); cudaFree(d_list);
+    for (int k = 0; k < job->nsubjobs; ++k) { cudaFree(d_ref[k]); cudaFree(d_obs[k]); cudaFree(d_first[k]); }
     return rc;
 }
 

@@ -60,8 +60,8 @@ def test_distance_oracle_matches_reference_binary_report(oracle):
 
 @pytest.mark.gpu
 def test_distance_cuda_matches_oracle(oracle):
-    """fp64 sums are reduced in a fixed tree order on the GPU and in loop order by the reference:
-    tolerance 1e-9 relative (the reference prints 3-4 significant digits); closest distances are exact."""
+    """Bit-exact: the kernel returns the squared distances below the cutoff in the reference's loop order and the host
+    replays the reference's sequential REAL(8) accumulation on them (same chain of additions, same libm expf)."""
     names, texts, stdout = _dist_fixture()
     fx, traj = _bmim_two_steps()
     els, nmol = _type_info(fx)
@@ -77,7 +77,7 @@ def test_distance_cuda_matches_oracle(oracle):
             assert g["ffc_weight"] == e["ffc_weight"]
             for key in ("closest_average", "closest_stdev", "exponential_average", "exponential_stdev", "exponential_weight",
                         "ffc_average", "ffcexp_average"):
-                assert g[key] == pytest.approx(e[key], rel=1e-9, abs=1e-300), key
+                assert g[key] == e[key] or (g[key] != g[key] and e[key] != e[key]), key      # identical doubles (NaN == NaN)
         assert inputs.distance_report(spec, got) == ref_lines
 
 
