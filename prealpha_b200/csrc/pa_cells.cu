@@ -194,14 +194,21 @@ __global__ void __launch_bounds__(128) pa_build_tiles_kernel(PaCellGrid g, int n
     unsigned int t = FILL ? (unsigned int)row_off[id] : 0u;
     int n = 0;
     if (CHUNKS) {
-        const int beg = cs[0], cnt = cs[gx] - beg;
-        for (int off = 0; off < cnt; off += PC_TILE, ++n) {
+        // a piece ends after PC_TILE molecules or at the end of the max_run-th cell it touches (sparse types: the tile's
+        // x extent plus one observed cell must stay below L/2), whichever comes first
+        const int row_end = cs[gx];
+        int pos = cs[0], cx = 0;
+        while (pos < row_end) {
+            while (cs[cx + 1] <= pos) ++cx;                       // cell that holds `pos`
+            const int end = min(min(pos + PC_TILE, cs[min(cx + max_run, gx)]), row_end);
             if (FILL && t + n < cap) {
                 PaTile tl;
-                tl.frame = f; tl.begin = beg + off; tl.count = min(PC_TILE, cnt - off);
-                tl.cx0 = 0; tl.cx1 = gx - 1; tl.cy = row % g.g[1]; tl.cz = row / g.g[1]; tl.pad = 0;
+                tl.frame = f; tl.begin = pos; tl.count = end - pos;
+                tl.cx0 = cx; tl.cx1 = min(cx + max_run, gx) - 1; tl.cy = row % g.g[1]; tl.cz = row / g.g[1]; tl.pad = 0;
                 tiles[t + n] = tl;
             }
+            ++n;
+            pos = end;
         }
     } else {
         int cx = 0;

@@ -69,6 +69,7 @@ struct JobState {
 };
 
 constexpr unsigned int kExcCap = 4u << 20;
+constexpr int kCellsMinMolecules = 2000;
 
 }  // namespace
 
@@ -443,7 +444,8 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
             }
         }
     }
-    // cell-sorted path: both partners of a pass need >= 12500 molecules (grid of >= 5^3 cells of ~100)
+    // cell-sorted path: both partners of a pass need >= kCellsMinMolecules molecules (the grid never has fewer than 5 x 5 rows
+    // of 20 cells; below ~2000 molecules a warp tile of 64 spans most of a row and nothing is pruned)
     s->grids.resize(traj->ntypes);
     // (with wrap_trajectory the positions are used as they are: the grid then needs every centre of mass inside the box,
     //  which pa_cell_count_kernel checks -- otherwise the sticky flag sends the call to the brute-force kernels)
@@ -454,7 +456,7 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
             if (js.job.mode == PA_MODE_CHARGE_ARM) continue;
             for (int o = 0; o < traj->ntypes; ++o) {
                 if (js.job.obs_type >= 1 && o != js.job.obs_type - 1) continue;
-                if (s->types[r].nmol >= 12500 && s->types[o].nmol >= 12500) { s->grids[r].enabled = true; s->grids[o].enabled = true; }
+                if (s->types[r].nmol >= kCellsMinMolecules && s->types[o].nmol >= kCellsMinMolecules) { s->grids[r].enabled = true; s->grids[o].enabled = true; }
             }
         }
         for (int t = 0; t < traj->ntypes; ++t) {
@@ -480,7 +482,7 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
             tg.tile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.ncell + nm / 256 + 1), 0x7fffffffu);
             PA_CK(pool_malloc(&tg.tiles, sizeof(PaTile) * tg.tile_cap));
             // warp tiles: every row of cells yields at most one partial piece plus one per 64 molecules
-            tg.wtile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.g[1] * g.g[2] + nm / 64 + 1), 0x7fffffffu);
+            tg.wtile_cap = (unsigned int)std::min<size_t>(nf * ((size_t)g.ncell + nm / 64 + 1), 0x7fffffffu);
             PA_CK(pool_malloc(&tg.wtiles, sizeof(PaTile) * tg.wtile_cap));
             PA_CK(pool_malloc(&tg.row_off, sizeof(int) * (nf * (size_t)g.g[1] * g.g[2] + 1)));
             PA_CK(pool_malloc(&tg.counters, sizeof(unsigned int) * 4));

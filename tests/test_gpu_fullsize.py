@@ -3,7 +3,7 @@
 The oracle evaluates 27 images per pair at ~6e6 pairs/s per host core, so a full frame (1e12 ordered pairs) is out of
 its reach.  What is pinned here, on exactly the frames the benchmark uses:
   * the oracle's own loop nest (OpenMP over blocks of reference molecules, `oracle_lib.histogram_frame`) against the
-    CUDA path for reference types cut out of the frame: 12 500 molecules (cell-sorted kernels) and 3 125 molecules
+    CUDA path for reference types cut out of the frame: 12 500 molecules (cell-sorted kernels) and 1 900 molecules
     (brute-force tile kernels) around ALL 1M atoms -- same box, same cutoff, same 1000 bins as the headline line;
   * the cell-sorted float32 / symmetric / merged launches of the whole frame against the brute-force kernels of the
     whole frame (the kernels pinned on the oracle by the rows above and by every smaller test), bit for bit, with the
@@ -42,10 +42,10 @@ def _rdf_job(traj, ref, obs):
                                                  maxdist_optimize=True, sampling_interval=1))
 
 
-@pytest.mark.parametrize("nref,expect_cells", [(12500, True), (3125, False)], ids=["cells_12500_rows", "brute_3125_rows"])
+@pytest.mark.parametrize("nref,expect_cells", [(12500, True), (1900, False)], ids=["cells_12500_rows", "brute_1900_rows"])
 def test_headline_frame_reference_rows_against_oracle(nref, expect_cells, oracle):
     """`nref` reference atoms of the 1M-atom benchmark frame around all 1M atoms: histogram, within and out-of-bounds
-    counts equal the oracle's (1.25e10 resp. 3.1e9 literal 27-image pair evaluations on the host cores)."""
+    counts equal the oracle's (1.25e10 resp. 1.9e9 literal 27-image pair evaluations on the host cores)."""
     n_half, L = bench.N_PER_TYPE, float(bench.L_BOX)
     frame = bench.synth_frame(0, 2 * n_half, L)
     traj = _cut_traj(frame, [nref, n_half - nref, n_half], L)

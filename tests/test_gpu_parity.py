@@ -169,6 +169,16 @@ CASES = [
 ]
 
 
+# sparse types just above the cell-path threshold (2000 molecules): warp tiles limited by their x extent, half-empty warps,
+# partner types below the threshold (brute force) in the same call
+CASES.append((4, 2, [(+1, 1, 2100, ["Na"]), (-1, 1, 2600, ["Cl"]), (0, 1, 800, ["Ar"])], 52.0, dict(decimals=4),
+              [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
+               dict(mode="pdf", ref_type=2, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
+               dict(mode="pdf", ref_type=2, obs_type=1, bin_a=90, bin_b=1, maxdist=13.0),
+               dict(mode="pdf", vec=(1, 0, 1), ref_type=1, obs_type=2, bin_a=30, bin_b=20, maxdist=11.0),
+               dict(mode="pdf", ref_type=3, obs_type=-1, bin_a=200, bin_b=1, maxdist_optimize=True)]))
+
+
 @pytest.mark.parametrize("case", CASES, ids=[f"case{c[0]}" for c in CASES])
 def test_random_systems_against_oracle(case, oracle):
     seed, nsteps, types, L, tkw, reqs = case
