@@ -16,6 +16,9 @@
 #include <chrono>
 #include <array>
 #include <thread>
+#include <fcntl.h>
+#include <unistd.h>
+#include <sys/stat.h>
 #include "pa_internal.h"
 
 namespace {
@@ -316,14 +319,136 @@ struct TrajStream {
     bool eof = false;
     int frames_done = 0;                // frames parsed so far = index of the next frame
     double t_read = 0, t_count = 0, t_parse = 0;
-    ~TrajStream() { if (f) fclose(f); }
+    // binary frame cache (see below): read side / write side
+    int cache_fd = -1;                  // >= 0: frames come from the cache, the text file is not opened
+    size_t cache_data_off = 0;
+    int cache_frames = 0;
+    int wcache_fd = -1;                 // >= 0: parsed frames are appended to a cache under construction
+    std::string wcache_tmp, wcache_final;
+    ~TrajStream()
+    {
+        if (f) fclose(f);
+        if (cache_fd >= 0) close(cache_fd);
+        if (wcache_fd >= 0) { close(wcache_fd); unlink(wcache_tmp.c_str()); }      // incomplete: discard
+    }
 };
 
-bool open_stream(Run &r, TrajStream &ts)
+// Binary frame cache (optional): the first read of a text trajectory can leave the parsed REAL(4)
+// coordinates next to it -- [frame][atom in file order][3] float32 after a header that pins the source file (size,
+// modification time), the molecule table, the box of an lmp header and the element names -- and every later run
+// (another analysis, the kernel ladder re-reading the file, several GPUs consuming frames faster than the text parser
+// delivers them) reads frames with pread at memory-copy speed instead of parsing 35 bytes of text per atom.
+// Enabled by the environment variable PREALPHA_B200_CACHE: "1" = next to the trajectory, otherwise a directory.
+struct CacheHeader {
+    char magic[8];                      // "PAB200C1"
+    uint32_t version, ntypes, lmp, elem_bytes;
+    uint64_t natoms_total, nsteps, src_size;
+    int64_t src_mtime_ns;
+    double box_lo[3], box_hi[3];
+};
+
+std::string cache_path_for(const Run &r)
+{
+    const char *e = getenv("PREALPHA_B200_CACHE");
+    if (!e || !*e || !strcmp(e, "0")) return "";
+    std::string dir = !strcmp(e, "1") ? r.path_traj : std::string(e);
+    if (!dir.empty() && dir.back() != '/') dir += '/';
+    std::string name = r.traj_file;
+    for (char &c : name) if (c == '/') c = '_';
+    return dir + name + ".pab200cache";
+}
+
+bool source_stat(const std::string &path, uint64_t &size, int64_t &mtime_ns)
+{
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return false;
+    size = (uint64_t)st.st_size;
+    mtime_ns = (int64_t)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+    return true;
+}
+
+// opens a valid cache for this run (same source file, same molecule table, enough frames); fills elements and box
+bool open_cache(Run &r, TrajStream &ts, const std::string &src)
+{
+    const std::string cp = cache_path_for(r);
+    if (cp.empty()) return false;
+    const int fd = open(cp.c_str(), O_RDONLY);
+    if (fd < 0) return false;
+    CacheHeader h;
+    uint64_t size = 0; int64_t mt = 0;
+    uint64_t natoms_total = 0;
+    for (auto &t : r.types) natoms_total += (uint64_t)t.natoms * t.nmol;
+    bool ok = pread(fd, &h, sizeof h, 0) == (ssize_t)sizeof h && !memcmp(h.magic, "PAB200C1", 8) && h.version == 1 &&
+              source_stat(src, size, mt) && h.src_size == size && h.src_mtime_ns == mt && h.ntypes == r.types.size() &&
+              h.natoms_total == natoms_total && h.lmp == (r.traj_type == "lmp" ? 1u : 0u) && h.nsteps >= (uint64_t)r.nsteps;
+    std::vector<uint32_t> table(2 * r.types.size());
+    std::vector<char> elems;
+    if (ok) ok = pread(fd, table.data(), table.size() * 4, sizeof h) == (ssize_t)(table.size() * 4);
+    if (ok) for (size_t t = 0; t < r.types.size(); ++t) if (table[2 * t] != (uint32_t)r.types[t].natoms || table[2 * t + 1] != (uint32_t)r.types[t].nmol) ok = false;
+    if (ok) { elems.resize(h.elem_bytes); ok = pread(fd, elems.data(), elems.size(), sizeof h + table.size() * 4) == (ssize_t)elems.size(); }
+    size_t need = 0;
+    for (auto &t : r.types) need += (size_t)t.natoms * 2;
+    if (ok && elems.size() != need) ok = false;
+    if (!ok) { close(fd); return false; }
+    size_t o = 0;
+    for (auto &t : r.types) for (int a = 0; a < t.natoms; ++a, o += 2) t.elements[a] = std::string(elems.data() + o, elems[o + 1] ? 2 : (elems[o] ? 1 : 0));
+    if (h.lmp) for (int k = 0; k < 3; ++k) { r.box_lo[k] = h.box_lo[k]; r.box_hi[k] = h.box_hi[k]; }
+    ts.cache_fd = fd;
+    ts.cache_data_off = (sizeof h + table.size() * 4 + elems.size() + 63) & ~(size_t)63;
+    ts.cache_frames = (int)h.nsteps;
+    return true;
+}
+
+void begin_cache_write(Run &r, TrajStream &ts)
+{
+    const std::string cp = cache_path_for(r);
+    if (cp.empty()) return;
+    ts.wcache_final = cp;
+    ts.wcache_tmp = cp + ".tmp." + std::to_string((long long)getpid());
+    ts.wcache_fd = open(ts.wcache_tmp.c_str(), O_CREAT | O_TRUNC | O_WRONLY, 0644);
+    if (ts.wcache_fd < 0) return;
+    size_t elem_bytes = 0;
+    for (auto &t : r.types) elem_bytes += (size_t)t.natoms * 2;
+    ts.cache_data_off = (sizeof(CacheHeader) + r.types.size() * 8 + elem_bytes + 63) & ~(size_t)63;
+}
+
+// the header is written last (elements and the lmp box are known after frame 1, the frame count at the end); the file
+// becomes visible under its final name only when it is complete
+void finish_cache_write(Run &r, TrajStream &ts, const std::string &src)
+{
+    if (ts.wcache_fd < 0) return;
+    CacheHeader h{};
+    memcpy(h.magic, "PAB200C1", 8);
+    h.version = 1; h.ntypes = (uint32_t)r.types.size(); h.lmp = r.traj_type == "lmp" ? 1u : 0u;
+    h.natoms_total = 0;
+    for (auto &t : r.types) h.natoms_total += (uint64_t)t.natoms * t.nmol;
+    h.nsteps = (uint64_t)ts.frames_done;
+    bool ok = source_stat(src, h.src_size, h.src_mtime_ns);
+    for (int k = 0; k < 3; ++k) { h.box_lo[k] = r.box_lo[k]; h.box_hi[k] = r.box_hi[k]; }
+    std::vector<uint32_t> table;
+    std::vector<char> elems;
+    for (auto &t : r.types) {
+        table.push_back((uint32_t)t.natoms); table.push_back((uint32_t)t.nmol);
+        for (int a = 0; a < t.natoms; ++a) { elems.push_back(t.elements[a].size() > 0 ? t.elements[a][0] : 0); elems.push_back(t.elements[a].size() > 1 ? t.elements[a][1] : 0); }
+    }
+    h.elem_bytes = (uint32_t)elems.size();
+    ok = ok && pwrite(ts.wcache_fd, &h, sizeof h, 0) == (ssize_t)sizeof h &&
+         pwrite(ts.wcache_fd, table.data(), table.size() * 4, sizeof h) == (ssize_t)(table.size() * 4) &&
+         pwrite(ts.wcache_fd, elems.data(), elems.size(), sizeof h + table.size() * 4) == (ssize_t)elems.size();
+    close(ts.wcache_fd);
+    ts.wcache_fd = -1;
+    if (ok && rename(ts.wcache_tmp.c_str(), ts.wcache_final.c_str()) == 0) {
+        if (r.verbose) printf(" wrote the binary frame cache '%s' (%d steps).\n", ts.wcache_final.c_str(), ts.frames_done);
+    } else unlink(ts.wcache_tmp.c_str());
+}
+
+bool open_stream(Run &r, TrajStream &ts, bool may_write_cache = true)
 {
     const std::string path = r.path_traj + r.traj_file;
+    if (open_cache(r, ts, path)) return true;
     ts.f = fopen(path.c_str(), "r");
     if (!ts.f) { r.error(9, "trajectory file '" + path + "' not found"); return false; }
+    if (may_write_cache) begin_cache_write(r, ts);
     return true;
 }
 
@@ -339,6 +464,34 @@ int read_frames(Run &r, TrajStream &ts, int want_frames, const std::vector<float
     const long long lines_per_frame = header + natoms_total;
     std::vector<long long> type_first(r.types.size() + 1, 0);           // first atom line of each type inside a frame
     for (size_t t = 0; t < r.types.size(); ++t) type_first[t + 1] = type_first[t] + (long long)r.types[t].natoms * r.types[t].nmol;
+    if (ts.cache_fd >= 0) {
+        // binary cache: a frame is natoms_total * 12 bytes in file order, i.e. one contiguous block per molecule type
+        const double t0 = now_s();
+        const int n = std::max(0, std::min(want_frames, ts.cache_frames - ts.frames_done));
+        const unsigned nth = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+        std::vector<std::thread> th;
+        bool bad = false;
+        for (unsigned w = 0; w < nth; ++w)
+            th.emplace_back([&, w] {
+                for (int s = (int)w; s < n; s += (int)nth)
+                    for (size_t t = 0; t < r.types.size(); ++t) {
+                        const size_t bytes = (size_t)(type_first[t + 1] - type_first[t]) * 12;
+                        const off_t off = (off_t)(ts.cache_data_off + ((size_t)(ts.frames_done + s) * (size_t)natoms_total + (size_t)type_first[t]) * 12);
+                        char *out = reinterpret_cast<char *>(dst[t] + (size_t)s * (size_t)(type_first[t + 1] - type_first[t]) * 3);
+                        size_t done = 0;
+                        while (done < bytes) {
+                            const ssize_t got = pread(ts.cache_fd, out + done, bytes - done, off + (off_t)done);
+                            if (got <= 0) { bad = true; break; }
+                            done += (size_t)got;
+                        }
+                    }
+            });
+        for (auto &x : th) x.join();
+        ts.t_read += now_s() - t0;
+        if (bad) return 0;
+        ts.frames_done += n;
+        return n;
+    }
     auto parse_atom_line = [&](const char *p, int step, long long a_total, bool first_frame) {
         size_t t = 0;
         while (t + 1 < r.types.size() && a_total >= type_first[t + 1]) ++t;
@@ -461,6 +614,15 @@ int read_frames(Run &r, TrajStream &ts, int want_frames, const std::vector<float
             for (auto &x : th) x.join();
         }
         ts.t_parse += now_s() - t0;
+        if (ts.wcache_fd >= 0) {                                            // append the parsed frames to the cache under construction
+            for (int s2 = 0; s2 < nframes && ts.wcache_fd >= 0; ++s2)
+                for (size_t t = 0; t < r.types.size(); ++t) {
+                    const size_t bytes = (size_t)(type_first[t + 1] - type_first[t]) * 12;
+                    const off_t off = (off_t)(ts.cache_data_off + ((size_t)(ts.frames_done + s2) * (size_t)natoms_total + (size_t)type_first[t]) * 12);
+                    const char *src = reinterpret_cast<const char *>(dst[t] + (size_t)(steps_read + s2) * (size_t)(type_first[t + 1] - type_first[t]) * 3);
+                    if (pwrite(ts.wcache_fd, src, bytes, off) != (ssize_t)bytes) { close(ts.wcache_fd); ts.wcache_fd = -1; unlink(ts.wcache_tmp.c_str()); break; }
+                }
+        }
         steps_read += nframes;
         ts.frames_done += nframes;
         // 5. keep the unparsed tail
@@ -475,7 +637,8 @@ int read_frames(Run &r, TrajStream &ts, int want_frames, const std::vector<float
 bool load_trajectory(Run &r)
 {
     TrajStream ts;
-    if (!open_stream(r, ts)) return false;
+    if (!open_stream(r, ts, /*may_write_cache=*/!r.stream)) return false;
+    if (ts.cache_fd >= 0 && r.verbose) printf(" reading the binary frame cache '%s' instead of the text file.\n", cache_path_for(r).c_str());
     const auto t_load0 = std::chrono::steady_clock::now();
     const bool lmp = (r.traj_type == "lmp");
     long long natoms_total = 0;
@@ -483,6 +646,7 @@ bool load_trajectory(Run &r)
     std::vector<float *> dst;
     for (auto &t : r.types) { natoms_total += (long long)t.natoms * t.nmol; t.xyz.assign((size_t)want * t.natoms * t.nmol * 3, 0.f); dst.push_back(t.xyz.data()); }
     const int steps_read = read_frames(r, ts, want, dst);
+    if (!r.stream && steps_read > 0) finish_cache_write(r, ts, r.path_traj + r.traj_file);
     if (getenv("PA_DEBUG_TIMING")) fprintf(stderr, "[prealpha_b200] ingestion: read %.3f s, frame cut %.3f s, parse %.3f s\n", ts.t_read, ts.t_count, ts.t_parse);
     if (steps_read < want) {                                      // Molecular:5003-5009, error 84
         r.error(84, "trajectory is shorter than specified; using " + std::to_string(steps_read) + " steps");
@@ -715,26 +879,38 @@ void make_traj(Run &r, std::vector<pa_type> &types, pa_traj &t)
 }
 
 // sequential_read T: the trajectory never sits in host memory as a whole.  Batches of frames are parsed from the file
-// (read_frames) into a staging array, handed to a session (pinned copy + cudaMemcpyAsync on its copy stream) and
-// evaluated while the host threads already parse the next batch; the sampled frames of a batch are picked by the
-// stride of pa_session_upload.  The kernel ladder of pa_distribution_histogram_multi (cells -> brute force ->
-// general kernel when a sticky device flag asks for it) is repeated here by re-reading the file.
+// (read_frames: text on all host threads, or pread from the binary cache) into a staging array, handed to a session
+// (pinned copy + cudaMemcpyAsync on its copy stream) and evaluated while the host already reads the next batch; the
+// sampled frames of a batch are picked by the stride of pa_session_upload.  With several devices (pa_exec.ndevices) the
+// batches are dealt round-robin to one session per GPU -- uploads and launches are asynchronous, so the one reading
+// thread keeps all of them busy as long as frames arrive fast enough -- and the int64 accumulators are combined on the
+// first device at the end (pa_sessions_reduce_to_first: ncclReduce over NVLink).  The kernel ladder of
+// pa_distribution_histogram_multi (cells -> brute force -> general kernel when a sticky device flag asks for it) is
+// repeated here by re-reading the file.
 int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, std::vector<int64_t *> &hp,
-                        std::vector<int64_t> &within, std::vector<int64_t> &oob, pa_stats *st)
+                        std::vector<int64_t> &within, std::vector<int64_t> &oob, pa_stats *st, pa_exec ex)
 {
     const int dt = jobs[0].sampling_interval;
     long long floats_per_frame = 0;
     for (auto &t : r.types) floats_per_frame += (long long)t.natoms * t.nmol * 3;
+    int ndev = ex.ndevices < 0 ? pa_device_count() - ex.device : std::max(1, ex.ndevices);
+    if (ndev < 1 || ex.device + ndev > pa_device_count()) { pa::set_error("pa_exec.device/ndevices: not that many usable devices"); return PA_ERR_BAD_ARG; }
+    ex.ndevices = 1;
     int B = (int)std::max<long long>(1, std::min<long long>(256, ((long long)256 << 20) / std::max<long long>(1, floats_per_frame * 4)));
-    B = (int)std::min<long long>(B, std::max<long long>(1, ((long long)r.nsteps + 7) / 8));       // at least ~8 batches: parsing overlaps the kernels
+    B = (int)std::min<long long>(B, std::max<long long>(1, ((long long)r.nsteps + 8 * ndev - 1) / (8 * ndev)));   // at least ~8 batches per device: reading overlaps the kernels
     if (const char *e = getenv("PA_STREAM_BATCH")) B = std::max(1, std::min(256, atoi(e)));      // test hook: frames per batch
-    pa_exec ex = r.exec;
+    const std::string src = r.path_traj + r.traj_file;
     for (int attempt = 0; attempt < 3; ++attempt) {
         TrajStream ts;
         if (!open_stream(r, ts)) return PA_ERR_IO;
-        pa_session *s = nullptr;
-        int rc = pa_session_create(&meta, jobs.data(), (int)jobs.size(), &ex, (B + dt - 1) / dt, &s);
-        if (rc) return rc;
+        std::vector<pa_session *> sess(ndev, nullptr);
+        int rc = 0;
+        for (int d = 0; d < ndev && rc == 0; ++d) {
+            pa_exec e = ex;
+            e.device = ex.device + d;
+            rc = pa_session_create(&meta, jobs.data(), (int)jobs.size(), &e, (B + dt - 1) / dt, &sess[d]);
+        }
+        if (rc) { for (pa_session *s : sess) if (s) pa_session_destroy(s); return rc; }
         std::vector<std::vector<float>> batch(r.types.size());
         std::vector<pa_type> vt(meta.types, meta.types + meta.ntypes);
         std::vector<float *> dst;
@@ -746,6 +922,7 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
         pa_traj view = meta;
         view.types = vt.data();
         int g0 = 0;                                               // global index of the first frame of the batch
+        long long nbatch = 0;
         bool short_file = false;
         while (g0 < r.nsteps && rc == 0) {
             const int want = std::min(B, r.nsteps - g0);
@@ -753,6 +930,8 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
             if (n > 0) {
                 const int first = (dt - g0 % dt) % dt;            // sampled frames are the global multiples of dt (Distribution:718)
                 if (first < n) {
+                    pa_session *s = sess[nbatch % ndev];
+                    ++nbatch;
                     view.nsteps = n;
                     rc = pa_session_upload(s, &view, first, (n - first + dt - 1) / dt, dt);
                     if (rc == 0) rc = pa_session_run(s);
@@ -761,9 +940,13 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
             }
             if (n < want) { short_file = true; break; }
         }
-        if (rc == 0) rc = pa_session_download(s, hp.data(), within.data(), oob.data(), 0);
-        if (st) pa_session_stats(s, st);
-        pa_session_destroy(s);
+        if (rc == 0) finish_cache_write(r, ts, src);              // (no-op unless a cache is being written)
+        // sticky flags of every device, then the sum on the first one
+        for (int d = 0; d < ndev && rc == 0; ++d) rc = pa_session_download(sess[d], nullptr, nullptr, nullptr, 0);
+        if (rc == 0) rc = pa_sessions_reduce_to_first(sess.data(), ndev);
+        if (rc == 0) rc = pa_session_download(sess[0], hp.data(), within.data(), oob.data(), 0);
+        if (st) pa_sessions_merge_stats(sess.data(), ndev, true, st);
+        for (pa_session *s : sess) pa_session_destroy(s);
         if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_NO_CELLS)) { ex.flags |= PA_EXEC_NO_CELLS; continue; }
         if (rc == PA_ERR_UNSUPPORTED && !(ex.flags & PA_EXEC_FORCE_GENERAL)) { ex.flags |= PA_EXEC_FORCE_GENERAL; continue; }
         if (rc == 0 && short_file) {                              // Molecular:5003-5009
@@ -822,7 +1005,7 @@ int perform_distribution(Run &r, const std::string &input_name)     // Distribut
         }
         if (evals < 2.0e11 || pa_device_count() - ex.device < 2) ex.ndevices = 1;
     }
-    if (r.stream) rc = histogram_streaming(r, traj, jobs, hp, within, oob, &st);
+    if (r.stream) rc = histogram_streaming(r, traj, jobs, hp, within, oob, &st, ex);
     else rc = pa_distribution_histogram_multi(&traj, jobs.data(), (int)jobs.size(), &ex, hp.data(), within.data(), oob.data(), &st);
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc) { r.error(rc, std::string("GPU histogram failed: ") + pa_last_error()); return rc; }

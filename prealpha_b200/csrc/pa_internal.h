@@ -160,6 +160,11 @@ int pa_general_ri(int nref);
 #define PA_TILE_THREADS 128
 #define PA_J_CHUNK 128
 
+// several sessions, one per device, working on shards of one job (pa_session.cu): combine the int64 accumulators on the
+// first session's device (ncclReduce over NVLink, or peer copies + add) / merge their statistics
+int pa_sessions_reduce_to_first(pa_session *const *sess, int n, const std::vector<void *> *comms_in = nullptr);
+void pa_sessions_merge_stats(pa_session *const *sess, int n, bool by_frames, pa_stats *out);
+
 // ---------------------------------------------------------------------------
 // Host-side float32-exact logic (pa_host.cpp)
 

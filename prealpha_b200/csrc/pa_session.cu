@@ -225,6 +225,8 @@ int upload_types_table(pa_session *s, int slot)
 int pa_multi_device_histogram(const pa_traj *traj, const pa_job *jobs, int32_t njobs, pa_exec ex,
                               int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, pa_stats *stats);
 void pa_multi_device_trim();
+int pa_sessions_reduce_to_first(pa_session *const *sess, int n, const std::vector<void *> *comms_in);
+void pa_sessions_merge_stats(pa_session *const *sess, int n, bool by_frames, pa_stats *out);
 
 extern "C" {
 
@@ -1008,6 +1010,69 @@ void pa_multi_device_trim()
     g_comm_cache.clear();
 }
 
+// Adds the accumulators of sessions 1..n-1 (one per device) to those of session 0: one ncclReduce(sum) of the int64 words
+// over NVLink, or -- when libnccl cannot be loaded -- peer copies and an add kernel on the first device.
+int pa_sessions_reduce_to_first(pa_session *const *sess, int n, const std::vector<void *> *comms_in)
+{
+    if (n < 2) return 0;
+    int rc = 0;
+    std::vector<int> devs(n);
+    for (int d = 0; d < n; ++d) devs[d] = sess[d]->device;
+    const size_t words = sess[0]->acc_words;
+    for (int d = 1; d < n; ++d) if (sess[d]->acc_words != words) { pa::set_error("sessions with different accumulators"); return PA_ERR_BAD_ARG; }
+    std::vector<void *> comms = comms_in ? *comms_in : nccl_comms_for(devs);
+    bool reduced = false;
+    if (!comms.empty()) {
+        const NcclApi &api = nccl_api();
+        int nrc = api.GroupStart();
+        for (int d = 0; d < n && nrc == 0; ++d) {
+            cudaSetDevice(devs[d]);
+            nrc = api.Reduce(sess[d]->d_acc, sess[d]->d_acc, words, /*ncclUint64*/ 5, /*ncclSum*/ 0, 0, comms[d], sess[d]->s_compute);
+        }
+        const int erc = api.GroupEnd();
+        if (nrc == 0) nrc = erc;
+        for (int d = 0; d < n; ++d) { cudaSetDevice(devs[d]); cudaStreamSynchronize(sess[d]->s_compute); }
+        if (nrc == 0) reduced = true;
+        else if (getenv("PA_DEBUG")) fprintf(stderr, "[prealpha_b200] ncclReduce failed (%s): falling back to peer copies\n", api.GetErrorString ? api.GetErrorString(nrc) : "?");
+    }
+    if (!reduced) {
+        // device d's accumulators are copied to a scratch buffer on the first device and added there; a few KB per job,
+        // so the serial order does not matter
+        for (int d = 1; d < n; ++d) { cudaSetDevice(devs[d]); cudaStreamSynchronize(sess[d]->s_compute); }
+        cudaSetDevice(devs[0]);
+        unsigned long long *scratch = nullptr;
+        if (cudaMalloc(&scratch, sizeof(unsigned long long) * words) != cudaSuccess) { pa::set_error("cudaMalloc (reduce scratch)"); rc = PA_ERR_CUDA; }
+        for (int d = 1; d < n && rc == 0; ++d) {
+            if (cudaMemcpyPeerAsync(scratch, devs[0], sess[d]->d_acc, devs[d], sizeof(unsigned long long) * words, sess[0]->s_compute) != cudaSuccess) {
+                pa::set_error("cudaMemcpyPeerAsync"); rc = PA_ERR_CUDA; break;
+            }
+            pa_acc_add_kernel<<<(unsigned)std::min<size_t>((words + 255) / 256, 1184), 256, 0, sess[0]->s_compute>>>(sess[0]->d_acc, scratch, words);
+        }
+        if (rc == 0 && cudaStreamSynchronize(sess[0]->s_compute) != cudaSuccess) { pa::set_error("peer reduce"); rc = PA_ERR_CUDA; }
+        cudaFree(scratch);
+    }
+    cudaSetDevice(devs[0]);
+    return rc;
+}
+
+void pa_sessions_merge_stats(pa_session *const *sess, int n, bool by_frames, pa_stats *out)
+{
+    pa_stats sum{};
+    for (int d = 0; d < n; ++d) {
+        pa_stats st{};
+        pa_session_stats(sess[d], &st);
+        sum.pairs_evaluated += st.pairs_evaluated;
+        sum.frames_done = by_frames ? sum.frames_done + st.frames_done : st.frames_done;
+        sum.kernel_launches += st.kernel_launches; sum.exception_pairs += st.exception_pairs;
+        sum.h2d_bytes += st.h2d_bytes; sum.d2h_bytes += st.d2h_bytes;
+        sum.kernel_ms = std::max(sum.kernel_ms, st.kernel_ms);
+        sum.cell_pair_evals += st.cell_pair_evals; sum.smem_atomics += st.smem_atomics; sum.unique_pairs_counted += st.unique_pairs_counted;
+        sum.dominant_launches += st.dominant_launches; sum.dominant_ms = std::max(sum.dominant_ms, st.dominant_ms);
+        sum.dominant_pair_evals += st.dominant_pair_evals; sum.dominant_atomics += st.dominant_atomics;
+    }
+    *out = sum;
+}
+
 int pa_multi_device_histogram(const pa_traj *traj, const pa_job *jobs, int32_t njobs, pa_exec ex,
                               int64_t *const *hists, int64_t *within_bin, int64_t *out_of_bounds, pa_stats *stats)
 {
@@ -1047,56 +1112,13 @@ int pa_multi_device_histogram(const pa_traj *traj, const pa_job *jobs, int32_t n
     comm_thread.join();
     int rc = 0;
     for (int d = 0; d < n && rc == 0; ++d) if (rcs[d]) { rc = rcs[d]; pa::set_error("device " + std::to_string(devs[d]) + ": " + errs[d]); }
-    // ---- combine the integer accumulators on the first device ------------------------------------------------
-    const size_t words = rc == 0 ? sess[0]->acc_words : 0;
-    bool reduced = false;
-    if (rc == 0 && !comms.empty()) {
-        const NcclApi &api = nccl_api();
-        int nrc = api.GroupStart();
-        for (int d = 0; d < n && nrc == 0; ++d) {
-            cudaSetDevice(devs[d]);
-            nrc = api.Reduce(sess[d]->d_acc, sess[d]->d_acc, words, /*ncclUint64*/ 5, /*ncclSum*/ 0, 0, comms[d], sess[d]->s_compute);
-        }
-        const int erc = api.GroupEnd();
-        if (nrc == 0) nrc = erc;
-        for (int d = 0; d < n; ++d) { cudaSetDevice(devs[d]); cudaStreamSynchronize(sess[d]->s_compute); }
-        if (nrc == 0) reduced = true;
-        else if (getenv("PA_DEBUG")) fprintf(stderr, "[prealpha_b200] ncclReduce failed (%s): falling back to peer copies\n", api.GetErrorString ? api.GetErrorString(nrc) : "?");
-    }
-    if (rc == 0 && !reduced) {
-        // peer copies + add kernel (libnccl not loadable): device d's accumulators are copied to a scratch buffer on the
-        // first device and added there; 16 KB per job, so the serial order does not matter
-        cudaSetDevice(devs[0]);
-        unsigned long long *scratch = nullptr;
-        if (cudaMalloc(&scratch, sizeof(unsigned long long) * words) != cudaSuccess) { pa::set_error("cudaMalloc (reduce scratch)"); rc = PA_ERR_CUDA; }
-        for (int d = 1; d < n && rc == 0; ++d) {
-            if (cudaMemcpyPeerAsync(scratch, devs[0], sess[d]->d_acc, devs[d], sizeof(unsigned long long) * words, sess[0]->s_compute) != cudaSuccess) {
-                pa::set_error("cudaMemcpyPeerAsync"); rc = PA_ERR_CUDA; break;
-            }
-            pa_acc_add_kernel<<<(unsigned)std::min<size_t>((words + 255) / 256, 1184), 256, 0, sess[0]->s_compute>>>(sess[0]->d_acc, scratch, words);
-        }
-        if (rc == 0 && cudaStreamSynchronize(sess[0]->s_compute) != cudaSuccess) { pa::set_error("peer reduce"); rc = PA_ERR_CUDA; }
-        cudaFree(scratch);
-    }
+    if (rc == 0) rc = pa_sessions_reduce_to_first(sess.data(), n, &comms);
     if (rc == 0) rc = pa_session_download(sess[0], hists, within_bin, out_of_bounds, 0);
     if (rc == 0 && stats) {
-        pa_stats sum{};
-        for (int d = 0; d < n; ++d) {
-            pa_stats st{};
-            pa_session_stats(sess[d], &st);
-            sum.pairs_evaluated += st.pairs_evaluated;
-            sum.frames_done = by_frames ? sum.frames_done + st.frames_done : st.frames_done;
-            sum.kernel_launches += st.kernel_launches; sum.exception_pairs += st.exception_pairs;
-            sum.h2d_bytes += st.h2d_bytes; sum.d2h_bytes += st.d2h_bytes;
-            sum.kernel_ms = std::max(sum.kernel_ms, st.kernel_ms);
-            sum.total_ms = std::max(sum.total_ms, (double)total_ms[d]);
-            sum.cell_pair_evals += st.cell_pair_evals; sum.smem_atomics += st.smem_atomics; sum.unique_pairs_counted += st.unique_pairs_counted;
-            sum.dominant_launches += st.dominant_launches; sum.dominant_ms = std::max(sum.dominant_ms, st.dominant_ms);
-            sum.dominant_pair_evals += st.dominant_pair_evals; sum.dominant_atomics += st.dominant_atomics;
-        }
-        sum.pairs_binned = 0;
-        for (int j = 0; j < njobs; ++j) if (within_bin) sum.pairs_binned += within_bin[j];
-        *stats = sum;
+        pa_sessions_merge_stats(sess.data(), n, by_frames, stats);
+        for (int d = 0; d < n; ++d) stats->total_ms = std::max(stats->total_ms, (double)total_ms[d]);
+        stats->pairs_binned = 0;
+        for (int j = 0; j < njobs; ++j) if (within_bin) stats->pairs_binned += within_bin[j];
     }
     for (int d = 0; d < n; ++d) if (sess[d]) pa_session_destroy(sess[d]);
     return rc;

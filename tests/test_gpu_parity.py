@@ -496,6 +496,24 @@ def test_cli_drop_in_end_to_end(name, stream, oracle, tmp_path):
     assert set(produced) == set(fx.files)
     for fn, content in produced.items():
         assert content == fx.files[fn], fn
+    if name in ("synth", "lmp", "charge_arm"):
+        # binary frame cache: the first run with PREALPHA_B200_CACHE writes it, the second reads frames from it instead of
+        # parsing text (also through the streaming path); with two GPUs or more the frames / batches are dealt out to all
+        # of them.  Same bytes in every output file.
+        env["PREALPHA_B200_CACHE"] = "1"
+        runs = [([cli, "general.inp"], False), ([cli, "general.inp"], True)]
+        if api.device_count() >= 2:
+            runs.append(([cli, "-g", "all", "general.inp"], True))
+        for cmd, cached in runs:
+            for fn in os.listdir(wd / "out"):
+                os.remove(wd / "out" / fn)
+            p = subprocess.run(cmd, cwd=wd, capture_output=True, timeout=600, env=env)
+            out = p.stdout.decode()
+            assert p.returncode == 0, out[-3000:] + p.stderr.decode()[-2000:]
+            assert ("reading the binary frame cache" in out) == cached and ("wrote the binary frame cache" in out) == (not cached)
+            assert oracle.parse_within(out) == fx.counts
+            again = {fn: (wd / "out" / fn).read_bytes() for fn in os.listdir(wd / "out")}
+            assert again == produced, cmd
 
 
 def test_exception_list_overflow_falls_back(oracle):

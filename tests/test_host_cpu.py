@@ -267,12 +267,13 @@ def test_fast_coordinate_parser_equals_strtof():
     assert len(cases) > 40000
 
 
-def _run_general_inp(workdir):
+def _run_general_inp(workdir, env=None):
     """pa_run_general_input in a subprocess (its report goes to the C stdout); returns (error count, stdout)."""
     import subprocess, sys
     code = ("import sys, ctypes as C; sys.path.insert(0, %r); from prealpha_b200 import capi, api; "
             "rc = capi.load().pa_run_general_input(b'general.inp', C.byref(api.make_exec())); print('RC', rc)" % ROOT)
-    p = subprocess.run([sys.executable, "-c", code], cwd=workdir, capture_output=True, timeout=300)
+    p = subprocess.run([sys.executable, "-c", code], cwd=workdir, capture_output=True, timeout=300,
+                       env=dict(os.environ, **(env or {})))
     out = p.stdout.decode()
     assert p.returncode == 0, out + p.stderr.decode()
     return int(out.rsplit("RC", 1)[1]), out
@@ -319,3 +320,41 @@ def test_general_inp_host_logic_without_gpu(tmp_path):
         rc, out = _run_general_inp(wd)
         assert "GPU histogram failed" in out and "no CPU fallback" in out and rc >= 1
         assert not any(f.startswith("reference_") for f in os.listdir(wd))
+
+
+def test_binary_frame_cache_is_written_validated_and_reused(tmp_path):
+    """PREALPHA_B200_CACHE: the first read of a text trajectory leaves the parsed float32 frames next to it, the second
+    run reads them back (no text parsing), a changed source file or molecule table invalidates the cache, and a short
+    file (error 84) caches only the frames it has."""
+    wd = tmp_path / "cache"; wd.mkdir()
+    _write_small_case(wd)
+    env = {"PREALPHA_B200_CACHE": "1"}
+    rc, out = _run_general_inp(wd, env)
+    assert rc == 0 and "wrote the binary frame cache" in out and "(12 steps)" in out
+    cache = wd / "traj.xyz.pab200cache"
+    assert cache.exists()
+    blob = cache.read_bytes()
+    assert blob[:8] == b"PAB200C1"
+    # payload: [frame][atom][3] float32 in file order, bit-identical to strtof of the text
+    data = np.frombuffer(blob[-12 * 24 * 12:], dtype=np.float32).reshape(12, 24, 3)
+    text = [ln.split() for ln in open(wd / "traj.xyz") if len(ln.split()) == 4]
+    exp = np.array([[np.float32(v) for v in t[1:]] for t in text], dtype=np.float32).reshape(12, 24, 3)
+    assert np.array_equal(data, exp)
+    rc, out = _run_general_inp(wd, env)
+    assert rc == 0 and "reading the binary frame cache" in out and "wrote the binary frame cache" not in out
+    assert "reading the trajectory...done (12 steps of 24 atoms" in out
+    # without the variable the cache is ignored
+    rc, out = _run_general_inp(wd)
+    assert "binary frame cache" not in out
+    # another molecule table: not this cache
+    (wd / "molecular.inp").write_text(" 12\n 1\n +1 2 12\nquit\n")
+    rc, out = _run_general_inp(wd, env)
+    assert "reading the binary frame cache" not in out and "wrote the binary frame cache" in out
+    # the source changes (size / mtime): re-parsed and re-written
+    _write_small_case(wd, nsteps_declared=12, nsteps_written=13)
+    rc, out = _run_general_inp(wd, env)
+    assert "reading the binary frame cache" not in out and "wrote the binary frame cache" in out
+    # a cache directory instead of "next to the trajectory"
+    cdir = tmp_path / "elsewhere"; cdir.mkdir()
+    rc, out = _run_general_inp(wd, {"PREALPHA_B200_CACHE": str(cdir)})
+    assert (cdir / "traj.xyz.pab200cache").exists()
