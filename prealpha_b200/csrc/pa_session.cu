@@ -70,6 +70,7 @@ struct JobState {
 
 constexpr unsigned int kExcCap = 4u << 20;
 constexpr int kCellsMinMolecules = 2000;
+constexpr double kCellsMinPairs = 2.0e7;
 
 }  // namespace
 
@@ -458,7 +459,9 @@ static int session_create_impl(pa_session *s, const pa_traj *traj, const pa_job 
             if (js.job.mode == PA_MODE_CHARGE_ARM) continue;
             for (int o = 0; o < traj->ntypes; ++o) {
                 if (js.job.obs_type >= 1 && o != js.job.obs_type - 1) continue;
-                if (s->types[r].nmol >= kCellsMinMolecules && s->types[o].nmol >= kCellsMinMolecules) { s->grids[r].enabled = true; s->grids[o].enabled = true; }
+                // ... and a pass below ~2e7 pairs per frame is finished by the brute-force tiles before the sort of a frame is
+                if (s->types[r].nmol >= kCellsMinMolecules && s->types[o].nmol >= kCellsMinMolecules &&
+                    (double)s->types[r].nmol * (double)s->types[o].nmol >= kCellsMinPairs) { s->grids[r].enabled = true; s->grids[o].enabled = true; }
             }
         }
         for (int t = 0; t < traj->ntypes; ++t) {

@@ -169,9 +169,9 @@ CASES = [
 ]
 
 
-# sparse types just above the cell-path threshold (2000 molecules): warp tiles limited by their x extent, half-empty warps,
+# sparse types just above the cell-path thresholds (2000 molecules, 2e7 pairs per frame): warp tiles limited by their x extent,
 # partner types below the threshold (brute force) in the same call
-CASES.append((4, 2, [(+1, 1, 2100, ["Na"]), (-1, 1, 2600, ["Cl"]), (0, 1, 800, ["Ar"])], 52.0, dict(decimals=4),
+CASES.append((4, 2, [(+1, 1, 4300, ["Na"]), (-1, 1, 5200, ["Cl"]), (0, 1, 800, ["Ar"])], 64.0, dict(decimals=4),
               [dict(mode="pdf", ref_type=1, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
                dict(mode="pdf", ref_type=2, obs_type=-1, bin_a=1000, bin_b=1, maxdist_optimize=True),
                dict(mode="pdf", ref_type=2, obs_type=1, bin_a=90, bin_b=1, maxdist=13.0),
