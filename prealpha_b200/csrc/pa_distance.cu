@@ -639,6 +639,114 @@ __global__ void __launch_bounds__(PC_THREADS) pa_neighbour_kernel(PnArgs a)
     }
 }
 
+// ---- cell list (the fast path): the b-instances are binned into a grid whose cells are at least as wide as the largest
+// cutoff, and every a-instance only meets the b-instances of the 27 cells around its own (periodic).  The test on a
+// candidate pair is the same literal REAL(4) predicate as in the brute-force kernel, so the set of pairs is identical --
+// a pair closer than the cutoff differs by less than one cell width per component in its minimum image, hence sits in
+// adjacent cells.  Needs >= 3 cells per component and every wrapped position inside the box (else: brute force).
+struct PnGrid { int g[3]; double lo[3], inv_w[3]; int ncell; };
+
+__global__ void pn_cell_count_kernel(PnArgs a, PnGrid G, int *cell_of_b, int *cell_count, unsigned int *err)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n_b) return;
+    const int at = a.ib_atom[j];
+    const double p[3] = { a.x[at], a.y[at], a.z[at] };
+    int c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double u = (p[k] - G.lo[k]) * G.inv_w[k];
+        if (!(u >= 0.0 && u <= (double)G.g[k])) { atomicOr(err, 1u); c[k] = 0; continue; }     // outside the box / NaN
+        c[k] = min(G.g[k] - 1, (int)u);
+    }
+    const int cell = (c[2] * G.g[1] + c[1]) * G.g[0] + c[0];
+    cell_of_b[j] = cell;
+    atomicAdd(&cell_count[cell], 1);
+}
+
+// exclusive scan of cell_count[0..n) into cell_start[0..n] (one block)
+__global__ void __launch_bounds__(1024) pn_scan_kernel(const int *cell_count, int *cell_start, int n)
+{
+    __shared__ int s_part[1024];
+    const int per = (n + 1023) / 1024;
+    const int b = min(n, (int)threadIdx.x * per), e = min(n, b + per);
+    int sum = 0;
+    for (int i = b; i < e; ++i) sum += cell_count[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+        int v = threadIdx.x >= off ? s_part[threadIdx.x - off] : 0;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    int run = threadIdx.x ? s_part[threadIdx.x - 1] : 0;
+    for (int i = b; i < e; ++i) { cell_start[i] = run; run += cell_count[i]; }
+    if (threadIdx.x == 1023) cell_start[n] = s_part[1023];
+}
+
+__global__ void pn_scatter_kernel(PnArgs a, const int *cell_of_b, const int *cell_start, int *cell_fill, int *sorted_b)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= a.n_b) return;
+    const int cell = cell_of_b[j];
+    sorted_b[cell_start[cell] + atomicAdd(&cell_fill[cell], 1)] = j;
+}
+
+__global__ void __launch_bounds__(128) pn_cells_kernel(PnArgs a, PnGrid G, const int *cell_start, const int *sorted_b, unsigned int *err,
+                                                       unsigned long long *tests)
+{
+    const int ia = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long ntest = 0;
+    if (ia < a.n_a) {
+        const int at = a.ia_atom[ia];
+        const double xi = a.x[at], yi = a.y[at], zi = a.z[at];
+        const int moli = a.ia_mol[ia];
+        const int rowi = (a.a_class ? a.a_class[ia] : 0) * a.n_class_b;
+        int c[3];
+        const double p[3] = { xi, yi, zi };
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double u = (p[k] - G.lo[k]) * G.inv_w[k];
+            if (!(u >= 0.0 && u <= (double)G.g[k])) { ok = false; c[k] = 0; continue; }
+            c[k] = min(G.g[k] - 1, (int)u);
+        }
+        if (!ok) atomicOr(err, 1u);
+        else {
+            for (int dz = -1; dz <= 1; ++dz) {
+                const int cz = (c[2] + dz + G.g[2]) % G.g[2];
+                for (int dy = -1; dy <= 1; ++dy) {
+                    const int cy = (c[1] + dy + G.g[1]) % G.g[1];
+                    for (int dx = -1; dx <= 1; ++dx) {
+                        const int cx = (c[0] + dx + G.g[0]) % G.g[0];
+                        const int cell = (cz * G.g[1] + cy) * G.g[0] + cx;
+                        for (int q = cell_start[cell]; q < cell_start[cell + 1]; ++q) {
+                            const int j = sorted_b[q];
+                            if ((a.same_list && j <= ia) || (a.skip_same_molecule && a.ib_mol[j] == moli)) continue;
+                            const int bt = a.ib_atom[j];
+                            const double px = a.x[bt], py = a.y[bt], pz = a.z[bt];
+                            const double s = __dadd_rn(__dadd_rn(pc_component(__dadd_rn(px, -a.L[0]), px, __dadd_rn(px, a.L[0]), xi),
+                                                                 pc_component(__dadd_rn(py, -a.L[1]), py, __dadd_rn(py, a.L[1]), yi)),
+                                                       pc_component(__dadd_rn(pz, -a.L[2]), pz, __dadd_rn(pz, a.L[2]), zi));
+                            ++ntest;
+                            // REAL(4) function result (Molecular:1400,1418) against the REAL(4) squared cutoff
+                            if (__double2float_rn(s < a.mds ? s : a.mds) < a.cutoff_sq[rowi + (a.b_class ? a.b_class[j] : 0)]) {
+                                const unsigned long long slot = atomicAdd(a.count, 1ull);
+                                if (slot < a.capacity) a.out[slot] = make_int2(ia, j);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    // distance tests carried out (statistics)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ntest += __shfl_xor_sync(0xffffffffu, ntest, o);
+    if ((threadIdx.x & 31) == 0 && ntest) atomicAdd(tests, ntest);
+}
+
 }  // namespace
 
 extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *rq, const pa_exec *exec,
@@ -688,6 +796,8 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
     int *d_idx = nullptr;
     int2 *d_out = nullptr;
     unsigned long long *d_count = nullptr, h_count = 0;
+    int *d_cellbuf = nullptr;
+    unsigned long long *d_aux = nullptr;
     {
         size_t max_raw = 1;
         for (int t = 0; t < nt; ++t) max_raw = std::max(max_raw, (size_t)(first[t + 1] - first[t]) * 3);
@@ -728,13 +838,54 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         a.same_list = rq->same_list ? 1 : 0; a.skip_same_molecule = rq->skip_same_molecule ? 1 : 0;
         a.L[0] = L.x; a.L[1] = L.y; a.L[2] = L.z; a.mds = traj->max_dist_sq;
         a.out = d_out; a.capacity = (unsigned long long)capacity; a.count = d_count;
-        const int bx = (rq->n_a + PC_THREADS - 1) / PC_THREADS;
-        int splits = std::max(1, (148 * 8 + bx - 1) / bx);
-        splits = std::min(std::min(splits, std::max(1, (rq->n_b + PC_CHUNK - 1) / PC_CHUNK)), 65535);
-        a.jsplit = (((rq->n_b + splits - 1) / splits + PC_CHUNK - 1) / PC_CHUNK) * PC_CHUNK;
-        splits = (rq->n_b + a.jsplit - 1) / a.jsplit;
-        pa_neighbour_kernel<<<dim3(bx, splits), PC_THREADS>>>(a);
-        PD_CK(cudaGetLastError());
+        // cell list when the box holds at least 3 x 3 x 3 cells of the largest cutoff (flag 0x800 of pa_exec: brute force)
+        bool used_cells = false;
+        unsigned long long h_tests = 0;
+        {
+            float cmax2 = 0.f;
+            for (size_t i = 0; i < ncut; ++i) cmax2 = std::max(cmax2, rq->cutoff_sq[i]);
+            const double cmax = std::sqrt((double)cmax2) * (1.0 + 1e-9) + 1e-9;     // margin >> rounding of the cell index
+            PnGrid G{};
+            const double Lk[3] = { L.x, L.y, L.z };
+            bool grid_ok = cmax2 > 0.f && std::isfinite(cmax) && rq->n_b >= 1024 && !(exec && (exec->flags & 0x800));
+            long long ncell = 1;
+            for (int k = 0; k < 3; ++k) {
+                G.g[k] = (int)std::min(128.0, std::floor(Lk[k] / cmax));
+                if (!(G.g[k] >= 3)) grid_ok = false;
+                G.lo[k] = traj->box_lo[k]; G.inv_w[k] = (double)G.g[k] / Lk[k];
+                ncell *= std::max(G.g[k], 1);
+            }
+            if (grid_ok) {
+                G.ncell = (int)ncell;
+                PD_CK(cudaMalloc(&d_cellbuf, sizeof(int) * ((size_t)2 * rq->n_b + 3 * (size_t)ncell + 2)));
+                int *cell_of_b = d_cellbuf, *sorted_b = d_cellbuf + rq->n_b, *cell_count = sorted_b + rq->n_b, *cell_start = cell_count + ncell,
+                    *cell_fill = cell_start + ncell + 1;
+                PD_CK(cudaMemset(cell_count, 0, sizeof(int) * (size_t)ncell));
+                PD_CK(cudaMemset(cell_fill, 0, sizeof(int) * (size_t)ncell));
+                PD_CK(cudaMalloc(&d_aux, sizeof(unsigned long long) * 2));
+                PD_CK(cudaMemset(d_aux, 0, sizeof(unsigned long long) * 2));
+                unsigned int *d_err = reinterpret_cast<unsigned int *>(d_aux);
+                unsigned long long *d_tests = d_aux + 1;
+                pn_cell_count_kernel<<<(rq->n_b + 255) / 256, 256>>>(a, G, cell_of_b, cell_count, d_err);
+                pn_scan_kernel<<<1, 1024>>>(cell_count, cell_start, (int)ncell);
+                pn_scatter_kernel<<<(rq->n_b + 255) / 256, 256>>>(a, cell_of_b, cell_start, cell_fill, sorted_b);
+                pn_cells_kernel<<<(rq->n_a + 127) / 128, 128>>>(a, G, cell_start, sorted_b, d_err, d_tests);
+                PD_CK(cudaGetLastError());
+                unsigned long long aux[2];
+                PD_CK(cudaMemcpy(aux, d_aux, sizeof aux, cudaMemcpyDeviceToHost));
+                if ((unsigned int)(aux[0] & 0xffffffffu) == 0u) { used_cells = true; h_tests = aux[1]; }
+                else PD_CK(cudaMemset(d_count, 0, sizeof(unsigned long long)));      // a position outside the box: start over, brute force
+            }
+        }
+        if (!used_cells) {
+            const int bx = (rq->n_a + PC_THREADS - 1) / PC_THREADS;
+            int splits = std::max(1, (148 * 8 + bx - 1) / bx);
+            splits = std::min(std::min(splits, std::max(1, (rq->n_b + PC_CHUNK - 1) / PC_CHUNK)), 65535);
+            a.jsplit = (((rq->n_b + splits - 1) / splits + PC_CHUNK - 1) / PC_CHUNK) * PC_CHUNK;
+            splits = (rq->n_b + a.jsplit - 1) / a.jsplit;
+            pa_neighbour_kernel<<<dim3(bx, splits), PC_THREADS>>>(a);
+            PD_CK(cudaGetLastError());
+        }
         PD_CK(cudaMemcpy(&h_count, d_count, sizeof h_count, cudaMemcpyDeviceToHost));
         *count = (int64_t)h_count;
         const size_t ncopy = (size_t)std::min<unsigned long long>(h_count, (unsigned long long)capacity);
@@ -747,10 +898,10 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         if (tests) {
             long long t = (long long)rq->n_a * rq->n_b;
             if (rq->same_list) t = (long long)rq->n_a * (rq->n_a - 1) / 2;
-            *tests = t;                                         // upper bound when skip_same_molecule removes pairs
+            *tests = used_cells ? (long long)h_tests : t;       // brute force: upper bound when skip_same_molecule removes pairs
         }
     }
 done:
-    cudaFree(d_pos); cudaFree(d_raw); cudaFree(d_cut); cudaFree(d_idx); cudaFree(d_out); cudaFree(d_count);
+    cudaFree(d_pos); cudaFree(d_raw); cudaFree(d_cut); cudaFree(d_idx); cudaFree(d_out); cudaFree(d_count); cudaFree(d_cellbuf); cudaFree(d_aux);
     return rc;
 }

@@ -1047,6 +1047,29 @@ std::vector<std::array<int, 2>> atoms_of_element(const Run &r, const std::string
     return v;
 }
 
+// Fortran Ew.d edit descriptor (0.ddddE+ee, right-justified in w): the digits are the correctly rounded decimal
+// expansion of the binary value (exact ties to even, like libgfortran), taken from printf's %.{d-1}e
+std::string fortran_E(double v, int w, int d)
+{
+    char buf[64];
+    std::string body;
+    if (std::isnan(v)) body = "NaN";
+    else if (std::isinf(v)) body = v < 0 ? "-Infinity" : "Infinity";
+    else if (v == 0.0) body = std::string(std::signbit(v) ? "-0." : "0.") + std::string((size_t)d, '0') + "E+00";
+    else {
+        snprintf(buf, sizeof buf, "%.*e", d - 1, std::fabs(v));          // D.DDDDe+XX
+        std::string digits;
+        int ex = 0;
+        const char *e = strchr(buf, 'e');
+        for (const char *p = buf; p < e; ++p) if (*p >= '0' && *p <= '9') digits += *p;
+        ex = atoi(e + 1) + 1;
+        snprintf(buf, sizeof buf, "%s0.%sE%+03d", v < 0 ? "-" : "", digits.c_str(), ex);
+        body = buf;
+    }
+    if ((int)body.size() < w) body = std::string((size_t)w - body.size(), ' ') + body;
+    return body;
+}
+
 std::string fortran_e93(double v)           // E9.3 = 0.dddE+ee
 {
     if (std::isnan(v)) return "      NaN";
@@ -1240,6 +1263,267 @@ int perform_distance(Run &r, const std::string &input_name)
     return 0;
 }
 
+// ---- `cluster` keyword (SURVEY 8f-4 consumer): Module_Cluster's statistics path ------------------------------------
+// The reference tests every pair of listed atoms with give_smallest_atom_distance_squared(...) < cutoff**2 in a serial
+// double loop per time step (Cluster:1092-1100 GLOBAL, :1411-1426 PAIRS) and merges clusters as it goes.  Pairs it skips
+// because both atoms already share a cluster would have been no-ops, so the outcome depends only on the qualifying
+// pairs and the order in which they are met: pa_neighbour_pairs (GPU cell list, same REAL(4) predicate) returns
+// exactly those pairs in loop order, and the merge bookkeeping below replays Cluster:1101-1180 on them.  Written:
+// `<prefix>cluster_statistics.dat` (Cluster:1296-1330 / :1640-1660), byte-identical to the reference's; the cluster
+// xyz dumps (print_step) and the intermittent autocorrelation function are outside this path and are not produced.
+struct ClusterAtom { int type, mol, atom; float weight; };
+struct ClusterPair { int a0, a1, b0, b1, type_a, atom_a, type_b, atom_b; };
+
+int perform_cluster(Run &r, const std::string &input_name)
+{
+    std::vector<std::string> lines;
+    if (!read_lines(r.path_in + input_name, lines)) { r.error(170, "cluster input file '" + r.path_in + input_name + "' not found"); return 170; }
+    std::vector<std::vector<std::string>> toks;
+    for (auto &l : lines) { auto t = tokens_of(l); if (!t.empty()) toks.push_back(t); }
+    if (toks.empty()) { r.error(177, "cannot read the operation mode of the cluster analysis"); return 177; }
+    const std::string m0 = toks[0][0];
+    bool pairs_mode;
+    if (m0 == "PAIRS" || m0 == "Pairs" || m0 == "pairs" || m0 == "PAIR" || m0 == "Pair" || m0 == "pair") pairs_mode = true;
+    else if (m0 == "GLOBAL" || m0 == "Global" || m0 == "global") pairs_mode = false;
+    else { r.error(177, "cannot read the operation mode of the cluster analysis"); return 177; }
+    printf(pairs_mode ? " PAIRS operation mode:\n Uses a set of pairs of atoms with their corresponding cutoffs.\n"
+                      : " GLOBAL operation mode:\n Uses a set of atoms and a global cutoff, applied to any combination of atoms.\n");
+    const int nt = (int)r.types.size();
+    auto valid_type = [&](int t) { return t >= 1 && t <= nt; };
+    auto valid_atom = [&](int t, int a) { return valid_type(t) && a >= 1 && a <= r.types[t - 1].natoms; };
+    int nsteps = 1, sampling = 1;
+    bool print_statistics = false;
+    std::vector<ClusterAtom> atoms;
+    std::vector<ClusterPair> pairs;
+    std::vector<float> cutoffs;
+    float current_weight = 0.0f;
+    auto add_instances = [&](int type, int atom) {             // one list entry per molecule of the type
+        const int first = (int)atoms.size();
+        for (int m = 1; m <= r.types[type - 1].nmol; ++m) atoms.push_back({ type, m, atom, current_weight });
+        return std::make_pair(first, (int)atoms.size() - 1);
+    };
+    for (size_t n = 1; n < toks.size(); ++n) {                 // read_body, Cluster:509-891 (keywords of the statistics path)
+        const auto &t = toks[n];
+        const std::string &k = t[0];
+        int i1, i2, i3, i4;
+        float f1, f2;
+        bool b1;
+        if (k == "quit") break;
+        if (k == "nsteps") { if (t.size() > 1 && parse_int(t[1], i1)) nsteps = i1; else r.error(170, "cannot read 'nsteps' (cluster input)"); }
+        else if (k == "sampling_interval") { if (t.size() > 1 && parse_int(t[1], i1)) sampling = i1; else r.error(170, "cannot read 'sampling_interval' (cluster input)"); }
+        else if (k == "print_statistics" || k == "statistics") { if (t.size() > 1 && parse_logical(t[1], b1)) print_statistics = b1; else r.error(170, "cannot read 'print_statistics'"); }
+        else if (k == "custom_weight" || k == "custom_weights" || k == "weight" || k == "weights" || k == "set_weight" || k == "set_weights") {
+            if (t.size() > 1 && parse_real4(t[1], f1)) current_weight = f1; else r.error(170, "cannot read 'custom_weight'");
+        } else if (k == "single_cutoff" || k == "cutoff") {
+            if (pairs_mode) { r.error(178, "keyword not available in this operation mode"); continue; }
+            if (!(t.size() > 1 && parse_real4(t[1], f1))) { r.error(170, "cannot read 'single_cutoff'"); continue; }
+            if (f1 > 0.0f) cutoffs.push_back(f1); else r.error(175, "invalid cutoff");
+        } else if (k == "scan_cutoff") {
+            if (pairs_mode) { r.error(178, "keyword not available in this operation mode"); continue; }
+            if (!(t.size() > 3 && parse_real4(t[1], f1) && parse_real4(t[2], f2) && parse_int(t[3], i1))) { r.error(170, "cannot read 'scan_cutoff'"); continue; }
+            if (i1 > 0 || f1 < 0.0f || f1 > f2) {              // [sic], Cluster:542
+                const float interval = (f2 - f1) / (float)(i1 - 1);
+                for (int m = 0; m < i1; ++m) cutoffs.push_back(f1 + (float)m * interval);
+            } else r.error(175, "invalid cutoff");
+        } else if (k == "add_molecule_type" || k == "add_molecule_type_index" || k == "add_molecule") {
+            if (pairs_mode) { r.error(178, "keyword not available in this operation mode"); continue; }
+            if (!(t.size() > 1 && parse_int(t[1], i1))) { r.error(170, "cannot read 'add_molecule_type'"); continue; }
+            if (valid_type(i1))
+                for (int m = 1; m <= r.types[i1 - 1].nmol; ++m)
+                    for (int a = 1; a <= r.types[i1 - 1].natoms; ++a) atoms.push_back({ i1, m, a, current_weight });
+        } else if (k == "add_atom_index" || k == "add_atom") {
+            if (pairs_mode) { r.error(178, "keyword not available in this operation mode"); continue; }
+            if (!(t.size() > 2 && parse_int(t[1], i1) && parse_int(t[2], i2))) { r.error(170, "cannot read 'add_atom_index'"); continue; }
+            if (valid_atom(i1, i2)) add_instances(i1, i2);
+        } else if (k == "pair" || k == "Pair" || k == "add_pair") {
+            if (!pairs_mode) { r.error(178, "keyword not available in this operation mode"); continue; }
+            if (!(t.size() > 5 && parse_int(t[1], i1) && parse_int(t[2], i2) && parse_int(t[3], i3) && parse_int(t[4], i4) && parse_real4(t[5], f1))) continue;
+            if (!(valid_atom(i1, i2) && valid_atom(i3, i4))) continue;
+            ClusterPair cp{ -1, -1, -1, -1, i1, i2, i3, i4 };
+            // an (atom index, molecule type) that an earlier pair already listed reuses that part of the atom list
+            // (Cluster:652-726: A against old A, then old B; B against old A, then old B; finally B against the new A)
+            for (const ClusterPair &q : pairs) {
+                if (q.type_a == i1 && q.atom_a == i2) { cp.a0 = q.a0; cp.a1 = q.a1; break; }
+                if (q.type_b == i1 && q.atom_b == i2) { cp.a0 = q.b0; cp.a1 = q.b1; break; }
+            }
+            for (const ClusterPair &q : pairs) {
+                if (q.type_a == i3 && q.atom_a == i4) { cp.b0 = q.a0; cp.b1 = q.a1; break; }
+                if (q.type_b == i3 && q.atom_b == i4) { cp.b0 = q.b0; cp.b1 = q.b1; break; }
+            }
+            if (cp.a0 < 0) { auto ab = add_instances(i1, i2); cp.a0 = ab.first; cp.a1 = ab.second; }
+            if (cp.b0 < 0 && i3 == i1 && i4 == i2) { cp.b0 = cp.a0; cp.b1 = cp.a1; }
+            if (cp.b0 < 0) { auto ab = add_instances(i3, i4); cp.b0 = ab.first; cp.b1 = ab.second; }
+            pairs.push_back(cp);
+            cutoffs.push_back(f1);
+        }
+        // print_step, print_spectators, autocorrelation, tmax, use_log: outputs outside this path (see above)
+    }
+    const int N_atoms = (int)atoms.size(), N_cutoffs = (int)cutoffs.size();
+    if (N_atoms == 0) { r.error(173, "no atoms specified for the cluster analysis"); return 173; }
+    if (N_cutoffs == 0) { r.error(174, "no cutoffs specified for the cluster analysis"); return 174; }
+    if (nsteps < 1) { r.error(57, "timestep out of range"); nsteps = 1; }
+    else if (nsteps > r.nsteps) { r.error(57, "timestep out of range"); nsteps = r.nsteps; }
+    if (sampling < 1) sampling = 1;
+    if (pairs_mode) printf("   Expecting %d pairs and %d atoms.\n", (int)pairs.size(), N_atoms);
+    else printf("   Expecting %d atoms and %d cutoffs.\n", N_atoms, N_cutoffs);
+    if (print_statistics) {
+        // custom_weights is never set by the reference's reader (Cluster:28,206,331): the molecular charge is always used
+        printf(" no custom weights have been specified, using molecular charge.\n (Note: even for more than one atom, they are all assigned the full charge)\n");
+        for (ClusterAtom &a : atoms) a.weight = (float)r.types[a.type - 1].charge;
+    }
+    if (!pairs_mode) std::sort(cutoffs.begin(), cutoffs.end());
+    const int navg = std::max((nsteps - 1 + sampling) / sampling, 0);
+    printf(" Using %d timesteps in intervals of %d for averaging.\n Starting cluster analysis.\n", navg, sampling);
+    printf(" (B200 drop-in: neighbour pairs on the GPU, cluster bookkeeping replayed in the reference's order; the xyz dumps\n"
+           "  of print_step and the intermittent autocorrelation function are not part of the accelerated path.)\n");
+    std::vector<pa_type> types; pa_traj traj;
+    make_traj(r, types, traj);
+    const int ncol = pairs_mode ? 1 : N_cutoffs;
+    std::vector<long long> occurrence((size_t)(N_atoms + 1) * ncol, 0), ccdf((size_t)ncol, 0);
+    std::vector<double> avg_weight((size_t)(N_atoms + 1) * ncol, 0.0);
+    std::vector<int32_t> inst((size_t)N_atoms * 3);
+    for (int i = 0; i < N_atoms; ++i) { inst[3 * i] = atoms[i].type; inst[3 * i + 1] = atoms[i].mol; inst[3 * i + 2] = atoms[i].atom; }
+    std::vector<int> cluster_number((size_t)N_atoms + 1);
+    std::vector<float> cl_weight((size_t)N_atoms + 1);
+    std::vector<int> cl_members((size_t)N_atoms + 1);
+    std::vector<pa_neigh_pair> found((size_t)1 << 16);
+    long long tests_total = 0, pairs_total = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int step = 1; step <= nsteps; step += sampling) {
+        int current = 0;
+        std::fill(cluster_number.begin(), cluster_number.end(), 0);
+        std::fill(cl_weight.begin(), cl_weight.end(), 0.0f);
+        std::fill(cl_members.begin(), cl_members.end(), 0);
+        auto merge = [&](int m, int n) {                      // Cluster:1101-1180 (1-based list positions)
+            if (cluster_number[m] != 0 && cluster_number[m] == cluster_number[n]) return;
+            if (cluster_number[m] == 0) {
+                if (cluster_number[n] == 0) {
+                    ++current;
+                    cluster_number[m] = cluster_number[n] = current;
+                    cl_weight[current] = atoms[m - 1].weight + atoms[n - 1].weight;
+                    cl_members[current] = 2;
+                } else {
+                    cluster_number[m] = cluster_number[n];
+                    cl_weight[cluster_number[n]] = cl_weight[cluster_number[n]] + atoms[m - 1].weight;
+                    cl_members[cluster_number[n]] += 1;
+                }
+            } else if (cluster_number[n] == 0) {
+                cluster_number[n] = cluster_number[m];
+                cl_weight[cluster_number[m]] = cl_weight[cluster_number[m]] + atoms[n - 1].weight;
+                cl_members[cluster_number[m]] += 1;
+            } else {
+                const int del = cluster_number[n], keep = cluster_number[m];
+                cl_members[keep] += cl_members[del];
+                cl_weight[keep] = cl_weight[keep] + cl_weight[del];
+                for (int i = 1; i <= N_atoms; ++i) if (cluster_number[i] == del) cluster_number[i] = keep;
+                if (current != del) {                          // the cluster with the highest number takes the free slot
+                    cl_weight[del] = cl_weight[current];
+                    cl_members[del] = cl_members[current];
+                    for (int i = 1; i <= N_atoms; ++i) if (cluster_number[i] == current) cluster_number[i] = del;
+                }
+                --current;
+            }
+        };
+        auto neighbour_pairs = [&](const int32_t *a, int na, const int32_t *b, int nb, bool same, float cutoff, int64_t &count) -> int {
+            const float csq = cutoff * cutoff;                 // squared_cutoff_list(i)=cutoff_list(i)**2, REAL(4)
+            pa_neigh_request rq{};
+            rq.timestep = step; rq.n_a = na; rq.n_b = nb; rq.a = a; rq.b = b;
+            rq.n_class_a = rq.n_class_b = 1; rq.cutoff_sq = &csq; rq.same_list = same ? 1 : 0; rq.skip_same_molecule = 0;
+            for (;;) {
+                int64_t tests = 0;
+                const int rc = pa_neighbour_pairs(&traj, &rq, &r.exec, found.data(), (int64_t)found.size(), &count, &tests);
+                if (rc) return rc;
+                if (count <= (int64_t)found.size()) { tests_total += tests; pairs_total += count; return 0; }
+                found.resize((size_t)count);
+            }
+        };
+        auto statistics = [&](int col) {                       // Cluster:1185-1205 / :1516-1543
+            long long counts = current;
+            for (int i = 1; i <= current; ++i) {
+                avg_weight[(size_t)cl_members[i] * ncol + col] += (double)cl_weight[i];
+                occurrence[(size_t)cl_members[i] * ncol + col] += 1;
+            }
+            for (int i = 1; i <= N_atoms; ++i)
+                if (cluster_number[i] == 0) {
+                    ++counts;
+                    occurrence[(size_t)1 * ncol + col] += 1;
+                    avg_weight[(size_t)1 * ncol + col] += (double)atoms[i - 1].weight;
+                }
+            ccdf[col] += counts;
+        };
+        int rc = 0;
+        int64_t count = 0;
+        if (pairs_mode) {
+            for (size_t p = 0; p < pairs.size() && rc == 0; ++p) {
+                const ClusterPair &cp = pairs[p];
+                rc = neighbour_pairs(inst.data() + 3 * (size_t)cp.a0, cp.a1 - cp.a0 + 1, inst.data() + 3 * (size_t)cp.b0, cp.b1 - cp.b0 + 1, false, cutoffs[p], count);
+                for (int64_t q = 0; q < count && rc == 0; ++q) {
+                    const int m = cp.a0 + found[q].ia + 1, n = cp.b0 + found[q].ib + 1;
+                    if (m == n) continue;                      // the same atom (Cluster:1427-1429)
+                    merge(m, n);
+                }
+            }
+            if (rc == 0 && print_statistics) statistics(0);
+        } else {
+            for (int c = 0; c < N_cutoffs && rc == 0; ++c) {   // ascending cutoffs build on the clusters of the previous one
+                rc = neighbour_pairs(inst.data(), N_atoms, inst.data(), N_atoms, true, cutoffs[c], count);
+                for (int64_t q = 0; q < count && rc == 0; ++q) merge(found[q].ia + 1, found[q].ib + 1);
+                if (rc == 0 && print_statistics) statistics(c);
+            }
+        }
+        if (rc) { r.error(rc, std::string("GPU neighbour search failed: ") + pa_last_error()); return rc; }
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    printf("   ### B200 execution (cluster analysis): %d steps, %lld distance tests, %lld neighbour pairs, %.3f seconds\n", navg, tests_total, pairs_total, sec);
+    if (print_statistics) {
+        const std::string fn = r.path_out + r.prefix + "cluster_statistics.dat";
+        if (r.verbose) printf(" Writing cluster statistics to '%s'\n", fn.c_str());
+        FILE *f = fopen(fn.c_str(), "w");
+        if (!f) { r.error(26, "cannot open '" + fn + "'"); return 26; }
+        fprintf(f, " This file contains cluster statistics based on the input file '%s'\n", input_name.c_str());
+        fprintf(f, " atom_fraction    = #(specified atoms in this cluster size) / total #(specified atoms)\n");
+        fprintf(f, " cluster_fraction = #(clusters of this size) / total number of clusters\n");
+        if (!pairs_mode) {
+            if (N_cutoffs == 1) fprintf(f, " The cutoff was %s\n", fortran_E((double)cutoffs[0], 9, 3).c_str());
+            else fprintf(f, "%9s", "cutoff");
+        }
+        fprintf(f, "%8s%15s%15s%17s\n", "members", "weight_average", "atom_fraction", "cluster_fraction");
+        for (int c = 0; c < ncol; ++c) {
+            float normalisation = 0.0f;
+            long long sum_occ = 0;
+            for (int i = 1; i <= N_atoms; ++i) {
+                normalisation = normalisation + (float)(occurrence[(size_t)i * ncol + c] * i);
+                sum_occ += occurrence[(size_t)i * ncol + c];
+            }
+            for (int i = 1; i <= N_atoms; ++i) {
+                const long long occ = occurrence[(size_t)i * ncol + c];
+                if (occ <= 0) continue;
+                if (!pairs_mode && N_cutoffs > 1) fprintf(f, "%s", fortran_E((double)cutoffs[c], 9, 3).c_str());
+                const double wavg = avg_weight[(size_t)i * ncol + c] / (double)(float)occ;
+                const float afrac = (float)(occ * i) / normalisation;
+                const float cfrac = (float)occ / (float)sum_occ;
+                fprintf(f, "%8d%s%s%s\n", i, fortran_E(wavg, 15, 6).c_str(), fortran_E((double)afrac, 15, 6).c_str(), fortran_E((double)cfrac, 17, 6).c_str());
+            }
+        }
+        fclose(f);
+        if (pairs_mode) {
+            const float ccf = (float)ccdf[0] / (float)navg;
+            if (ccf < 0.01f || ccf > 99.99f) printf(" The 'CCF' for this analysis was%s\n", fortran_E((double)ccf, 11, 4).c_str());
+            else printf(" The 'CCF' for this analysis was%6.2f\n", (double)ccf);
+            printf(" ( CCF = cluster count function = average number of separate clusters per box)\n");
+        } else {
+            printf(" The following values of the CCF were observed:\n%10s%10s\n", "cutoff", "CCF");
+            for (int c = 0; c < N_cutoffs; ++c) {
+                const float ccf = (float)ccdf[c] / (float)navg;
+                auto fmt = [](float v) { char b[32]; if (v < 0.01f || !(v < 99999.9f)) return fortran_E((double)v, 10, 4); snprintf(b, sizeof b, "%10.3f", (double)v); return std::string(b); };
+                printf("%s%s\n", fmt(cutoffs[c]).c_str(), fmt(ccf).c_str());
+            }
+            printf(" ( CCF = cluster count function, for comparison with TRAVIS:\n J. Chem. Inf. Model., 2022, 62, 5634-5644, dx.doi.org/10.1021/acs.jcim.2c01244 )\n");
+        }
+    }
+    return 0;
+}
+
 void write_simple_sumrules(Run &r)                            // Distribution:43-67
 {
     const std::string path = r.path_in + "prealpha_simple.inp";
@@ -1347,7 +1631,7 @@ const char *kOtherModuleKeywords[] = {
     "temperature", "temperature_simple", "gyradius", "gyradius_simple", "jump_velocity", "jump_velocity_simple",
     "convert", "convert_simple", "convert_coc", "convert_coc_simple", "unwrap_full", "unwrap_full_simple",
     "correlation", "autocorrelation", "dihedral", "reorientation", "rmm-vcf", "conductivity", "velocity",
-    "conductivity_simple", "diffusion", "diffusion_simple", "cross_diffusion", "cluster", "cluster_simple",
+    "conductivity_simple", "diffusion", "diffusion_simple", "cross_diffusion", "cluster_simple",
     "speciation", "speciation_simple", "charge_arm_simple", "clm_simple", "cubic_box_edge_simple", "time_scaling",
     "time_scaling_factor", "error_output", "time_output", "set_threads", "set_threads_simple", "parallel_operation",
     "parallel_execution", "print_atom_masses", "print_atomic_weights", "print_atom_weights", "print_atom_charges",
@@ -1423,7 +1707,7 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             if (t.empty()) continue;
             if (t[0] == "quit" || t[0] == "exit") break;
             if (t[0] == "distance" || t[0] == "distances" || t[0] == "distance_simple" || t[0] == "distances_simple" ||
-                t[0] == "contact_distance" || t[0] == "contact_distance_simple") r.stream = false;
+                t[0] == "contact_distance" || t[0] == "contact_distance_simple" || t[0] == "cluster") r.stream = false;
         }
         printf(r.stream ? " sequential_read T: the distribution analysis streams the trajectory from the file, batch by batch.\n"
                         : " sequential_read T: this input needs the whole trajectory in RAM; it is loaded once.\n");
@@ -1487,6 +1771,11 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             printf(" distance module invoked.\n");
             perform_distance(r, t[1]);
+        } else if (k == "cluster") {                                          // Main: cluster keyword -> perform_cluster_analysis (Cluster:1931)
+            if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
+            if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
+            printf(" Cluster module invoked.\n");
+            perform_cluster(r, t[1]);
         } else if (k == "set_prefix") {
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             r.prefix = t[1];

@@ -432,7 +432,52 @@ def case_charge_arm():
                     atom_charge_2=charges[2]))
 
 
-CASES = {"dist_simple": case_dist_simple, "contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+CLUSTER_INPUTS = {
+    # the two inputs Research_Example_4/general.inp runs (cluster_PAIRS.inp / cluster_GLOBAL.inp), 12 steps
+    "cluster_PAIRS.inp": "PAIRS\n\nnsteps 12\nsampling_interval 1\nprint_spectators T\nprint_statistics T\nprint_step 1\n"
+                         "pair 1 1 3 1 4.25 P-Li\npair 2 2 3 1 2.85 O-Li\npair 2 5 3 1 2.85 O-Li\nquit\n",
+    "cluster_GLOBAL.inp": "GLOBAL\n\nnsteps 12\nsampling_interval 1\nprint_spectators T\nprint_statistics T\nprint_step 1\n"
+                          "add_atom_index 1 1 # P atom\nadd_atom_index 3 1 # Li atom\nsingle_cutoff 4.25 #use this cutoff\nquit\n",
+    # several cutoffs (scan + single, unsorted), custom weights, a whole molecule type, a sampling interval
+    "cluster_SCAN.inp": "GLOBAL\nnsteps 11\nsampling_interval 2\nprint_statistics T\nautocorrelation F\ncustom_weight 0.25\n"
+                        "add_molecule_type 1\ncustom_weight -1.5\nadd_atom_index 3 1\nsingle_cutoff 3.1\nscan_cutoff 1.5 2.75 3\nquit\n",
+    # pairs that share lists in every way the reader distinguishes (A=old A, A=old B, B=old A, B=new A), custom weights
+    "cluster_PAIRS2.inp": "pairs\nnsteps 12\nsampling_interval 3\nprint_statistics T\nautocorrelation F\ncustom_weight 2.0\n"
+                          "pair 3 1 1 2 2.3\ncustom_weight -0.5\npair 1 2 2 2 3.4\npair 2 5 3 1 2.9\npair 2 2 2 2 3.3\npair 1 3 1 3 3.0\nquit\n",
+}
+
+
+def case_re4_cluster():
+    """SURVEY 8f-4 consumer: the cluster analysis (Module_Cluster) of the reference binary on the first 12 frames of
+    Research_Example_4 -- the `*cluster_statistics.dat` files it writes for the inputs above (the coordinates are those
+    of re4.npz)."""
+    src = os.path.join(REF, "Research_Example_4", "LiG1G1G1DFP-noH-1ns-363K.xyz")
+    wd = tempfile.mkdtemp()
+    with open(src) as f, open(os.path.join(wd, "traj.xyz"), "w") as g:
+        for _ in range(12 * (1680 + 2)):
+            g.write(f.readline())
+    os.makedirs(os.path.join(wd, "output"))
+    open(os.path.join(wd, "molecular.inp"), "w").write(" 12\n 3\n -1 5 70\n +0 6 210\n +1 1 70\nquit\n")
+    gen = ' "traj.xyz"\n "molecular.inp"\n "./"\n "./"\n "./output/"\n set_threads 4\n cubic_box_edge 0.0 34.7853\n parallel_operation T\n sequential_read F\n trajectory_type xyz\n'
+    for name, text in CLUSTER_INPUTS.items():
+        open(os.path.join(wd, name), "w").write(text)
+        gen += f' set_prefix "{name[8:-4]}_"\n cluster {name}\n'
+    open(os.path.join(wd, "general.inp"), "w").write(gen + " quit\n")
+    out, _ = orc.run_reference(wd)
+    files = {}
+    for name in CLUSTER_INPUTS:
+        fn = f"{name[8:-4]}_cluster_statistics.dat"
+        files[fn] = open(os.path.join(wd, "output", fn), "rb").read()
+    ccf = [ln for ln in out.splitlines() if "CCF" in ln or (ln.strip() and ln.strip()[0].isdigit() and len(ln.split()) == 2)]
+    np.savez_compressed(os.path.join(OUT, "re4_cluster.npz"),
+                        input_names=np.array(list(CLUSTER_INPUTS)), input_texts=np.array(list(CLUSTER_INPUTS.values())),
+                        file_names=np.array(list(files)), file_bytes=np.array([np.frombuffer(b, dtype=np.uint8) for b in files.values()], dtype=object),
+                        ccf_lines=np.array(ccf), stdout=np.array(out))
+    shutil.rmtree(wd)
+    print("re4_cluster:", {k: len(v) for k, v in files.items()})
+
+
+CASES = {"re4_cluster": case_re4_cluster, "dist_simple": case_dist_simple, "contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"

@@ -108,6 +108,34 @@ def test_neighbour_pairs_larger_random_system(oracle):
     inst = np.array([(1, m, 1) for m in range(1, 2501)] + [(2, m, a) for m in range(1, 1501) for a in (1, 2)], dtype=np.int32)
     rq, keep = capi.make_neigh_request(1, a=inst, b=None, cutoff_sq=np.float32(3.0) ** 2, same_list=True, skip_same_molecule=True)
     exp = oracle.neighbour_pairs(traj, rq)
+    got, tests = api.neighbour_pairs(traj, rq)                                    # cell list: 13 x 13 x 13 cells of >= 3 A
+    brute, tests_brute = api.neighbour_pairs(traj, rq, exec_=api.make_exec(flags=0x800))
+    assert len(exp) > 1000 and np.array_equal(got, exp) and np.array_equal(brute, exp)
+    assert tests_brute == len(inst) * (len(inst) - 1) // 2 and 0 < tests < tests_brute // 20
+
+
+@pytest.mark.gpu
+def test_neighbour_cell_list_equals_brute_force_on_100k_atoms():
+    """The size SURVEY 8f-4 names (all-atom list of a 100k-atom box against itself, 3 A cutoff): the cell-list kernel
+    returns exactly the brute-force kernel's pairs (both apply the same literal REAL(4) predicate), with per-class
+    cutoffs, positions on the box faces and outside the box (wrapped by wrap_vector first), and it does ~1e-3 of the
+    distance tests."""
+    rng = np.random.default_rng(7)
+    n, L = 50_000, 126.0
+    pos = np.round(rng.random((2, n, 3)) * L, 4)
+    pos[0, :50] = pos[1, :50] + 0.5                      # close pairs across the two types
+    pos[0, 50:60, 0] = 0.0                               # on the lower face
+    pos[1, 50:60, 0] = L                                 # on the upper face (periodic neighbours of the ones above)
+    pos[1, 60:70, 1] += L                                # outside the box: wrapped before the search
+    types = [dict(charge=+1, natoms=1, nmol=n, elements=["Na"], xyz=pos[0].reshape(1, n, 1, 3).astype(np.float32)),
+             dict(charge=-1, natoms=1, nmol=n, elements=["Cl"], xyz=pos[1].reshape(1, n, 1, 3).astype(np.float32))]
+    lo, hi = capi.cubic_box_edge(0.0, L)
+    traj = capi.Trajectory(types, lo, hi)
+    inst = np.array([(t, m, 1) for t in (1, 2) for m in range(1, n + 1)], dtype=np.int32)
+    cls = np.array([0] * n + [1] * n, dtype=np.int32)
+    cut = (np.array([[3.0, 2.6], [2.6, 3.2]], dtype=np.float32) ** 2).astype(np.float32)
+    rq, keep = capi.make_neigh_request(1, a=inst, b=None, cutoff_sq=cut, a_class=cls, b_class=cls, same_list=True)
     got, tests = api.neighbour_pairs(traj, rq)
-    assert len(exp) > 1000 and np.array_equal(got, exp)
-    assert tests == len(inst) * (len(inst) - 1) // 2
+    brute, tests_brute = api.neighbour_pairs(traj, rq, exec_=api.make_exec(flags=0x800))
+    assert len(brute) > 100_000 and np.array_equal(got, brute)
+    assert tests < tests_brute // 500
