@@ -11,6 +11,7 @@
 // powers -- Distances:1188-1235), which makes every REAL(8) result bit-identical to the reference's.
 #include <cuda_runtime.h>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <vector>
@@ -847,7 +848,9 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
             const double cmax = std::sqrt((double)cmax2) * (1.0 + 1e-9) + 1e-9;     // margin >> rounding of the cell index
             PnGrid G{};
             const double Lk[3] = { L.x, L.y, L.z };
-            bool grid_ok = cmax2 > 0.f && std::isfinite(cmax) && rq->n_b >= 1024 && !(exec && (exec->flags & 0x800));
+            int min_b = 1024;                                  // below that the brute-force kernel is done before the grid is built
+            if (const char *e = getenv("PA_NEIGH_MIN_CELLS")) min_b = atoi(e);       // test hook
+            bool grid_ok = cmax2 > 0.f && std::isfinite(cmax) && rq->n_b >= min_b && !(exec && (exec->flags & 0x800));
             long long ncell = 1;
             for (int k = 0; k < 3; ++k) {
                 G.g[k] = (int)std::min(128.0, std::floor(Lk[k] / cmax));

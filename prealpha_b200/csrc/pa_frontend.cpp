@@ -15,6 +15,7 @@
 #include <sstream>
 #include <chrono>
 #include <array>
+#include <algorithm>
 #include <thread>
 #include <fcntl.h>
 #include <unistd.h>
