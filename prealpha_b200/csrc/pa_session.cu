@@ -857,8 +857,11 @@ static int choose_batch(const pa_traj *traj, const pa_exec *ex, int nsamp_local)
     if (ex && ex->frames_per_batch > 0) return std::min(ex->frames_per_batch, std::max(nsamp_local, 1));
     int64_t atoms = 0, M = 0;
     for (int t = 0; t < traj->ntypes; ++t) { atoms += (int64_t)traj->types[t].natoms * traj->types[t].nmol; M += traj->types[t].nmol; }
-    // ~2^24 atoms of raw coordinates (200 MB) and ~2^23 molecule slots (72-96 B each) per batch
-    int64_t b = std::min<int64_t>((int64_t(1) << 24) / std::max<int64_t>(atoms, 1), (int64_t(1) << 23) / std::max<int64_t>(M, 1));
+    // ~2^22 atoms of raw coordinates (50 MB of page-locked staging per buffer) and ~2^22 molecule slots (72-96 B each) per
+    // batch: small enough that page-locking the staging buffers and the first host copy do not delay the first kernel by
+    // more than a few ms, and that the copy of batch k+1 hides behind the kernels of batch k; large enough (>= 8 batches
+    // when the trajectory allows) that the ~40 launches per batch do not matter
+    int64_t b = std::min<int64_t>((int64_t(1) << 22) / std::max<int64_t>(atoms, 1), (int64_t(1) << 22) / std::max<int64_t>(M, 1));
     b = std::max<int64_t>(1, std::min<int64_t>(b, nsamp_local));
     return (int)b;
 }
