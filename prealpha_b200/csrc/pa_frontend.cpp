@@ -906,10 +906,20 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
         if (!open_stream(r, ts)) return PA_ERR_IO;
         std::vector<pa_session *> sess(ndev, nullptr);
         int rc = 0;
-        for (int d = 0; d < ndev && rc == 0; ++d) {
-            pa_exec e = ex;
-            e.device = ex.device + d;
-            rc = pa_session_create(&meta, jobs.data(), (int)jobs.size(), &e, (B + dt - 1) / dt, &sess[d]);
+        {
+            // one thread per device: allocation and table uploads of the sessions run concurrently
+            std::vector<int> rcs(ndev, 0);
+            std::vector<std::string> errs(ndev);
+            std::vector<std::thread> th;
+            for (int d = 0; d < ndev; ++d)
+                th.emplace_back([&, d] {
+                    pa_exec e = ex;
+                    e.device = ex.device + d;
+                    rcs[d] = pa_session_create(&meta, jobs.data(), (int)jobs.size(), &e, (B + dt - 1) / dt, &sess[d]);
+                    if (rcs[d]) errs[d] = pa_last_error();
+                });
+            for (auto &t : th) t.join();
+            for (int d = 0; d < ndev && rc == 0; ++d) if (rcs[d]) { rc = rcs[d]; pa::set_error(errs[d]); }
         }
         if (rc) { for (pa_session *s : sess) if (s) pa_session_destroy(s); return rc; }
         std::vector<std::vector<float>> batch(r.types.size());
@@ -1660,8 +1670,17 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
     r.general_path = general_inp_path;
     // CUDA context creation and the load of the kernel image take ~1 s in a fresh process: start them now, on a helper
     // thread, so that they overlap with reading the input files and the trajectory instead of delaying the first analysis
-    const int warm_device = r.exec.device;
-    std::thread warm([warm_device] { if (pa_device_count() > 0 && cudaSetDevice(warm_device) == cudaSuccess) { cudaFree(nullptr); pa_kernels_selfcheck(); } });
+    // (every device the run may use, one helper thread each: contexts are created concurrently)
+    const int warm_device = r.exec.device, warm_n = r.exec.ndevices;
+    std::thread warm([warm_device, warm_n] {
+        const int usable = pa_device_count();
+        if (usable < 1) return;
+        const int n = warm_n < 0 ? usable - warm_device : std::max(1, warm_n);
+        std::vector<std::thread> th;
+        for (int d = warm_device; d < std::min(usable, warm_device + n); ++d)
+            th.emplace_back([d] { if (cudaSetDevice(d) == cudaSuccess) { cudaFree(nullptr); pa_kernels_selfcheck(); } });
+        for (auto &t : th) t.join();
+    });
     struct Joiner { std::thread &t; ~Joiner() { if (t.joinable()) t.join(); } } warm_joiner{ warm };
     std::vector<std::string> lines;
     if (!read_lines(r.general_path, lines)) { r.error(5, "general input file '" + r.general_path + "' not found"); return r.errors; }

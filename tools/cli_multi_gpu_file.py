@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""BASELINE config 4 from FILES through the drop-in CLI at 1 and N GPUs: an xyz text trajectory of
+NF frames x 1M atoms (two one-atom types, density 0.05; written by a small C generator, ~35 MB per frame) is analysed
+with `sequential_read T` (streamed) -- text on one GPU (this run also writes the binary frame cache), cache on one
+GPU, text on N GPUs, cache on N GPUs.  Prints one JSON line per run (wall time from process start to exit, the CLI's
+own timing lines) and checks that all runs write byte-identical output files.
+usage: python tools/cli_multi_gpu_file.py [NF] [N]"""
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+sys.path.insert(0, ".")
+import bench  # noqa: E402
+from prealpha_b200 import api, capi  # noqa: E402
+
+nf = int(sys.argv[1]) if len(sys.argv) > 1 else 48
+ngpu = int(sys.argv[2]) if len(sys.argv) > 2 else api.device_count()
+n_half, L = bench.N_PER_TYPE, float(bench.L_BOX)
+wd = tempfile.mkdtemp(prefix="cli_multi_")
+os.makedirs(os.path.join(wd, "out"))
+gen = r'''
+#include <stdio.h>
+#include <stdlib.h>
+int main(int argc, char **argv) {
+    const int nf = atoi(argv[1]), n = atoi(argv[2]); const double L = atof(argv[3]);
+    static char buf[1 << 22];
+    FILE *f = fopen(argv[4], "w"); setvbuf(f, buf, _IOFBF, sizeof buf);
+    unsigned long long s = 88172645463325252ull;
+    for (int k = 0; k < nf; ++k) {
+        fprintf(f, "%d\nstep %d\n", n, k);
+        for (int i = 0; i < n; ++i) {
+            double x[3];
+            for (int c = 0; c < 3; ++c) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x[c] = (double)(s >> 11) / 9007199254740992.0 * L; }
+            fprintf(f, "%s %.5f %.5f %.5f\n", i < n / 2 ? "Na" : "Cl", x[0], x[1], x[2]);
+        }
+    }
+    fclose(f); return 0;
+}
+'''
+open(os.path.join(wd, "gen.c"), "w").write(gen)
+subprocess.check_call(["gcc", "-O2", "-o", os.path.join(wd, "gen"), os.path.join(wd, "gen.c")])
+t0 = time.time()
+subprocess.check_call([os.path.join(wd, "gen"), str(nf), str(2 * n_half), bench.L_BOX, os.path.join(wd, "traj.xyz")])
+size = os.path.getsize(os.path.join(wd, "traj.xyz"))
+print(json.dumps({"what": "generated", "frames": nf, "atoms": 2 * n_half, "bytes": size, "seconds": time.time() - t0, "host_threads": os.cpu_count(), "gpus": ngpu}), flush=True)
+open(os.path.join(wd, "molecular.inp"), "w").write(f" {nf}\n 2\n +1 1 {n_half}\n -1 1 {n_half}\nquit\n")
+open(os.path.join(wd, "rdf.inp"), "w").write("pdf 2\n+0 +0 +1 1 -1\n+0 +0 +1 2 -1\nmaxdist_optimize\nsampling_interval 1\nbin_count_a 1000\nbin_count_b 1\nquit\n")
+open(os.path.join(wd, "general.inp"), "w").write(
+    f' "traj.xyz"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n cubic_box_edge 0.0 {bench.L_BOX}\n sequential_read T\n distribution "rdf.inp"\n quit\n')
+cli = os.path.join(os.path.dirname(capi.LIB_PATH), "prealpha_b200_cli")
+
+
+def digest():
+    h = hashlib.sha256()
+    for fn in sorted(os.listdir(os.path.join(wd, "out"))):
+        h.update(fn.encode()); h.update(open(os.path.join(wd, "out", fn), "rb").read())
+    return h.hexdigest()
+
+
+results, ref = [], None
+for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{ngpu}gpu", ngpu, "0"), (f"cache_{ngpu}gpu", ngpu, "1")):
+    if g > 1 and ngpu < 2:
+        continue
+    for fn in os.listdir(os.path.join(wd, "out")):
+        os.remove(os.path.join(wd, "out", fn))
+    env = dict(os.environ, PREALPHA_B200_CACHE=cache)
+    t0 = time.time()
+    p = subprocess.run([cli, "-g", str(g), "general.inp"], cwd=wd, capture_output=True, timeout=3600, env=env)
+    wall = time.time() - t0
+    out = p.stdout.decode()
+    assert p.returncode == 0, out[-2000:] + p.stderr.decode()[-2000:]
+    d = digest()
+    ref = ref or d
+    keep = [ln.strip() for ln in out.splitlines() if "B200 execution" in ln or "accelerated section" in ln or "frame cache" in ln]
+    rec = {"run": label, "gpus": g, "wall_s": wall, "frames_per_s": nf / wall, "atoms_per_s": nf * 2 * n_half / wall,
+           "pair_evals_per_s": nf * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "same_files_as_first_run": d == ref, "cli": keep}
+    results.append(rec)
+    print(json.dumps(rec), flush=True)
+    assert d == ref, "output files differ between runs"
+if len(results) >= 4:
+    print(json.dumps({"what": "speedup", "text_N_over_1": results[0]["wall_s"] / results[2]["wall_s"], "cache_N_over_cache_1": results[1]["wall_s"] / results[3]["wall_s"],
+                      "cache_N_over_text_1": results[0]["wall_s"] / results[3]["wall_s"]}), flush=True)
