@@ -906,6 +906,9 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
         if (!open_stream(r, ts)) return PA_ERR_IO;
         std::vector<pa_session *> sess(ndev, nullptr);
         int rc = 0;
+        // NCCL communicators take a few hundred ms to create: do it while the file is read and the kernels run
+        std::thread comm_thread([&] { if (ndev > 1) pa_multi_device_prepare(ex.device, ndev); });
+        struct CommJoin { std::thread &t; ~CommJoin() { if (t.joinable()) t.join(); } } comm_join{ comm_thread };
         {
             // one thread per device: allocation and table uploads of the sessions run concurrently
             std::vector<int> rcs(ndev, 0);
@@ -954,6 +957,7 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
         if (rc == 0) finish_cache_write(r, ts, src);              // (no-op unless a cache is being written)
         // sticky flags of every device, then the sum on the first one
         for (int d = 0; d < ndev && rc == 0; ++d) rc = pa_session_download(sess[d], nullptr, nullptr, nullptr, 0);
+        if (comm_thread.joinable()) comm_thread.join();
         if (rc == 0) rc = pa_sessions_reduce_to_first(sess.data(), ndev);
         if (rc == 0) rc = pa_session_download(sess[0], hp.data(), within.data(), oob.data(), 0);
         if (st) pa_sessions_merge_stats(sess.data(), ndev, true, st);
@@ -1664,6 +1668,11 @@ extern "C" float pa_debug_parse_coordinate(const char *s, int32_t *consumed)
 extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec *exec)
 {
     if (!general_inp_path) return PA_ERR_BAD_ARG;
+    const auto t_start = std::chrono::steady_clock::now();
+    const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
+    auto mark = [&](const char *what) {
+        if (dbg_t) fprintf(stderr, "[prealpha_b200] cli %-22s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
     Run r;
     if (exec) r.exec = *exec;
     if (r.exec.shard_count < 1) r.exec.shard_count = 1;
@@ -1733,7 +1742,9 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
                         : " sequential_read T: this input needs the whole trajectory in RAM; it is loaded once.\n");
     }
     if (!read_molecular_input(r)) return r.errors;
+    mark("inputs read");
     if (!load_trajectory(r)) return r.errors;
+    mark("trajectory loaded");
     if ((r.wrap || r.unwrap) && !r.box_given) { r.error(41, "box volume required for wrapping"); return r.errors; }
     if (r.wrap) {                                                // Molecular:4801-4804
         printf(" Wrapping centres of mass of each specified molecule into box *now*.\n");
@@ -1759,7 +1770,9 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             printf(" Distribution module invoked.\n");
+            mark("distribution begins");
             perform_distribution(r, t[1]);
+            mark("distribution done");
         } else if (k == "distribution_simple") {
             if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
             write_simple_sumrules(r);
@@ -1816,6 +1829,7 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
         }
     }
     printf("\n Encountered %d errors/warnings globally.\n", r.errors);
+    mark("all keywords done");
     return r.errors;
 }
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <string>
 #include <vector>
 #include "../../include/prealpha_b200.h"
@@ -32,5 +33,8 @@ int main(int argc, char **argv)
     }
     int errors = 0;
     for (const std::string &g : inputs) errors += pa_run_general_input(g.c_str(), &ex);
-    return errors ? 1 : 0;
+    fflush(stdout);
+    // the results are on disk: skip the orderly teardown of CUDA contexts, memory pools and NCCL communicators, which
+    // costs up to a second per device and frees nothing the operating system does not free anyway
+    _exit(errors ? 1 : 0);
 }

@@ -1007,6 +1007,14 @@ std::vector<void *> nccl_comms_for(const std::vector<int> &devs)
 
 }  // namespace
 
+// creates (and caches) the NCCL communicators of devices first..first+n-1 ahead of the reduce
+void pa_multi_device_prepare(int first, int n)
+{
+    std::vector<int> devs(n);
+    for (int d = 0; d < n; ++d) devs[d] = first + d;
+    nccl_comms_for(devs);
+}
+
 void pa_multi_device_trim()
 {
     std::lock_guard<std::mutex> lock(g_nccl_mutex);

@@ -25,24 +25,34 @@ os.makedirs(os.path.join(wd, "out"))
 gen = r'''
 #include <stdio.h>
 #include <stdlib.h>
+#include <omp.h>
+/* frames are formatted by all host threads (one frame per thread at a time) and written in order */
 int main(int argc, char **argv) {
     const int nf = atoi(argv[1]), n = atoi(argv[2]); const double L = atof(argv[3]);
-    static char buf[1 << 22];
-    FILE *f = fopen(argv[4], "w"); setvbuf(f, buf, _IOFBF, sizeof buf);
-    unsigned long long s = 88172645463325252ull;
-    for (int k = 0; k < nf; ++k) {
-        fprintf(f, "%d\nstep %d\n", n, k);
-        for (int i = 0; i < n; ++i) {
-            double x[3];
-            for (int c = 0; c < 3; ++c) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x[c] = (double)(s >> 11) / 9007199254740992.0 * L; }
-            fprintf(f, "%s %.5f %.5f %.5f\n", i < n / 2 ? "Na" : "Cl", x[0], x[1], x[2]);
+    FILE *f = fopen(argv[4], "w");
+    const int nt = omp_get_max_threads();
+    char **buf = malloc(sizeof(char *) * nt); size_t *len = malloc(sizeof(size_t) * nt);
+    for (int t = 0; t < nt; ++t) buf[t] = malloc((size_t)n * 40 + 64);
+    for (int k0 = 0; k0 < nf; k0 += nt) {
+        #pragma omp parallel for schedule(static, 1)
+        for (int k = k0; k < (k0 + nt < nf ? k0 + nt : nf); ++k) {
+            char *p = buf[k - k0];
+            unsigned long long s = 88172645463325252ull ^ (0x9E3779B97F4A7C15ull * (unsigned long long)(k + 1));
+            p += sprintf(p, "%d\nstep %d\n", n, k);
+            for (int i = 0; i < n; ++i) {
+                double x[3];
+                for (int c = 0; c < 3; ++c) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; x[c] = (double)(s >> 11) / 9007199254740992.0 * L; }
+                p += sprintf(p, "%s %.5f %.5f %.5f\n", i < n / 2 ? "Na" : "Cl", x[0], x[1], x[2]);
+            }
+            len[k - k0] = (size_t)(p - buf[k - k0]);
         }
+        for (int k = k0; k < (k0 + nt < nf ? k0 + nt : nf); ++k) fwrite(buf[k - k0], 1, len[k - k0], f);
     }
     fclose(f); return 0;
 }
 '''
 open(os.path.join(wd, "gen.c"), "w").write(gen)
-subprocess.check_call(["gcc", "-O2", "-o", os.path.join(wd, "gen"), os.path.join(wd, "gen.c")])
+subprocess.check_call(["gcc", "-O2", "-fopenmp", "-o", os.path.join(wd, "gen"), os.path.join(wd, "gen.c")])
 t0 = time.time()
 subprocess.check_call([os.path.join(wd, "gen"), str(nf), str(2 * n_half), bench.L_BOX, os.path.join(wd, "traj.xyz")])
 size = os.path.getsize(os.path.join(wd, "traj.xyz"))
@@ -67,7 +77,7 @@ for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{
         continue
     for fn in os.listdir(os.path.join(wd, "out")):
         os.remove(os.path.join(wd, "out", fn))
-    env = dict(os.environ, PREALPHA_B200_CACHE=cache)
+    env = dict(os.environ, PREALPHA_B200_CACHE=cache, PA_DEBUG_TIMING="1")
     t0 = time.time()
     p = subprocess.run([cli, "-g", str(g), "general.inp"], cwd=wd, capture_output=True, timeout=3600, env=env)
     wall = time.time() - t0
@@ -77,7 +87,8 @@ for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{
     ref = ref or d
     keep = [ln.strip() for ln in out.splitlines() if "B200 execution" in ln or "accelerated section" in ln or "frame cache" in ln]
     rec = {"run": label, "gpus": g, "wall_s": wall, "frames_per_s": nf / wall, "atoms_per_s": nf * 2 * n_half / wall,
-           "pair_evals_per_s": nf * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "same_files_as_first_run": d == ref, "cli": keep}
+           "pair_evals_per_s": nf * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "same_files_as_first_run": d == ref, "cli": keep,
+           "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln]}
     results.append(rec)
     print(json.dumps(rec), flush=True)
     assert d == ref, "output files differ between runs"
