@@ -92,6 +92,50 @@ for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{
     results.append(rec)
     print(json.dumps(rec), flush=True)
     assert d == ref, "output files differ between runs"
+# ---- a long trajectory (LONG x the frames above) from the binary cache only: the text of a 400-frame trajectory would be
+# 14 GB, so the cache the first run wrote is extended by repeating its frames (header: nsteps patched; the source file
+# it is pinned to is a hard link of the text above).  This is the regime in which the fixed costs of a run (driver
+# initialisation ~1.5 s, one CUDA context per device, communicators) stop mattering.
+LONG = int(os.environ.get("PA_LONG_FACTOR", "0"))
+if LONG > 1:
+    wl = os.path.join(wd, "long")
+    os.makedirs(os.path.join(wl, "out"))
+    os.link(os.path.join(wd, "traj.xyz"), os.path.join(wl, "traj.xyz"))
+    blob = open(os.path.join(wd, "traj.xyz.pab200cache"), "rb").read()
+    data_bytes = nf * 2 * n_half * 12
+    head, data = bytearray(blob[:len(blob) - data_bytes]), blob[len(blob) - data_bytes:]
+    import struct
+    assert struct.unpack_from("<Q", head, 32)[0] == nf          # CacheHeader.nsteps
+    struct.pack_into("<Q", head, 32, nf * LONG)
+    with open(os.path.join(wl, "traj.xyz.pab200cache"), "wb") as f:
+        f.write(head)
+        for _ in range(LONG):
+            f.write(data)
+    del blob, data
+    open(os.path.join(wl, "molecular.inp"), "w").write(f" {nf * LONG}\n 2\n +1 1 {n_half}\n -1 1 {n_half}\nquit\n")
+    for fn in ("rdf.inp", "general.inp"):
+        open(os.path.join(wl, fn), "w").write(open(os.path.join(wd, fn)).read())
+    longres = []
+    for g in ([1, ngpu] if ngpu > 1 else [1]):
+        env = dict(os.environ, PREALPHA_B200_CACHE="1", PA_DEBUG_TIMING="1")
+        t0 = time.time()
+        p = subprocess.run([cli, "-g", str(g), "general.inp"], cwd=wl, capture_output=True, timeout=3600, env=env)
+        wall = time.time() - t0
+        out = p.stdout.decode()
+        assert p.returncode == 0 and "reading the binary frame cache" in out, out[-2000:] + p.stderr.decode()[-2000:]
+        h = hashlib.sha256()
+        for fn in sorted(os.listdir(os.path.join(wl, "out"))):
+            h.update(fn.encode()); h.update(open(os.path.join(wl, "out", fn), "rb").read())
+        rec = {"run": f"long_cache_{g}gpu", "gpus": g, "frames": nf * LONG, "wall_s": wall, "frames_per_s": nf * LONG / wall,
+               "pair_evals_per_s": nf * LONG * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "digest": h.hexdigest()[:16],
+               "cli": [ln.strip() for ln in out.splitlines() if "B200 execution" in ln or "accelerated section" in ln],
+               "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln]}
+        longres.append(rec)
+        print(json.dumps(rec), flush=True)
+    if len(longres) == 2:
+        assert longres[0]["digest"] == longres[1]["digest"], "output files differ between 1 and N GPUs"
+        print(json.dumps({"what": "speedup_long", "frames": nf * LONG, "N": ngpu, "wall_1": longres[0]["wall_s"], "wall_N": longres[1]["wall_s"],
+                          "speedup": longres[0]["wall_s"] / longres[1]["wall_s"]}), flush=True)
 if len(results) >= 4:
     print(json.dumps({"what": "speedup", "text_N_over_1": results[0]["wall_s"] / results[2]["wall_s"], "cache_N_over_cache_1": results[1]["wall_s"] / results[3]["wall_s"],
                       "cache_N_over_text_1": results[0]["wall_s"] / results[3]["wall_s"]}), flush=True)
