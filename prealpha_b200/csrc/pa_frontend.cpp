@@ -938,22 +938,33 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
         int g0 = 0;                                               // global index of the first frame of the batch
         long long nbatch = 0;
         bool short_file = false;
+        const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
+        double t_read = 0, t_upload = 0, t_run = 0;
+        auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        const double t_loop0 = now_s();
         while (g0 < r.nsteps && rc == 0) {
             const int want = std::min(B, r.nsteps - g0);
+            double t0 = now_s();
             const int n = read_frames(r, ts, want, dst);
+            t_read += now_s() - t0;
             if (n > 0) {
                 const int first = (dt - g0 % dt) % dt;            // sampled frames are the global multiples of dt (Distribution:718)
                 if (first < n) {
                     pa_session *s = sess[nbatch % ndev];
                     ++nbatch;
                     view.nsteps = n;
+                    t0 = now_s();
                     rc = pa_session_upload(s, &view, first, (n - first + dt - 1) / dt, dt);
+                    t_upload += now_s() - t0; t0 = now_s();
                     if (rc == 0) rc = pa_session_run(s);
+                    t_run += now_s() - t0;
                 }
                 g0 += n;
             }
             if (n < want) { short_file = true; break; }
         }
+        if (dbg_t) fprintf(stderr, "[prealpha_b200] streaming: %lld batches of <= %d frames on %d device(s); host loop %.3f s = read %.3f + upload %.3f + launch %.3f\n",
+                           nbatch, B, ndev, now_s() - t_loop0, t_read, t_upload, t_run);
         if (rc == 0) finish_cache_write(r, ts, src);              // (no-op unless a cache is being written)
         // sticky flags of every device, then the sum on the first one
         for (int d = 0; d < ndev && rc == 0; ++d) rc = pa_session_download(sess[d], nullptr, nullptr, nullptr, 0);

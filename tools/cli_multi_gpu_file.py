@@ -88,7 +88,7 @@ for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{
     keep = [ln.strip() for ln in out.splitlines() if "B200 execution" in ln or "accelerated section" in ln or "frame cache" in ln]
     rec = {"run": label, "gpus": g, "wall_s": wall, "frames_per_s": nf / wall, "atoms_per_s": nf * 2 * n_half / wall,
            "pair_evals_per_s": nf * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "same_files_as_first_run": d == ref, "cli": keep,
-           "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln]}
+           "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln or "] streaming" in ln or "] dev " in ln]}
     results.append(rec)
     print(json.dumps(rec), flush=True)
     assert d == ref, "output files differ between runs"
@@ -129,7 +129,7 @@ if LONG > 1:
         rec = {"run": f"long_cache_{g}gpu", "gpus": g, "frames": nf * LONG, "wall_s": wall, "frames_per_s": nf * LONG / wall,
                "pair_evals_per_s": nf * LONG * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "digest": h.hexdigest()[:16],
                "cli": [ln.strip() for ln in out.splitlines() if "B200 execution" in ln or "accelerated section" in ln],
-               "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln]}
+               "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln or "] streaming" in ln or "] dev " in ln]}
         longres.append(rec)
         print(json.dumps(rec), flush=True)
     if len(longres) == 2:
