@@ -897,7 +897,9 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
     int ndev = ex.ndevices < 0 ? pa_device_count() - ex.device : std::max(1, ex.ndevices);
     if (ndev < 1 || ex.device + ndev > pa_device_count()) { pa::set_error("pa_exec.device/ndevices: not that many usable devices"); return PA_ERR_BAD_ARG; }
     ex.ndevices = 1;
-    int B = (int)std::max<long long>(1, std::min<long long>(256, ((long long)256 << 20) / std::max<long long>(1, floats_per_frame * 4)));
+    // frames per batch: ~32 MB of raw coordinates (two page-locked staging buffers of that size per session: page-locking
+    // is slow, and with several devices the allocations serialise in the driver), at least one frame
+    int B = (int)std::max<long long>(1, std::min<long long>(256, ((long long)32 << 20) / std::max<long long>(1, floats_per_frame * 4)));
     B = (int)std::min<long long>(B, std::max<long long>(1, ((long long)r.nsteps + 8 * ndev - 1) / (8 * ndev)));   // at least ~8 batches per device: reading overlaps the kernels
     if (const char *e = getenv("PA_STREAM_BATCH")) B = std::max(1, std::min(256, atoi(e)));      // test hook: frames per batch
     const std::string src = r.path_traj + r.traj_file;
