@@ -30,6 +30,8 @@ class Fixture:
         self.lmp = "lmp" in z.files
         self.wrap = "wrap" in z.files
         self.unwrap = "unwrap" in z.files
+        self.mol_tail = str(z["mol_tail"]) if "mol_tail" in z.files else ""            # extra sections of molecular.inp
+        self.general_extra = str(z["general_extra"]) if "general_extra" in z.files else ""
 
     def trajectory(self) -> capi.Trajectory:
         tl, off = [], 0

