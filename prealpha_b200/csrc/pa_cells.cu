@@ -1205,6 +1205,369 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? PC_MINB : 0) pa_rdf_ce
 }
 
 // ---------------------------------------------------------------------------
+// Cell-sorted 2-D (distance x polar angle) kernel for `pdf` jobs with bin_count_b > 1 or any reference vector: the
+// warp-autonomous tiles, layer classification, staging filter and compaction of the RDF kernel, with a pair loop that
+// brackets BOTH classes in float32:
+//   a-class  as in pc_segment_f32 (MUFU.SQRT, two round-down FMAs; brackets must agree);
+//   b-class  = #{k >= 1 : dot <= thr_b[k]}, dot = link.v / |link| (Distribution:812-827).  In local float32
+//            coordinates: N~ = fma(dz~,vz~, fma(dy~,vy~, dx~ vx~)), dot~ = N~ * rcp.approx(r~).  With u = 2^-24,
+//            |d~ - d| <= 2u(r + |T|), |v~ - v| <= u:  |N~ - N| <= u(8.2 r + 2|T|);  r~ = sqrt.approx(d2~) is within
+//            5.5u r + 2u|T| of r and rcp.approx adds 2u, so 1/r~ = (1/r)(1 + rho), |rho| <= 7.5u + 2u|T|/r; the product
+//            rounds once more:   |dot~ - dot| <= u(16.7 + 4|T|/r)   (first order; pairs with a bound above 1e-3, i.e.
+//            r within ~1e-4 |T| of zero, are never decided here).  E = 1.2e-6 + 2.6e-7 |T| / r~ covers that with 5 %
+//            to spare plus 1e-7 for the float32 rounding of the threshold table and of dot~ +- E; the reference's own
+//            fp64 normalisation and the wrap-shift bookkeeping of its link vector differ from the exact quotient by
+//            < 1e-12.  The class c found by binary search in the float table is accepted when the whole interval
+//            [dot~ - E, dot~ + E] lies inside (thr_b[c+1], thr_b[c]].
+// A pair whose a- or b-class is not certain, whose b-class would be bin_count_b (polar angle pi: out of bounds), or
+// that may be the molecule itself goes to the warp's queue and is decided by pa_eval_pair_exact from the original
+// slots (the literal evaluation every other kernel uses), so the result is bit-identical by construction.  Runs that
+// are not float32-eligible (two candidate images for a component, tiles wider than 32 A) are evaluated pair by pair in
+// fp64 and every pair inside the cutoff takes the literal path.  Needs the same job properties as the float32 RDF
+// launch (cutoff within 3e-7 of the last bin boundary), no centre of charge, and a cutoff below
+// maximum_distance_squared; other jobs use pa_general_cells_kernel below.
+struct PdfConsts {
+    float vx, vy, vz;          // reference vector, float32
+    float e_a, e_b;            // E = e_a + e_b / r~
+    unsigned int tab;          // shared address of the float threshold table T[0..nb+1] (T[0] = +inf, T[nb+1] = -inf)
+    int nb, steps;             // bin_count_b, binary-search steps (2^steps > nb)
+};
+
+// largest c in [0, nb] with x <= T[c] (T decreasing, T[0] = +inf)
+static __device__ __forceinline__ int pdf_class(const PdfConsts &C, float x)
+{
+    int c = 0;
+    for (int h = 1 << (C.steps - 1); h > 0; h >>= 1) {
+        const int t = c + h;
+        if (t <= C.nb) {
+            float th;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(th) : "r"(C.tab + 4u * (unsigned)t));
+            if (x <= th) c = t;
+        }
+    }
+    return c;
+}
+
+template <bool VERIFY>
+static __device__ __noinline__ void pdf_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                              const unsigned long long *queue, int count, long long jbase,
+                                              unsigned long long &g_within, unsigned long long &g_oob)
+{
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    if (lane < count) {
+        const unsigned long long ent = queue[lane];
+        const int src = (int)((ent >> 48) & 31u);
+        unsigned int mask = (unsigned int)((ent >> 53) & 15u);
+        const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+        while (mask) {
+            const int q = __ffs((int)mask) - 1;
+            mask &= mask - 1u;
+            const int r = q % PC_RI, u = q / PC_RI;
+            const long long jpos = (long long)((ent >> (24 * u)) & 0xffffffull);
+            const long long iref = (long long)tl.frame * gi.nmol + tl.begin + r * 32 + src;
+            const int io = gi.sorig[iref], jo = go.sorig[jbase + jpos];
+            if (p.same_type && io == jo) continue;                       // the molecule itself (Distribution:778)
+            int bin = 0;
+            const int st = pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
+            if (st == 1) { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
+            else if (st == 2) ++g_oob;
+        }
+    }
+    __syncwarp();
+}
+
+template <bool NEAR, bool VERIFY>
+static __device__ __forceinline__ void pc_segment_pdf(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                                      const float (&xf)[PC_RI], const float (&yf)[PC_RI], const float (&zf)[PC_RI],
+                                                      float hx, float hy, float hz, double ox, double oy, double oz,
+                                                      long long jbase, int jb, int je, double sxa, double sya, double sza,
+                                                      float4 *s_jf, int *s_jidx, const PcTables &T, const PdfConsts &C, float near_a,
+                                                      unsigned long long *queue, float dead_d2,
+                                                      unsigned int &it_all, unsigned long long &g_within, unsigned long long &g_oob)
+{
+    int qn = 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lane_lt = (1u << lane) - 1u;
+    const unsigned long long X01 = pc_pack(xf[0], xf[1]), Y01 = pc_pack(yf[0], yf[1]), Z01 = pc_pack(zf[0], zf[1]);
+    const unsigned long long F2 = pc_pack(p.f32_lo, p.f32_hi), M2 = pc_pack(8388608.0f, 8388608.0f), A2 = pc_pack(-near_a, near_a);
+    const int na = T.na;
+    const unsigned int tlim = 0x4B000000u + (unsigned)na;
+    const unsigned int kmask = (pc_kidx(0) < tl.count ? 0x5u : 0u) | (pc_kidx(1) < tl.count ? 0xAu : 0u);
+    const unsigned int a_jf = (unsigned int)__cvta_generic_to_shared(s_jf);
+    const long long ibase = (long long)tl.frame * gi.nmol + tl.begin;
+    const double cxa = __dsub_rn(sxa, ox), cya = __dsub_rn(sya, oy), cza = __dsub_rn(sza, oz);
+    const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+    int fill = 0;
+    for (int jc = jb; jc < je; jc += 32) {
+        {
+            const int j = jc + lane;
+            bool live = false;
+            float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (j < je) {
+                f.x = __double2float_rn(__dadd_rn(go.sx[jbase + j], cxa));
+                f.y = __double2float_rn(__dadd_rn(go.sy[jbase + j], cya));
+                f.z = __double2float_rn(__dadd_rn(go.sz[jbase + j], cza));
+                const float g1 = fmaxf(__fsub_rd(fabsf(f.x), hx), 0.0f), g2 = fmaxf(__fsub_rd(fabsf(f.y), hy), 0.0f), g3 = fmaxf(__fsub_rd(fabsf(f.z), hz), 0.0f);
+                live = !(__fmaf_rn(g3, g3, __fmaf_rn(g2, g2, __fmul_rn(g1, g1))) >= dead_d2);
+            }
+            const unsigned int m = __ballot_sync(0xffffffffu, live);
+            if (live) { const int pos = fill + __popc(m & lane_lt); s_jf[pos] = f; s_jidx[pos] = j; }
+            fill += __popc(m);
+        }
+        if (!(fill > PC_FBUF - 32 || (jc + 32 >= je && fill > 0))) continue;
+        if ((fill & 1) && lane == 0) { s_jf[fill] = make_float4(T.pad_x, 0.0f, 0.0f, 0.0f); s_jidx[fill] = 0; }
+        __syncwarp();
+        it_all += (unsigned)((fill + 1) / 2);
+        const unsigned int a_end = a_jf + (unsigned)fill * 16u;
+        for (unsigned int aj = a_jf; aj < a_end; aj += 32u) {
+            const int jj = (int)((aj - a_jf) >> 4);
+            unsigned int need = 0u;
+            int bins[4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float4 w = pc_lds_f32x4(aj + 16u * u);
+                const unsigned long long dx = pc_sub2(pc_pack(w.x, w.x), X01), dy = pc_sub2(pc_pack(w.y, w.y), Y01), dz = pc_sub2(pc_pack(w.z, w.z), Z01);
+                const unsigned long long d2p = pc_fma2(dz, dz, pc_fma2(dy, dy, pc_mul2(dx, dx)));
+                const unsigned long long np = pc_fma2(dz, pc_pack(C.vz, C.vz), pc_fma2(dy, pc_pack(C.vy, C.vy), pc_mul2(dx, pc_pack(C.vx, C.vx))));
+#pragma unroll
+                for (int r = 0; r < PC_RI; ++r) {
+                    const int q = u * PC_RI + r;
+                    const float d2 = r ? pc_hi(d2p) : pc_lo(d2p), num = r ? pc_hi(np) : pc_lo(np);
+                    float rt, rinv;
+                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(d2));
+                    unsigned long long rr = pc_pack(rt, rt);
+                    if (NEAR) rr = pc_add2(rr, A2);
+                    const unsigned long long tt = pc_fma2_rm(rr, F2, M2);
+                    const unsigned int tlo = __float_as_uint(pc_lo(tt)), thi = __float_as_uint(pc_hi(tt));
+                    bins[q] = -1;
+                    if (tlo > tlim) continue;                                     // beyond the cutoff (lower bracket): never counted
+                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(rt));
+                    const float dot = num * rinv;
+                    const float E = __fmaf_rn(C.e_b, rinv, C.e_a);
+                    const int c = pdf_class(C, dot);
+                    float t_hi, t_lo;                                             // thr_b[c] >= dot > thr_b[c+1] must hold with margin E
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t_hi) : "r"(C.tab + 4u * (unsigned)c));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t_lo) : "r"(C.tab + 4u * (unsigned)(c + 1)));
+                    // (|dot| + E <= 1: next to +-1 the reference's fp64 dot product can exceed 1 by an ulp -> ACOS = NaN -> out of bounds)
+                    const bool sure = tlo == thi && tlo < tlim && c < C.nb && E < 1.0e-3f && (dot + E <= t_hi) && (dot - E > t_lo) &&
+                                      (fabsf(dot) + E <= 1.0f);
+                    if (sure) bins[q] = c * na + (int)(tlo - 0x4B000000u);
+                    else need |= 1u << q;
+                }
+            }
+            need &= kmask;
+            if (jj + 1 >= fill) need &= 0x3u;                                     // the padded slot of an odd buffer
+#pragma unroll
+            for (int q = 0; q < 4; ++q) if (!((kmask >> q) & 1u) || (q >= 2 && jj + 1 >= fill)) bins[q] = -1;
+            if (VERIFY) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (bins[q] < 0) continue;
+                    const int r = q % PC_RI, u = q / PC_RI;
+                    const int io = gi.sorig[ibase + pc_kidx(r)], jo = go.sorig[jbase + s_jidx[jj + u]];
+                    int bin = -1;
+                    const int st = pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
+                    if (!(st == 1 && bin == bins[q]) || (p.same_type && io == jo)) atomicAdd(p.verify_fail, 1u);
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (bins[q] >= 0) { atomicAdd(&p.job.acc[bins[q]], (unsigned long long)p.weight); ++g_within; }
+            const unsigned int m = __ballot_sync(0xffffffffu, need != 0u);
+            if (m != 0u) {
+                const int add = __popc(m);
+                if (qn + add > PC_QCAP) { pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob); qn = 0; }
+                if (need)
+                    queue[qn + __popc(m & lane_lt)] = (unsigned long long)(unsigned int)s_jidx[jj] | ((unsigned long long)(unsigned int)s_jidx[jj + 1] << 24) |
+                                                      ((unsigned long long)lane << 48) | ((unsigned long long)need << 53);
+                qn += add;
+            }
+        }
+        fill = 0;
+        __syncwarp();
+    }
+    if (qn > 0) pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob);
+}
+
+// runs that are not float32-eligible: every pair in fp64 (two candidate images per component), pairs inside the cutoff
+// go to the queue and are evaluated literally
+template <bool VERIFY>
+static __device__ __forceinline__ void pc_segment_pdf64(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
+                                                        const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
+                                                        long long jbase, int jb, int je, double sxa, double sxb, double sya, double syb, double sza, double szb,
+                                                        unsigned long long *queue, unsigned int &it_all, unsigned long long &g_within, unsigned long long &g_oob)
+{
+    int qn = 0;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lane_lt = (1u << lane) - 1u;
+    const unsigned long long cut = p.job.cut_bits;
+    for (int j = jb; j < je; j += 2) {                                           // two observed molecules per step (uniform loads)
+        unsigned int need = 0u;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (j + u >= je) continue;
+            const double gx0 = go.sx[jbase + j + u], gy0 = go.sy[jbase + j + u], gz0 = go.sz[jbase + j + u];
+#pragma unroll
+            for (int r = 0; r < PC_RI; ++r) {
+                if (pc_kidx(r) >= tl.count) continue;
+                const double ex = pc_comp_sq<2>(__dadd_rn(gx0, sxa), __dadd_rn(gx0, sxb), p1x[r]);
+                const double ey = pc_comp_sq<2>(__dadd_rn(gy0, sya), __dadd_rn(gy0, syb), p1y[r]);
+                const double ez = pc_comp_sq<2>(__dadd_rn(gz0, sza), __dadd_rn(gz0, szb), p1z[r]);
+                if (dbits(__dadd_rn(__dadd_rn(ex, ey), ez)) < cut) need |= 1u << (u * PC_RI + r);
+            }
+        }
+        ++it_all;
+        const unsigned int m = __ballot_sync(0xffffffffu, need != 0u);
+        if (m == 0u) continue;
+        const int add = __popc(m);
+        if (qn + add > PC_QCAP) { pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob); qn = 0; }
+        if (need)
+            queue[qn + __popc(m & lane_lt)] = (unsigned long long)(unsigned int)j | ((unsigned long long)(unsigned int)(j + 1 < je ? j + 1 : j) << 24) |
+                                              ((unsigned long long)lane << 48) | ((unsigned long long)need << 53);
+        qn += add;
+    }
+    if (qn > 0) pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob);
+}
+
+template <bool VERIFY>
+__global__ void __launch_bounds__(PC_THREADS, 4) pa_pdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
+                                                                     const unsigned int *ntiles_ptr, unsigned int tile_cap, unsigned int *work_counter, int nzg)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int na = p.job.bin_a, nb = p.job.bin_b;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int nlay = go.g[0] + go.g[1] + go.g[2];
+    float *s_tab = reinterpret_cast<float *>(smem_raw);                                   // nb + 2 floats
+    unsigned char *wbase = smem_raw + ((((size_t)(nb + 2) * 4) + 15) & ~(size_t)15) + (size_t)warp * pc_warp_bytes(true, nlay);
+    float4 *s_jf = reinterpret_cast<float4 *>(wbase);
+    int *s_jidx = reinterpret_cast<int *>(s_jf + PC_FBUF);
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(s_jidx + PC_FBUF);
+    PcLayer *lay = reinterpret_cast<PcLayer *>(wbase + (size_t)PC_FBUF * 20 + (size_t)PC_QCAP * 8);
+    for (int k = threadIdx.x; k < nb + 2; k += blockDim.x)
+        s_tab[k] = k == 0 ? __int_as_float(0x7f800000) : (k <= nb ? __double2float_rn(p.job.thr_b[k]) : __int_as_float(0xff800000));
+    __syncthreads();
+    PcTables T{};
+    T.na = na; T.cut = p.job.cut_bits;
+    const float t2max = 32.0f;
+    T.pad_x = p.job.maxdist * 1.001f + 3.0f * t2max;
+    PdfConsts C;
+    C.vx = __double2float_rn(p.job.ref_vec[0]); C.vy = __double2float_rn(p.job.ref_vec[1]); C.vz = __double2float_rn(p.job.ref_vec[2]);
+    C.tab = (unsigned int)__cvta_generic_to_shared(s_tab);
+    C.nb = nb; C.steps = 1;
+    while ((1 << C.steps) <= nb) ++C.steps;
+    C.e_a = 1.2e-6f;
+    const double cut_d2 = __longlong_as_double((long long)T.cut) * (1.0 + 1e-12);
+    const float cutf = (float)fmin(cut_d2 * (1.0 + 1e-6), 3.0e38);
+    const unsigned int ntiles = min(*ntiles_ptr, tile_cap);
+    if (*ntiles_ptr > tile_cap && threadIdx.x == 0 && blockIdx.x == 0) atomicOr(p.flags + 1, 1u);
+    const long long n_items = (long long)ntiles * nzg;
+    const int gx = go.g[0], gy = go.g[1], gz = go.g[2];
+    unsigned int it_all = 0;
+    unsigned long long st_all = 0, g_within = 0, g_oob = 0;
+    for (;;) {
+        st_all += it_all; it_all = 0;
+        __syncwarp();
+        unsigned int w = 0;
+        if (lane == 0) w = atomicAdd(work_counter, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        const long long item = (long long)w * p.tshard_count + p.tshard_rank;
+        if (item >= n_items) break;
+        const PaTile tl = tiles[item / nzg];
+        const int zg = (int)(item % nzg);
+        const int z0 = (int)((long long)gz * zg / nzg), z1 = (int)((long long)gz * (zg + 1) / nzg);
+        if (z0 == z1) continue;
+        double p1x[PC_RI], p1y[PC_RI], p1z[PC_RI], q1x[PC_RI], q1y[PC_RI], q1z[PC_RI];
+        const long long ibase = (long long)tl.frame * gi.nmol;
+#pragma unroll
+        for (int r = 0; r < PC_RI; ++r) {
+            const int k = pc_kidx(r), kk = min(k, tl.count - 1);
+            q1x[r] = gi.sx[ibase + tl.begin + kk]; q1y[r] = gi.sy[ibase + tl.begin + kk]; q1z[r] = gi.sz[ibase + tl.begin + kk];
+            p1x[r] = q1x[r]; p1y[r] = q1y[r]; p1z[r] = q1z[r];
+        }
+        double blox = fmin(q1x[0], q1x[1]), bloy = fmin(q1y[0], q1y[1]), bloz = fmin(q1z[0], q1z[1]);
+        double bhix = fmax(q1x[0], q1x[1]), bhiy = fmax(q1y[0], q1y[1]), bhiz = fmax(q1z[0], q1z[1]);
+        blox = pc_warp_min(blox); bloy = pc_warp_min(bloy); bloz = pc_warp_min(bloz);
+        bhix = pc_warp_max(bhix); bhiy = pc_warp_max(bhiy); bhiz = pc_warp_max(bhiz);
+        const double ox = 0.5 * (blox + bhix), oy = 0.5 * (bloy + bhiy), oz = 0.5 * (bloz + bhiz);
+        float xf[PC_RI], yf[PC_RI], zf[PC_RI];
+        float tile_t2 = 0.0f, hx = 0.0f, hy = 0.0f, hz = 0.0f;
+#pragma unroll
+        for (int r = 0; r < PC_RI; ++r) {
+            xf[r] = __double2float_rn(__dsub_rn(q1x[r], ox)); yf[r] = __double2float_rn(__dsub_rn(q1y[r], oy)); zf[r] = __double2float_rn(__dsub_rn(q1z[r], oz));
+            tile_t2 = fmaxf(tile_t2, __fmaf_ru(zf[r], zf[r], __fmaf_ru(yf[r], yf[r], __fmul_ru(xf[r], xf[r]))));
+            hx = fmaxf(hx, fabsf(xf[r])); hy = fmaxf(hy, fabsf(yf[r])); hz = fmaxf(hz, fabsf(zf[r]));
+        }
+        tile_t2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(tile_t2)));
+        hx = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hx)));
+        hy = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hy)));
+        hz = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(hz)));
+        __syncwarp();
+        for (int t = lane; t < nlay; t += 32) {
+            const int c = t < gx ? 0 : (t < gx + gy ? 1 : 2);
+            const int k = c == 0 ? t : (c == 1 ? t - gx : t - gx - gy);
+            const long long lj = ((long long)tl.frame * 3 + c) * go.gmax;
+            PcLayer cl;
+            if (go.lay_lo[lj + k] > go.lay_hi[lj + k]) { cl.mode = 0; cl.ca = cl.cb = 1; cl.pad = 0; cl.dmin2 = 3.0e38f; }
+            else cl = pc_classify(c == 0 ? blox : (c == 1 ? bloy : bloz), c == 0 ? bhix : (c == 1 ? bhiy : bhiz),
+                                  okey_inv(go.lay_lo[lj + k]), okey_inv(go.lay_hi[lj + k]), c == 0 ? p.box.L[0] : (c == 1 ? p.box.L[1] : p.box.L[2]));
+            if (cl.mode == 3) atomicOr(p.flags + 1, 1u);
+            lay[t] = cl;
+        }
+        __syncwarp();
+        const bool tile_f32 = tile_t2 <= t2max * t2max;
+        const float rmin2 = 4.0f * tile_t2 * 1.0001f + 1.0e-3f;
+        const float near_a = 1.25e-7f * sqrtf(tile_t2) + 1.0e-12f;
+        const float dead_r = __fadd_ru(p.dead_r, near_a);
+        const float dead_d2 = __fmul_ru(__fmul_ru(dead_r, dead_r), 1.000001f);
+        C.e_b = 2.6e-7f * __fsqrt_ru(tile_t2) + 1.0e-12f;
+        const long long jbase = (long long)tl.frame * go.nmol;
+        const int *cs = go.cell_start + (long long)tl.frame * (go.ncell + 1);
+        for (int cz = z0; cz < z1; ++cz) {
+            const PcLayer lz = lay[gx + gy + cz];
+            if (!(lz.dmin2 < cutf)) continue;
+            for (int cy = 0; cy < gy; ++cy) {
+                const PcLayer ly = lay[gx + cy];
+                const float dyz2 = lz.dmin2 + ly.dmin2;
+                if (!(dyz2 < cutf)) continue;
+                const int *row = cs + ((long long)cz * gy + cy) * gx;
+                int cx = 0;
+                while (cx < gx) {
+                    const PcLayer lx = lay[cx];
+                    if (!(dyz2 + lx.dmin2 < cutf)) { ++cx; continue; }
+                    const bool nearr = !(dyz2 + lx.dmin2 >= rmin2);
+                    int ce = cx;
+                    while (ce + 1 < gx) {
+                        const PcLayer ln = lay[ce + 1];
+                        if (ln.mode != lx.mode || ln.ca != lx.ca || ln.cb != lx.cb || !(dyz2 + ln.dmin2 < cutf)) break;
+                        if (tile_f32 && (!(dyz2 + ln.dmin2 >= rmin2) != nearr)) break;
+                        ++ce;
+                    }
+                    const int jb = row[cx], je = row[ce + 1];
+                    cx = ce + 1;
+                    if (jb >= je) continue;
+                    const double Lx = p.box.L[0], Ly = p.box.L[1], Lz = p.box.L[2];
+                    const double sxa = (double)(lx.ca - 1) * Lx, sxb = (double)(lx.cb - 1) * Lx;
+                    const double sya = (double)(ly.ca - 1) * Ly, syb = (double)(ly.cb - 1) * Ly;
+                    const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
+                    const bool single = lx.mode <= 1 && ly.mode <= 1 && lz.mode <= 1;
+                    if (tile_f32 && single) {
+                        if (nearr) pc_segment_pdf<true, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, queue, dead_d2, it_all, g_within, g_oob);
+                        else pc_segment_pdf<false, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, queue, dead_d2, it_all, g_within, g_oob);
+                    } else {
+                        pc_segment_pdf64<VERIFY>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, queue, it_all, g_within, g_oob);
+                    }
+                }
+            }
+        }
+    }
+    const int nbins = na * nb;
+    if (g_within) atomicAdd(&p.job.acc[nbins], g_within);
+    if (g_oob) atomicAdd(&p.job.acc[nbins + 1], g_oob);
+    if (p.kstats && lane == 0) { st_all += it_all; if (st_all) atomicAdd(p.kstats + 4, st_all * 128ull); }
+}
+
+// ---------------------------------------------------------------------------
 // Cell-sorted GENERAL kernel (2-D pdf, cdf, centre of charge, any reference vector).  Same tiles,
 // same per-run image classification and cutoff pruning as above; a pair inside the cutoff gets the
 // literal evaluation (pa_eval_pair_exact) through its original slots.  With cutoffs well below L/2
@@ -1541,6 +1904,24 @@ int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
 #undef PC_LAUNCH3
 #undef PC_LAUNCH2
 #undef PC_LAUNCH
+    return (int)cudaGetLastError();
+}
+
+int pa_launch_pdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
+                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = ((((size_t)(p.job.bin_b + 2) * 4) + 15) & ~(size_t)15) + (size_t)PC_WARPS * pc_warp_bytes(true, go.g[0] + go.g[1] + go.g[2]) + 16;
+    cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
+#define PDF_LAUNCH(V_)                                                                                          \
+    do {                                                                                                        \
+        int occ = 1;                                                                                            \
+        cudaFuncSetAttribute(pa_pdf_cells_kernel<V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_pdf_cells_kernel<V_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
+        pa_pdf_cells_kernel<V_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+    } while (0)
+    if (p.verify_fail) PDF_LAUNCH(true); else PDF_LAUNCH(false);
+#undef PDF_LAUNCH
     return (int)cudaGetLastError();
 }
 

@@ -141,6 +141,9 @@ int pa_launch_build_tiles(const PaCellGrid &g, int nframes, bool chunks, PaTile 
 int pa_launch_rdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
                         unsigned int tile_cap, unsigned int *work_counter, int nzg, int variant, int sm_count, void *stream,
                         void *ev_f32_begin, void *ev_f32_end);   // optional CUDA events around the float32 launch (the dominant kernel)
+// 2-D pdf jobs (distance x polar angle) on warp tiles with both classes bracketed in float32 (see pa_cells.cu)
+int pa_launch_pdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
+                        unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream);
 int pa_launch_general_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid &go, const PaTile *tiles, const unsigned int *ntiles,
                             unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream);
 void pa_cell_grid_dims(int nmol, int g[3]);

@@ -682,7 +682,26 @@ int pa_session_run_frames(pa_session *s, int32_t first, int32_t count)
         len = ((len + PA_J_CHUNK - 1) / PA_J_CHUNK) * PA_J_CHUNK;
         p.jsplit_len = len;
         p.n_jsplits = (p.nobs + len - 1) / len;
-        if (pl.cells && !js.fast) {
+        double cut_d;
+        memcpy(&cut_d, &js.dj.cut_bits, 8);
+        const bool pdf_f32 = pl.cells && !js.fast && !s->force_general && js.job.mode == PA_MODE_PDF && !js.job.use_coc &&
+                             js.cells_variant == 0 && !(s->exec.flags & PA_EXEC_NO_F32) && cut_d < s->box.max_dist_sq &&
+                             s->types[r].nmol < (1 << 24) && s->types[o].nmol < (1 << 24);
+        if (pdf_f32) {
+            // 2-D pdf job on warp tiles, both classes bracketed in float32 (pa_pdf_cells_kernel)
+            TypeGrid &gr = s->grids[r];
+            if (!gr.wtiles_ready) {
+                PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, true, gr.wtiles, gr.counters + 2, gr.row_off, gr.wtile_cap, s->s_compute));
+                gr.wtiles_ready = true;
+                s->stats.kernel_launches += 3;
+            }
+            const long long tiles_est = std::max<long long>(1, (long long)count * (p.nref / 60 + (long long)gr.g.g[1] * gr.g.g[2]));
+            long long nzg = (40ll * s->sm_count * 16 + tiles_est - 1) / tiles_est;
+            nzg = std::max<long long>(1, std::min<long long>(nzg, s->grids[o].g.g[2]));
+            PA_CK((cudaError_t)pa_launch_pdf_cells(p, gr.g, s->grids[o].g, gr.wtiles, gr.counters + 2, gr.wtile_cap, gr.counters + 1,
+                                                   (int)nzg, s->sm_count, s->s_compute));
+            s->stats.kernel_launches += 1;
+        } else if (pl.cells && !js.fast) {
             TypeGrid &gr = s->grids[r];
             if (!gr.tiles_ready) {
                 PA_CK((cudaError_t)pa_launch_build_tiles(gr.g, count, false, gr.tiles, gr.counters, gr.row_off, gr.tile_cap, s->s_compute));

@@ -320,9 +320,14 @@ def test_cell_sorted_general_kernel(name, kw, oracle):
     reqs = [dict(mode="pdf", vec=(1, 1, 0), ref_type=1, obs_type=2, bin_a=24, bin_b=12, maxdist=9.0),
             dict(mode="cdf", vec=(0, 0, 1), ref_type=2, obs_type=-1, bin_a=30, bin_b=30, maxdist=11.5, weigh_charge=True),
             dict(mode="pdf", vec=(0, 0, 1), ref_type=1, obs_type=1, bin_a=300, bin_b=300, maxdist=8.0),     # 90 000 bins: global atomics
-            dict(mode="pdf", vec=(0, 0, 1), ref_type=2, obs_type=1, bin_a=50, bin_b=1, maxdist=7.0, use_coc=True)]
+            dict(mode="pdf", vec=(0, 0, 1), ref_type=2, obs_type=1, bin_a=50, bin_b=1, maxdist=7.0, use_coc=True),
+            # cutoff L/2: runs with two candidate images (fp64 segment of the float32 2-D kernel), 1000 angle bins, a skew
+            # reference vector, weights
+            dict(mode="pdf", vec=(2, -1, 1), ref_type=1, obs_type=-1, bin_a=40, bin_b=1000, maxdist_optimize=True, weigh_charge=True)]
     pjobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, **r)) for r in reqs]
-    api.histogram_multi(traj, pjobs)                              # warm-up: the first launch of a kernel includes its lazy load
+    # warm-up (the first launch of a kernel includes its lazy load) with the VERIFY hook: every pair the float32 2-D kernel
+    # bins without the literal evaluation is re-evaluated literally on the device and must land in the same bin
+    api.histogram_multi(traj, pjobs, api.make_exec(flags=VERIFY))
     cells = api.histogram_multi(traj, pjobs)
     api.histogram_multi(traj, pjobs, api.make_exec(flags=capi.PA_EXEC_NO_CELLS))
     brute = api.histogram_multi(traj, pjobs, api.make_exec(flags=capi.PA_EXEC_NO_CELLS))
@@ -330,7 +335,7 @@ def test_cell_sorted_general_kernel(name, kw, oracle):
     for k in range(len(pjobs)):
         assert np.array_equal(cells[0][k], brute[0][k]) and cells[1][k] == brute[1][k] and cells[2][k] == brute[2][k], (name, k)
     if name == "clustered":
-        for k in (0, 1):
+        for k in (0, 1, 4):
             h0, w0, o0 = oracle.histogram(traj, pjobs[k])
             assert np.array_equal(cells[0][k], h0) and (int(cells[1][k]), int(cells[2][k])) == (w0, o0), (name, k)
     if name == "uniform":
