@@ -33,6 +33,9 @@
 #define PC_PREFETCH 0               // float32 launch: load the candidates of the next staging step one step ahead (measured:
                                     // 212 ms instead of 203 ms per 1M-atom frame -- the six extra registers cost more than the latency)
 #endif
+#ifndef PDF_MINB
+#define PDF_MINB 4                  // resident CTAs per SM the float32 2-D launch is compiled for
+#endif
 #ifndef PC_MINB
 #define PC_MINB 6                   // resident CTAs per SM the float32 launch is compiled for (80 registers per thread)
 #endif
@@ -1217,8 +1220,8 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? PC_MINB : 0) pa_rdf_ce
 //            r within ~1e-4 |T| of zero, are never decided here).  E = 1.2e-6 + 2.6e-7 |T| / r~ covers that with 5 %
 //            to spare plus 1e-7 for the float32 rounding of the threshold table and of dot~ +- E; the reference's own
 //            fp64 normalisation and the wrap-shift bookkeeping of its link vector differ from the exact quotient by
-//            < 1e-12.  The class c found by binary search in the float table is accepted when the whole interval
-//            [dot~ - E, dot~ + E] lies inside (thr_b[c+1], thr_b[c]].
+//            < 1e-12.  A class c seeded by an approximate acos is accepted when the whole interval
+//            [dot~ - E, dot~ + E] lies inside (thr_b[c+1], thr_b[c]] of the float threshold table.
 // A pair whose a- or b-class is not certain, whose b-class would be bin_count_b (polar angle pi: out of bounds), or
 // that may be the molecule itself goes to the warp's queue and is decided by pa_eval_pair_exact from the original
 // slots (the literal evaluation every other kernel uses), so the result is bit-identical by construction.  Runs that
@@ -1230,21 +1233,28 @@ struct PdfConsts {
     float vx, vy, vz;          // reference vector, float32
     float e_a, e_b;            // E = e_a + e_b / r~
     unsigned int tab;          // shared address of the float threshold table T[0..nb+1] (T[0] = +inf, T[nb+1] = -inf)
-    int nb, steps;             // bin_count_b, binary-search steps (2^steps > nb)
+    int nb;                    // bin_count_b
+    float inv_step_b;
 };
 
-// largest c in [0, nb] with x <= T[c] (T decreasing, T[0] = +inf)
-static __device__ __forceinline__ int pdf_class(const PdfConsts &C, float x)
+// candidate b-class of a dot product: floor(acos~(x) / step_b) from a 4-term approximation of acos (|error| < 7e-5 rad,
+// Abramowitz & Stegun 4.4.45), moved by at most one class towards the interval of the float threshold table that holds
+// x (T decreasing, T[0] = +inf, T[nb+1] = -inf).  Only a seed: the caller accepts it when [x - E, x + E] lies inside
+// (T[c+1], T[c]] and sends the pair to the literal evaluation otherwise, so a wrong seed costs time, never a count.
+static __device__ __forceinline__ int pdf_class(const PdfConsts &C, float x, float &t_hi, float &t_lo)
 {
-    int c = 0;
-    for (int h = 1 << (C.steps - 1); h > 0; h >>= 1) {
-        const int t = c + h;
-        if (t <= C.nb) {
-            float th;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(th) : "r"(C.tab + 4u * (unsigned)t));
-            if (x <= th) c = t;
-        }
-    }
+    const float ax = fminf(fabsf(x), 1.0f);
+    float s;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(1.0f - ax));
+    float th = s * __fmaf_rn(__fmaf_rn(__fmaf_rn(-0.0187293f, ax, 0.0742610f), ax, -0.2121144f), ax, 1.5707288f);
+    if (x < 0.0f) th = 3.14159265f - th;
+    int c = min(max((int)(th * C.inv_step_b), 0), C.nb - 1);
+    float t0, t1;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t0) : "r"(C.tab + 4u * (unsigned)c));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t1) : "r"(C.tab + 4u * (unsigned)(c + 1)));
+    c += (x <= t1) ? 1 : ((x > t0 && c > 0) ? -1 : 0);
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t_hi) : "r"(C.tab + 4u * (unsigned)c));
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t_lo) : "r"(C.tab + 4u * (unsigned)(c + 1)));
     return c;
 }
 
@@ -1345,10 +1355,8 @@ static __device__ __forceinline__ void pc_segment_pdf(const PaPass &p, const PaC
                     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(rt));
                     const float dot = num * rinv;
                     const float E = __fmaf_rn(C.e_b, rinv, C.e_a);
-                    const int c = pdf_class(C, dot);
                     float t_hi, t_lo;                                             // thr_b[c] >= dot > thr_b[c+1] must hold with margin E
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t_hi) : "r"(C.tab + 4u * (unsigned)c));
-                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t_lo) : "r"(C.tab + 4u * (unsigned)(c + 1)));
+                    const int c = pdf_class(C, dot, t_hi, t_lo);
                     // (|dot| + E <= 1: next to +-1 the reference's fp64 dot product can exceed 1 by an ulp -> ACOS = NaN -> out of bounds)
                     const bool sure = tlo == thi && tlo < tlim && c < C.nb && E < 1.0e-3f && (dot + E <= t_hi) && (dot - E > t_lo) &&
                                       (fabsf(dot) + E <= 1.0f);
@@ -1431,7 +1439,7 @@ static __device__ __forceinline__ void pc_segment_pdf64(const PaPass &p, const P
 }
 
 template <bool VERIFY>
-__global__ void __launch_bounds__(PC_THREADS, 4) pa_pdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
+__global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
                                                                      const unsigned int *ntiles_ptr, unsigned int tile_cap, unsigned int *work_counter, int nzg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1454,8 +1462,7 @@ __global__ void __launch_bounds__(PC_THREADS, 4) pa_pdf_cells_kernel(const __gri
     PdfConsts C;
     C.vx = __double2float_rn(p.job.ref_vec[0]); C.vy = __double2float_rn(p.job.ref_vec[1]); C.vz = __double2float_rn(p.job.ref_vec[2]);
     C.tab = (unsigned int)__cvta_generic_to_shared(s_tab);
-    C.nb = nb; C.steps = 1;
-    while ((1 << C.steps) <= nb) ++C.steps;
+    C.nb = nb; C.inv_step_b = 1.0f / p.job.step_b;
     C.e_a = 1.2e-6f;
     const double cut_d2 = __longlong_as_double((long long)T.cut) * (1.0 + 1e-12);
     const float cutf = (float)fmin(cut_d2 * (1.0 + 1e-6), 3.0e38);

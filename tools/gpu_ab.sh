@@ -4,7 +4,7 @@
 TAG=$1; shift
 mkdir -p gpurun_out
 cp prealpha_b200/libprealpha_b200.so /tmp/lib_A.so
-run() { timeout 600 python bench.py --steps 6 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_$1.json 2> gpurun_out/${TAG}_$1.err; echo "$1 rc=$?"; }
+run() { timeout 600 python bench.py ${BENCH_ARGS:---steps 6 --warmup 3} --no-cpu-baseline > gpurun_out/${TAG}_$1.json 2> gpurun_out/${TAG}_$1.err; echo "$1 rc=$?"; }
 run A
 n=0
 for EXTRA in "$@"; do
@@ -21,7 +21,7 @@ flags = ["(shipped)"] + sys.argv[1:]
 for n, f in zip(names, flags):
     try:
         d = json.load(open("gpurun_out/${TAG}_%s.json" % n)); r = d["roofline"]
-        print(n, f, "ms/step %.1f value %.3e e2e %.3e (%.1f ms) frac %.3f useful %.3f atomics/step %.3e dom_ms %.1f" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["ms_per_step"], r["frac"], r["useful_frac"], r["atomics_per_step_per_gpu"], r["ms_per_launch"]))
+        print(n, f, "ms/step %.1f value %.3e e2e %.3e (%.1f ms)" % (d["ms_per_step"], d["value"], d["e2e"]["value"], d["e2e"]["ms_per_step"]), r.get("frac"), r.get("useful_frac"))
     except Exception as e:
         print(n, f, "unreadable", e)
 PY
