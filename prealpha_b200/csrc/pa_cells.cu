@@ -1287,27 +1287,69 @@ static __device__ __noinline__ void pdf_drain(const PaPass &p, const PaCellGrid 
     __syncwarp();
 }
 
+// Pair loop in two phases, because only about half of the pairs that survive the staging filter are inside the cutoff
+// and the classification costs ~60 instructions: phase 1 evaluates d2~ for the 4 pairs of a lane's iteration (packed)
+// and appends the pairs that may be inside the cutoff -- (dx~, dy~, dz~, reference index | observed position) -- to a
+// stack of the warp (ballot + popc); whenever the stack holds 32 entries or more, phase 2 pops one entry per lane and
+// classifies it at full lane occupancy.  A popped pair that is not certain is evaluated literally on the spot (~1e-3
+// of the pairs).
+#define PDF_STACK 160               // 31 left over + 4 x 32 appended by one iteration
+template <bool NEAR, bool VERIFY>
+static __device__ __forceinline__ void pdf_classify(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl, const float4 e,
+                                                    const PcTables &T, const PdfConsts &C, float near_a, long long jbase,
+                                                    unsigned long long &g_within, unsigned long long &g_oob)
+{
+    const int na = T.na;
+    const unsigned int tlim = 0x4B000000u + (unsigned)na;
+    const float d2 = __fmaf_rn(e.z, e.z, __fmaf_rn(e.y, e.y, __fmul_rn(e.x, e.x)));
+    float rt, rinv;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(d2));
+    unsigned long long rr = pc_pack(rt, rt);
+    if (NEAR) rr = pc_add2(rr, pc_pack(-near_a, near_a));
+    const unsigned long long tt = pc_fma2_rm(rr, pc_pack(p.f32_lo, p.f32_hi), pc_pack(8388608.0f, 8388608.0f));
+    const unsigned int tlo = __float_as_uint(pc_lo(tt)), thi = __float_as_uint(pc_hi(tt));
+    if (tlo > tlim) return;                                                   // beyond the cutoff (lower bracket): never counted
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(rt));
+    const float dot = __fmaf_rn(e.z, C.vz, __fmaf_rn(e.y, C.vy, __fmul_rn(e.x, C.vx))) * rinv;
+    const float E = __fmaf_rn(C.e_b, rinv, C.e_a);
+    float t_hi, t_lo;                                                         // thr_b[c] >= dot > thr_b[c+1] must hold with margin E
+    const int c = pdf_class(C, dot, t_hi, t_lo);
+    // (|dot| + E <= 1: next to +-1 the reference's fp64 dot product can exceed 1 by an ulp -> ACOS = NaN -> out of bounds)
+    const bool sure = tlo == thi && tlo < tlim && c < C.nb && E < 1.0e-3f && (dot + E <= t_hi) && (dot - E > t_lo) && (fabsf(dot) + E <= 1.0f);
+    const unsigned int id = __float_as_uint(e.w);
+    if (sure && !VERIFY) {
+        atomicAdd(&p.job.acc[c * na + (int)(tlo - 0x4B000000u)], (unsigned long long)p.weight);
+        ++g_within;
+        return;
+    }
+    // literal evaluation from the original slots
+    const long long iref = (long long)tl.frame * gi.nmol + tl.begin + (int)(id & 63u);
+    const int io = gi.sorig[iref], jo = go.sorig[jbase + (long long)(id >> 6)];
+    const bool self = p.same_type && io == jo;                                // the molecule itself (Distribution:778)
+    const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
+    int bin = -1;
+    const int st = self ? 0 : pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
+    if (VERIFY && sure && !(st == 1 && bin == c * na + (int)(tlo - 0x4B000000u))) atomicAdd(p.verify_fail, 1u);
+    if (st == 1) { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
+    else if (st == 2) ++g_oob;
+}
+
 template <bool NEAR, bool VERIFY>
 static __device__ __forceinline__ void pc_segment_pdf(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                       const float (&xf)[PC_RI], const float (&yf)[PC_RI], const float (&zf)[PC_RI],
                                                       float hx, float hy, float hz, double ox, double oy, double oz,
                                                       long long jbase, int jb, int je, double sxa, double sya, double sza,
                                                       float4 *s_jf, int *s_jidx, const PcTables &T, const PdfConsts &C, float near_a,
-                                                      unsigned long long *queue, float dead_d2,
+                                                      float4 *stack, float dead_d2,
                                                       unsigned int &it_all, unsigned long long &g_within, unsigned long long &g_oob)
 {
-    int qn = 0;
+    int sn = 0;                                          // entries on the warp's stack (warp-uniform)
     const int lane = threadIdx.x & 31;
     const unsigned int lane_lt = (1u << lane) - 1u;
     const unsigned long long X01 = pc_pack(xf[0], xf[1]), Y01 = pc_pack(yf[0], yf[1]), Z01 = pc_pack(zf[0], zf[1]);
-    const unsigned long long F2 = pc_pack(p.f32_lo, p.f32_hi), M2 = pc_pack(8388608.0f, 8388608.0f), A2 = pc_pack(-near_a, near_a);
-    const int na = T.na;
-    const unsigned int tlim = 0x4B000000u + (unsigned)na;
     const unsigned int kmask = (pc_kidx(0) < tl.count ? 0x5u : 0u) | (pc_kidx(1) < tl.count ? 0xAu : 0u);
     const unsigned int a_jf = (unsigned int)__cvta_generic_to_shared(s_jf);
-    const long long ibase = (long long)tl.frame * gi.nmol + tl.begin;
     const double cxa = __dsub_rn(sxa, ox), cya = __dsub_rn(sya, oy), cza = __dsub_rn(sza, oz);
-    const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
     int fill = 0;
     for (int jc = jb; jc < je; jc += 32) {
         {
@@ -1332,70 +1374,43 @@ static __device__ __forceinline__ void pc_segment_pdf(const PaPass &p, const PaC
         const unsigned int a_end = a_jf + (unsigned)fill * 16u;
         for (unsigned int aj = a_jf; aj < a_end; aj += 32u) {
             const int jj = (int)((aj - a_jf) >> 4);
-            unsigned int need = 0u;
-            int bins[4];
+            const unsigned int valid = kmask & (jj + 1 < fill ? 0xFu : 0x3u);  // real reference slots, not the padded observed slot
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const float4 w = pc_lds_f32x4(aj + 16u * u);
                 const unsigned long long dx = pc_sub2(pc_pack(w.x, w.x), X01), dy = pc_sub2(pc_pack(w.y, w.y), Y01), dz = pc_sub2(pc_pack(w.z, w.z), Z01);
                 const unsigned long long d2p = pc_fma2(dz, dz, pc_fma2(dy, dy, pc_mul2(dx, dx)));
-                const unsigned long long np = pc_fma2(dz, pc_pack(C.vz, C.vz), pc_fma2(dy, pc_pack(C.vy, C.vy), pc_mul2(dx, pc_pack(C.vx, C.vx))));
+                const unsigned int jid = (unsigned int)s_jidx[jj + u] << 6;
 #pragma unroll
                 for (int r = 0; r < PC_RI; ++r) {
                     const int q = u * PC_RI + r;
-                    const float d2 = r ? pc_hi(d2p) : pc_lo(d2p), num = r ? pc_hi(np) : pc_lo(np);
-                    float rt, rinv;
-                    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(d2));
-                    unsigned long long rr = pc_pack(rt, rt);
-                    if (NEAR) rr = pc_add2(rr, A2);
-                    const unsigned long long tt = pc_fma2_rm(rr, F2, M2);
-                    const unsigned int tlo = __float_as_uint(pc_lo(tt)), thi = __float_as_uint(pc_hi(tt));
-                    bins[q] = -1;
-                    if (tlo > tlim) continue;                                     // beyond the cutoff (lower bracket): never counted
-                    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(rt));
-                    const float dot = num * rinv;
-                    const float E = __fmaf_rn(C.e_b, rinv, C.e_a);
-                    float t_hi, t_lo;                                             // thr_b[c] >= dot > thr_b[c+1] must hold with margin E
-                    const int c = pdf_class(C, dot, t_hi, t_lo);
-                    // (|dot| + E <= 1: next to +-1 the reference's fp64 dot product can exceed 1 by an ulp -> ACOS = NaN -> out of bounds)
-                    const bool sure = tlo == thi && tlo < tlim && c < C.nb && E < 1.0e-3f && (dot + E <= t_hi) && (dot - E > t_lo) &&
-                                      (fabsf(dot) + E <= 1.0f);
-                    if (sure) bins[q] = c * na + (int)(tlo - 0x4B000000u);
-                    else need |= 1u << q;
+                    // d2~ >= dead_d2: the lower class bracket is beyond the cutoff, the pair can never be counted
+                    const bool in = ((valid >> q) & 1u) && (r ? pc_hi(d2p) : pc_lo(d2p)) < dead_d2;
+                    const unsigned int m = __ballot_sync(0xffffffffu, in);
+                    if (in)
+                        stack[sn + __popc(m & lane_lt)] = make_float4(r ? pc_hi(dx) : pc_lo(dx), r ? pc_hi(dy) : pc_lo(dy), r ? pc_hi(dz) : pc_lo(dz),
+                                                                      __uint_as_float(jid | (unsigned int)pc_kidx(r)));
+                    sn += __popc(m);
                 }
             }
-            need &= kmask;
-            if (jj + 1 >= fill) need &= 0x3u;                                     // the padded slot of an odd buffer
-#pragma unroll
-            for (int q = 0; q < 4; ++q) if (!((kmask >> q) & 1u) || (q >= 2 && jj + 1 >= fill)) bins[q] = -1;
-            if (VERIFY) {
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (bins[q] < 0) continue;
-                    const int r = q % PC_RI, u = q / PC_RI;
-                    const int io = gi.sorig[ibase + pc_kidx(r)], jo = go.sorig[jbase + s_jidx[jj + u]];
-                    int bin = -1;
-                    const int st = pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
-                    if (!(st == 1 && bin == bins[q]) || (p.same_type && io == jo)) atomicAdd(p.verify_fail, 1u);
-                }
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (bins[q] >= 0) { atomicAdd(&p.job.acc[bins[q]], (unsigned long long)p.weight); ++g_within; }
-            const unsigned int m = __ballot_sync(0xffffffffu, need != 0u);
-            if (m != 0u) {
-                const int add = __popc(m);
-                if (qn + add > PC_QCAP) { pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob); qn = 0; }
-                if (need)
-                    queue[qn + __popc(m & lane_lt)] = (unsigned long long)(unsigned int)s_jidx[jj] | ((unsigned long long)(unsigned int)s_jidx[jj + 1] << 24) |
-                                                      ((unsigned long long)lane << 48) | ((unsigned long long)need << 53);
-                qn += add;
+            while (sn >= 32) {
+                __syncwarp();
+                sn -= 32;
+                const float4 e = stack[sn + lane];
+                __syncwarp();
+                pdf_classify<NEAR, VERIFY>(p, go, gi, tl, e, T, C, near_a, jbase, g_within, g_oob);
             }
         }
         fill = 0;
         __syncwarp();
     }
-    if (qn > 0) pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob);
+    // the brackets of the entries depend on this run (NEAR): empty the stack before the next run
+    __syncwarp();
+    if (lane < sn) {
+        const float4 e = stack[lane];
+        pdf_classify<NEAR, VERIFY>(p, go, gi, tl, e, T, C, near_a, jbase, g_within, g_oob);
+    }
+    __syncwarp();
 }
 
 // runs that are not float32-eligible: every pair in fp64 (two candidate images per component), pairs inside the cutoff
@@ -1447,11 +1462,13 @@ __global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nlay = go.g[0] + go.g[1] + go.g[2];
     float *s_tab = reinterpret_cast<float *>(smem_raw);                                   // nb + 2 floats
-    unsigned char *wbase = smem_raw + ((((size_t)(nb + 2) * 4) + 15) & ~(size_t)15) + (size_t)warp * pc_warp_bytes(true, nlay);
+    const size_t warp_bytes = pc_warp_bytes(true, nlay) + (size_t)PDF_STACK * 16;
+    unsigned char *wbase = smem_raw + ((((size_t)(nb + 2) * 4) + 15) & ~(size_t)15) + (size_t)warp * warp_bytes;
     float4 *s_jf = reinterpret_cast<float4 *>(wbase);
-    int *s_jidx = reinterpret_cast<int *>(s_jf + PC_FBUF);
-    unsigned long long *queue = reinterpret_cast<unsigned long long *>(s_jidx + PC_FBUF);
-    PcLayer *lay = reinterpret_cast<PcLayer *>(wbase + (size_t)PC_FBUF * 20 + (size_t)PC_QCAP * 8);
+    float4 *stack = s_jf + PC_FBUF;                                                        // PDF_STACK entries
+    int *s_jidx = reinterpret_cast<int *>(stack + PDF_STACK);
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(s_jidx + PC_FBUF);  // fp64 segments (pc_segment_pdf64)
+    PcLayer *lay = reinterpret_cast<PcLayer *>(wbase + (size_t)PC_FBUF * 20 + (size_t)PDF_STACK * 16 + (size_t)PC_QCAP * 8);
     for (int k = threadIdx.x; k < nb + 2; k += blockDim.x)
         s_tab[k] = k == 0 ? __int_as_float(0x7f800000) : (k <= nb ? __double2float_rn(p.job.thr_b[k]) : __int_as_float(0xff800000));
     __syncthreads();
@@ -1559,8 +1576,8 @@ __global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(cons
                     const double sza = (double)(lz.ca - 1) * Lz, szb = (double)(lz.cb - 1) * Lz;
                     const bool single = lx.mode <= 1 && ly.mode <= 1 && lz.mode <= 1;
                     if (tile_f32 && single) {
-                        if (nearr) pc_segment_pdf<true, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, queue, dead_d2, it_all, g_within, g_oob);
-                        else pc_segment_pdf<false, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, queue, dead_d2, it_all, g_within, g_oob);
+                        if (nearr) pc_segment_pdf<true, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, stack, dead_d2, it_all, g_within, g_oob);
+                        else pc_segment_pdf<false, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, stack, dead_d2, it_all, g_within, g_oob);
                     } else {
                         pc_segment_pdf64<VERIFY>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, queue, it_all, g_within, g_oob);
                     }
@@ -1918,7 +1935,8 @@ int pa_launch_pdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
                         unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = ((((size_t)(p.job.bin_b + 2) * 4) + 15) & ~(size_t)15) + (size_t)PC_WARPS * pc_warp_bytes(true, go.g[0] + go.g[1] + go.g[2]) + 16;
+    const size_t smem = ((((size_t)(p.job.bin_b + 2) * 4) + 15) & ~(size_t)15) +
+                        (size_t)PC_WARPS * (pc_warp_bytes(true, go.g[0] + go.g[1] + go.g[2]) + (size_t)PDF_STACK * 16) + 16;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
 #define PDF_LAUNCH(V_)                                                                                          \
     do {                                                                                                        \
