@@ -1308,7 +1308,10 @@ static __device__ __forceinline__ void pdf_classify(const PaPass &p, const PaCel
     if (NEAR) rr = pc_add2(rr, pc_pack(-near_a, near_a));
     const unsigned long long tt = pc_fma2_rm(rr, pc_pack(p.f32_lo, p.f32_hi), pc_pack(8388608.0f, 8388608.0f));
     const unsigned int tlo = __float_as_uint(pc_lo(tt)), thi = __float_as_uint(pc_hi(tt));
-    if (tlo > tlim) return;                                                   // beyond the cutoff (lower bracket): never counted
+    // beyond the cutoff: lower bracket above class na, or both brackets ON class na -- the job's cutoff sits within
+    // delta_top of the boundary of bin na and the brackets are wider than that, so a pair of true class na ("inside the
+    // cutoff, a-bin out of range") always has disagreeing brackets (same argument as VARIANT 0 of the RDF kernel)
+    if (tlo > tlim || (tlo == tlim && thi == tlim)) return;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(rt));
     const float dot = __fmaf_rn(e.z, C.vz, __fmaf_rn(e.y, C.vy, __fmul_rn(e.x, C.vx))) * rinv;
     const float E = __fmaf_rn(C.e_b, rinv, C.e_a);
