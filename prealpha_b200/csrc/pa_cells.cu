@@ -1235,6 +1235,7 @@ struct PdfConsts {
     unsigned int tab;          // shared address of the float threshold table T[0..nb+1] (T[0] = +inf, T[nb+1] = -inf)
     int nb;                    // bin_count_b
     float inv_step_b;
+    unsigned int hist;         // shared address of the CTA's 32-bit histogram [bin_a * bin_b | out of bounds], 0: global atomics
 };
 
 // candidate b-class of a dot product: floor(acos~(x) / step_b) from a 4-term approximation of acos (|error| < 7e-5 rad,
@@ -1260,7 +1261,7 @@ static __device__ __forceinline__ int pdf_class(const PdfConsts &C, float x, flo
 
 template <bool VERIFY>
 static __device__ __noinline__ void pdf_drain(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
-                                              const unsigned long long *queue, int count, long long jbase,
+                                              const unsigned long long *queue, int count, long long jbase, unsigned int hist,
                                               unsigned long long &g_within, unsigned long long &g_oob)
 {
     __syncwarp();
@@ -1280,8 +1281,13 @@ static __device__ __noinline__ void pdf_drain(const PaPass &p, const PaCellGrid 
             if (p.same_type && io == jo) continue;                       // the molecule itself (Distribution:778)
             int bin = 0;
             const int st = pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
-            if (st == 1) { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
-            else if (st == 2) ++g_oob;
+            if (st == 1) {
+                if (hist) pc_red(hist + 4u * (unsigned)bin);
+                else { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
+            } else if (st == 2) {
+                if (hist) pc_red(hist + 4u * (unsigned)(p.job.bin_a * p.job.bin_b));
+                else ++g_oob;
+            }
         }
     }
     __syncwarp();
@@ -1321,8 +1327,9 @@ static __device__ __forceinline__ void pdf_classify(const PaPass &p, const PaCel
     const bool sure = tlo == thi && tlo < tlim && c < C.nb && E < 1.0e-3f && (dot + E <= t_hi) && (dot - E > t_lo) && (fabsf(dot) + E <= 1.0f);
     const unsigned int id = __float_as_uint(e.w);
     if (sure && !VERIFY) {
-        atomicAdd(&p.job.acc[c * na + (int)(tlo - 0x4B000000u)], (unsigned long long)p.weight);
-        ++g_within;
+        const int b0 = c * na + (int)(tlo - 0x4B000000u);
+        if (C.hist) pc_red(C.hist + 4u * (unsigned)b0);
+        else { atomicAdd(&p.job.acc[b0], (unsigned long long)p.weight); ++g_within; }
         return;
     }
     // literal evaluation from the original slots
@@ -1333,8 +1340,13 @@ static __device__ __forceinline__ void pdf_classify(const PaPass &p, const PaCel
     int bin = -1;
     const int st = self ? 0 : pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
     if (VERIFY && sure && !(st == 1 && bin == c * na + (int)(tlo - 0x4B000000u))) atomicAdd(p.verify_fail, 1u);
-    if (st == 1) { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
-    else if (st == 2) ++g_oob;
+    if (st == 1) {
+        if (C.hist) pc_red(C.hist + 4u * (unsigned)bin);
+        else { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
+    } else if (st == 2) {
+        if (C.hist) pc_red(C.hist + 4u * (unsigned)(na * C.nb));
+        else ++g_oob;
+    }
 }
 
 template <bool NEAR, bool VERIFY>
@@ -1422,7 +1434,7 @@ template <bool VERIFY>
 static __device__ __forceinline__ void pc_segment_pdf64(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl,
                                                         const double (&p1x)[PC_RI], const double (&p1y)[PC_RI], const double (&p1z)[PC_RI],
                                                         long long jbase, int jb, int je, double sxa, double sxb, double sya, double syb, double sza, double szb,
-                                                        unsigned long long *queue, unsigned int &it_all, unsigned long long &g_within, unsigned long long &g_oob)
+                                                        unsigned long long *queue, unsigned int hist, unsigned int &it_all, unsigned long long &g_within, unsigned long long &g_oob)
 {
     int qn = 0;
     const int lane = threadIdx.x & 31;
@@ -1447,17 +1459,33 @@ static __device__ __forceinline__ void pc_segment_pdf64(const PaPass &p, const P
         const unsigned int m = __ballot_sync(0xffffffffu, need != 0u);
         if (m == 0u) continue;
         const int add = __popc(m);
-        if (qn + add > PC_QCAP) { pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob); qn = 0; }
+        if (qn + add > PC_QCAP) { pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, hist, g_within, g_oob); qn = 0; }
         if (need)
             queue[qn + __popc(m & lane_lt)] = (unsigned long long)(unsigned int)j | ((unsigned long long)(unsigned int)(j + 1 < je ? j + 1 : j) << 24) |
                                               ((unsigned long long)lane << 48) | ((unsigned long long)need << 53);
         qn += add;
     }
-    if (qn > 0) pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, g_within, g_oob);
+    if (qn > 0) pdf_drain<VERIFY>(p, go, gi, tl, queue, qn, jbase, hist, g_within, g_oob);
 }
 
-template <bool VERIFY>
-__global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
+// flush of the CTA's shared histogram by ONE warp while the others keep counting (atomic exchange), and at the end
+static __device__ void pdf_flush(const PaPass &p, unsigned int hist, int nbins, int first, int stride)
+{
+    unsigned long long within = 0;
+    for (int k = first; k < nbins + 1; k += stride) {
+        const unsigned int c = pc_exch_u32(hist + 4u * (unsigned)k);
+        if (!c) continue;
+        if (k < nbins) { atomicAdd(&p.job.acc[k], (unsigned long long)((long long)c * p.weight)); within += c; }
+        else atomicAdd(&p.job.acc[nbins + 1], (unsigned long long)c);
+    }
+    if (within) atomicAdd(&p.job.acc[nbins], within);
+}
+
+// SMEMH: one CTA of 16 warps per SM sharing a 32-bit histogram of all bins in shared memory (global 64-bit atomics of
+// 148 x 16 warps into the few thousand words of a 2-D histogram run at ~1e11/s and were the limit of the first version);
+// otherwise 4-warp CTAs and global atomics (histograms above ~40 000 bins).
+template <bool VERIFY, bool SMEMH>
+__global__ void __launch_bounds__(SMEMH ? 512 : PC_THREADS, SMEMH ? 1 : PDF_MINB) pa_pdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
                                                                      const unsigned int *ntiles_ptr, unsigned int tile_cap, unsigned int *work_counter, int nzg)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1465,8 +1493,10 @@ __global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nlay = go.g[0] + go.g[1] + go.g[2];
     float *s_tab = reinterpret_cast<float *>(smem_raw);                                   // nb + 2 floats
+    const int nbins = na * nb;
     const size_t warp_bytes = pc_warp_bytes(true, nlay) + (size_t)PDF_STACK * 16;
-    unsigned char *wbase = smem_raw + ((((size_t)(nb + 2) * 4) + 15) & ~(size_t)15) + (size_t)warp * warp_bytes;
+    unsigned int *s_hist = reinterpret_cast<unsigned int *>(smem_raw + ((((size_t)(nb + 2) * 4) + 15) & ~(size_t)15));   // nbins + 1 (SMEMH)
+    unsigned char *wbase = reinterpret_cast<unsigned char *>(s_hist) + (SMEMH ? ((((size_t)(nbins + 1) * 4) + 15) & ~(size_t)15) : 0) + (size_t)warp * warp_bytes;
     float4 *s_jf = reinterpret_cast<float4 *>(wbase);
     float4 *stack = s_jf + PC_FBUF;                                                        // PDF_STACK entries
     int *s_jidx = reinterpret_cast<int *>(stack + PDF_STACK);
@@ -1474,6 +1504,7 @@ __global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(cons
     PcLayer *lay = reinterpret_cast<PcLayer *>(wbase + (size_t)PC_FBUF * 20 + (size_t)PDF_STACK * 16 + (size_t)PC_QCAP * 8);
     for (int k = threadIdx.x; k < nb + 2; k += blockDim.x)
         s_tab[k] = k == 0 ? __int_as_float(0x7f800000) : (k <= nb ? __double2float_rn(p.job.thr_b[k]) : __int_as_float(0xff800000));
+    if (SMEMH) for (int k = threadIdx.x; k < nbins + 1; k += blockDim.x) s_hist[k] = 0u;
     __syncthreads();
     PcTables T{};
     T.na = na; T.cut = p.job.cut_bits;
@@ -1483,7 +1514,10 @@ __global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(cons
     C.vx = __double2float_rn(p.job.ref_vec[0]); C.vy = __double2float_rn(p.job.ref_vec[1]); C.vz = __double2float_rn(p.job.ref_vec[2]);
     C.tab = (unsigned int)__cvta_generic_to_shared(s_tab);
     C.nb = nb; C.inv_step_b = 1.0f / p.job.step_b;
+    C.hist = SMEMH ? (unsigned int)__cvta_generic_to_shared(s_hist) : 0u;
     C.e_a = 1.2e-6f;
+    const int nwarps = (int)(blockDim.x >> 5);
+    unsigned long long since_flush = 0;
     const double cut_d2 = __longlong_as_double((long long)T.cut) * (1.0 + 1e-12);
     const float cutf = (float)fmin(cut_d2 * (1.0 + 1e-6), 3.0e38);
     const unsigned int ntiles = min(*ntiles_ptr, tile_cap);
@@ -1542,6 +1576,12 @@ __global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(cons
             lay[t] = cl;
         }
         __syncwarp();
+        if (SMEMH) {
+            // 32-bit shared counters: the CTA's warps together add less than 2^31 between two flushes of any one of them
+            const unsigned long long item_pairs = (unsigned long long)PC_TILE * (unsigned long long)go.nmol;
+            if (since_flush + item_pairs > (0x7fffffffull / (unsigned)nwarps)) { pdf_flush(p, C.hist, nbins, lane, 32); since_flush = 0; }
+            since_flush += item_pairs;
+        }
         const bool tile_f32 = tile_t2 <= t2max * t2max;
         const float rmin2 = 4.0f * tile_t2 * 1.0001f + 1.0e-3f;
         const float near_a = 1.25e-7f * sqrtf(tile_t2) + 1.0e-12f;
@@ -1582,15 +1622,18 @@ __global__ void __launch_bounds__(PC_THREADS, PDF_MINB) pa_pdf_cells_kernel(cons
                         if (nearr) pc_segment_pdf<true, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, stack, dead_d2, it_all, g_within, g_oob);
                         else pc_segment_pdf<false, VERIFY>(p, go, gi, tl, xf, yf, zf, hx, hy, hz, ox, oy, oz, jbase, jb, je, sxa, sya, sza, s_jf, s_jidx, T, C, near_a, stack, dead_d2, it_all, g_within, g_oob);
                     } else {
-                        pc_segment_pdf64<VERIFY>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, queue, it_all, g_within, g_oob);
+                        pc_segment_pdf64<VERIFY>(p, go, gi, tl, p1x, p1y, p1z, jbase, jb, je, sxa, sxb, sya, syb, sza, szb, queue, C.hist, it_all, g_within, g_oob);
                     }
                 }
             }
         }
     }
-    const int nbins = na * nb;
     if (g_within) atomicAdd(&p.job.acc[nbins], g_within);
     if (g_oob) atomicAdd(&p.job.acc[nbins + 1], g_oob);
+    if (SMEMH) {
+        __syncthreads();
+        pdf_flush(p, C.hist, nbins, (int)threadIdx.x, (int)blockDim.x);
+    }
     if (p.kstats && lane == 0) { st_all += it_all; if (st_all) atomicAdd(p.kstats + 4, st_all * 128ull); }
 }
 
@@ -1938,17 +1981,22 @@ int pa_launch_pdf_cells(const PaPass &p, const PaCellGrid &gi, const PaCellGrid 
                         unsigned int tile_cap, unsigned int *work_counter, int nzg, int sm_count, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = ((((size_t)(p.job.bin_b + 2) * 4) + 15) & ~(size_t)15) +
-                        (size_t)PC_WARPS * (pc_warp_bytes(true, go.g[0] + go.g[1] + go.g[2]) + (size_t)PDF_STACK * 16) + 16;
+    const int nbins = p.job.bin_a * p.job.bin_b;
+    const size_t warp_bytes = pc_warp_bytes(true, go.g[0] + go.g[1] + go.g[2]) + (size_t)PDF_STACK * 16;
+    const size_t tab = (((size_t)(p.job.bin_b + 2) * 4) + 15) & ~(size_t)15;
+    const size_t smem_h = tab + ((((size_t)(nbins + 1) * 4) + 15) & ~(size_t)15) + 16 * warp_bytes + 16;     // 16 warps, shared histogram
+    const size_t smem_g = tab + (size_t)PC_WARPS * warp_bytes + 16;
+    const bool smemh = smem_h <= 200 * 1024;
     cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), st);
-#define PDF_LAUNCH(V_)                                                                                          \
+#define PDF_LAUNCH(V_, H_, THREADS_, SMEM_)                                                                     \
     do {                                                                                                        \
         int occ = 1;                                                                                            \
-        cudaFuncSetAttribute(pa_pdf_cells_kernel<V_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);  \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_pdf_cells_kernel<V_>, PC_THREADS, smem) != cudaSuccess || occ < 1) occ = 1; \
-        pa_pdf_cells_kernel<V_><<<sm_count * occ, PC_THREADS, smem, st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
+        cudaFuncSetAttribute(pa_pdf_cells_kernel<V_, H_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SMEM_)); \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, pa_pdf_cells_kernel<V_, H_>, (THREADS_), (SMEM_)) != cudaSuccess || occ < 1) occ = 1; \
+        pa_pdf_cells_kernel<V_, H_><<<sm_count * occ, (THREADS_), (SMEM_), st>>>(p, gi, go, tiles, ntiles, tile_cap, work_counter, nzg); \
     } while (0)
-    if (p.verify_fail) PDF_LAUNCH(true); else PDF_LAUNCH(false);
+    if (smemh) { if (p.verify_fail) PDF_LAUNCH(true, true, 512, smem_h); else PDF_LAUNCH(false, true, 512, smem_h); }
+    else { if (p.verify_fail) PDF_LAUNCH(true, false, PC_THREADS, smem_g); else PDF_LAUNCH(false, false, PC_THREADS, smem_g); }
 #undef PDF_LAUNCH
     return (int)cudaGetLastError();
 }
