@@ -1296,14 +1296,14 @@ static __device__ __noinline__ void pdf_drain(const PaPass &p, const PaCellGrid 
 // Pair loop in two phases, because only about half of the pairs that survive the staging filter are inside the cutoff
 // and the classification costs ~60 instructions: phase 1 evaluates d2~ for the 4 pairs of a lane's iteration (packed)
 // and appends the pairs that may be inside the cutoff -- (dx~, dy~, dz~, reference index | observed position) -- to a
-// stack of the warp (ballot + popc); whenever the stack holds 32 entries or more, phase 2 pops one entry per lane and
-// classifies it at full lane occupancy.  A popped pair that is not certain is evaluated literally on the spot (~1e-3
+// stack of the warp (ballot + popc); whenever the stack holds 64 entries or more, phase 2 pops two entries per lane and
+// classifies them at full lane occupancy.  A popped pair that is not certain is evaluated literally on the spot (~1e-3
 // of the pairs).
-#define PDF_STACK 160               // 31 left over + 4 x 32 appended by one iteration
-template <bool NEAR, bool VERIFY>
-static __device__ __forceinline__ void pdf_classify(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl, const float4 e,
-                                                    const PcTables &T, const PdfConsts &C, float near_a, long long jbase,
-                                                    unsigned long long &g_within, unsigned long long &g_oob)
+#define PDF_STACK 192               // 63 left over + 4 x 32 appended by one iteration
+// classification of one popped pair: straight-line arithmetic (so that two pairs of a lane interleave), then the decision
+struct PdfDecision { int bin; bool alive, sure; };
+template <bool NEAR>
+static __device__ __forceinline__ PdfDecision pdf_decide(const PaPass &p, const float4 e, const PcTables &T, const PdfConsts &C, float near_a)
 {
     const int na = T.na;
     const unsigned int tlim = 0x4B000000u + (unsigned)na;
@@ -1314,37 +1314,47 @@ static __device__ __forceinline__ void pdf_classify(const PaPass &p, const PaCel
     if (NEAR) rr = pc_add2(rr, pc_pack(-near_a, near_a));
     const unsigned long long tt = pc_fma2_rm(rr, pc_pack(p.f32_lo, p.f32_hi), pc_pack(8388608.0f, 8388608.0f));
     const unsigned int tlo = __float_as_uint(pc_lo(tt)), thi = __float_as_uint(pc_hi(tt));
-    // beyond the cutoff: lower bracket above class na, or both brackets ON class na -- the job's cutoff sits within
-    // delta_top of the boundary of bin na and the brackets are wider than that, so a pair of true class na ("inside the
-    // cutoff, a-bin out of range") always has disagreeing brackets (same argument as VARIANT 0 of the RDF kernel)
-    if (tlo > tlim || (tlo == tlim && thi == tlim)) return;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rinv) : "f"(rt));
     const float dot = __fmaf_rn(e.z, C.vz, __fmaf_rn(e.y, C.vy, __fmul_rn(e.x, C.vx))) * rinv;
     const float E = __fmaf_rn(C.e_b, rinv, C.e_a);
     float t_hi, t_lo;                                                         // thr_b[c] >= dot > thr_b[c+1] must hold with margin E
     const int c = pdf_class(C, dot, t_hi, t_lo);
+    PdfDecision d;
+    // beyond the cutoff: lower bracket above class na, or both brackets ON class na -- the job's cutoff sits within
+    // delta_top of the boundary of bin na and the brackets are wider than that, so a pair of true class na ("inside the
+    // cutoff, a-bin out of range") always has disagreeing brackets (same argument as VARIANT 0 of the RDF kernel)
+    d.alive = !(tlo > tlim || (tlo == tlim && thi == tlim));
     // (|dot| + E <= 1: next to +-1 the reference's fp64 dot product can exceed 1 by an ulp -> ACOS = NaN -> out of bounds)
-    const bool sure = tlo == thi && tlo < tlim && c < C.nb && E < 1.0e-3f && (dot + E <= t_hi) && (dot - E > t_lo) && (fabsf(dot) + E <= 1.0f);
-    const unsigned int id = __float_as_uint(e.w);
-    if (sure && !VERIFY) {
-        const int b0 = c * na + (int)(tlo - 0x4B000000u);
-        if (C.hist) pc_red(C.hist + 4u * (unsigned)b0);
-        else { atomicAdd(&p.job.acc[b0], (unsigned long long)p.weight); ++g_within; }
+    d.sure = tlo == thi && tlo < tlim && c < C.nb && E < 1.0e-3f && (dot + E <= t_hi) && (dot - E > t_lo) && (fabsf(dot) + E <= 1.0f);
+    d.bin = c * na + (int)(tlo - 0x4B000000u);
+    return d;
+}
+
+template <bool VERIFY>
+static __device__ __forceinline__ void pdf_commit(const PaPass &p, const PaCellGrid &go, const PaCellGrid &gi, const PaTile &tl, const float4 e,
+                                                  const PdfDecision d, const PdfConsts &C, long long jbase,
+                                                  unsigned long long &g_within, unsigned long long &g_oob)
+{
+    if (!d.alive) return;
+    if (d.sure && !VERIFY) {
+        if (C.hist) pc_red(C.hist + 4u * (unsigned)d.bin);
+        else { atomicAdd(&p.job.acc[d.bin], (unsigned long long)p.weight); ++g_within; }
         return;
     }
     // literal evaluation from the original slots
+    const unsigned int id = __float_as_uint(e.w);
     const long long iref = (long long)tl.frame * gi.nmol + tl.begin + (int)(id & 63u);
     const int io = gi.sorig[iref], jo = go.sorig[jbase + (long long)(id >> 6)];
     const bool self = p.same_type && io == jo;                                // the molecule itself (Distribution:778)
     const long long fb = (long long)(p.frame0 + tl.frame) * p.pts.M;
     int bin = -1;
     const int st = self ? 0 : pa_eval_pair_exact(p, fb + p.ref_off + io, fb + p.obs_off + jo, &bin);
-    if (VERIFY && sure && !(st == 1 && bin == c * na + (int)(tlo - 0x4B000000u))) atomicAdd(p.verify_fail, 1u);
+    if (VERIFY && d.sure && !(st == 1 && bin == d.bin)) atomicAdd(p.verify_fail, 1u);
     if (st == 1) {
         if (C.hist) pc_red(C.hist + 4u * (unsigned)bin);
         else { atomicAdd(&p.job.acc[bin], (unsigned long long)p.weight); ++g_within; }
     } else if (st == 2) {
-        if (C.hist) pc_red(C.hist + 4u * (unsigned)(na * C.nb));
+        if (C.hist) pc_red(C.hist + 4u * (unsigned)(p.job.bin_a * C.nb));
         else ++g_oob;
     }
 }
@@ -1408,12 +1418,14 @@ static __device__ __forceinline__ void pc_segment_pdf(const PaPass &p, const PaC
                     sn += __popc(m);
                 }
             }
-            while (sn >= 32) {
+            while (sn >= 64) {                                                    // two entries per lane: their arithmetic interleaves
                 __syncwarp();
-                sn -= 32;
-                const float4 e = stack[sn + lane];
+                sn -= 64;
+                const float4 e0 = stack[sn + lane], e1 = stack[sn + 32 + lane];
                 __syncwarp();
-                pdf_classify<NEAR, VERIFY>(p, go, gi, tl, e, T, C, near_a, jbase, g_within, g_oob);
+                const PdfDecision d0 = pdf_decide<NEAR>(p, e0, T, C, near_a), d1 = pdf_decide<NEAR>(p, e1, T, C, near_a);
+                pdf_commit<VERIFY>(p, go, gi, tl, e0, d0, C, jbase, g_within, g_oob);
+                pdf_commit<VERIFY>(p, go, gi, tl, e1, d1, C, jbase, g_within, g_oob);
             }
         }
         fill = 0;
@@ -1421,10 +1433,11 @@ static __device__ __forceinline__ void pc_segment_pdf(const PaPass &p, const PaC
     }
     // the brackets of the entries depend on this run (NEAR): empty the stack before the next run
     __syncwarp();
-    if (lane < sn) {
-        const float4 e = stack[lane];
-        pdf_classify<NEAR, VERIFY>(p, go, gi, tl, e, T, C, near_a, jbase, g_within, g_oob);
-    }
+    for (int b = 0; b < sn; b += 32)
+        if (b + lane < sn) {
+            const float4 e = stack[b + lane];
+            pdf_commit<VERIFY>(p, go, gi, tl, e, pdf_decide<NEAR>(p, e, T, C, near_a), C, jbase, g_within, g_oob);
+        }
     __syncwarp();
 }
 
