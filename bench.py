@@ -406,12 +406,13 @@ def main():
         cell_evals, atomics, unique, dom_evals, dom_atomics, dom_launches, launches_all = (float(x) for x in pe[1:])
         traffic, traffic_src = _traffic_from_profiles()
         if c5:
-            # general cell-sorted kernel: latency / issue bound; reported against the FP64 issue rate of the
-            # literal per-binned-pair evaluation is not meaningful, so the line carries the pair-evaluation rate only
+            # pa_pdf_cells_kernel (float32 brackets for the distance AND the angle class): latency / issue bound;
+            # the line carries the rate of pair evaluations after cell pruning and the staging filter, no hardware peak is claimed
             roofline = {"bound": "issue", "achieved": cell_evals / (kernel_ms_max * 1e-3) if cell_evals else None,
                         "peak": None, "unit": "pair evaluations/s", "frac": None, "traffic": None,
                         "kernel_ms_per_step": kernel_ms_max / K,
-                        "note": "pa_general_cells_kernel: drain-latency bound (ncu: issue slots ~50 % busy); no hardware peak is claimed for it"}
+                        "note": "pa_pdf_cells_kernel: ~25 % of the issue rate (16 warps per SM at 128 registers, dependent MUFU / LDS chain "
+                                "per classified pair), bins in a per-SM shared histogram; see profiles/README.md"}
         else:
             # dominant kernel: pa_rdf_cells_kernel<0,*,*,1> (float32 launch of the cell-sorted RDF kernel; 3 launches per step:
             # two symmetric same-type passes and the merged cross-type pass).  Its binding resource is the shared-memory
