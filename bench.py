@@ -411,8 +411,8 @@ def main():
             roofline = {"bound": "issue", "achieved": cell_evals / (kernel_ms_max * 1e-3) if cell_evals else None,
                         "peak": None, "unit": "pair evaluations/s", "frac": None, "traffic": None,
                         "kernel_ms_per_step": kernel_ms_max / K,
-                        "note": "pa_pdf_cells_kernel: ~25 % of the issue rate (16 warps per SM at 128 registers, dependent MUFU / LDS chain "
-                                "per classified pair), bins in a per-SM shared histogram; see profiles/README.md"}
+                        "note": "pa_pdf_cells_kernel: issue slots 62 % busy (ncu, 16 warps per SM at 128 registers, ~83 instructions per evaluated "
+                                "pair), bins in a per-SM shared histogram; see profiles/README.md"}
         else:
             # dominant kernel: pa_rdf_cells_kernel<0,*,*,1> (float32 launch of the cell-sorted RDF kernel; 3 launches per step:
             # two symmetric same-type passes and the merged cross-type pass).  Its binding resource is the shared-memory
