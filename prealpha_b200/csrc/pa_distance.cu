@@ -694,8 +694,13 @@ __global__ void pn_scatter_kernel(PnArgs a, const int *cell_of_b, const int *cel
     sorted_b[cell_start[cell] + atomicAdd(&cell_fill[cell], 1)] = j;
 }
 
+// Two passes over the same candidates, so that the pair list leaves the device already in the order of the reference's
+// nested loops (a-instance, then b-instance) and the host has nothing to sort: FILL = false counts the hits of every
+// a-instance, an exclusive scan turns the counts into segment starts, FILL = true writes each a-instance's hits into its
+// segment and orders the (few) entries of the segment by b-instance.
+template <bool FILL>
 __global__ void __launch_bounds__(128) pn_cells_kernel(PnArgs a, PnGrid G, const int *cell_start, const int *sorted_b, unsigned int *err,
-                                                       unsigned long long *tests)
+                                                       unsigned long long *tests, int *hits, const int *seg_start)
 {
     const int ia = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long ntest = 0;
@@ -713,6 +718,8 @@ __global__ void __launch_bounds__(128) pn_cells_kernel(PnArgs a, PnGrid G, const
             if (!(u >= 0.0 && u <= (double)G.g[k])) { ok = false; c[k] = 0; continue; }
             c[k] = min(G.g[k] - 1, (int)u);
         }
+        int nhit = 0;
+        const unsigned long long seg = FILL ? (unsigned long long)seg_start[ia] : 0ull;
         if (!ok) atomicOr(err, 1u);
         else {
             for (int dz = -1; dz <= 1; ++dz) {
@@ -733,19 +740,35 @@ __global__ void __launch_bounds__(128) pn_cells_kernel(PnArgs a, PnGrid G, const
                             ++ntest;
                             // REAL(4) function result (Molecular:1400,1418) against the REAL(4) squared cutoff
                             if (__double2float_rn(s < a.mds ? s : a.mds) < a.cutoff_sq[rowi + (a.b_class ? a.b_class[j] : 0)]) {
-                                const unsigned long long slot = atomicAdd(a.count, 1ull);
-                                if (slot < a.capacity) a.out[slot] = make_int2(ia, j);
+                                if (FILL) {
+                                    // insertion into the ordered segment (a handful of entries)
+                                    int k = nhit;
+                                    for (; k > 0; --k) {
+                                        const int jp = a.out[seg + (unsigned)(k - 1)].y;
+                                        if (jp < j) break;
+                                        a.out[seg + (unsigned)k] = make_int2(ia, jp);
+                                    }
+                                    a.out[seg + (unsigned)k] = make_int2(ia, j);
+                                }
+                                ++nhit;
                             }
                         }
                     }
                 }
             }
         }
+        if (!FILL) hits[ia] = nhit;
+        if (!FILL) ntest |= (unsigned long long)nhit << 40;                  // (tests of one thread < 2^40) hits ride along
     }
-    // distance tests carried out (statistics)
+    if (!FILL) {
+        // distance tests carried out (statistics) and the 64-bit number of pairs (the scan of `hits` is 32-bit)
+        unsigned long long nh = ntest >> 40;
+        ntest &= (1ull << 40) - 1ull;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ntest += __shfl_xor_sync(0xffffffffu, ntest, o);
-    if ((threadIdx.x & 31) == 0 && ntest) atomicAdd(tests, ntest);
+        for (int o = 16; o > 0; o >>= 1) { ntest += __shfl_xor_sync(0xffffffffu, ntest, o); nh += __shfl_xor_sync(0xffffffffu, nh, o); }
+        if ((threadIdx.x & 31) == 0 && ntest) atomicAdd(tests, ntest);
+        if ((threadIdx.x & 31) == 0 && nh) atomicAdd(a.count, nh);
+    }
 }
 
 }  // namespace
@@ -828,7 +851,6 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         const size_t ncut = (size_t)rq->n_class_a * rq->n_class_b;
         PD_CK(cudaMalloc(&d_cut, sizeof(float) * ncut));
         PD_CK(cudaMemcpy(d_cut, rq->cutoff_sq, sizeof(float) * ncut, cudaMemcpyHostToDevice));
-        PD_CK(cudaMalloc(&d_out, sizeof(int2) * (size_t)std::max<int64_t>(capacity, 1)));
         PD_CK(cudaMalloc(&d_count, sizeof(unsigned long long)));
         PD_CK(cudaMemset(d_count, 0, sizeof(unsigned long long)));
         PnArgs a{};
@@ -838,7 +860,7 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         a.cutoff_sq = d_cut; a.n_a = rq->n_a; a.n_b = rq->n_b; a.n_class_b = rq->n_class_b;
         a.same_list = rq->same_list ? 1 : 0; a.skip_same_molecule = rq->skip_same_molecule ? 1 : 0;
         a.L[0] = L.x; a.L[1] = L.y; a.L[2] = L.z; a.mds = traj->max_dist_sq;
-        a.out = d_out; a.capacity = (unsigned long long)capacity; a.count = d_count;
+        a.out = nullptr; a.capacity = (unsigned long long)capacity; a.count = d_count;
         // cell list when the box holds at least 3 x 3 x 3 cells of the largest cutoff (flag 0x800 of pa_exec: brute force)
         bool used_cells = false;
         unsigned long long h_tests = 0;
@@ -860,9 +882,9 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
             }
             if (grid_ok) {
                 G.ncell = (int)ncell;
-                PD_CK(cudaMalloc(&d_cellbuf, sizeof(int) * ((size_t)2 * rq->n_b + 3 * (size_t)ncell + 2)));
+                PD_CK(cudaMalloc(&d_cellbuf, sizeof(int) * ((size_t)2 * rq->n_b + 3 * (size_t)ncell + 2 + 2 * (size_t)rq->n_a + 1)));
                 int *cell_of_b = d_cellbuf, *sorted_b = d_cellbuf + rq->n_b, *cell_count = sorted_b + rq->n_b, *cell_start = cell_count + ncell,
-                    *cell_fill = cell_start + ncell + 1;
+                    *cell_fill = cell_start + ncell + 1, *hits = cell_fill + ncell + 1, *seg_start = hits + rq->n_a;
                 PD_CK(cudaMemset(cell_count, 0, sizeof(int) * (size_t)ncell));
                 PD_CK(cudaMemset(cell_fill, 0, sizeof(int) * (size_t)ncell));
                 PD_CK(cudaMalloc(&d_aux, sizeof(unsigned long long) * 2));
@@ -872,15 +894,34 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
                 pn_cell_count_kernel<<<(rq->n_b + 255) / 256, 256>>>(a, G, cell_of_b, cell_count, d_err);
                 pn_scan_kernel<<<1, 1024>>>(cell_count, cell_start, (int)ncell);
                 pn_scatter_kernel<<<(rq->n_b + 255) / 256, 256>>>(a, cell_of_b, cell_start, cell_fill, sorted_b);
-                pn_cells_kernel<<<(rq->n_a + 127) / 128, 128>>>(a, G, cell_start, sorted_b, d_err, d_tests);
+                pn_cells_kernel<false><<<(rq->n_a + 127) / 128, 128>>>(a, G, cell_start, sorted_b, d_err, d_tests, hits, nullptr);
+                pn_scan_kernel<<<1, 1024>>>(hits, seg_start, rq->n_a);
                 PD_CK(cudaGetLastError());
-                unsigned long long aux[2];
+                unsigned long long aux[2], total = 0;
                 PD_CK(cudaMemcpy(aux, d_aux, sizeof aux, cudaMemcpyDeviceToHost));
-                if ((unsigned int)(aux[0] & 0xffffffffu) == 0u) { used_cells = true; h_tests = aux[1]; }
-                else PD_CK(cudaMemset(d_count, 0, sizeof(unsigned long long)));      // a position outside the box: start over, brute force
+                PD_CK(cudaMemcpy(&total, d_count, sizeof total, cudaMemcpyDeviceToHost));
+                if ((unsigned int)(aux[0] & 0xffffffffu) != 0u) {
+                    PD_CK(cudaMemset(d_count, 0, sizeof(unsigned long long)));      // a position outside the box: start over, brute force
+                } else {
+                    if (total > 0x7fffffffull) { pa::set_error("more than 2^31 neighbour pairs"); rc = PA_ERR_UNSUPPORTED; goto done; }
+                    used_cells = true; h_tests = aux[1];
+                    h_count = total;
+                    if (total > 0 && total <= (unsigned long long)capacity) {
+                        PD_CK(cudaMalloc(&d_out, sizeof(int2) * (size_t)total));
+                        a.out = d_out;
+                        pn_cells_kernel<true><<<(rq->n_a + 127) / 128, 128>>>(a, G, cell_start, sorted_b, d_err, d_tests, nullptr, seg_start);
+                        PD_CK(cudaGetLastError());
+                        static_assert(sizeof(pa_neigh_pair) == sizeof(int2), "layout");
+                        PD_CK(cudaMemcpy(out, d_out, sizeof(int2) * (size_t)total, cudaMemcpyDeviceToHost));     // already in loop order
+                    }
+                }
             }
         }
         if (!used_cells) {
+            // brute force (few instances, or a box of fewer than 3 cells per component): pairs are appended as they are found
+            // and ordered on the host
+            PD_CK(cudaMalloc(&d_out, sizeof(int2) * (size_t)std::max<int64_t>(capacity, 1)));
+            a.out = d_out;
             const int bx = (rq->n_a + PC_THREADS - 1) / PC_THREADS;
             int splits = std::max(1, (148 * 8 + bx - 1) / bx);
             splits = std::min(std::min(splits, std::max(1, (rq->n_b + PC_CHUNK - 1) / PC_CHUNK)), 65535);
@@ -888,16 +929,16 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
             splits = (rq->n_b + a.jsplit - 1) / a.jsplit;
             pa_neighbour_kernel<<<dim3(bx, splits), PC_THREADS>>>(a);
             PD_CK(cudaGetLastError());
+            PD_CK(cudaMemcpy(&h_count, d_count, sizeof h_count, cudaMemcpyDeviceToHost));
+            const size_t ncopy = (size_t)std::min<unsigned long long>(h_count, (unsigned long long)capacity);
+            if (ncopy > 0) {
+                static_assert(sizeof(pa_neigh_pair) == sizeof(int2), "layout");
+                PD_CK(cudaMemcpy(out, d_out, sizeof(int2) * ncopy, cudaMemcpyDeviceToHost));
+                if (h_count <= (unsigned long long)capacity)       // complete list: the order of the reference's nested loops
+                    std::sort(out, out + ncopy, [](const pa_neigh_pair &p, const pa_neigh_pair &q) { return p.ia != q.ia ? p.ia < q.ia : p.ib < q.ib; });
+            }
         }
-        PD_CK(cudaMemcpy(&h_count, d_count, sizeof h_count, cudaMemcpyDeviceToHost));
         *count = (int64_t)h_count;
-        const size_t ncopy = (size_t)std::min<unsigned long long>(h_count, (unsigned long long)capacity);
-        if (ncopy > 0) {
-            static_assert(sizeof(pa_neigh_pair) == sizeof(int2), "layout");
-            PD_CK(cudaMemcpy(out, d_out, sizeof(int2) * ncopy, cudaMemcpyDeviceToHost));
-            if (h_count <= (unsigned long long)capacity)       // complete list: the order of the reference's nested loops
-                std::sort(out, out + ncopy, [](const pa_neigh_pair &p, const pa_neigh_pair &q) { return p.ia != q.ia ? p.ia < q.ia : p.ib < q.ib; });
-        }
         if (tests) {
             long long t = (long long)rq->n_a * rq->n_b;
             if (rq->same_list) t = (long long)rq->n_a * (rq->n_a - 1) / 2;

@@ -16,6 +16,9 @@
 #include <chrono>
 #include <array>
 #include <algorithm>
+#include <mutex>
+#include <deque>
+#include <condition_variable>
 #include <thread>
 #include <fcntl.h>
 #include <unistd.h>
@@ -911,62 +914,124 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
         // NCCL communicators take a few hundred ms to create: do it while the file is read and the kernels run
         std::thread comm_thread([&] { if (ndev > 1) pa_multi_device_prepare(ex.device, ndev); });
         struct CommJoin { std::thread &t; ~CommJoin() { if (t.joinable()) t.join(); } } comm_join{ comm_thread };
-        {
-            // one thread per device: allocation and table uploads of the sessions run concurrently
-            std::vector<int> rcs(ndev, 0);
-            std::vector<std::string> errs(ndev);
-            std::vector<std::thread> th;
-            for (int d = 0; d < ndev; ++d)
-                th.emplace_back([&, d] {
-                    pa_exec e = ex;
-                    e.device = ex.device + d;
-                    rcs[d] = pa_session_create(&meta, jobs.data(), (int)jobs.size(), &e, (B + dt - 1) / dt, &sess[d]);
-                    if (rcs[d]) errs[d] = pa_last_error();
-                });
-            for (auto &t : th) t.join();
-            for (int d = 0; d < ndev && rc == 0; ++d) if (rcs[d]) { rc = rcs[d]; pa::set_error(errs[d]); }
+        // ---- producer / consumers -------------------------------------------------------------------------------
+        // This thread reads batches into a ring of host buffers; one thread per device creates its session and then
+        // takes whatever batch is next (pinned copy + async upload + launches), so a device that is ready early, or
+        // faster, simply takes more batches.  The sums are integers: the dealing order cannot change the result.
+        struct Slot { std::vector<std::vector<float>> xyz; std::vector<float *> dst; std::vector<pa_type> vt; pa_traj view; int n = 0, g0 = 0; };
+        const int nslots = ndev + 2;
+        std::vector<Slot> slots(nslots);
+        for (Slot &sl : slots) {
+            sl.xyz.resize(r.types.size());
+            sl.vt.assign(meta.types, meta.types + meta.ntypes);
+            for (size_t t = 0; t < r.types.size(); ++t) {
+                sl.xyz[t].assign((size_t)B * r.types[t].natoms * r.types[t].nmol * 3, 0.f);
+                sl.dst.push_back(sl.xyz[t].data());
+                sl.vt[t].xyz = sl.xyz[t].data();
+            }
+            sl.view = meta;
+            sl.view.types = sl.vt.data();
         }
-        if (rc) { for (pa_session *s : sess) if (s) pa_session_destroy(s); return rc; }
-        std::vector<std::vector<float>> batch(r.types.size());
-        std::vector<pa_type> vt(meta.types, meta.types + meta.ntypes);
-        std::vector<float *> dst;
-        for (size_t t = 0; t < r.types.size(); ++t) {
-            batch[t].assign((size_t)B * r.types[t].natoms * r.types[t].nmol * 3, 0.f);
-            dst.push_back(batch[t].data());
-            vt[t].xyz = batch[t].data();
-        }
-        pa_traj view = meta;
-        view.types = vt.data();
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<int> free_slots, full_slots;
+        for (int i = 0; i < nslots; ++i) free_slots.push_back(i);
+        bool done = false;                                        // no more batches will be queued
+        int first_rc = 0;                                         // first failure of any thread (stops everybody)
+        std::string first_err;
+        const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
+        auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        std::vector<double> t_create(ndev, 0.0), t_upload(ndev, 0.0), t_run(ndev, 0.0);
+        std::vector<long long> dealt(ndev, 0);
+        auto fail = [&](int code, const std::string &msg) {
+            std::lock_guard<std::mutex> lk(mu);
+            if (!first_rc) { first_rc = code; first_err = msg; }
+            cv.notify_all();
+        };
+        std::vector<std::thread> workers;
+        for (int d = 0; d < ndev; ++d)
+            workers.emplace_back([&, d] {
+                pa_exec e = ex;
+                e.device = ex.device + d;
+                double t0 = now_s();
+                int wrc = pa_session_create(&meta, jobs.data(), (int)jobs.size(), &e, (B + dt - 1) / dt, &sess[d]);
+                t_create[d] = now_s() - t0;
+                if (wrc) { fail(wrc, pa_last_error()); return; }
+                for (;;) {
+                    int i;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&] { return first_rc || done || !full_slots.empty(); });
+                        if (first_rc || full_slots.empty()) return;
+                        i = full_slots.front();
+                        full_slots.pop_front();
+                    }
+                    Slot &sl = slots[i];
+                    const int first = (dt - sl.g0 % dt) % dt;     // sampled frames are the global multiples of dt (Distribution:718)
+                    sl.view.nsteps = sl.n;
+                    t0 = now_s();
+                    wrc = pa_session_upload(sess[d], &sl.view, first, (sl.n - first + dt - 1) / dt, dt);
+                    t_upload[d] += now_s() - t0;
+                    {                                             // the frames sit in the session's pinned buffer now
+                        std::lock_guard<std::mutex> lk(mu);
+                        free_slots.push_back(i);
+                        cv.notify_all();
+                    }
+                    t0 = now_s();
+                    if (wrc == 0) wrc = pa_session_run(sess[d]);
+                    t_run[d] += now_s() - t0;
+                    ++dealt[d];
+                    if (wrc) { fail(wrc, pa_last_error()); return; }
+                }
+            });
         int g0 = 0;                                               // global index of the first frame of the batch
         long long nbatch = 0;
         bool short_file = false;
-        const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
-        double t_read = 0, t_upload = 0, t_run = 0;
-        auto now_s = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+        double t_read = 0, t_wait = 0;
         const double t_loop0 = now_s();
-        while (g0 < r.nsteps && rc == 0) {
-            const int want = std::min(B, r.nsteps - g0);
-            double t0 = now_s();
-            const int n = read_frames(r, ts, want, dst);
-            t_read += now_s() - t0;
-            if (n > 0) {
-                const int first = (dt - g0 % dt) % dt;            // sampled frames are the global multiples of dt (Distribution:718)
-                if (first < n) {
-                    pa_session *s = sess[nbatch % ndev];
-                    ++nbatch;
-                    view.nsteps = n;
-                    t0 = now_s();
-                    rc = pa_session_upload(s, &view, first, (n - first + dt - 1) / dt, dt);
-                    t_upload += now_s() - t0; t0 = now_s();
-                    if (rc == 0) rc = pa_session_run(s);
-                    t_run += now_s() - t0;
-                }
-                g0 += n;
+        while (g0 < r.nsteps) {
+            int i;
+            {
+                double t0 = now_s();
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return first_rc || !free_slots.empty(); });
+                if (first_rc) break;
+                i = free_slots.front();
+                free_slots.pop_front();
+                t_wait += now_s() - t0;
             }
+            const int want = std::min(B, r.nsteps - g0);
+            const double t0 = now_s();
+            const int n = read_frames(r, ts, want, slots[i].dst);
+            t_read += now_s() - t0;
+            const bool sampled = n > 0 && (dt - g0 % dt) % dt < n;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (sampled) { slots[i].n = n; slots[i].g0 = g0; full_slots.push_back(i); ++nbatch; }
+                else free_slots.push_back(i);
+                cv.notify_all();
+            }
+            if (n > 0) g0 += n;
             if (n < want) { short_file = true; break; }
         }
-        if (dbg_t) fprintf(stderr, "[prealpha_b200] streaming: %lld batches of <= %d frames on %d device(s); host loop %.3f s = read %.3f + upload %.3f + launch %.3f\n",
-                           nbatch, B, ndev, now_s() - t_loop0, t_read, t_upload, t_run);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            done = true;
+            cv.notify_all();
+        }
+        for (auto &w : workers) w.join();
+        if (first_rc) { rc = first_rc; pa::set_error(first_err); }
+        if (dbg_t) {
+            fprintf(stderr, "[prealpha_b200] streaming: %lld batches of <= %d frames on %d device(s); reader %.3f s = read %.3f + wait for a free buffer %.3f\n",
+                    nbatch, B, ndev, now_s() - t_loop0, t_read, t_wait);
+            for (int d = 0; d < ndev; ++d)
+                fprintf(stderr, "[prealpha_b200] streaming: device %d took %lld batches; session %.3f s, upload %.3f s, launch %.3f s\n",
+                        ex.device + d, dealt[d], t_create[d], t_upload[d], t_run[d]);
+        }
+        if (std::find(sess.begin(), sess.end(), nullptr) != sess.end()) {                 // a session could not be created
+            for (pa_session *s : sess) if (s) pa_session_destroy(s);
+            return rc ? rc : PA_ERR_CUDA;
+        }
         if (rc == 0) finish_cache_write(r, ts, src);              // (no-op unless a cache is being written)
         // sticky flags of every device, then the sum on the first one
         for (int d = 0; d < ndev && rc == 0; ++d) rc = pa_session_download(sess[d], nullptr, nullptr, nullptr, 0);

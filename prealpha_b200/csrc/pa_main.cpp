@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <unistd.h>
+#include <chrono>
 #include <string>
 #include <vector>
 #include "../../include/prealpha_b200.h"
@@ -36,13 +37,19 @@ int main(int argc, char **argv)
         setenv("CUDA_VISIBLE_DEVICES", vis.c_str(), 1);
         ex.device = 0;
     }
-    if (pa_device_count() < 1) {
+    const bool dbg_t = getenv("PA_DEBUG_TIMING") != nullptr;
+    const auto t_main = std::chrono::steady_clock::now();
+    auto since_main = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_main).count(); };
+    const int usable = pa_device_count();                        // first CUDA call: the driver initialises here
+    if (dbg_t) fprintf(stderr, "[prealpha_b200] main: driver initialised, %d usable device(s) %9.1f ms\n", usable, since_main());
+    if (usable < 1) {
         fprintf(stderr, "prealpha_b200: no usable B200 (sm_100) device; this program has no CPU fallback.\n");
         return 2;
     }
     int errors = 0;
     for (const std::string &g : inputs) errors += pa_run_general_input(g.c_str(), &ex);
     fflush(stdout);
+    if (dbg_t) fprintf(stderr, "[prealpha_b200] main: leaving %9.1f ms\n", since_main());
     // the results are on disk: skip the orderly teardown of CUDA contexts, memory pools and NCCL communicators, which
     // costs up to a second per device and frees nothing the operating system does not free anyway
     _exit(errors ? 1 : 0);

@@ -71,9 +71,13 @@ def digest():
     return h.hexdigest()
 
 
+# PA_LEGS: which runs to do (default all): text1, cache1, textN, cacheN, long1, longN -- so that the 1-GPU legs of a long
+# trajectory can run on a 1-GPU box and only the N-GPU leg on the (N x more expensive) N-GPU box; text1 writes the cache
+LEGS = set(os.environ.get("PA_LEGS", "text1,cache1,textN,cacheN,long1,longN").split(","))
 results, ref = [], None
-for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{ngpu}gpu", ngpu, "0"), (f"cache_{ngpu}gpu", ngpu, "1")):
-    if g > 1 and ngpu < 2:
+for leg, label, g, cache in (("text1", "text_1gpu", 1, "1"), ("cache1", "cache_1gpu", 1, "1"), ("textN", f"text_{ngpu}gpu", ngpu, "0"),
+                             ("cacheN", f"cache_{ngpu}gpu", ngpu, "1")):
+    if (g > 1 and ngpu < 2) or leg not in LEGS:
         continue
     for fn in os.listdir(os.path.join(wd, "out")):
         os.remove(os.path.join(wd, "out", fn))
@@ -88,7 +92,7 @@ for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{
     keep = [ln.strip() for ln in out.splitlines() if "B200 execution" in ln or "accelerated section" in ln or "frame cache" in ln]
     rec = {"run": label, "gpus": g, "wall_s": wall, "frames_per_s": nf / wall, "atoms_per_s": nf * 2 * n_half / wall,
            "pair_evals_per_s": nf * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "same_files_as_first_run": d == ref, "cli": keep,
-           "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln or "] streaming" in ln or "] dev " in ln]}
+           "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln or "] streaming" in ln or "] dev " in ln or "] main" in ln]}
     results.append(rec)
     print(json.dumps(rec), flush=True)
     assert d == ref, "output files differ between runs"
@@ -97,6 +101,12 @@ for label, g, cache in (("text_1gpu", 1, "1"), ("cache_1gpu", 1, "1"), (f"text_{
 # it is pinned to is a hard link of the text above).  This is the regime in which the fixed costs of a run (driver
 # initialisation ~1.5 s, one CUDA context per device, communicators) stop mattering.
 LONG = int(os.environ.get("PA_LONG_FACTOR", "0"))
+if LONG > 1:
+    import shutil
+    room = int(shutil.disk_usage(wd).free * 0.7 // (nf * 2 * n_half * 12))
+    if room < LONG:
+        print(json.dumps({"what": "long factor reduced (disk space)", "asked": LONG, "used": max(room, 0)}), flush=True)
+        LONG = room
 if LONG > 1:
     wl = os.path.join(wd, "long")
     os.makedirs(os.path.join(wl, "out"))
@@ -117,6 +127,8 @@ if LONG > 1:
         open(os.path.join(wl, fn), "w").write(open(os.path.join(wd, fn)).read())
     longres = []
     for g in ([1, ngpu] if ngpu > 1 else [1]):
+        if ("long1" if g == 1 else "longN") not in LEGS:
+            continue
         env = dict(os.environ, PREALPHA_B200_CACHE="1", PA_DEBUG_TIMING="1")
         t0 = time.time()
         p = subprocess.run([cli, "-g", str(g), "general.inp"], cwd=wl, capture_output=True, timeout=3600, env=env)
@@ -129,7 +141,7 @@ if LONG > 1:
         rec = {"run": f"long_cache_{g}gpu", "gpus": g, "frames": nf * LONG, "wall_s": wall, "frames_per_s": nf * LONG / wall,
                "pair_evals_per_s": nf * LONG * (2.0 * n_half) * (2.0 * n_half - 1) / wall, "digest": h.hexdigest()[:16],
                "cli": [ln.strip() for ln in out.splitlines() if "B200 execution" in ln or "accelerated section" in ln],
-               "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln or "] streaming" in ln or "] dev " in ln]}
+               "marks": [ln.strip() for ln in p.stderr.decode().splitlines() if "] cli " in ln or "] streaming" in ln or "] dev " in ln or "] main" in ln]}
         longres.append(rec)
         print(json.dumps(rec), flush=True)
     if len(longres) == 2:
