@@ -257,7 +257,6 @@ __global__ void __launch_bounds__(1024) pa_tile_scan_kernel(int *row_off, int n,
 // ---------------------------------------------------------------------------
 // per (tile, observed layer, component) image classification
 struct PcLayer { float dmin2; signed char mode, ca, cb, pad; };    // ca/cb: shift code 0,1,2 = -L,0,+L
-static_assert(sizeof(PcLayer) == 8, "pc_row_masks reads a layer as one 8-byte word");
 
 static __device__ PcLayer pc_classify(double ilo, double ihi, double jlo, double jhi, double L)
 {
@@ -952,51 +951,6 @@ static __device__ __forceinline__ double pc_warp_max(double v)
     return v;
 }
 
-// Runs of one row (cy, cz) of observed cells for a tile: maximal stretches of consecutive x-layers that can reach the
-// cutoff and share the image classification (mode, ca, cb) -- and, for a float32 tile, the "closer than 2|T|" and
-// "same xy column" properties of the brackets.  The layers are examined 32 at a time, one per lane: a position is a
-// boundary when reachability or the classification differs from the position before it (position gx, never reachable,
-// closes the last run), and the boundary / reachability bits of the row go to two small bit masks of the warp.  The run
-// loop then jumps from boundary to boundary instead of visiting every layer (a row has 3-6 runs in 68+ layers).
-#define PC_MASKW ((PC_MAXG + 32) / 32)
-#define PC_MASK_BYTES ((2 * PC_MASKW * 4 + 15) & ~15)
-static __device__ __forceinline__ void pc_row_masks(const PcLayer *lay, int gx, float dyz2, float ly_dmin2, float cutf, float rmin2,
-                                                    bool tile_f32, bool use_zcol, unsigned int *mask)
-{
-    const int lane = threadIdx.x & 31;
-    int ckey = 0;                                        // last position of the previous chunk (0: not reachable)
-    __syncwarp();                                        // the masks of the previous row are no longer read
-    for (int c0 = 0, w = 0; c0 <= gx; c0 += 32, ++w) {
-        const int t = c0 + lane;
-        // (one 8-byte load: dmin2 and the bytes mode, ca, cb, pad -- the warp's slice is 16-byte aligned)
-        const uint2 lw = reinterpret_cast<const uint2 *>(lay)[min(t, gx - 1)];
-        const float ldmin2 = __uint_as_float(lw.x);
-        const float d = dyz2 + ldmin2;
-        // reachable position: classification key (mode, ca, cb) with bit 26 set; anything else: 0
-        int key = 0x4000000 | (int)(lw.y & 0xffffffu);
-        if (tile_f32) key |= (!(d >= rmin2) ? 0x1000000 : 0) | ((use_zcol && !(ldmin2 + ly_dmin2 > 1.0e-6f)) ? 0x2000000 : 0);
-        if (!(t < gx && d < cutf)) key = 0;
-        int pkey = __shfl_up_sync(0xffffffffu, key, 1);
-        if (lane == 0) pkey = ckey;
-        ckey = __shfl_sync(0xffffffffu, key, 31);
-        const unsigned int B = __ballot_sync(0xffffffffu, key != pkey), R = __ballot_sync(0xffffffffu, key != 0);
-        if (lane == 0) { mask[w] = B; mask[PC_MASKW + w] = R; }
-    }
-    __syncwarp();
-}
-// first set bit at or after `pos` in the first `nw` words, -1: none
-static __device__ __forceinline__ int pc_next_bit(const unsigned int *words, int nw, int pos)
-{
-    int wi = pos >> 5;
-    if (wi >= nw) return -1;
-    unsigned int w = words[wi] & (0xffffffffu << (pos & 31));
-    while (!w) {
-        if (++wi >= nw) return -1;
-        w = words[wi];
-    }
-    return wi * 32 + __ffs((int)w) - 1;
-}
-
 // PART 0: every run in one launch.  PART 1 / PART 2: the float32-eligible runs (single image or one two-image
 // component) and all other runs as two launches over the same work items, so that each gets its own register allocation.
 static __host__ __device__ __forceinline__ size_t pc_warp_bytes(bool part1, int nlay)
@@ -1004,7 +958,7 @@ static __host__ __device__ __forceinline__ size_t pc_warp_bytes(bool part1, int 
     // per warp (16-byte aligned slices): PART 1: staged local float4 (PC_FBUF) + their sorted positions + queue of deferred
     // exact decisions; other parts: staged doubles (PC_JC * 6); both: layer classification of the warp's tile
     const size_t stage = part1 ? (size_t)PC_FBUF * 16 + (size_t)PC_FBUF * 4 + (size_t)PC_QCAP * 8 : (size_t)PC_JC * 6 * 8;
-    return stage + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15) + PC_MASK_BYTES;
+    return stage + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15);
 }
 template <int VARIANT, bool VERIFY, bool SYM, int PART>
 __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? PC_MINB : 0) pa_rdf_cells_kernel(const __grid_constant__ PaPass p, const __grid_constant__ PaCellGrid gi, const __grid_constant__ PaCellGrid go, const PaTile *tiles,
@@ -1027,7 +981,6 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? PC_MINB : 0) pa_rdf_ce
     int *s_jidx = reinterpret_cast<int *>(s_jf + PC_FBUF);
     unsigned long long *queue = reinterpret_cast<unsigned long long *>(s_jidx + PC_FBUF);
     PcLayer *lay = reinterpret_cast<PcLayer *>(wbase + (PART == 1 ? (size_t)PC_FBUF * 20 + (size_t)PC_QCAP * 8 : (size_t)PC_JC * 6 * 8));
-    unsigned int *rmask = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(lay) + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15));
 
     for (int k = threadIdx.x; k < (PART == 1 ? 0 : na + 3); k += blockDim.x)
         s_thr[k] = p.job.thr_a[k];       // "never" (all ones) is a NaN as a double: every `d2 >= NaN` is false, as required
@@ -1169,25 +1122,24 @@ __global__ void __launch_bounds__(PC_THREADS, PART == 1 ? PC_MINB : 0) pa_rdf_ce
                 if (PART == 2 && tile_f32 && ly.mode == 1 && lz.mode == 1 && dyz2 >= rmin2 && ly.dmin2 > 1.0e-6f &&
                     !(SYM && cz * gy + cy == tile_row)) continue;
                 const int *row = cs + ((long long)cz * gy + cy) * gx;
-                // runs of x-layers: reachable, same image classification, same nearr / zcol for a float32 tile (pc_row_masks)
-                pc_row_masks(lay, gx, dyz2, ly.dmin2, cutf, rmin2, tile_f32, true, rmask);
-                const int nmw = (gx + 32) >> 5;
-                int pos = 0;
-                for (;;) {
-                    const int cx = pc_next_bit(rmask, nmw, pos);                   // next boundary
-                    if (cx < 0) break;
-                    if (!((rmask[PC_MASKW + (cx >> 5)] >> (cx & 31)) & 1u)) { pos = cx + 1; continue; }   // nothing reachable begins here
-                    const int cend = pc_next_bit(rmask, nmw, cx + 1);              // the boundary that closes the run (position gx at the latest)
-                    if (cend < 0) break;
-                    pos = cend;
-                    const int ce = cend - 1;
+                int cx = 0;
+                while (cx < gx) {
                     const PcLayer lx = lay[cx];
+                    if (!(dyz2 + lx.dmin2 < cutf)) { ++cx; continue; }            // cannot reach the cutoff
                     // float32 segment: all components single-image, boxes >= 2|T| apart; zcol: the link vector of a
                     // pair of this run can be (anti)parallel to z
                     const bool far = tile_f32;                                     // every single-image run of a float32 tile
                     const bool nearr = !(dyz2 + lx.dmin2 >= rmin2);                // closer than 2|T|: brackets get the absolute term
                     const bool zcol = !(lx.dmin2 + ly.dmin2 > 1.0e-6f);
+                    int ce = cx;                                                   // extend while the x classification is identical
+                    while (ce + 1 < gx) {
+                        const PcLayer ln = lay[ce + 1];
+                        if (ln.mode != lx.mode || ln.ca != lx.ca || ln.cb != lx.cb || !(dyz2 + ln.dmin2 < cutf)) break;
+                        if (tile_f32 && (!(dyz2 + ln.dmin2 >= rmin2) != nearr || !(ln.dmin2 + ly.dmin2 > 1.0e-6f) != zcol)) break;
+                        ++ce;
+                    }
                     int jb = row[cx], je = row[ce + 1];
+                    cx = ce + 1;
                     // float32-eligible runs belong to the PART 1 launch -- except the part of a run that overlaps the tile
                     // itself in a symmetric pass (db..de below), which always takes the fp64 segment of PART 0 / 2
                     // (all components single image, or -- far runs only -- exactly one component with two candidates)
@@ -1563,7 +1515,6 @@ __global__ void __launch_bounds__(SMEMH ? 512 : PC_THREADS, SMEMH ? 1 : PDF_MINB
     int *s_jidx = reinterpret_cast<int *>(stack + PDF_STACK);
     unsigned long long *queue = reinterpret_cast<unsigned long long *>(s_jidx + PC_FBUF);  // fp64 segments (pc_segment_pdf64)
     PcLayer *lay = reinterpret_cast<PcLayer *>(wbase + (size_t)PC_FBUF * 20 + (size_t)PDF_STACK * 16 + (size_t)PC_QCAP * 8);
-    unsigned int *rmask = reinterpret_cast<unsigned int *>(reinterpret_cast<unsigned char *>(lay) + (((size_t)nlay * sizeof(PcLayer) + 15) & ~(size_t)15));
     for (int k = threadIdx.x; k < nb + 2; k += blockDim.x)
         s_tab[k] = k == 0 ? __int_as_float(0x7f800000) : (k <= nb ? __double2float_rn(p.job.thr_b[k]) : __int_as_float(0xff800000));
     if (SMEMH) for (int k = threadIdx.x; k < nbins + 1; k += blockDim.x) s_hist[k] = 0u;
@@ -1660,20 +1611,20 @@ __global__ void __launch_bounds__(SMEMH ? 512 : PC_THREADS, SMEMH ? 1 : PDF_MINB
                 const float dyz2 = lz.dmin2 + ly.dmin2;
                 if (!(dyz2 < cutf)) continue;
                 const int *row = cs + ((long long)cz * gy + cy) * gx;
-                pc_row_masks(lay, gx, dyz2, ly.dmin2, cutf, rmin2, tile_f32, false, rmask);
-                const int nmw = (gx + 32) >> 5;
-                int pos = 0;
-                for (;;) {
-                    const int cx = pc_next_bit(rmask, nmw, pos);
-                    if (cx < 0) break;
-                    if (!((rmask[PC_MASKW + (cx >> 5)] >> (cx & 31)) & 1u)) { pos = cx + 1; continue; }
-                    const int cend = pc_next_bit(rmask, nmw, cx + 1);
-                    if (cend < 0) break;
-                    pos = cend;
-                    const int ce = cend - 1;
+                int cx = 0;
+                while (cx < gx) {
                     const PcLayer lx = lay[cx];
+                    if (!(dyz2 + lx.dmin2 < cutf)) { ++cx; continue; }
                     const bool nearr = !(dyz2 + lx.dmin2 >= rmin2);
+                    int ce = cx;
+                    while (ce + 1 < gx) {
+                        const PcLayer ln = lay[ce + 1];
+                        if (ln.mode != lx.mode || ln.ca != lx.ca || ln.cb != lx.cb || !(dyz2 + ln.dmin2 < cutf)) break;
+                        if (tile_f32 && (!(dyz2 + ln.dmin2 >= rmin2) != nearr)) break;
+                        ++ce;
+                    }
                     const int jb = row[cx], je = row[ce + 1];
+                    cx = ce + 1;
                     if (jb >= je) continue;
                     const double Lx = p.box.L[0], Ly = p.box.L[1], Lz = p.box.L[2];
                     const double sxa = (double)(lx.ca - 1) * Lx, sxb = (double)(lx.cb - 1) * Lx;
