@@ -888,7 +888,7 @@ void make_traj(Run &r, std::vector<pa_type> &types, pa_traj &t)
 // sampled frames of a batch are picked by the stride of pa_session_upload.  With several devices (pa_exec.ndevices) the
 // batches are dealt round-robin to one session per GPU -- uploads and launches are asynchronous, so the one reading
 // thread keeps all of them busy as long as frames arrive fast enough -- and the int64 accumulators are combined on the
-// first device at the end (pa_sessions_reduce_to_first: ncclReduce over NVLink).  The kernel ladder of
+// first device at the end (pa_sessions_reduce_to_first: peer copies or ncclReduce over NVLink, by size).  The kernel ladder of
 // pa_distribution_histogram_multi (cells -> brute force -> general kernel when a sticky device flag asks for it) is
 // repeated here by re-reading the file.
 int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, std::vector<int64_t *> &hp,
@@ -912,7 +912,7 @@ int histogram_streaming(Run &r, const pa_traj &meta, std::vector<pa_job> &jobs, 
         std::vector<pa_session *> sess(ndev, nullptr);
         int rc = 0;
         // NCCL communicators take a few hundred ms to create: do it while the file is read and the kernels run
-        std::thread comm_thread([&] { if (ndev > 1) pa_multi_device_prepare(ex.device, ndev); });
+        std::thread comm_thread([&] { if (ndev > 1) pa_multi_device_prepare(ex.device, ndev, jobs.data(), (int)jobs.size()); });
         struct CommJoin { std::thread &t; ~CommJoin() { if (t.joinable()) t.join(); } } comm_join{ comm_thread };
         // ---- producer / consumers -------------------------------------------------------------------------------
         // This thread reads batches into a ring of host buffers; one thread per device creates its session and then

@@ -167,7 +167,7 @@ int pa_general_ri(int nref);
 // first session's device (ncclReduce over NVLink, or peer copies + add) / merge their statistics
 int pa_sessions_reduce_to_first(pa_session *const *sess, int n, const std::vector<void *> *comms_in = nullptr);
 void pa_sessions_merge_stats(pa_session *const *sess, int n, bool by_frames, pa_stats *out);
-void pa_multi_device_prepare(int first_device, int ndevices);   // NCCL communicators ahead of time (cached)
+void pa_multi_device_prepare(int first_device, int ndevices, const pa_job *jobs, int njobs);   // NCCL communicators ahead of time (cached), if the reduce will use them
 
 // ---------------------------------------------------------------------------
 // Host-side float32-exact logic (pa_host.cpp)

@@ -1010,6 +1010,16 @@ const NcclApi &nccl_api()
     return g_nccl;
 }
 
+// The accumulators of a run are a few KB to a few MB.  Below this size the first device fetches them from its peers
+// (copies over NVLink + an add kernel, microseconds); from this size on the sum is an ncclReduce.  A communicator set for
+// 8 GPUs costs ~1 s to create, connects its transports on the first collective and has to be torn down at exit, which a
+// 16 KB sum never earns back.  PA_NCCL_MIN_BYTES overrides the threshold (0: always NCCL -- the tests use it).
+size_t nccl_min_bytes()
+{
+    if (const char *e = getenv("PA_NCCL_MIN_BYTES")) return (size_t)strtoull(e, nullptr, 10);
+    return (size_t)4 << 20;
+}
+
 // communicators are expensive to create (hundreds of ms): one set per device list, kept until pa_trim()
 std::vector<void *> nccl_comms_for(const std::vector<int> &devs)
 {
@@ -1026,9 +1036,19 @@ std::vector<void *> nccl_comms_for(const std::vector<int> &devs)
 
 }  // namespace
 
-// creates (and caches) the NCCL communicators of devices first..first+n-1 ahead of the reduce
-void pa_multi_device_prepare(int first, int n)
+// accumulator bytes of a session for these jobs (upper bound: bins + the within / out-of-bounds words of every job)
+static size_t acc_bytes_estimate(const pa_job *jobs, int njobs)
 {
+    size_t words = 0;
+    for (int j = 0; j < njobs; ++j) words += (size_t)std::max(jobs[j].bin_a, 1) * (size_t)std::max(jobs[j].bin_b, 1) + 8;
+    return words * sizeof(unsigned long long);
+}
+
+// creates (and caches) the NCCL communicators of devices first..first+n-1 ahead of the reduce -- when the reduce of these
+// jobs is going to use them (see nccl_min_bytes)
+void pa_multi_device_prepare(int first, int n, const pa_job *jobs, int njobs)
+{
+    if (acc_bytes_estimate(jobs, njobs) < nccl_min_bytes()) return;
     std::vector<int> devs(n);
     for (int d = 0; d < n; ++d) devs[d] = first + d;
     nccl_comms_for(devs);
@@ -1043,8 +1063,9 @@ void pa_multi_device_trim()
     g_comm_cache.clear();
 }
 
-// Adds the accumulators of sessions 1..n-1 (one per device) to those of session 0: one ncclReduce(sum) of the int64 words
-// over NVLink, or -- when libnccl cannot be loaded -- peer copies and an add kernel on the first device.
+// Adds the accumulators of sessions 1..n-1 (one per device) to those of session 0: peer copies over NVLink and an add
+// kernel on the first device for the usual few KB, one ncclReduce(sum) of the int64 words for large histograms (see
+// nccl_min_bytes; also peer copies when libnccl cannot be loaded).
 int pa_sessions_reduce_to_first(pa_session *const *sess, int n, const std::vector<void *> *comms_in)
 {
     if (n < 2) return 0;
@@ -1053,7 +1074,8 @@ int pa_sessions_reduce_to_first(pa_session *const *sess, int n, const std::vecto
     for (int d = 0; d < n; ++d) devs[d] = sess[d]->device;
     const size_t words = sess[0]->acc_words;
     for (int d = 1; d < n; ++d) if (sess[d]->acc_words != words) { pa::set_error("sessions with different accumulators"); return PA_ERR_BAD_ARG; }
-    std::vector<void *> comms = comms_in ? *comms_in : nccl_comms_for(devs);
+    std::vector<void *> comms;
+    if (words * sizeof(unsigned long long) >= nccl_min_bytes()) comms = (comms_in && !comms_in->empty()) ? *comms_in : nccl_comms_for(devs);
     bool reduced = false;
     if (!comms.empty()) {
         const NcclApi &api = nccl_api();
@@ -1125,7 +1147,7 @@ int pa_multi_device_histogram(const pa_traj *traj, const pa_job *jobs, int32_t n
     for (int d = 0; d < n; ++d) devs[d] = ex.device + d;
     // communicators are created while the kernels run
     std::vector<void *> comms;
-    std::thread comm_thread([&] { comms = nccl_comms_for(devs); });
+    std::thread comm_thread([&] { if (acc_bytes_estimate(jobs, njobs) >= nccl_min_bytes()) comms = nccl_comms_for(devs); });
     std::vector<pa_session *> sess(n, nullptr);
     std::vector<int> rcs(n, 0);
     std::vector<float> total_ms(n, 0.f);

@@ -653,5 +653,7 @@ print("ok")
     env = dict(os.environ)
     if no_nccl:
         env["PA_NO_NCCL"] = "1"
+    else:
+        env["PA_NCCL_MIN_BYTES"] = "0"                 # small accumulators default to peer copies: force the ncclReduce path
     out = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
