@@ -514,7 +514,71 @@ def case_re4_cluster():
     print("re4_cluster:", {k: len(v) for k, v in files.items()})
 
 
-CASES = {"lmp_masses": case_lmp_masses, "re4_cluster": case_re4_cluster, "dist_simple": case_dist_simple, "contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
+SPECIATION_INPUTS = {
+    # Research_Example_4's own two inputs on 12 frames (nsteps / tmax shortened), autocorrelation and dumps off
+    "spec_toLi.inp": " 1 acceptor\n 3 1 0.0\n 3 donors\n 1 1 4.25 to phosphorus\n 2 2 3.0\n 2 5 3.0\n new_donor_group 2\n assign_to_donor_group 2\n assign_to_donor_group 5\n"
+                     " N_species 50\n N_neighbours 40\n nsteps 12\n tmax 11\n use_ccc T\n sampling_interval 1\n quit\n",
+    "spec_fromLi.inp": " 3 acceptors\n 1 1 4.25 to phosphorus\n 2 2 3.0\n 2 5 3.0\n 1 donor\n 3 1 0.0\n new_acceptor_group 2\n assign_to_acceptor_group 2\n assign_to_acceptor_group 5\n"
+                       " N_species 40\n N_neighbours 40\n nsteps 12\n tmax 11\n use_ccc T\n sampling_interval 1\n quit\n",
+    # every second step, radii on both sides (cutoff = acceptor + donor contribution), fluorine and carbon atoms as well
+    "spec_mixed.inp": " 2 acceptors\n 3 1 1.0\n 1 1 2.0\n 4 donors\n 2 2 1.9\n 2 5 2.0\n 1 4 1.25\n 2 1 2.5\n"
+                      " N_species 60\n N_neighbours 40\n nsteps 12\n tmax 11\n use_ccc T\n sampling_interval 2\n quit\n",
+}
+
+
+def _parse_speciation_statistics(text):
+    """`*_speciation_statistics.dat` -> list of (percent string, connections, neighbour atoms, neighbour molecules)."""
+    out, cur = [], None
+    for ln in text.splitlines():
+        t = ln.strip()
+        if t.startswith("Species #("):
+            cur = [t.split(" in ")[1].split("%")[0], None, None, None]
+            out.append(cur)
+        elif t.startswith("This species has a total of") and cur is not None:
+            cur[1] = int(t.split()[6])
+        elif t.startswith("with a total of") and cur is not None:
+            w = t.split()
+            cur[2], cur[3] = int(w[4]), int(w[8])
+    return out
+
+
+def case_re4_speciation():
+    """SURVEY 8f-4, the speciation module's neighbour stage (Speciation:1405-1500): the reference binary's speciation
+    analysis of the first 12 frames of Research_Example_4.  The species it reports (occurrence fraction <h> to 10 digits
+    from `*_speciation_statistics_table.dat`, connections / neighbour atoms / neighbour molecules from
+    `*_speciation_statistics.dat`) fix, for every acceptor molecule type, how many (acceptor molecule, step) cases have
+    which (connections, neighbour atoms, neighbour molecules) triple -- a function of the neighbour test alone."""
+    src = os.path.join(REF, "Research_Example_4", "LiG1G1G1DFP-noH-1ns-363K.xyz")
+    wd = tempfile.mkdtemp()
+    with open(src) as f, open(os.path.join(wd, "traj.xyz"), "w") as g:
+        for _ in range(12 * (1680 + 2)):
+            g.write(f.readline())
+    os.makedirs(os.path.join(wd, "output"))
+    open(os.path.join(wd, "molecular.inp"), "w").write(" 12\n 3\n -1 5 70\n +0 6 210\n +1 1 70\nquit\n")
+    gen = ' "traj.xyz"\n "molecular.inp"\n "./"\n "./"\n "./output/"\n cubic_box_edge 0.0 34.7853\n parallel_operation F\n sequential_read F\n trajectory_type xyz\n'
+    for name, text in SPECIATION_INPUTS.items():
+        open(os.path.join(wd, name), "w").write(text)
+        gen += f' set_prefix "{name[5:-4]}_"\n speciation "{name}"\n'
+    open(os.path.join(wd, "general.inp"), "w").write(gen + " quit\n")
+    out, _ = orc.run_reference(wd)
+    names, texts, tables, none_lines = [], [], [], []
+    for fn in sorted(os.listdir(os.path.join(wd, "output"))):
+        if fn.endswith("_speciation_statistics.dat"):
+            names.append(fn)
+            texts.append(open(os.path.join(wd, "output", fn)).read())
+            tables.append(open(os.path.join(wd, "output", fn[:-4] + "_table.dat")).read())
+    keep = [ln for ln in out.splitlines() if "without neighbouring donors" in ln or "different species were observed" in ln or "For this acceptor" in ln
+            or "There was one acceptor" in ln or "Acceptor " in ln or "overflow" in ln.lower()]
+    np.savez_compressed(os.path.join(OUT, "re4_speciation.npz"),
+                        input_names=np.array(list(SPECIATION_INPUTS)), input_texts=np.array(list(SPECIATION_INPUTS.values())),
+                        file_names=np.array(names), file_texts=np.array(texts), table_texts=np.array(tables),
+                        stdout_lines=np.array(keep), stdout=np.array(out))
+    shutil.rmtree(wd)
+    print("re4_speciation:", names, [len(_parse_speciation_statistics(t)) for t in texts])
+    print("\n".join(keep))
+
+
+CASES = {"re4_speciation": case_re4_speciation, "lmp_masses": case_lmp_masses, "re4_cluster": case_re4_cluster, "dist_simple": case_dist_simple, "contact": case_contact, "charge_arm": case_charge_arm, "lmp": case_lmp, "dist": case_dist, "bmim": case_bmim, "re4": case_re4, "re4_atoms": case_re4_atoms, "synth": case_synth}
 
 if __name__ == "__main__":
     assert orc.ref_available(), "run `make -C oracle` first (needs /root/reference)"
