@@ -523,7 +523,11 @@ int pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, in
         for (double v : { s->box.lo[k], s->box.hi[k] })
             if (!((double)(float)v == v && (v == 0.0 || (std::fabs(v) >= 7.62939453125e-06 && std::fabs(v) < 1024.0)))) exact = false;
     }
-    size_t poff = 0;
+    // copy into the page-locked staging buffer (and scan for the exactness certificate) frame by frame; batches of tens of
+    // MB are split over a few host threads -- one thread moves ~10 GB/s, the PCIe link takes five times that
+    struct Seg { float *dst; const float *src; size_t n; };
+    std::vector<Seg> segs;
+    size_t poff = 0, total_floats = 0;
     for (size_t t = 0; t < s->types.size(); ++t) {
         const TypeMeta &m = s->types[t];
         if (!m.needed) continue;
@@ -531,20 +535,47 @@ int pa_session_upload(pa_session *s, const pa_traj *traj, int32_t first_step, in
         if (!ty.xyz || ty.natoms != m.natoms || ty.nmol != m.nmol) { pa::set_error("pa_session_upload: trajectory does not match the session"); return PA_ERR_BAD_ARG; }
         const size_t ff = m.frame_floats();
         float *dst = s->h_pinned[slot] + poff;
-        for (int f = 0; f < nframes; ++f) {
-            const float *src = ty.xyz + (size_t)(first_step + (int64_t)f * step_stride) * ff;
-            memcpy(dst + (size_t)f * ff, src, ff * sizeof(float));
-            if (exact) {
-                unsigned int bad = 0;
-                const uint32_t *u = reinterpret_cast<const uint32_t *>(src);
-                for (size_t i = 0; i < ff; ++i) {
-                    const uint32_t a = u[i] & 0x7fffffffu;                     // |x| as bits: 2^-17 = 0x37000000, 2^10 = 0x44800000
-                    bad |= (unsigned)((a != 0u) & ((a < 0x37000000u) | (a >= 0x44800000u)));
+        for (int f = 0; f < nframes; ++f)
+            segs.push_back({ dst + (size_t)f * ff, ty.xyz + (size_t)(first_step + (int64_t)f * step_stride) * ff, ff });
+        total_floats += ff * (size_t)nframes;
+        poff += ff * (size_t)s->max_frames;
+    }
+    {
+        const bool scan = exact;
+        auto work = [&segs, scan](size_t b, size_t e) -> bool {
+            unsigned int bad = 0;
+            for (size_t k = b; k < e; ++k) {
+                memcpy(segs[k].dst, segs[k].src, segs[k].n * sizeof(float));
+                if (scan) {
+                    const uint32_t *u = reinterpret_cast<const uint32_t *>(segs[k].src);
+                    for (size_t i = 0; i < segs[k].n; ++i) {
+                        const uint32_t a = u[i] & 0x7fffffffu;                     // |x| as bits: 2^-17 = 0x37000000, 2^10 = 0x44800000
+                        bad |= (unsigned)((a != 0u) & ((a < 0x37000000u) | (a >= 0x44800000u)));
+                    }
                 }
-                if (bad) exact = false;
             }
+            return bad != 0;
+        };
+        const size_t nthreads = std::min<size_t>({ (size_t)8, std::max<size_t>(1, std::thread::hardware_concurrency() / 2), segs.size(),
+                                                   std::max<size_t>(1, total_floats * sizeof(float) >> 23) });     // >= 8 MB per thread
+        bool bad = false;
+        if (nthreads <= 1) bad = work(0, segs.size());
+        else {
+            std::vector<char> flags(nthreads, 0);
+            std::vector<std::thread> th;
+            for (size_t k = 0; k < nthreads; ++k)
+                th.emplace_back([&, k] { flags[k] = work(segs.size() * k / nthreads, segs.size() * (k + 1) / nthreads) ? 1 : 0; });
+            for (auto &t : th) t.join();
+            for (char f : flags) bad = bad || f;
         }
-        PA_CK(cudaMemcpyAsync(s->d_raw[slot][t], dst, sizeof(float) * ff * nframes, cudaMemcpyHostToDevice, s->s_copy));
+        if (bad) exact = false;
+    }
+    poff = 0;
+    for (size_t t = 0; t < s->types.size(); ++t) {
+        const TypeMeta &m = s->types[t];
+        if (!m.needed) continue;
+        const size_t ff = m.frame_floats();
+        PA_CK(cudaMemcpyAsync(s->d_raw[slot][t], s->h_pinned[slot] + poff, sizeof(float) * ff * nframes, cudaMemcpyHostToDevice, s->s_copy));
         s->stats.h2d_bytes += (int64_t)(sizeof(float) * ff * nframes);
         poff += ff * (size_t)s->max_frames;
     }
