@@ -773,6 +773,25 @@ __global__ void __launch_bounds__(128) pn_cells_kernel(PnArgs a, PnGrid G, const
 
 }  // namespace
 
+// Work buffers of pa_neighbour_pairs: stream-ordered allocations from the device's default memory pool (kept by the driver
+// between calls -- the release threshold is raised once per device), so that a cluster analysis calling this once per
+// time step does not pay eight cudaMalloc / cudaFree round trips every time.  Everything runs on the default stream.
+template <typename T> static cudaError_t pn_alloc(T **ptr, size_t bytes)
+{
+    static bool pool_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_set[dev] = true;
+    }
+    return cudaMallocAsync(reinterpret_cast<void **>(ptr), std::max<size_t>(bytes, 16), 0);
+}
+
 extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *rq, const pa_exec *exec,
                                   pa_neigh_pair *out, int64_t capacity, int64_t *count, int64_t *tests)
 {
@@ -825,8 +844,8 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
     {
         size_t max_raw = 1;
         for (int t = 0; t < nt; ++t) max_raw = std::max(max_raw, (size_t)(first[t + 1] - first[t]) * 3);
-        PD_CK(cudaMalloc(&d_pos, sizeof(double) * 3 * (size_t)std::max(n_all, 1)));
-        PD_CK(cudaMalloc(&d_raw, sizeof(float) * max_raw));
+        PD_CK(pn_alloc(&d_pos, sizeof(double) * 3 * (size_t)std::max(n_all, 1)));
+        PD_CK(pn_alloc(&d_raw, sizeof(float) * max_raw));
         double *x = d_pos, *y = d_pos + n_all, *z = d_pos + 2 * (size_t)n_all;
         const double3 lo = make_double3(traj->box_lo[0], traj->box_lo[1], traj->box_lo[2]);
         const double3 hi = make_double3(traj->box_hi[0], traj->box_hi[1], traj->box_hi[2]);
@@ -841,7 +860,7 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         }
         // index block: [a atoms][a mols][a classes][b atoms][b mols][b classes]
         const size_t na = (size_t)rq->n_a, nb = (size_t)rq->n_b;
-        PD_CK(cudaMalloc(&d_idx, sizeof(int) * 3 * (na + nb)));
+        PD_CK(pn_alloc(&d_idx, sizeof(int) * 3 * (na + nb)));
         PD_CK(cudaMemcpy(d_idx, h_at[0].data(), sizeof(int) * na, cudaMemcpyHostToDevice));
         PD_CK(cudaMemcpy(d_idx + na, h_mol[0].data(), sizeof(int) * na, cudaMemcpyHostToDevice));
         if (rq->a_class) PD_CK(cudaMemcpy(d_idx + 2 * na, rq->a_class, sizeof(int) * na, cudaMemcpyHostToDevice));
@@ -849,9 +868,9 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         PD_CK(cudaMemcpy(d_idx + 3 * na + nb, h_mol[1].data(), sizeof(int) * nb, cudaMemcpyHostToDevice));
         if (rq->b_class) PD_CK(cudaMemcpy(d_idx + 3 * na + 2 * nb, rq->b_class, sizeof(int) * nb, cudaMemcpyHostToDevice));
         const size_t ncut = (size_t)rq->n_class_a * rq->n_class_b;
-        PD_CK(cudaMalloc(&d_cut, sizeof(float) * ncut));
+        PD_CK(pn_alloc(&d_cut, sizeof(float) * ncut));
         PD_CK(cudaMemcpy(d_cut, rq->cutoff_sq, sizeof(float) * ncut, cudaMemcpyHostToDevice));
-        PD_CK(cudaMalloc(&d_count, sizeof(unsigned long long)));
+        PD_CK(pn_alloc(&d_count, sizeof(unsigned long long)));
         PD_CK(cudaMemset(d_count, 0, sizeof(unsigned long long)));
         PnArgs a{};
         a.x = x; a.y = y; a.z = z;
@@ -882,12 +901,12 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
             }
             if (grid_ok) {
                 G.ncell = (int)ncell;
-                PD_CK(cudaMalloc(&d_cellbuf, sizeof(int) * ((size_t)2 * rq->n_b + 3 * (size_t)ncell + 2 + 2 * (size_t)rq->n_a + 1)));
+                PD_CK(pn_alloc(&d_cellbuf, sizeof(int) * ((size_t)2 * rq->n_b + 3 * (size_t)ncell + 2 + 2 * (size_t)rq->n_a + 1)));
                 int *cell_of_b = d_cellbuf, *sorted_b = d_cellbuf + rq->n_b, *cell_count = sorted_b + rq->n_b, *cell_start = cell_count + ncell,
                     *cell_fill = cell_start + ncell + 1, *hits = cell_fill + ncell + 1, *seg_start = hits + rq->n_a;
                 PD_CK(cudaMemset(cell_count, 0, sizeof(int) * (size_t)ncell));
                 PD_CK(cudaMemset(cell_fill, 0, sizeof(int) * (size_t)ncell));
-                PD_CK(cudaMalloc(&d_aux, sizeof(unsigned long long) * 2));
+                PD_CK(pn_alloc(&d_aux, sizeof(unsigned long long) * 2));
                 PD_CK(cudaMemset(d_aux, 0, sizeof(unsigned long long) * 2));
                 unsigned int *d_err = reinterpret_cast<unsigned int *>(d_aux);
                 unsigned long long *d_tests = d_aux + 1;
@@ -907,7 +926,7 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
                     used_cells = true; h_tests = aux[1];
                     h_count = total;
                     if (total > 0 && total <= (unsigned long long)capacity) {
-                        PD_CK(cudaMalloc(&d_out, sizeof(int2) * (size_t)total));
+                        PD_CK(pn_alloc(&d_out, sizeof(int2) * (size_t)total));
                         a.out = d_out;
                         pn_cells_kernel<true><<<(rq->n_a + 127) / 128, 128>>>(a, G, cell_start, sorted_b, d_err, d_tests, nullptr, seg_start);
                         PD_CK(cudaGetLastError());
@@ -920,7 +939,7 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         if (!used_cells) {
             // brute force (few instances, or a box of fewer than 3 cells per component): pairs are appended as they are found
             // and ordered on the host
-            PD_CK(cudaMalloc(&d_out, sizeof(int2) * (size_t)std::max<int64_t>(capacity, 1)));
+            PD_CK(pn_alloc(&d_out, sizeof(int2) * (size_t)std::max<int64_t>(capacity, 1)));
             a.out = d_out;
             const int bx = (rq->n_a + PC_THREADS - 1) / PC_THREADS;
             int splits = std::max(1, (148 * 8 + bx - 1) / bx);
@@ -946,6 +965,8 @@ extern "C" int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *r
         }
     }
 done:
-    cudaFree(d_pos); cudaFree(d_raw); cudaFree(d_cut); cudaFree(d_idx); cudaFree(d_out); cudaFree(d_count); cudaFree(d_cellbuf); cudaFree(d_aux);
+    for (void *ptr : { (void *)d_pos, (void *)d_raw, (void *)d_cut, (void *)d_idx, (void *)d_out, (void *)d_count, (void *)d_cellbuf, (void *)d_aux })
+        if (ptr) cudaFreeAsync(ptr, 0);
+    cudaStreamSynchronize(0);
     return rc;
 }

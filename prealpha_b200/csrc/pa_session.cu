@@ -242,6 +242,16 @@ void pa_trim(void)
     }
     pool_trim();
     pa_multi_device_trim();
+    // the stream-ordered work buffers of pa_neighbour_pairs (default memory pool of every device this process has used)
+    int n = 0, cur = 0;
+    if (cudaGetDeviceCount(&n) == cudaSuccess && cudaGetDevice(&cur) == cudaSuccess) {
+        for (int d = 0; d < n; ++d) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        }
+        cudaSetDevice(cur);
+    }
+    cudaGetLastError();
 }
 const char *pa_last_error(void) { return g_last_error.c_str(); }
 
