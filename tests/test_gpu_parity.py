@@ -657,3 +657,18 @@ print("ok")
         env["PA_NCCL_MIN_BYTES"] = "0"                 # small accumulators default to peer copies: force the ncclReduce path
     out = subprocess.run([os.sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and out.stdout.strip().endswith("ok"), out.stdout + out.stderr
+
+
+def test_large_batches_equal_single_frame_batches():
+    """Batches of tens of MB are copied into the page-locked staging buffer by several host threads (pa_session_upload):
+    40 frames of 70 000 atoms in batches of 20 frames (16.8 MB each, two copy threads, exactness scan included) against
+    the same frames one per batch; a frame with a coordinate outside the exactness range sits in the middle of a batch."""
+    traj = _big_system(seed=33, n1=34000, n2=36000, L=110.0, nsteps=40)
+    traj.xyz[1][23, 17, 0, 2] = np.float32(3.0e-6)               # |z| < 2^-17: this batch must take the non-symmetric passes
+    jobs = [api.job_setup(traj, capi.make_request(sampling_interval=1, mode="pdf", ref_type=r, obs_type=-1, bin_a=400, bin_b=1, maxdist_optimize=True))
+            for r in (1, 2)]
+    big = api.histogram_multi(traj, jobs, api.make_exec(frames_per_batch=20))
+    one = api.histogram_multi(traj, jobs, api.make_exec(frames_per_batch=1))
+    assert big[3].frames_done == one[3].frames_done == 40 and big[3].kernel_launches < one[3].kernel_launches
+    for k in range(2):
+        assert np.array_equal(big[0][k], one[0][k]) and big[1][k] == one[1][k] and big[2][k] == one[2][k], k
