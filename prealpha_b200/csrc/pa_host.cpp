@@ -32,7 +32,6 @@ inline int int_of_float_x86(float x)                   // cvttss2si
     if (!(x > -2147483904.0f && x < 2147483648.0f)) return INT_MIN;
     return (int)x;
 }
-inline int plus1_wrap(int v) { return (int)((unsigned)v + 1u); }
 
 void normalize3(double v[3])                            // SETTINGS:1052-1059
 {
