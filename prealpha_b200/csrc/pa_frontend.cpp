@@ -16,6 +16,7 @@
 #include <chrono>
 #include <array>
 #include <algorithm>
+#include <functional>
 #include <mutex>
 #include <deque>
 #include <condition_variable>
@@ -321,6 +322,7 @@ struct TrajStream {
     std::vector<char> buf;
     size_t have = 0;                    // valid bytes in buf
     bool eof = false;
+    size_t file_off = 0;                // bytes of the text file consumed into buf so far
     int frames_done = 0;                // frames parsed so far = index of the next frame
     double t_read = 0, t_count = 0, t_parse = 0;
     // binary frame cache (see below): read side / write side
@@ -531,32 +533,83 @@ int read_frames(Run &r, TrajStream &ts, int want_frames, const std::vector<float
         }
     };
     const unsigned nthreads = std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
-    const size_t block_bytes = (size_t)64 << 20;
+    size_t block_bytes = (size_t)64 << 20;
+    if (const char *e = getenv("PA_READ_BLOCK")) block_bytes = (size_t)std::max(64, atoi(e));      // test hook: bytes per read
     std::vector<char> &buf = ts.buf;
     int steps_read = 0;
+    // runs fn(k, begin, end) for nthreads equal byte ranges of [0, n) on the host threads (ranges >= `grain` bytes)
+    auto parallel_ranges = [&](size_t n, size_t grain, const std::function<void(unsigned, size_t, size_t)> &fn) {
+        const unsigned nt = (unsigned)std::max<size_t>(1, std::min<size_t>(nthreads, n / std::max<size_t>(grain, 1)));
+        if (nt <= 1) { fn(0, 0, n); return 1u; }
+        std::vector<std::thread> th;
+        for (unsigned k = 0; k < nt; ++k) th.emplace_back([&, k] { fn(k, n * k / nt, n * (k + 1) / nt); });
+        for (auto &x : th) x.join();
+        return nt;
+    };
     while (steps_read < want_frames) {
         // 1. top up the buffer (only when it does not already hold a whole frame)
         double t0 = now_s();
         const int want = want_frames - steps_read;
         long long nl = 0; size_t end = 0; int nframes = 0;
+        // how many whole frames does the buffer hold, and where does the last of them end?  Newlines are counted on all
+        // host threads (byte ranges), the frame boundary is then located inside the one range that contains it.
         auto count_frames = [&] {
             nl = 0; end = 0; nframes = 0;
-            for (const char *p = buf.data(), *lim = buf.data() + ts.have; p < lim && nframes < want;) {
+            std::vector<long long> cnt(nthreads, 0);
+            std::vector<size_t> rb(nthreads + 1, ts.have);
+            const unsigned nt = parallel_ranges(ts.have, (size_t)1 << 20, [&](unsigned k, size_t b, size_t e) {
+                rb[k] = b;
+                long long c = 0;
+                for (const char *p = buf.data() + b, *lim = buf.data() + e; p < lim;) {
+                    const char *q = (const char *)memchr(p, '\n', (size_t)(lim - p));
+                    if (!q) break;
+                    ++c; p = q + 1;
+                }
+                cnt[k] = c;
+            });
+            rb[nt] = ts.have;
+            for (unsigned k = 0; k < nt; ++k) nl += cnt[k];
+            nframes = (int)std::min<long long>(want, nl / lines_per_frame);
+            if (nframes == 0) return;
+            long long need = (long long)nframes * lines_per_frame;         // the need-th newline ends the last whole frame
+            unsigned k = 0;
+            while (k + 1 < nt && need > cnt[k]) { need -= cnt[k]; ++k; }
+            const char *p = buf.data() + rb[k], *lim = buf.data() + rb[k + 1];
+            while (need > 0 && p < lim) {
                 const char *q = (const char *)memchr(p, '\n', (size_t)(lim - p));
                 if (!q) break;
-                ++nl; p = q + 1;
-                if (nl % lines_per_frame == 0) { ++nframes; end = (size_t)(p - buf.data()); }
+                --need; p = q + 1;
             }
+            end = (size_t)(p - buf.data());
+            nl = (long long)nframes * lines_per_frame;
         };
         if (ts.have > 0) count_frames();
         ts.t_count += now_s() - t0; t0 = now_s();
         if (nframes < want && !ts.eof) {
             if (buf.size() < ts.have + block_bytes + 1) buf.resize(ts.have + block_bytes + 1);
-            const size_t got = fread(buf.data() + ts.have, 1, block_bytes, ts.f);
+            // the next block of the file, read by several threads at once (page-cache copies scale with the threads)
+            const int fd = fileno(ts.f);
+            std::vector<size_t> part(nthreads, 0);
+            std::vector<size_t> asked(nthreads, 0);
+            const off_t base = (off_t)ts.file_off;
+            char *into = buf.data() + ts.have;
+            const unsigned nt = parallel_ranges(block_bytes, (size_t)4 << 20, [&](unsigned k, size_t b, size_t e) {
+                asked[k] = e - b;
+                size_t done = 0;
+                while (done < e - b) {
+                    const ssize_t got = pread(fd, into + b + done, e - b - done, base + (off_t)(b + done));
+                    if (got <= 0) break;
+                    done += (size_t)got;
+                }
+                part[k] = done;
+            });
+            size_t got = 0;                                               // contiguous bytes from the start of the block
+            for (unsigned k = 0; k < nt; ++k) { got += part[k]; if (part[k] < asked[k]) break; }
+            ts.file_off += got;
             ts.have += got;
             if (got < block_bytes) { ts.eof = true; if (ts.have && buf[ts.have - 1] != '\n') buf[ts.have++] = '\n'; }
             ts.t_read += now_s() - t0; t0 = now_s();
-            // 2. how many whole frames does it hold?  (count newlines, stop at the last frame boundary)
+            // 2. how many whole frames does it hold now?
             count_frames();
             ts.t_count += now_s() - t0; t0 = now_s();
         }

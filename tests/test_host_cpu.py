@@ -358,3 +358,38 @@ def test_binary_frame_cache_is_written_validated_and_reused(tmp_path):
     cdir = tmp_path / "elsewhere"; cdir.mkdir()
     rc, out = _run_general_inp(wd, {"PREALPHA_B200_CACHE": str(cdir)})
     assert (cdir / "traj.xyz.pab200cache").exists()
+
+
+@pytest.mark.parametrize("fmt,block,trailing_newline", [("xyz", 64, True), ("xyz", 257, False), ("xyz", 5000, True), ("lmp", 97, True),
+                                                        ("lmp", 100000, False), ("xyz", 1 << 20, True)])
+def test_block_reader_is_independent_of_block_and_thread_boundaries(fmt, block, trailing_newline, tmp_path):
+    """The threaded text reader (read_frames: blocks read by several threads, newlines counted on byte ranges, frames cut
+    at the newline count, lines parsed on all host threads) with blocks far smaller than a frame, blocks holding many
+    frames, a last line without newline, lmp headers and a two-type molecule table: the float32 payload it leaves in the
+    binary frame cache equals numpy's correctly rounded float32 of every number in the text, whatever the block size
+    (PA_READ_BLOCK is the test hook for the bytes per read)."""
+    wd = tmp_path / "blk"; wd.mkdir()
+    rng = np.random.default_rng(block)
+    nsteps, n1, n2 = 13, 7, 5                                     # type 1: 7 molecules of 2 atoms, type 2: 5 atoms
+    n = 2 * n1 + n2
+    lines, exp = [], np.zeros((nsteps, n, 3), dtype=np.float32)
+    for s in range(nsteps):
+        if fmt == "xyz":
+            lines += [f"{n}", f"step {s}"]
+        else:
+            lines += ["ITEM: TIMESTEP", f"{s * 10}", "ITEM: NUMBER OF ATOMS", f"{n}", "ITEM: BOX BOUNDS pp pp pp", "0.0 12.0", "0.0 12.0", "0.0 12.0",
+                      "ITEM: ATOMS element xu yu zu"]
+        for a in range(n):
+            txt = [f"{v:.{int(rng.integers(1, 9))}f}" if rng.random() < 0.8 else f"{v:.4e}" for v in (rng.random(3) - 0.2) * 15.0]
+            pad = " " * int(rng.integers(1, 4))
+            lines.append(("  " if a % 3 == 0 else "") + ("C" if a < 2 * n1 else "Na") + pad + pad.join(txt) + ("  " if a % 5 == 0 else ""))
+            exp[s, a] = [np.float32(t) for t in txt]
+    (wd / f"traj.{fmt}").write_text("\n".join(lines) + ("\n" if trailing_newline else ""))
+    (wd / "molecular.inp").write_text(f" {nsteps}\n 2\n +0 2 {n1}\n +0 1 {n2}\nquit\n")
+    (wd / "general.inp").write_text(f' "traj.{fmt}"\n "molecular.inp"\n "./"\n "./"\n "./"\n' + (" cubic_box_edge 0.0 12.0\n" if fmt == "xyz" else "") +
+                                    f" trajectory_type {fmt}\n sequential_read F\n quit\n")
+    rc, out = _run_general_inp(wd, {"PREALPHA_B200_CACHE": "1", "PA_READ_BLOCK": str(block)})
+    assert rc == 0 and f"reading the trajectory...done ({nsteps} steps of {n} atoms" in out, out
+    blob = (wd / f"traj.{fmt}.pab200cache").read_bytes()
+    data = np.frombuffer(blob[-12 * n * nsteps:], dtype=np.float32).reshape(nsteps, n, 3)
+    assert np.array_equal(data.view(np.uint32), exp.view(np.uint32))
