@@ -139,8 +139,9 @@ typedef struct pa_job {
  * the analogue of `set_threads` (Main:3313-3330) for the parallel region
  * Distribution:704-753 -- sharding frames when there are at least ndevices
  * sampled frames and tiles otherwise, and combines the int64 accumulators on
- * `device` with one ncclReduce over NVLink (peer copies + an add kernel when
- * libnccl cannot be loaded).  ndevices < 0: all usable devices.  The caller's
+ * `device` over NVLink: peer copies + an add kernel for the usual few KB, one
+ * ncclReduce from 4 MiB of accumulators on (environment PA_NCCL_MIN_BYTES).
+ * ndevices < 0: all usable devices.  The caller's
  * shard_* / tile_shard_* then describe this process's share of a larger job
  * and are subdivided further. */
 typedef struct pa_exec {
