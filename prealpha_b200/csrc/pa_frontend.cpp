@@ -193,6 +193,8 @@ struct Run {
     std::map<std::string, float> mass_override, charge_override;
     int errors = 0;
     pa_exec exec{};
+    // test seam of the speciation bookkeeping (pa_debug_run_general_input_with_connections): rows of 8 int32
+    const int32_t *dbg_conns = nullptr; int64_t dbg_nconns = 0; int spec_calls = 0;
     // Distances:288-296: set_defaults() does NOT reset these two, they persist between `distance` lines
     bool dist_calc_exp = false, dist_calc_ffc = false;
 
@@ -1670,6 +1672,575 @@ int perform_cluster(Run &r, const std::string &input_name)
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// `speciation` keyword (Module_Speciation, statistics path): donor / acceptor coordination species.
+//   input      read_acceptors_and_donors (Speciation:978-1256), read_body (:400-679: atom groups, N_species, N_neighbours,
+//              nsteps, sampling_interval, use_ccc; the switches of the outputs that are not built are read and ignored)
+//   neighbours the REAL(4) test of Speciation:1420-1428 for every acceptor atom x donor atom of a step, cutoffs
+//              (r_acceptor + r_donor)**2 -- ONE pa_neighbour_pairs call per step and acceptor molecule type on the GPU
+//   replay     the species clipboard of every acceptor molecule in the reference's loop order (:1383-1483), collapse to
+//              atom groups and ordering (:1990-2078), recognition of an already known species by the greedy molecule
+//              matching of :1778-1870, occurrence counts, communal cluster correction (:1509-1590, :1660-1674)
+//   output     <prefix>acceptorN_speciation_statistics.dat and ..._speciation_statistics_table.dat (:2082-2885)
+// Not built: the first / last structure dumps (speciesN_first.xyz ...), the species time series and its intermittent
+// autocorrelation function, `group_elements` and covalence-radius cutoffs (negative radii).
+struct SpecConn { int n_donor, dmol, dentry, aentry; };       // 1-based; dentry / aentry = position in the atom_index_list
+struct SpecSide {
+    int type = 0;                                              // molecule_type_index
+    std::vector<int> atom, group;                              // atom_index_list(:,1), (:,2): own index, or -group number
+    std::vector<float> radius;                                 // cutoff_list
+    int n_groups = 0;
+};
+struct SpecMolRange { int first, extra; bool unmatched; };     // neighbour_molecule_starting_indices
+struct SpecSpecies {
+    int nconn = 0, natoms = 0, nmol = 0;
+    long long occurrences = 0;
+    std::vector<std::array<int, 4>> conn;                      // collapsed + ordered: donor type, donor molecule, donor group, acceptor group
+    std::vector<SpecMolRange> mol;
+    std::vector<std::array<double, 2>> ccc;                    // per donor type: sum of 1/sharing acceptors, connections
+};
+struct SpecDvs { int id, n_donor, parent; };
+
+static std::string sum_formula(const HostType &t)             // give_sum_formula, Molecular:2194-2222
+{
+    std::string out;
+    std::vector<char> used(t.elements.size(), 0);
+    for (size_t o = 0; o < t.elements.size(); ++o) {
+        if (used[o]) continue;
+        int n = 1;
+        for (size_t i = o + 1; i < t.elements.size(); ++i) if (t.elements[i] == t.elements[o]) { used[i] = 1; ++n; }
+        out += t.elements[o];
+        if (n > 1) out += std::to_string(n);
+    }
+    return out;
+}
+
+// source of the connections of one step and acceptor type: per acceptor molecule, in the reference's loop order
+// (donor type, donor molecule, donor atom, acceptor atom)
+using SpecSource = std::function<int(int step, int n_acceptor, std::vector<std::vector<SpecConn>> &per_molecule)>;
+
+int perform_speciation(Run &r, const std::string &input_name)
+{
+    std::vector<std::string> lines;
+    if (!read_lines(r.path_in + input_name, lines)) { r.error(158, "speciation input file '" + r.path_in + input_name + "' not found"); return 158; }
+    std::vector<std::vector<std::string>> toks;
+    for (auto &l : lines) { auto t = tokens_of(l); if (!t.empty()) toks.push_back(t); }
+    const int nt = (int)r.types.size();
+    size_t ln = 0;
+    std::vector<SpecSide> acc, don;
+    auto read_side = [&](std::vector<SpecSide> &side, const char *what) -> int {
+        int n = 0;
+        if (ln >= toks.size() || !parse_int(toks[ln][0], n)) { r.error(155, "incorrect format in speciation input"); return 155; }
+        ++ln;
+        if (r.verbose) printf(" reading %d user-specified %s atoms...\n", n, what);
+        int good = 0;
+        for (int k = 0; k < n; ++k, ++ln) {
+            int ty, at; float cut;
+            if (ln >= toks.size() || toks[ln].size() < 3 || !parse_int(toks[ln][0], ty) || !parse_int(toks[ln][1], at) || !parse_real4(toks[ln][2], cut)) {
+                r.error(155, "incorrect format in speciation input"); return 155;
+            }
+            if (ty < 1 || ty > nt) { r.error(33, "invalid molecule type index in speciation input"); return 33; }
+            if (at < 1 || at > r.types[ty - 1].natoms) { r.error(111, "invalid atom index in speciation input"); continue; }
+            if (cut < -0.1f) { r.error(158, "covalence-radius cutoffs (negative radius) are not available in the B200 drop-in"); return 158; }
+            SpecSide *s = nullptr;
+            for (SpecSide &q : side) if (q.type == ty) s = &q;
+            if (!s) { side.emplace_back(); s = &side.back(); s->type = ty; }
+            s->atom.push_back(at); s->group.push_back(at); s->radius.push_back(cut);
+            ++good;
+        }
+        if (good < 1) { r.error(159, std::string("no valid ") + what + " atoms"); return 159; }
+        if (r.verbose) {
+            printf(" Successfully read %d %s atoms:\n", good, what);
+            for (const SpecSide &q : side) {
+                printf("    Molecule type %d (%s):\n", q.type, sum_formula(r.types[q.type - 1]).c_str());
+                for (size_t i = 0; i < q.atom.size(); ++i) {
+                    printf("      Atom index %d (%s), cutoff ", q.atom[i], r.types[q.type - 1].elements[q.atom[i] - 1].c_str());
+                    if (q.radius[i] < 0.01f) printf("< 0.01\n"); else printf("= %.2f\n", (double)q.radius[i]);
+                }
+            }
+        }
+        return 0;
+    };
+    if (int rc = read_side(acc, "acceptor")) return rc;
+    if (int rc = read_side(don, "donor")) return rc;
+    // ---- read_body --------------------------------------------------------------------------------------
+    int nsteps = 100, sampling = 1, max_species = 11, max_conn = 10, group_type = 0;
+    bool atoms_grouped = false, use_ccc = false;
+    for (; ln < toks.size(); ++ln) {
+        const auto &t = toks[ln];
+        const std::string &k = t[0];
+        int i1; bool b1;
+        if (k == "quit") break;
+        if (k == "maximum_number_of_connections" || k == "neighbours" || k == "N_neighbours") {
+            if (t.size() > 1 && parse_int(t[1], i1)) max_conn = i1; else r.error(158, "cannot read 'maximum_number_of_connections'");
+        } else if (k == "maximum_number_of_species" || k == "species" || k == "N_species") {
+            if (t.size() > 1 && parse_int(t[1], i1)) max_species = i1; else r.error(158, "cannot read 'maximum_number_of_species'");
+        } else if (k == "nsteps" || k == "n_steps") {
+            if (t.size() > 1 && parse_int(t[1], i1)) nsteps = i1; else r.error(158, "cannot read 'nsteps'");
+        } else if (k == "sampling_interval") {
+            if (t.size() > 1 && parse_int(t[1], i1)) sampling = i1; else r.error(158, "cannot read 'sampling_interval'");
+        } else if (k == "ccc" || k == "use_ccc" || k == "cluster_correction" || k == "use_cluster_correction" || k == "communal_solvation" ||
+                   k == "use_communal_solvation" || k == "use_communal_cluster_correction" || k == "communal_cluster_correction") {
+            if (t.size() > 1 && parse_logical(t[1], b1)) use_ccc = b1; else r.error(158, "cannot read 'communal_cluster_correction'");
+        } else if (k == "group_elements" || k == "group_element_names" || k == "group_element_symbols") {
+            r.error(158, "'group_elements' is not available in the B200 drop-in"); return 158;
+        } else if (k == "new_acceptor_group" || k == "acceptor_new_group" || k == "acceptor_group" || k == "acceptors_new_group" ||
+                   k == "new_donor_group" || k == "donor_new_group" || k == "donor_group" || k == "donors_new_group") {
+            const bool is_acc = k.find("acceptor") != std::string::npos;
+            if (!(t.size() > 1 && parse_int(t[1], i1))) { r.error(158, "cannot read the molecule type of the new group"); continue; }
+            group_type = i1;
+            if (!atoms_grouped) {
+                printf("   turned on atom groups.\n");
+                for (SpecSide &q : (is_acc ? acc : don)) q.n_groups = 0;
+            }
+            bool ok = false;
+            std::vector<SpecSide> &side = is_acc ? acc : don;
+            for (size_t n = 0; n < side.size(); ++n)
+                if (side[n].type == i1) {
+                    ok = true;
+                    side[n].n_groups += 1;
+                    if (r.verbose) printf("   Added group %d to %s #%zu (molecule_type_index %d)\n", side[n].n_groups, is_acc ? "acceptor" : "donor", n + 1, i1);
+                    atoms_grouped = true;
+                }
+            if (!ok) r.error(110, "no such molecule type among the " + std::string(is_acc ? "acceptors" : "donors"));
+        } else if (k == "assign_to_acceptor_group" || k == "assign_atom_to_acceptor_group" || k == "add_to_acceptor_group" || k == "add_atom_to_acceptor_group" ||
+                   k == "assign_to_donor_group" || k == "assign_atom_to_donor_group" || k == "add_to_donor_group" || k == "add_atom_to_donor_group") {
+            const bool is_acc = k.find("acceptor") != std::string::npos;
+            if (!atoms_grouped || group_type == 0) { r.error(164, "open a group before assigning atoms to it"); continue; }
+            if (!(t.size() > 1 && parse_int(t[1], i1))) { r.error(158, "cannot read the atom index"); continue; }
+            bool ok = false;
+            for (SpecSide &q : (is_acc ? acc : don))
+                if (q.type == group_type)
+                    for (size_t i = 0; i < q.atom.size(); ++i)
+                        if (q.atom[i] == i1) {
+                            ok = true;
+                            q.group[i] = -q.n_groups;
+                            if (r.verbose) printf("   Added atom_index %d to %s group #%d (molecule_type_index %d)\n", i1, is_acc ? "acceptor" : "donor", q.n_groups, group_type);
+                        }
+            if (!ok) r.error(111, "invalid atom index in group assignment");
+        }
+        // print_beads, use_log, autocorrelation, tmax: switches of outputs that are not part of this path
+    }
+    if (nsteps < 1) { r.error(57, "timestep out of range"); nsteps = 1; }
+    else if (nsteps > r.nsteps) { r.error(57, "timestep out of range"); nsteps = r.nsteps; }
+    if (sampling < 1) sampling = 1;
+    if (max_conn < 1 || max_species < 1) { r.error(158, "N_species and N_neighbours must be positive"); return 158; }
+    const int NA = (int)acc.size(), ND = (int)don.size();
+    const int navg = std::max((nsteps - 1 + sampling) / sampling, 0);
+    printf(" Using %d timesteps in intervals of %d for averaging.\n Starting speciation analysis.\n", navg, sampling);
+    printf(" (B200 drop-in: neighbour pairs on the GPU, species bookkeeping replayed in the reference's order; structure dumps and\n"
+           "  the species autocorrelation function are not part of the accelerated path.)\n");
+    // ---- the neighbour stage ---------------------------------------------------------------------------------
+    std::vector<int> acc_off(NA + 1, 0), don_off(ND + 1, 0);   // global entry index (cutoff classes)
+    for (int n = 0; n < NA; ++n) acc_off[n + 1] = acc_off[n] + (int)acc[n].atom.size();
+    for (int n = 0; n < ND; ++n) don_off[n + 1] = don_off[n] + (int)don[n].atom.size();
+    std::vector<float> cut_sq((size_t)acc_off[NA] * don_off[ND]);
+    for (int n = 0; n < NA; ++n)
+        for (size_t a = 0; a < acc[n].atom.size(); ++a)
+            for (int m = 0; m < ND; ++m)
+                for (size_t b = 0; b < don[m].atom.size(); ++b) {
+                    const float d = acc[n].radius[a] + don[m].radius[b];           // REAL :: real_space_distance, Speciation:386-389
+                    cut_sq[(size_t)(acc_off[n] + (int)a) * don_off[ND] + (size_t)(don_off[m] + (int)b)] = d * d;
+                }
+    std::vector<int32_t> b_inst, b_cls;
+    std::vector<int> b_ndonor, b_mol, b_entry;
+    for (int m = 0; m < ND; ++m)
+        for (int mol = 1; mol <= r.types[don[m].type - 1].nmol; ++mol)
+            for (size_t b = 0; b < don[m].atom.size(); ++b) {
+                b_inst.push_back(don[m].type); b_inst.push_back(mol); b_inst.push_back(don[m].atom[b]);
+                b_cls.push_back(don_off[m] + (int)b);
+                b_ndonor.push_back(m + 1); b_mol.push_back(mol); b_entry.push_back((int)b + 1);
+            }
+    std::vector<pa_type> types; pa_traj traj;
+    make_traj(r, types, traj);
+    std::vector<pa_neigh_pair> found((size_t)1 << 16);
+    long long tests_total = 0, pairs_total = 0;
+    SpecSource gpu_source = [&](int step, int n_acc, std::vector<std::vector<SpecConn>> &per_mol) -> int {
+        const SpecSide &A = acc[n_acc - 1];
+        const int nmol = r.types[A.type - 1].nmol, na_e = (int)A.atom.size();
+        std::vector<int32_t> a_inst, a_cls;
+        for (int mol = 1; mol <= nmol; ++mol)
+            for (int a = 0; a < na_e; ++a) { a_inst.push_back(A.type); a_inst.push_back(mol); a_inst.push_back(A.atom[a]); a_cls.push_back(acc_off[n_acc - 1] + a); }
+        pa_neigh_request rq{};
+        rq.timestep = step; rq.n_a = nmol * na_e; rq.n_b = (int)b_cls.size(); rq.a = a_inst.data(); rq.b = b_inst.data();
+        rq.a_class = a_cls.data(); rq.b_class = b_cls.data(); rq.n_class_a = acc_off[NA]; rq.n_class_b = don_off[ND];
+        rq.cutoff_sq = cut_sq.data(); rq.same_list = 0; rq.skip_same_molecule = 1;     // Speciation:1394-1395
+        int64_t count = 0;
+        for (;;) {
+            int64_t tests = 0;
+            const int rc = pa_neighbour_pairs(&traj, &rq, &r.exec, found.data(), (int64_t)found.size(), &count, &tests);
+            if (rc) return rc;
+            if (count <= (int64_t)found.size()) { tests_total += tests; pairs_total += count; break; }
+            found.resize((size_t)count);
+        }
+        per_mol.assign((size_t)nmol, {});
+        for (int64_t q = 0; q < count; ++q) {
+            const int ia = found[q].ia, ib = found[q].ib;
+            per_mol[(size_t)(ia / na_e)].push_back({ b_ndonor[ib], b_mol[ib], b_entry[ib], ia % na_e + 1 });
+        }
+        // pairs arrive ordered by (acceptor atom, donor instance); the reference's loops run donor type, donor molecule,
+        // donor atom, acceptor atom
+        for (auto &v : per_mol)
+            std::stable_sort(v.begin(), v.end(), [](const SpecConn &x, const SpecConn &y) {
+                if (x.n_donor != y.n_donor) return x.n_donor < y.n_donor;
+                if (x.dmol != y.dmol) return x.dmol < y.dmol;
+                if (x.dentry != y.dentry) return x.dentry < y.dentry;
+                return x.aentry < y.aentry;
+            });
+        return 0;
+    };
+    // test seam (pa_debug_run_general_input_with_connections): the connections come from a table the caller computed, so
+    // that the bookkeeping below can be checked on a machine without a GPU; pa_run_general_input never takes this branch
+    const int call_ordinal = r.spec_calls++;
+    SpecSource table_source = [&](int step, int n_acc, std::vector<std::vector<SpecConn>> &per_mol) -> int {
+        per_mol.assign((size_t)r.types[acc[n_acc - 1].type - 1].nmol, {});
+        for (int64_t q = 0; q < r.dbg_nconns; ++q) {
+            const int32_t *c = r.dbg_conns + 8 * q;
+            if (c[0] != call_ordinal || c[1] != step || c[2] != n_acc) continue;
+            if (c[3] < 1 || c[3] > (int)per_mol.size()) return PA_ERR_BAD_ARG;
+            per_mol[(size_t)c[3] - 1].push_back({ c[4], c[5], c[6], c[7] });
+        }
+        for (auto &v : per_mol)
+            std::stable_sort(v.begin(), v.end(), [](const SpecConn &x, const SpecConn &y) {
+                if (x.n_donor != y.n_donor) return x.n_donor < y.n_donor;
+                if (x.dmol != y.dmol) return x.dmol < y.dmol;
+                if (x.dentry != y.dentry) return x.dentry < y.dentry;
+                return x.aentry < y.aentry;
+            });
+        return 0;
+    };
+    const SpecSource &source = r.dbg_conns ? table_source : gpu_source;
+    // ---- replay ------------------------------------------------------------------------------------------------
+    std::vector<std::vector<SpecSpecies>> species(NA);
+    std::vector<long long> none(NA, 0), species_overflow(NA, 0);
+    long long neighbour_atom_overflow = 0;
+    int maxmol = 0;
+    for (const SpecSide &A : acc) maxmol = std::max(maxmol, r.types[A.type - 1].nmol);
+    std::vector<SpecDvs> dvs((size_t)maxmol * max_conn + 2, SpecDvs{ 0, 0, 0 });     // donor_vs_species_list (persistent, :1298)
+    std::vector<int> donor_id_off(ND + 1, 0);
+    for (int m = 0; m < ND; ++m) donor_id_off[m + 1] = donor_id_off[m] + r.types[don[m].type - 1].nmol;
+    const auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::vector<SpecConn>> per_mol;
+    for (int step = 1; step <= nsteps; step += sampling) {
+        for (int n_acc = 1; n_acc <= NA; ++n_acc) {
+            const SpecSide &A = acc[n_acc - 1];
+            std::vector<SpecSpecies> &list = species[n_acc - 1];
+            if (int rc = source(step, n_acc, per_mol)) { r.error(rc, std::string("GPU neighbour search failed: ") + pa_last_error()); return rc; }
+            int logged = 0, new_conn = 0;
+            for (size_t am = 0; am < per_mol.size(); ++am) {
+                // ---- clipboard of this acceptor molecule (:1383-1470) ----
+                SpecSpecies clip;
+                new_conn = 0;
+                {
+                    int cur_nd = -1, cur_mol = -1, cur_atom = -1;
+                    bool atom_counted = false, mol_counted = false;
+                    for (const SpecConn &c : per_mol[am]) {
+                        if (c.n_donor != cur_nd || c.dmol != cur_mol) { cur_nd = c.n_donor; cur_mol = c.dmol; cur_atom = -1; mol_counted = false; }
+                        if (c.dentry != cur_atom) { cur_atom = c.dentry; atom_counted = false; }
+                        if (clip.nconn == max_conn) { ++neighbour_atom_overflow; continue; }
+                        clip.conn.push_back({ c.n_donor, c.dmol, c.dentry, c.aentry });
+                        ++clip.nconn;
+                        if (!atom_counted) { atom_counted = true; ++clip.natoms; if (!mol_counted) { mol_counted = true; ++clip.nmol; } }
+                        if (use_ccc) {
+                            ++new_conn;
+                            SpecDvs &d = dvs[(size_t)(logged + new_conn)];
+                            d.id = donor_id_off[c.n_donor - 1] + c.dmol; d.n_donor = c.n_donor;
+                        }
+                    }
+                }
+                int observed = 0;
+                if (clip.nconn == 0) { ++none[n_acc - 1]; }
+                else {
+                    // ---- collapse_and_sort_atom_indices (:1990-2078) ----
+                    for (auto &c : clip.conn) { c[2] = don[c[0] - 1].group[c[2] - 1]; c[3] = A.group[c[3] - 1]; }
+                    auto sort_level = [&](int level, int first, int last) {           // insertion sort, positions first..last (0-based, inclusive)
+                        for (int i = first + 1; i <= last; ++i) {
+                            const std::array<int, 4> x = clip.conn[i];
+                            int j = i;
+                            while (j > first && clip.conn[j - 1][level] > x[level]) { clip.conn[j] = clip.conn[j - 1]; --j; }
+                            clip.conn[j] = x;
+                        }
+                    };
+                    auto finish_molecule = [&](int first, int last) {
+                        clip.mol.push_back({ first, last - first, false });
+                        sort_level(2, first, last);
+                        int afirst = first, cur = clip.conn[first][2];
+                        for (int i = first; i < last; ++i)
+                            if (clip.conn[i + 1][2] != cur) { sort_level(3, afirst, i); afirst = i + 1; cur = clip.conn[i + 1][2]; }
+                        sort_level(3, afirst, last);
+                    };
+                    {
+                        int first = 0;
+                        for (int i = 0; i + 1 < clip.nconn; ++i)
+                            if (clip.conn[i + 1][0] != clip.conn[first][0] || clip.conn[i + 1][1] != clip.conn[first][1]) { finish_molecule(first, i); first = i + 1; }
+                        finish_molecule(first, clip.nconn - 1);
+                    }
+                    // ---- is it a known species?  (:1739-1772) ----
+                    std::vector<char> potential(list.size(), 1);
+                    for (size_t s = 0; s < list.size(); ++s)                          // eliminate_number_mismatches
+                        if (list[s].nconn != clip.nconn || list[s].natoms != clip.natoms || list[s].nmol != clip.nmol) potential[s] = 0;
+                    for (size_t s = 0; s < list.size(); ++s) {                        // eliminate_connection_mismatches
+                        if (!potential[s]) continue;
+                        SpecSpecies &ref = list[s];
+                        bool success = false;
+                        for (auto &m : clip.mol) m.unmatched = true;
+                        for (auto &m : ref.mol) m.unmatched = true;
+                        const int nm = clip.nmol;
+                        for (int cm = 0; cm < nm && !success; ++cm) {
+                            if (cm >= (int)clip.mol.size() || !clip.mol[cm].unmatched) continue;
+                            for (int rm = 0; rm < nm; ++rm) {
+                                if (rm >= (int)ref.mol.size()) break;
+                                if (!ref.mol[rm].unmatched || !clip.mol[cm].unmatched) continue;
+                                bool mismatch = false;
+                                if (clip.mol[cm].extra != ref.mol[rm].extra) mismatch = true;
+                                else
+                                    for (int k = 0; k <= ref.mol[rm].extra; ++k) {
+                                        const auto &x = ref.conn[(size_t)(ref.mol[rm].first + k)];
+                                        const auto &y = clip.conn[(size_t)(clip.mol[cm].first + k)];
+                                        if (x[0] != y[0] || x[2] != y[2] || x[3] != y[3]) { mismatch = true; break; }
+                                    }
+                                if (!mismatch) {
+                                    clip.mol[cm].unmatched = false; ref.mol[rm].unmatched = false;
+                                    bool any = false;
+                                    for (auto &m : clip.mol) any = any || m.unmatched;
+                                    for (auto &m : ref.mol) any = any || m.unmatched;
+                                    if (!any) { success = true; break; }
+                                }
+                            }
+                        }
+                        potential[s] = success ? 1 : 0;
+                    }
+                    int match = -1;
+                    for (size_t s = 0; s < list.size(); ++s) if (potential[s]) { match = (int)s; break; }
+                    if (match < 0) {                                                  // append_species
+                        if ((int)list.size() < max_species) {
+                            clip.occurrences = 1;
+                            clip.ccc.assign((size_t)ND, { 0.0, 0.0 });
+                            list.push_back(clip);
+                            observed = (int)list.size();
+                        } else { ++species_overflow[n_acc - 1]; observed = 0; }
+                    } else { list[(size_t)match].occurrences += 1; observed = match + 1; }
+                }
+                if (use_ccc && new_conn > 0 && observed > 0) {
+                    for (int k = 1; k <= new_conn; ++k) dvs[(size_t)(logged + k)].parent = observed;
+                    logged += new_conn;
+                }
+            }
+            // ---- communal cluster correction of this step (:1509-1590) ----
+            if (use_ccc && logged > 0) {
+                if (logged == 1) {
+                    // [sic] the donor type is read at position logged_connections + new_connections, new_connections being
+                    // that of the LAST acceptor molecule of the loop (Speciation:1516-1523)
+                    const SpecDvs &d = dvs[(size_t)std::min<long long>((long long)logged + new_conn, (long long)dvs.size() - 1)];
+                    const int sp = dvs[1].parent;
+                    if (sp >= 1 && sp <= (int)list.size() && d.n_donor >= 1 && d.n_donor <= ND) {
+                        list[(size_t)sp - 1].ccc[(size_t)d.n_donor - 1][0] += 1.0;
+                        list[(size_t)sp - 1].ccc[(size_t)d.n_donor - 1][1] += 1.0;
+                    }
+                } else {
+                    std::vector<double> frac(list.size() * (size_t)ND, 0.0);
+                    std::vector<int> cnt(list.size() * (size_t)ND, 0);
+                    std::stable_sort(dvs.begin() + 1, dvs.begin() + 1 + logged, [](const SpecDvs &x, const SpecDvs &y) { return x.id < y.id; });
+                    int first = 1;
+                    auto chunk = [&](int f, int l) {
+                        for (int n = f; n <= l; ++n) {
+                            const size_t cell = (size_t)(dvs[(size_t)n].parent - 1) * ND + (size_t)(dvs[(size_t)n].n_donor - 1);
+                            frac[cell] += (double)(1.0f / (float)(l - f + 1));                // 1.0/FLOAT(last-first+1): REAL(4)
+                            cnt[cell] += 1;
+                        }
+                    };
+                    for (int m = 2; m <= logged; ++m)
+                        if (dvs[(size_t)m].id != dvs[(size_t)first].id) { chunk(first, m - 1); first = m; }
+                    chunk(first, logged);
+                    for (size_t s = 0; s < list.size(); ++s)
+                        for (int n = 0; n < ND; ++n)
+                            if (cnt[s * ND + n] != 0) { list[s].ccc[(size_t)n][0] += frac[s * ND + n]; list[s].ccc[(size_t)n][1] += (double)cnt[s * ND + n]; }
+                }
+            }
+        }
+    }
+    if (use_ccc)
+        for (auto &list : species) for (SpecSpecies &s : list) for (auto &c : s.ccc) c[0] = c[0] / c[1];          // (:1662-1672; 0/0 for absent donors)
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!r.dbg_conns)
+        printf("   ### B200 execution (speciation): %d steps, %lld distance tests, %lld connections, %.3f seconds\n", navg, tests_total, pairs_total, sec);
+    if (neighbour_atom_overflow > 0) r.error(160, "neighbour atom overflow (" + std::to_string(neighbour_atom_overflow) + "): increase N_neighbours");
+    {
+        long long so = 0;
+        for (long long v : species_overflow) so += v;
+        if (so > 0) r.error(161, "species overflow (" + std::to_string(so) + "): increase N_species");
+    }
+    // ---- print_acceptor_summary (:2082-2885) ---------------------------------------------------------------------
+    auto elem2 = [&](int type, int atom) {                       // CHARACTER(LEN=2) element symbol, untrimmed
+        std::string e = r.types[type - 1].elements[atom - 1];
+        e.resize(2, ' ');
+        return e;
+    };
+    auto elem = [&](int type, int atom) { return r.types[type - 1].elements[atom - 1]; };
+    auto formula = [&](int type) { return sum_formula(r.types[type - 1]); };
+    auto describe_groups = [&](FILE *f, const SpecSide &S, const char *who) {
+        for (int g = 1; g <= S.n_groups; ++g) {
+            bool firsttime = true;
+            for (size_t i = 0; i < S.atom.size(); ++i)
+                if (g == -S.group[i]) {
+                    if (firsttime) { firsttime = false; fprintf(f, "     Group #%d, atom indices %d(%s)", g, S.atom[i], elem(S.type, S.atom[i]).c_str()); }
+                    else fprintf(f, ", %d(%s)", S.atom[i], elem(S.type, S.atom[i]).c_str());
+                }
+            if (firsttime) fprintf(f, "     Group #%d was empty.\n", g); else fprintf(f, ".\n");
+        }
+        bool none_ungrouped = true, firsttime = true;
+        for (size_t i = 0; i < S.atom.size(); ++i)
+            if (S.group[i] > 0) {
+                none_ungrouped = false;
+                if (firsttime) { fprintf(f, "     Atoms not assigned to a group, treated as their own group:\n       Atom indices %d", S.atom[i]); firsttime = false; }
+                else fprintf(f, ", %d", S.atom[i]);
+            }
+        if (none_ungrouped) fprintf(f, "     All atoms of this %s were assigned to a group.\n", who); else fprintf(f, ".\n");
+    };
+    if (NA == 1) printf(" There was one acceptor: "); else printf(" There were %d acceptor molecules:\n", NA);
+    for (int n_acc = 1; n_acc <= NA; ++n_acc) {
+        const SpecSide &A = acc[n_acc - 1];
+        std::vector<SpecSpecies> &list = species[n_acc - 1];
+        if (NA > 1) printf("  Acceptor %d/%d was ", n_acc, NA);
+        const std::string fn = r.path_out + r.prefix + "acceptor" + std::to_string(n_acc) + "_speciation_statistics.dat";
+        FILE *f = fopen(fn.c_str(), "w");
+        if (!f) { r.error(26, "cannot open '" + fn + "'"); return 26; }
+        fprintf(f, " This file contains speciation statistics for acceptors coordinated by donors.\n");
+        if (A.atom.size() == 1) fprintf(f, " This acceptor was atom %d (%s) of molecule type %d (%s).\n", A.atom[0], elem2(A.type, A.atom[0]).c_str(), A.type, formula(A.type).c_str());
+        else if (atoms_grouped) {
+            fprintf(f, " Molecule type %d (%s) was the acceptor.\n", A.type, formula(A.type).c_str());
+            if (A.n_groups == 0) fprintf(f, "   This acceptor (#%d) has no custom groups defined.\n", n_acc);
+            else fprintf(f, "   Groups for this acceptor (#%d):\n", n_acc);
+            describe_groups(f, A, "acceptor");
+        } else {
+            fprintf(f, " Molecule type %d (%s) was the acceptor, with the following atom indices:\n", A.type, formula(A.type).c_str());
+            for (size_t i = 0; i < A.atom.size(); ++i) fprintf(f, "      Atom index %d (%s)\n", A.atom[i], elem(A.type, A.atom[i]).c_str());
+        }
+        fprintf(f, " The donor molecule types and atom types are given at the bottom.\n");
+        fprintf(f, " For this acceptor, %zu different species were observed,\n", list.size());
+        fprintf(f, " Which are now given in order of decreasing probability:\n");
+        printf("molecule type %d (%s).\n   For this acceptor, %zu different species were observed:\n", A.type, formula(A.type).c_str(), list.size());
+        std::vector<float> occ(list.size());
+        float total = 0.0f;
+        for (size_t s = 0; s < list.size(); ++s) { occ[s] = (float)list[s].occurrences; total = total + occ[s]; }
+        total = total + (float)species_overflow[n_acc - 1];
+        total = total + (float)none[n_acc - 1];
+        FILE *ft = nullptr;
+        std::vector<int> formal((size_t)ND, 0);
+        if (use_ccc) {
+            const std::string fnt = r.path_out + r.prefix + "acceptor" + std::to_string(n_acc) + "_speciation_statistics_table.dat";
+            ft = fopen(fnt.c_str(), "w");
+            if (!ft) { fclose(f); r.error(26, "cannot open '" + fnt + "'"); return 26; }
+            fprintf(ft, " This file contains the detailed communal cluster correction factors.\n");
+            fprintf(ft, "%15s%15s", "#species", "<h>");
+            for (int n = 0; n < ND; ++n) fprintf(ft, "%15s", formula(don[n].type).c_str());
+            fprintf(ft, " sum_formula(formally)\n");
+            if (none[n_acc - 1] > 0) {
+                fprintf(ft, "%15d%15.10f", 0, (double)(species_overflow[n_acc - 1] + none[n_acc - 1]) / (double)total);
+                for (int n = 0; n < ND; ++n) fprintf(ft, "%s", fortran_E(0.0, 15, 6).c_str());
+                fprintf(ft, " [%s]\n", formula(A.type).c_str());
+            }
+        }
+        int out_counter = 0;
+        for (;;) {
+            int best = -1; float best_value = 0.0f;
+            for (size_t s = 0; s < list.size(); ++s) if (occ[s] > best_value) { best_value = occ[s]; best = (int)s; }
+            if (best < 0) break;
+            ++out_counter;
+            occ[(size_t)best] = -1.0f;
+            SpecSpecies &S = list[(size_t)best];
+            const float share = (float)S.occurrences / total;
+            fprintf(f, "   -------\n");
+            if (share > 0.01f) fprintf(f, "   Species #(%d) in %.1f%% of the cases.\n", out_counter, (double)(100.0f * (float)S.occurrences / total));
+            else fprintf(f, "     Species #(%d) in %lld cases (less than 1%%).\n", out_counter, S.occurrences);
+            if (ft) { std::fill(formal.begin(), formal.end(), 0); fprintf(ft, "%15d%15.10f", out_counter, (double)share); }
+            if (out_counter < 6) {
+                if (share > 0.01f) printf("     Species #(%d) in %.1f%% of the cases.\n", out_counter, (double)(100.0f * (float)S.occurrences / total));
+                else printf("     Species #(%d) in %lld cases (less than 1%%).\n", out_counter, S.occurrences);
+            } else if (out_counter == 6) printf("     (Only the first 5 printed here)\n");
+            fprintf(f, "   This species has a total of %d connections,\n", S.nconn);
+            fprintf(f, "   with a total of %d neighbour atoms in %d neighbour molecules:\n", S.natoms, S.nmol);
+            int charge = r.types[A.type - 1].charge;
+            for (auto &m : S.mol) m.unmatched = true;
+            for (int sm = 0; sm < S.nmol && sm < (int)S.mol.size(); ++sm) {
+                const int first = S.mol[sm].first, extra = S.mol[sm].extra;
+                charge += r.types[don[S.conn[(size_t)first][0] - 1].type - 1].charge;
+                if (!S.mol[sm].unmatched) continue;
+                int doubles = 1;
+                for (int s2 = sm + 1; s2 < S.nmol && s2 < (int)S.mol.size(); ++s2) {
+                    if (S.mol[s2].extra != extra) continue;
+                    bool same = true;
+                    for (int k = 0; k <= extra; ++k) {
+                        const auto &x = S.conn[(size_t)(first + k)], &y = S.conn[(size_t)(S.mol[s2].first + k)];
+                        if (x[2] != y[2] || x[3] != y[3] || x[0] != y[0]) { same = false; break; }
+                    }
+                    if (!same) continue;
+                    ++doubles;
+                    S.mol[s2].unmatched = false;
+                }
+                if (doubles > 1) fprintf(f, "     %d Molecules of type ", doubles); else fprintf(f, "     One molecule of type ");
+                const int nd = S.conn[(size_t)first][0];
+                if (ft) formal[(size_t)nd - 1] += doubles;
+                fprintf(f, "%d(%s) with ", don[nd - 1].type, formula(don[nd - 1].type).c_str());
+                if (extra == 0) fprintf(f, "one connection"); else fprintf(f, "%d connections", extra + 1);
+                fprintf(f, doubles > 1 ? " each:\n" : ":\n");
+                for (int k = 0; k <= extra; ++k) {
+                    const int ag = S.conn[(size_t)(first + k)][3], dg = S.conn[(size_t)(first + k)][2];
+                    if (dg < 0) fprintf(f, "       atom group %d (donor) ", -dg); else fprintf(f, "       atom index %d (donor) ", dg);
+                    if (ag < 0) fprintf(f, "to atom group %d (acceptor)\n", -ag); else fprintf(f, "to atom index %d (acceptor)\n", ag);
+                }
+            }
+            fprintf(f, "   The total formal charge including the acceptor was %+d.\n", charge);
+            if (ft) {
+                fprintf(f, "   The correction factors for communal solvation were:\n");
+                for (int n = 0; n < ND; ++n) {
+                    int per_donor = 0;
+                    for (int k = 0; k < S.nconn; ++k) if (S.conn[(size_t)k][0] == n + 1) ++per_donor;
+                    if (formal[(size_t)n] == 0) S.ccc[(size_t)n][0] = 0.0;
+                    const double factor = S.ccc[(size_t)n][0], corr = factor * (double)(float)per_donor;
+                    fprintf(ft, "%s", fortran_E(corr, 15, 6).c_str());
+                    if (per_donor > 0) {
+                        char b1[32], b2[32];
+                        snprintf(b1, sizeof b1, "%4.2f", factor);
+                        if (corr < 1.0) snprintf(b2, sizeof b2, "%4.2f", corr); else snprintf(b2, sizeof b2, "%.2f", corr);
+                        fprintf(f, "     x%s for molecule type %d corresponding to %s %s\n", b1, n + 1, b2, formula(don[n].type).c_str());
+                    }
+                }
+                fprintf(ft, " [%s][", formula(A.type).c_str());
+                for (int n = 0; n < ND; ++n) fprintf(ft, "(%s)%d", formula(don[n].type).c_str(), formal[(size_t)n]);
+                fprintf(ft, "]\n");
+            }
+        }
+        if (species_overflow[n_acc - 1] > 0) {
+            const float so = (float)species_overflow[n_acc - 1] / total;
+            if (so > 0.01f) printf("     There was species overflow amounting to %.1f%%\n", (double)(100.0f * (float)species_overflow[n_acc - 1] / total));
+            else printf("     There was species overflow amounting to %s\n", fortran_e93((double)so).c_str());
+        }
+        if (none[n_acc - 1] > 0) {
+            if ((float)none[n_acc - 1] / total > 0.01f) printf("     There were %.1f%% acceptor molecules without any neighbouring donors.\n", (double)(100.0f * (float)none[n_acc - 1] / total));
+            else printf("     There were %lld acceptor molecules without neighbouring donors (less than 1%%).\n", none[n_acc - 1]);
+        } else printf("     There were no acceptor molecules without neighbouring donors.\n");
+        printf("   Detailed statistics written to '%sacceptor%d_speciation_statistics.dat'\n", r.prefix.c_str(), n_acc);
+        fprintf(f, "\n The donors of this analysis were:\n");
+        for (int n = 0; n < ND; ++n) {
+            const SpecSide &D = don[n];
+            if (D.atom.size() == 1) {
+                if (ND == 1) fprintf(f, " Atom %d (%s) of molecule type %d (%s) was the sole donor.\n", D.atom[0], elem2(D.type, D.atom[0]).c_str(), D.type, formula(D.type).c_str());
+                else fprintf(f, "   Donor #%d was atom %d (%s) of molecule type %d (%s).\n", n + 1, D.atom[0], elem2(D.type, D.atom[0]).c_str(), D.type, formula(D.type).c_str());
+            } else if (atoms_grouped) {
+                fprintf(f, "   Donor #%d was molecule type %d (%s), with the following atom groups:\n", n + 1, D.type, formula(D.type).c_str());
+                describe_groups(f, D, "donor");
+            } else {
+                fprintf(f, "   Donor #%d was molecule type %d (%s), with the following atom indices:\n", n + 1, D.type, formula(D.type).c_str());
+                for (size_t i = 0; i < D.atom.size(); ++i) fprintf(f, "     Atom index %d (%s)\n", D.atom[i], elem(D.type, D.atom[i]).c_str());
+            }
+        }
+        fclose(f);
+        if (ft) fclose(ft);
+    }
+    return 0;
+}
+
 void write_simple_sumrules(Run &r)                            // Distribution:43-67
 {
     const std::string path = r.path_in + "prealpha_simple.inp";
@@ -1796,7 +2367,27 @@ extern "C" float pa_debug_parse_coordinate(const char *s, int32_t *consumed)
     return f;
 }
 
+static int run_general_input_impl(const char *general_inp_path, const pa_exec *exec, const int32_t *dbg_conns, int64_t dbg_nconns);
+
 extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec *exec)
+{
+    return run_general_input_impl(general_inp_path, exec, nullptr, 0);
+}
+
+// Test seam for the host-side bookkeeping of the `speciation` keyword: the same front end, but the connections of every
+// (speciation keyword, step, acceptor type) come from the caller's table instead of pa_neighbour_pairs, so that the species
+// recognition and the writers can be checked against the reference binary's files on a machine without a GPU (the tests
+// fill the table from the oracle's neighbour loops).  Rows of 8 int32: ordinal of the speciation keyword in the input
+// (0-based), step, acceptor type (n_acceptor), acceptor molecule, donor type (n_donor), donor molecule, donor atom entry,
+// acceptor atom entry (all 1-based).  Nothing in the product calls this; every other keyword behaves as in
+// pa_run_general_input and still needs the GPU.
+extern "C" int pa_debug_run_general_input_with_connections(const char *general_inp_path, const pa_exec *exec, const int32_t *conns, int64_t nconns)
+{
+    if (!conns || nconns < 0) return PA_ERR_BAD_ARG;
+    return run_general_input_impl(general_inp_path, exec, conns, nconns);
+}
+
+static int run_general_input_impl(const char *general_inp_path, const pa_exec *exec, const int32_t *dbg_conns, int64_t dbg_nconns)
 {
     if (!general_inp_path) return PA_ERR_BAD_ARG;
     const auto t_start = std::chrono::steady_clock::now();
@@ -1808,6 +2399,7 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
     if (exec) r.exec = *exec;
     if (r.exec.shard_count < 1) r.exec.shard_count = 1;
     r.general_path = general_inp_path;
+    r.dbg_conns = dbg_conns; r.dbg_nconns = dbg_nconns;
     // CUDA context creation and the load of the kernel image take ~1 s in a fresh process: start them now, on a helper
     // thread, so that they overlap with reading the input files and the trajectory instead of delaying the first analysis
     // (every device the run may use, one helper thread each: contexts are created concurrently)
@@ -1867,7 +2459,7 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             if (t.empty()) continue;
             if (t[0] == "quit" || t[0] == "exit") break;
             if (t[0] == "distance" || t[0] == "distances" || t[0] == "distance_simple" || t[0] == "distances_simple" ||
-                t[0] == "contact_distance" || t[0] == "contact_distance_simple" || t[0] == "cluster") r.stream = false;
+                t[0] == "contact_distance" || t[0] == "contact_distance_simple" || t[0] == "cluster" || t[0] == "speciation") r.stream = false;
         }
         printf(r.stream ? " sequential_read T: the distribution analysis streams the trajectory from the file, batch by batch.\n"
                         : " sequential_read T: this input needs the whole trajectory in RAM; it is loaded once.\n");
@@ -1940,6 +2532,11 @@ extern "C" int pa_run_general_input(const char *general_inp_path, const pa_exec 
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             printf(" Cluster module invoked.\n");
             perform_cluster(r, t[1]);
+        } else if (k == "speciation") {                                       // Main: speciation keyword -> perform_speciation_analysis (Speciation:3230)
+            if (!r.box_given) { r.error(41, "box volume required for this analysis"); continue; }
+            if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
+            printf(" Speciation module invoked.\n");
+            perform_speciation(r, t[1]);
         } else if (k == "set_prefix") {
             if (t.size() < 2) { r.error(19, "cannot read general input line"); break; }
             r.prefix = t[1];

@@ -523,6 +523,14 @@ SPECIATION_INPUTS = {
     # every second step, radii on both sides (cutoff = acceptor + donor contribution), fluorine and carbon atoms as well
     "spec_mixed.inp": " 2 acceptors\n 3 1 1.0\n 1 1 2.0\n 4 donors\n 2 2 1.9\n 2 5 2.0\n 1 4 1.25\n 2 1 2.5\n"
                       " N_species 60\n N_neighbours 40\n nsteps 12\n tmax 11\n use_ccc T\n sampling_interval 2\n quit\n",
+    # limits: species overflow (error 161) and connection overflow (error 160), one grouped and one ungrouped acceptor
+    # atom in the same molecule, generous radii so that acceptor molecules share donors
+    "spec_limits.inp": " 3 acceptors\n 2 2 1.8\n 2 5 1.8\n 1 1 2.2\n 3 donors\n 3 1 1.7\n 1 2 1.2\n 1 3 1.2\n new_acceptor_group 2\n assign_to_acceptor_group 2\n"
+                       " new_donor_group 1\n assign_to_donor_group 2\n assign_to_donor_group 3\n"
+                       " N_species 7\n N_neighbours 3\n nsteps 11\n tmax 5\n use_ccc T\n sampling_interval 3\n quit\n",
+    # no communal cluster correction (no table file), no groups, several atoms per acceptor and donor
+    "spec_plain.inp": " 2 acceptors\n 2 2 1.5\n 2 5 1.5\n 3 donors\n 3 1 1.5\n 1 4 1.6\n 1 5 1.6\n"
+                      " N_species 30\n N_neighbours 12\n nsteps 8\n tmax 5\n sampling_interval 1\n quit\n",
 }
 
 
@@ -566,7 +574,8 @@ def case_re4_speciation():
         if fn.endswith("_speciation_statistics.dat"):
             names.append(fn)
             texts.append(open(os.path.join(wd, "output", fn)).read())
-            tables.append(open(os.path.join(wd, "output", fn[:-4] + "_table.dat")).read())
+            tp = os.path.join(wd, "output", fn[:-4] + "_table.dat")
+            tables.append(open(tp).read() if os.path.exists(tp) else "")
     keep = [ln for ln in out.splitlines() if "without neighbouring donors" in ln or "different species were observed" in ln or "For this acceptor" in ln
             or "There was one acceptor" in ln or "Acceptor " in ln or "overflow" in ln.lower()]
     np.savez_compressed(os.path.join(OUT, "re4_speciation.npz"),
