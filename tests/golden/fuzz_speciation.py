@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Differential check of the `speciation` replay against the reference binary on random inputs (development tool; needs
-oracle/_ref, i.e. /root/reference -- it is not part of the test suite).  For every random speciation input on the first
+"""Differential check of the `speciation` replay against the reference binary on random inputs (test infrastructure like
+make_golden.py: needs oracle/_ref, i.e. /root/reference, so it is run by hand and not collected by pytest).  For every random speciation input on the first
 12 frames of Research_Example_4 the binary writes its statistics / table files; the drop-in's bookkeeping runs on the
 oracle's neighbour pairs through the test seam, and the files are compared byte for byte.
-usage: python tools/fuzz_speciation.py [ncases] [seed]"""
+usage: python tests/golden/fuzz_speciation.py [ncases] [seed]"""
 import ctypes as C
 import os
 import shutil
@@ -12,7 +12,7 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import oracle_lib as orc  # noqa: E402
