@@ -1218,18 +1218,10 @@ std::string fortran_E(double v, int w, int d)
     return body;
 }
 
-std::string fortran_e93(double v)           // E9.3 = 0.dddE+ee
+std::string fortran_e93(double v)           // E9.3 = 0.dddE+ee; correctly rounded digits of the binary value, exact ties to even
 {
     if (std::isnan(v)) return "      NaN";
-    if (v == 0.0) return "0.000E+00";
-    int e = (int)std::floor(std::log10(std::fabs(v))) + 1;
-    double m = std::fabs(v) / std::pow(10.0, e);
-    long mi = std::lround(m * 1000.0);
-    if (mi >= 1000) { mi = 100; ++e; }
-    if (mi < 100) { mi *= 10; --e; }
-    char buf[32];
-    snprintf(buf, sizeof buf, "%s0.%03ldE%+03d", v < 0 ? "-" : "", mi, e);
-    return buf;
+    return fortran_E(v, 9, 3);
 }
 
 void formatted_distance_output(const std::string &what, double d)   // Distances:1145-1157

@@ -254,16 +254,11 @@ def make_dist_job(spec):
 
 
 def _e93(v):
-    import math
+    """E9.3: 0.dddE+ee with the correctly rounded digits of the binary value (exact ties go to the even digit)."""
     if v == 0.0:
         return "0.000E+00"
-    e = int(math.floor(math.log10(abs(v)))) + 1
-    mi = int(round(abs(v) / 10.0 ** e * 1000.0))
-    if mi >= 1000:
-        mi, e = 100, e + 1
-    if mi < 100:
-        mi, e = mi * 10, e - 1
-    return f"{'-' if v < 0 else ''}0.{mi:03d}E{e:+03d}"
+    mant, exp = ("%.2e" % abs(v)).split("e")
+    return f"{'-' if v < 0 else ''}0.{mant.replace('.', '')}E{int(exp) + 1:+03d}"
 
 
 def format_distance(d):
