@@ -84,6 +84,23 @@ for case in range(ncases):
     fx = FIX[fxname]
     text = random_input(fx)
     wrap = " wrap_trajectory T\n" if rng.random() < 0.3 else ""
+    # optional sections of molecular.inp: element masses / charges, masses / charges of single atoms (centres of mass, charge arms)
+    tail = ""
+    els = sorted(set(fx.elements))
+    if rng.random() < 0.4:
+        pick = [e for e in els if rng.random() < 0.5] or els[:1]
+        tail += f"masses {len(pick)}\n" + "".join(f" {e} {rng.uniform(1.0, 40.0):.3f}\n" for e in pick)
+    if rng.random() < 0.4:
+        rows = [(t + 1, int(rng.integers(1, fx.types[t][1] + 1))) for t in range(len(fx.types)) if rng.random() < 0.6]
+        if rows:
+            tail += f"atomic_masses {len(rows)}\n" + "".join(f" {t} {a} {rng.uniform(0.5, 50.0):.2f}\n" for t, a in rows)
+    if rng.random() < 0.4:
+        pick = [e for e in els if rng.random() < 0.5] or els[:1]
+        tail += f"charges {len(pick)}\n" + "".join(f" {e} {rng.uniform(-1.5, 1.5):.3f}\n" for e in pick)
+    if rng.random() < 0.5:
+        rows = [(t + 1, a) for t in range(len(fx.types)) for a in range(1, fx.types[t][1] + 1) if rng.random() < 0.5]
+        if rows:
+            tail += f"atomic_charges {len(rows)}\n" + "".join(f" {t} {a} {rng.uniform(-1.2, 1.2):.4f}\n" for t, a in rows)
     dirs = []
     for who in ("ref", "mine"):
         wd = tempfile.mkdtemp(prefix=f"fuzzd_{who}_")
@@ -94,7 +111,7 @@ for case in range(ncases):
         else:
             orc.write_lmp(os.path.join(wd, "traj.lmp"), fx.elements, fx.coords.astype(np.float64), fx.box_lo, fx.box_hi, fmt="%.9g")
             tname, box, ttype = "traj.lmp", "", "lmp"
-        open(os.path.join(wd, "molecular.inp"), "w").write(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + "quit\n")
+        open(os.path.join(wd, "molecular.inp"), "w").write(f" {fx.nsteps}\n {len(fx.types)}\n" + "".join(f" {c:+d} {a} {m}\n" for c, a, m in fx.types) + tail + "quit\n")
         open(os.path.join(wd, "dist.inp"), "w").write(text)
         open(os.path.join(wd, "general.inp"), "w").write(f' "{tname}"\n "molecular.inp"\n "./"\n "./"\n "./output/"\n set_threads 8\n{box} parallel_operation T\n'
                                                           f' sequential_read F\n{wrap} trajectory_type {ttype}\n set_prefix "f_"\n distribution dist.inp\n quit\n')
@@ -120,6 +137,7 @@ for case in range(ncases):
         shutil.copytree(dirs[0], keep + "/ref"); shutil.copytree(dirs[1], keep + "/mine")
         open(keep + "/ref_stdout.txt", "w").write(out); open(keep + "/my_stdout.txt", "w").write(p.stdout.decode() + p.stderr.decode())
         diff = [f for f in ref_files if f in my_files and open(os.path.join(dirs[0], "output", f), "rb").read() != open(os.path.join(dirs[1], "output", f), "rb").read()]
+        print(f"molecular.inp tail:\n{tail}")
         print(f"case {case}: MISMATCH [{fxname}{' wrap' if wrap else ''}] (kept in {keep}); only ref={sorted(set(ref_files) - set(my_files))} only mine={sorted(set(my_files) - set(ref_files))} differ={diff}\n{text}")
     else:
         errs = sorted({ln.strip()[:60] for ln in out.splitlines() if "ERROR" in ln})
