@@ -563,9 +563,9 @@ done:
 // ---------------------------------------------------------------------------
 // neighbour pairs: the REAL(4) test give_smallest_atom_distance_squared(...) < cutoff**2 of the
 // cluster / speciation analyses (Cluster:1094-1100, Speciation:1407-1431) for every pair of two atom lists.
-// Brute force like the reference (every a-instance against every b-instance, observed atoms staged as
-// (x-L, x, x+L) triples); qualifying pairs are appended with one atomic per warp and sorted on the host into
-// the order of the reference's nested loops.
+// Fast path: a cell list (further down).  Fallback for short lists and boxes of fewer than 3 x 3 x 3 cells: brute force
+// like the reference (every a-instance against every b-instance, observed atoms staged as (x-L, x, x+L) triples), hits
+// appended with one atomic per warp and sorted on the host into the order of the reference's nested loops.
 namespace {
 
 struct PnArgs {

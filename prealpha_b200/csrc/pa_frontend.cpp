@@ -940,9 +940,9 @@ void make_traj(Run &r, std::vector<pa_type> &types, pa_traj &t)
 // sequential_read T: the trajectory never sits in host memory as a whole.  Batches of frames are parsed from the file
 // (read_frames: text on all host threads, or pread from the binary cache) into a staging array, handed to a session
 // (pinned copy + cudaMemcpyAsync on its copy stream) and evaluated while the host already reads the next batch; the
-// sampled frames of a batch are picked by the stride of pa_session_upload.  With several devices (pa_exec.ndevices) the
-// batches are dealt round-robin to one session per GPU -- uploads and launches are asynchronous, so the one reading
-// thread keeps all of them busy as long as frames arrive fast enough -- and the int64 accumulators are combined on the
+// sampled frames of a batch are picked by the stride of pa_session_upload.  With several devices (pa_exec.ndevices) one
+// worker thread per GPU owns a session and takes the next batch the reading thread has queued as soon as it can, and the
+// int64 accumulators are combined on the
 // first device at the end (pa_sessions_reduce_to_first: peer copies or ncclReduce over NVLink, by size).  The kernel ladder of
 // pa_distribution_histogram_multi (cells -> brute force -> general kernel when a sticky device flag asks for it) is
 // repeated here by re-reading the file.

@@ -1004,7 +1004,8 @@ int pa_distribution_histogram_multi(const pa_traj *traj, const pa_job *jobs, int
 // ---------------------------------------------------------------------------
 // several devices inside one call (pa_exec.ndevices): the parallel region of iterate_timesteps_parallelised
 // (Distribution:704-753) with one host thread per GPU instead of one per core, and the CRITICAL-section merge of the
-// private histograms (Distribution:745-751) as ONE ncclReduce(sum) of the int64 accumulators over NVLink.
+// private histograms (Distribution:745-751) as ONE sum of the int64 accumulators on the first device over NVLink (peer
+// copies + an add kernel, or ncclReduce for large histograms: nccl_min_bytes).
 namespace {
 
 __global__ void pa_acc_add_kernel(unsigned long long *dst, const unsigned long long *src, size_t n)
