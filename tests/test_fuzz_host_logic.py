@@ -13,7 +13,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("script,ncases,seed", [("fuzz_distribution.py", 6, 101), ("fuzz_distance.py", 6, 102), ("fuzz_cluster.py", 6, 103),
+@pytest.mark.parametrize("script,ncases,seed", [("fuzz_distribution.py", 6, 101), ("fuzz_streaming.py", 5, 105), ("fuzz_distance.py", 6, 102), ("fuzz_cluster.py", 6, 103),
                                                 ("fuzz_speciation.py", 6, 104)])
 def test_host_logic_equals_the_reference_binary_on_random_inputs(script, ncases, seed, oracle):
     if not oracle.ref_available():
