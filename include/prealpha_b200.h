@@ -336,7 +336,8 @@ int pa_neighbour_pairs(const pa_traj *traj, const pa_neigh_request *req, const p
  * Runs a general.inp the way `./prealpha general.inp` does for the keywords
  * of this path (Main:103-357 header, Main:2882-3666 body; unknown keywords
  * are reported as error 20 and skipped, like the reference).  Returns the
- * number of errors/warnings encountered (the reference's final counter). */
+ * number of errors/warnings encountered (the reference's final counter), or
+ * PA_ERR_CUDA (< 0) when a GPU entry point failed along the way. */
 int pa_run_general_input(const char *general_inp_path, const pa_exec *exec);
 
 #ifdef __cplusplus

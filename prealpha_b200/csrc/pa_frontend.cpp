@@ -192,6 +192,7 @@ struct Run {
     std::vector<HostType> types;
     std::map<std::string, float> mass_override, charge_override;
     int errors = 0;
+    bool gpu_failed = false;      // a GPU entry point failed: pa_run_general_input then returns PA_ERR_CUDA instead of the warning count
     pa_exec exec{};
     // test seam of the speciation bookkeeping (pa_debug_run_general_input_with_connections): rows of 8 int32
     const int32_t *dbg_conns = nullptr; int64_t dbg_nconns = 0; int spec_calls = 0;
@@ -203,6 +204,9 @@ struct Run {
         ++errors;
         printf("  #  ERROR %d: %s\n", code, msg.c_str());
     }
+    // the reference's NOTICEs (40, 114, 133, 140, 145, 153, 161, 163, 165, 168) take their increment of the global counter
+    // back (`error_count=error_count-1`, SETTINGS:805,886,958 ...): reported, not counted
+    void notice(int code, const std::string &msg) { printf("  #  NOTICE %d: %s\n", code, msg.c_str()); }
 };
 
 void set_cubic_box(Run &r, float lower, float upper)         // Molecular:931-941
@@ -1156,7 +1160,7 @@ int perform_distribution(Run &r, const std::string &input_name)     // Distribut
     if (r.stream) rc = histogram_streaming(r, traj, jobs, hp, within, oob, &st, ex);
     else rc = pa_distribution_histogram_multi(&traj, jobs.data(), (int)jobs.size(), &ex, hp.data(), within.data(), oob.data(), &st);
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (rc) { r.error(rc, std::string("GPU histogram failed: ") + pa_last_error()); return rc; }
+    if (rc) { r.gpu_failed = true; r.error(rc, std::string("GPU histogram failed: ") + pa_last_error()); return rc; }
     traj.nsteps = r.nsteps;                                   // (a streamed file may have turned out shorter: error 84)
     printf("   ### B200 execution (distribution function): %lld frames, %lld pair evaluations, %lld kernel launches\n",
            (long long)st.frames_done, (long long)st.pairs_evaluated, (long long)st.kernel_launches);
@@ -1267,8 +1271,7 @@ int perform_distance(Run &r, const std::string &input_name)
                 e1 = tk[0].substr(0, 2);
                 if (c < 1 || c > natoms_of(b)) { r.error(natoms_of(b) ? 111 : 110, "invalid index - this line is ignored"); continue; }
                 if (atoms_of_element(r, e1, 0).empty()) { r.error(136, "no atoms of element '" + e1 + "'"); continue; }
-                printf("  #  NOTICE 140: Swapped reference and observed atoms (wildcard -> specific not allowed).\n");
-                ++r.errors;
+                r.notice(140, "Swapped reference and observed atoms (wildcard -> specific not allowed).");
                 wild = 1; t1 = b; a1 = c; e2 = e1;
             } else if (tk.size() >= 3 && parse_int(tk[0], a) && parse_int(tk[1], b)) {                 // type atom El
                 e2 = tk[2].substr(0, 2);
@@ -1289,8 +1292,7 @@ int perform_distance(Run &r, const std::string &input_name)
                 e1 = tk[1].substr(0, 2);
                 if (c < 1 || c > natoms_of(a)) { r.error(natoms_of(a) ? 111 : 110, "invalid index - this line is ignored"); continue; }
                 if (atoms_of_element(r, e1, a).empty()) { r.error(136, "no atoms of element '" + e1 + "' in that molecule"); continue; }
-                printf("  #  NOTICE 140: Swapped reference and observed atoms (wildcard -> specific not allowed).\n");
-                ++r.errors;
+                r.notice(140, "Swapped reference and observed atoms (wildcard -> specific not allowed).");
                 wild = 1; t1 = a; a1 = c; e2 = e1;
             } else if (tk.size() >= 3 && parse_int(tk[0], a) && parse_int(tk[1], b)) {                 // type atom El
                 e2 = tk[2].substr(0, 2);
@@ -1379,7 +1381,7 @@ int perform_distance(Run &r, const std::string &input_name)
     job.maxdist = maxdist; job.exponent = exponent;
     std::vector<pa_dist_result> res(csj.size());
     const int rc = pa_distance_subjobs(&traj, &job, &r.exec, res.data());
-    if (rc) { r.error(rc, std::string("GPU distance analysis failed: ") + pa_last_error()); return rc; }
+    if (rc) { r.gpu_failed = true; r.error(rc, std::string("GPU distance analysis failed: ") + pa_last_error()); return rc; }
     // report_distances, Distances:1093-1143
     printf(" Done with %smolecular distance calculation. Results:\n", mode.c_str());
     for (size_t i = 0; i < subs.size(); ++i) {
@@ -1431,7 +1433,7 @@ int perform_cluster(Run &r, const std::string &input_name)
     const int nt = (int)r.types.size();
     auto valid_type = [&](int t) { return t >= 1 && t <= nt; };
     auto valid_atom = [&](int t, int a) { return valid_type(t) && a >= 1 && a <= r.types[t - 1].natoms; };
-    int nsteps = 1, sampling = 1;
+    int nsteps = 1, sampling = 1, tmax = 10000;
     bool print_statistics = false;
     std::vector<ClusterAtom> atoms;
     std::vector<ClusterPair> pairs;
@@ -1451,6 +1453,7 @@ int perform_cluster(Run &r, const std::string &input_name)
         if (k == "quit") break;
         if (k == "nsteps") { if (t.size() > 1 && parse_int(t[1], i1)) nsteps = i1; else r.error(170, "cannot read 'nsteps' (cluster input)"); }
         else if (k == "sampling_interval") { if (t.size() > 1 && parse_int(t[1], i1)) sampling = i1; else r.error(170, "cannot read 'sampling_interval' (cluster input)"); }
+        else if (k == "tmax" || k == "t_max") { if (t.size() > 1 && parse_int(t[1], i1)) tmax = i1; else { r.error(24, "cannot read 'tmax'"); tmax = 10000; } }
         else if (k == "print_statistics" || k == "statistics") { if (t.size() > 1 && parse_logical(t[1], b1)) print_statistics = b1; else r.error(170, "cannot read 'print_statistics'"); }
         else if (k == "custom_weight" || k == "custom_weights" || k == "weight" || k == "weights" || k == "set_weight" || k == "set_weights") {
             if (t.size() > 1 && parse_real4(t[1], f1)) current_weight = f1; else r.error(170, "cannot read 'custom_weight'");
@@ -1504,6 +1507,8 @@ int perform_cluster(Run &r, const std::string &input_name)
     if (nsteps < 1) { r.error(57, "timestep out of range"); nsteps = 1; }
     else if (nsteps > r.nsteps) { r.error(57, "timestep out of range"); nsteps = r.nsteps; }
     if (sampling < 1) sampling = 1;
+    // the largest time shift of the (not built) autocorrelation function is checked whether or not it is computed (Cluster:887-890)
+    if (tmax > std::max((nsteps - 1 + sampling) / sampling, 0) - 1 || tmax < 1) r.error(28, "tmax is too large (or too small)");
     if (pairs_mode) printf("   Expecting %d pairs and %d atoms.\n", (int)pairs.size(), N_atoms);
     else printf("   Expecting %d atoms and %d cutoffs.\n", N_atoms, N_cutoffs);
     if (print_statistics) {
@@ -1611,7 +1616,7 @@ int perform_cluster(Run &r, const std::string &input_name)
                 if (rc == 0 && print_statistics) statistics(c);
             }
         }
-        if (rc) { r.error(rc, std::string("GPU neighbour search failed: ") + pa_last_error()); return rc; }
+        if (rc) { r.gpu_failed = true; r.error(rc, std::string("GPU neighbour search failed: ") + pa_last_error()); return rc; }
     }
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     printf("   ### B200 execution (cluster analysis): %d steps, %lld distance tests, %lld neighbour pairs, %.3f seconds\n", navg, tests_total, pairs_total, sec);
@@ -1756,7 +1761,7 @@ int perform_speciation(Run &r, const std::string &input_name)
     if (int rc = read_side(acc, "acceptor")) return rc;
     if (int rc = read_side(don, "donor")) return rc;
     // ---- read_body --------------------------------------------------------------------------------------
-    int nsteps = 100, sampling = 1, max_species = 11, max_conn = 10, group_type = 0;
+    int nsteps = 100, sampling = 1, max_species = 11, max_conn = 10, group_type = 0, tmax = 10000;
     bool atoms_grouped = false, use_ccc = false;
     for (; ln < toks.size(); ++ln) {
         const auto &t = toks[ln];
@@ -1771,6 +1776,8 @@ int perform_speciation(Run &r, const std::string &input_name)
             if (t.size() > 1 && parse_int(t[1], i1)) nsteps = i1; else r.error(158, "cannot read 'nsteps'");
         } else if (k == "sampling_interval") {
             if (t.size() > 1 && parse_int(t[1], i1)) sampling = i1; else r.error(158, "cannot read 'sampling_interval'");
+        } else if (k == "tmax") {
+            if (t.size() > 1 && parse_int(t[1], i1)) tmax = i1; else { r.error(24, "cannot read 'tmax'"); tmax = 10000; }
         } else if (k == "ccc" || k == "use_ccc" || k == "cluster_correction" || k == "use_cluster_correction" || k == "communal_solvation" ||
                    k == "use_communal_solvation" || k == "use_communal_cluster_correction" || k == "communal_cluster_correction") {
             if (t.size() > 1 && parse_logical(t[1], b1)) use_ccc = b1; else r.error(158, "cannot read 'communal_cluster_correction'");
@@ -1816,6 +1823,8 @@ int perform_speciation(Run &r, const std::string &input_name)
     if (nsteps < 1) { r.error(57, "timestep out of range"); nsteps = 1; }
     else if (nsteps > r.nsteps) { r.error(57, "timestep out of range"); nsteps = r.nsteps; }
     if (sampling < 1) sampling = 1;
+    // the largest time shift of the (not built) autocorrelation function is checked whether or not it is computed (:673-677)
+    if (tmax > std::max((nsteps - 1 + sampling) / sampling, 0) - 1 || tmax < 1) r.error(28, "tmax is too large (or too small)");
     if (max_conn < 1 || max_species < 1) { r.error(158, "N_species and N_neighbours must be positive"); return 158; }
     const int NA = (int)acc.size(), ND = (int)don.size();
     const int navg = std::max((nsteps - 1 + sampling) / sampling, 0);
@@ -1917,7 +1926,7 @@ int perform_speciation(Run &r, const std::string &input_name)
         for (int n_acc = 1; n_acc <= NA; ++n_acc) {
             const SpecSide &A = acc[n_acc - 1];
             std::vector<SpecSpecies> &list = species[n_acc - 1];
-            if (int rc = source(step, n_acc, per_mol)) { r.error(rc, std::string("GPU neighbour search failed: ") + pa_last_error()); return rc; }
+            if (int rc = source(step, n_acc, per_mol)) { r.gpu_failed = true; r.error(rc, std::string("GPU neighbour search failed: ") + pa_last_error()); return rc; }
             int logged = 0, new_conn = 0;
             for (size_t am = 0; am < per_mol.size(); ++am) {
                 // ---- clipboard of this acceptor molecule (:1383-1470) ----
@@ -2060,7 +2069,7 @@ int perform_speciation(Run &r, const std::string &input_name)
     {
         long long so = 0;
         for (long long v : species_overflow) so += v;
-        if (so > 0) r.error(161, "species overflow (" + std::to_string(so) + "): increase N_species");
+        if (so > 0) r.notice(161, "species overflow (" + std::to_string(so) + "): increase N_species");
     }
     // ---- print_acceptor_summary (:2082-2885) ---------------------------------------------------------------------
     auto elem2 = [&](int type, int atom) {                       // CHARACTER(LEN=2) element symbol, untrimmed
@@ -2236,6 +2245,7 @@ int perform_speciation(Run &r, const std::string &input_name)
 void write_simple_sumrules(Run &r)                            // Distribution:43-67
 {
     const std::string path = r.path_in + "prealpha_simple.inp";
+    if (access(path.c_str(), F_OK) == 0) r.notice(114, "overwriting existing 'prealpha_simple.inp'");      // NOTICE 114, e.g. Distribution:48-49
     FILE *f = fopen(path.c_str(), "w");
     if (!f) { r.error(46, "cannot write '" + path + "'"); return; }
     fprintf(f, "pdf %zu\n", r.types.size());
@@ -2250,6 +2260,7 @@ void write_simple_sumrules(Run &r)                            // Distribution:43
 bool write_simple_distances(Run &r, bool inter)
 {
     const std::string path = r.path_in + "prealpha_simple.inp";
+    if (access(path.c_str(), F_OK) == 0) r.notice(114, "overwriting existing 'prealpha_simple.inp'");      // NOTICE 114, e.g. Distribution:48-49
     FILE *f = fopen(path.c_str(), "w");
     if (!f) { r.error(46, "cannot write '" + path + "'"); return false; }
     bool h_av = false, f_av = false, both = false;
@@ -2297,7 +2308,7 @@ int perform_contact_distance(Run &r, int timestep, int type_in)       // Debug:5
     auto print_distances = [&](int type) -> int {
         pa_contact_result res{};
         const int rc = pa_contact_distance(&traj, timestep, type, &r.exec, &res);
-        if (rc) { r.error(rc, std::string("GPU contact distance failed: ") + pa_last_error()); return rc; }
+        if (rc) { r.gpu_failed = true; r.error(rc, std::string("GPU contact distance failed: ") + pa_last_error()); return rc; }
         const char *ind = type_in < 1 ? "  " : "";
         printf("%s   Largest intramolecular distance:  %s\n", ind, fortran_f0_3(res.largest_intramolecular).c_str());
         printf("%s   Smallest intramolecular distance: %s\n", ind, fortran_f0_3(res.smallest_intramolecular).c_str());
@@ -2320,6 +2331,7 @@ int perform_contact_distance(Run &r, int timestep, int type_in)       // Debug:5
 void write_simple_charge_arm(Run &r, bool normalise)          // Distribution:69-96
 {
     const std::string path = r.path_in + "prealpha_simple.inp";
+    if (access(path.c_str(), F_OK) == 0) r.notice(114, "overwriting existing 'prealpha_simple.inp'");      // NOTICE 114, e.g. Distribution:48-49
     FILE *f = fopen(path.c_str(), "w");
     if (!f) { r.error(46, "cannot write '" + path + "'"); return; }
     fprintf(f, "charge_arm %zu\n", r.types.size());
@@ -2473,6 +2485,8 @@ static int run_general_input_impl(const char *general_inp_path, const pa_exec *e
         unwrap_full(r);
     }
     // body, Main:2882-3666
+    // Main:2869: only the header of a lammps trajectory says whether it holds positions or velocities (Molecular:4861-4870)
+    if (r.traj_type == "xyz") r.error(55, "unknown trajectory format (velocities or Cartesian coordinates?) - please check results and input");
     int nline = 5;
     for (const auto &t : body) {
         ++nline;
@@ -2550,6 +2564,6 @@ static int run_general_input_impl(const char *general_inp_path, const pa_exec *e
     }
     printf("\n Encountered %d errors/warnings globally.\n", r.errors);
     mark("all keywords done");
-    return r.errors;
+    return r.gpu_failed ? PA_ERR_CUDA : r.errors;
 }
 

@@ -46,11 +46,13 @@ int main(int argc, char **argv)
         fprintf(stderr, "prealpha_b200: no usable B200 (sm_100) device; this program has no CPU fallback.\n");
         return 2;
     }
-    int errors = 0;
-    for (const std::string &g : inputs) errors += pa_run_general_input(g.c_str(), &ex);
+    // Exit status: 0 like the reference binary, whose warnings and errors only go to the report ("Encountered N
+    // errors/warnings globally"); 3 when a GPU entry point failed (pa_run_general_input < 0), 2 without a usable device.
+    int failures = 0;
+    for (const std::string &g : inputs) if (pa_run_general_input(g.c_str(), &ex) < 0) ++failures;
     fflush(stdout);
     if (dbg_t) fprintf(stderr, "[prealpha_b200] main: leaving %9.1f ms\n", since_main());
     // the results are on disk: skip the orderly teardown of CUDA contexts, memory pools and NCCL communicators, which
     // costs up to a second per device and frees nothing the operating system does not free anyway
-    _exit(errors ? 1 : 0);
+    _exit(failures ? 3 : 0);
 }

@@ -611,7 +611,7 @@ def test_cli_rejects_short_trajectories(oracle, tmp_path):
     cli = os.path.join(os.path.dirname(capi.LIB_PATH), "prealpha_b200_cli")
     p = subprocess.run([cli, "general.inp"], cwd=wd, capture_output=True, timeout=120)
     out = p.stdout.decode()
-    assert p.returncode == 1 and "ERROR 37" in out and "ERROR 20" in out
+    assert p.returncode == 0 and "ERROR 37" in out and "ERROR 20" in out          # exit status 0 like the binary's: errors go to the report
     assert not [f for f in os.listdir(wd) if f.startswith("reference_")]
 
 
