@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.parametrize("script,ncases,seed", [("fuzz_distribution.py", 6, 101), ("fuzz_streaming.py", 5, 105), ("fuzz_distance.py", 6, 102), ("fuzz_cluster.py", 6, 103),
-                                                ("fuzz_speciation.py", 6, 104)])
+                                                ("fuzz_speciation.py", 6, 104), ("fuzz_general.py", 6, 106)])
 def test_host_logic_equals_the_reference_binary_on_random_inputs(script, ncases, seed, oracle):
     if not oracle.ref_available():
         pytest.skip("reference binary not staged (oracle/_ref)")
