@@ -76,7 +76,7 @@ def dist_input():
     n = int(rng.integers(1, 3))
     text = f"{mode} {n}\n"
     for _ in range(n):
-        ref = int(rng.integers(1, 4))
+        ref = int(rng.integers(1, 4)) if rng.random() < 0.93 else int(rng.choice([0, 4, 9]))      # (now and then an invalid molecule type)
         text += f"{rng.choice(VECS)} {ref}\n" if mode == "charge_arm" else f"{rng.choice(VECS)} {ref} {int(rng.choice([-1, 1, 2, 3]))}\n"
     text += "maxdist_optimize\n" if rng.random() < 0.5 else f"maxdist {rng.uniform(2.0, 20.0):.2f}\n"
     if rng.random() < 0.5:
@@ -89,7 +89,9 @@ def distance_input():
     text = f"{'intermolecular' if inter else 'intramolecular'} 2\n"
     for _ in range(2):
         t1, t2 = int(rng.choice([1, 2])), int(rng.choice([1, 2, 3]))
-        if rng.random() < 0.5:
+        if rng.random() < 0.08:
+            text += f"{t1} {int(rng.choice([0, 9]))} {t2} 1\n" if inter else f"{t1} 9 1\n"          # invalid atom index
+        elif rng.random() < 0.5:
             text += (f"{t1} {int(rng.integers(1, natoms[t1] + 1))} {t2} {int(rng.integers(1, natoms[t2] + 1))}\n" if inter
                      else f"{t1} {int(rng.integers(1, natoms[t1] + 1))} {int(rng.integers(1, natoms[t1] + 1))}\n")
         else:
@@ -108,7 +110,7 @@ def cluster_input():
     else:
         text = "PAIRS\n" + "".join(f"pair {a} {int(rng.integers(1, natoms[a] + 1))} {b} {int(rng.integers(1, natoms[b] + 1))} {rng.uniform(2.0, 4.5):.2f}\n"
                                    for a, b in rng.choice([1, 2, 3], size=(2, 2)))
-    return text + f"nsteps {int(rng.integers(2, 13))}\nsampling_interval {int(rng.integers(1, 3))}\nprint_statistics T\nautocorrelation F\nquit\n"
+    return text + f"nsteps {int(rng.choice([int(rng.integers(2, 13)), 40]))}\nsampling_interval {int(rng.integers(1, 3))}\nprint_statistics T\nautocorrelation F\nquit\n"
 
 
 def speciation_input():
@@ -165,9 +167,11 @@ for case in range(ncases):
         for d in dirs:
             shutil.rmtree(d)
         continue
-    if "ERROR 0." in out:
+    if "ERROR 0." in out or "Encountered" not in out:
+        # its own internal error, or a severe error ended the binary early (e.g. error 22 "couldn't allocate memory" in the
+        # distribution analysis that follows one rejected with error 33: the arrays of the rejected one are still allocated)
         skipped += 1
-        print(f"case {case}: the reference reports its internal error 0, skipped")
+        print(f"case {case}: the reference reports its internal error 0 or stopped early, skipped")
         for d in dirs:
             shutil.rmtree(d)
         continue
